@@ -1,0 +1,299 @@
+"""Per-primitive sample / logpdf restatement (oracle; test infrastructure only).
+
+Reference call sites: ``ExactDensity.random_weighted / estimate_logpdf``
+(src/genjax/_src/generative_functions/distributions/distribution.py:371-396,
+non-scalar logpdf is sum-reduced at :393-394) which call
+``tfd.<Dist>(*args).sample(seed=key)`` / ``.log_prob(v)``
+(distributions/tensorflow_probability/__init__.py:52-62).
+
+tensorflow-probability 0.23.0 (poetry.lock:5015-5016) is NOT vendored and not
+installable here; the log_prob formulas below restate its published source in
+TFP's float32 operation order.  PINNED: Normal (reference KAT
+tests/generative_functions/test_static_gen_fn.py:317-318).  UNPINNED: every
+other logpdf and every sampler ("parity unpinned").  Samplers are this build's
+own bits->variate maps (see oracle/rng.py) -- same distributions as TFP's,
+different streams.
+
+Every function is vectorised over a leading particle axis and computes in
+float32 with float64 only inside transcendental calls (rounded once).
+"""
+
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import rng
+
+F32 = np.float32
+_HALF_LOG_2PI = F32(0.5 * math.log(2.0 * math.pi))
+
+
+def _f(x):
+    return np.asarray(x, dtype=F32)
+
+
+def _log(x):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.log(_f(x).astype(np.float64)).astype(F32)
+
+
+def _exp(x):
+    with np.errstate(over="ignore"):
+        return np.exp(_f(x).astype(np.float64)).astype(F32)
+
+
+def _log1p(x):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.log1p(_f(x).astype(np.float64)).astype(F32)
+
+
+def _softplus(x):
+    x = _f(x).astype(np.float64)
+    return (np.maximum(x, 0.0) + np.log1p(np.exp(-np.abs(x)))).astype(F32)
+
+
+def _lgamma(x):
+    from scipy.special import gammaln
+
+    return gammaln(_f(x).astype(np.float64)).astype(F32)
+
+
+# ----------------------------------------------------------------- logpdfs
+
+
+def normal_logpdf(v, loc, scale):
+    """tfd.Normal._log_prob: -0.5*squared_difference(x/s, m/s) - (0.5 log 2pi + log s)."""
+    v, loc, scale = _f(v), _f(loc), _f(scale)
+    z = (v / scale - loc / scale).astype(F32)
+    return (F32(-0.5) * (z * z) - (_HALF_LOG_2PI + _log(scale))).astype(F32)
+
+
+def uniform_logpdf(v, low, high):
+    """tfd.Uniform._log_prob: -log(high-low) inside [low, high], -inf outside."""
+    v, low, high = _f(v), _f(low), _f(high)
+    inside = (v >= low) & (v <= high)
+    return np.where(inside, -_log(high - low), F32(-np.inf)).astype(F32)
+
+
+def flip_logpdf(v, p):
+    """tfd.Bernoulli(probs=p)._log_prob: xlogy(x, p) + xlog1py(1-x, -p)."""
+    x = _f(np.asarray(v).astype(F32))
+    p = _f(p)
+    a = np.where(x == 0, F32(0), x * _log(p))
+    b = np.where((F32(1) - x) == 0, F32(0), (F32(1) - x) * _log1p(-p))
+    return (a + b).astype(F32)
+
+
+def bernoulli_logpdf(v, logits):
+    """tfd.Bernoulli(logits=l)._log_prob: -softplus(-l)*x - softplus(l)*(1-x)."""
+    x = _f(np.asarray(v).astype(F32))
+    l = _f(logits)
+    return (-_softplus(-l) * x - _softplus(l) * (F32(1) - x)).astype(F32)
+
+
+def log_softmax(logits):
+    l = _f(logits)
+    m = np.max(l, axis=-1, keepdims=True)
+    sh = (l - m).astype(F32)
+    # sequential left-to-right float32 sum, the order the device loop uses
+    e = _exp(sh)
+    s = np.zeros(e.shape[:-1], dtype=F32)
+    for j in range(e.shape[-1]):
+        s = (s + e[..., j]).astype(F32)
+    return (sh - _log(s)[..., None]).astype(F32)
+
+
+def categorical_logpdf(v, logits):
+    """tfd.Categorical(logits)._log_prob: log_softmax(logits)[k]."""
+    ls = log_softmax(logits)
+    k = np.asarray(v).astype(np.int64)
+    if ls.ndim == 1:
+        return ls[k].astype(F32)
+    return np.take_along_axis(ls, k[..., None], axis=-1)[..., 0].astype(F32)
+
+
+def exponential_logpdf(v, rate):
+    """tfd.Exponential._log_prob: log(rate) - rate*x (x >= 0)."""
+    v, rate = _f(v), _f(rate)
+    lp = (_log(rate) - rate * v).astype(F32)
+    return np.where(v < 0, F32(-np.inf), lp).astype(F32)
+
+
+def mv_normal_diag_logpdf(v, loc, scale_diag):
+    """tfd.MultivariateNormalDiag: sum of independent Normal log_probs
+    (left-to-right over the event axis in float32)."""
+    lp = normal_logpdf(v, loc, scale_diag)
+    out = np.zeros(lp.shape[:-1], dtype=F32)
+    for j in range(lp.shape[-1]):
+        out = (out + lp[..., j]).astype(F32)
+    return out
+
+
+def gamma_logpdf(v, concentration, rate):
+    """tfd.Gamma._log_prob: xlogy(a-1, x) - rate*x - (lgamma(a) - a*log(rate))."""
+    v, a, b = _f(v), _f(concentration), _f(rate)
+    t = np.where((a - F32(1)) == 0, F32(0), (a - F32(1)) * _log(v))
+    return (t - b * v - (_lgamma(a) - a * _log(b))).astype(F32)
+
+
+def beta_logpdf(v, a, b):
+    """tfd.Beta._log_prob: xlogy(a-1,x) + xlog1py(b-1,-x) - lbeta(a,b)."""
+    v, a, b = _f(v), _f(a), _f(b)
+    t1 = np.where((a - F32(1)) == 0, F32(0), (a - F32(1)) * _log(v))
+    t2 = np.where((b - F32(1)) == 0, F32(0), (b - F32(1)) * _log1p(-v))
+    lbeta = (_lgamma(a) + _lgamma(b) - _lgamma(a + b)).astype(F32)
+    return (t1 + t2 - lbeta).astype(F32)
+
+
+def half_normal_logpdf(v, scale):
+    """tfd.HalfNormal._log_prob: 0.5 log(2/pi) - log s - 0.5 (x/s)^2, x >= 0."""
+    v, s = _f(v), _f(scale)
+    z = (v / s).astype(F32)
+    lp = (F32(0.5 * math.log(2.0 / math.pi)) - _log(s) - F32(0.5) * z * z).astype(F32)
+    return np.where(v < 0, F32(-np.inf), lp).astype(F32)
+
+
+# ---------------------------------------------------------------- samplers
+# sampler(words, idx, site, *args) -> values for the lanes in idx
+
+
+def _bc(a, n):
+    a = _f(a)
+    return np.broadcast_to(a, (n,) + a.shape[1:]) if a.ndim >= 1 and a.shape[0] == n else np.broadcast_to(a, (n,) + a.shape)
+
+
+def normal_sample(words, idx, site, loc, scale):
+    w0, w1, _, _ = rng.site_words(words, idx, site, 0)
+    z, _ = rng.box_muller(w0, w1)
+    return (_f(loc) + _f(scale) * z).astype(F32)
+
+
+def uniform_sample(words, idx, site, low, high):
+    w0, _, _, _ = rng.site_words(words, idx, site, 0)
+    u = rng.u01(w0)
+    return (_f(low) + (_f(high) - _f(low)) * u).astype(F32)
+
+
+def flip_sample(words, idx, site, p):
+    w0, _, _, _ = rng.site_words(words, idx, site, 0)
+    return rng.u01(w0) < _f(p)
+
+
+def bernoulli_sample(words, idx, site, logits):
+    w0, _, _, _ = rng.site_words(words, idx, site, 0)
+    l = _f(logits).astype(np.float64)
+    p = (1.0 / (1.0 + np.exp(-l))).astype(F32)
+    return rng.u01(w0) < p
+
+
+def categorical_sample(words, idx, site, logits):
+    """Inverse-CDF over exp(l - max l): first k with cumsum_k > u * total.
+    (TFP draws argmax(logits + Gumbel); same distribution, different stream.)"""
+    w0, _, _, _ = rng.site_words(words, idx, site, 0)
+    u = rng.u01(w0)
+    l = _f(logits)
+    if l.ndim == 1:
+        l = np.broadcast_to(l, (u.shape[0], l.shape[0]))
+    m = np.max(l, axis=-1, keepdims=True)
+    e = _exp((l - m).astype(F32))
+    K = e.shape[-1]
+    tot = np.zeros(u.shape, dtype=F32)
+    for j in range(K):
+        tot = (tot + e[:, j]).astype(F32)
+    t = (u * tot).astype(F32)
+    acc = np.zeros(u.shape, dtype=F32)
+    k = np.full(u.shape, K - 1, dtype=np.int32)
+    done = np.zeros(u.shape, dtype=bool)
+    for j in range(K):
+        acc = (acc + e[:, j]).astype(F32)
+        hit = (~done) & (acc > t)
+        k[hit] = j
+        done |= hit
+    return k
+
+
+def exponential_sample(words, idx, site, rate):
+    w0, _, _, _ = rng.site_words(words, idx, site, 0)
+    return (-_log(rng.u01(w0)) / _f(rate)).astype(F32)
+
+
+def mv_normal_diag_sample(words, idx, site, loc, scale_diag):
+    loc = _f(loc)
+    scale_diag = _f(scale_diag)
+    d = max(loc.shape[-1] if loc.ndim else 1, scale_diag.shape[-1] if scale_diag.ndim else 1)
+    z = rng.normal_vec(words, idx, site, d)
+    return (loc + scale_diag * z).astype(F32)
+
+
+def half_normal_sample(words, idx, site, scale):
+    w0, w1, _, _ = rng.site_words(words, idx, site, 0)
+    z, _ = rng.box_muller(w0, w1)
+    return (np.abs(z) * _f(scale)).astype(F32)
+
+
+def _gamma_mt(words, idx, site, a, chunk0=0, max_iter=64):
+    """Marsaglia-Tsang (2000) Gamma(a,1) for a >= 1; a < 1 boosted by u^(1/a).
+
+    Attempt t uses Philox chunk ``chunk0 + t``: words (0,1) -> normal x,
+    word 2 -> acceptance uniform, word 3 (attempt 0 only) -> boost uniform.
+    """
+    idx = np.asarray(idx, dtype=np.uint64)
+    n = idx.shape[0]
+    a = np.broadcast_to(_f(a), (n,)).astype(F32)
+    boost = a < F32(1)
+    a_eff = np.where(boost, a + F32(1), a).astype(F32)
+    d = (a_eff - F32(1.0 / 3.0)).astype(F32)
+    c = (F32(1) / np.sqrt(F32(9) * d)).astype(F32)
+    out = np.zeros(n, dtype=F32)
+    done = np.zeros(n, dtype=bool)
+    ub = None
+    for t in range(max_iter):
+        w0, w1, w2, w3 = rng.site_words(words, idx, site, chunk0 + t)
+        if t == 0:
+            ub = rng.u01(w3)
+        x, _ = rng.box_muller(w0, w1)
+        u = rng.u01(w2)
+        v = (F32(1) + c * x).astype(F32)
+        v3 = (v * v * v).astype(F32)
+        ok = v > 0
+        with np.errstate(invalid="ignore", divide="ignore"):
+            lhs = _log(u)
+            rhs = (F32(0.5) * x * x + d - d * v3 + d * _log(v3)).astype(F32)
+        acc = ok & (lhs < rhs) & (~done)
+        out[acc] = (d * v3)[acc]
+        done |= acc
+        if done.all():
+            break
+    g = out
+    with np.errstate(divide="ignore"):
+        bf = _exp(_log(ub) / a)
+    return np.where(boost, g * bf, g).astype(F32)
+
+
+def gamma_sample(words, idx, site, concentration, rate):
+    g = _gamma_mt(words, idx, site, concentration, 0)
+    return (g / _f(rate)).astype(F32)
+
+
+def beta_sample(words, idx, site, a, b):
+    """X = Ga / (Ga + Gb) with Ga ~ Gamma(a,1) on chunks [0,64), Gb on [64,128)."""
+    ga = _gamma_mt(words, idx, site, a, 0)
+    gb = _gamma_mt(words, idx, site, b, 64)
+    return (ga / (ga + gb)).astype(F32)
+
+
+# registry: name -> (sampler, logpdf, n_args, value kind)
+DISTS = {
+    "normal": (normal_sample, normal_logpdf),
+    "uniform": (uniform_sample, uniform_logpdf),
+    "flip": (flip_sample, flip_logpdf),
+    "bernoulli": (bernoulli_sample, bernoulli_logpdf),
+    "categorical": (categorical_sample, categorical_logpdf),
+    "exponential": (exponential_sample, exponential_logpdf),
+    "mv_normal_diag": (mv_normal_diag_sample, mv_normal_diag_logpdf),
+    "half_normal": (half_normal_sample, half_normal_logpdf),
+    "gamma": (gamma_sample, gamma_logpdf),
+    "beta": (beta_sample, beta_logpdf),
+}

@@ -1,0 +1,246 @@
+"""Counter-based RNG restatement (oracle; test infrastructure only).
+
+What the reference does: every random choice draws from JAX's threefry2x32
+PRNG -- ``jax.random.key/split/fold_in`` at static.py:260-263 (per-site key
+``fold_in(key, counter)``, counter from 1), smc.py:154,171,299-300,386,
+vmap.py:186,201, hmc.py:125,167,180 -- and TFP samplers turn the bits into
+variates (tensorflow_probability/__init__.py:52-62).  jax and tfp are not
+vendored under /root/reference and are not installable here, so:
+
+  * threefry2x32 and Philox4x32-10 are restated from the published algorithms
+    (Salmon et al., SC'11, "Parallel random numbers: as easy as 1, 2, 3") and
+    PINNED against the Random123 known-answer vectors (tests/test_oracle_rng.py);
+  * the key tree (split / fold_in layout) and the bits->variate maps are this
+    build's own, fully specified below; sampled VALUES are "parity unpinned"
+    against the reference (nothing in its tests pins one), and bit-level parity
+    is defined between this oracle and the CUDA kernels.
+
+Stream layout shared with genjax_b200/csrc/gjb_rng.cuh:
+
+    words = philox4x32_10(ctr=(idx_lo, idx_hi, chunk, site), key=(k0, k1))
+
+``(k0, k1)`` is the batch key, ``idx`` the GLOBAL particle/chain index (so a
+result does not depend on how particles are sharded over GPUs), ``site`` the
+1-based visit counter of the random choice inside the model (static.py:260-263
+starts its counter at 1 too) and ``chunk`` numbers successive 4-word blocks a
+site consumes (vector sites: chunk = dim // 4; rejection samplers: attempt).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+U32 = np.uint32
+U64 = np.uint64
+_M32 = 0xFFFFFFFF
+
+# --------------------------------------------------------------------------
+# threefry2x32 (20 rounds) -- used host-side for the key tree
+# --------------------------------------------------------------------------
+
+_ROT = ((13, 15, 26, 6), (17, 29, 16, 24))
+
+
+def _rotl32(x, r):
+    x = x.astype(U32)
+    return ((x << U32(r)) | (x >> U32(32 - r))).astype(U32)
+
+
+def threefry2x32(key, ctr):
+    """threefry2x32-20.  key: (2,) uint32; ctr: (..., 2) uint32 -> (..., 2)."""
+    key = np.asarray(key, dtype=U32)
+    ctr = np.asarray(ctr, dtype=U32)
+    ks0, ks1 = key[0], key[1]
+    ks2 = U32(0x1BD11BDA) ^ ks0 ^ ks1
+    ks = (ks0, ks1, ks2)
+    with np.errstate(over="ignore"):
+        x0 = (ctr[..., 0] + ks0).astype(U32)
+        x1 = (ctr[..., 1] + ks1).astype(U32)
+        for g in range(5):
+            rots = _ROT[g % 2]
+            for r in rots:
+                x0 = (x0 + x1).astype(U32)
+                x1 = _rotl32(x1, r)
+                x1 = x1 ^ x0
+            x0 = (x0 + ks[(g + 1) % 3]).astype(U32)
+            x1 = (x1 + ks[(g + 2) % 3] + U32(g + 1)).astype(U32)
+    return np.stack([x0, x1], axis=-1)
+
+
+# --------------------------------------------------------------------------
+# Philox4x32-10 -- the per-particle device stream
+# --------------------------------------------------------------------------
+
+_PH_M0 = U64(0xD2511F53)
+_PH_M1 = U64(0xCD9E8D57)
+_PH_W0 = 0x9E3779B9
+_PH_W1 = 0xBB67AE85
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10.  All inputs broadcastable uint32 arrays -> 4 uint32 arrays."""
+    c0, c1, c2, c3 = np.broadcast_arrays(
+        *(np.asarray(c, dtype=U32) for c in (c0, c1, c2, c3))
+    )
+    k0 = int(k0) & _M32
+    k1 = int(k1) & _M32
+    for _ in range(10):
+        p0 = c0.astype(U64) * _PH_M0
+        p1 = c2.astype(U64) * _PH_M1
+        hi0 = (p0 >> U64(32)).astype(U32)
+        lo0 = (p0 & U64(_M32)).astype(U32)
+        hi1 = (p1 >> U64(32)).astype(U32)
+        lo1 = (p1 & U64(_M32)).astype(U32)
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ U32(k0), lo1, hi0 ^ c3 ^ U32(k1), lo0)
+        k0 = (k0 + _PH_W0) & _M32
+        k1 = (k1 + _PH_W1) & _M32
+    return c0, c1, c2, c3
+
+
+# --------------------------------------------------------------------------
+# key tree (host side; mirrors genjax_b200/core/key.py)
+# --------------------------------------------------------------------------
+
+
+class Key:
+    """A PRNG key = 2 threefry words + a 64-bit lane index.
+
+    ``split(key, n)[i]`` is ``Key(child_words, index=i)``: the batch shares one
+    pair of words and lane ``i`` is addressed through the Philox counter, so a
+    batched GFI call over ``split(key, n)`` and a scalar call with
+    ``split(key, n)[i]`` produce the same numbers for lane ``i`` (what
+    ``jax.vmap`` over ``jax.random.split`` guarantees in the reference).
+    """
+
+    __slots__ = ("words", "index")
+
+    def __init__(self, words, index=0):
+        self.words = (int(words[0]) & _M32, int(words[1]) & _M32)
+        self.index = int(index)
+
+    def __repr__(self):
+        return f"Key({self.words[0]:#010x},{self.words[1]:#010x};{self.index})"
+
+
+def key(seed: int) -> Key:
+    """``jax.random.key(seed)``: key data = [seed >> 32, seed & 0xffffffff]."""
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    return Key((seed >> 32, seed & _M32), 0)
+
+
+def _collapse(k: Key):
+    """Fold the lane index into the words (identity for index 0)."""
+    if k.index == 0:
+        return k.words
+    out = threefry2x32(
+        np.array(k.words, dtype=U32),
+        np.array([(k.index >> 32) & _M32 ^ 0x5851F42D, k.index & _M32], dtype=U32),
+    )
+    return (int(out[0]), int(out[1]))
+
+
+def fold_in(k: Key, data: int) -> Key:
+    """``jax.random.fold_in``: hash the key with one 32-bit datum."""
+    w = _collapse(k)
+    out = threefry2x32(np.array(w, dtype=U32), np.array([0, int(data) & _M32], dtype=U32))
+    return Key((int(out[0]), int(out[1])), 0)
+
+
+class KeyBatch:
+    """Lazy result of ``split(key, n)``: n lanes over one pair of words."""
+
+    def __init__(self, words, n, offset=0):
+        self.words = (int(words[0]) & _M32, int(words[1]) & _M32)
+        self.n = int(n)
+        self.offset = int(offset)
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            start, stop, step = i.indices(self.n)
+            assert step == 1
+            return KeyBatch(self.words, max(0, stop - start), self.offset + start)
+        if i < 0:
+            i += self.n
+        if not 0 <= i < self.n:
+            raise IndexError(i)
+        return Key(self.words, self.offset + i)
+
+    def __iter__(self):
+        return (self[i] for i in range(self.n))
+
+
+def split(k: Key, n: int = 2) -> KeyBatch:
+    """``jax.random.split``: child words = threefry(key, [0x73706c74, 0])."""
+    w = _collapse(k)
+    out = threefry2x32(np.array(w, dtype=U32), np.array([0x73706C74, 0], dtype=U32))
+    return KeyBatch((int(out[0]), int(out[1])), n, 0)
+
+
+def lanes(k) -> tuple[tuple[int, int], np.ndarray]:
+    """(words, uint64 lane indices) for a Key (1 lane) or KeyBatch (n lanes)."""
+    if isinstance(k, KeyBatch):
+        return k.words, (np.arange(k.n, dtype=np.uint64) + np.uint64(k.offset))
+    return k.words, np.array([k.index], dtype=np.uint64)
+
+
+# --------------------------------------------------------------------------
+# bits -> variates (float32, operation order shared with gjb_rng.cuh)
+# --------------------------------------------------------------------------
+
+F32 = np.float32
+_TWO_NEG23 = F32(2.0**-23)
+
+
+def site_words(words, idx, site, chunk=0):
+    """The 4 Philox words of (lane idx, site, chunk)."""
+    idx = np.asarray(idx, dtype=np.uint64)
+    lo = (idx & np.uint64(_M32)).astype(U32)
+    hi = (idx >> np.uint64(32)).astype(U32)
+    chunk = np.broadcast_to(np.asarray(chunk, dtype=U32), lo.shape) if np.ndim(chunk) == 0 else np.asarray(chunk, dtype=U32)
+    return philox4x32_10(lo, hi, chunk, U32(site), words[0], words[1])
+
+
+def u01(bits):
+    """uint32 -> float32 in (0,1): ((bits >> 9) + 0.5) * 2^-23 (exact in fp32)."""
+    return ((bits >> U32(9)).astype(F32) + F32(0.5)) * _TWO_NEG23
+
+
+def box_muller(b0, b1):
+    """Two N(0,1) float32 from two uint32 words.
+
+    r = sqrtf(-2 logf(u1)); (s, c) = sincospif(2 u2); z0 = r c; z1 = r s.
+    log / sin / cos are evaluated in float64 and rounded once (the CUDA
+    library functions are within 1-2 ulp of that).
+    """
+    u1 = u01(b0)
+    u2 = u01(b1)
+    lg = np.log(u1.astype(np.float64)).astype(F32)
+    r = np.sqrt(F32(-2.0) * lg).astype(F32)
+    ang = np.float64(2.0) * u2.astype(np.float64) * np.pi
+    c = np.cos(ang).astype(F32)
+    s = np.sin(ang).astype(F32)
+    return (r * c).astype(F32), (r * s).astype(F32)
+
+
+def normal4(words, idx, site, chunk=0):
+    """Four N(0,1) variates of one Philox block: (z0,z1)=BM(w0,w1), (z2,z3)=BM(w2,w3)."""
+    w0, w1, w2, w3 = site_words(words, idx, site, chunk)
+    z0, z1 = box_muller(w0, w1)
+    z2, z3 = box_muller(w2, w3)
+    return z0, z1, z2, z3
+
+
+def normal_vec(words, idx, site, d):
+    """[n, d] standard normals: dim j comes from chunk j // 4, slot j % 4."""
+    idx = np.asarray(idx, dtype=np.uint64)
+    out = np.empty((idx.shape[0], d), dtype=F32)
+    for c in range((d + 3) // 4):
+        z = normal4(words, idx, site, c)
+        for s in range(4):
+            j = 4 * c + s
+            if j < d:
+                out[:, j] = z[s]
+    return out
