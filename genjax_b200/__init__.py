@@ -1,0 +1,59 @@
+"""genjax_b200 -- a B200-native particle-parallel inference engine behind the
+GenJAX API surface (``@gen`` / ``Target`` / ``ChoiceMap`` / GFI).
+
+Only the hot path of genjax-community/genjax is rebuilt here (SURVEY.md
+section 8): batched simulate / assess / importance / update over static
+``@gen`` models, the SMC propose-weight-resample step, and batched MH / HMC
+transitions -- each as hand-written sm_100a CUDA reached through the C-ABI in
+``include/genjax_b200.h``.  There is no CPU fallback.
+"""
+
+from .core.choice_map import (
+    ChoiceMap,
+    ChoiceMapBuilder,
+    ChoiceMapNoValueAtAddress,
+    Selection,
+    SelectionBuilder,
+)
+from .core.key import KeyBatch, PRNGKey, fold_in, key, split
+from .gen import numpy_api as numpy
+from .gen.capture import AddressReuse, MissingAddress
+from .gen.distributions import (
+    Distribution,
+    ExactDensity,
+    NotFusable,
+    bernoulli,
+    beta,
+    categorical,
+    exact_density,
+    exponential,
+    flip,
+    gamma,
+    half_normal,
+    mv_normal_diag,
+    normal,
+    register_primitive,
+    uniform,
+)
+from .gen.gfi import (
+    Diff,
+    DiffAnnotate,
+    EditRequest,
+    EmptyRequest,
+    GenerativeFunction,
+    NoChange,
+    NotSupportedEditRequest,
+    Regenerate,
+    StaticRequest,
+    Trace,
+    UnknownChange,
+    Update,
+)
+from .gen.static import Batched, StaticGenerativeFunction, StaticTrace, gen, vmap
+from .inference.sp import Algorithm, SampleDistribution, Target
+from . import inference
+
+C = ChoiceMapBuilder
+S = SelectionBuilder
+
+__version__ = "0.1.0"

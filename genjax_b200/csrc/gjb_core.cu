@@ -1,0 +1,493 @@
+// libgjb_core.so -- model-independent kernels of the SMC hot path (sm_100a):
+// weight max / exact integer mass (log-sum-exp), systematic + multinomial
+// resampling over the integer CDF, ancestor gather, RNG test hooks.
+// C-ABI declared in include/genjax_b200.h; CPU restatement in oracle/smc.py.
+//
+// All kernels are HBM/L2-streaming integer/fp32 work: coalesced 128-bit loads,
+// warp-shuffle reductions and scans, no tensor cores.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/genjax_b200.h"
+#include "gjb_rng.cuh"
+
+namespace gjb {
+
+constexpr int kTile = 2048;      // particles per tile (fixed: part of the ABI)
+constexpr int kThreads = 256;    // threads per block in tile kernels
+constexpr int kItems = 8;        // particles per thread
+static_assert(kTile == kThreads * kItems, "tile shape");
+
+// floor(2^30 * exp(x)), x <= 0, from IEEE fp32 mul/add only (oracle/smc.py det_exp_q).
+__device__ __forceinline__ uint64_t det_exp_q(float x) {
+  float t = __fmul_rn(x, 0x1.715476p+0f);
+  if (!(t >= -62.0f)) return 0ull;  // NaN, -inf, negligible
+  t = fminf(t, 0.0f);
+  const float n = floorf(t);
+  const float g = __fadd_rn(__fadd_rn(t, -n), -0.5f);
+  float p = 0x1.ffcbfcp-17f;                         // ln2^7/7!
+  p = __fadd_rn(__fmul_rn(p, g), 0x1.430912p-13f);  // ln2^6/6!
+  p = __fadd_rn(__fmul_rn(p, g), 0x1.5d87fep-10f);  // ln2^5/5!
+  p = __fadd_rn(__fmul_rn(p, g), 0x1.3b2ab6p-7f);   // ln2^4/4!
+  p = __fadd_rn(__fmul_rn(p, g), 0x1.c6b08ep-5f);   // ln2^3/3!
+  p = __fadd_rn(__fmul_rn(p, g), 0x1.ebfbep-3f);    // ln2^2/2!
+  p = __fadd_rn(__fmul_rn(p, g), 0x1.62e43p-1f);    // ln2
+  p = __fadd_rn(__fmul_rn(p, g), 1.0f);
+  p = __fmul_rn(p, 0x1.6a09e6p+0f);                 // sqrt(2)
+  const uint64_t m = (uint64_t)__fmul_rn(p, 1073741824.0f);
+  return m >> (uint32_t)(-n);
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------- wmax
+
+__global__ void wmax_reset_kernel(uint32_t* wmax) { *wmax = GJB_WMAX_NEG_INF; }
+
+__global__ void __launch_bounds__(256) weight_max_kernel(const float* __restrict__ logw, int64_t n,
+                                                         uint32_t* __restrict__ wmax) {
+  float m = -INFINITY;
+  const int64_t n4 = n >> 2;
+  const float4* __restrict__ p4 = reinterpret_cast<const float4*>(logw);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(p4 + i);
+    m = fmaxf(fmaxf(m, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));  // fmaxf drops NaN
+  }
+  for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, logw[i]);
+  m = warp_max(m);
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : -INFINITY;
+    m = warp_max(m);
+    if (threadIdx.x == 0 && m > -INFINITY) atomicMax(wmax, fenc(m));
+  }
+}
+
+// ---------------------------------------------------------------- mass
+
+__device__ __forceinline__ float ref_max(const uint32_t* wmax, const float* m_global) {
+  return m_global ? __ldg(m_global) : fdec(__ldg(wmax));
+}
+
+// loads the 8 consecutive log-weights of this thread (0-mass padding past n)
+__device__ __forceinline__ void load_items(const float* __restrict__ logw, int64_t n, int64_t base, float (&x)[kItems]) {
+  if (base + kItems <= n && ((reinterpret_cast<uintptr_t>(logw + base) & 15) == 0)) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(logw + base));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(logw + base) + 1);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+    x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) x[k] = (base + k < n) ? logw[base + k] : -INFINITY;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) weight_mass_kernel(const float* __restrict__ logw, int64_t n,
+                                                               const uint32_t* __restrict__ wmax,
+                                                               const float* __restrict__ m_global,
+                                                               uint64_t* __restrict__ tile_mass) {
+  const float M = ref_max(wmax, m_global);
+  const int64_t base = (int64_t)blockIdx.x * kTile + threadIdx.x * kItems;
+  float x[kItems];
+  load_items(logw, n, base, x);
+  uint64_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) s += det_exp_q(__fadd_rn(x[k], -M));
+  s = warp_sum_u64(s);
+  __shared__ uint64_t sm[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < kThreads / 32 ? sm[threadIdx.x] : 0ull;
+    s = warp_sum_u64(s);
+    if (threadIdx.x == 0) tile_mass[blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) lse_finalize_kernel(const uint64_t* __restrict__ tile_mass, int n_tiles,
+                                                           const uint32_t* __restrict__ wmax,
+                                                           const float* __restrict__ m_global, int64_t n_total,
+                                                           double* __restrict__ out) {
+  uint64_t s = 0;
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) s += tile_mass[t];
+  s = warp_sum_u64(s);
+  __shared__ uint64_t sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t tot = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) tot += sm[w];
+    const double M = (double)ref_max(wmax, m_global);
+    out[0] = M;
+    out[1] = (double)tot;
+    out[2] = tot ? M + log((double)tot) - 30.0 * 0.693147180559945309417 - log((double)n_total) : -INFINITY;
+  }
+}
+
+// ------------------------------------------------------------ systematic
+
+// cumulative offspring count of a particle whose inclusive CDF value is C
+__device__ __forceinline__ int64_t offspring_cnt(uint64_t C, uint64_t S, double scale, double u0, int64_t n_total) {
+  if (C == S) return n_total;
+  const double pos = __dsub_rn(__dmul_rn((double)C, scale), u0);
+  double c = ceil(pos);
+  c = fmin(fmax(c, 0.0), (double)n_total);
+  return (int64_t)c;
+}
+
+__global__ void __launch_bounds__(kThreads) resample_systematic_kernel(const __grid_constant__ gjb_resample_args R) {
+  const float* __restrict__ logw = R.logw;
+  const int64_t n = R.n, n_total = R.n_total, out_lo = R.out_lo, out_n = R.out_n, anc_base = R.anc_base;
+  const uint32_t* __restrict__ wmax = R.wmax;
+  const float* __restrict__ m_global = R.m_global;
+  const uint64_t* __restrict__ tile_mass = R.tile_mass;
+  const uint64_t* __restrict__ c_offset = R.c_offset;
+  const uint64_t* __restrict__ s_total = R.s_total;
+  int32_t* __restrict__ ancestors = R.ancestors;
+  uint32_t key0 = R.key0, key1 = R.key1;
+  uint64_t key_index = R.key_index;
+  if (R.key_dev) {
+    key0 = __ldg(R.key_dev);
+    key1 = __ldg(R.key_dev + 1);
+    key_index = (uint64_t)__ldg(R.key_dev + 2) | ((uint64_t)__ldg(R.key_dev + 3) << 32);
+  }
+  __shared__ uint64_t sm_a[kThreads / 32];
+  __shared__ uint64_t sm_b[kThreads / 32];
+  __shared__ int64_t cnt_s[kTile + 1];
+  __shared__ int big_n;
+  __shared__ int big_list[64];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int n_tiles = gridDim.x;
+
+  // 1. exclusive prefix of the tiles before this one + total mass
+  uint64_t pre = 0, tot = 0;
+  for (int t = tid; t < n_tiles; t += kThreads) {
+    const uint64_t v = tile_mass[t];
+    tot += v;
+    if (t < (int)blockIdx.x) pre += v;
+  }
+  pre = warp_sum_u64(pre);
+  tot = warp_sum_u64(tot);
+  if (lane == 0) { sm_a[warp] = pre; sm_b[warp] = tot; }
+  if (tid == 0) big_n = 0;
+  __syncthreads();
+  pre = 0; tot = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) { pre += sm_a[w]; tot += sm_b[w]; }
+  __syncthreads();
+  const uint64_t S = s_total ? __ldg(s_total) : tot;
+  const uint64_t off = pre + (c_offset ? __ldg(c_offset) : 0ull);
+  if (blockIdx.x == 0 && tid == 0) {
+    if (R.lse_out) {
+      const double Md = (double)ref_max(wmax, m_global);
+      R.lse_out[0] = Md;
+      R.lse_out[1] = (double)S;
+      R.lse_out[2] = S ? Md + log((double)S) - 30.0 * 0.693147180559945309417 - log((double)n_total) : -INFINITY;
+    }
+    if (R.wmax_next) *R.wmax_next = GJB_WMAX_NEG_INF;
+  }
+
+  const int64_t tile_base = (int64_t)blockIdx.x * kTile;
+  if (S == 0) {  // every weight is zero: identity ancestors (collection invalid)
+    for (int k = tid; k < kTile; k += kThreads) {
+      const int64_t i = tile_base + k;
+      const int64_t j = anc_base + i;
+      if (i < n && j >= out_lo && j < out_lo + out_n) ancestors[j - out_lo] = (int32_t)j;
+    }
+    return;
+  }
+
+  // 2. q_i and block-wide inclusive scan
+  const float M = ref_max(wmax, m_global);
+  float x[kItems];
+  load_items(logw, n, tile_base + tid * kItems, x);
+  uint64_t q[kItems];
+  uint64_t tsum = 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) { q[k] = det_exp_q(__fadd_rn(x[k], -M)); tsum += q[k]; }
+  uint64_t inc = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) sm_a[warp] = inc;
+  __syncthreads();
+  uint64_t wpre = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) if (w < warp) wpre += sm_a[w];
+  uint64_t C = off + wpre + inc - tsum;  // exclusive prefix of this thread
+
+  // 3. cumulative offspring counts -> shared (blocked -> striped transpose)
+  const double u0 = (double)u01(philox4x32_10(make_uint4((uint32_t)key_index, (uint32_t)(key_index >> 32), 0u, 0u), key0, key1).x);
+  const double scale = __ddiv_rn((double)n_total, (double)S);
+  if (tid == 0) cnt_s[0] = offspring_cnt(C, S, scale, u0, n_total);
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    C += q[k];
+    cnt_s[1 + tid * kItems + k] = offspring_cnt(C, S, scale, u0, n_total);
+  }
+  __syncthreads();
+
+  // 4. striped write-out: consecutive threads own consecutive particles
+  const int64_t win_hi = out_lo + out_n;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    const int il = k * kThreads + tid;
+    const int64_t i = tile_base + il;
+    if (i >= n) break;
+    int64_t lo = cnt_s[il] > out_lo ? cnt_s[il] : out_lo;
+    int64_t hi = cnt_s[il + 1] < win_hi ? cnt_s[il + 1] : win_hi;
+    if (hi - lo > 16) {
+      const int slot = atomicAdd(&big_n, 1);
+      if (slot < 64) { big_list[slot] = il; continue; }
+    }
+    const int32_t a = (int32_t)(anc_base + i);
+    for (int64_t j = lo; j < hi; ++j) ancestors[j - out_lo] = a;
+  }
+  __syncthreads();
+  // heavy particles (degenerate weights): the whole block fills their range
+  const int nb = big_n < 64 ? big_n : 64;
+  for (int b = 0; b < nb; ++b) {
+    const int il = big_list[b];
+    int64_t lo = cnt_s[il] > out_lo ? cnt_s[il] : out_lo;
+    int64_t hi = cnt_s[il + 1] < win_hi ? cnt_s[il + 1] : win_hi;
+    const int32_t a = (int32_t)(anc_base + tile_base + il);
+    for (int64_t j = lo + tid; j < hi; j += kThreads) ancestors[j - out_lo] = a;
+  }
+}
+
+// ----------------------------------------------------------- multinomial
+
+__global__ void __launch_bounds__(kThreads) cdf_kernel(const float* __restrict__ logw, int64_t n,
+                                                       const uint32_t* __restrict__ wmax,
+                                                       const uint64_t* __restrict__ tile_mass,
+                                                       uint64_t* __restrict__ cdf) {
+  __shared__ uint64_t sm_a[kThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint64_t pre = 0;
+  for (int t = tid; t < (int)blockIdx.x; t += kThreads) pre += tile_mass[t];
+  pre = warp_sum_u64(pre);
+  if (lane == 0) sm_a[warp] = pre;
+  __syncthreads();
+  pre = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) pre += sm_a[w];
+  __syncthreads();
+  const float M = fdec(__ldg(wmax));
+  const int64_t base = (int64_t)blockIdx.x * kTile + tid * kItems;
+  float x[kItems];
+  load_items(logw, n, base, x);
+  uint64_t q[kItems], tsum = 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) { q[k] = det_exp_q(__fadd_rn(x[k], -M)); tsum += q[k]; }
+  uint64_t inc = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) sm_a[warp] = inc;
+  __syncthreads();
+  uint64_t wpre = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) if (w < warp) wpre += sm_a[w];
+  uint64_t C = pre + wpre + inc - tsum;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    C += q[k];
+    if (base + k < n) cdf[base + k] = C;
+  }
+}
+
+__global__ void __launch_bounds__(256) multinomial_search_kernel(const uint64_t* __restrict__ cdf, int64_t n,
+                                                                 uint32_t key0, uint32_t key1, uint64_t idx_offset,
+                                                                 int64_t n_out, int32_t* __restrict__ ancestors) {
+  const uint64_t S = cdf[n - 1];
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_out; j += (int64_t)gridDim.x * blockDim.x) {
+    if (S == 0) { ancestors[j] = (int32_t)(j < n ? j : n - 1); continue; }
+    const uint64_t g = idx_offset + (uint64_t)j;
+    const uint4 w = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), 1u, 0u), key0, key1);
+    const uint64_t r = ((uint64_t)w.x << 32) | (uint64_t)w.y;
+    const uint64_t tgt = __umul64hi(r, S);
+    int64_t lo = 0, hi = n;  // first i with cdf[i] > tgt
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (__ldg(cdf + mid) > tgt) hi = mid; else lo = mid + 1;
+    }
+    ancestors[j] = (int32_t)lo;
+  }
+}
+
+// ---------------------------------------------------------------- gather
+
+template <typename T>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const T* __restrict__ src, const int32_t* __restrict__ anc,
+                                                          T* __restrict__ dst, int64_t n_out, int32_t w) {
+  const int64_t total = n_out * w;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = k / w;
+    const int32_t col = (int32_t)(k - row * w);
+    dst[k] = __ldg(src + (int64_t)__ldg(anc + row) * w + col);
+  }
+}
+
+// ------------------------------------------------------------- RNG hooks
+
+__global__ void philox_fill_kernel(uint32_t k0, uint32_t k1, uint64_t off, uint32_t site, uint32_t chunk, int64_t n,
+                                   uint4* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t g = off + (uint64_t)i;
+    out[i] = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), chunk, site), k0, k1);
+  }
+}
+
+__global__ void normal_fill_kernel(uint32_t k0, uint32_t k1, uint64_t off, uint32_t site, int64_t n, int d,
+                                   float* __restrict__ out) {
+  const int chunks = (d + 3) >> 2;
+  const int64_t total = n * chunks;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = k / chunks;
+    const int c = (int)(k - i * chunks);
+    const Lane l = make_lane(k0, k1, off + (uint64_t)i);
+    const float4 z = normal4(l, site, (uint32_t)c);
+    const float zz[4] = {z.x, z.y, z.z, z.w};
+    for (int s = 0; s < 4; ++s)
+      if (4 * c + s < d) out[i * d + 4 * c + s] = zz[s];
+  }
+}
+
+static int grid_for(int64_t work, int threads, int max_blocks = 148 * 8) {
+  int64_t b = (work + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+static inline int launch_status() {
+  const cudaError_t e = cudaGetLastError();
+  return (int)e;
+}
+
+}  // namespace gjb
+
+using namespace gjb;
+
+extern "C" {
+
+int gjb_abi_version(void) { return GJB_ABI_VERSION; }
+
+int64_t gjb_resample_workspace_bytes(int64_t n) {
+  if (n < 0) return GJB_E_ARG;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  return (tiles > 0 ? tiles : 1) * 8;
+}
+
+int gjb_wmax_reset(uint32_t* wmax, void* stream) {
+  if (!wmax) return GJB_E_ARG;
+  wmax_reset_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(wmax);
+  return launch_status();
+}
+
+int gjb_weight_max(const float* logw, int64_t n, uint32_t* wmax, void* stream) {
+  if (!logw || !wmax || n < 0) return GJB_E_ARG;
+  if ((reinterpret_cast<uintptr_t>(logw) & 15) != 0) return GJB_E_ARG;
+  if (n == 0) return 0;
+  weight_max_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(logw, n, wmax);
+  return launch_status();
+}
+
+int gjb_weight_mass(const float* logw, int64_t n, const uint32_t* wmax, const float* m_global, uint64_t* tile_mass,
+                    void* stream) {
+  if (!logw || !tile_mass || (!wmax && !m_global) || n < 0) return GJB_E_ARG;
+  if (n == 0) return 0;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  if (tiles > 0x7fffffff) return GJB_E_RANGE;
+  weight_mass_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(logw, n, wmax, m_global, tile_mass);
+  return launch_status();
+}
+
+int gjb_lse_finalize(const uint64_t* tile_mass, int64_t n, const uint32_t* wmax, const float* m_global,
+                     int64_t n_total, double* lse_out, void* stream) {
+  if (!tile_mass || !lse_out || (!wmax && !m_global) || n <= 0 || n_total <= 0) return GJB_E_ARG;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  lse_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(tile_mass, (int)tiles, wmax, m_global, n_total, lse_out);
+  return launch_status();
+}
+
+int gjb_resample_systematic(const gjb_resample_args* a, void* stream) {
+  if (!a || !a->logw || !a->tile_mass || !a->ancestors || (!a->wmax && !a->m_global)) return GJB_E_ARG;
+  if (a->n <= 0 || a->n_total <= 0 || a->out_n < 0 || a->out_lo < 0) return GJB_E_ARG;
+  if (a->n_total > 0x7fffffffLL) return GJB_E_RANGE;  // int32 ancestors
+  const int64_t tiles = (a->n + kTile - 1) / kTile;
+  resample_systematic_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a);
+  return launch_status();
+}
+
+int gjb_resample_multinomial(const float* logw, int64_t n, const uint32_t* wmax, const uint64_t* tile_mass,
+                             uint64_t* cdf, uint32_t key0, uint32_t key1, uint64_t idx_offset, int64_t n_out,
+                             int32_t* ancestors, void* stream) {
+  if (!logw || !wmax || !tile_mass || !cdf || !ancestors || n <= 0 || n_out < 0) return GJB_E_ARG;
+  if (n > 0x7fffffffLL) return GJB_E_RANGE;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  cdf_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(logw, n, wmax, tile_mass, cdf);
+  int e = launch_status();
+  if (e) return e;
+  if (n_out == 0) return 0;
+  multinomial_search_kernel<<<grid_for(n_out, 256), 256, 0, (cudaStream_t)stream>>>(cdf, n, key0, key1, idx_offset,
+                                                                                   n_out, ancestors);
+  return launch_status();
+}
+
+int gjb_gather_rows(const void* src, const int32_t* ancestors, void* dst, int64_t n_out, int32_t row_bytes,
+                    void* stream) {
+  if (!src || !ancestors || !dst || n_out < 0 || row_bytes <= 0 || (row_bytes & 3)) return GJB_E_ARG;
+  if (n_out == 0) return 0;
+  const bool v16 = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+  if (v16) {
+    const int w = row_bytes / 16;
+    gather_rows_kernel<uint4><<<grid_for(n_out * w, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)src, ancestors, (uint4*)dst, n_out, w);
+  } else {
+    const int w = row_bytes / 4;
+    gather_rows_kernel<uint32_t><<<grid_for(n_out * w, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+        (const uint32_t*)src, ancestors, (uint32_t*)dst, n_out, w);
+  }
+  return launch_status();
+}
+
+int gjb_philox_fill(uint32_t key0, uint32_t key1, uint64_t idx_offset, uint32_t site, uint32_t chunk, int64_t n,
+                    uint32_t* out4, void* stream) {
+  if (!out4 || n < 0) return GJB_E_ARG;
+  if (n == 0) return 0;
+  philox_fill_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(key0, key1, idx_offset, site, chunk, n,
+                                                                       (uint4*)out4);
+  return launch_status();
+}
+
+int gjb_normal_fill(uint32_t key0, uint32_t key1, uint64_t idx_offset, uint32_t site, int64_t n, int32_t d,
+                    float* out, void* stream) {
+  if (!out || n < 0 || d <= 0) return GJB_E_ARG;
+  if (n == 0) return 0;
+  normal_fill_kernel<<<grid_for(n * ((d + 3) / 4), 256), 256, 0, (cudaStream_t)stream>>>(key0, key1, idx_offset, site,
+                                                                                        n, d, out);
+  return launch_status();
+}
+
+}  // extern "C"

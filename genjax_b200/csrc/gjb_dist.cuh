@@ -1,0 +1,152 @@
+// Device library of primitive distributions: (sampler, logpdf) pairs used by
+// the generated model kernels.  Formulas follow TFP 0.23's float32 operation
+// order as restated in oracle/dists.py (reference call sites:
+// generative_functions/distributions/tensorflow_probability/__init__.py:52-62,
+// distribution.py:371-396).
+#pragma once
+#include <math.h>
+
+#include "gjb_rng.cuh"
+
+namespace gjb {
+
+constexpr float kHalfLog2Pi = 0.91893853320467274178f;
+constexpr float kLog2OverPiHalf = -0.22579135264472743236f;  // 0.5*log(2/pi)
+
+// ------------------------------------------------------------------ normal
+struct Normal {
+  __device__ static __forceinline__ float sample(const Lane& l, uint32_t site, float loc, float scale) {
+    return loc + scale * normal1(l, site, 0);
+  }
+  __device__ static __forceinline__ float logpdf(float v, float loc, float scale) {
+    const float z = v / scale - loc / scale;
+    return -0.5f * (z * z) - (kHalfLog2Pi + logf(scale));
+  }
+};
+
+struct Uniform {
+  __device__ static __forceinline__ float sample(const Lane& l, uint32_t site, float lo, float hi) {
+    return lo + (hi - lo) * u01(l.words(site, 0).x);
+  }
+  __device__ static __forceinline__ float logpdf(float v, float lo, float hi) {
+    return (v >= lo && v <= hi) ? -logf(hi - lo) : -INFINITY;
+  }
+};
+
+struct Exponential {
+  __device__ static __forceinline__ float sample(const Lane& l, uint32_t site, float rate) {
+    return -logf(u01(l.words(site, 0).x)) / rate;
+  }
+  __device__ static __forceinline__ float logpdf(float v, float rate) {
+    return v < 0.0f ? -INFINITY : logf(rate) - rate * v;
+  }
+};
+
+struct HalfNormal {
+  __device__ static __forceinline__ float sample(const Lane& l, uint32_t site, float scale) {
+    return fabsf(normal1(l, site, 0)) * scale;
+  }
+  __device__ static __forceinline__ float logpdf(float v, float scale) {
+    const float z = v / scale;
+    return v < 0.0f ? -INFINITY : kLog2OverPiHalf - logf(scale) - 0.5f * z * z;
+  }
+};
+
+// --------------------------------------------------------- flip / bernoulli
+__device__ __forceinline__ float softplusf(float x) { return fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x))); }
+
+struct Flip {  // tfd.Bernoulli(probs=p); value is int32 0/1
+  __device__ static __forceinline__ int sample(const Lane& l, uint32_t site, float p) {
+    return u01(l.words(site, 0).x) < p ? 1 : 0;
+  }
+  __device__ static __forceinline__ float logpdf(int v, float p) {
+    const float x = (float)v;
+    const float a = (x == 0.0f) ? 0.0f : x * logf(p);
+    const float b = ((1.0f - x) == 0.0f) ? 0.0f : (1.0f - x) * log1pf(-p);
+    return a + b;
+  }
+};
+
+struct Bernoulli {  // tfd.Bernoulli(logits=l)
+  __device__ static __forceinline__ int sample(const Lane& l, uint32_t site, float logit) {
+    const float p = 1.0f / (1.0f + expf(-logit));
+    return u01(l.words(site, 0).x) < p ? 1 : 0;
+  }
+  __device__ static __forceinline__ float logpdf(int v, float logit) {
+    const float x = (float)v;
+    return -softplusf(-logit) * x - softplusf(logit) * (1.0f - x);
+  }
+};
+
+// -------------------------------------------------------------- categorical
+// logits: K contiguous floats (shared memory row, global row or registers)
+struct Categorical {
+  __device__ static __forceinline__ int sample(const Lane& l, uint32_t site, const float* logits, int K) {
+    float m = -INFINITY;
+    for (int j = 0; j < K; ++j) m = fmaxf(m, logits[j]);
+    float tot = 0.0f;
+    for (int j = 0; j < K; ++j) tot += expf(logits[j] - m);
+    const float t = u01(l.words(site, 0).x) * tot;
+    float acc = 0.0f;
+    int k = K - 1;
+    for (int j = 0; j < K; ++j) {
+      acc += expf(logits[j] - m);
+      if (acc > t) { k = j; break; }
+    }
+    return k;
+  }
+  __device__ static __forceinline__ float logpdf(int v, const float* logits, int K) {
+    float m = -INFINITY;
+    for (int j = 0; j < K; ++j) m = fmaxf(m, logits[j]);
+    float tot = 0.0f;
+    for (int j = 0; j < K; ++j) tot += expf(logits[j] - m);
+    const int k = min(max(v, 0), K - 1);
+    return (logits[k] - m) - logf(tot);
+  }
+};
+
+// -------------------------------------------------------------- gamma, beta
+// Marsaglia-Tsang; attempt t uses chunk chunk0+t: words (x,y) -> normal,
+// z -> acceptance uniform, w (attempt 0) -> boost uniform for a < 1.
+__device__ __forceinline__ float gamma_mt(const Lane& l, uint32_t site, float a, uint32_t chunk0) {
+  const bool boost = a < 1.0f;
+  const float ae = boost ? a + 1.0f : a;
+  const float d = ae - (1.0f / 3.0f);
+  const float c = 1.0f / sqrtf(9.0f * d);
+  float out = 0.0f, ub = 0.5f;
+  for (uint32_t t = 0; t < 64u; ++t) {
+    const uint4 w = l.words(site, chunk0 + t);
+    if (t == 0) ub = u01(w.w);
+    const float x = box_muller(w.x, w.y).x;
+    const float u = u01(w.z);
+    const float v = 1.0f + c * x;
+    const float v3 = v * v * v;
+    if (v > 0.0f && logf(u) < 0.5f * x * x + d - d * v3 + d * logf(v3)) { out = d * v3; break; }
+  }
+  return boost ? out * expf(logf(ub) / a) : out;
+}
+
+struct Gamma {
+  __device__ static __forceinline__ float sample(const Lane& l, uint32_t site, float a, float rate) {
+    return gamma_mt(l, site, a, 0) / rate;
+  }
+  __device__ static __forceinline__ float logpdf(float v, float a, float rate) {
+    const float t = ((a - 1.0f) == 0.0f) ? 0.0f : (a - 1.0f) * logf(v);
+    return t - rate * v - (lgammaf(a) - a * logf(rate));
+  }
+};
+
+struct Beta {
+  __device__ static __forceinline__ float sample(const Lane& l, uint32_t site, float a, float b) {
+    const float ga = gamma_mt(l, site, a, 0);
+    const float gb = gamma_mt(l, site, b, 64);
+    return ga / (ga + gb);
+  }
+  __device__ static __forceinline__ float logpdf(float v, float a, float b) {
+    const float t1 = ((a - 1.0f) == 0.0f) ? 0.0f : (a - 1.0f) * logf(v);
+    const float t2 = ((b - 1.0f) == 0.0f) ? 0.0f : (b - 1.0f) * log1pf(-v);
+    return t1 + t2 - (lgammaf(a) + lgammaf(b) - lgammaf(a + b));
+  }
+};
+
+}  // namespace gjb

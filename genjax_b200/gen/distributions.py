@@ -1,0 +1,393 @@
+"""Primitive distributions: host objects with a device-side (sampler, logpdf)
+pair in csrc/gjb_dist.cuh.
+
+API mirror of ``Distribution`` / ``ExactDensity`` / ``exact_density``
+(generative_functions/distributions/distribution.py:90-106, 359-396, 436-476)
+and of the TFP wrappers the hot path uses
+(distributions/tensorflow_probability/__init__.py:72-294).  In the reference a
+distribution's ``sample`` / ``logpdf`` are arbitrary JAX-traceable Python; here
+a primitive can be fused only if it has device code registered under its name
+-- anything else raises ``NotFusable`` instead of falling back to the CPU.
+"""
+
+from __future__ import annotations
+
+import warnings
+from typing import Any
+
+from . import expr as E
+from .expr import Expr, F32, I32
+from .gfi import GenerativeFunction, GenerativeFunctionClosure
+
+
+class NotFusable(NotImplementedError):
+    pass
+
+
+def implicit_logit_warning():
+    """distribution.py:479-500: bare positional arg to categorical/bernoulli = logits."""
+    warnings.warn(
+        "You are using the implicit logits argument; use the explicit `logits=` or `probs=` keyword instead.",
+        DeprecationWarning,
+        stacklevel=3,
+    )
+
+
+class Distribution(GenerativeFunction):
+    """A single random choice.  Subclasses define the canonical argument list
+    and the CUDA snippets the code generator splices into the fused kernel."""
+
+    name: str = "?"
+    cuda: str = "?"  # struct in gjb_dist.cuh
+    n_args: int = 0
+    value_dtype: str = F32
+    vector: bool = False  # value has an event axis
+
+    # -- closure syntax: dist(args) @ "addr"
+    def __call__(self, *args, **kwargs) -> GenerativeFunctionClosure:
+        return GenerativeFunctionClosure(self, args, kwargs)
+
+    def canonical_args(self, args) -> list[Expr]:
+        args, kwargs = _split_kwargs(args)
+        return [E.lift(a) for a in self._canonical(args, kwargs)]
+
+    def _canonical(self, args, kwargs) -> list:
+        if kwargs:
+            raise TypeError(f"{self.name} takes positional arguments only")
+        if len(args) != self.n_args:
+            raise TypeError(f"{self.name} expects {self.n_args} arguments, got {len(args)}")
+        return list(args)
+
+    def value_type(self, cargs: list[Expr]) -> tuple[str, tuple]:
+        return self.value_dtype, ()
+
+    # -- codegen hooks (scalar distributions) ---------------------------
+    def emit_sample(self, site: int, a: list[str], cg) -> str:
+        return f"gjb::{self.cuda}::sample(rng, {site + 1}u, {', '.join(a)})"
+
+    def emit_logpdf(self, v: str, a: list[str], cg) -> str:
+        return f"gjb::{self.cuda}::logpdf({v}, {', '.join(a)})"
+
+    def __repr__(self):
+        return f"genjax_b200.{self.name}"
+
+
+def _split_kwargs(args):
+    """Unpack the reference's ``(args, kwargs_dict)`` convention (distribution.py:448-462)."""
+    if isinstance(args, tuple) and len(args) == 2 and isinstance(args[1], dict) and isinstance(args[0], tuple):
+        return args[0], args[1]
+    return tuple(args), {}
+
+
+class _Normal(Distribution):
+    name, cuda, n_args = "normal", "Normal", 2
+
+    def _canonical(self, args, kwargs):
+        if kwargs:
+            args = tuple(args) + tuple(kwargs[k] for k in ("loc", "scale") if k in kwargs)
+        return super()._canonical(args, {})
+
+
+class _Uniform(Distribution):
+    name, cuda, n_args = "uniform", "Uniform", 2
+
+    def _canonical(self, args, kwargs):
+        if kwargs:
+            args = tuple(args) + tuple(kwargs[k] for k in ("low", "high") if k in kwargs)
+        if len(args) == 0:
+            args = (0.0, 1.0)
+        return super()._canonical(args, {})
+
+
+class _Exponential(Distribution):
+    name, cuda, n_args = "exponential", "Exponential", 1
+
+
+class _HalfNormal(Distribution):
+    name, cuda, n_args = "half_normal", "HalfNormal", 1
+
+
+class _Gamma(Distribution):
+    name, cuda, n_args = "gamma", "Gamma", 2
+
+
+class _Beta(Distribution):
+    name, cuda, n_args = "beta", "Beta", 2
+
+
+class _Flip(Distribution):
+    """tfd.Bernoulli(probs=p, dtype=bool) (tensorflow_probability/__init__.py:155)."""
+
+    name, cuda, n_args, value_dtype = "flip", "Flip", 1, I32
+    bool_valued = True
+
+
+class _Bernoulli(Distribution):
+    """tfd.Bernoulli(logits=...) or (probs=...) (tensorflow_probability/__init__.py:72)."""
+
+    name, cuda, n_args, value_dtype = "bernoulli", "Bernoulli", 1, I32
+
+    def _canonical(self, args, kwargs):
+        if "probs" in kwargs:
+            p = E.lift(kwargs["probs"])
+            return [E.unary("log", p) - E.unary("log1p", -p)]
+        if "logits" in kwargs:
+            return [kwargs["logits"]]
+        if len(args) == 1:
+            implicit_logit_warning()
+            return [args[0]]
+        raise TypeError("bernoulli expects logits= or probs=")
+
+
+class _Categorical(Distribution):
+    """tfd.Categorical(logits=...) (tensorflow_probability/__init__.py:102)."""
+
+    name, cuda, n_args, value_dtype = "categorical", "Categorical", 1, I32
+
+    def _canonical(self, args, kwargs):
+        kwargs = {k: v for k, v in kwargs.items() if k != "sample_shape"}
+        if "probs" in kwargs:
+            return [E.unary("log", E.lift(kwargs["probs"]))]
+        if "logits" in kwargs:
+            return [kwargs["logits"]]
+        if len(args) == 1:
+            implicit_logit_warning()
+            return [args[0]]
+        raise TypeError("categorical expects logits= or probs=")
+
+    def value_type(self, cargs):
+        if cargs[0].ndim != 1:
+            raise TypeError("categorical logits must be a vector")
+        return I32, ()
+
+    def emit_sample(self, site, a, cg):
+        ptr, k = a[0]
+        return f"gjb::Categorical::sample(rng, {site + 1}u, {ptr}, {k})"
+
+    def emit_logpdf(self, v, a, cg):
+        ptr, k = a[0]
+        return f"gjb::Categorical::logpdf({v}, {ptr}, {k})"
+
+
+class _MvNormalDiag(Distribution):
+    """tfd.MultivariateNormalDiag(loc, scale_diag) (tensorflow_probability/__init__.py:239)."""
+
+    name, cuda, n_args, vector = "mv_normal_diag", "MvNormalDiag", 2, True
+
+    def value_type(self, cargs):
+        d = max((c.shape[0] for c in cargs if c.ndim == 1), default=0)
+        if d == 0:
+            raise TypeError("mv_normal_diag needs a vector loc or scale_diag")
+        return F32, (d,)
+
+
+normal = _Normal()
+uniform = _Uniform()
+exponential = _Exponential()
+half_normal = _HalfNormal()
+gamma = _Gamma()
+beta = _Beta()
+flip = _Flip()
+bernoulli = _Bernoulli()
+categorical = _Categorical()
+mv_normal_diag = _MvNormalDiag()
+
+REGISTRY: dict[str, Distribution] = {
+    d.name: d
+    for d in (normal, uniform, exponential, half_normal, gamma, beta, flip, bernoulli, categorical, mv_normal_diag)
+}
+
+
+class ExactDensity(Distribution):
+    """Host-only distribution defined by Python ``sample`` / ``logpdf``
+    (distribution.py:359-396).  It keeps the reference's extension API but is
+    NOT fusable: using it inside a ``@gen`` model on the GPU path raises."""
+
+    def sample(self, key, *args):  # pragma: no cover - interface
+        raise NotImplementedError
+
+    def logpdf(self, v, *args):  # pragma: no cover - interface
+        raise NotImplementedError
+
+    def canonical_args(self, args):
+        raise NotFusable(
+            f"distribution {self.name!r} has no device-side (sampler, logpdf) pair; register one with "
+            "genjax_b200.register_primitive(...) -- there is no CPU fallback on the fused path"
+        )
+
+
+def exact_density(sample, logpdf, name: str = "custom") -> ExactDensity:
+    """``exact_density(sample, logpdf, name)`` (distribution.py:436-476)."""
+
+    class _Custom(ExactDensity):
+        pass
+
+    c = _Custom()
+    c.name = name
+    c.sample = lambda key, *a: sample(key, *a)  # type: ignore[assignment]
+    c.logpdf = lambda v, *a: logpdf(v, *a)  # type: ignore[assignment]
+    return c
+
+
+def register_primitive(name: str, cuda_struct: str, n_args: int, value_dtype: str = F32) -> Distribution:
+    """Register a primitive whose ``sample(rng, site, args...)`` / ``logpdf(v, args...)``
+    live in a CUDA struct visible to the generated kernels (gjb_dist.cuh or a
+    user header on the include path) -- the fusable form of ``exact_density``."""
+
+    class _P(Distribution):
+        pass
+
+    p = _P()
+    p.name, p.cuda, p.n_args, p.value_dtype = name, cuda_struct, n_args, value_dtype
+    REGISTRY[name] = p
+    return p
+
+
+# ---------------------------------------------------------------------------
+# Direct GFI use of a distribution (``genjax.normal.sample(key, 0., 1.)``,
+# ``normal(0., 1.).simulate(key, ())``, ``categorical.random_weighted(key, logits)``;
+# distribution.py:92-161, 360-419): a one-site static model on the same fused path.
+
+
+class DistributionTrace:
+    """distribution.py:60-87: trace of a single random choice."""
+
+    def __init__(self, gen_fn, inner, args):
+        self.gen_fn = gen_fn
+        self.inner = inner
+        self.args = args
+
+    def get_gen_fn(self):
+        return self.gen_fn
+
+    def get_args(self):
+        return self.args
+
+    def get_retval(self):
+        return self.inner.get_retval()
+
+    def get_score(self):
+        return self.inner.get_score()
+
+    def get_choices(self):
+        from ..core.choice_map import ChoiceMap
+
+        return ChoiceMap.choice(self.inner.get_retval())
+
+    get_sample = get_choices
+
+    def get_value(self):
+        return self.inner.get_retval()
+
+
+def _wrapped_model(dist: Distribution, kw_names: tuple):
+    cache = dist.__dict__.setdefault("_wrapped", {})
+    m = cache.get(kw_names)
+    if m is None:
+        from .static import gen
+
+        n_kw = len(kw_names)
+
+        def body(*flat):
+            pos = flat[: len(flat) - n_kw] if n_kw else flat
+            kw = dict(zip(kw_names, flat[len(flat) - n_kw:])) if n_kw else {}
+            return dist(*pos, **kw) @ "_v"
+
+        body.__name__ = f"dist_{dist.name}"
+        m = gen(body)
+        cache[kw_names] = m
+    return m
+
+
+def _flat_call(dist, args):
+    pos, kw = _split_kwargs(args)
+    names = tuple(kw.keys())
+    return _wrapped_model(dist, names), tuple(pos) + tuple(kw[k] for k in names)
+
+
+def _d_simulate(self, key, args):
+    m, flat = _flat_call(self, args)
+    return DistributionTrace(self, m.simulate(key, flat), args)
+
+
+def _d_generate(self, key, constraint, args):
+    from ..core.choice_map import ChoiceMap
+
+    m, flat = _flat_call(self, args)
+    if constraint is not None and constraint.has_value():
+        chm = ChoiceMap.entry(constraint.get_value(), "_v")
+    else:
+        chm = ChoiceMap.empty()
+    tr, w = m.generate(key, chm, flat)
+    return DistributionTrace(self, tr, args), w
+
+
+def _d_assess(self, sample, args):
+    from ..core.choice_map import ChoiceMap
+
+    m, flat = _flat_call(self, args)
+    if not sample.has_value():
+        raise ValueError("assess on a distribution needs a value choice map")
+    return m.assess(ChoiceMap.entry(sample.get_value(), "_v"), flat)
+
+
+def _d_sample(self, key, *args, **kwargs):
+    a = (args, kwargs) if kwargs else args
+    return _d_simulate(self, key, a).get_retval()
+
+
+def _d_logpdf(self, v, *args, **kwargs):
+    from ..core.choice_map import ChoiceMap
+
+    a = (args, kwargs) if kwargs else args
+    score, _ = _d_assess(self, ChoiceMap.choice(v), a)
+    return score
+
+
+def _d_random_weighted(self, key, *args, **kwargs):
+    a = (args, kwargs) if kwargs else args
+    tr = _d_simulate(self, key, a)
+    return tr.get_score(), tr.get_retval()
+
+
+def _d_estimate_logpdf(self, key, v, *args, **kwargs):
+    return _d_logpdf(self, v, *args, **kwargs)
+
+
+def _d_edit(self, key, trace, request, argdiffs):
+    from ..core.choice_map import ChoiceMap
+    from .gfi import Diff, EmptyRequest, Regenerate, Update
+
+    new_args = Diff.tree_primal(argdiffs) if argdiffs not in (None, ()) else trace.get_args()
+    m, flat = _flat_call(self, new_args)
+    inner = trace.inner
+    if isinstance(request, Update):
+        c = request.constraint
+        chm = ChoiceMap.entry(c.get_value(), "_v") if c.has_value() else ChoiceMap.empty()
+        tr, w, rd, bwd = m.edit(key, inner, Update(chm), Diff.unknown_change(flat))
+        disc = bwd.constraint
+        back = ChoiceMap.choice(disc["_v"]) if "_v" in disc else ChoiceMap.empty()
+        return DistributionTrace(self, tr, new_args), w, rd, Update(back)
+    if isinstance(request, Regenerate):
+        from ..core.choice_map import Selection
+
+        sel = Selection.at["_v"] if request.selection.check() else Selection.none()
+        tr, w, rd, bwd = m.edit(key, inner, Regenerate(sel), Diff.unknown_change(flat))
+        disc = bwd.constraint
+        back = ChoiceMap.choice(disc["_v"]) if "_v" in disc else ChoiceMap.empty()
+        return DistributionTrace(self, tr, new_args), w, rd, Update(back)
+    if isinstance(request, EmptyRequest):
+        return _d_edit(self, key, trace, Update(ChoiceMap.empty()), argdiffs)
+    from .gfi import NotSupportedEditRequest
+
+    raise NotSupportedEditRequest(request)
+
+
+Distribution.simulate = _d_simulate
+Distribution.generate = _d_generate
+Distribution.assess = _d_assess
+Distribution.sample = _d_sample
+Distribution.logpdf = _d_logpdf
+Distribution.random_weighted = _d_random_weighted
+Distribution.estimate_logpdf = _d_estimate_logpdf
+Distribution.edit = _d_edit

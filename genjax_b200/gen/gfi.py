@@ -1,0 +1,326 @@
+"""Generative-function interface: abstract base, closure syntax, traces,
+edit requests and argdiffs.
+
+API mirror of src/genjax/_src/core/generative/generative_function.py
+(``Trace:72``, ``GenerativeFunction:238``, ``importance:629-675``,
+``update:611``, ``propose:677``, ``GenerativeFunctionClosure`` ``__matmul__:1568``,
+``Update:1688``), concepts.py (``EditRequest:95``), requests.py
+(``EmptyRequest:49``, ``Regenerate:64``) and core/compiler/interpreters/
+incremental.py (``Diff:89``, ``NoChange``, ``UnknownChange``).
+"""
+
+from __future__ import annotations
+
+from typing import Any
+
+from ..core.choice_map import ChoiceMap, Selection
+
+
+# --------------------------------------------------------------------- Diff
+
+
+class ChangeType:
+    pass
+
+
+class _NoChange(ChangeType):
+    def __repr__(self):
+        return "NoChange"
+
+
+class _UnknownChange(ChangeType):
+    def __repr__(self):
+        return "UnknownChange"
+
+
+NoChange = _NoChange()
+UnknownChange = _UnknownChange()
+
+
+class Diff:
+    """A value tagged with change information (incremental.py:89-294)."""
+
+    __slots__ = ("primal", "tangent")
+
+    def __init__(self, primal, tangent: ChangeType):
+        self.primal = primal
+        self.tangent = tangent
+
+    def get_primal(self):
+        return self.primal
+
+    def get_tangent(self):
+        return self.tangent
+
+    @staticmethod
+    def _map(tree, fn):
+        if isinstance(tree, Diff):
+            return fn(tree)
+        if isinstance(tree, tuple):
+            return tuple(Diff._map(t, fn) for t in tree)
+        if isinstance(tree, list):
+            return [Diff._map(t, fn) for t in tree]
+        if isinstance(tree, dict):
+            return {k: Diff._map(v, fn) for k, v in tree.items()}
+        return fn(tree)
+
+    @staticmethod
+    def no_change(tree):
+        return Diff._map(tree, lambda v: Diff(v.primal if isinstance(v, Diff) else v, NoChange))
+
+    @staticmethod
+    def unknown_change(tree):
+        return Diff._map(tree, lambda v: Diff(v.primal if isinstance(v, Diff) else v, UnknownChange))
+
+    @staticmethod
+    def tree_primal(tree):
+        return Diff._map(tree, lambda v: v.primal if isinstance(v, Diff) else v)
+
+    tree_diff_no_change = no_change
+    tree_diff_unknown_change = unknown_change
+
+    @staticmethod
+    def tree_tangent(tree):
+        return Diff._map(tree, lambda v: v.tangent if isinstance(v, Diff) else NoChange)
+
+    @staticmethod
+    def static_check_no_change(tree) -> bool:
+        ok = True
+
+        def chk(v):
+            nonlocal ok
+            if isinstance(v, Diff) and v.tangent is not NoChange:
+                ok = False
+            return v
+
+        Diff._map(tree, chk)
+        return ok
+
+    @staticmethod
+    def static_check_tree_diff(tree) -> bool:
+        ok = True
+
+        def chk(v):
+            nonlocal ok
+            if not isinstance(v, Diff):
+                ok = False
+            return v
+
+        Diff._map(tree, chk)
+        return ok
+
+    def __repr__(self):
+        return f"Diff({self.primal!r}, {self.tangent!r})"
+
+
+# ----------------------------------------------------------------- requests
+
+
+class NotSupportedEditRequest(Exception):
+    """distribution.py:341-342, static.py:980-981."""
+
+    def __init__(self, request):
+        self.request = request
+        super().__init__(request)
+
+
+class EditRequest:
+    """concepts.py:95-131: ``request.edit(key, trace, argdiffs)``."""
+
+    def edit(self, key, tr: "Trace", argdiffs):
+        return tr.get_gen_fn().edit(key, tr, self, argdiffs)
+
+    def dimap(self, *, pre=lambda v: v, post=lambda v: v):
+        return DiffAnnotate(self, argdiff_fn=pre, retdiff_fn=post)
+
+    def map(self, post):
+        return self.dimap(post=post)
+
+    def contramap(self, pre):
+        return self.dimap(pre=pre)
+
+
+class PrimitiveEditRequest(EditRequest):
+    pass
+
+
+class EmptyRequest(EditRequest):
+    """requests.py:49-61."""
+
+    def edit(self, key, tr, argdiffs):
+        if Diff.static_check_no_change(argdiffs):
+            return tr, _zero_weight(tr), Diff.no_change(tr.get_retval()), EmptyRequest()
+        return Update(ChoiceMap.empty()).edit(key, tr, argdiffs)
+
+
+class Update(PrimitiveEditRequest):
+    """generative_function.py:1688."""
+
+    def __init__(self, constraint: ChoiceMap):
+        self.constraint = constraint
+
+    def __repr__(self):
+        return f"Update({self.constraint!r})"
+
+
+class Regenerate(PrimitiveEditRequest):
+    """requests.py:64-66."""
+
+    def __init__(self, selection: Selection):
+        self.selection = selection
+
+    def __repr__(self):
+        return f"Regenerate({self.selection!r})"
+
+
+class StaticRequest(EditRequest):
+    """static.py:130-131: per-address sub-requests."""
+
+    def __init__(self, addressed: dict):
+        self.addressed = dict(addressed)
+
+
+class DiffAnnotate(EditRequest):
+    """requests.py:70-95."""
+
+    def __init__(self, request: EditRequest, argdiff_fn=lambda v: v, retdiff_fn=lambda v: v):
+        self.request = request
+        self.argdiff_fn = argdiff_fn
+        self.retdiff_fn = retdiff_fn
+
+    def edit(self, key, tr, argdiffs):
+        new_tr, w, retdiff, bwd = self.request.edit(key, tr, self.argdiff_fn(argdiffs))
+        return new_tr, w, self.retdiff_fn(retdiff), bwd
+
+
+def _zero_weight(tr):
+    import torch
+
+    s = tr.get_score()
+    return torch.zeros_like(s)
+
+
+# -------------------------------------------------------------------- Trace
+
+
+class Trace:
+    """generative_function.py:72-230."""
+
+    def get_args(self) -> tuple:
+        raise NotImplementedError
+
+    def get_retval(self):
+        raise NotImplementedError
+
+    def get_score(self):
+        raise NotImplementedError
+
+    def get_choices(self) -> ChoiceMap:
+        raise NotImplementedError
+
+    def get_sample(self) -> ChoiceMap:
+        return self.get_choices()
+
+    def get_gen_fn(self) -> "GenerativeFunction":
+        raise NotImplementedError
+
+    def edit(self, key, request: EditRequest, argdiffs=None):
+        if argdiffs is None:
+            argdiffs = Diff.no_change(self.get_args())
+        return request.edit(key, self, argdiffs)
+
+    def update(self, key, constraint: ChoiceMap, argdiffs=None):
+        if argdiffs is None:
+            argdiffs = Diff.no_change(self.get_args())
+        return self.get_gen_fn().update(key, self, constraint, argdiffs)
+
+    def project(self, key, selection: Selection):
+        return self.get_gen_fn().project(key, self, selection)
+
+
+# ------------------------------------------------------- GenerativeFunction
+
+
+class GenerativeFunctionClosure:
+    """``gen_fn(*args)``; ``closure @ "addr"`` traces it (generative_function.py:1568-1583)."""
+
+    def __init__(self, gen_fn, args: tuple, kwargs: dict):
+        self.gen_fn = gen_fn
+        self.args = args
+        self.kwargs = kwargs
+
+    def _packed_args(self):
+        return (self.args, self.kwargs) if self.kwargs else self.args
+
+    def __matmul__(self, addr):
+        from .capture import trace_site
+
+        return trace_site(addr, self.gen_fn, self._packed_args())
+
+    # direct GFI use: genjax.normal(0., 1.).simulate(key, ())
+    def simulate(self, key, args=()):
+        return self.gen_fn.simulate(key, self._full(args))
+
+    def importance(self, key, constraint, args=()):
+        return self.gen_fn.importance(key, constraint, self._full(args))
+
+    def assess(self, sample, args=()):
+        return self.gen_fn.assess(sample, self._full(args))
+
+    def propose(self, key, args=()):
+        return self.gen_fn.propose(key, self._full(args))
+
+    def _full(self, args):
+        full = self.args + tuple(args)
+        return (full, self.kwargs) if self.kwargs else full
+
+
+class GenerativeFunction:
+    """Abstract GFI (generative_function.py:238-699)."""
+
+    def __call__(self, *args, **kwargs) -> GenerativeFunctionClosure:
+        return GenerativeFunctionClosure(self, args, kwargs)
+
+    # -- abstract
+    def simulate(self, key, args: tuple) -> Trace:
+        raise NotImplementedError
+
+    def assess(self, sample: ChoiceMap, args: tuple):
+        raise NotImplementedError
+
+    def generate(self, key, constraint: ChoiceMap, args: tuple):
+        raise NotImplementedError
+
+    def project(self, key, trace: Trace, selection: Selection):
+        raise NotImplementedError
+
+    def edit(self, key, trace: Trace, request: EditRequest, argdiffs):
+        raise NotImplementedError
+
+    # -- derived (generative_function.py:611-689)
+    def importance(self, key, constraint: ChoiceMap, args: tuple):
+        return self.generate(key, constraint, args)
+
+    def update(self, key, trace: Trace, constraint: ChoiceMap, argdiffs=None):
+        if argdiffs is None:
+            argdiffs = Diff.no_change(trace.get_args())
+        new_tr, w, retdiff, bwd = self.edit(key, trace, Update(constraint), argdiffs)
+        assert isinstance(bwd, Update)
+        return new_tr, w, retdiff, bwd.constraint
+
+    def propose(self, key, args: tuple):
+        tr = self.simulate(key, args)
+        return tr.get_choices(), tr.get_score(), tr.get_retval()
+
+    def partial_apply(self, *bound):
+        from .static import gen
+
+        outer = self
+
+        def inner(*rest):
+            return outer(*bound, *rest) @ "_partial"
+
+        raise NotImplementedError("partial_apply is not on the fused hot path yet")
+
+    def get_zero_trace(self, *args):
+        raise NotImplementedError("zero traces belong to the jaxpr staging machinery (out of scope)")

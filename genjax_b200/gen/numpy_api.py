@@ -1,0 +1,80 @@
+"""``jnp``-style math for ``@gen`` bodies: works on traced values (``Expr``),
+Python numbers and torch tensors.  (The reference's bodies use ``jax.numpy``;
+import this module as ``jnp`` to port a model unchanged.)"""
+
+from __future__ import annotations
+
+import math as _math
+
+import torch as _torch
+
+from . import expr as _E
+from .expr import Expr as _Expr
+
+
+def _un(op, tfn, mfn):
+    def f(x):
+        if isinstance(x, _Expr):
+            return _E.unary(op, x)
+        if isinstance(x, _torch.Tensor):
+            return tfn(x)
+        return mfn(x)
+
+    f.__name__ = op
+    return f
+
+
+exp = _un("exp", _torch.exp, _math.exp)
+log = _un("log", _torch.log, _math.log)
+sqrt = _un("sqrt", _torch.sqrt, _math.sqrt)
+abs = _un("abs", _torch.abs, _math.fabs)  # noqa: A001
+tanh = _un("tanh", _torch.tanh, _math.tanh)
+log1p = _un("log1p", _torch.log1p, _math.log1p)
+expm1 = _un("expm1", _torch.expm1, _math.expm1)
+floor = _un("floor", _torch.floor, _math.floor)
+sin = _un("sin", _torch.sin, _math.sin)
+cos = _un("cos", _torch.cos, _math.cos)
+square = _un("square", _torch.square, lambda x: x * x)
+sigmoid = _un("sigmoid", _torch.sigmoid, lambda x: 1.0 / (1.0 + _math.exp(-x)))
+softplus = _un("softplus", _torch.nn.functional.softplus, lambda x: _math.log1p(_math.exp(x)))
+lgamma = _un("lgamma", _torch.lgamma, _math.lgamma)
+
+
+def _bin(op, tfn):
+    def f(a, b):
+        if isinstance(a, _Expr) or isinstance(b, _Expr):
+            return _E.binary(op, a, b)
+        return tfn(_torch.as_tensor(a), _torch.as_tensor(b))
+
+    f.__name__ = op
+    return f
+
+
+minimum = _bin("min", _torch.minimum)
+maximum = _bin("max", _torch.maximum)
+power = _bin("pow", _torch.pow)
+
+
+def where(c, a, b):
+    if any(isinstance(x, _Expr) for x in (c, a, b)):
+        return _E.where(c, a, b)
+    return _torch.where(_torch.as_tensor(c), _torch.as_tensor(a), _torch.as_tensor(b))
+
+
+def sum(x, axis=None):  # noqa: A001
+    if isinstance(x, _Expr):
+        return _E.vsum(x)
+    return _torch.sum(_torch.as_tensor(x)) if axis is None else _torch.sum(_torch.as_tensor(x), dim=axis)
+
+
+def array(x, dtype=None):
+    if isinstance(x, _Expr):
+        return x
+    return _torch.as_tensor(x, dtype=dtype)
+
+
+asarray = array
+float32 = _torch.float32
+int32 = _torch.int32
+pi = _math.pi
+inf = _math.inf

@@ -1,0 +1,626 @@
+"""``@gen``: the static modeling language on fused CUDA kernels.
+
+API mirror of src/genjax/_src/generative_functions/static.py
+(``StaticGenerativeFunction:726``, ``gen:1044``, ``StaticTrace:81``,
+``simulate:787``, ``generate:795-810``, ``assess:983-989``, ``edit:965-981``,
+``project``).  Where the reference re-interprets a jaxpr with a handler per GFI
+method under ``jax.vmap``, this class captures the body once per argument
+signature (gen/capture.py), compiles ONE fused kernel (gen/codegen.py ->
+nvcc -> genjax_b200/_lib/model_<digest>.so) and drives it through the C-ABI
+with per-site flags.  Batching: pass a ``KeyBatch`` (``split(key, n)``) as the
+key, or use ``genjax_b200.vmap`` with ``in_axes`` exactly like ``jax.vmap``.
+
+There is no CPU path: calling any GFI method without a CUDA device raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import json
+from typing import Any, Callable
+
+import numpy as np
+import torch
+
+from ..core.choice_map import ChoiceMap, Selection
+from ..core.key import KeyBatch, PRNGKey, lanes_of
+from ..runtime import build, cabi
+from . import capture as cap
+from . import codegen
+from .capture import AddressReuse, ArgSpec, MissingAddress, ModelIR
+from .expr import Expr, F32, I32
+from .gfi import (
+    Diff,
+    DiffAnnotate,
+    EditRequest,
+    EmptyRequest,
+    GenerativeFunction,
+    NotSupportedEditRequest,
+    Regenerate,
+    StaticRequest,
+    Trace,
+    Update,
+)
+
+__all__ = ["gen", "StaticGenerativeFunction", "StaticTrace", "vmap", "AddressReuse", "MissingAddress"]
+
+
+# --------------------------------------------------------------- batch specs
+
+
+class Batched:
+    """Marks a value that carries a leading particle axis (``in_axes=0``)."""
+
+    __slots__ = ("value",)
+
+    def __init__(self, value):
+        self.value = value
+
+
+def _is_scalar_number(v) -> bool:
+    return isinstance(v, (bool, int, float, np.integer, np.floating))
+
+
+def _mark(tree, axes):
+    """Wrap leaves with ``Batched`` where the in_axes tree says 0."""
+    if isinstance(tree, ChoiceMap):
+        return tree.map_leaves(lambda v: Batched(v)) if axes == 0 else tree
+    if isinstance(axes, (tuple, list)) and isinstance(tree, (tuple, list)):
+        if len(axes) != len(tree):
+            raise ValueError("in_axes structure does not match the argument structure")
+        return type(tree)(_mark(t, a) for t, a in zip(tree, axes))
+    if isinstance(tree, (tuple, list)):
+        return type(tree)(_mark(t, axes) for t in tree)
+    if isinstance(tree, dict):
+        return {k: _mark(v, axes[k] if isinstance(axes, dict) else axes) for k, v in tree.items()}
+    if axes is None or tree is None:
+        return tree
+    if axes == 0:
+        if isinstance(tree, (KeyBatch, PRNGKey, Trace)):
+            return tree
+        return Batched(tree)
+    raise NotImplementedError("only in_axes of 0 / None are supported (particles live on the leading axis)")
+
+
+def vmap(fn: Callable, in_axes=0):
+    """``jax.vmap`` for GFI calls: ``vmap(model.importance, in_axes=(0, None, (0,)))(keys, chm, (x_prev,))``.
+
+    The batch is not unrolled: the call runs ONE fused kernel over all lanes
+    of the ``KeyBatch`` / all rows of the ``in_axes=0`` arguments."""
+
+    def wrapped(*args):
+        axes = in_axes if isinstance(in_axes, (tuple, list)) else (in_axes,) * len(args)
+        if len(axes) != len(args):
+            raise ValueError("vmap in_axes must match the number of positional arguments")
+        return fn(*[_mark(a, ax) for a, ax in zip(args, axes)])
+
+    return wrapped
+
+
+# ----------------------------------------------------------------- compiled
+
+
+class CompiledModel:
+    def __init__(self, ir: ModelIR, lib, path):
+        self.ir = ir
+        self.lib = lib
+        self.path = path
+        self.info = json.loads(lib.gjb_model_info().decode())
+
+
+_COMPILED: dict[str, CompiledModel] = {}
+
+
+def compile_ir(ir: ModelIR) -> CompiledModel:
+    ir.digest = cap.ir_fingerprint(ir)
+    source = codegen.generate(ir)
+    key = build.model_digest(source)
+    cm = _COMPILED.get(key)
+    if cm is None:
+        path = build.build_model(source)
+        cm = CompiledModel(ir, cabi.load_model_library(path), path)
+        _COMPILED[key] = cm
+    return cm
+
+
+def _dev_tensor(v, device, want_int=None) -> torch.Tensor:
+    """Value -> contiguous float32 / int32 CUDA tensor."""
+    if isinstance(v, torch.Tensor):
+        t = v
+    else:
+        t = torch.as_tensor(np.asarray(v))
+    if t.dtype in (torch.float32,):
+        pass
+    elif t.dtype in (torch.float64, torch.float16, torch.bfloat16):
+        t = t.to(torch.float32)
+    elif t.dtype in (torch.int32,):
+        pass
+    elif t.dtype in (torch.int64, torch.int16, torch.int8, torch.uint8, torch.bool):
+        t = t.to(torch.int32)
+    else:
+        raise TypeError(f"unsupported dtype {t.dtype}")
+    if want_int is True and t.dtype != torch.int32:
+        t = t.to(torch.int32)
+    if want_int is False and t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    if t.device != device:
+        t = t.to(device)
+    return t.contiguous()
+
+
+def _dtype_of(t: torch.Tensor) -> str:
+    return F32 if t.dtype == torch.float32 else I32
+
+
+class _BoundArgs:
+    """Model args classified into the capture signature + launch payload."""
+
+    def __init__(self, args, device):
+        leaves, self.tree = cap.flatten(args)
+        self.specs: list[ArgSpec] = []
+        self.payload: list = []  # python scalar | tensor
+        self.n_batched = None
+        for leaf in leaves:
+            batched = isinstance(leaf, Batched)
+            v = leaf.value if batched else leaf
+            if isinstance(v, Diff):
+                v = v.primal
+            if _is_scalar_number(v) and not batched:
+                dt = I32 if isinstance(v, (bool, int, np.integer)) else F32
+                self.specs.append(ArgSpec("scalar", dt, ()))
+                self.payload.append(float(v))
+                continue
+            t = _dev_tensor(v, device)
+            if batched:
+                if t.ndim == 0:
+                    raise ValueError("in_axes=0 argument has no leading axis")
+                n = t.shape[0]
+                if self.n_batched is not None and self.n_batched != n:
+                    raise ValueError("batched arguments disagree on the particle-axis size")
+                self.n_batched = n
+                if t.ndim > 2:
+                    raise NotImplementedError("per-particle arguments must be [n] or [n, d]")
+                self.specs.append(ArgSpec("particle", _dtype_of(t), tuple(t.shape[1:])))
+            else:
+                if t.ndim > 2:
+                    raise NotImplementedError("shared arguments must have at most 2 axes")
+                self.specs.append(ArgSpec("shared", _dtype_of(t), tuple(t.shape)))
+            self.payload.append(t)
+
+    def signature(self):
+        return (repr(self.tree), tuple(s.key() for s in self.specs))
+
+
+# -------------------------------------------------------------------- trace
+
+
+class StaticTrace(Trace):
+    """Trace of a static model over ``n`` particles (struct-of-arrays: every
+    leaf has a leading [n] axis, as under ``jax.vmap`` in the reference).
+    ``batched=False`` traces expose 0-d / event-shaped views."""
+
+    def __init__(self, gen_fn, cm: CompiledModel, bound: _BoundArgs, args, n, batched, values, score, ret_leaves,
+                 bcast):
+        self.gen_fn = gen_fn
+        self.cm = cm
+        self.bound = bound
+        self.args = args
+        self.n = n
+        self.batched = batched
+        self.values = values  # site index -> tensor [n(, d)] or broadcast value tensor
+        self.bcast = bcast  # site index -> bool (value shared by all particles)
+        self.score = score  # [n]
+        self.ret_leaves = ret_leaves
+
+    def _view(self, t, is_bcast=False):
+        if t is None or not isinstance(t, torch.Tensor):
+            return t
+        if is_bcast:
+            return t
+        return t if self.batched else t[0]
+
+    def get_gen_fn(self):
+        return self.gen_fn
+
+    def get_args(self):
+        return _unmark(self.args)
+
+    def get_score(self):
+        return self._view(self.score)
+
+    def get_retval(self):
+        leaves = [self._view(r) for r in self.ret_leaves]
+        return cap.unflatten(self.cm.ir.ret_tree, leaves)
+
+    def _site_value(self, s):
+        v = self.values[s.index]
+        v = self._view(v, self.bcast[s.index])
+        if getattr(s.dist, "bool_valued", False) and isinstance(v, torch.Tensor):
+            v = v.to(torch.bool)
+        return v
+
+    def get_choices(self) -> ChoiceMap:
+        chm = ChoiceMap.empty()
+        for s in self.cm.ir.sites:
+            chm = chm | ChoiceMap.entry(self._site_value(s), *s.addr)
+        return chm
+
+    def get_subtrace(self, *addr):
+        raise NotImplementedError("per-site subtraces are fused away; use get_choices()(addr) / site_scores()")
+
+    def site_scores(self) -> dict:
+        """Per-site log-densities (recomputed by one assess-mode launch per site set)."""
+        return self.gen_fn._site_scores(self)
+
+    def take(self, idx) -> "StaticTrace":
+        """``tree_map(lambda v: v[idx])`` over the particle axis (smc.py:90-91)."""
+        if not self.batched:
+            raise ValueError("take() needs a batched trace")
+        if isinstance(idx, int):
+            sel = torch.tensor([idx], device=self.score.device)
+            out_batched = False
+        else:
+            sel = idx.to(self.score.device).long()
+            out_batched = True
+
+        def g(t, b):
+            return t if b or not isinstance(t, torch.Tensor) else t.index_select(0, sel)
+
+        values = {k: g(v, self.bcast[k]) for k, v in self.values.items()}
+        rets = [g(r, False) for r in self.ret_leaves]
+        args = _take_args(self.args, sel)
+        return StaticTrace(self.gen_fn, self.cm, None, args, int(sel.numel()), out_batched, values,
+                           self.score.index_select(0, sel), rets, dict(self.bcast))
+
+
+def _unmark(tree):
+    if isinstance(tree, Batched):
+        return tree.value
+    if isinstance(tree, tuple):
+        return tuple(_unmark(t) for t in tree)
+    if isinstance(tree, list):
+        return [_unmark(t) for t in tree]
+    if isinstance(tree, dict):
+        return {k: _unmark(v) for k, v in tree.items()}
+    return tree
+
+
+def _take_args(tree, sel):
+    if isinstance(tree, Batched):
+        return Batched(tree.value.index_select(0, sel.to(tree.value.device)))
+    if isinstance(tree, tuple):
+        return tuple(_take_args(t, sel) for t in tree)
+    if isinstance(tree, list):
+        return [_take_args(t, sel) for t in tree]
+    if isinstance(tree, dict):
+        return {k: _take_args(v, sel) for k, v in tree.items()}
+    return tree
+
+
+# ----------------------------------------------------- the generative function
+
+
+class StaticGenerativeFunction(GenerativeFunction):
+    def __init__(self, source: Callable):
+        self.source = source
+        self.__name__ = getattr(source, "__name__", "model")
+        self.__doc__ = getattr(source, "__doc__", None)
+        self._cache: dict = {}
+
+    def __repr__(self):
+        return f"StaticGenerativeFunction({self.__name__})"
+
+    def __get__(self, instance, owner):
+        # @gen on methods (static.py:757-763): bind `self` as the first argument
+        if instance is None:
+            return self
+        bound = StaticGenerativeFunction(lambda *a: self.source(instance, *a))
+        bound.__name__ = self.__name__
+        return bound
+
+    # -- capture ---------------------------------------------------------
+    def capture_inline(self, args):
+        """Nested call inside another @gen body: inline the sites."""
+        if isinstance(args, tuple) and len(args) == 2 and isinstance(args[1], dict) and isinstance(args[0], tuple):
+            return self.source(*args[0], **args[1])
+        return self.source(*args)
+
+    def compiled_for(self, bound: _BoundArgs) -> CompiledModel:
+        sig = bound.signature()
+        cm = self._cache.get(sig)
+        if cm is None:
+            ir = cap.capture(self.source, self.__name__, bound.specs, bound.tree)
+            cm = compile_ir(ir)
+            self._cache[sig] = cm
+        return cm
+
+    def prebuild(self, specs: list, tree=None) -> CompiledModel:
+        """Capture + compile for an explicit argument signature (no GPU needed):
+        ``specs`` is a list of ``ArgSpec``; used by ``__graft_entry__.build()``."""
+        if tree is None:
+            tree = ("tuple", [("leaf", i) for i in range(len(specs))])
+        sig = (repr(tree), tuple(s.key() for s in specs))
+        cm = self._cache.get(sig)
+        if cm is None:
+            ir = cap.capture(self.source, self.__name__, list(specs), tree)
+            cm = compile_ir(ir)
+            self._cache[sig] = cm
+        return cm
+
+    # -- engine ------------------------------------------------------------
+    def _run(self, key, args, constraints: ChoiceMap | None, *, sample_addrs=None, prev: StaticTrace | None = None,
+             weight_mode: str = "generate", weight_in=None, score_in=None, n=None, batched=None, want_score=True,
+             gather=None, wmax=None):
+        """One fused launch.  ``weight_mode``:
+        "generate": weight = sum logpdf over constrained sites;
+        "delta":    weight = new score - prev score (update / regenerate);
+        "none":     no weight."""
+        device = cabi.require_cuda()
+        args = args if isinstance(args, tuple) else tuple(args)
+        bound = _BoundArgs(args, device)
+        cm = self.compiled_for(bound)
+        ir = cm.ir
+        if key is not None:
+            words, lane0, n_key = lanes_of(key)
+            key_batched = isinstance(key, KeyBatch)
+        else:
+            words, lane0, n_key, key_batched = (0, 0), 0, None, False
+
+        constraints = constraints if constraints is not None else ChoiceMap.empty()
+        # resolve the batch size
+        sizes = [s for s in (n_key if key_batched else None, bound.n_batched, n, prev.n if prev is not None and prev.batched else None) if s is not None]
+        cvals = {}
+        for s in ir.sites:
+            sub = constraints.get_submap(*s.addr)
+            if sub.has_value():
+                v = sub.get_value()
+                if isinstance(v, Batched):
+                    t = _dev_tensor(v.value, device, want_int=(s.value.dtype == I32))
+                    sizes.append(t.shape[0])
+                    cvals[s.index] = (t, False)
+                else:
+                    cvals[s.index] = (v, True)
+        if sizes:
+            n_run = sizes[0]
+            if any(x != n_run for x in sizes):
+                raise ValueError(f"inconsistent particle-axis sizes {sizes}")
+            is_batched = True
+        else:
+            n_run, is_batched = 1, False
+        if batched is not None:
+            is_batched = batched
+
+        A = cabi.ModelArgs()
+        A.n = n_run
+        A.idx_offset = lane0
+        A.key0, A.key1 = words
+        keep = []
+        for i, (spec, pl) in enumerate(zip(bound.specs, bound.payload)):
+            if spec.kind == "scalar":
+                A.scalars[i] = pl
+            else:
+                if spec.kind == "particle" and pl.shape[0] != n_run and gather is None:
+                    raise ValueError("batched argument size does not match the batch")
+                A.args[i] = pl.data_ptr()
+                keep.append(pl)
+        if gather is not None:
+            A.gather = cabi.ptr(gather)
+
+        values, bcast = {}, {}
+        for s in ir.sites:
+            j = s.index
+            ev = tuple(s.value.shape)
+            tdt = torch.int32 if s.value.dtype == I32 else torch.float32
+            flags = 0
+            if j in cvals:
+                v, is_b = cvals[j]
+                if is_b:
+                    t = _dev_tensor(v, device, want_int=(s.value.dtype == I32))
+                    if tuple(t.shape) == (n_run,) + ev and is_batched and n_run > 1 and not isinstance(v, (int, float, bool)):
+                        is_b = False  # a full-size tensor constrains per particle
+                    elif tuple(t.shape) != ev:
+                        raise ValueError(f"constraint at {s.addr} has shape {tuple(t.shape)}, expected {ev}")
+                else:
+                    t = v
+                    if tuple(t.shape) != (n_run,) + ev:
+                        raise ValueError(f"batched constraint at {s.addr} has shape {tuple(t.shape)}")
+                A.site_in[j] = t.data_ptr()
+                flags |= cabi.SITE_BCAST if is_b else 0
+                if weight_mode in ("generate", "delta"):
+                    flags |= cabi.SITE_WEIGHT
+                values[j], bcast[j] = t, is_b
+                keep.append(t)
+            elif prev is not None and not (sample_addrs is not None and s.addr in sample_addrs):
+                t = prev.values[j]
+                A.site_in[j] = t.data_ptr()
+                flags |= cabi.SITE_BCAST if prev.bcast[j] else 0
+                if weight_mode == "delta":
+                    flags |= cabi.SITE_WEIGHT
+                values[j], bcast[j] = t, prev.bcast[j]
+            else:
+                if key is None:
+                    raise MissingAddress(s.addr[0] if len(s.addr) == 1 else s.addr)
+                flags |= cabi.SITE_SAMPLE
+                if weight_mode == "delta":
+                    flags |= cabi.SITE_WEIGHT
+                out = torch.empty((n_run,) + ev, dtype=tdt, device=device)
+                A.site_out[j] = out.data_ptr()
+                values[j], bcast[j] = out, False
+            A.site_flags[j] = flags
+
+        score = torch.empty(n_run, dtype=torch.float32, device=device) if want_score else None
+        if score is not None:
+            A.score_out = score.data_ptr()
+        weight = None
+        if weight_mode != "none":
+            weight = torch.empty(n_run, dtype=torch.float32, device=device)
+            A.weight_out = weight.data_ptr()
+        if weight_mode == "delta":
+            assert prev is not None
+            A.score_in = prev.score.data_ptr()
+        if score_in is not None:
+            A.score_in = cabi.ptr(score_in)
+        if weight_in is not None:
+            A.weight_in = cabi.ptr(weight_in)
+        if wmax is not None:
+            A.wmax = cabi.ptr(wmax)
+
+        ret_leaves = []
+        for k, r in enumerate(ir.ret_leaves):
+            if isinstance(r, Expr) and r.op == "site" and not bcast[r.attr]:
+                ret_leaves.append(values[r.attr])
+            elif isinstance(r, Expr):
+                tdt = torch.int32 if r.dtype == I32 else torch.float32
+                out = torch.empty((n_run,) + tuple(r.shape), dtype=tdt, device=device)
+                A.ret_out[k] = out.data_ptr()
+                ret_leaves.append(out)
+            else:
+                ret_leaves.append(r)
+
+        cabi.check(cm.lib.gjb_model_launch(C.byref(A), cabi.stream_ptr(device)), f"gjb_model_launch({self.__name__})")
+        tr = StaticTrace(self, cm, bound, args, n_run, is_batched, values, score, ret_leaves, bcast)
+        return tr, weight
+
+    def _w(self, tr: StaticTrace, w):
+        return w if tr.batched else w[0]
+
+    # -- GFI -------------------------------------------------------------
+    def simulate(self, key, args: tuple) -> StaticTrace:
+        tr, _ = self._run(key, args, None, weight_mode="none")
+        return tr
+
+    def generate(self, key, constraint: ChoiceMap, args: tuple):
+        tr, w = self._run(key, args, constraint, weight_mode="generate")
+        return tr, self._w(tr, w)
+
+    def assess(self, sample: ChoiceMap, args: tuple):
+        tr, _ = self._run(None, args, sample, weight_mode="none")
+        return tr.get_score(), tr.get_retval()
+
+    def project(self, key, trace: StaticTrace, selection: Selection):
+        sel_chm = trace.get_choices().filter(selection)
+        if sel_chm.static_is_empty():
+            return torch.zeros_like(trace.get_score())
+        scores = self._site_scores(trace)
+        tot = torch.zeros_like(trace.score)
+        for s in trace.cm.ir.sites:
+            if selection(s.addr).check():
+                tot = tot + scores[s.addr]
+        return tot if trace.batched else tot[0]
+
+    def _site_scores(self, trace: StaticTrace) -> dict:
+        """addr -> [n] logpdf: one generate launch per site with only that site weighted."""
+        out = {}
+        full = _rebatch(trace)
+        for s in trace.cm.ir.sites:
+            only = ChoiceMap.entry(full.get_submap(*s.addr), *s.addr)
+            rest = trace  # other sites read from the previous trace without weight
+            _, w = self._run(None, trace.args, only, prev=rest, weight_mode="generate", n=trace.n,
+                             batched=trace.batched, want_score=False)
+            out[s.addr] = w
+        return out
+
+    def edit(self, key, trace: StaticTrace, request: EditRequest, argdiffs):
+        new_args = Diff.tree_primal(argdiffs) if argdiffs is not None and argdiffs != () else trace.args
+        if new_args == () and trace.args != ():
+            new_args = trace.args
+        new_args = _carry_batch_marks(new_args, trace.args)
+        if isinstance(request, Update):
+            tr, w = self._run(key, new_args, _rebatch_constraint(request.constraint, trace), prev=trace,
+                              weight_mode="delta", n=trace.n, batched=trace.batched)
+            discard = ChoiceMap.empty()
+            for s in trace.cm.ir.sites:
+                if request.constraint.get_submap(*s.addr).has_value():
+                    discard = discard | ChoiceMap.entry(trace._site_value(s), *s.addr)
+            retdiff = Diff.unknown_change(tr.get_retval())
+            return tr, self._w(tr, w), retdiff, Update(discard)
+        if isinstance(request, Regenerate):
+            sel = {s.addr for s in trace.cm.ir.sites if request.selection(s.addr).check()}
+            tr, w = self._run(key, new_args, None, prev=trace, sample_addrs=sel, weight_mode="delta", n=trace.n,
+                              batched=trace.batched)
+            discard = ChoiceMap.empty()
+            for s in trace.cm.ir.sites:
+                if s.addr in sel:
+                    discard = discard | ChoiceMap.entry(trace._site_value(s), *s.addr)
+            return tr, self._w(tr, w), Diff.unknown_change(tr.get_retval()), Update(discard)
+        if isinstance(request, EmptyRequest):
+            return request.edit(key, trace, argdiffs)
+        if isinstance(request, StaticRequest):
+            return _edit_static_request(self, key, trace, request, argdiffs)
+        if isinstance(request, DiffAnnotate):
+            return request.edit(key, trace, argdiffs)
+        if hasattr(request, "edit") and type(request).edit is not EditRequest.edit:
+            return request.edit(key, trace, argdiffs)
+        raise NotSupportedEditRequest(request)
+
+
+def _carry_batch_marks(new_args, old_args):
+    """Primal args from argdiffs lose their ``Batched`` marks; restore them by position."""
+    if isinstance(old_args, Batched) and not isinstance(new_args, Batched):
+        return Batched(new_args)
+    if isinstance(old_args, tuple) and isinstance(new_args, tuple) and len(old_args) == len(new_args):
+        return tuple(_carry_batch_marks(n, o) for n, o in zip(new_args, old_args))
+    return new_args
+
+
+def _rebatch(trace: StaticTrace) -> ChoiceMap:
+    """Choice map of a trace with batched leaves marked for re-launch."""
+    chm = ChoiceMap.empty()
+    for s in trace.cm.ir.sites:
+        v = trace.values[s.index]
+        chm = chm | ChoiceMap.entry(v if trace.bcast[s.index] else Batched(v), *s.addr)
+    return chm
+
+
+def _rebatch_constraint(chm: ChoiceMap, trace: StaticTrace) -> ChoiceMap:
+    """Leaves of an update constraint that already carry the particle axis are batched."""
+    if not trace.batched:
+        return chm
+
+    def mark(v):
+        if isinstance(v, Batched):
+            return v
+        if isinstance(v, torch.Tensor) and v.ndim >= 1 and v.shape[0] == trace.n:
+            return Batched(v)
+        return v
+
+    return chm.map_leaves(mark)
+
+
+def _edit_static_request(gf, key, trace, request: StaticRequest, argdiffs):
+    """StaticRequest (static.py:512-566, 867-904): per-address sub-requests.
+    Update / Regenerate sub-requests fuse into ONE launch; other sub-requests
+    (Rejuvenate, HMC) are delegated to their own batched drivers."""
+    constraint = ChoiceMap.empty()
+    selected = []
+    custom = []
+    for addr, sub in request.addressed.items():
+        from ..core.choice_map import _norm_addr
+
+        a = _norm_addr(addr)
+        if isinstance(sub, Update):
+            constraint = constraint | ChoiceMap.entry(sub.constraint, *a)
+        elif isinstance(sub, Regenerate):
+            selected.append(Selection.all().extend(*a) if sub.selection.check() else sub.selection.extend(*a))
+        elif isinstance(sub, EmptyRequest):
+            pass
+        else:
+            custom.append((a, sub))
+    if custom:
+        if len(custom) > 1 or selected or not constraint.static_is_empty():
+            raise NotSupportedEditRequest(request)
+        a, sub = custom[0]
+        return sub.edit_at(key, trace, a, argdiffs)
+    if selected and not constraint.static_is_empty():
+        raise NotSupportedEditRequest(request)
+    if selected:
+        sel = selected[0]
+        for s in selected[1:]:
+            sel = sel | s
+        return gf.edit(key, trace, Regenerate(sel), argdiffs)
+    return gf.edit(key, trace, Update(constraint), argdiffs)
+
+
+def gen(source: Callable) -> StaticGenerativeFunction:
+    """``@gen`` (static.py:1044-1062)."""
+    return StaticGenerativeFunction(source)

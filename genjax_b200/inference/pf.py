@@ -1,0 +1,249 @@
+"""Bootstrap / guided particle filter: the extend - reweight - resample loop.
+
+The reference ships NO particle-filter class: the loop is a user idiom
+(docs/cookbook/inactive/inference/importance_sampling.ipynb cell 16,
+mapping_tutorial.ipynb cell 37; reweight formula inference/smc.py:383):
+
+    for t:  trs, w = vmap(step.importance, (0, None, 0))(keys_t, C["y"].set(y_t), (x_prev,))
+            log_w += w;  idx ~ categorical(log_w - logsumexp(log_w)) per offspring
+            x_prev = trs.get_retval()[idx]
+
+``ParticleFilter`` is that idiom as three fused launches per step on one
+stream -- (1) the model kernel: ancestor gather + propose + logpdf + running
+max, (2) exact integer weight mass per tile, (3) CDF scan + systematic
+offspring ranges + log-marginal increment -- captured once as a CUDA graph and
+replayed per run with device-resident keys / observations / initial state.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from ..core.choice_map import ChoiceMap
+from ..core.key import PRNGKey, pf_key_table
+from ..gen.capture import ArgSpec
+from ..gen.expr import Expr, I32
+from ..gen.static import StaticGenerativeFunction, _dev_tensor
+from ..runtime import cabi, smc_ops
+
+
+@dataclass
+class PFResult:
+    state: tuple  # final (resampled) per-particle state leaves
+    log_marginal_likelihood: torch.Tensor  # float64 0-d, sum of the increments
+    log_increments: torch.Tensor  # float64 [T]
+    lse_terms: torch.Tensor  # float64 [T, 3] = (M, S, increment)
+    ancestors: torch.Tensor | None  # int32 [T, N] when record=True
+    history: dict | None  # per-step pre-resampling state / log-weights when record=True
+
+
+class ParticleFilter:
+    """``ParticleFilter(step, n_particles)`` with ``step(*state, *shared)`` a
+    static ``@gen`` kernel whose return value is the next state.
+
+    observations: ChoiceMap whose leaves carry a leading time axis [T, ...];
+    every step constrains those addresses to the t-th slice (broadcast over
+    particles).  Every other site is proposed from the model (bootstrap)."""
+
+    def __init__(self, step: StaticGenerativeFunction, n_particles: int, *, n_state: int = 1, resampler: str = "systematic",
+                 idx_offset: int = 0, n_total: int | None = None):
+        if resampler != "systematic":
+            raise NotImplementedError("the fused filter loop uses systematic resampling; see ParticleCollection.resample")
+        self.step = step
+        self.n = int(n_particles)
+        self.n_state = n_state
+        self.idx_offset = int(idx_offset)
+        self.n_total = int(n_total) if n_total is not None else self.n
+        self._plans: dict = {}
+
+    # ------------------------------------------------------------------ plan
+    def _plan(self, state0: tuple, shared: tuple, obs: dict, T: int, record: bool, device):
+        sig = (tuple((tuple(s.shape[1:]), s.dtype) for s in state0),
+               tuple((tuple(s.shape), s.dtype) if isinstance(s, torch.Tensor) else ("scalar", type(s).__name__) for s in shared),
+               tuple((a, tuple(v.shape[1:])) for a, v in obs.items()), T, record)
+        plan = self._plans.get(sig)
+        if plan is None:
+            plan = _Plan(self, state0, shared, obs, T, record, device)
+            self._plans[sig] = plan
+        return plan
+
+    def run(self, key: PRNGKey, state0, observations: ChoiceMap, shared_args: tuple = (), *, record: bool = False,
+            use_graph: bool = True) -> PFResult:
+        device = cabi.require_cuda()
+        state0 = state0 if isinstance(state0, (tuple, list)) else (state0,)
+        state0 = tuple(_dev_tensor(s, device) for s in state0)
+        for s in state0:
+            if s.shape[0] != self.n:
+                raise ValueError("initial state must have n_particles rows")
+        obs = {}
+        T = None
+        for addr, v in observations.leaves():
+            t = _dev_tensor(v, device)
+            T = t.shape[0] if T is None else T
+            if t.shape[0] != T:
+                raise ValueError("observation leaves disagree on the number of steps")
+            obs[addr] = t
+        if T is None:
+            raise ValueError("no observations")
+        shared = tuple(s if isinstance(s, (int, float)) else _dev_tensor(s, device) for s in shared_args)
+        plan = self._plan(state0, shared, obs, T, record, device)
+        return plan.execute(key, state0, shared, obs, use_graph)
+
+
+class _Plan:
+    """Pre-built launch arguments (and CUDA graph) for one (model, N, T) shape."""
+
+    def __init__(self, pf: ParticleFilter, state0, shared, obs, T, record, device):
+        self.pf = pf
+        self.device = device
+        self.T = T
+        self.record = record
+        n = pf.n
+        step = pf.step
+        specs = [ArgSpec("particle", "i32" if s.dtype == torch.int32 else "f32", tuple(s.shape[1:])) for s in state0]
+        for s in shared:
+            if isinstance(s, torch.Tensor):
+                specs.append(ArgSpec("shared", "i32" if s.dtype == torch.int32 else "f32", tuple(s.shape)))
+            else:
+                specs.append(ArgSpec("scalar", "i32" if isinstance(s, int) else "f32", ()))
+        self.cm = step.prebuild(specs)
+        ir = self.cm.ir
+        self.ir = ir
+        # static buffers (graph replays read/write these)
+        self.state_in = tuple(torch.empty_like(s) for s in state0)
+        self.shared = tuple(torch.empty_like(s) if isinstance(s, torch.Tensor) else s for s in shared)
+        self.obs = {a: torch.empty_like(v) for a, v in obs.items()}
+        self.keys = torch.empty((T, 8), dtype=torch.int32, device=device)
+        self.logw = torch.empty(n, dtype=torch.float32, device=device)
+        self.anc = torch.empty((T if record else 2, n), dtype=torch.int32, device=device)
+        self.lse = torch.empty((T, 3), dtype=torch.float64, device=device)
+        self.ws = smc_ops.WeightWorkspace(n, device)
+        self.wmax2 = torch.empty(2, dtype=torch.int32, device=device)
+        # the next state = the model's return leaves (ping-pong buffers)
+        rets = ir.ret_leaves
+        if len(rets) != len(state0):
+            raise ValueError(f"step returns {len(rets)} leaves but the state has {len(state0)}")
+        self.bufs = []
+        for r, s in zip(rets, state0):
+            if not isinstance(r, Expr):
+                raise ValueError("the step's return value must depend on its choices / arguments")
+            want = torch.int32 if r.dtype == I32 else torch.float32
+            if want != s.dtype or tuple(r.shape) != tuple(s.shape[1:]):
+                raise ValueError("the step's return value must have the dtype and shape of the state it replaces")
+            depth = T if record else 2
+            self.bufs.append(torch.empty((depth,) + tuple(s.shape), dtype=s.dtype, device=device))
+        self.logw_hist = torch.empty((T, n), dtype=torch.float32, device=device) if record else None
+        self.final = tuple(torch.empty_like(s) for s in state0)
+        self.obs_sites = {}
+        for addr in obs:
+            self.obs_sites[ir.site_index(addr)] = addr
+        self._build_args()
+        self.graph = None
+
+    def _build_args(self):
+        pf, ir, T, n = self.pf, self.ir, self.T, self.pf.n
+        self.margs = []
+        self.rargs = []
+        for t in range(T):
+            A = cabi.ModelArgs()
+            A.n = n
+            A.idx_offset = pf.idx_offset
+            A.key_dev = self.keys[t].data_ptr()
+            slot = t if self.record else (t & 1)
+            prev_slot = (t - 1) if self.record else ((t - 1) & 1)
+            for i in range(len(self.state_in)):
+                A.args[i] = self.state_in[i].data_ptr() if t == 0 else self.bufs[i][prev_slot].data_ptr()
+            if t > 0:
+                A.gather = self.anc[prev_slot].data_ptr()
+            for k, s in enumerate(self.shared):
+                i = len(self.state_in) + k
+                if isinstance(s, torch.Tensor):
+                    A.args[i] = s.data_ptr()
+                else:
+                    A.scalars[i] = float(s)
+            for site in ir.sites:
+                j = site.index
+                if j in self.obs_sites:
+                    A.site_in[j] = self.obs[self.obs_sites[j]][t].data_ptr()
+                    A.site_flags[j] = cabi.SITE_WEIGHT | cabi.SITE_BCAST
+                else:
+                    A.site_flags[j] = cabi.SITE_SAMPLE
+            # outputs: only what the next step needs
+            for k, r in enumerate(ir.ret_leaves):
+                out = self.bufs[k][slot]
+                if r.op == "site" and not (r.attr in self.obs_sites):
+                    A.site_out[r.attr] = out.data_ptr()
+                else:
+                    A.ret_out[k] = out.data_ptr()
+            lw = self.logw_hist[t] if self.record else self.logw
+            A.weight_out = lw.data_ptr()
+            A.wmax = self.wmax2[t & 1 :].data_ptr()
+            self.margs.append(A)
+            R = self.ws.systematic_args(
+                lw, None, self.anc[slot], n_total=pf.n_total, out_lo=pf.idx_offset, anc_base=pf.idx_offset,
+                key_dev=self.keys[t][2:], lse_out=self.lse[t], wmax=self.wmax2[t & 1 :],
+                wmax_next=self.wmax2[(t + 1) & 1 :],
+            )
+            self.rargs.append((lw, R))
+
+    def _enqueue(self):
+        core = cabi.core()
+        stream = cabi.stream_ptr(self.device)
+        lib = self.cm.lib
+        cabi.check(core.gjb_wmax_reset(self.wmax2.data_ptr(), stream), "gjb_wmax_reset")
+        for t in range(self.T):
+            cabi.check(lib.gjb_model_launch(C.byref(self.margs[t]), stream), "gjb_model_launch")
+            lw, R = self.rargs[t]
+            cabi.check(
+                core.gjb_weight_mass(lw.data_ptr(), lw.numel(), self.wmax2[t & 1 :].data_ptr(), None,
+                                     self.ws.tile_mass.data_ptr(), stream),
+                "gjb_weight_mass",
+            )
+            cabi.check(core.gjb_resample_systematic(C.byref(R), stream), "gjb_resample_systematic")
+        last = (self.T - 1) if self.record else ((self.T - 1) & 1)
+        for k in range(len(self.bufs)):
+            smc_ops.gather_rows(self.bufs[k][last], self.anc[last], self.final[k])
+
+    def launches_per_run(self) -> int:
+        return 1 + 3 * self.T + len(self.bufs)
+
+    def execute(self, key, state0, shared, obs, use_graph):
+        tab = torch.from_numpy(pf_key_table(key, self.T).view(np.int32))
+        self.keys.copy_(tab, non_blocking=True)
+        for dst, src in zip(self.state_in, state0):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        for dst, src in zip(self.shared, shared):
+            if isinstance(dst, torch.Tensor) and dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        for a in self.obs:
+            if self.obs[a].data_ptr() != obs[a].data_ptr():
+                self.obs[a].copy_(obs[a], non_blocking=True)
+        if use_graph:
+            if self.graph is None:
+                # warm-up launch outside capture (module load), then capture once
+                self._enqueue()
+                torch.cuda.current_stream(self.device).synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue()
+                self.graph = g
+            self.graph.replay()
+        else:
+            self._enqueue()
+        inc = self.lse[:, 2]
+        hist = None
+        if self.record:
+            hist = {"state": tuple(b for b in self.bufs), "log_weights": self.logw_hist}
+        return PFResult(
+            state=self.final,
+            log_marginal_likelihood=inc.sum(),
+            log_increments=inc,
+            lse_terms=self.lse,
+            ancestors=self.anc if self.record else None,
+            history=hist,
+        )

@@ -1,0 +1,278 @@
+"""Sequential Monte Carlo: particle collections, importance sampling, target
+changes.
+
+API mirror of src/genjax/_src/inference/smc.py: ``ParticleCollection:77``
+(``get_log_marginal_likelihood_estimate:96-97``, ``sample_particle:102-109``),
+``SMCAlgorithm:117`` (``random_weighted:162-179``, ``estimate_logpdf:181-198``),
+``Importance:234``, ``ImportanceK:283`` (``run_smc:298-315``),
+``ChangeTarget:360`` (``_reweight:378-384``).  The reference vmaps
+``target.importance`` over K split keys; here that is ONE fused kernel launch
+over the lanes of a ``KeyBatch``.
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+
+from ..core.choice_map import ChoiceMap
+from ..core.key import KeyBatch, PRNGKey, split
+from ..gen.static import Batched, StaticTrace, _rebatch
+from ..runtime import smc_ops
+from .sp import Algorithm, SampleDistribution, Target
+
+
+class ParticleCollection:
+    """Weighted particles (smc.py:77-109): a batched trace + log-weights."""
+
+    def __init__(self, particles: StaticTrace, log_weights: torch.Tensor, is_valid=True):
+        self.particles = particles
+        self.log_weights = log_weights
+        self.is_valid = is_valid
+        self._ws = None
+
+    def _workspace(self) -> smc_ops.WeightWorkspace:
+        if self._ws is None:
+            self._ws = smc_ops.WeightWorkspace(self.log_weights.numel(), self.log_weights.device)
+        return self._ws
+
+    def get_particles(self) -> StaticTrace:
+        return self.particles
+
+    def get_particle(self, idx) -> StaticTrace:
+        if isinstance(idx, torch.Tensor) and idx.ndim == 0:
+            idx = idx.reshape(1)
+            tr = self.particles.take(idx)
+            tr.batched = False
+            return tr
+        return self.particles.take(idx)
+
+    def get_log_weights(self) -> torch.Tensor:
+        return self.log_weights
+
+    def __len__(self):
+        return self.log_weights.numel()
+
+    def __getitem__(self, idx):
+        return self.get_particle(idx), self.log_weights[idx]
+
+    def lse_terms(self) -> torch.Tensor:
+        """Device float64 [M, S, log-mean-exp] from the exact integer mass."""
+        return self._workspace().lse_terms(self.log_weights)
+
+    def get_log_marginal_likelihood_estimate(self) -> torch.Tensor:
+        """``logsumexp(lw) - log K`` (smc.py:96-97)."""
+        return self.lse_terms()[2].to(torch.float32)
+
+    def check_valid(self) -> bool:
+        """False when every weight is zero / NaN (host sync)."""
+        return bool(self.lse_terms()[1].item() > 0)
+
+    def effective_sample_size(self) -> torch.Tensor:
+        lw = self.log_weights - self.lse_terms()[0].to(torch.float32)
+        w = torch.exp(lw)
+        return w.sum() ** 2 / (w * w).sum()
+
+    def sample_particle_index(self, key: PRNGKey) -> torch.Tensor:
+        """One categorical draw over the normalised weights (smc.py:105-108)."""
+        ws = self._workspace()
+        ws.lse_terms(self.log_weights)
+        n = self.log_weights.numel()
+        cdf = torch.empty(n, dtype=torch.int64, device=self.log_weights.device)
+        anc = torch.empty(1, dtype=torch.int32, device=self.log_weights.device)
+        ws.multinomial(self.log_weights, key.words, key.index, anc, cdf)
+        return anc
+
+    def sample_particle(self, key: PRNGKey) -> StaticTrace:
+        idx = self.sample_particle_index(key)
+        tr = self.particles.take(idx.long())
+        tr.batched = False
+        return tr
+
+    def resample(self, key: PRNGKey, method: str = "systematic") -> tuple["ParticleCollection", torch.Tensor]:
+        """Resampled collection with uniform weights log-mean-exp(lw) and the ancestors."""
+        ws = self._workspace()
+        terms = ws.lse_terms(self.log_weights)
+        n = self.log_weights.numel()
+        anc = torch.empty(n, dtype=torch.int32, device=self.log_weights.device)
+        if method == "systematic":
+            ws.systematic(self.log_weights, key, anc)
+        elif method == "multinomial":
+            kb = split(key, n)
+            cdf = torch.empty(n, dtype=torch.int64, device=self.log_weights.device)
+            ws.multinomial(self.log_weights, kb.words, kb.offset, anc, cdf)
+        else:
+            raise ValueError(method)
+        tr = self.particles.take(anc.long())
+        lw = terms[2].to(torch.float32).expand(n).contiguous()
+        return ParticleCollection(tr, lw, self.is_valid), anc
+
+
+class SMCAlgorithm(Algorithm):
+    """smc.py:117-230."""
+
+    def get_num_particles(self) -> int:
+        raise NotImplementedError
+
+    def get_final_target(self) -> Target:
+        raise NotImplementedError
+
+    def run_smc(self, key: PRNGKey) -> ParticleCollection:
+        raise NotImplementedError
+
+    def run_csmc(self, key: PRNGKey, retained: ChoiceMap) -> ParticleCollection:
+        raise NotImplementedError
+
+    # GenSP interface (smc.py:145-198)
+    def random_weighted(self, key: PRNGKey, *args):
+        (target,) = args
+        kb = split(key)
+        key, sub_key = kb[0], kb[1]
+        algorithm = ChangeTarget(self, target)
+        particle_collection = algorithm.run_smc(key)
+        log_marginal = particle_collection.get_log_marginal_likelihood_estimate()
+        particle = particle_collection.sample_particle(sub_key)
+        log_density_estimate = particle.get_score() - log_marginal
+        chm = target.filter_to_unconstrained(particle.get_choices())
+        return log_density_estimate, chm
+
+    def estimate_logpdf(self, key: PRNGKey, v: ChoiceMap, *args):
+        (target,) = args
+        algorithm = ChangeTarget(self, target)
+        particle_collection = algorithm.run_csmc(key, v)
+        particle = particle_collection.get_particle(-1 % len(particle_collection))
+        log_density_estimate = particle.get_score() - particle_collection.get_log_marginal_likelihood_estimate()
+        return log_density_estimate
+
+    def log_marginal_likelihood_estimate(self, key: PRNGKey, target: Target | None = None):
+        algorithm = ChangeTarget(self, target) if target is not None else self
+        return algorithm.run_smc(key).get_log_marginal_likelihood_estimate()
+
+    def simulate(self, key, args):
+        (target,) = args
+        w, chm = self.random_weighted(key, target)
+        return _SampleTrace(self, args, chm, w)
+
+
+class _SampleTrace:
+    def __init__(self, gen_fn, args, chm, score):
+        self._gf, self._args, self._chm, self._score = gen_fn, args, chm, score
+
+    def get_gen_fn(self):
+        return self._gf
+
+    def get_args(self):
+        return self._args
+
+    def get_choices(self):
+        return self._chm
+
+    get_sample = get_choices
+
+    def get_retval(self):
+        return self._chm
+
+    def get_score(self):
+        return self._score
+
+
+def _as_batch(tr: StaticTrace, w: torch.Tensor):
+    """A scalar-key trace as a 1-particle batch (``jnp.expand_dims(v, 0)``, smc.py:262)."""
+    tr.batched = True
+    return tr, w.reshape(1)
+
+
+class Importance(SMCAlgorithm):
+    """One-particle importance sampling (smc.py:234-279)."""
+
+    def __init__(self, target: Target, q: SampleDistribution | None = None):
+        self.target = target
+        self.q = q
+
+    def get_num_particles(self):
+        return 1
+
+    def get_final_target(self):
+        return self.target
+
+    def run_smc(self, key: PRNGKey):
+        kb = split(key)
+        key, sub_key = kb[0], kb[1]
+        if self.q is not None:
+            log_weight, choice = self.q.random_weighted(sub_key, self.target)
+            tr, target_score = self.target.importance(key, choice)
+            tr, w = _as_batch(tr, target_score - log_weight)
+        else:
+            tr, target_score = self.target.importance(key, ChoiceMap.empty())
+            tr, w = _as_batch(tr, target_score)
+        return ParticleCollection(tr, w, True)
+
+    def run_csmc(self, key: PRNGKey, retained: ChoiceMap):
+        kb = split(key)
+        key, sub_key = kb[0], kb[1]
+        q_score = self.q.estimate_logpdf(sub_key, retained, self.target) if self.q else 0.0
+        tr, target_score = self.target.importance(key, retained)
+        tr, w = _as_batch(tr, target_score - q_score)
+        return ParticleCollection(tr, w, True)
+
+
+class ImportanceK(SMCAlgorithm):
+    """K-particle importance sampling (smc.py:283-351)."""
+
+    def __init__(self, target: Target, q: SampleDistribution | None = None, k_particles: int = 2):
+        self.target = target
+        self.q = q
+        self.k_particles = int(k_particles)
+
+    def get_num_particles(self):
+        return self.k_particles
+
+    def get_final_target(self):
+        return self.target
+
+    def run_smc(self, key: PRNGKey):
+        kb = split(key)
+        key, sub_key = kb[0], kb[1]
+        sub_keys = split(sub_key, self.get_num_particles())
+        if self.q is not None:
+            log_weights, choices = self.q.random_weighted(sub_keys, self.target)
+            trs, target_scores = self.target.importance(sub_keys, choices)
+            lw = target_scores - log_weights
+        else:
+            trs, lw = self.target.importance(sub_keys, ChoiceMap.empty())
+        return ParticleCollection(trs, lw, True)
+
+    def run_csmc(self, key: PRNGKey, retained: ChoiceMap):
+        raise NotImplementedError("conditional SMC is a 'next' row (SURVEY.md 8f-2)")
+
+
+class ChangeTarget(SMCAlgorithm):
+    """Reweight a collection for a new target (smc.py:360-396)."""
+
+    def __init__(self, prev: SMCAlgorithm, target: Target):
+        self.prev = prev
+        self.target = target
+
+    def get_num_particles(self):
+        return self.prev.get_num_particles()
+
+    def get_final_target(self):
+        return self.target
+
+    def run_smc(self, key: PRNGKey) -> ParticleCollection:
+        collection = self.prev.run_smc(key)
+        particles = collection.get_particles()
+        # latents of every particle, batched along the particle axis
+        latents = self.prev.get_final_target().filter_to_unconstrained(_rebatch(particles))
+        sub_keys = split(key, self.get_num_particles())
+        merged = self.target.constraint.merge(latents)
+        # this_weight = new_weight - particle.get_score() + weight   (smc.py:383)
+        new_tr, new_w = self.target.p._run(
+            sub_keys, self.target.args, merged, weight_mode="generate", weight_in=collection.get_log_weights(),
+            score_in=particles.score, n=particles.n, batched=True
+        )
+        return ParticleCollection(new_tr, new_w, True)
+
+    def run_csmc(self, key: PRNGKey, retained: ChoiceMap):
+        raise NotImplementedError("conditional SMC is a 'next' row (SURVEY.md 8f-2)")

@@ -1,0 +1,187 @@
+"""ctypes bindings of the C-ABI in ``include/genjax_b200.h``.
+
+This is the ONLY way the Python host reaches the CUDA kernels; there is no
+CPU or PyTorch-op fallback -- a missing library or a non-CUDA tensor raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+from . import build
+
+GJB_MAX_SITES = 16
+GJB_MAX_ARGS = 16
+GJB_MAX_RETS = 8
+
+SITE_SAMPLE = 1
+SITE_WEIGHT = 2
+SITE_BCAST = 4
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_u64 = C.c_uint64
+_u32 = C.c_uint32
+_i32 = C.c_int32
+
+
+class GjbError(RuntimeError):
+    pass
+
+
+class ModelArgs(C.Structure):
+    """``gjb_model_args`` (include/genjax_b200.h)."""
+
+    _fields_ = [
+        ("n", _i64),
+        ("idx_offset", _u64),
+        ("key0", _u32),
+        ("key1", _u32),
+        ("key_dev", _p),
+        ("gather", _p),
+        ("args", _p * GJB_MAX_ARGS),
+        ("scalars", C.c_float * GJB_MAX_ARGS),
+        ("site_in", _p * GJB_MAX_SITES),
+        ("site_out", _p * GJB_MAX_SITES),
+        ("ret_out", _p * GJB_MAX_RETS),
+        ("site_flags", _u32 * GJB_MAX_SITES),
+        ("score_in", _p),
+        ("weight_in", _p),
+        ("score_out", _p),
+        ("weight_out", _p),
+        ("wmax", _p),
+    ]
+
+
+class ResampleArgs(C.Structure):
+    """``gjb_resample_args`` (include/genjax_b200.h)."""
+
+    _fields_ = [
+        ("logw", _p),
+        ("n", _i64),
+        ("wmax", _p),
+        ("m_global", _p),
+        ("tile_mass", _p),
+        ("c_offset", _p),
+        ("s_total", _p),
+        ("n_total", _i64),
+        ("out_lo", _i64),
+        ("out_n", _i64),
+        ("anc_base", _i64),
+        ("key0", _u32),
+        ("key1", _u32),
+        ("key_index", _u64),
+        ("key_dev", _p),
+        ("ancestors", _p),
+        ("lse_out", _p),
+        ("wmax_next", _p),
+    ]
+
+
+class ChainArgs(C.Structure):
+    """``gjb_chain_args`` (include/genjax_b200.h)."""
+
+    _fields_ = [
+        ("n", _i64),
+        ("idx_offset", _u64),
+        ("key0", _u32),
+        ("key1", _u32),
+        ("args", _p * GJB_MAX_ARGS),
+        ("scalars", C.c_float * GJB_MAX_ARGS),
+        ("site_in", _p * GJB_MAX_SITES),
+        ("site_flags", _u32 * GJB_MAX_SITES),
+        ("state", _p),
+        ("logp", _p),
+        ("accept_count", _p),
+        ("n_steps", _i32),
+        ("step0", _i32),
+        ("step_size", C.c_float),
+        ("n_leapfrog", _i32),
+        ("compat_stale_grad", _i32),
+    ]
+
+
+CORE_PROTOTYPES = {
+    "gjb_abi_version": (C.c_int, []),
+    "gjb_resample_workspace_bytes": (_i64, [_i64]),
+    "gjb_wmax_reset": (C.c_int, [_p, _p]),
+    "gjb_weight_max": (C.c_int, [_p, _i64, _p, _p]),
+    "gjb_weight_mass": (C.c_int, [_p, _i64, _p, _p, _p, _p]),
+    "gjb_lse_finalize": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _p]),
+    "gjb_resample_systematic": (C.c_int, [C.POINTER(ResampleArgs), _p]),
+    "gjb_resample_multinomial": (C.c_int, [_p, _i64, _p, _p, _p, _u32, _u32, _u64, _i64, _p, _p]),
+    "gjb_gather_rows": (C.c_int, [_p, _p, _p, _i64, _i32, _p]),
+    "gjb_philox_fill": (C.c_int, [_u32, _u32, _u64, _u32, _u32, _i64, _p, _p]),
+    "gjb_normal_fill": (C.c_int, [_u32, _u32, _u64, _u32, _i64, _i32, _p, _p]),
+}
+
+MODEL_PROTOTYPES = {
+    "gjb_model_info": (C.c_char_p, []),
+    "gjb_model_launch": (C.c_int, [C.POINTER(ModelArgs), _p]),
+    "gjb_model_mh_chain": (C.c_int, [C.POINTER(ChainArgs), _p]),
+    "gjb_model_hmc_chain": (C.c_int, [C.POINTER(ChainArgs), _p]),
+}
+
+_core = None
+
+
+def _bind(lib, protos):
+    for name, (res, argtypes) in protos.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = argtypes
+    return lib
+
+
+def core_library_path() -> Path:
+    return build.LIB / "libgjb_core.so"
+
+
+def core():
+    """The loaded core library (built on demand); raises if unavailable."""
+    global _core
+    if _core is None:
+        path = build.build_core()
+        _core = _bind(C.CDLL(str(path)), CORE_PROTOTYPES)
+        if _core.gjb_abi_version() != 1:
+            raise GjbError("libgjb_core.so ABI mismatch")
+    return _core
+
+
+def load_model_library(path: Path):
+    return _bind(C.CDLL(str(path)), MODEL_PROTOTYPES)
+
+
+def check(code: int, what: str) -> None:
+    if code == 0:
+        return
+    if code < 0:
+        names = {-1: "GJB_E_ARG", -2: "GJB_E_RANGE", -3: "GJB_E_MODE"}
+        raise GjbError(f"{what}: {names.get(code, code)}")
+    raise GjbError(f"{what}: CUDA error {code}")
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    """Device pointer of a CUDA tensor (None stays null)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise GjbError("genjax_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise GjbError("tensor must be contiguous")
+    return t.data_ptr()
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise GjbError(
+            "genjax_b200 needs a CUDA device: the hot path is hand-written sm_100a CUDA and has no CPU fallback"
+        )
+    return torch.device("cuda", torch.cuda.current_device())

@@ -1,0 +1,212 @@
+/*
+ * genjax_b200 C-ABI -- the drop-in boundary of the particle-parallel hot path.
+ *
+ * The reference (genjax-community/genjax @ 80ef143) is pure Python and has no
+ * FFI; its extension points are Python ABCs.  Each entry point below names the
+ * reference interface whose *batched* (jax.vmap-ed) execution it replaces.
+ * Paths are relative to /root/reference/src/genjax/_src/.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless stated;
+ *     nothing here allocates or frees caller memory;
+ *   - calls only ENQUEUE work on `stream` (a cudaStream_t passed as void*),
+ *     they never synchronise;
+ *   - return value: 0 = ok, >0 = cudaError_t of the launch, <0 = argument
+ *     validation failure (GJB_E_*);
+ *   - particle arrays are row-major [n] or [n, d] float32 / int32;
+ *   - RNG: Philox4x32-10, key = (key0, key1), counter =
+ *     (idx_lo, idx_hi, chunk, site) with idx = idx_offset + local index, so
+ *     results do not depend on how particles are sharded over GPUs.
+ *
+ * Two libraries export these symbols:
+ *   libgjb_core.so          : everything in section 1 (model independent)
+ *   model_<hash>.so         : section 2, one library per captured @gen model
+ */
+#ifndef GENJAX_B200_H
+#define GENJAX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GJB_ABI_VERSION 1
+
+#define GJB_E_ARG (-1)      /* null / misaligned pointer, negative size          */
+#define GJB_E_RANGE (-2)    /* size beyond what the kernel supports              */
+#define GJB_E_MODE (-3)     /* unknown mode / flag                               */
+
+/* ------------------------------------------------------------------ 1. core */
+
+int gjb_abi_version(void);
+
+/* Device-side workspace sizes (bytes) for n particles. */
+int64_t gjb_resample_workspace_bytes(int64_t n);
+
+/*
+ * max_i logw_i  ->  *wmax (ordered-uint encoding, see gjb_wmax_decode).
+ * Replaces the max pass of jax.scipy.special.logsumexp at
+ * inference/smc.py:97,107.  `wmax` must have been reset with gjb_wmax_reset.
+ */
+int gjb_wmax_reset(uint32_t* wmax, void* stream);
+int gjb_weight_max(const float* logw, int64_t n, uint32_t* wmax, void* stream);
+
+/*
+ * Exact integer mass of the weights relative to the max:
+ *   tile_mass[b] = sum_{i in tile b} floor(2^30 * exp(logw_i - M)),  tile = 2048
+ * (uint64; integer addition is associative, so the total is independent of
+ * the reduction tree and of the GPU count).  Second pass of logsumexp,
+ * inference/smc.py:96-97.  `m_global` (device float*) overrides *wmax when
+ * non-null (multi-GPU: the all-reduced max).
+ */
+int gjb_weight_mass(const float* logw, int64_t n, const uint32_t* wmax,
+                    const float* m_global, uint64_t* tile_mass, void* stream);
+
+/*
+ * lse_out[0] = M (fp32 max as double), lse_out[1] = S (total mass as double,
+ * exact below 2^53), lse_out[2] = log-mean-exp = M + log S - 30 log 2 - log n_total.
+ * ParticleCollection.get_log_marginal_likelihood_estimate, inference/smc.py:96-97.
+ */
+int gjb_lse_finalize(const uint64_t* tile_mass, int64_t n, const uint32_t* wmax,
+                     const float* m_global, int64_t n_total, double* lse_out,
+                     void* stream);
+
+/*
+ * Systematic resampling over the exact integer CDF: ancestors[j] = i for
+ * j in [cnt_{i-1}, cnt_i), cnt_i = clamp(ceil(C_i * n_total / S - u0), 0, n_total).
+ * Replaces the user idiom `jax.random.categorical(key, logits)` per offspring
+ * (docs/cookbook/inactive/inference/mapping_tutorial.ipynb cell 37; the
+ * library's single draw is ParticleCollection.sample_particle,
+ * inference/smc.py:102-109).
+ */
+typedef struct gjb_resample_args {
+  const float* logw;          /* [n] local log-weights                            */
+  int64_t n;                  /* local particles                                  */
+  const uint32_t* wmax;       /* encoded max (gjb_weight_max / model kernel)      */
+  const float* m_global;      /* nullable: overrides *wmax (multi-GPU global max) */
+  const uint64_t* tile_mass;  /* from gjb_weight_mass                             */
+  const uint64_t* c_offset;   /* nullable: mass of the shards before this one     */
+  const uint64_t* s_total;    /* nullable: global mass (else local total)         */
+  int64_t n_total;            /* global particle count                            */
+  int64_t out_lo, out_n;      /* write offspring j in [out_lo, out_lo+out_n) to ancestors[j-out_lo] */
+  int64_t anc_base;           /* global id of local particle 0                    */
+  uint32_t key0, key1;        /* resample key words                               */
+  uint64_t key_index;         /* resample key lane: u0 = u01(Philox(idx=key_index, site 0, chunk 0).x) */
+  const uint32_t* key_dev;    /* nullable: {key0, key1, index_lo, index_hi} read on the device instead */
+  int32_t* ancestors;         /* [out_n]                                          */
+  double* lse_out;            /* nullable: {M, S, M + log S - 30 log 2 - log n_total} */
+  uint32_t* wmax_next;        /* nullable: reset to -inf for the next step        */
+} gjb_resample_args;
+
+int gjb_resample_systematic(const gjb_resample_args* a, void* stream);
+
+/*
+ * Multinomial resampling: offspring j draws r_j (64 bits of its Philox lane,
+ * site 0 chunk 1), target = mulhi64(r_j, S), ancestor = upper_bound(C, target).
+ * `cdf` is a caller workspace of n uint64 (filled here).
+ */
+int gjb_resample_multinomial(const float* logw, int64_t n, const uint32_t* wmax,
+                             const uint64_t* tile_mass, uint64_t* cdf,
+                             uint32_t key0, uint32_t key1, uint64_t idx_offset,
+                             int64_t n_out, int32_t* ancestors, void* stream);
+
+/*
+ * dst[j, :] = src[ancestors[j], :]  (row_bytes per row, multiple of 4).
+ * ParticleCollection.get_particle / tree_map(lambda v: v[idx]),
+ * inference/smc.py:90-91.
+ */
+int gjb_gather_rows(const void* src, const int32_t* ancestors, void* dst,
+                    int64_t n_out, int32_t row_bytes, void* stream);
+
+/* Raw Philox words / N(0,1) draws for RNG known-answer tests. */
+int gjb_philox_fill(uint32_t key0, uint32_t key1, uint64_t idx_offset,
+                    uint32_t site, uint32_t chunk, int64_t n, uint32_t* out4,
+                    void* stream);
+int gjb_normal_fill(uint32_t key0, uint32_t key1, uint64_t idx_offset,
+                    uint32_t site, int64_t n, int32_t d, float* out,
+                    void* stream);
+
+/* -------------------------------------------------------- 2. per-model .so */
+
+#define GJB_MAX_SITES 16
+#define GJB_MAX_ARGS 16
+#define GJB_MAX_RETS 8
+
+/* site_flags bits */
+#define GJB_SITE_SAMPLE 1u     /* draw the value (else read site_in)            */
+#define GJB_SITE_WEIGHT 2u     /* add this site's logpdf to the weight          */
+#define GJB_SITE_BCAST 4u      /* site_in holds ONE value shared by all particles */
+
+/*
+ * One fused launch over n particles of a captured static @gen model:
+ * visits every site in program order; a site either samples (Philox lane of
+ * the particle, site counter from 1 as static.py:260-263) or reads its value
+ * from site_in; accumulates score = sum logpdf and weight = sum logpdf over
+ * GJB_SITE_WEIGHT sites.  With the flags set by the host this single entry
+ * point is the batched form of
+ *   simulate  (generative_functions/static.py:254-278, 787-793)
+ *   assess    (static.py:298-321, 983-989)
+ *   generate / importance (static.py:341-380, 795-810;
+ *              core/generative/generative_function.py:629-675)
+ *   edit(Update)     (static.py:407-466; distributions/distribution.py:179-244)
+ *   edit(Regenerate) (static.py:616-673; distribution.py:258-300)
+ * weight_out[i] = (weight_in ? weight_in[i] : 0) + weight - (score_in ? score_in[i] : 0).
+ */
+typedef struct gjb_model_args {
+  int64_t n;                 /* particles in this launch                        */
+  uint64_t idx_offset;       /* global index of local particle 0                */
+  uint32_t key0, key1;       /* batch key words                                 */
+  const uint32_t* key_dev;   /* nullable: {key0, key1} read on the device instead (graph replay) */
+  const int32_t* gather;     /* nullable: per-particle args are read at gather[i] */
+  const void* args[GJB_MAX_ARGS];      /* model args: per-particle arrays or shared blocks */
+  float scalars[GJB_MAX_ARGS];         /* model args passed by value (host scalars)        */
+  const void* site_in[GJB_MAX_SITES];  /* constrained / previous values        */
+  void* site_out[GJB_MAX_SITES];       /* nullable: where to store site values */
+  void* ret_out[GJB_MAX_RETS];         /* nullable: return-value leaves        */
+  uint32_t site_flags[GJB_MAX_SITES];
+  const float* score_in;     /* nullable: previous total score (update/regenerate) */
+  const float* weight_in;    /* nullable: log-weights to accumulate onto        */
+  float* score_out;          /* nullable                                        */
+  float* weight_out;         /* nullable                                        */
+  uint32_t* wmax;            /* nullable: atomic max of weight_out (ordered-uint) */
+} gjb_model_args;
+
+/* JSON description of the captured model (sites, args, layouts); static storage. */
+const char* gjb_model_info(void);
+int gjb_model_launch(const gjb_model_args* a, void* stream);
+
+/*
+ * Batched MCMC drivers generated for the same model (one chain per lane).
+ *   mh  : Rejuvenate-style random-walk proposal on the selected sites +
+ *         accept `log(u) < alpha` (inference/requests/rejuvenate.py:70-94;
+ *         tests/inference/test_requests.py:136-137,190-191)
+ *   hmc : HMC.edit + accept (inference/requests/hmc.py:156-211); compat_stale_grad=1
+ *         reproduces the carried-gradient quirk at hmc.py:186.
+ * state: [n_chains, D] latent values (site order), logp: [n_chains].
+ */
+typedef struct gjb_chain_args {
+  int64_t n;
+  uint64_t idx_offset;
+  uint32_t key0, key1;
+  const void* args[GJB_MAX_ARGS];
+  float scalars[GJB_MAX_ARGS];
+  const void* site_in[GJB_MAX_SITES];  /* observed (unselected) site values, broadcast or per chain */
+  uint32_t site_flags[GJB_MAX_SITES];
+  float* state;              /* in/out [n, D] selected-site values              */
+  float* logp;               /* in/out [n]                                      */
+  int32_t* accept_count;     /* in/out [n] (nullable)                           */
+  int32_t n_steps;           /* transitions per launch                          */
+  int32_t step0;             /* global index of the first transition (RNG)      */
+  float step_size;           /* MH proposal scale / HMC eps                     */
+  int32_t n_leapfrog;        /* HMC L                                           */
+  int32_t compat_stale_grad; /* HMC: reproduce hmc.py:186                       */
+} gjb_chain_args;
+
+int gjb_model_mh_chain(const gjb_chain_args* a, void* stream);
+int gjb_model_hmc_chain(const gjb_chain_args* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENJAX_B200_H */

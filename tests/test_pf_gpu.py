@@ -1,0 +1,163 @@
+"""GPU parity of the fused model kernel and the particle-filter loop against
+the oracle (teacher-forced per step) and the exact Kalman filter."""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dists as od
+from oracle import gfi as ogfi
+from oracle import rng as orng
+from oracle import smc as osmc
+
+pytestmark = pytest.mark.gpu
+
+A_, Q_, C_, R_ = 0.9, 1.0, 1.0, 0.5
+
+
+def _models():
+    import genjax_b200 as gj
+
+    @gj.gen
+    def step(x_prev):
+        x = gj.normal(A_ * x_prev, Q_) @ "x"
+        gj.normal(C_ * x, R_) @ "y"
+        return x
+
+    @gj.gen
+    def step_vec(x_prev, q, r):
+        x = gj.mv_normal_diag(A_ * x_prev, q) @ "x"
+        gj.mv_normal_diag(C_ * x, r) @ "y"
+        return x
+
+    return gj, step, step_vec
+
+
+def o_step(h, x_prev):
+    x = h.normal("x", np.float32(A_) * x_prev, np.float32(Q_))
+    h.normal("y", np.float32(C_) * x, np.float32(R_))
+    return x
+
+
+def o_step_vec(h, x_prev, q, r):
+    x = h.mv_normal_diag("x", np.float32(A_) * x_prev, q)
+    h.mv_normal_diag("y", np.float32(C_) * x, r)
+    return x
+
+
+@pytest.mark.parametrize("n", [1, 5, 4096, 100_001])
+def test_step_importance_matches_oracle(device, n):
+    gj, step, _ = _models()
+    key = gj.key(314159)
+    keys = gj.split(key, n)
+    g = np.random.default_rng(0)
+    x_prev = g.standard_normal(n).astype(np.float32)
+    tr, w = gj.vmap(step.importance, in_axes=(0, None, (0,)))(
+        keys, gj.C["y"].set(0.7), (torch.from_numpy(x_prev).to(device),)
+    )
+    okeys = orng.split(orng.key(314159), n)
+    otr, ow = ogfi.generate(o_step, okeys, {"y": np.float32(0.7)}, (x_prev,))
+    np.testing.assert_allclose(tr.get_choices()["x"].cpu().numpy(), otr.choices["x"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(w.cpu().numpy(), ow, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(tr.get_score().cpu().numpy(), otr.get_score(), rtol=1e-5, atol=1e-5)
+    assert torch.equal(tr.get_retval(), tr.get_choices()["x"])
+
+
+def test_assess_kat(device):
+    """tests/generative_functions/test_static_gen_fn.py:317-318 of the reference."""
+    import genjax_b200 as gj
+
+    @gj.gen
+    def model():
+        y1 = gj.normal(0.0, 1.0) @ "y1"
+        gj.normal(0.0, 1.0) @ "y2"
+        return 0.0
+
+    score, ret = model.assess(gj.C["y1"].set(1.0).at["y2"].set(-1.0), ())
+    assert score.item() == pytest.approx(-2.837877, abs=1e-6)
+    assert ret == 0.0
+
+
+@pytest.mark.parametrize("d", [8, 32])
+def test_step_vec_importance_matches_oracle(device, d):
+    gj, _, step_vec = _models()
+    n = 3001
+    keys = gj.split(gj.key(7), n)
+    g = np.random.default_rng(1)
+    x_prev = g.standard_normal((n, d)).astype(np.float32)
+    q = np.full(d, Q_, dtype=np.float32)
+    r = (0.5 + 0.01 * np.arange(d)).astype(np.float32)
+    y = g.standard_normal(d).astype(np.float32)
+    tr, w = gj.vmap(step_vec.importance, in_axes=(0, None, (0, None, None)))(
+        keys, gj.C["y"].set(torch.from_numpy(y)), (torch.from_numpy(x_prev).to(device), torch.from_numpy(q), torch.from_numpy(r))
+    )
+    otr, ow = ogfi.generate(o_step_vec, orng.split(orng.key(7), n), {"y": y}, (x_prev, q, r))
+    np.testing.assert_allclose(tr.get_choices()["x"].cpu().numpy(), otr.choices["x"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(w.cpu().numpy(), ow, rtol=2e-5, atol=2e-4)
+    np.testing.assert_allclose(tr.get_score().cpu().numpy(), otr.get_score(), rtol=2e-5, atol=2e-4)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_particle_filter_teacher_forced_vs_oracle(device, use_graph):
+    """Per step: CUDA log-weights == oracle log-weights (fp32 tolerance) given the same
+    inputs, and the CUDA ancestors are BIT-EXACT the oracle's resample of the CUDA weights."""
+    gj, step, _ = _models()
+    from genjax_b200.inference.pf import ParticleFilter
+
+    n, T = 6000, 12
+    ys = osmc.simulate_lgssm(0, T, 1, A_, Q_, C_, R_)[:, 0]
+    g = np.random.default_rng(3)
+    x0 = g.standard_normal(n).astype(np.float32)
+    key = gj.key(99)
+    pf = ParticleFilter(step, n)
+    res = pf.run(key, torch.from_numpy(x0), gj.C["y"].set(torch.from_numpy(ys)), record=True, use_graph=use_graph)
+    anc = res.ancestors.cpu().numpy()
+    xs = res.history["state"][0].cpu().numpy()
+    lws = res.history["log_weights"].cpu().numpy()
+    okey = orng.key(99)
+    x_in = x0
+    for t in range(T):
+        k_prop, k_res = osmc.pf_step_keys(okey, t)
+        otr, ow = ogfi.generate(o_step, orng.split(k_prop, n), {"y": np.float32(ys[t])}, (x_in,))
+        np.testing.assert_allclose(xs[t], otr.choices["x"], rtol=1e-5, atol=2e-6, err_msg=f"x step {t}")
+        np.testing.assert_allclose(lws[t], ow, rtol=1e-5, atol=2e-5, err_msg=f"logw step {t}")
+        exp_anc = osmc.resample_systematic(lws[t], k_res)
+        assert np.array_equal(anc[t], exp_anc), f"ancestors step {t}"
+        assert res.log_increments[t].item() == pytest.approx(osmc.log_mean_exp(lws[t]), abs=1e-9)
+        x_in = xs[t][anc[t]]  # teacher forcing: continue from the CUDA state
+    np.testing.assert_array_equal(res.state[0].cpu().numpy(), x_in)
+
+
+def test_particle_filter_matches_kalman(device):
+    gj, step, _ = _models()
+    from genjax_b200.inference.pf import ParticleFilter
+
+    n, T = 1 << 18, 50
+    ys = osmc.simulate_lgssm(0, T, 1, A_, Q_, C_, R_)[:, 0]
+    exact = osmc.kalman_logz(ys, A_, Q_, C_, R_)
+    keys0 = gj.split(gj.key(1), n)
+    x0 = gj.normal.sample(keys0, 0.0, 1.0)
+    ests = []
+    for seed in range(4):
+        pf = ParticleFilter(step, n)
+        res = pf.run(gj.key(seed), x0, gj.C["y"].set(torch.from_numpy(ys)))
+        ests.append(res.log_marginal_likelihood.item())
+    assert np.mean(ests) == pytest.approx(exact, abs=0.05)
+    assert np.std(ests) < 0.05
+
+
+def test_particle_filter_vec_matches_kalman(device):
+    gj, _, step_vec = _models()
+    from genjax_b200.inference.pf import ParticleFilter
+
+    d, n, T = 8, 1 << 17, 20
+    ys = osmc.simulate_lgssm(2, T, d, A_, Q_, C_, R_)
+    exact = osmc.kalman_logz(ys, A_, Q_, C_, R_)
+    x0 = torch.randn(n, d, generator=torch.Generator().manual_seed(0))
+    q = torch.full((d,), Q_)
+    r = torch.full((d,), R_)
+    pf = ParticleFilter(step_vec, n)
+    res = pf.run(gj.key(5), x0, gj.C["y"].set(torch.from_numpy(ys)), shared_args=(q, r))
+    assert res.log_marginal_likelihood.item() == pytest.approx(exact, abs=0.5)
