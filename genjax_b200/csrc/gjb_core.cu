@@ -17,9 +17,10 @@ namespace gjb {
 constexpr int kTile = 2048;      // particles per tile (fixed: part of the ABI)
 constexpr int kThreads = 256;    // threads per block in tile kernels
 constexpr int kItems = 8;        // particles per thread
+constexpr double kQLog = 36.0 * 0.693147180559945309417;  // log(2^kQBits)
 static_assert(kTile == kThreads * kItems, "tile shape");
 
-// floor(2^30 * exp(x)), x <= 0, from IEEE fp32 mul/add only (oracle/smc.py det_exp_q).
+// round(2^36 * exp(x)), x <= 0, from IEEE fp32 mul/add only (oracle/smc.py det_exp_q).
 __device__ __forceinline__ uint64_t det_exp_q(float x) {
   float t = __fmul_rn(x, 0x1.715476p+0f);
   if (!(t >= -62.0f)) return 0ull;  // NaN, -inf, negligible
@@ -35,8 +36,9 @@ __device__ __forceinline__ uint64_t det_exp_q(float x) {
   p = __fadd_rn(__fmul_rn(p, g), 0x1.62e43p-1f);    // ln2
   p = __fadd_rn(__fmul_rn(p, g), 1.0f);
   p = __fmul_rn(p, 0x1.6a09e6p+0f);                 // sqrt(2)
-  const uint64_t m = (uint64_t)__fmul_rn(p, 1073741824.0f);
-  return m >> (uint32_t)(-n);
+  const uint64_t m = (uint64_t)__fmul_rn(p, 68719476736.0f);  // 2^kQBits
+  const uint32_t sh = (uint32_t)(-n);
+  return sh ? ((m + (1ull << (sh - 1))) >> sh) : m;  // round to nearest: unbiased mass
 }
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(256) lse_finalize_kernel(const uint64_t* __res
     const double M = (double)ref_max(wmax, m_global);
     out[0] = M;
     out[1] = (double)tot;
-    out[2] = tot ? M + log((double)tot) - 30.0 * 0.693147180559945309417 - log((double)n_total) : -INFINITY;
+    out[2] = tot ? M + log((double)tot) - kQLog - log((double)n_total) : -INFINITY;
   }
 }
 
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(kThreads) resample_systematic_kernel(const __g
       const double Md = (double)ref_max(wmax, m_global);
       R.lse_out[0] = Md;
       R.lse_out[1] = (double)S;
-      R.lse_out[2] = S ? Md + log((double)S) - 30.0 * 0.693147180559945309417 - log((double)n_total) : -INFINITY;
+      R.lse_out[2] = S ? Md + log((double)S) - kQLog - log((double)n_total) : -INFINITY;
     }
     if (R.wmax_next) *R.wmax_next = GJB_WMAX_NEG_INF;
   }

@@ -54,7 +54,7 @@ int gjb_weight_max(const float* logw, int64_t n, uint32_t* wmax, void* stream);
 
 /*
  * Exact integer mass of the weights relative to the max:
- *   tile_mass[b] = sum_{i in tile b} floor(2^30 * exp(logw_i - M)),  tile = 2048
+ *   tile_mass[b] = sum_{i in tile b} round(2^36 * exp(logw_i - M)),  tile = 2048
  * (uint64; integer addition is associative, so the total is independent of
  * the reduction tree and of the GPU count).  Second pass of logsumexp,
  * inference/smc.py:96-97.  `m_global` (device float*) overrides *wmax when
@@ -65,7 +65,7 @@ int gjb_weight_mass(const float* logw, int64_t n, const uint32_t* wmax,
 
 /*
  * lse_out[0] = M (fp32 max as double), lse_out[1] = S (total mass as double,
- * exact below 2^53), lse_out[2] = log-mean-exp = M + log S - 30 log 2 - log n_total.
+ * exact below 2^53), lse_out[2] = log-mean-exp = M + log S - 36 log 2 - log n_total.
  * ParticleCollection.get_log_marginal_likelihood_estimate, inference/smc.py:96-97.
  */
 int gjb_lse_finalize(const uint64_t* tile_mass, int64_t n, const uint32_t* wmax,
@@ -95,7 +95,7 @@ typedef struct gjb_resample_args {
   uint64_t key_index;         /* resample key lane: u0 = u01(Philox(idx=key_index, site 0, chunk 0).x) */
   const uint32_t* key_dev;    /* nullable: {key0, key1, index_lo, index_hi} read on the device instead */
   int32_t* ancestors;         /* [out_n]                                          */
-  double* lse_out;            /* nullable: {M, S, M + log S - 30 log 2 - log n_total} */
+  double* lse_out;            /* nullable: {M, S, M + log S - 36 log 2 - log n_total} */
   uint32_t* wmax_next;        /* nullable: reset to -inf for the next step        */
 } gjb_resample_args;
 

@@ -23,13 +23,13 @@ Reference:
 The deterministic weight pipeline (bit-identical in gjb_resample.cuh):
 
     M   = max_i lw_i                                   (fp32, order-free)
-    q_i = floor(2^30 * exp(lw_i - M))  via det_exp_q   (uint64, <= 2^31)
+    q_i = round(2^36 * exp(lw_i - M))  via det_exp_q   (uint64, <= 2^37)
     C_i = inclusive prefix sum of q                    (uint64, exact => any
           reduction tree / GPU count gives the same bits)
     S   = C_{N-1}
     cnt_i = clamp(ceil(C_i * (N / S) - u0), 0, N)      (fp64 rn mul, rn sub)
     ancestors[j] = i  for j in [cnt_{i-1}, cnt_i)      (systematic)
-    logZ-hat    = M + log(S) - 30 log 2 - log N        (fp64 on the host)
+    logZ-hat    = M + log(S) - 36 log 2 - log N        (fp64 on the host)
 """
 
 from __future__ import annotations
@@ -43,7 +43,7 @@ from . import gfi, rng
 F32 = np.float32
 U64 = np.uint64
 
-Q_BITS = 30
+Q_BITS = 36
 _LOG2E = F32(1.4426950408889634)
 _SQRT2 = F32(1.4142135623730951)
 # Taylor coefficients of 2^g = exp(g ln 2), g in [-0.5, 0.5), degree 7
@@ -51,7 +51,7 @@ _EXP2_COEF = [F32((math.log(2.0) ** k) / math.factorial(k)) for k in range(8)]
 
 
 def det_exp_q(x):
-    """floor(2^30 * exp(x)) for x <= 0 using only IEEE fp32 mul/add (no fma,
+    """round(2^36 * exp(x)) for x <= 0 using only IEEE fp32 mul/add (no fma,
     no libm) so that NumPy and CUDA agree bit for bit.  NaN / -inf / tiny -> 0."""
     x = np.asarray(x, dtype=F32)
     with np.errstate(invalid="ignore", over="ignore"):
@@ -67,7 +67,8 @@ def det_exp_q(x):
         p = (p * _SQRT2).astype(F32)
         m = (p * F32(2.0**Q_BITS)).astype(F32).astype(U64)
         sh = (-n).astype(np.int64).astype(U64)
-        q = m >> sh
+        half = np.where(sh > 0, U64(1) << np.maximum(sh, U64(1)) - U64(1), U64(0)).astype(U64)
+        q = (m + half) >> sh
     return np.where(ok, q, U64(0)).astype(U64)
 
 

@@ -148,16 +148,47 @@ def test_particle_filter_matches_kalman(device):
     assert np.std(ests) < 0.05
 
 
+def test_particle_filter_vec_teacher_forced_vs_oracle(device):
+    gj, _, step_vec = _models()
+    from genjax_b200.inference.pf import ParticleFilter
+
+    d, n, T = 8, 5000, 6
+    ys = osmc.simulate_lgssm(2, T, d, A_, Q_, C_, R_)
+    x0 = torch.randn(n, d, generator=torch.Generator().manual_seed(0))
+    q = torch.full((d,), Q_)
+    r = torch.full((d,), R_)
+    res = ParticleFilter(step_vec, n).run(
+        gj.key(5), x0, gj.C["y"].set(torch.from_numpy(ys)), shared_args=(q, r), record=True
+    )
+    anc = res.ancestors.cpu().numpy()
+    xs = res.history["state"][0].cpu().numpy()
+    lws = res.history["log_weights"].cpu().numpy()
+    x_in = x0.numpy()
+    okey = orng.key(5)
+    for t in range(T):
+        kp, kr = osmc.pf_step_keys(okey, t)
+        otr, ow = ogfi.generate(o_step_vec, orng.split(kp, n), {"y": ys[t]}, (x_in, q.numpy(), r.numpy()))
+        np.testing.assert_allclose(xs[t], otr.choices["x"], rtol=1e-5, atol=4e-6)
+        np.testing.assert_allclose(lws[t], ow, rtol=2e-5, atol=2e-4)
+        assert np.array_equal(anc[t], osmc.resample_systematic(lws[t], kr))
+        x_in = xs[t][anc[t]]
+    np.testing.assert_array_equal(res.state[0].cpu().numpy(), x_in)
+
+
 def test_particle_filter_vec_matches_kalman(device):
     gj, _, step_vec = _models()
     from genjax_b200.inference.pf import ParticleFilter
 
-    d, n, T = 8, 1 << 17, 20
-    ys = osmc.simulate_lgssm(2, T, d, A_, Q_, C_, R_)
-    exact = osmc.kalman_logz(ys, A_, Q_, C_, R_)
+    d, n, T = 8, 1 << 18, 20
+    r_obs = 2.0  # weakly informative observations keep the 8-D bootstrap filter's variance small
+    ys = osmc.simulate_lgssm(2, T, d, A_, Q_, C_, r_obs)
+    exact = osmc.kalman_logz(ys, A_, Q_, C_, r_obs)
     x0 = torch.randn(n, d, generator=torch.Generator().manual_seed(0))
     q = torch.full((d,), Q_)
-    r = torch.full((d,), R_)
-    pf = ParticleFilter(step_vec, n)
-    res = pf.run(gj.key(5), x0, gj.C["y"].set(torch.from_numpy(ys)), shared_args=(q, r))
-    assert res.log_marginal_likelihood.item() == pytest.approx(exact, abs=0.5)
+    r = torch.full((d,), r_obs)
+    ests = []
+    for seed in (5, 6):
+        pf = ParticleFilter(step_vec, n)
+        res = pf.run(gj.key(seed), x0, gj.C["y"].set(torch.from_numpy(ys)), shared_args=(q, r))
+        ests.append(res.log_marginal_likelihood.item())
+    assert np.mean(ests) == pytest.approx(exact, abs=0.15)
