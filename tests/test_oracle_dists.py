@@ -1,0 +1,110 @@
+"""Oracle distributions: the reference KAT for Normal, and every restated TFP
+log_prob against an independent float64 implementation (scipy.stats)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+from scipy import stats
+
+from oracle import dists, gfi, rng
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))
+RNG = np.random.default_rng(0)
+
+
+def test_reference_kat_assess_two_normals():
+    """tests/generative_functions/test_static_gen_fn.py:317-318."""
+    g = GOLD["assess_two_normals"]
+
+    def model(h):
+        y1 = h.normal("y1", np.float32(0.0), np.float32(1.0))
+        y2 = h.normal("y2", np.float32(0.0), np.float32(1.0))
+        return y1 + y2
+
+    score, rv = gfi.assess(model, {k: np.float32(v) for k, v in g["choices"].items()}, ())
+    assert score[0] == pytest.approx(g["score"], abs=1e-6)
+    assert float(rv) == 0.0
+
+
+def _close(a, b, rtol=2e-6, atol=2e-6):
+    np.testing.assert_allclose(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), rtol=rtol, atol=atol)
+
+
+def test_logpdfs_against_scipy():
+    v = RNG.standard_normal(1000).astype(np.float32) * 3
+    loc = RNG.standard_normal(1000).astype(np.float32)
+    sc = (0.1 + RNG.random(1000) * 4).astype(np.float32)
+    _close(dists.normal_logpdf(v, loc, sc), stats.norm.logpdf(v.astype(np.float64), loc, sc), rtol=1e-5, atol=1e-5)
+    u = RNG.random(1000).astype(np.float32)
+    _close(dists.uniform_logpdf(u * 3 - 1, -1.0, 2.0), np.full(1000, -math.log(3.0)))
+    assert dists.uniform_logpdf(np.float32(2.5), -1.0, 2.0) == -np.inf
+    p = (0.01 + 0.98 * RNG.random(1000)).astype(np.float32)
+    x = (RNG.random(1000) < 0.5).astype(np.int32)
+    _close(dists.flip_logpdf(x, p), stats.bernoulli.logpmf(x, p.astype(np.float64)), rtol=1e-5)
+    lg = RNG.standard_normal(1000).astype(np.float32) * 3
+    _close(dists.bernoulli_logpdf(x, lg), stats.bernoulli.logpmf(x, 1 / (1 + np.exp(-lg.astype(np.float64)))), rtol=1e-5, atol=1e-6)
+    r = (0.1 + 5 * RNG.random(1000)).astype(np.float32)
+    e = (RNG.exponential(1.0, 1000) / r).astype(np.float32)
+    _close(dists.exponential_logpdf(e, r), stats.expon.logpdf(e.astype(np.float64), scale=1 / r.astype(np.float64)), rtol=1e-5, atol=1e-5)
+    a = (0.2 + 5 * RNG.random(1000)).astype(np.float32)
+    gv = (RNG.gamma(a) / r).astype(np.float32) + np.float32(1e-3)
+    _close(dists.gamma_logpdf(gv, a, r), stats.gamma.logpdf(gv.astype(np.float64), a.astype(np.float64), scale=1 / r.astype(np.float64)), rtol=2e-5, atol=2e-5)
+    b = (0.2 + 5 * RNG.random(1000)).astype(np.float32)
+    bv = np.clip(RNG.beta(a, b), 1e-3, 1 - 1e-3).astype(np.float32)
+    _close(dists.beta_logpdf(bv, a, b), stats.beta.logpdf(bv.astype(np.float64), a.astype(np.float64), b.astype(np.float64)), rtol=2e-5, atol=2e-5)
+    hv = np.abs(v)
+    _close(dists.half_normal_logpdf(hv, sc), stats.halfnorm.logpdf(hv.astype(np.float64), scale=sc.astype(np.float64)), rtol=1e-5, atol=1e-5)
+    assert dists.half_normal_logpdf(np.float32(-1.0), 1.0) == -np.inf
+
+
+def test_categorical_and_mvn_logpdf():
+    logits = RNG.standard_normal((50, 16)).astype(np.float32) * 2
+    k = RNG.integers(0, 16, 50)
+    ref = logits.astype(np.float64) - np.log(np.exp(logits.astype(np.float64)).sum(-1, keepdims=True))
+    _close(dists.categorical_logpdf(k, logits), ref[np.arange(50), k], rtol=1e-5, atol=1e-5)
+    v = RNG.standard_normal((100, 8)).astype(np.float32)
+    loc = RNG.standard_normal(8).astype(np.float32)
+    sc = (0.5 + RNG.random(8)).astype(np.float32)
+    ref = stats.norm.logpdf(v.astype(np.float64), loc, sc).sum(-1)
+    _close(dists.mv_normal_diag_logpdf(v, loc, sc), ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize(
+    "name,args,cdf",
+    [
+        ("normal", (1.5, 2.0), lambda x: stats.norm.cdf(x, 1.5, 2.0)),
+        ("uniform", (-1.0, 3.0), lambda x: stats.uniform.cdf(x, -1.0, 4.0)),
+        ("exponential", (2.5,), lambda x: stats.expon.cdf(x, scale=1 / 2.5)),
+        ("half_normal", (1.7,), lambda x: stats.halfnorm.cdf(x, scale=1.7)),
+        ("gamma", (2.5, 1.5), lambda x: stats.gamma.cdf(x, 2.5, scale=1 / 1.5)),
+        ("gamma", (0.4, 1.0), lambda x: stats.gamma.cdf(x, 0.4)),
+        ("beta", (2.0, 2.0), lambda x: stats.beta.cdf(x, 2.0, 2.0)),
+        ("beta", (0.5, 3.0), lambda x: stats.beta.cdf(x, 0.5, 3.0)),
+    ],
+)
+def test_continuous_samplers_ks(name, args, cdf):
+    n = 40_000
+    idx = np.arange(n, dtype=np.uint64)
+    x = dists.DISTS[name][0]((11, 22), idx, 1, *[np.float32(a) for a in args])
+    assert x.dtype == np.float32 and x.shape == (n,)
+    d, p = stats.kstest(x.astype(np.float64), cdf)
+    assert p > 1e-3, (name, d, p)
+
+
+def test_discrete_samplers_frequencies():
+    n = 100_000
+    idx = np.arange(n, dtype=np.uint64)
+    x = dists.flip_sample((1, 2), idx, 1, np.float32(0.3))
+    assert abs(x.mean() - 0.3) < 5e-3
+    x = dists.bernoulli_sample((1, 2), idx, 2, np.float32(-1.0))
+    assert abs(x.mean() - 1 / (1 + math.e)) < 5e-3
+    logits = np.log(np.array([0.1, 0.2, 0.3, 0.4], dtype=np.float32))
+    k = dists.categorical_sample((1, 2), idx, 3, logits)
+    f = np.bincount(k, minlength=4) / n
+    np.testing.assert_allclose(f, [0.1, 0.2, 0.3, 0.4], atol=6e-3)
+    # per-particle logits rows
+    rows = np.tile(logits, (n, 1))
+    k2 = dists.categorical_sample((1, 2), idx, 3, rows)
+    assert np.array_equal(k, k2)
