@@ -1,0 +1,190 @@
+"""Host-side logic that needs no GPU: ChoiceMap / Selection algebra (after
+/root/reference/tests/core/test_choice_maps.py), the key tree, model capture
+(site discovery, error conventions) and code generation."""
+import numpy as np
+import pytest
+
+import genjax_b200 as gj
+from genjax_b200 import C, S, ChoiceMap, Selection
+from genjax_b200.gen import capture as cap
+from genjax_b200.gen import codegen
+from genjax_b200.gen.capture import ArgSpec
+from genjax_b200.gen.expr import TracedControlFlow
+
+
+# ---------------------------------------------------------------- selections
+def test_selection_basic():
+    new = S["x"] | S["z", "y"]
+    assert new["x"] and new["z", "y"] and new["z", "y", "tail"]
+    new = S["x", "y", "z"]
+    assert new["x", "y", "z"] and not new["x"] and not new["x", "y"]
+
+
+def test_selection_all_none_complement():
+    assert Selection.all()["x"] and Selection.all()["y", "z"]
+    assert not Selection.none()["x"]
+    sel = S["x"] | S["y"]
+    comp = ~sel
+    assert not comp["x"] and not comp["y"] and comp["z"]
+    both = S["x"] & S["x"]
+    assert both["x"] and not both["y"]
+    assert (S["x"] & S["y"])["x"] is False
+
+
+def test_selection_extend_and_descend():
+    sel = Selection.all().extend("a", "b")
+    assert sel["a", "b"] and sel["a", "b", "c"] and not sel["a"]
+    assert sel("a")["b"]
+    assert "x" in S["x"]
+
+
+# --------------------------------------------------------------- choice maps
+def test_choicemap_builder_forms():
+    chm = C["x"].set(1.0)
+    assert chm["x"] == 1.0 and "x" in chm and "y" not in chm
+    chm = C["a", "b"].set(2.0)
+    assert chm["a", "b"] == 2.0 and chm("a")["b"] == 2.0
+    assert C.kw(x=1, y=2)["y"] == 2
+    assert C.d({"x": 1, "y": {"z": 3}})["y", "z"] == 3
+    assert C.n().static_is_empty()
+    assert C.v(5.0).get_value() == 5.0
+    assert ChoiceMap.empty().static_is_empty()
+    assert ChoiceMap.choice(3).has_value()
+
+
+def test_choicemap_at_set_and_merge():
+    chm = ChoiceMap.empty().at["x"].set(1.0).at["y", "z"].set(2.0)
+    assert chm["x"] == 1.0 and chm["y", "z"] == 2.0
+    merged = C["x"].set(1.0) | C["y"].set(2.0)
+    assert merged["x"] == 1.0 and merged["y"] == 2.0
+    # left-biased merge like the reference's `|` (choice_map.py:1227-1299)
+    assert (C["x"].set(1.0) | C["x"].set(5.0))["x"] == 1.0
+    assert C["x"].set(1.0).merge(C["y"].set(2.0))["y"] == 2.0
+
+
+def test_choicemap_missing_value_raises():
+    with pytest.raises(gj.ChoiceMapNoValueAtAddress):
+        C["x"].set(1.0)["y"]
+
+
+def test_choicemap_filter_and_selection_roundtrip():
+    chm = C.d({"x": 1.0, "y": 2.0, "z": {"w": 3.0}})
+    f = chm.filter(S["x"] | S["z"])
+    assert "x" in f and ("z", "w") in f and "y" not in f
+    g = chm.filter(~chm.filter(S["x"]).get_selection())
+    assert "x" not in g and "y" in g
+    assert sorted(a for a, _ in chm.leaves()) == [("x",), ("y",), ("z", "w")]
+
+
+def test_target_filter_to_unconstrained():
+    from genjax_b200.workloads import beta_bernoulli
+
+    t = gj.Target(beta_bernoulli, (2.0, 2.0), C["v"].set(True))
+    latents = t.filter_to_unconstrained(C.d({"p": 0.3, "v": True}))
+    assert "p" in latents and "v" not in latents
+    assert t["v"] is True
+    with pytest.raises(TypeError):
+        gj.Target(beta_bernoulli, (2.0, 2.0), {"v": True})
+
+
+# ------------------------------------------------------------------- capture
+def _specs(*kinds):
+    return [ArgSpec(k, "f32", s) for k, s in kinds]
+
+
+def test_capture_sites_in_program_order():
+    from genjax_b200.workloads import lgssm_step
+
+    ir = cap.capture(lgssm_step.source, "lgssm", _specs(("particle", ())), ("tuple", [("leaf", 0)]))
+    assert [s.addr for s in ir.sites] == [("x",), ("y",)]
+    assert [s.dist.name for s in ir.sites] == ["normal", "normal"]
+    assert ir.width == 0 and len(ir.ret_leaves) == 1
+    assert ir.ret_leaves[0].op == "site" and ir.ret_leaves[0].attr == 0
+
+
+def test_capture_address_reuse_raises():
+    @gj.gen
+    def bad():
+        gj.normal(0.0, 1.0) @ "x"
+        gj.normal(0.0, 1.0) @ "x"
+
+    with pytest.raises(gj.AddressReuse):
+        cap.capture(bad.source, "bad", [], ("tuple", []))
+
+
+def test_capture_traced_control_flow_raises():
+    @gj.gen
+    def bad(x):
+        if x > 0:
+            return gj.normal(0.0, 1.0) @ "a"
+        return gj.normal(1.0, 1.0) @ "b"
+
+    with pytest.raises(TracedControlFlow):
+        cap.capture(bad.source, "bad", _specs(("particle", ())), ("tuple", [("leaf", 0)]))
+
+
+def test_capture_nested_gen_inlines_under_prefix():
+    @gj.gen
+    def inner(m):
+        return gj.normal(m, 1.0) @ "z"
+
+    @gj.gen
+    def outer(m):
+        a = inner(m) @ "sub"
+        return gj.normal(a, 2.0) @ "y"
+
+    ir = cap.capture(outer.source, "outer", _specs(("scalar", ())), ("tuple", [("leaf", 0)]))
+    assert [s.addr for s in ir.sites] == [("sub", "z"), ("y",)]
+
+
+def test_exact_density_is_not_fusable():
+    d = gj.exact_density(lambda key, a: a, lambda v, a: 0.0, "mine")
+
+    @gj.gen
+    def m():
+        return d(1.0) @ "x"
+
+    with pytest.raises(gj.NotFusable):
+        cap.capture(m.source, "m", [], ("tuple", []))
+
+
+def test_fingerprint_is_structural():
+    from genjax_b200.workloads import lgssm_step
+
+    a = cap.capture(lgssm_step.source, "a", _specs(("particle", ())), ("tuple", [("leaf", 0)]))
+    b = cap.capture(lgssm_step.source, "b", _specs(("particle", ())), ("tuple", [("leaf", 0)]))
+    c = cap.capture(lgssm_step.source, "c", _specs(("scalar", ())), ("tuple", [("leaf", 0)]))
+    assert cap.ir_fingerprint(a) == cap.ir_fingerprint(b) != cap.ir_fingerprint(c)
+
+
+# ------------------------------------------------------------------- codegen
+def test_codegen_mappings():
+    assert codegen.group_lanes(32) == 8 and codegen.group_lanes(8) == 2 and codegen.group_lanes(4) == 1
+    assert codegen.group_lanes(12) == 0 and codegen.group_lanes(0) == 0 and codegen.group_lanes(256) == 0
+    from genjax_b200.workloads import lgssm_step, lgssm_step_vec
+
+    ir = cap.capture(lgssm_step.source, "lgssm", _specs(("particle", ())), ("tuple", [("leaf", 0)]))
+    ir.digest = cap.ir_fingerprint(ir)
+    src = codegen.generate(ir)
+    assert "quad mapping" in src and "gjb_model_launch" in src and "gjb::Normal::" in src
+    ir = cap.capture(lgssm_step_vec.source, "v", _specs(("particle", (32,)), ("shared", (32,)), ("shared", (32,))),
+                     ("tuple", [("leaf", 0), ("leaf", 1), ("leaf", 2)]))
+    ir.digest = cap.ir_fingerprint(ir)
+    src = codegen.generate(ir)
+    assert "group mapping, G=8" in src
+
+
+def test_new_model_compiles_for_sm100a():
+    """A model outside the prebuilt set goes capture -> codegen -> nvcc (sm_100a) -> loadable .so."""
+
+    @gj.gen
+    def m(x_prev, rate):
+        s = gj.exponential(rate) @ "s"
+        u = gj.uniform(0.0, 1.0) @ "u"
+        b = gj.flip(gj.numpy.sigmoid(x_prev)) @ "b"
+        y = gj.normal(x_prev * s + u, 1.0 + gj.numpy.exp(-s)) @ "y"
+        return gj.numpy.where(b, y, -y)
+
+    cm = m.prebuild([ArgSpec("particle", "f32", ()), ArgSpec("scalar", "f32", ())])
+    assert cm.path.exists() and cm.info["mapping"] == "quad"
+    assert [s["dist"] for s in cm.info["sites"]] == ["exponential", "uniform", "flip", "normal"]
