@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--particles", type=int, default=1 << 20, help="particles per GPU")
     ap.add_argument("--T", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="persistent", choices=["persistent", "graph"],
+                    help="persistent: one cooperative launch per filter; graph: 3 launches per step in a CUDA graph")
     return ap.parse_args()
 
 
@@ -246,7 +248,7 @@ def run_ours(args):
         shared = (torch.full((d,), LG_Q, device=device), torch.full((d,), LG_R, device=device))
     # weak scaling: every rank filters its own block of n particles; lanes are
     # global particle indices so the streams of different ranks never overlap
-    pf = ParticleFilter(model, n, idx_offset=0)
+    pf = ParticleFilter(model, n, idx_offset=0, mode=args.mode)
     obs_dev = gj.C["y"].set(ys_dev)
     obs_host = gj.C["y"].set(ys_host)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
@@ -317,45 +319,73 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (fused gather + propose + logpdf)
+    # ---- roofline of the dominant kernel
     plan = next(iter(pf._plans.values()))
     import ctypes as C
 
     stream = cabi.stream_ptr(device)
-    A = plan.margs[min(1, T - 1)]  # a step with the ancestor gather fused in
-    reps = 200
-    for _ in range(20):
-        plan.cm.lib.gjb_model_launch(C.byref(A), stream)
-    torch.cuda.synchronize(device)
-    k0 = torch.cuda.Event(enable_timing=True)
-    k1 = torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for _ in range(reps):
-        plan.cm.lib.gjb_model_launch(C.byref(A), stream)
-    k1.record()
-    torch.cuda.synchronize(device)
-    kernel_ms = k0.elapsed_time(k1) / reps
-    bytes_per_particle = 8 * d + 12  # read ancestor 4 + x_prev 4d, write x 4d + logw 4
-    alg_bytes = bytes_per_particle * n
-    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     peak, how = peaks()
-    step_bytes = (8 * d + 24) * n * T
     ms_per_step = t_dev.item() / args.steps
-    roofline = {
-        "bound": "hbm",
-        "kernel": "model_kernel (fused ancestor-gather + propose + logpdf + running max)",
-        "achieved": achieved,
-        "peak": peak,
-        "peak_source": how,
-        "unit": "GB/s",
-        "frac": achieved / peak,
-        "traffic": None,
-        "kernel_us": kernel_ms * 1e3,
-        "algorithmic_bytes_per_launch": alg_bytes,
-        "working_set_note": ("L2-resident: %d MB of particle arrays < 126 MB L2" % (alg_bytes >> 20)) if alg_bytes < (100 << 20)
-        else "HBM-resident: particle arrays exceed the 126 MB L2",
-        "whole_step_GBps": step_bytes / (ms_per_step * 1e-3) / 1e9,
-    }
+    step_bytes = (8 * d + 24) * n * T  # whole bootstrap-PF step with fused gather
+
+    def time_launches(fn, reps, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(device)
+        k0 = torch.cuda.Event(enable_timing=True)
+        k1 = torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(reps):
+            fn()
+        k1.record()
+        torch.cuda.synchronize(device)
+        return k0.elapsed_time(k1) / reps
+
+    # (i) the stand-alone fused gather + propose + logpdf launch (gjb_model_launch), as ImportanceK / ChangeTarget use it
+    MA = cabi.ModelArgs()
+    MA.n = n
+    MA.key0, MA.key1 = 1, 2
+    anc_id = torch.arange(n, dtype=torch.int32, device=device)
+    x_out = torch.empty_like(x0_dev)
+    lw_out = torch.empty(n, dtype=torch.float32, device=device)
+    wmax = torch.zeros(1, dtype=torch.int32, device=device)
+    y_one = ys_dev[0].contiguous() if d > 1 else ys_dev[:1].contiguous()
+    MA.args[0] = x0_dev.data_ptr()
+    for k_, s_ in enumerate(shared):
+        MA.args[1 + k_] = s_.data_ptr()
+    MA.gather = anc_id.data_ptr()
+    MA.site_flags[0] = cabi.SITE_SAMPLE
+    MA.site_out[0] = x_out.data_ptr()
+    MA.site_in[1] = y_one.data_ptr()
+    MA.site_flags[1] = cabi.SITE_WEIGHT | cabi.SITE_BCAST
+    MA.weight_out = lw_out.data_ptr()
+    MA.wmax = wmax.data_ptr()
+    model_ms = time_launches(lambda: plan.cm.lib.gjb_model_launch(C.byref(MA), stream), 200, 20)
+    model_bytes = (8 * d + 12) * n  # read ancestor 4 + x_prev 4d, write x 4d + logw 4
+    model_gbs = model_bytes / (model_ms * 1e-3) / 1e9
+
+    if plan.persistent:
+        pf_ms = time_launches(lambda: plan.cm.lib.gjb_model_pf_run(C.byref(plan.pf_args), stream), 10, 2)
+        achieved = step_bytes / (pf_ms * 1e-3) / 1e9
+        roofline = {
+            "bound": "hbm",
+            "kernel": "pf_kernel (persistent cooperative filter: per step gather+propose+logpdf+max | integer mass | CDF scan+systematic ancestors)",
+            "achieved": achieved, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "kernel_us": pf_ms * 1e3, "algorithmic_bytes_per_launch": step_bytes,
+            "algorithmic_bytes_per_particle_step": 8 * d + 24,
+        }
+    else:
+        roofline = {
+            "bound": "hbm", "kernel": "model_kernel (fused ancestor-gather + propose + logpdf + running max)",
+            "achieved": model_gbs, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": model_gbs / peak,
+            "traffic": None, "kernel_us": model_ms * 1e3, "algorithmic_bytes_per_launch": model_bytes,
+        }
+    roofline["working_set_note"] = (
+        "L2-resident: %d MB of particle arrays < 126 MB L2, DRAM traffic is only the first touch" % ((8 * d + 12) * n >> 20)
+        if (8 * d + 12) * n < (100 << 20) else "HBM-resident: particle arrays exceed the 126 MB L2")
+    roofline["whole_step_GBps"] = step_bytes / (ms_per_step * 1e-3) / 1e9
+    roofline["model_kernel_alone"] = {"kernel_us": model_ms * 1e3, "algorithmic_bytes_per_launch": model_bytes,
+                                      "achieved": model_gbs, "frac": model_gbs / peak}
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -383,7 +413,8 @@ def run_ours(args):
             "workload": f"linear-Gaussian SSM bootstrap SMC (BASELINE configs[1]): T={T}, N={n} particles/GPU, d={d}, "
                         "systematic resampling every step",
             "particles_per_gpu": n, "T": T, "d": d,
-            "l2": "flushed between timed steps (256 MiB write); within a step the 1M-particle arrays are L2-resident by size",
+            "l2": "flushed between timed steps (256 MiB write)",
+            "mode": args.mode,
             "multi_gpu": "independent particle blocks per rank (weak scaling), no data-path collective",
             "logZ_last": logz,
         },

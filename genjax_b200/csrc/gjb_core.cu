@@ -10,47 +10,10 @@
 #include <stdint.h>
 
 #include "../../include/genjax_b200.h"
+#include "gjb_resample.cuh"
 #include "gjb_rng.cuh"
 
 namespace gjb {
-
-constexpr int kTile = 2048;      // particles per tile (fixed: part of the ABI)
-constexpr int kThreads = 256;    // threads per block in tile kernels
-constexpr int kItems = 8;        // particles per thread
-constexpr double kQLog = 36.0 * 0.693147180559945309417;  // log(2^kQBits)
-static_assert(kTile == kThreads * kItems, "tile shape");
-
-// round(2^36 * exp(x)), x <= 0, from IEEE fp32 mul/add only (oracle/smc.py det_exp_q).
-__device__ __forceinline__ uint64_t det_exp_q(float x) {
-  float t = __fmul_rn(x, 0x1.715476p+0f);
-  if (!(t >= -62.0f)) return 0ull;  // NaN, -inf, negligible
-  t = fminf(t, 0.0f);
-  const float n = floorf(t);
-  const float g = __fadd_rn(__fadd_rn(t, -n), -0.5f);
-  float p = 0x1.ffcbfcp-17f;                         // ln2^7/7!
-  p = __fadd_rn(__fmul_rn(p, g), 0x1.430912p-13f);  // ln2^6/6!
-  p = __fadd_rn(__fmul_rn(p, g), 0x1.5d87fep-10f);  // ln2^5/5!
-  p = __fadd_rn(__fmul_rn(p, g), 0x1.3b2ab6p-7f);   // ln2^4/4!
-  p = __fadd_rn(__fmul_rn(p, g), 0x1.c6b08ep-5f);   // ln2^3/3!
-  p = __fadd_rn(__fmul_rn(p, g), 0x1.ebfbep-3f);    // ln2^2/2!
-  p = __fadd_rn(__fmul_rn(p, g), 0x1.62e43p-1f);    // ln2
-  p = __fadd_rn(__fmul_rn(p, g), 1.0f);
-  p = __fmul_rn(p, 0x1.6a09e6p+0f);                 // sqrt(2)
-  const uint64_t m = (uint64_t)__fmul_rn(p, 68719476736.0f);  // 2^kQBits
-  const uint32_t sh = (uint32_t)(-n);
-  return sh ? ((m + (1ull << (sh - 1))) >> sh) : m;  // round to nearest: unbiased mass
-}
-
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 // ---------------------------------------------------------------- wmax
 
@@ -84,39 +47,14 @@ __device__ __forceinline__ float ref_max(const uint32_t* wmax, const float* m_gl
   return m_global ? __ldg(m_global) : fdec(__ldg(wmax));
 }
 
-// loads the 8 consecutive log-weights of this thread (0-mass padding past n)
-__device__ __forceinline__ void load_items(const float* __restrict__ logw, int64_t n, int64_t base, float (&x)[kItems]) {
-  if (base + kItems <= n && ((reinterpret_cast<uintptr_t>(logw + base) & 15) == 0)) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(logw + base));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(logw + base) + 1);
-    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
-    x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-  } else {
-#pragma unroll
-    for (int k = 0; k < kItems; ++k) x[k] = (base + k < n) ? logw[base + k] : -INFINITY;
-  }
-}
-
 __global__ void __launch_bounds__(kThreads) weight_mass_kernel(const float* __restrict__ logw, int64_t n,
                                                                const uint32_t* __restrict__ wmax,
                                                                const float* __restrict__ m_global,
                                                                uint64_t* __restrict__ tile_mass) {
-  const float M = ref_max(wmax, m_global);
-  const int64_t base = (int64_t)blockIdx.x * kTile + threadIdx.x * kItems;
-  float x[kItems];
-  load_items(logw, n, base, x);
-  uint64_t s = 0;
-#pragma unroll
-  for (int k = 0; k < kItems; ++k) s += det_exp_q(__fadd_rn(x[k], -M));
-  s = warp_sum_u64(s);
   __shared__ uint64_t sm[kThreads / 32];
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    s = threadIdx.x < kThreads / 32 ? sm[threadIdx.x] : 0ull;
-    s = warp_sum_u64(s);
-    if (threadIdx.x == 0) tile_mass[blockIdx.x] = s;
-  }
+  const float M = ref_max(wmax, m_global);
+  const uint64_t s = tile_mass_of<false>(logw, n, (int64_t)blockIdx.x * kTile, M, sm);
+  if (threadIdx.x == 0) tile_mass[blockIdx.x] = s;
 }
 
 __global__ void __launch_bounds__(256) lse_finalize_kernel(const uint64_t* __restrict__ tile_mass, int n_tiles,
@@ -141,24 +79,8 @@ __global__ void __launch_bounds__(256) lse_finalize_kernel(const uint64_t* __res
 
 // ------------------------------------------------------------ systematic
 
-// cumulative offspring count of a particle whose inclusive CDF value is C
-__device__ __forceinline__ int64_t offspring_cnt(uint64_t C, uint64_t S, double scale, double u0, int64_t n_total) {
-  if (C == S) return n_total;
-  const double pos = __dsub_rn(__dmul_rn((double)C, scale), u0);
-  double c = ceil(pos);
-  c = fmin(fmax(c, 0.0), (double)n_total);
-  return (int64_t)c;
-}
-
 __global__ void __launch_bounds__(kThreads) resample_systematic_kernel(const __grid_constant__ gjb_resample_args R) {
-  const float* __restrict__ logw = R.logw;
   const int64_t n = R.n, n_total = R.n_total, out_lo = R.out_lo, out_n = R.out_n, anc_base = R.anc_base;
-  const uint32_t* __restrict__ wmax = R.wmax;
-  const float* __restrict__ m_global = R.m_global;
-  const uint64_t* __restrict__ tile_mass = R.tile_mass;
-  const uint64_t* __restrict__ c_offset = R.c_offset;
-  const uint64_t* __restrict__ s_total = R.s_total;
-  int32_t* __restrict__ ancestors = R.ancestors;
   uint32_t key0 = R.key0, key1 = R.key1;
   uint64_t key_index = R.key_index;
   if (R.key_dev) {
@@ -166,37 +88,26 @@ __global__ void __launch_bounds__(kThreads) resample_systematic_kernel(const __g
     key1 = __ldg(R.key_dev + 1);
     key_index = (uint64_t)__ldg(R.key_dev + 2) | ((uint64_t)__ldg(R.key_dev + 3) << 32);
   }
-  __shared__ uint64_t sm_a[kThreads / 32];
+  __shared__ TileSmem sm;
   __shared__ uint64_t sm_b[kThreads / 32];
-  __shared__ int64_t cnt_s[kTile + 1];
-  __shared__ int big_n;
-  __shared__ int big_list[64];
-
+  __shared__ __align__(16) int32_t heads[kWin];
   const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
   const int n_tiles = gridDim.x;
 
-  // 1. exclusive prefix of the tiles before this one + total mass
+  // exclusive prefix of the tiles before this one + total mass
   uint64_t pre = 0, tot = 0;
   for (int t = tid; t < n_tiles; t += kThreads) {
-    const uint64_t v = tile_mass[t];
+    const uint64_t v = R.tile_mass[t];
     tot += v;
     if (t < (int)blockIdx.x) pre += v;
   }
-  pre = warp_sum_u64(pre);
-  tot = warp_sum_u64(tot);
-  if (lane == 0) { sm_a[warp] = pre; sm_b[warp] = tot; }
-  if (tid == 0) big_n = 0;
-  __syncthreads();
-  pre = 0; tot = 0;
-#pragma unroll
-  for (int w = 0; w < kThreads / 32; ++w) { pre += sm_a[w]; tot += sm_b[w]; }
-  __syncthreads();
-  const uint64_t S = s_total ? __ldg(s_total) : tot;
-  const uint64_t off = pre + (c_offset ? __ldg(c_offset) : 0ull);
+  pre = block_sum_u64(pre, sm.red);
+  tot = block_sum_u64(tot, sm_b);
+  const uint64_t S = R.s_total ? __ldg(R.s_total) : tot;
+  const uint64_t off = pre + (R.c_offset ? __ldg(R.c_offset) : 0ull);
   if (blockIdx.x == 0 && tid == 0) {
     if (R.lse_out) {
-      const double Md = (double)ref_max(wmax, m_global);
+      const double Md = (double)ref_max(R.wmax, R.m_global);
       R.lse_out[0] = Md;
       R.lse_out[1] = (double)S;
       R.lse_out[2] = S ? Md + log((double)S) - kQLog - log((double)n_total) : -INFINITY;
@@ -209,69 +120,13 @@ __global__ void __launch_bounds__(kThreads) resample_systematic_kernel(const __g
     for (int k = tid; k < kTile; k += kThreads) {
       const int64_t i = tile_base + k;
       const int64_t j = anc_base + i;
-      if (i < n && j >= out_lo && j < out_lo + out_n) ancestors[j - out_lo] = (int32_t)j;
+      if (i < n && j >= out_lo && j < out_lo + out_n) R.ancestors[j - out_lo] = (int32_t)j;
     }
     return;
   }
-
-  // 2. q_i and block-wide inclusive scan
-  const float M = ref_max(wmax, m_global);
-  float x[kItems];
-  load_items(logw, n, tile_base + tid * kItems, x);
-  uint64_t q[kItems];
-  uint64_t tsum = 0;
-#pragma unroll
-  for (int k = 0; k < kItems; ++k) { q[k] = det_exp_q(__fadd_rn(x[k], -M)); tsum += q[k]; }
-  uint64_t inc = tsum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint64_t v = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += v;
-  }
-  if (lane == 31) sm_a[warp] = inc;
-  __syncthreads();
-  uint64_t wpre = 0;
-#pragma unroll
-  for (int w = 0; w < kThreads / 32; ++w) if (w < warp) wpre += sm_a[w];
-  uint64_t C = off + wpre + inc - tsum;  // exclusive prefix of this thread
-
-  // 3. cumulative offspring counts -> shared (blocked -> striped transpose)
-  const double u0 = (double)u01(philox4x32_10(make_uint4((uint32_t)key_index, (uint32_t)(key_index >> 32), 0u, 0u), key0, key1).x);
-  const double scale = __ddiv_rn((double)n_total, (double)S);
-  if (tid == 0) cnt_s[0] = offspring_cnt(C, S, scale, u0, n_total);
-#pragma unroll
-  for (int k = 0; k < kItems; ++k) {
-    C += q[k];
-    cnt_s[1 + tid * kItems + k] = offspring_cnt(C, S, scale, u0, n_total);
-  }
-  __syncthreads();
-
-  // 4. striped write-out: consecutive threads own consecutive particles
-  const int64_t win_hi = out_lo + out_n;
-#pragma unroll
-  for (int k = 0; k < kItems; ++k) {
-    const int il = k * kThreads + tid;
-    const int64_t i = tile_base + il;
-    if (i >= n) break;
-    int64_t lo = cnt_s[il] > out_lo ? cnt_s[il] : out_lo;
-    int64_t hi = cnt_s[il + 1] < win_hi ? cnt_s[il + 1] : win_hi;
-    if (hi - lo > 16) {
-      const int slot = atomicAdd(&big_n, 1);
-      if (slot < 64) { big_list[slot] = il; continue; }
-    }
-    const int32_t a = (int32_t)(anc_base + i);
-    for (int64_t j = lo; j < hi; ++j) ancestors[j - out_lo] = a;
-  }
-  __syncthreads();
-  // heavy particles (degenerate weights): the whole block fills their range
-  const int nb = big_n < 64 ? big_n : 64;
-  for (int b = 0; b < nb; ++b) {
-    const int il = big_list[b];
-    int64_t lo = cnt_s[il] > out_lo ? cnt_s[il] : out_lo;
-    int64_t hi = cnt_s[il + 1] < win_hi ? cnt_s[il + 1] : win_hi;
-    const int32_t a = (int32_t)(anc_base + tile_base + il);
-    for (int64_t j = lo + tid; j < hi; j += kThreads) ancestors[j - out_lo] = a;
-  }
+  const float M = ref_max(R.wmax, R.m_global);
+  const double u0 = resample_u0(key0, key1, key_index);
+  resample_tile<false>(R.logw, n, tile_base, M, off, S, n_total, u0, out_lo, out_n, anc_base, R.ancestors, sm, heads);
 }
 
 // ----------------------------------------------------------- multinomial
@@ -294,7 +149,7 @@ __global__ void __launch_bounds__(kThreads) cdf_kernel(const float* __restrict__
   const float M = fdec(__ldg(wmax));
   const int64_t base = (int64_t)blockIdx.x * kTile + tid * kItems;
   float x[kItems];
-  load_items(logw, n, base, x);
+  load_items<false>(logw, n, base, x);
   uint64_t q[kItems], tsum = 0;
 #pragma unroll
   for (int k = 0; k < kItems; ++k) { q[k] = det_exp_q(__fadd_rn(x[k], -M)); tsum += q[k]; }

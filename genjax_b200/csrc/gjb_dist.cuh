@@ -15,8 +15,11 @@ constexpr float kLog2OverPiHalf = -0.22579135264472743236f;  // 0.5*log(2/pi)
 
 // ------------------------------------------------------------------ normal
 struct Normal {
-  __device__ static __forceinline__ float sample(const Lane& l, uint32_t site, float loc, float scale) {
-    return loc + scale * normal1(l, site, 0);
+  __device__ static __forceinline__ float sample(float z, float loc, float scale) { return loc + scale * z; }
+  // logpdf with the particle-invariant pieces precomputed: inv = 1/scale, lc = 0.5 log 2pi + log scale
+  __device__ static __forceinline__ float logpdf_r(float v, float loc, float inv, float lc) {
+    const float z = v * inv - loc * inv;
+    return -0.5f * (z * z) - lc;
   }
   __device__ static __forceinline__ float logpdf(float v, float loc, float scale) {
     const float z = v / scale - loc / scale;
@@ -25,27 +28,21 @@ struct Normal {
 };
 
 struct Uniform {
-  __device__ static __forceinline__ float sample(const Lane& l, uint32_t site, float lo, float hi) {
-    return lo + (hi - lo) * u01(l.words(site, 0).x);
-  }
+  __device__ static __forceinline__ float sample(float u, float lo, float hi) { return lo + (hi - lo) * u; }
   __device__ static __forceinline__ float logpdf(float v, float lo, float hi) {
     return (v >= lo && v <= hi) ? -logf(hi - lo) : -INFINITY;
   }
 };
 
 struct Exponential {
-  __device__ static __forceinline__ float sample(const Lane& l, uint32_t site, float rate) {
-    return -logf(u01(l.words(site, 0).x)) / rate;
-  }
+  __device__ static __forceinline__ float sample(float u, float rate) { return -logf(u) / rate; }
   __device__ static __forceinline__ float logpdf(float v, float rate) {
     return v < 0.0f ? -INFINITY : logf(rate) - rate * v;
   }
 };
 
 struct HalfNormal {
-  __device__ static __forceinline__ float sample(const Lane& l, uint32_t site, float scale) {
-    return fabsf(normal1(l, site, 0)) * scale;
-  }
+  __device__ static __forceinline__ float sample(float z, float scale) { return fabsf(z) * scale; }
   __device__ static __forceinline__ float logpdf(float v, float scale) {
     const float z = v / scale;
     return v < 0.0f ? -INFINITY : kLog2OverPiHalf - logf(scale) - 0.5f * z * z;
@@ -56,9 +53,7 @@ struct HalfNormal {
 __device__ __forceinline__ float softplusf(float x) { return fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x))); }
 
 struct Flip {  // tfd.Bernoulli(probs=p); value is int32 0/1
-  __device__ static __forceinline__ int sample(const Lane& l, uint32_t site, float p) {
-    return u01(l.words(site, 0).x) < p ? 1 : 0;
-  }
+  __device__ static __forceinline__ int sample(float u, float p) { return u < p ? 1 : 0; }
   __device__ static __forceinline__ float logpdf(int v, float p) {
     const float x = (float)v;
     const float a = (x == 0.0f) ? 0.0f : x * logf(p);
@@ -68,9 +63,9 @@ struct Flip {  // tfd.Bernoulli(probs=p); value is int32 0/1
 };
 
 struct Bernoulli {  // tfd.Bernoulli(logits=l)
-  __device__ static __forceinline__ int sample(const Lane& l, uint32_t site, float logit) {
+  __device__ static __forceinline__ int sample(float u, float logit) {
     const float p = 1.0f / (1.0f + expf(-logit));
-    return u01(l.words(site, 0).x) < p ? 1 : 0;
+    return u < p ? 1 : 0;
   }
   __device__ static __forceinline__ float logpdf(int v, float logit) {
     const float x = (float)v;
@@ -81,12 +76,12 @@ struct Bernoulli {  // tfd.Bernoulli(logits=l)
 // -------------------------------------------------------------- categorical
 // logits: K contiguous floats (shared memory row, global row or registers)
 struct Categorical {
-  __device__ static __forceinline__ int sample(const Lane& l, uint32_t site, const float* logits, int K) {
+  __device__ static __forceinline__ int sample(float u, const float* logits, int K) {
     float m = -INFINITY;
     for (int j = 0; j < K; ++j) m = fmaxf(m, logits[j]);
     float tot = 0.0f;
     for (int j = 0; j < K; ++j) tot += expf(logits[j] - m);
-    const float t = u01(l.words(site, 0).x) * tot;
+    const float t = u * tot;
     float acc = 0.0f;
     int k = K - 1;
     for (int j = 0; j < K; ++j) {

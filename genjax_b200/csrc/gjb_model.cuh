@@ -11,6 +11,7 @@
 // G = D/4 lanes to one particle, each lane owning one float4 of every vector
 // value, and reduce the per-lane logpdf partials with warp shuffles.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -25,9 +26,18 @@ __device__ __forceinline__ float as_f(uint32_t w) { return __uint_as_float(w); }
 __device__ __forceinline__ uint32_t as_u(float f) { return __float_as_uint(f); }
 __device__ __forceinline__ uint32_t as_u(int i) { return (uint32_t)i; }
 
-// 4 consecutive 32-bit words starting at element i0 (nv valid), optionally
-// through a gather index per element or broadcast from element 0.
-__device__ __forceinline__ void load4(const void* __restrict__ base, int64_t i0, int nv, const int32_t (&g)[4],
+// coherent (L2) vs read-only-path loads: kCg = true inside the persistent
+// filter kernel, where the buffers were written earlier in the same launch
+template <bool kCg, typename T>
+__device__ __forceinline__ T ldx(const T* p) { return kCg ? __ldcg(p) : __ldg(p); }
+template <bool kCg>
+__device__ __forceinline__ float ldf(const float* p) { return kCg ? __ldcg(p) : __ldg(p); }
+
+// 4 consecutive 32-bit words starting at element i0 (elements u in [lo, hi)
+// valid), optionally through a gather index per element or broadcast from
+// element 0.
+template <bool kCg>
+__device__ __forceinline__ void load4(const void* __restrict__ base, int64_t i0, int lo, int hi, const int32_t (&g)[4],
                                       bool gathered, bool bcast, uint32_t (&w)[4]) {
   const uint32_t* __restrict__ p = reinterpret_cast<const uint32_t*>(base);
   if (bcast) {
@@ -35,39 +45,61 @@ __device__ __forceinline__ void load4(const void* __restrict__ base, int64_t i0,
     w[0] = w[1] = w[2] = w[3] = v;
   } else if (gathered) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) w[u] = (u < nv) ? __ldg(p + g[u]) : 0u;
-  } else if (nv == 4 && ((reinterpret_cast<uintptr_t>(p + i0) & 15) == 0)) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + i0));
+    for (int u = 0; u < 4; ++u) w[u] = (u >= lo && u < hi) ? ldx<kCg>(p + g[u]) : 0u;
+  } else if (lo == 0 && hi == 4 && ((reinterpret_cast<uintptr_t>(p + i0) & 15) == 0)) {
+    const uint4 v = ldx<kCg>(reinterpret_cast<const uint4*>(p + i0));
     w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
   } else {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) w[u] = (u < nv) ? __ldg(p + i0 + u) : 0u;
+    for (int u = 0; u < 4; ++u) w[u] = (u >= lo && u < hi) ? ldx<kCg>(p + i0 + u) : 0u;
   }
 }
 
-__device__ __forceinline__ void load4_idx(const int32_t* __restrict__ gather, int64_t i0, int nv, int32_t (&g)[4]) {
+template <bool kCg>
+__device__ __forceinline__ void load4_idx(const int32_t* __restrict__ gather, int64_t i0, int lo, int hi, int32_t (&g)[4]) {
   if (!gather) {
     g[0] = g[1] = g[2] = g[3] = 0;
     return;
   }
-  if (nv == 4 && ((reinterpret_cast<uintptr_t>(gather + i0) & 15) == 0)) {
-    const int4 v = __ldg(reinterpret_cast<const int4*>(gather + i0));
+  if (lo == 0 && hi == 4 && ((reinterpret_cast<uintptr_t>(gather + i0) & 15) == 0)) {
+    const int4 v = ldx<kCg>(reinterpret_cast<const int4*>(gather + i0));
     g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
   } else {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) g[u] = (u < nv) ? __ldg(gather + i0 + u) : 0;
+    for (int u = 0; u < 4; ++u) g[u] = (u >= lo && u < hi) ? ldx<kCg>(gather + i0 + u) : 0;
   }
 }
 
-__device__ __forceinline__ void store4(void* __restrict__ base, int64_t i0, int nv, const uint32_t (&w)[4]) {
+__device__ __forceinline__ void store4(void* __restrict__ base, int64_t i0, int lo, int hi, const uint32_t (&w)[4]) {
   uint32_t* __restrict__ p = reinterpret_cast<uint32_t*>(base);
-  if (nv == 4 && ((reinterpret_cast<uintptr_t>(p + i0) & 15) == 0)) {
+  if (lo == 0 && hi == 4 && ((reinterpret_cast<uintptr_t>(p + i0) & 15) == 0)) {
     *reinterpret_cast<uint4*>(p + i0) = make_uint4(w[0], w[1], w[2], w[3]);
   } else {
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (u < nv) p[i0 + u] = w[u];
+      if (u >= lo && u < hi) p[i0 + u] = w[u];
   }
+}
+
+// Grid-wide barrier of a persistent cooperative launch (all CTAs resident).
+// Measured on B200 (scratch/barrier_bench.cu, 592 CTAs x 256 threads):
+// cooperative_groups grid.sync 1.7 us, red.release + ld.acquire polling 2.2 us,
+// __threadfence + atomicAdd + volatile polling 3.0 us -- so grid.sync it is.
+__device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t nblocks) {
+  (void)bar; (void)nblocks;
+  cooperative_groups::this_grid().sync();
+}
+
+// CTAs of `fn` that are co-resident on the current device (host side)
+static inline int resident_blocks(const void* fn, int threads, int max_per_sm, int dyn_smem = 0) {
+  int dev = 0, sms = 0, occ = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, dyn_smem);
+  if (occ > max_per_sm) occ = max_per_sm;
+  if (occ < 1) occ = 1;
+  if (sms < 1) sms = 148;
+  return sms * occ;
 }
 
 // block-wide max of the per-thread running max -> atomicMax(wmax)
@@ -126,6 +158,10 @@ __device__ __forceinline__ V4 v4_from(float4 f) { return V4{{f.x, f.y, f.z, f.w}
 __device__ __forceinline__ float4 v4_to(const V4& a) { return make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
 __device__ __forceinline__ V4 v4_load(const float* p) { return v4_from(*reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ V4 v4_ldg(const float* p) { return v4_from(__ldg(reinterpret_cast<const float4*>(p))); }
+template <bool kCg>
+__device__ __forceinline__ V4 v4_ld(const float* p) {
+  return v4_from(kCg ? __ldcg(reinterpret_cast<const float4*>(p)) : __ldg(reinterpret_cast<const float4*>(p)));
+}
 
 #define GJB_V4_BIN(name, expr)                                                               \
   __device__ __forceinline__ V4 name(const V4& a, const V4& b) {                             \
@@ -189,6 +225,18 @@ __device__ __forceinline__ float mvn_diag_logpdf4(const V4& v, const V4& loc, co
   float s = 0.0f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) s += Normal::logpdf(v.v[k], loc.v[k], scale.v[k]);
+  return s;
+}
+
+// same with the particle-invariant pieces precomputed: inv = 1/scale (this
+// lane's 4 elements), lc = sum over those elements of 0.5 log 2pi + log scale
+__device__ __forceinline__ float mvn_diag_logpdf4_r(const V4& v, const V4& loc, const V4& inv, float lc) {
+  float s = -lc;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float z = v.v[k] * inv.v[k] - loc.v[k] * inv.v[k];
+    s -= 0.5f * (z * z);
+  }
   return s;
 }
 

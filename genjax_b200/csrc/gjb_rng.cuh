@@ -69,6 +69,21 @@ __device__ __forceinline__ float4 normal4(const Lane& l, uint32_t site, uint32_t
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// ---- quad streams: SCALAR sites share one Philox block between the 4
+// consecutive particles of a global quad (idx >> 2); particle idx takes slot
+// idx & 3 (word for uniform-driven samplers, normal4 component for normals).
+// Vector sites and rejection samplers keep one stream per particle (Lane).
+__device__ __forceinline__ uint4 quad_words(uint32_t k0, uint32_t k1, uint64_t quad, uint32_t site, uint32_t chunk = 0) {
+  return philox4x32_10(make_uint4((uint32_t)quad, (uint32_t)(quad >> 32), chunk, site), k0, k1);
+}
+__device__ __forceinline__ float4 normal4_of(const uint4& w) {
+  const float2 a = box_muller(w.x, w.y);
+  const float2 b = box_muller(w.z, w.w);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ uint32_t pick(const uint4& w, int s) { return s == 0 ? w.x : (s == 1 ? w.y : (s == 2 ? w.z : w.w)); }
+__device__ __forceinline__ float pick(const float4& w, int s) { return s == 0 ? w.x : (s == 1 ? w.y : (s == 2 ? w.z : w.w)); }
+
 // ordered-uint encoding of a float for atomicMax
 __device__ __forceinline__ uint32_t fenc(float f) {
   const uint32_t b = __float_as_uint(f);

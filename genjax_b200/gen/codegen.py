@@ -1,19 +1,31 @@
 """ModelIR -> one CUDA translation unit (sm_100a) exporting the per-model
 C-ABI of include/genjax_b200.h (``gjb_model_info`` / ``gjb_model_launch`` /
-``gjb_model_mh_chain`` / ``gjb_model_hmc_chain``).
+``gjb_model_pf_run`` / ``gjb_model_mh_chain`` / ``gjb_model_hmc_chain``).
 
-The generated ``model_kernel`` is the fused, batched form of the reference's
+The generated per-particle body is the fused, batched form of the reference's
 static-language handlers (static.py:254-278, 298-321, 341-380, 407-466,
 616-673): sites are visited in program order; per-site launch flags choose
 sample-vs-read and whether the site's logpdf joins the importance weight, so
-ONE kernel serves simulate / assess / generate / update / regenerate.
+ONE body serves simulate / assess / generate / update / regenerate.  It is
+instantiated twice:
+
+  * ``model_kernel``  one GFI call over n particles (grid-stride, one wave);
+  * ``pf_kernel``     the whole T-step bootstrap particle filter as ONE
+    persistent cooperative launch: per step (A) ancestor gather + propose +
+    logpdf + running max, (B) exact integer weight mass per CTA, (C) CDF scan
+    + systematic offspring ranges, separated by grid barriers.
 
 Two thread mappings:
-  * "quad"  (all-scalar models or odd event widths): a thread owns 4
-    consecutive particles, 128-bit loads/stores of every [N] array;
+  * "quad"  (all-scalar models or odd event widths): a thread owns the 4
+    consecutive particles of a global quad, 128-bit loads/stores of every [N]
+    array, ONE Philox block per (quad, sampled site);
   * "group" (event width D, D % 4 == 0, D/4 a power of two <= 32): G = D/4
     lanes own one particle, each lane one float4 of every width-D value;
     logpdf partials are reduced with warp shuffles.
+
+Particle-invariant sub-expressions (functions of constants, scalar and shared
+arguments only: 1/scale, log scale, table rows ...) are hoisted out of the
+particle loop into a per-thread ``Uni`` struct computed once per launch.
 """
 
 from __future__ import annotations
@@ -46,18 +58,43 @@ def group_lanes(width: int) -> int:
 
 class _Emitter:
     """Emits the per-particle body.  ``group`` selects lane-distributed V4
-    vectors (True) or per-thread float arrays (False)."""
+    vectors (True) or per-thread float arrays (False).  Values that do not
+    depend on particle data are emitted into the ``Uni`` struct instead."""
 
     def __init__(self, ir: ModelIR, group: bool):
         self.ir = ir
         self.group = group
         self.D = ir.width
-        self.lines: list[str] = []
+        self.lines: list[str] = []  # per-particle body
+        self.uni_decl: list[str] = []  # members of struct Uni
+        self.uni_init: list[str] = []  # statements of make_uni()
         self.names: dict[int, str] = {}
-        self.consts: list[str] = []  # namespace-scope __constant__ arrays
+        self.consts: list[str] = []  # namespace-scope constant arrays
+        self._uniform: dict[int, bool] = {}
+        self._v4cache: dict[int, str] = {}
+        self.n_tmp = 0
 
     def w(self, s: str):
         self.lines.append("      " + s)
+
+    def fresh(self, prefix="e") -> str:
+        self.n_tmp += 1
+        return f"{prefix}{self.n_tmp}"
+
+    # ---- classification
+    def is_uniform(self, e: Expr) -> bool:
+        u = self._uniform.get(e._id)
+        if u is None:
+            if e.op in ("const", "constvec"):
+                u = True
+            elif e.op == "arg":
+                u = e.attr["kind"] != "particle"
+            elif e.op == "site":
+                u = False
+            else:
+                u = all(self.is_uniform(i) for i in e.ins)
+            self._uniform[e._id] = u
+        return u
 
     # ---- type helpers
     def ctype(self, e: Expr) -> str:
@@ -70,11 +107,6 @@ class _Emitter:
     @staticmethod
     def _is_shared_vec(e: Expr) -> bool:
         return e.op == "arg" and e.attr["kind"] == "shared"
-
-    def is_ptr_vec(self, e: Expr) -> bool:
-        """Vector values that live behind a pointer (indexable as name[k])."""
-        return e.ndim == 1 and (e.op in ("row", "constvec") or self._is_shared_vec(e) or not self.group
-                                or e.shape[0] != self.D)
 
     def ref(self, e: Expr) -> str:
         return self.names[e._id]
@@ -91,12 +123,24 @@ class _Emitter:
             return f"gjb::v4_splat((float){self.ref(e)})"
         if self.ctype(e) == "gjb::V4":
             return self.ref(e)
-        # pointer vector of width D: this lane's 4 elements
-        return f"gjb::v4_load({self.ref(e)} + 4 * lane)" if self._aligned_ptr(e) else (
-            f"gjb::V4{{{{{self.ref(e)}[4*lane], {self.ref(e)}[4*lane+1], {self.ref(e)}[4*lane+2], {self.ref(e)}[4*lane+3]}}}}")
+        # pointer vector of width D: this lane's 4 elements, loaded once per launch when particle-invariant
+        r = self.ref(e)
+        load = (f"gjb::v4_load({r} + 4 * lane)" if self._is_shared_vec(e) else
+                f"gjb::V4{{{{{r}[4*lane], {r}[4*lane+1], {r}[4*lane+2], {r}[4*lane+3]}}}}")
+        if not self.is_uniform(e):
+            return load
+        c = self._v4cache.get(e._id)
+        if c is None:
+            c = self.fresh("v")
+            self.uni_decl.append(f"  gjb::V4 {c};")
+            self.uni_init.append(f"  U.{c} = {load.replace(r, self._uni_local(r))};")
+            c = f"U.{c}"
+            self._v4cache[e._id] = c
+        return c
 
-    def _aligned_ptr(self, e: Expr) -> bool:
-        return self._is_shared_vec(e)
+    @staticmethod
+    def _uni_local(name: str) -> str:
+        return name
 
     # ---- expression emission
     def emit_expr(self, e: Expr):
@@ -104,7 +148,6 @@ class _Emitter:
             return
         for i in e.ins:
             self.emit_expr(i)
-        n = f"e{len(self.names)}"
         op = e.op
         if op == "const":
             self.names[e._id] = E.fmt_float(e.attr) if e.dtype == F32 else str(int(e.attr))
@@ -121,53 +164,77 @@ class _Emitter:
             self.consts.append(f"__device__ const float {cname}[{len(e.attr)}] = {{{vals}}};")
             self.names[e._id] = cname
             return
-        self.names[e._id] = n
+        uni = self.is_uniform(e)
+        n = self.fresh("h" if uni else "e")
         t = self.ctype(e)
+
+        def out(decl_type: str, rhs: str, array: int = 0):
+            """define value `n` (in Uni or in the body)"""
+            if uni:
+                self.uni_decl.append(f"  {decl_type} {n}{f'[{array}]' if array else ''};")
+                self.names[e._id] = f"U.{n}"
+            else:
+                self.names[e._id] = n
+            return f"U.{n}" if uni else n
+
+        emit = self.uni_init.append if uni else self.w
+        pad = "  " if uni else ""
         if op == "row":
             mat, idx = e.ins
             K = mat.shape[1]
-            self.w(f"const float* {n} = {self.ref(mat)} + (int)({self.ref(idx)}) * {K};")
+            nm = out("const float*", "")
+            emit(f"{pad}{'' if uni else 'const float* '}{nm} = {self.ref(mat)} + (int)({self.ref(idx)}) * {K};")
             return
         if op == "gather1":
             vec, idx = e.ins
-            self.w(f"const float {n}_f = {self.ref(vec)}[(int)({self.ref(idx)})];")
+            ct = "int" if e.dtype == I32 else "float"
+            nm = out(ct, "")
+            val = f"{self.ref(vec)}[(int)({self.ref(idx)})]"
             if e.dtype == I32:
-                self.w(f"const int {n} = __float_as_int({n}_f);")
-            else:
-                self.w(f"const float {n} = {n}_f;")
+                val = f"__float_as_int({val})"
+            emit(f"{pad}{'' if uni else 'const ' + ct + ' '}{nm} = {val};")
             return
         if op == "elem":
             (vec,) = e.ins
             j = int(e.attr)
+            nm = out("float", "")
             if self.ctype(vec) == "gjb::V4":
-                self.w(f"const float {n} = __shfl_sync(0xffffffffu, {self.ref(vec)}.v[{j % 4}], (threadIdx.x & 31 & ~(G - 1)) + {j // 4});")
+                val = f"__shfl_sync(0xffffffffu, {self.ref(vec)}.v[{j % 4}], (threadIdx.x & 31 & ~(G - 1)) + {j // 4})"
             else:
-                self.w(f"const float {n} = {self.ref(vec)}[{j}];")
+                val = f"{self.ref(vec)}[{j}]"
+            emit(f"{pad}{'' if uni else 'const float '}{nm} = {val};")
             return
         if op == "sum":
             (x,) = e.ins
+            nm = out("float", "")
             if self.ctype(x) == "gjb::V4":
-                self.w(f"const float {n} = gjb::group_sum<G>(gjb::v4_hsum({self.ref(x)}));")
+                emit(f"{pad}{'' if uni else 'const float '}{nm} = gjb::group_sum<G>(gjb::v4_hsum({self.ref(x)}));")
             else:
                 K = x.shape[0]
-                self.w(f"float {n} = 0.0f;")
-                self.w(f"for (int k = 0; k < {K}; ++k) {n} += {self.ref(x)}[k];")
+                emit(f"{pad}{'' if uni else 'float '}{nm} = 0.0f;")
+                emit(f"{pad}for (int k = 0; k < {K}; ++k) {nm} += {self.ref(x)}[k];")
             return
         if op == "cast":
             (x,) = e.ins
             if t in ("int", "float"):
-                self.w(f"const {t} {n} = ({t}){self.ref(x)};")
+                nm = out(t, "")
+                emit(f"{pad}{'' if uni else 'const ' + t + ' '}{nm} = ({t}){self.ref(x)};")
                 return
             raise NotImplementedError("vector casts")
         # elementwise ----------------------------------------------------
         if t in ("int", "float"):
-            self.w(f"const {t} {n} = {self.scalar_rhs(e, None)};")
+            nm = out(t, "")
+            emit(f"{pad}{'' if uni else 'const ' + t + ' '}{nm} = {self.scalar_rhs(e, None)};")
         elif t == "gjb::V4":
-            self.w(f"const gjb::V4 {n} = {self.v4_rhs(e)};")
+            rhs = self.v4_rhs(e)
+            nm = out("gjb::V4", "")
+            emit(f"{pad}{'' if uni else 'const gjb::V4 '}{nm} = {rhs};")
         else:
             K = e.shape[0]
-            self.w(f"float {n}[{K}];")
-            self.w(f"for (int k = 0; k < {K}; ++k) {n}[k] = {self.scalar_rhs(e, 'k')};")
+            nm = out("float", "", array=K)
+            if not uni:
+                emit(f"float {nm}[{K}];")
+            emit(f"{pad}for (int k = 0; k < {K}; ++k) {nm}[k] = {self.scalar_rhs(e, 'k')};")
 
     def scalar_rhs(self, e: Expr, k) -> str:
         r = (lambda x: self.elem_ref(x, k)) if k is not None else self.ref
@@ -201,12 +268,42 @@ class _Emitter:
         i = e.attr["index"]
         kind = e.attr["kind"]
         if kind == "scalar":
-            return f"((int)A.scalars[{i}])" if e.dtype == I32 else f"A.scalars[{i}]"
+            return f"((int)U.sc[{i}])" if e.dtype == I32 else f"U.sc[{i}]"
         if kind == "shared":
             if e.ndim == 0:
                 return f"(__float_as_int(sh{i}[0]))" if e.dtype == I32 else f"sh{i}[0]"
             return f"sh{i}"
         return f"a{i}"  # particle arg: local loaded before the body
+
+    # ---- particle-invariant pieces of the Normal family ----------------
+    def normal_consts(self, j: int, scale: Expr, vec_width: int = 0) -> tuple[str, str]:
+        """(inv, lc) names: inv = 1/scale, lc = sum_k (0.5 log 2pi + log scale_k); hoisted when scale is uniform."""
+        uni = self.is_uniform(scale)
+        emit = self.uni_init.append if uni else self.w
+        pad = "  " if uni else ""
+        pre = "U." if uni else ""
+        inv, lc = f"inv{j}", f"lc{j}"
+        if vec_width == 0:
+            if uni:
+                self.uni_decl.append(f"  float {inv}, {lc};")
+            emit(f"{pad}{'' if uni else 'const float '}{pre}{inv} = 1.0f / {self.ref(scale)};")
+            emit(f"{pad}{'' if uni else 'const float '}{pre}{lc} = gjb::kHalfLog2Pi + logf({self.ref(scale)});")
+        elif self.group:
+            if uni:
+                self.uni_decl.append(f"  gjb::V4 {inv}; float {lc};")
+            sv = self.as_v4(scale)
+            emit(f"{pad}{'' if uni else 'const gjb::V4 '}{pre}{inv} = gjb::f_reciprocal({sv});")
+            emit(f"{pad}{'' if uni else 'const float '}{pre}{lc} = gjb::v4_hsum(gjb::kHalfLog2Pi + gjb::f_log({sv}));")
+        else:
+            D = vec_width
+            if uni:
+                self.uni_decl.append(f"  float {inv}[{D}]; float {lc};")
+            else:
+                emit(f"float {inv}[{D}]; float {lc};")
+            emit(f"{pad}{pre}{lc} = 0.0f;")
+            emit(f"{pad}for (int k = 0; k < {D}; ++k) {{ {pre}{inv}[k] = 1.0f / {self.elem_ref(scale, 'k')}; "
+                 f"{pre}{lc} += gjb::kHalfLog2Pi + logf({self.elem_ref(scale, 'k')}); }}")
+        return pre + inv, pre + lc
 
     # ---- sites
     def emit_site(self, s):
@@ -214,7 +311,7 @@ class _Emitter:
         j = s.index
         for a in s.args:
             self.emit_expr(a)
-        fl = f"fl{j}"
+        fl = f"FL({j})"
         need = f"(need_score || ({fl} & GJB_SITE_WEIGHT))"
         self.w(f"// site {j} {'/'.join(map(str, s.addr))!r}: {d.name}")
         if not d.vector:
@@ -226,23 +323,29 @@ class _Emitter:
                 a = [self.ref(x) for x in s.args]
             self.w(f"{vt} s{j};")
             self.w(f"if ({fl} & GJB_SITE_SAMPLE) s{j} = {d.emit_sample(j, a, self)}; else s{j} = in_s{j};")
-            self.w(f"if {need} {{ const float lp = {d.emit_logpdf(f's{j}', a, self)}; score += lp; if ({fl} & GJB_SITE_WEIGHT) weight += lp; }}")
+            if d.name == "normal":
+                inv, lc = self.normal_consts(j, s.args[1])
+                lp = f"gjb::Normal::logpdf_r(s{j}, {a[0]}, {inv}, {lc})"
+            else:
+                lp = d.emit_logpdf(f"s{j}", a, self)
+            self.w(f"if {need} {{ const float lp = {lp}; score += lp; if ({fl} & GJB_SITE_WEIGHT) weight += lp; }}")
             return
         if d.name != "mv_normal_diag":
             raise NotImplementedError(d.name)
         loc, scale = s.args
         D = s.value.shape[0]
+        inv, lc = self.normal_consts(j, scale, vec_width=D)
         if self.group:
             self.w(f"gjb::V4 s{j};")
             self.w(f"if ({fl} & GJB_SITE_SAMPLE) s{j} = gjb::mvn_diag_sample(rng, {j + 1}u, (uint32_t)lane, {self.as_v4(loc)}, {self.as_v4(scale)}); else s{j} = in_s{j};")
-            self.w(f"if {need} {{ const float lp = gjb::mvn_diag_logpdf4(s{j}, {self.as_v4(loc)}, {self.as_v4(scale)}); vscore += lp; if ({fl} & GJB_SITE_WEIGHT) vweight += lp; }}")
+            self.w(f"if {need} {{ const float lp = gjb::mvn_diag_logpdf4_r(s{j}, {self.as_v4(loc)}, {inv}, {lc}); vscore += lp; if ({fl} & GJB_SITE_WEIGHT) vweight += lp; }}")
         else:
             self.w(f"float s{j}[{D}];")
             self.w(f"if ({fl} & GJB_SITE_SAMPLE) {{")
             self.w(f"  for (int c = 0; c < {(D + 3) // 4}; ++c) {{ const float4 z = gjb::normal4(rng, {j + 1}u, (uint32_t)c); const float zz[4] = {{z.x, z.y, z.z, z.w}};")
             self.w(f"    for (int t = 0; t < 4; ++t) {{ const int k = 4 * c + t; if (k < {D}) s{j}[k] = {self.elem_ref(loc, 'k')} + {self.elem_ref(scale, 'k')} * zz[t]; }} }}")
             self.w(f"}} else {{ for (int k = 0; k < {D}; ++k) s{j}[k] = in_s{j}[k]; }}")
-            self.w(f"if {need} {{ float lp = 0.0f; for (int k = 0; k < {D}; ++k) lp += gjb::Normal::logpdf(s{j}[k], {self.elem_ref(loc, 'k')}, {self.elem_ref(scale, 'k')}); score += lp; if ({fl} & GJB_SITE_WEIGHT) weight += lp; }}")
+            self.w(f"if {need} {{ float lp = -{lc}; for (int k = 0; k < {D}; ++k) {{ const float z = s{j}[k] * {inv}[k] - {self.elem_ref(loc, 'k')} * {inv}[k]; lp -= 0.5f * (z * z); }} score += lp; if ({fl} & GJB_SITE_WEIGHT) weight += lp; }}")
 
 
 def _info_json(ir: ModelIR, mapping: str, G: int) -> str:
@@ -263,6 +366,7 @@ def _info_json(ir: ModelIR, mapping: str, G: int) -> str:
 
 
 def _shared_decls(ir: ModelIR) -> tuple[list[str], list[str]]:
+    """namespace-scope __shared__ blocks for the shared (un-batched) arguments + their staging calls."""
     decl, stage = [], []
     for i, a in enumerate(ir.args):
         if a.kind == "shared":
@@ -270,263 +374,485 @@ def _shared_decls(ir: ModelIR) -> tuple[list[str], list[str]]:
             for d in a.shape:
                 n *= d
             n = max(n, 1)
-            decl.append(f"  __shared__ __align__(16) float sh{i}[{(n + 3) // 4 * 4}];")
-            stage.append(f"  gjb::stage_shared(sh{i}, A.args[{i}], {n});")
+            decl.append(f"__shared__ __align__(16) float sh{i}[{(n + 3) // 4 * 4}];")
+            stage.append(f"  gjb::stage_shared(sh{i}, ARGS[{i}], {n});")
     return decl, stage
 
 
-def generate(ir: ModelIR) -> str:
+def generate(ir: ModelIR, pf_obs: tuple | None = None) -> str:
+    """CUDA source for ``ir``.  ``pf_obs`` (site indices observed at every
+    filter step) bakes the per-site flags of the persistent filter kernel in at
+    compile time, so the paths a bootstrap filter never takes (reading proposed
+    sites, scoring unweighted ones) are removed from ``pf_kernel``."""
     G = group_lanes(ir.width)
-    if G:
-        # categorical tables etc. are allowed only as pointer vectors; everything of width D is lane-distributed
-        return _generate_group(ir, G)
-    return _generate_quad(ir)
+    gen = _Generator(ir, G, pf_obs)
+    return gen.source()
 
 
-# ============================================================== quad mapping
+class _Generator:
+    def __init__(self, ir: ModelIR, G: int, pf_obs: tuple | None = None):
+        self.ir = ir
+        self.G = G
+        self.pf_obs = None if pf_obs is None else tuple(sorted(int(j) for j in pf_obs))
+        self.group = G > 0
+        self.em = _Emitter(ir, group=self.group)
+        self.ns = len(ir.sites)
+        self.na = max(len(ir.args), 1)
+        self.nr = max(len(ir.ret_leaves), 1)
+        em = self.em
+        for s in ir.sites:
+            em.emit_site(s)
+        self.ret_names = []
+        for r in ir.ret_leaves:
+            if isinstance(r, Expr):
+                em.emit_expr(r)
+                if self.group:
+                    self.ret_names.append(em.ref(r) if r.ndim == 0 else em.as_v4(r))
+                else:
+                    self.ret_names.append(em.ref(r))
+            else:
+                self.ret_names.append(E.fmt_float(float(r)))
+        self.body = "\n".join(em.lines)
+        self.needs_lane = any(s.dist.rng_kind == "lane" for s in ir.sites)
 
-
-def _generate_quad(ir: ModelIR) -> str:
-    em = _Emitter(ir, group=False)
-    ns = len(ir.sites)
-    out: list[str] = []
-    decl, stage = _shared_decls(ir)
-
-    # body ----------------------------------------------------------------
-    for s in ir.sites:
-        em.emit_site(s)
-    ret_names = []
-    for r in ir.ret_leaves:
-        if isinstance(r, Expr):
-            em.emit_expr(r)
-            ret_names.append(em.ref(r))
+    # ------------------------------------------------------------ pieces
+    def header(self) -> list[str]:
+        ir, em = self.ir, self.em
+        decl, stage = _shared_decls(ir)
+        self.stage = stage
+        out = [f"// generated by genjax_b200.gen.codegen -- model '{ir.name}' [{ir.digest}] "
+               f"({'group mapping, G=%d' % self.G if self.group else 'quad mapping'})",
+               '#include "gjb_model.cuh"', '#include "gjb_resample.cuh"', "namespace {"]
+        out.extend(em.consts)
+        out.append("constexpr int kThreads = 256;")
+        out.append(f"constexpr int kPfMinBlocks = {3 if self.group else 4};  // CTAs per SM the filter kernel is compiled for")
+        out.append("constexpr int kPfCacheTiles = 2;  // tiles per CTA whose masses stay in shared memory between phases")
+        out.append(f"constexpr int NS = {max(self.ns, 1)}, NA = {self.na}, NR = {self.nr};")
+        if self.group:
+            out.append(f"constexpr int G = {self.G};")
+            out.append("constexpr int kPPB = kThreads / G;  // particles per block iteration")
+        out.extend(decl)
+        if self.pf_obs is not None:
+            vals = ", ".join("(GJB_SITE_WEIGHT | GJB_SITE_BCAST)" if j in self.pf_obs else "GJB_SITE_SAMPLE"
+                             for j in range(self.ns)) or "0u"
         else:
-            ret_names.append(E.fmt_float(float(r)))
-    body = "\n".join(em.lines)
+            vals = ", ".join("0u" for _ in range(max(self.ns, 1)))
+        out.append(f"__device__ constexpr uint32_t kPfFl[NS] = {{{vals}}};  // flags baked into pf_kernel")
+        out.append(f"constexpr uint32_t kPfFl_host[NS] = {{{vals}}};")
+        out.append(f"constexpr bool kPfStatic = {'true' if self.pf_obs is not None else 'false'};")
+        out.append("#define FL(j) (kSt ? kPfFl[j] : fl[j])")
+        out.append("struct Io {  // what one launch (or one filter step) reads and writes")
+        out.append("  const void* args[NA]; const void* site_in[NS]; void* site_out[NS]; void* ret_out[NR];")
+        out.append("  const int32_t* gather; const float* score_in; const float* weight_in; float* score_out; float* weight_out;")
+        out.append("};")
+        out.append("struct Uni {  // particle-invariant values, computed once per thread per launch")
+        out.append("  float sc[NA];")
+        out.extend(em.uni_decl)
+        out.append("};")
+        out.append("__device__ __forceinline__ void make_uni(Uni& U, const float* __restrict__ scalars) {")
+        if self.group:
+            out.append("  const int lane = threadIdx.x & (G - 1); (void)lane;")
+        out.append("  for (int i = 0; i < NA; ++i) U.sc[i] = scalars[i];")
+        out.extend(em.uni_init)
+        out.append("}")
+        return out
 
-    P = ["struct P {"]
-    pre: list[str] = []   # loads before the body (per quad)
-    bind: list[str] = []  # per-u local bindings
-    post: list[str] = []  # stores after the body
-    save: list[str] = []  # per-u saves into P
-    for i, a in enumerate(ir.args):
-        if a.kind != "particle":
-            continue
-        ct = "int" if a.dtype == I32 else "float"
-        if a.shape == ():
-            P.append(f"  {ct} a{i};")
-            conv = "(int)w[u]" if a.dtype == I32 else "gjb::as_f(w[u])"
-            pre.append(f"    gjb::load4(A.args[{i}], i0, nv, g, A.gather != nullptr, false, w);")
-            pre.append(f"    for (int u = 0; u < 4; ++u) p[u].a{i} = {conv};")
-            bind.append(f"      const {ct} a{i} = p[u].a{i};")
-        else:
-            D = a.shape[0]
-            P.append(f"  float a{i}[{D}];")
-            pre.append(f"    for (int u = 0; u < 4; ++u) {{ const int64_t row = A.gather ? (int64_t)g[u] : i0 + u;")
-            pre.append(f"      for (int k = 0; k < {D}; ++k) p[u].a{i}[k] = (u < nv) ? __ldg(reinterpret_cast<const float*>(A.args[{i}]) + row * {D} + k) : 0.0f; }}")
-            bind.append(f"      const float* a{i} = p[u].a{i};")
-    for s in ir.sites:
-        j = s.index
-        ct = "int" if s.value.dtype == I32 else "float"
-        if s.value.ndim == 0:
-            P.append(f"  {ct} s{j};")
-            conv = "(int)w[u]" if s.value.dtype == I32 else "gjb::as_f(w[u])"
-            pre.append(f"    if (!(fl{j} & GJB_SITE_SAMPLE)) {{ gjb::load4(A.site_in[{j}], i0, nv, g0, false, (fl{j} & GJB_SITE_BCAST) != 0, w);")
-            pre.append(f"      for (int u = 0; u < 4; ++u) p[u].s{j} = {conv}; }}")
-            bind.append(f"      const {ct} in_s{j} = p[u].s{j};")
-            save.append(f"      p[u].s{j} = s{j};")
-            post.append(f"    if (A.site_out[{j}]) {{ for (int u = 0; u < 4; ++u) w[u] = gjb::as_u(p[u].s{j}); gjb::store4(A.site_out[{j}], i0, nv, w); }}")
-        else:
-            D = s.value.shape[0]
-            P.append(f"  float s{j}[{D}];")
-            pre.append(f"    if (!(fl{j} & GJB_SITE_SAMPLE)) {{ for (int u = 0; u < 4; ++u) for (int k = 0; k < {D}; ++k)")
-            pre.append(f"      p[u].s{j}[k] = (u < nv) ? __ldg(reinterpret_cast<const float*>(A.site_in[{j}]) + ((fl{j} & GJB_SITE_BCAST) ? 0 : (i0 + u) * {D}) + k) : 0.0f; }}")
-            bind.append(f"      const float* in_s{j} = p[u].s{j};")
-            save.append(f"      for (int k = 0; k < {D}; ++k) p[u].s{j}[k] = s{j}[k];")
-            post.append(f"    if (A.site_out[{j}]) {{ for (int u = 0; u < nv; ++u) for (int k = 0; k < {D}; ++k) reinterpret_cast<float*>(A.site_out[{j}])[(i0 + u) * {D} + k] = p[u].s{j}[k]; }}")
-    for k, r in enumerate(ir.ret_leaves):
-        is_vec = isinstance(r, Expr) and r.ndim == 1
-        is_int = isinstance(r, Expr) and r.dtype == I32
-        if is_vec:
-            D = r.shape[0]
-            P.append(f"  float r{k}[{D}];")
-            save.append(f"      for (int k = 0; k < {D}; ++k) p[u].r{k}[k] = {ret_names[k]}[k];")
-            post.append(f"    if (A.ret_out[{k}]) {{ for (int u = 0; u < nv; ++u) for (int k = 0; k < {D}; ++k) reinterpret_cast<float*>(A.ret_out[{k}])[(i0 + u) * {D} + k] = p[u].r{k}[k]; }}")
-        else:
-            P.append(f"  {'int' if is_int else 'float'} r{k};")
-            save.append(f"      p[u].r{k} = {ret_names[k]};")
-            post.append(f"    if (A.ret_out[{k}]) {{ for (int u = 0; u < 4; ++u) w[u] = gjb::as_u(p[u].r{k}); gjb::store4(A.ret_out[{k}], i0, nv, w); }}")
-    P.append("  float score, weight;")
-    P.append("};")
+    def stage_lines(self, args_expr: str) -> list[str]:
+        if not self.stage:
+            return []
+        return [s.replace("ARGS", args_expr) for s in self.stage] + ["  __syncthreads();"]
 
-    out.append(f"// generated by genjax_b200.gen.codegen -- model '{ir.name}' [{ir.digest}] (quad mapping)")
-    out.append('#include "gjb_model.cuh"')
-    out.append("namespace {")
-    out.extend(em.consts)
-    out.extend(P)
-    out.append("constexpr int kThreads = 256;")
-    out.append("__global__ void __launch_bounds__(kThreads) model_kernel(const __grid_constant__ gjb_model_args A) {")
-    out.extend(decl)
-    out.extend(stage)
-    if stage:
-        out.append("  __syncthreads();")
-    for j in range(ns):
-        out.append(f"  const uint32_t fl{j} = A.site_flags[{j}];")
-    out.append("  const bool need_score = A.score_out != nullptr;")
-    out.append("  const uint32_t key0 = A.key_dev ? __ldg(A.key_dev) : A.key0, key1 = A.key_dev ? __ldg(A.key_dev + 1) : A.key1;")
-    out.append("  float run_max = -INFINITY;")
-    out.append("  const int32_t g0[4] = {0, 0, 0, 0};")
-    out.append("  const int64_t nq = (A.n + 3) >> 2;")
-    out.append("  for (int64_t q = blockIdx.x * (int64_t)kThreads + threadIdx.x; q < nq; q += (int64_t)gridDim.x * kThreads) {")
-    out.append("    const int64_t i0 = q << 2;")
-    out.append("    const int nv = (A.n - i0) < 4 ? (int)(A.n - i0) : 4;")
-    out.append("    P p[4];")
-    out.append("    int32_t g[4];")
-    out.append("    gjb::load4_idx(A.gather, i0, nv, g);")
-    out.append("    uint32_t w[4];")
-    out.append("    (void)g0; (void)w;")
-    out.extend(pre)
-    out.append("#pragma unroll")
-    out.append("    for (int u = 0; u < 4; ++u) {")
-    out.append("      const gjb::Lane rng = gjb::make_lane(key0, key1, A.idx_offset + (uint64_t)(i0 + u));")
-    out.append("      (void)rng;")
-    out.append("      float score = 0.0f, weight = 0.0f;")
-    out.extend(bind)
-    out.append(body)
-    out.extend(save)
-    out.append("      p[u].score = score; p[u].weight = weight;")
-    out.append("    }")
-    out.extend(post)
-    out.append("    if (A.score_out) { for (int u = 0; u < 4; ++u) w[u] = gjb::as_u(p[u].score); gjb::store4(A.score_out, i0, nv, w); }")
-    out.append("    if (A.weight_out || A.wmax) {")
-    out.append("      uint32_t wi[4] = {0u, 0u, 0u, 0u}, si[4] = {0u, 0u, 0u, 0u};")
-    out.append("      if (A.weight_in) gjb::load4(A.weight_in, i0, nv, g0, false, false, wi);")
-    out.append("      if (A.score_in) gjb::load4(A.score_in, i0, nv, g0, false, false, si);")
-    out.append("      for (int u = 0; u < 4; ++u) {")
-    out.append("        float t = p[u].weight;")
-    out.append("        if (A.weight_in) t = gjb::as_f(wi[u]) + t;")
-    out.append("        if (A.score_in) t = t - gjb::as_f(si[u]);")
-    out.append("        w[u] = gjb::as_u(t);")
-    out.append("        if (u < nv) run_max = fmaxf(run_max, t);")
-    out.append("      }")
-    out.append("      if (A.weight_out) gjb::store4(A.weight_out, i0, nv, w);")
-    out.append("    }")
-    out.append("  }")
-    out.append("  if (A.wmax) gjb::block_wmax(run_max, A.wmax);")
-    out.append("}")
-    out.append("}  // namespace")
-    out.append(_extern_c(ir, "quad", 1, work_per_thread=4))
-    return "\n".join(out) + "\n"
-
-
-# ============================================================= group mapping
-
-
-def _generate_group(ir: ModelIR, G: int) -> str:
-    em = _Emitter(ir, group=True)
-    D = ir.width
-    ns = len(ir.sites)
-    decl, stage = _shared_decls(ir)
-    for s in ir.sites:
-        em.emit_site(s)
-    ret_names = []
-    for r in ir.ret_leaves:
-        if isinstance(r, Expr):
-            em.emit_expr(r)
-            ret_names.append(em.ref(r) if r.ndim == 0 else em.as_v4(r))
-        else:
-            ret_names.append(E.fmt_float(float(r)))
-    body = "\n".join(em.lines)
-
-    pre: list[str] = []
-    post: list[str] = []
-    for i, a in enumerate(ir.args):
-        if a.kind != "particle":
-            continue
-        if a.shape == ():
+    # ------------------------------------------------------------- quads
+    def run_quads(self) -> list[str]:
+        ir = self.ir
+        P = ["struct P {"]
+        pre: list[str] = []
+        bind: list[str] = []
+        post: list[str] = []
+        save: list[str] = []
+        for i, a in enumerate(ir.args):
+            if a.kind != "particle":
+                continue
             ct = "int" if a.dtype == I32 else "float"
-            cast = "const int*" if a.dtype == I32 else "const float*"
-            pre.append(f"      const {ct} a{i} = valid ? __ldg(reinterpret_cast<{cast}>(A.args[{i}]) + row) : 0;")
-        else:
-            pre.append(f"      const gjb::V4 a{i} = valid ? gjb::v4_ldg(reinterpret_cast<const float*>(A.args[{i}]) + row * {D} + 4 * lane) : gjb::v4_splat(0.0f);")
-    for s in ir.sites:
-        j = s.index
-        if s.value.ndim == 0:
+            if a.shape == ():
+                P.append(f"  {ct} a{i};")
+                conv = "(int)w[u]" if a.dtype == I32 else "gjb::as_f(w[u])"
+                pre.append(f"    gjb::load4<kCg>(io.args[{i}], i0, lo, hi, g, io.gather != nullptr, false, w);")
+                pre.append(f"    for (int u = 0; u < 4; ++u) p[u].a{i} = {conv};")
+                bind.append(f"      const {ct} a{i} = p[u].a{i};")
+            else:
+                D = a.shape[0]
+                P.append(f"  float a{i}[{D}];")
+                pre.append(f"    for (int u = 0; u < 4; ++u) {{ const int64_t row = io.gather ? (int64_t)g[u] : i0 + u;")
+                pre.append(f"      for (int k = 0; k < {D}; ++k) p[u].a{i}[k] = (u >= lo && u < hi) ? gjb::ldf<kCg>(reinterpret_cast<const float*>(io.args[{i}]) + row * {D} + k) : 0.0f; }}")
+                bind.append(f"      const float* a{i} = p[u].a{i};")
+        for s in ir.sites:
+            j = s.index
             ct = "int" if s.value.dtype == I32 else "float"
-            cast = "const int*" if s.value.dtype == I32 else "const float*"
-            pre.append(f"      {ct} in_s{j} = 0;")
-            pre.append(f"      if (!(fl{j} & GJB_SITE_SAMPLE) && valid) in_s{j} = __ldg(reinterpret_cast<{cast}>(A.site_in[{j}]) + ((fl{j} & GJB_SITE_BCAST) ? 0 : i));")
-            post.append(f"      if (A.site_out[{j}] && valid && lane == 0) reinterpret_cast<{ct}*>(A.site_out[{j}])[i] = s{j};")
+            if s.value.ndim == 0:
+                P.append(f"  {ct} s{j};")
+                conv = "(int)w[u]" if s.value.dtype == I32 else "gjb::as_f(w[u])"
+                pre.append(f"    if (!(FL({j}) & GJB_SITE_SAMPLE)) {{ gjb::load4<false>(io.site_in[{j}], i0, lo, hi, g0, false, (FL({j}) & GJB_SITE_BCAST) != 0, w);")
+                pre.append(f"      for (int u = 0; u < 4; ++u) p[u].s{j} = {conv}; }}")
+                bind.append(f"      const {ct} in_s{j} = p[u].s{j};")
+                save.append(f"      p[u].s{j} = s{j};")
+                post.append(f"    if (io.site_out[{j}]) {{ for (int u = 0; u < 4; ++u) w[u] = gjb::as_u(p[u].s{j}); gjb::store4(io.site_out[{j}], i0, lo, hi, w); }}")
+            else:
+                D = s.value.shape[0]
+                P.append(f"  float s{j}[{D}];")
+                pre.append(f"    if (!(FL({j}) & GJB_SITE_SAMPLE)) {{ for (int u = 0; u < 4; ++u) for (int k = 0; k < {D}; ++k)")
+                pre.append(f"      p[u].s{j}[k] = (u >= lo && u < hi) ? __ldg(reinterpret_cast<const float*>(io.site_in[{j}]) + ((FL({j}) & GJB_SITE_BCAST) ? 0 : (i0 + u) * {D}) + k) : 0.0f; }}")
+                bind.append(f"      const float* in_s{j} = p[u].s{j};")
+                save.append(f"      for (int k = 0; k < {D}; ++k) p[u].s{j}[k] = s{j}[k];")
+                post.append(f"    if (io.site_out[{j}]) {{ for (int u = lo; u < hi; ++u) for (int k = 0; k < {D}; ++k) reinterpret_cast<float*>(io.site_out[{j}])[(i0 + u) * {D} + k] = p[u].s{j}[k]; }}")
+        for k, r in enumerate(ir.ret_leaves):
+            is_vec = isinstance(r, Expr) and r.ndim == 1
+            is_int = isinstance(r, Expr) and r.dtype == I32
+            if is_vec:
+                D = r.shape[0]
+                P.append(f"  float r{k}[{D}];")
+                save.append(f"      for (int k = 0; k < {D}; ++k) p[u].r{k}[k] = {self.ret_names[k]}[k];")
+                post.append(f"    if (io.ret_out[{k}]) {{ for (int u = lo; u < hi; ++u) for (int k = 0; k < {D}; ++k) reinterpret_cast<float*>(io.ret_out[{k}])[(i0 + u) * {D} + k] = p[u].r{k}[k]; }}")
+            else:
+                P.append(f"  {'int' if is_int else 'float'} r{k};")
+                save.append(f"      p[u].r{k} = {self.ret_names[k]};")
+                post.append(f"    if (io.ret_out[{k}]) {{ for (int u = 0; u < 4; ++u) w[u] = gjb::as_u(p[u].r{k}); gjb::store4(io.ret_out[{k}], i0, lo, hi, w); }}")
+        P.append("  float score, weight;")
+        P.append("};")
+
+        rngpre: list[str] = []
+        for s in ir.sites:
+            j = s.index
+            kind = s.dist.rng_kind
+            if s.dist.vector or kind == "lane":
+                continue
+            rngpre.append(f"    uint4 W{j} = make_uint4(0u, 0u, 0u, 0u); (void)W{j};")
+            if kind == "normal":
+                rngpre.append(f"    float4 Z{j} = make_float4(0.f, 0.f, 0.f, 0.f); (void)Z{j};")
+            rngpre.append(f"    if (FL({j}) & GJB_SITE_SAMPLE) {{ W{j} = gjb::quad_words(key0, key1, quad0 + (uint64_t)ql, {j + 1}u);"
+                          + (f" Z{j} = gjb::normal4_of(W{j});" if kind == "normal" else "") + " }")
+
+        out = list(P)
+        out.append("// quads [ql_begin, ql_end) step ql_stride of the launch; local particle i0 = 4*ql - (idx_offset & 3)")
+        out.append("template <bool kCg, bool kSt>")
+        out.append("__device__ __forceinline__ void run_quads(const Io& io, const Uni& U, const uint32_t (&fl)[NS], int64_t n,")
+        out.append("    uint64_t idx_offset, uint32_t key0, uint32_t key1, int64_t ql_begin, int64_t ql_end, int64_t ql_stride, float& run_max) {")
+        out.append("  const bool need_score = !kSt && io.score_out != nullptr;")
+        out.append("  const int shift = kSt ? 0 : (int)(idx_offset & 3);")
+        out.append("  const uint64_t quad0 = idx_offset >> 2;")
+        out.append("  const int32_t g0[4] = {0, 0, 0, 0};")
+        out.append("  for (int64_t ql = ql_begin; ql < ql_end; ql += ql_stride) {")
+        out.append("    const int64_t i0 = (ql << 2) - shift;")
+        out.append("    const int lo = i0 < 0 ? (int)(-i0) : 0;")
+        out.append("    const int hi = (n - i0) < 4 ? (int)(n - i0) : 4;")
+        out.append("    P p[4];")
+        out.append("    int32_t g[4];")
+        out.append("    gjb::load4_idx<kCg>(io.gather, i0, lo, hi, g);")
+        out.append("    uint32_t w[4];")
+        out.append("    (void)g0; (void)w; (void)quad0;")
+        out.extend(pre)
+        out.extend(rngpre)
+        out.append("#pragma unroll")
+        out.append("    for (int u = 0; u < 4; ++u) {")
+        out.append("      const int sub = u; (void)sub;")
+        if self.needs_lane:
+            out.append("      const gjb::Lane rng = gjb::make_lane(key0, key1, idx_offset + (uint64_t)(i0 + u));")
+        out.append("      float score = 0.0f, weight = 0.0f;")
+        out.extend(bind)
+        out.append(self.body)
+        out.extend(save)
+        out.append("      p[u].score = score; p[u].weight = weight;")
+        out.append("    }")
+        out.extend(post)
+        out.append("    if (!kSt && io.score_out) { for (int u = 0; u < 4; ++u) w[u] = gjb::as_u(p[u].score); gjb::store4(io.score_out, i0, lo, hi, w); }")
+        out.append("    {")
+        out.append("      uint32_t wi[4] = {0u, 0u, 0u, 0u}, si[4] = {0u, 0u, 0u, 0u};")
+        out.append("      if (!kSt && io.weight_in) gjb::load4<false>(io.weight_in, i0, lo, hi, g0, false, false, wi);")
+        out.append("      if (!kSt && io.score_in) gjb::load4<false>(io.score_in, i0, lo, hi, g0, false, false, si);")
+        out.append("      for (int u = 0; u < 4; ++u) {")
+        out.append("        float t = p[u].weight;")
+        out.append("        if (!kSt && io.weight_in) t = gjb::as_f(wi[u]) + t;")
+        out.append("        if (!kSt && io.score_in) t = t - gjb::as_f(si[u]);")
+        out.append("        w[u] = gjb::as_u(t);")
+        out.append("        if (u >= lo && u < hi) run_max = fmaxf(run_max, t);")
+        out.append("      }")
+        out.append("      if (io.weight_out) gjb::store4(io.weight_out, i0, lo, hi, w);")
+        out.append("    }")
+        out.append("  }")
+        out.append("}")
+        return out
+
+    # ------------------------------------------------------------ groups
+    def run_groups(self) -> list[str]:
+        ir = self.ir
+        D = ir.width
+        pre: list[str] = []
+        post: list[str] = []
+        for i, a in enumerate(ir.args):
+            if a.kind != "particle":
+                continue
+            if a.shape == ():
+                ct = "int" if a.dtype == I32 else "float"
+                cast = "const int*" if a.dtype == I32 else "const float*"
+                pre.append(f"      const {ct} a{i} = valid ? gjb::ldx<kCg>(reinterpret_cast<{cast}>(io.args[{i}]) + row) : 0;")
+            else:
+                pre.append(f"      const gjb::V4 a{i} = valid ? gjb::v4_ld<kCg>(reinterpret_cast<const float*>(io.args[{i}]) + row * {D} + 4 * lane) : gjb::v4_splat(0.0f);")
+        for s in ir.sites:
+            j = s.index
+            if s.value.ndim == 0:
+                ct = "int" if s.value.dtype == I32 else "float"
+                cast = "const int*" if s.value.dtype == I32 else "const float*"
+                pre.append(f"      {ct} in_s{j} = 0;")
+                pre.append(f"      if (!(FL({j}) & GJB_SITE_SAMPLE) && valid) in_s{j} = __ldg(reinterpret_cast<{cast}>(io.site_in[{j}]) + ((FL({j}) & GJB_SITE_BCAST) ? 0 : i));")
+                post.append(f"      if (io.site_out[{j}] && valid && lane == 0) reinterpret_cast<{ct}*>(io.site_out[{j}])[i] = s{j};")
+                kind = s.dist.rng_kind
+                if kind != "lane":
+                    pre.append(f"      uint4 W{j} = make_uint4(0u, 0u, 0u, 0u); (void)W{j};")
+                    if kind == "normal":
+                        pre.append(f"      float4 Z{j} = make_float4(0.f, 0.f, 0.f, 0.f); (void)Z{j};")
+                    pre.append(f"      if (FL({j}) & GJB_SITE_SAMPLE) {{ W{j} = gjb::quad_words(key0, key1, (idx_offset + (uint64_t)i) >> 2, {j + 1}u);"
+                               + (f" Z{j} = gjb::normal4_of(W{j});" if kind == "normal" else "") + " }")
+            else:
+                pre.append(f"      gjb::V4 in_s{j} = gjb::v4_splat(0.0f);")
+                pre.append(f"      if (!(FL({j}) & GJB_SITE_SAMPLE) && valid) in_s{j} = gjb::v4_ldg(reinterpret_cast<const float*>(io.site_in[{j}]) + ((FL({j}) & GJB_SITE_BCAST) ? 0 : i * {D}) + 4 * lane);")
+                post.append(f"      if (io.site_out[{j}] && valid) *reinterpret_cast<float4*>(reinterpret_cast<float*>(io.site_out[{j}]) + i * {D} + 4 * lane) = gjb::v4_to(s{j});")
+        for k, r in enumerate(ir.ret_leaves):
+            if isinstance(r, Expr) and r.ndim == 1:
+                post.append(f"      if (io.ret_out[{k}] && valid) *reinterpret_cast<float4*>(reinterpret_cast<float*>(io.ret_out[{k}]) + i * {D} + 4 * lane) = gjb::v4_to({self.ret_names[k]});")
+            else:
+                ct = "int" if isinstance(r, Expr) and r.dtype == I32 else "float"
+                post.append(f"      if (io.ret_out[{k}] && valid && lane == 0) reinterpret_cast<{ct}*>(io.ret_out[{k}])[i] = {self.ret_names[k]};")
+
+        out: list[str] = []
+        out.append("// particles [p_begin, p_end): block-iteration base steps by p_stride; G lanes per particle")
+        out.append("template <bool kCg, bool kSt>")
+        out.append("__device__ __forceinline__ void run_groups(const Io& io, const Uni& U, const uint32_t (&fl)[NS], int64_t n,")
+        out.append("    uint64_t idx_offset, uint32_t key0, uint32_t key1, int64_t p_begin, int64_t p_end, int64_t p_stride, float& run_max) {")
+        out.append("  const bool need_score = !kSt && io.score_out != nullptr;")
+        out.append("  const int lane = threadIdx.x & (G - 1);")
+        out.append("  const int sub_p = threadIdx.x / G;")
+        out.append("  for (int64_t base = p_begin; base < p_end; base += p_stride) {")
+        out.append("    {")
+        out.append("      const int64_t i = base + sub_p;")
+        out.append("      const bool valid = i < p_end && i < n;")
+        out.append("      const int64_t row = valid ? (io.gather ? (int64_t)gjb::ldx<kCg>(io.gather + i) : i) : 0;")
+        out.append("      (void)row;")
+        out.append("      const int sub = (int)((idx_offset + (uint64_t)i) & 3); (void)sub;")
+        out.append("      const gjb::Lane rng = gjb::make_lane(key0, key1, idx_offset + (uint64_t)i); (void)rng;")
+        out.append("      float score = 0.0f, weight = 0.0f, vscore = 0.0f, vweight = 0.0f;")
+        out.extend(pre)
+        out.append(self.body)
+        out.append("      if (need_score) score += gjb::group_sum<G>(vscore);")
+        out.append("      weight += gjb::group_sum<G>(vweight);")
+        out.extend(post)
+        out.append("      if (!kSt && io.score_out && valid && lane == 0) io.score_out[i] = score;")
+        out.append("      if (valid) {")
+        out.append("        float t = weight;")
+        out.append("        if (!kSt && io.weight_in) t = __ldg(io.weight_in + i) + t;")
+        out.append("        if (!kSt && io.score_in) t = t - __ldg(io.score_in + i);")
+        out.append("        if (io.weight_out && lane == 0) io.weight_out[i] = t;")
+        out.append("        run_max = fmaxf(run_max, t);")
+        out.append("      }")
+        out.append("    }")
+        out.append("  }")
+        out.append("}")
+        return out
+
+    # ------------------------------------------------------------ kernels
+    def model_kernel(self) -> list[str]:
+        out = ["__global__ void __launch_bounds__(kThreads) model_kernel(const __grid_constant__ gjb_model_args A) {"]
+        out.extend(self.stage_lines("A.args"))
+        out.append("  Uni U; make_uni(U, A.scalars);")
+        out.append("  uint32_t fl[NS];")
+        out.append(f"  for (int j = 0; j < {self.ns}; ++j) fl[j] = A.site_flags[j];")
+        out.append("  Io io;")
+        out.append("  for (int i = 0; i < NA; ++i) io.args[i] = A.args[i];")
+        out.append("  for (int j = 0; j < NS; ++j) { io.site_in[j] = A.site_in[j]; io.site_out[j] = A.site_out[j]; }")
+        out.append("  for (int k = 0; k < NR; ++k) io.ret_out[k] = A.ret_out[k];")
+        out.append("  io.gather = A.gather; io.score_in = A.score_in; io.weight_in = A.weight_in; io.score_out = A.score_out; io.weight_out = A.weight_out;")
+        out.append("  const uint32_t key0 = A.key_dev ? __ldg(A.key_dev) : A.key0, key1 = A.key_dev ? __ldg(A.key_dev + 1) : A.key1;")
+        out.append("  float run_max = -INFINITY;")
+        if self.group:
+            out.append("  run_groups<false, false>(io, U, fl, A.n, A.idx_offset, key0, key1, (int64_t)blockIdx.x * kPPB, A.n, (int64_t)gridDim.x * kPPB, run_max);")
         else:
-            pre.append(f"      gjb::V4 in_s{j} = gjb::v4_splat(0.0f);")
-            pre.append(f"      if (!(fl{j} & GJB_SITE_SAMPLE) && valid) in_s{j} = gjb::v4_ldg(reinterpret_cast<const float*>(A.site_in[{j}]) + ((fl{j} & GJB_SITE_BCAST) ? 0 : i * {D}) + 4 * lane);")
-            post.append(f"      if (A.site_out[{j}] && valid) *reinterpret_cast<float4*>(reinterpret_cast<float*>(A.site_out[{j}]) + i * {D} + 4 * lane) = gjb::v4_to(s{j});")
-    for k, r in enumerate(ir.ret_leaves):
-        if isinstance(r, Expr) and r.ndim == 1:
-            post.append(f"      if (A.ret_out[{k}] && valid) *reinterpret_cast<float4*>(reinterpret_cast<float*>(A.ret_out[{k}]) + i * {D} + 4 * lane) = gjb::v4_to({ret_names[k]});")
+            out.append("  const int64_t nq = (A.n + (int64_t)(A.idx_offset & 3) + 3) >> 2;")
+            out.append("  run_quads<false, false>(io, U, fl, A.n, A.idx_offset, key0, key1, blockIdx.x * (int64_t)kThreads + threadIdx.x, nq, (int64_t)gridDim.x * kThreads, run_max);")
+        out.append("  if (A.wmax) gjb::block_wmax(run_max, A.wmax);")
+        out.append("}")
+        return out
+
+    def pf_kernel(self) -> list[str]:
+        """The persistent particle-filter kernel (None when the model's return
+        leaves cannot feed back as its leading particle arguments)."""
+        ir = self.ir
+        out = ["__global__ void __launch_bounds__(kThreads, kPfMinBlocks) pf_kernel(const __grid_constant__ gjb_pf_args Q) {"]
+        out.extend(self.stage_lines("Q.shared"))
+        out.append("  Uni U; make_uni(U, Q.scalars);")
+        out.append("  uint32_t fl[NS];")
+        out.append(f"  for (int j = 0; j < {self.ns}; ++j) fl[j] = Q.site_flags[j];")
+        out.append("  constexpr bool kSt = kPfStatic;")
+        out.append("  __shared__ gjb::TileSmem tsm;")
+        out.append("  extern __shared__ __align__(16) unsigned char dyn_smem[];")
+        out.append("  uint64_t* qcache = reinterpret_cast<uint64_t*>(dyn_smem);  // masses of this CTA's tiles, phase B -> phase C")
+        out.append("  const int tid = threadIdx.x;")
+        out.append("  const int64_t n = Q.n;")
+        out.append("  const int64_t G_ = gridDim.x;")
+        out.append("  const int64_t chunk = (((n + G_ - 1) / G_) + 7) & ~(int64_t)7;  // particles per CTA, multiple of 8")
+        out.append("  const int64_t c0 = (int64_t)blockIdx.x * chunk < n ? (int64_t)blockIdx.x * chunk : n;")
+        out.append("  const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;")
+        out.append("  const bool cache_q = (chunk + gjb::kTile - 1) / gjb::kTile <= kPfCacheTiles;")
+        out.append("  for (int t = 0; t < Q.T; ++t) {")
+        out.append("    const int slot = Q.record ? t : (t & 1);")
+        out.append("    const int pslot = Q.record ? t - 1 : ((t - 1) & 1);")
+        out.append("    Io io;")
+        out.append("    for (int i = 0; i < NA; ++i) io.args[i] = nullptr;")
+        out.append("    for (int j = 0; j < NS; ++j) { io.site_in[j] = nullptr; io.site_out[j] = nullptr; }")
+        out.append("    for (int k = 0; k < NR; ++k) io.ret_out[k] = nullptr;")
+        out.append("    io.score_in = nullptr; io.weight_in = nullptr; io.score_out = nullptr;")
+        for i in range(len(ir.ret_leaves)):
+            out.append(f"    io.args[{i}] = t == 0 ? Q.state0[{i}] : (const void*)((const char*)Q.state_buf[{i}] + (int64_t)pslot * Q.state_stride[{i}]);")
+        out.append("    io.gather = t == 0 ? nullptr : Q.ancestors + (int64_t)pslot * n;")
+        for s in ir.sites:
+            j = s.index
+            out.append(f"    if (Q.obs[{j}]) io.site_in[{j}] = (const char*)Q.obs[{j}] + (int64_t)t * Q.obs_stride[{j}];")
+        for k, r in enumerate(ir.ret_leaves):
+            dst = f"(void*)((char*)Q.state_buf[{k}] + (int64_t)slot * Q.state_stride[{k}])"
+            if isinstance(r, Expr) and r.op == "site":
+                # a sampled site that is returned: write it once, as the next state
+                out.append(f"    if (FL({r.attr}) & GJB_SITE_SAMPLE) io.site_out[{r.attr}] = {dst}; else io.ret_out[{k}] = {dst};")
+            else:
+                out.append(f"    io.ret_out[{k}] = {dst};")
+        out.append("    float* lw = Q.logw + (Q.record ? (int64_t)t * n : 0);")
+        out.append("    io.weight_out = lw;")
+        out.append("    const uint32_t* kt = Q.keys + 8 * t;")
+        out.append("    const uint32_t key0 = __ldg(kt), key1 = __ldg(kt + 1);")
+        out.append("    // ---- phase A: gather + propose + logpdf over this CTA's particles, running max")
+        out.append("    float run_max = -INFINITY;")
+        if self.group:
+            out.append("    run_groups<true, kPfStatic>(io, U, fl, n, Q.idx_offset, key0, key1, c0, c1, kPPB, run_max);")
         else:
-            ct = "int" if isinstance(r, Expr) and r.dtype == I32 else "float"
-            post.append(f"      if (A.ret_out[{k}] && valid && lane == 0) reinterpret_cast<{ct}*>(A.ret_out[{k}])[i] = {ret_names[k]};")
+            out.append("    run_quads<true, kPfStatic>(io, U, fl, n, Q.idx_offset, key0, key1, (c0 >> 2) + tid, (c1 + 3) >> 2, kThreads, run_max);")
+        out.append("    uint32_t* wm = Q.wmax + (t & 1);")
+        out.append("    gjb::block_wmax(run_max, wm);")
+        out.append("    gjb::grid_barrier(Q.barrier, (uint32_t)G_);")
+        out.append("    // ---- phase B: exact integer mass of this CTA's weights relative to the global max")
+        out.append("    const float M = gjb::fdec(__ldcg(wm));")
+        out.append("    uint64_t mass = 0;")
+        out.append("    for (int64_t tb = c0; tb < c1; tb += gjb::kTile)")
+        out.append("      mass += gjb::tile_mass_of<true>(lw, c1, tb, M, tsm.red, cache_q ? qcache + (tb - c0) : nullptr);")
+        out.append("    if (tid == 0) __stcg(reinterpret_cast<unsigned long long*>(Q.cta_mass) + blockIdx.x, (unsigned long long)mass);")
+        out.append("    gjb::grid_barrier(Q.barrier, (uint32_t)G_);")
+        out.append("    // ---- phase C: CDF offset of this CTA, systematic offspring ranges -> ancestors")
+        out.append("    uint64_t pre = 0, tot = 0;")
+        out.append("    for (int b = tid; b < (int)G_; b += kThreads) {")
+        out.append("      const uint64_t v = __ldcg(reinterpret_cast<const unsigned long long*>(Q.cta_mass) + b);")
+        out.append("      tot += v; if (b < (int)blockIdx.x) pre += v;")
+        out.append("    }")
+        out.append("    pre = gjb::block_sum_u64(pre, tsm.red);")
+        out.append("    tot = gjb::block_sum_u64(tot, tsm.red);")
+        out.append("    const uint64_t S = tot;")
+        out.append("    int32_t* anc = Q.ancestors + (int64_t)slot * n;")
+        out.append("    if (blockIdx.x == 0 && tid == 0) {")
+        out.append("      double* o = Q.lse + 3 * t;")
+        out.append("      o[0] = (double)M; o[1] = (double)S;")
+        out.append("      o[2] = S ? (double)M + log((double)S) - gjb::kQLog - log((double)Q.n_total) : -INFINITY;")
+        out.append("      Q.wmax[(t + 1) & 1] = GJB_WMAX_NEG_INF;")
+        out.append("    }")
+        out.append("    if (S == 0) {")
+        out.append("      for (int64_t i = c0 + tid; i < c1; i += kThreads) anc[i] = (int32_t)i;")
+        out.append("    } else {")
+        out.append("      const double u0 = gjb::resample_u0(__ldg(kt + 2), __ldg(kt + 3), (uint64_t)__ldg(kt + 4) | ((uint64_t)__ldg(kt + 5) << 32));")
+        out.append("      uint64_t off = pre;")
+        out.append("      for (int64_t tb = c0; tb < c1; tb += gjb::kTile)")
+        out.append("        off += gjb::resample_tile<true>(lw, c1, tb, M, off, S, Q.n_total, u0, 0, n, 0, anc, tsm, reinterpret_cast<int32_t*>(qcache + (cache_q ? (tb - c0) : 0)), cache_q ? qcache + (tb - c0) : nullptr);")
+        out.append("    }")
+        out.append("    gjb::grid_barrier(Q.barrier, (uint32_t)G_);")
+        out.append("  }")
+        out.append("}")
+        out.append("__global__ void pf_init_kernel(uint32_t* wmax, uint32_t* barrier) {")
+        out.append("  if (threadIdx.x == 0) { wmax[0] = GJB_WMAX_NEG_INF; wmax[1] = GJB_WMAX_NEG_INF; barrier[0] = 0u; barrier[1] = 0u; }")
+        out.append("}")
+        return out
 
-    out: list[str] = []
-    out.append(f"// generated by genjax_b200.gen.codegen -- model '{ir.name}' [{ir.digest}] (group mapping, G={G})")
-    out.append('#include "gjb_model.cuh"')
-    out.append("namespace {")
-    out.extend(em.consts)
-    out.append("constexpr int kThreads = 256;")
-    out.append(f"constexpr int G = {G};")
-    out.append("constexpr int kPPB = kThreads / G;  // particles per block iteration")
-    out.append("__global__ void __launch_bounds__(kThreads) model_kernel(const __grid_constant__ gjb_model_args A) {")
-    out.extend(decl)
-    out.extend(stage)
-    if stage:
-        out.append("  __syncthreads();")
-    for j in range(ns):
-        out.append(f"  const uint32_t fl{j} = A.site_flags[{j}];")
-    out.append("  const bool need_score = A.score_out != nullptr;")
-    out.append("  const uint32_t key0 = A.key_dev ? __ldg(A.key_dev) : A.key0, key1 = A.key_dev ? __ldg(A.key_dev + 1) : A.key1;")
-    out.append("  float run_max = -INFINITY;")
-    out.append("  const int lane = threadIdx.x & (G - 1);")
-    out.append("  const int sub = threadIdx.x / G;")
-    out.append("  for (int64_t base = (int64_t)blockIdx.x * kPPB; base < A.n; base += (int64_t)gridDim.x * kPPB) {")
-    out.append("    {")
-    out.append("      const int64_t i = base + sub;")
-    out.append("      const bool valid = i < A.n;")
-    out.append("      const int64_t row = valid ? (A.gather ? (int64_t)__ldg(A.gather + i) : i) : 0;")
-    out.append("      (void)row;")
-    out.append("      const gjb::Lane rng = gjb::make_lane(key0, key1, A.idx_offset + (uint64_t)i);")
-    out.append("      float score = 0.0f, weight = 0.0f, vscore = 0.0f, vweight = 0.0f;")
-    out.extend(pre)
-    out.append(body)
-    out.append("      if (need_score) score += gjb::group_sum<G>(vscore);")
-    out.append("      weight += gjb::group_sum<G>(vweight);")
-    out.extend(post)
-    out.append("      if (A.score_out && valid && lane == 0) A.score_out[i] = score;")
-    out.append("      if ((A.weight_out || A.wmax) && valid) {")
-    out.append("        float t = weight;")
-    out.append("        if (A.weight_in) t = __ldg(A.weight_in + i) + t;")
-    out.append("        if (A.score_in) t = t - __ldg(A.score_in + i);")
-    out.append("        if (A.weight_out && lane == 0) A.weight_out[i] = t;")
-    out.append("        run_max = fmaxf(run_max, t);")
-    out.append("      }")
-    out.append("    }")
-    out.append("  }")
-    out.append("  if (A.wmax) gjb::block_wmax(run_max, A.wmax);")
-    out.append("}")
-    out.append("}  // namespace")
-    out.append(_extern_c(ir, "group", G, work_per_thread=0))
-    return "\n".join(out) + "\n"
+    def pf_supported(self) -> bool:
+        ir = self.ir
+        n_state = len(ir.ret_leaves)
+        if n_state == 0 or n_state > len(ir.args):
+            return False
+        for r, a in zip(ir.ret_leaves, ir.args):
+            if not isinstance(r, Expr) or a.kind != "particle":
+                return False
+            if tuple(r.shape) != tuple(a.shape) or r.dtype != a.dtype:
+                return False
+        return all(a.kind != "particle" for a in ir.args[n_state:])
 
+    def source(self) -> str:
+        out = self.header()
+        out.extend(self.run_groups() if self.group else self.run_quads())
+        out.extend(self.model_kernel())
+        pf = self.pf_supported()
+        if pf:
+            out.extend(self.pf_kernel())
+        out.append("}  // namespace")
+        out.append(self.extern_c(pf))
+        return "\n".join(out) + "\n"
 
-def _extern_c(ir: ModelIR, mapping: str, G: int, work_per_thread: int) -> str:
-    info = _info_json(ir, mapping, G).replace("\\", "\\\\").replace('"', '\\"')
-    if mapping == "quad":
-        work = "(a->n + 3) / 4"
-        per_block = "kThreads"
-    else:
-        work = "a->n"
-        per_block = "kPPB"
-    return f"""
+    def extern_c(self, pf: bool) -> str:
+        ir = self.ir
+        mapping = "group" if self.group else "quad"
+        info = _info_json(ir, mapping, max(self.G, 1)).replace("\\", "\\\\").replace('"', '\\"')
+        if self.group:
+            work = "a->n"
+            per_block = "kPPB"
+        else:
+            work = "(a->n + (int64_t)(a->idx_offset & 3) + 3) / 4"
+            per_block = "kThreads"
+        if pf:
+            pf_code = f"""
+static int pf_smem_for(int64_t n, int grid) {{
+  const int64_t chunk = (((n + grid - 1) / grid) + 7) & ~(int64_t)7;
+  const int64_t tiles = (chunk + gjb::kTile - 1) / gjb::kTile;
+  return tiles <= kPfCacheTiles ? (int)(tiles * gjb::kTile * 8) : gjb::kTile * 8;  // >= one window of heads
+}}
+
+static int pf_grid_for(int64_t n) {{
+  // sized with the largest dynamic shared memory the kernel may ask for
+  const int resident = gjb::resident_blocks((const void*)pf_kernel, kThreads, 4, kPfCacheTiles * gjb::kTile * 8);
+  int64_t want = (n + 255) / 256;  // at least 256 particles per CTA
+  if (want < 1) want = 1;
+  return (int)(want < resident ? want : resident);
+}}
+
+int gjb_model_pf_grid(int64_t n) {{ return n < 0 ? GJB_E_ARG : pf_grid_for(n); }}
+
+int gjb_model_pf_run(const gjb_pf_args* a, void* stream) {{
+  if (!a || a->n <= 0 || a->T <= 0 || !a->keys || !a->logw || !a->ancestors || !a->lse || !a->wmax || !a->cta_mass || !a->barrier)
+    return GJB_E_ARG;
+  if (a->n_state != {len(ir.ret_leaves)}) return GJB_E_ARG;
+  if ((a->idx_offset & 3) != 0) return GJB_E_ARG;  // quads must align with the global quad streams
+  if (a->n_total > 0x7fffffffLL || a->n > 0x7fffffffLL) return GJB_E_RANGE;
+  for (int i = 0; i < a->n_state; ++i) if (!a->state0[i] || !a->state_buf[i]) return GJB_E_ARG;
+  if (kPfStatic) for (int j = 0; j < {self.ns}; ++j) if (a->site_flags[j] != kPfFl_host[j]) return GJB_E_MODE;  // flags are baked in
+  const int grid = pf_grid_for(a->n);
+  const int smem = pf_smem_for(a->n, grid);
+  static bool attr_set = false;
+  if (!attr_set) {{
+    cudaFuncSetAttribute((const void*)pf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfCacheTiles * gjb::kTile * 8);
+    attr_set = true;
+  }}
+  pf_init_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a->wmax, a->barrier);
+  void* params[1] = {{(void*)a}};
+  const cudaError_t e = cudaLaunchCooperativeKernel((const void*)pf_kernel, dim3(grid), dim3(kThreads), params, smem, (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaGetLastError();
+}}
+"""
+        else:
+            pf_code = """
+int gjb_model_pf_grid(int64_t n) { (void)n; return GJB_E_MODE; }
+int gjb_model_pf_run(const gjb_pf_args* a, void* stream) { (void)a; (void)stream; return GJB_E_MODE; }
+"""
+        return f"""
 extern "C" {{
 const char* gjb_model_info(void) {{ return "{info}"; }}
 
@@ -535,12 +861,12 @@ int gjb_model_launch(const gjb_model_args* a, void* stream) {{
   if (a->n == 0) return 0;
   const int64_t work = {work};
   int64_t blocks = (work + {per_block} - 1) / {per_block};
-  const int64_t cap = 148 * 8;  // persistent-style grid: a multiple of the 148 SMs
+  const int64_t cap = gjb::resident_blocks((const void*)model_kernel, kThreads, 8);  // one full wave, grid-stride inside
   if (blocks > cap) blocks = cap;
   model_kernel<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(*a);
   return (int)cudaGetLastError();
 }}
-
+{pf_code}
 int gjb_model_mh_chain(const gjb_chain_args* a, void* stream) {{ (void)a; (void)stream; return GJB_E_MODE; }}
 int gjb_model_hmc_chain(const gjb_chain_args* a, void* stream) {{ (void)a; (void)stream; return GJB_E_MODE; }}
 }}

@@ -62,8 +62,21 @@ class Distribution(GenerativeFunction):
         return self.value_dtype, ()
 
     # -- codegen hooks (scalar distributions) ---------------------------
+    # rng_kind: what the sampler consumes from the site's Philox block
+    #   "uniform": one u01 word of the quad block W{site} (slot `sub`)
+    #   "normal" : one component of normal4_of(W{site}) = Z{site}
+    #   "lane"   : its own per-particle stream (rejection samplers)
+    rng_kind: str = "uniform"
+
+    def draw_expr(self, site: int) -> str:
+        if self.rng_kind == "normal":
+            return f"gjb::pick(Z{site}, sub)"
+        if self.rng_kind == "uniform":
+            return f"gjb::u01(gjb::pick(W{site}, sub))"
+        return f"rng, {site + 1}u"
+
     def emit_sample(self, site: int, a: list[str], cg) -> str:
-        return f"gjb::{self.cuda}::sample(rng, {site + 1}u, {', '.join(a)})"
+        return f"gjb::{self.cuda}::sample({self.draw_expr(site)}, {', '.join(a)})"
 
     def emit_logpdf(self, v: str, a: list[str], cg) -> str:
         return f"gjb::{self.cuda}::logpdf({v}, {', '.join(a)})"
@@ -81,6 +94,7 @@ def _split_kwargs(args):
 
 class _Normal(Distribution):
     name, cuda, n_args = "normal", "Normal", 2
+    rng_kind = "normal"
 
     def _canonical(self, args, kwargs):
         if kwargs:
@@ -105,14 +119,17 @@ class _Exponential(Distribution):
 
 class _HalfNormal(Distribution):
     name, cuda, n_args = "half_normal", "HalfNormal", 1
+    rng_kind = "normal"
 
 
 class _Gamma(Distribution):
     name, cuda, n_args = "gamma", "Gamma", 2
+    rng_kind = "lane"
 
 
 class _Beta(Distribution):
     name, cuda, n_args = "beta", "Beta", 2
+    rng_kind = "lane"
 
 
 class _Flip(Distribution):
@@ -162,7 +179,7 @@ class _Categorical(Distribution):
 
     def emit_sample(self, site, a, cg):
         ptr, k = a[0]
-        return f"gjb::Categorical::sample(rng, {site + 1}u, {ptr}, {k})"
+        return f"gjb::Categorical::sample({self.draw_expr(site)}, {ptr}, {k})"
 
     def emit_logpdf(self, v, a, cg):
         ptr, k = a[0]
@@ -173,6 +190,7 @@ class _MvNormalDiag(Distribution):
     """tfd.MultivariateNormalDiag(loc, scale_diag) (tensorflow_probability/__init__.py:239)."""
 
     name, cuda, n_args, vector = "mv_normal_diag", "MvNormalDiag", 2, True
+    rng_kind = "lane"
 
     def value_type(self, cargs):
         d = max((c.shape[0] for c in cargs if c.ndim == 1), default=0)
@@ -239,6 +257,7 @@ def register_primitive(name: str, cuda_struct: str, n_args: int, value_dtype: st
 
     p = _P()
     p.name, p.cuda, p.n_args, p.value_dtype = name, cuda_struct, n_args, value_dtype
+    p.rng_kind = "lane"  # user primitives get the particle's own stream: sample(rng, site, args...)
     REGISTRY[name] = p
     return p
 

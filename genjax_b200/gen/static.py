@@ -111,9 +111,9 @@ class CompiledModel:
 _COMPILED: dict[str, CompiledModel] = {}
 
 
-def compile_ir(ir: ModelIR) -> CompiledModel:
+def compile_ir(ir: ModelIR, pf_obs: tuple | None = None) -> CompiledModel:
     ir.digest = cap.ir_fingerprint(ir)
-    source = codegen.generate(ir)
+    source = codegen.generate(ir, pf_obs)
     key = build.model_digest(source)
     cm = _COMPILED.get(key)
     if cm is None:
@@ -121,6 +121,12 @@ def compile_ir(ir: ModelIR) -> CompiledModel:
         cm = CompiledModel(ir, cabi.load_model_library(path), path)
         _COMPILED[key] = cm
     return cm
+
+
+def cap_norm(addr) -> tuple:
+    from ..core.choice_map import _norm_addr
+
+    return _norm_addr(addr)
 
 
 def _dev_tensor(v, device, want_int=None) -> torch.Tensor:
@@ -334,16 +340,20 @@ class StaticGenerativeFunction(GenerativeFunction):
             self._cache[sig] = cm
         return cm
 
-    def prebuild(self, specs: list, tree=None) -> CompiledModel:
+    def prebuild(self, specs: list, tree=None, pf_obs: tuple | None = None) -> CompiledModel:
         """Capture + compile for an explicit argument signature (no GPU needed):
-        ``specs`` is a list of ``ArgSpec``; used by ``__graft_entry__.build()``."""
+        ``specs`` is a list of ``ArgSpec``; used by ``__graft_entry__.build()``.
+        ``pf_obs`` (addresses observed at every filter step) selects the
+        variant whose persistent filter kernel has its site flags baked in."""
         if tree is None:
             tree = ("tuple", [("leaf", i) for i in range(len(specs))])
-        sig = (repr(tree), tuple(s.key() for s in specs))
+        obs_key = None if pf_obs is None else tuple(sorted(cap_norm(a) for a in pf_obs))
+        sig = (repr(tree), tuple(s.key() for s in specs), obs_key)
         cm = self._cache.get(sig)
         if cm is None:
             ir = cap.capture(self.source, self.__name__, list(specs), tree)
-            cm = compile_ir(ir)
+            idx = None if obs_key is None else tuple(ir.site_index(a) for a in obs_key)
+            cm = compile_ir(ir, idx)
             self._cache[sig] = cm
         return cm
 

@@ -8,11 +8,20 @@ mapping_tutorial.ipynb cell 37; reweight formula inference/smc.py:383):
             log_w += w;  idx ~ categorical(log_w - logsumexp(log_w)) per offspring
             x_prev = trs.get_retval()[idx]
 
-``ParticleFilter`` is that idiom as three fused launches per step on one
-stream -- (1) the model kernel: ancestor gather + propose + logpdf + running
-max, (2) exact integer weight mass per tile, (3) CDF scan + systematic
-offspring ranges + log-marginal increment -- captured once as a CUDA graph and
-replayed per run with device-resident keys / observations / initial state.
+``ParticleFilter`` is that idiom on the GPU in one of two forms:
+
+  * ``mode="persistent"`` (default): the whole T-step filter is ONE cooperative
+    launch of the model's generated ``pf_kernel`` (gen/codegen.py,
+    ``gjb_model_pf_run``): per step (A) ancestor gather + propose + logpdf +
+    running max, (B) exact integer weight mass per CTA, (C) CDF scan +
+    systematic offspring ranges + log-marginal increment, separated by
+    grid-wide barriers instead of kernel boundaries;
+  * ``mode="graph"``: the same three phases as three launches per step
+    (``gjb_model_launch`` / ``gjb_weight_mass`` / ``gjb_resample_systematic``)
+    captured once as a CUDA graph.
+
+Both read device-resident keys / observations / initial state and give
+bit-identical results.
 """
 
 from __future__ import annotations
@@ -50,9 +59,12 @@ class ParticleFilter:
     particles).  Every other site is proposed from the model (bootstrap)."""
 
     def __init__(self, step: StaticGenerativeFunction, n_particles: int, *, n_state: int = 1, resampler: str = "systematic",
-                 idx_offset: int = 0, n_total: int | None = None):
+                 idx_offset: int = 0, n_total: int | None = None, mode: str = "persistent"):
         if resampler != "systematic":
             raise NotImplementedError("the fused filter loop uses systematic resampling; see ParticleCollection.resample")
+        if mode not in ("persistent", "graph"):
+            raise ValueError(mode)
+        self.mode = mode
         self.step = step
         self.n = int(n_particles)
         self.n_state = n_state
@@ -110,7 +122,7 @@ class _Plan:
                 specs.append(ArgSpec("shared", "i32" if s.dtype == torch.int32 else "f32", tuple(s.shape)))
             else:
                 specs.append(ArgSpec("scalar", "i32" if isinstance(s, int) else "f32", ()))
-        self.cm = step.prebuild(specs)
+        self.cm = step.prebuild(specs, pf_obs=tuple(obs.keys()) if pf.mode == "persistent" else None)
         ir = self.cm.ir
         self.ir = ir
         # static buffers (graph replays read/write these)
@@ -141,8 +153,54 @@ class _Plan:
         self.obs_sites = {}
         for addr in obs:
             self.obs_sites[ir.site_index(addr)] = addr
-        self._build_args()
         self.graph = None
+        self.persistent = pf.mode == "persistent"
+        if self.persistent:
+            self._build_pf_args()
+        else:
+            self._build_args()
+
+    def _build_pf_args(self):
+        """One ``gjb_pf_args`` for the persistent kernel."""
+        pf, ir, T, n = self.pf, self.ir, self.T, self.pf.n
+        lib = self.cm.lib
+        grid = lib.gjb_model_pf_grid(n)
+        cabi.check(min(grid, 0), "gjb_model_pf_grid")
+        self.pf_grid = grid
+        if self.record:
+            self.logw = self.logw_hist
+        self.cta_mass = torch.empty(grid, dtype=torch.int64, device=self.device)
+        self.barrier = torch.zeros(2, dtype=torch.int32, device=self.device)
+        Q = cabi.PfArgs()
+        Q.n, Q.n_total, Q.idx_offset = n, pf.n_total, pf.idx_offset
+        Q.T, Q.record, Q.n_state = T, int(self.record), len(self.state_in)
+        Q.keys = self.keys.data_ptr()
+        for i, s in enumerate(self.state_in):
+            Q.state0[i] = s.data_ptr()
+            Q.state_buf[i] = self.bufs[i].data_ptr()
+            Q.state_stride[i] = self.bufs[i][0].numel() * 4
+        for k, s in enumerate(self.shared):
+            i = len(self.state_in) + k
+            if isinstance(s, torch.Tensor):
+                Q.shared[i] = s.data_ptr()
+            else:
+                Q.scalars[i] = float(s)
+        for site in ir.sites:
+            j = site.index
+            if j in self.obs_sites:
+                o = self.obs[self.obs_sites[j]]
+                Q.obs[j] = o.data_ptr()
+                Q.obs_stride[j] = (o[0].numel() if o.ndim > 1 else 1) * 4
+                Q.site_flags[j] = cabi.SITE_WEIGHT | cabi.SITE_BCAST
+            else:
+                Q.site_flags[j] = cabi.SITE_SAMPLE
+        Q.logw = self.logw.data_ptr()
+        Q.ancestors = self.anc.data_ptr()
+        Q.lse = self.lse.data_ptr()
+        Q.wmax = self.wmax2.data_ptr()
+        Q.cta_mass = self.cta_mass.data_ptr()
+        Q.barrier = self.barrier.data_ptr()
+        self.pf_args = Q
 
     def _build_args(self):
         pf, ir, T, n = self.pf, self.ir, self.T, self.pf.n
@@ -194,6 +252,12 @@ class _Plan:
         core = cabi.core()
         stream = cabi.stream_ptr(self.device)
         lib = self.cm.lib
+        if self.persistent:
+            cabi.check(lib.gjb_model_pf_run(C.byref(self.pf_args), stream), "gjb_model_pf_run")
+            last = (self.T - 1) if self.record else ((self.T - 1) & 1)
+            for k in range(len(self.bufs)):
+                smc_ops.gather_rows(self.bufs[k][last], self.anc[last], self.final[k])
+            return
         cabi.check(core.gjb_wmax_reset(self.wmax2.data_ptr(), stream), "gjb_wmax_reset")
         for t in range(self.T):
             cabi.check(lib.gjb_model_launch(C.byref(self.margs[t]), stream), "gjb_model_launch")
@@ -209,6 +273,8 @@ class _Plan:
             smc_ops.gather_rows(self.bufs[k][last], self.anc[last], self.final[k])
 
     def launches_per_run(self) -> int:
+        if self.persistent:
+            return 2 + len(self.bufs)  # init + persistent filter kernel + final gather(s)
         return 1 + 3 * self.T + len(self.bufs)
 
     def execute(self, key, state0, shared, obs, use_graph):
@@ -223,7 +289,7 @@ class _Plan:
         for a in self.obs:
             if self.obs[a].data_ptr() != obs[a].data_ptr():
                 self.obs[a].copy_(obs[a], non_blocking=True)
-        if use_graph:
+        if use_graph and not self.persistent:
             if self.graph is None:
                 # warm-up launch outside capture (module load), then capture once
                 self._enqueue()

@@ -81,6 +81,35 @@ class ResampleArgs(C.Structure):
     ]
 
 
+class PfArgs(C.Structure):
+    """``gjb_pf_args`` (include/genjax_b200.h)."""
+
+    _fields_ = [
+        ("n", _i64),
+        ("n_total", _i64),
+        ("idx_offset", _u64),
+        ("T", _i32),
+        ("record", _i32),
+        ("n_state", _i32),
+        ("reserved", _i32),
+        ("keys", _p),
+        ("state0", _p * GJB_MAX_ARGS),
+        ("state_buf", _p * GJB_MAX_ARGS),
+        ("state_stride", _i64 * GJB_MAX_ARGS),
+        ("shared", _p * GJB_MAX_ARGS),
+        ("scalars", C.c_float * GJB_MAX_ARGS),
+        ("obs", _p * GJB_MAX_SITES),
+        ("obs_stride", _i64 * GJB_MAX_SITES),
+        ("site_flags", _u32 * GJB_MAX_SITES),
+        ("logw", _p),
+        ("ancestors", _p),
+        ("lse", _p),
+        ("wmax", _p),
+        ("cta_mass", _p),
+        ("barrier", _p),
+    ]
+
+
 class ChainArgs(C.Structure):
     """``gjb_chain_args`` (include/genjax_b200.h)."""
 
@@ -121,6 +150,8 @@ CORE_PROTOTYPES = {
 MODEL_PROTOTYPES = {
     "gjb_model_info": (C.c_char_p, []),
     "gjb_model_launch": (C.c_int, [C.POINTER(ModelArgs), _p]),
+    "gjb_model_pf_grid": (C.c_int, [_i64]),
+    "gjb_model_pf_run": (C.c_int, [C.POINTER(PfArgs), _p]),
     "gjb_model_mh_chain": (C.c_int, [C.POINTER(ChainArgs), _p]),
     "gjb_model_hmc_chain": (C.c_int, [C.POINTER(ChainArgs), _p]),
 }
@@ -146,7 +177,7 @@ def core():
     if _core is None:
         path = build.build_core()
         _core = _bind(C.CDLL(str(path)), CORE_PROTOTYPES)
-        if _core.gjb_abi_version() != 1:
+        if _core.gjb_abi_version() != 2:
             raise GjbError("libgjb_core.so ABI mismatch")
     return _core
 

@@ -47,11 +47,16 @@ def hmm_step(z_prev, trans_logits, obs_logits):
 def prebuild_all():
     """Compile every workload kernel for sm_100a (no GPU needed)."""
     out = {}
-    out["lgssm_step"] = lgssm_step.prebuild([ArgSpec("particle", "f32", ())])
-    for d in (8, 32):
-        out[f"lgssm_step_vec{d}"] = lgssm_step_vec.prebuild(
-            [ArgSpec("particle", "f32", (d,)), ArgSpec("shared", "f32", (d,)), ArgSpec("shared", "f32", (d,))]
-        )
+    for obs in (None, ("y",)):  # generic GFI variant + the bootstrap-filter variant (flags baked into pf_kernel)
+        tag = "" if obs is None else "_pf"
+        out["lgssm_step" + tag] = lgssm_step.prebuild([ArgSpec("particle", "f32", ())], pf_obs=obs)
+        for d in (8, 32):
+            out[f"lgssm_step_vec{d}" + tag] = lgssm_step_vec.prebuild(
+                [ArgSpec("particle", "f32", (d,)), ArgSpec("shared", "f32", (d,)), ArgSpec("shared", "f32", (d,))], pf_obs=obs
+            )
+    out["hmm_step_pf"] = hmm_step.prebuild(
+        [ArgSpec("particle", "i32", ()), ArgSpec("shared", "f32", (16, 16)), ArgSpec("shared", "f32", (16, 16))], pf_obs=("y",)
+    )
     out["beta_bernoulli"] = beta_bernoulli.prebuild([ArgSpec("scalar", "f32", ()), ArgSpec("scalar", "f32", ())])
     out["hmm_step"] = hmm_step.prebuild(
         [ArgSpec("particle", "i32", ()), ArgSpec("shared", "f32", (16, 16)), ArgSpec("shared", "f32", (16, 16))]

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GJB_ABI_VERSION 1
+#define GJB_ABI_VERSION 2
 
 #define GJB_E_ARG (-1)      /* null / misaligned pointer, negative size          */
 #define GJB_E_RANGE (-2)    /* size beyond what the kernel supports              */
@@ -175,6 +175,48 @@ typedef struct gjb_model_args {
 /* JSON description of the captured model (sites, args, layouts); static storage. */
 const char* gjb_model_info(void);
 int gjb_model_launch(const gjb_model_args* a, void* stream);
+
+/*
+ * The whole T-step bootstrap particle filter as ONE persistent cooperative
+ * launch.  The reference has no filter class: this is the batched form of the
+ * user idiom "vmap(step.importance) -> log_w += w -> categorical resample ->
+ * gather" (docs/cookbook/inactive/inference/importance_sampling.ipynb cell 16,
+ * mapping_tutorial.ipynb cell 37; reweight formula inference/smc.py:383).
+ * The model's return leaves are the next state and feed back as its first
+ * n_state (per-particle) arguments.  Per step t:
+ *   A  gather x[anc] + propose + logpdf -> logw, running max      (grid barrier)
+ *   B  exact integer mass of each CTA's weights relative to max   (grid barrier)
+ *   C  CDF scan + systematic offspring ranges -> ancestors[t]     (grid barrier)
+ * lse[t] = {M, S, log-mean-exp increment} as gjb_lse_finalize.
+ */
+typedef struct gjb_pf_args {
+  int64_t n;                 /* particles on this device                        */
+  int64_t n_total;           /* global particle count (== n on one device)      */
+  uint64_t idx_offset;       /* global index of local particle 0 (multiple of 4) */
+  int32_t T;                 /* filter steps                                    */
+  int32_t record;            /* 1: state_buf / ancestors / logw keep all T steps */
+  int32_t n_state;           /* state leaves = leading model args = return leaves */
+  int32_t reserved;
+  const uint32_t* keys;      /* [T, 8] {prop_k0, prop_k1, res_k0, res_k1, res_idx_lo, res_idx_hi, 0, 0} */
+  const void* state0[GJB_MAX_ARGS];     /* initial state leaves [n(, d)]        */
+  void* state_buf[GJB_MAX_ARGS];        /* [slots, n(, d)]; slots = record ? T : 2 */
+  int64_t state_stride[GJB_MAX_ARGS];   /* bytes between slots                  */
+  const void* shared[GJB_MAX_ARGS];     /* shared args, indexed by model arg position */
+  float scalars[GJB_MAX_ARGS];          /* scalar args, indexed by model arg position */
+  const void* obs[GJB_MAX_SITES];       /* observed sites: [T, ...] values (null = proposed) */
+  int64_t obs_stride[GJB_MAX_SITES];    /* bytes per step                       */
+  uint32_t site_flags[GJB_MAX_SITES];
+  float* logw;               /* [record ? T : 1, n] pre-resampling log-weights  */
+  int32_t* ancestors;        /* [slots, n]                                      */
+  double* lse;               /* [T, 3]                                          */
+  uint32_t* wmax;            /* [2] scratch                                     */
+  uint64_t* cta_mass;        /* [gjb_model_pf_grid(n)] scratch                  */
+  uint32_t* barrier;         /* [2] scratch                                     */
+} gjb_pf_args;
+
+/* CTAs the persistent kernel uses for n particles (sizes cta_mass). */
+int gjb_model_pf_grid(int64_t n);
+int gjb_model_pf_run(const gjb_pf_args* a, void* stream);
 
 /*
  * Batched MCMC drivers generated for the same model (one chain per lane).

@@ -111,6 +111,7 @@ def categorical_logpdf(v, logits):
     k = np.asarray(v).astype(np.int64)
     if ls.ndim == 1:
         return ls[k].astype(F32)
+    k = np.broadcast_to(k, ls.shape[:-1])
     return np.take_along_axis(ls, k[..., None], axis=-1)[..., 0].astype(F32)
 
 
@@ -165,34 +166,29 @@ def _bc(a, n):
 
 
 def normal_sample(words, idx, site, loc, scale):
-    w0, w1, _, _ = rng.site_words(words, idx, site, 0)
-    z, _ = rng.box_muller(w0, w1)
+    z = rng.quad_normal(words, idx, site)
     return (_f(loc) + _f(scale) * z).astype(F32)
 
 
 def uniform_sample(words, idx, site, low, high):
-    w0, _, _, _ = rng.site_words(words, idx, site, 0)
-    u = rng.u01(w0)
+    u = rng.quad_u01(words, idx, site)
     return (_f(low) + (_f(high) - _f(low)) * u).astype(F32)
 
 
 def flip_sample(words, idx, site, p):
-    w0, _, _, _ = rng.site_words(words, idx, site, 0)
-    return rng.u01(w0) < _f(p)
+    return rng.quad_u01(words, idx, site) < _f(p)
 
 
 def bernoulli_sample(words, idx, site, logits):
-    w0, _, _, _ = rng.site_words(words, idx, site, 0)
     l = _f(logits).astype(np.float64)
     p = (1.0 / (1.0 + np.exp(-l))).astype(F32)
-    return rng.u01(w0) < p
+    return rng.quad_u01(words, idx, site) < p
 
 
 def categorical_sample(words, idx, site, logits):
     """Inverse-CDF over exp(l - max l): first k with cumsum_k > u * total.
     (TFP draws argmax(logits + Gumbel); same distribution, different stream.)"""
-    w0, _, _, _ = rng.site_words(words, idx, site, 0)
-    u = rng.u01(w0)
+    u = rng.quad_u01(words, idx, site)
     l = _f(logits)
     if l.ndim == 1:
         l = np.broadcast_to(l, (u.shape[0], l.shape[0]))
@@ -215,8 +211,7 @@ def categorical_sample(words, idx, site, logits):
 
 
 def exponential_sample(words, idx, site, rate):
-    w0, _, _, _ = rng.site_words(words, idx, site, 0)
-    return (-_log(rng.u01(w0)) / _f(rate)).astype(F32)
+    return (-_log(rng.quad_u01(words, idx, site)) / _f(rate)).astype(F32)
 
 
 def mv_normal_diag_sample(words, idx, site, loc, scale_diag):
@@ -228,8 +223,7 @@ def mv_normal_diag_sample(words, idx, site, loc, scale_diag):
 
 
 def half_normal_sample(words, idx, site, scale):
-    w0, w1, _, _ = rng.site_words(words, idx, site, 0)
-    z, _ = rng.box_muller(w0, w1)
+    z = rng.quad_normal(words, idx, site)
     return (np.abs(z) * _f(scale)).astype(F32)
 
 

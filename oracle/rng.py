@@ -24,6 +24,13 @@ result does not depend on how particles are sharded over GPUs), ``site`` the
 1-based visit counter of the random choice inside the model (static.py:260-263
 starts its counter at 1 too) and ``chunk`` numbers successive 4-word blocks a
 site consumes (vector sites: chunk = dim // 4; rejection samplers: attempt).
+
+SCALAR sites driven by one uniform or one normal use QUAD streams: the four
+consecutive particles of global quad ``idx >> 2`` share the block
+``philox(ctr=(quad_lo, quad_hi, 0, site))`` and particle ``idx`` takes slot
+``idx & 3`` -- word ``slot`` for uniform-driven samplers, component ``slot``
+of ``(BM(w0,w1), BM(w2,w3))`` for normal-driven ones (one Philox block and
+two Box-Muller pairs per four particles instead of per particle).
 """
 
 from __future__ import annotations
@@ -231,6 +238,27 @@ def normal4(words, idx, site, chunk=0):
     z0, z1 = box_muller(w0, w1)
     z2, z3 = box_muller(w2, w3)
     return z0, z1, z2, z3
+
+
+def quad_slot_words(words, idx, site):
+    """The word slot ``idx & 3`` of the quad block of each lane (uint32 [n])."""
+    idx = np.asarray(idx, dtype=np.uint64)
+    w = site_words(words, idx >> np.uint64(2), site, 0)
+    sub = (idx & np.uint64(3)).astype(np.int64)
+    return np.choose(sub, w)
+
+
+def quad_u01(words, idx, site):
+    """One uniform per lane from the quad stream of a scalar site."""
+    return u01(quad_slot_words(words, idx, site))
+
+
+def quad_normal(words, idx, site):
+    """One N(0,1) per lane from the quad stream of a scalar site."""
+    idx = np.asarray(idx, dtype=np.uint64)
+    z = normal4(words, idx >> np.uint64(2), site, 0)
+    sub = (idx & np.uint64(3)).astype(np.int64)
+    return np.choose(sub, z).astype(F32)
 
 
 def normal_vec(words, idx, site, d):

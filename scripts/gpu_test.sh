@@ -1,0 +1,3 @@
+set -x
+cd $GRAFT_REPO_ROOT
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -25

@@ -22,6 +22,7 @@ ap.add_argument("--dim", type=int, default=1)
 ap.add_argument("--particles", type=int, default=1 << 20)
 ap.add_argument("--T", type=int, default=8)
 ap.add_argument("--graph", action="store_true")
+ap.add_argument("--mode", default="persistent")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 n, d, T = a.particles, a.dim, a.T
@@ -32,7 +33,7 @@ if d == 1:
     model, shared = lgssm_step, ()
 else:
     model, shared = lgssm_step_vec, (torch.full((d,), LG_Q, device=dev), torch.full((d,), LG_R, device=dev))
-pf = ParticleFilter(model, n)
+pf = ParticleFilter(model, n, mode=a.mode)
 res = pf.run(gj.key(1), x0, gj.C["y"].set(torch.from_numpy(ys).to(dev)), shared_args=shared, use_graph=a.graph)
 torch.cuda.synchronize()
 print("logZ", res.log_marginal_likelihood.item())

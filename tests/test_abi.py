@@ -48,7 +48,8 @@ def test_core_library_exports_every_declared_symbol(libs):
     from genjax_b200.runtime import cabi
 
     assert set(cabi.CORE_PROTOTYPES) == set(core), "ctypes prototypes and the header disagree"
-    assert core_lib.gjb_abi_version() == 1
+    version = int(re.search(r"#define GJB_ABI_VERSION (\d+)", open(HEADER).read()).group(1))
+    assert core_lib.gjb_abi_version() == version
 
 
 def test_model_libraries_export_every_declared_symbol(libs):

@@ -99,8 +99,8 @@ def test_step_vec_importance_matches_oracle(device, d):
     np.testing.assert_allclose(tr.get_score().cpu().numpy(), otr.get_score(), rtol=2e-5, atol=2e-4)
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_particle_filter_teacher_forced_vs_oracle(device, use_graph):
+@pytest.mark.parametrize("mode,use_graph", [("persistent", False), ("graph", False), ("graph", True)])
+def test_particle_filter_teacher_forced_vs_oracle(device, mode, use_graph):
     """Per step: CUDA log-weights == oracle log-weights (fp32 tolerance) given the same
     inputs, and the CUDA ancestors are BIT-EXACT the oracle's resample of the CUDA weights."""
     gj, step, _ = _models()
@@ -111,7 +111,7 @@ def test_particle_filter_teacher_forced_vs_oracle(device, use_graph):
     g = np.random.default_rng(3)
     x0 = g.standard_normal(n).astype(np.float32)
     key = gj.key(99)
-    pf = ParticleFilter(step, n)
+    pf = ParticleFilter(step, n, mode=mode)
     res = pf.run(key, torch.from_numpy(x0), gj.C["y"].set(torch.from_numpy(ys)), record=True, use_graph=use_graph)
     anc = res.ancestors.cpu().numpy()
     xs = res.history["state"][0].cpu().numpy()
@@ -192,3 +192,105 @@ def test_particle_filter_vec_matches_kalman(device):
         res = pf.run(gj.key(seed), x0, gj.C["y"].set(torch.from_numpy(ys)), shared_args=(q, r))
         ests.append(res.log_marginal_likelihood.item())
     assert np.mean(ests) == pytest.approx(exact, abs=0.15)
+
+
+@pytest.mark.parametrize("n", [1, 7, 2049, 300_001, 3_000_000])
+def test_persistent_filter_equals_three_kernel_filter(device, n):
+    """The one-launch cooperative filter and the 3-launches-per-step filter are the same
+    algorithm: bit-identical states, log-weights, ancestors and log-marginal increments
+    (n = 3M exercises several 2048-particle tiles per CTA)."""
+    gj, step, _ = _models()
+    from genjax_b200.inference.pf import ParticleFilter
+
+    T = 5
+    ys = osmc.simulate_lgssm(1, T, 1, A_, Q_, C_, R_)[:, 0]
+    x0 = torch.randn(n, generator=torch.Generator().manual_seed(n))
+    out = {}
+    for mode in ("persistent", "graph"):
+        res = ParticleFilter(step, n, mode=mode).run(gj.key(17), x0, gj.C["y"].set(torch.from_numpy(ys)), record=True, use_graph=False)
+        torch.cuda.synchronize()
+        out[mode] = res
+    a, b = out["persistent"], out["graph"]
+    assert torch.equal(a.ancestors, b.ancestors)
+    assert torch.equal(a.history["log_weights"], b.history["log_weights"])
+    assert torch.equal(a.history["state"][0], b.history["state"][0])
+    assert torch.equal(a.log_increments, b.log_increments)
+    assert torch.equal(a.state[0], b.state[0])
+    # and the last step's ancestors are the oracle's resample of those weights
+    _, k_res = osmc.pf_step_keys(orng.key(17), T - 1)
+    lw = a.history["log_weights"][T - 1].cpu().numpy()
+    assert np.array_equal(a.ancestors[T - 1].cpu().numpy(), osmc.resample_systematic(lw, k_res))
+
+
+def test_persistent_filter_non_record_matches_record(device):
+    gj, step, _ = _models()
+    from genjax_b200.inference.pf import ParticleFilter
+
+    n, T = 50_000, 9
+    ys = osmc.simulate_lgssm(4, T, 1, A_, Q_, C_, R_)[:, 0]
+    x0 = torch.randn(n, generator=torch.Generator().manual_seed(1))
+    r1 = ParticleFilter(step, n).run(gj.key(3), x0, gj.C["y"].set(torch.from_numpy(ys)), record=True)
+    s1, z1 = r1.state[0].clone(), r1.log_increments.clone()
+    r2 = ParticleFilter(step, n).run(gj.key(3), x0, gj.C["y"].set(torch.from_numpy(ys)), record=False)
+    assert torch.equal(s1, r2.state[0]) and torch.equal(z1, r2.log_increments)
+
+
+def o_hmm_step(h, z_prev, trans, obs):
+    z = h.categorical("z", trans[z_prev])
+    h.categorical("y", obs[z])
+    return z
+
+
+def _hmm_tables(K=16, sig_t=0.5, sig_o=0.5):
+    """Banded circulant log-potentials a la discrete_hmm.py:42-52 (scaled_circulant)."""
+    i = np.arange(K)
+    d = np.minimum((i[:, None] - i[None, :]) % K, (i[None, :] - i[:, None]) % K).astype(np.float64)
+    trans = -0.5 * (d / sig_t) ** 2
+    obs = -0.5 * (d / sig_o) ** 2
+    return trans.astype(np.float32), obs.astype(np.float32)
+
+
+def test_hmm_filter_teacher_forced_and_exact(device):
+    """16-state HMM bootstrap filter (BASELINE configs[3] model): categorical sites reading
+    rows of shared logit tables staged in shared memory; integer particle state."""
+    import genjax_b200 as gj
+    from genjax_b200.inference.pf import ParticleFilter
+    from genjax_b200.workloads import hmm_step
+
+    K, n, T = 16, 40_000, 10
+    trans, obs = _hmm_tables(K)
+    g = np.random.default_rng(3)
+    z = 0
+    ys = np.empty(T, dtype=np.int32)
+    pt = np.exp(trans - trans.max(1, keepdims=True)); pt /= pt.sum(1, keepdims=True)
+    po = np.exp(obs - obs.max(1, keepdims=True)); po /= po.sum(1, keepdims=True)
+    for t in range(T):
+        z = g.choice(K, p=pt[z])
+        ys[t] = g.choice(K, p=po[z])
+    z0 = g.integers(0, K, n).astype(np.int32)
+    res = ParticleFilter(hmm_step, n).run(
+        gj.key(11), torch.from_numpy(z0), gj.C["y"].set(torch.from_numpy(ys)),
+        shared_args=(torch.from_numpy(trans), torch.from_numpy(obs)), record=True)
+    anc = res.ancestors.cpu().numpy()
+    zs = res.history["state"][0].cpu().numpy()
+    lws = res.history["log_weights"].cpu().numpy()
+    okey = orng.key(11)
+    z_in = z0
+    mism = 0
+    for t in range(T):
+        kp, kr = osmc.pf_step_keys(okey, t)
+        otr, ow = ogfi.generate(o_hmm_step, orng.split(kp, n), {"y": np.int32(ys[t])}, (z_in, trans, obs))
+        same = zs[t] == otr.choices["z"]
+        mism += int((~same).sum())  # a draw within 1 ulp of a CDF edge may land in the neighbouring state
+        np.testing.assert_allclose(lws[t][same], ow[same], rtol=1e-5, atol=1e-5)
+        assert np.array_equal(anc[t], osmc.resample_systematic(lws[t], kr))
+        z_in = zs[t][anc[t]]
+    assert mism <= 2e-5 * n * T
+    # exact forward algorithm for the empirical initial distribution
+    alpha = np.bincount(z0, minlength=K) / n
+    ll = 0.0
+    for t in range(T):
+        alpha = (alpha @ pt) * po[:, ys[t]]
+        ll += np.log(alpha.sum())
+        alpha /= alpha.sum()
+    assert res.log_marginal_likelihood.item() == pytest.approx(ll, abs=0.05)
