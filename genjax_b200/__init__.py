@@ -29,6 +29,7 @@ from .gen.distributions import (
     exponential,
     flip,
     gamma,
+    gmm_diag,
     half_normal,
     mv_normal_diag,
     normal,

@@ -100,6 +100,43 @@ struct Categorical {
   }
 };
 
+// ------------------------------------------------ mixture of diagonal Gaussians
+// gmm_diag(logits[K], mu[K, D] row major, sigma[K]); value: D floats of one thread
+struct GmmDiag {
+  template <int K, int D>
+  __device__ static __forceinline__ void sample(const Lane& l, uint32_t site, const float* logits, const float* mu,
+                                                const float* sigma, float* out) {
+    const int k = Categorical::sample(u01(l.words(site, 0xFFFFu).x), logits, K);
+#pragma unroll
+    for (int c = 0; c < (D + 3) / 4; ++c) {
+      const float4 z = normal4(l, site, (uint32_t)c);
+      const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (4 * c + t < D) out[4 * c + t] = mu[k * D + 4 * c + t] + sigma[k] * zz[t];
+    }
+  }
+  template <int K, int D>
+  __device__ static __forceinline__ float logpdf(const float* v, const float* logits, const float* mu, const float* sigma) {
+    float m = -INFINITY;
+    for (int j = 0; j < K; ++j) m = fmaxf(m, logits[j]);
+    float tot = 0.0f;
+    for (int j = 0; j < K; ++j) tot += expf(logits[j] - m);
+    const float lse = m + logf(tot);
+    float comp[K];
+    float M = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+      float lp = 0.0f;
+      for (int d = 0; d < D; ++d) lp += Normal::logpdf(v[d], mu[k * D + d], sigma[k]);
+      comp[k] = (logits[k] - lse) + lp;
+      M = fmaxf(M, comp[k]);
+    }
+    float s = 0.0f;
+    for (int k = 0; k < K; ++k) s += expf(comp[k] - M);
+    return M + logf(s);
+  }
+};
+
 // -------------------------------------------------------------- gamma, beta
 // Marsaglia-Tsang; attempt t uses chunk chunk0+t: words (x,y) -> normal,
 // z -> acceptance uniform, w (attempt 0) -> boost uniform for a < 1.

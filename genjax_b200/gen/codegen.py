@@ -61,9 +61,10 @@ class _Emitter:
     vectors (True) or per-thread float arrays (False).  Values that do not
     depend on particle data are emitted into the ``Uni`` struct instead."""
 
-    def __init__(self, ir: ModelIR, group: bool):
+    def __init__(self, ir: ModelIR, group: bool, const_prefix: str = "cv"):
         self.ir = ir
         self.group = group
+        self.const_prefix = const_prefix
         self.D = ir.width
         self.lines: list[str] = []  # per-particle body
         self.uni_decl: list[str] = []  # members of struct Uni
@@ -73,6 +74,7 @@ class _Emitter:
         self._uniform: dict[int, bool] = {}
         self._v4cache: dict[int, str] = {}
         self.n_tmp = 0
+        self.hoist_vectors = True  # False: width-D temporaries are recomputed per use instead of living in Uni
 
     def w(self, s: str):
         self.lines.append("      " + s)
@@ -89,10 +91,12 @@ class _Emitter:
                 u = True
             elif e.op == "arg":
                 u = e.attr["kind"] != "particle"
-            elif e.op == "site":
+            elif e.op in ("site", "chain_step"):
                 u = False
             else:
                 u = all(self.is_uniform(i) for i in e.ins)
+                if u and e.ndim == 1 and e.op != "row" and not self.hoist_vectors:
+                    u = False
             self._uniform[e._id] = u
         return u
 
@@ -160,7 +164,7 @@ class _Emitter:
             return
         if op == "constvec":
             vals = ", ".join(E.fmt_float(v) if e.dtype == F32 else f"(float){int(v)}" for v in e.attr)
-            cname = f"cv{len(self.consts)}"
+            cname = f"{self.const_prefix}{len(self.consts)}"
             self.consts.append(f"__device__ const float {cname}[{len(e.attr)}] = {{{vals}}};")
             self.names[e._id] = cname
             return
@@ -330,6 +334,14 @@ class _Emitter:
                 lp = d.emit_logpdf(f"s{j}", a, self)
             self.w(f"if {need} {{ const float lp = {lp}; score += lp; if ({fl} & GJB_SITE_WEIGHT) weight += lp; }}")
             return
+        if d.name == "gmm_diag":
+            logits, mu, sigma = s.args
+            K, D = mu.shape
+            a = f"{self.ref(logits)}, {self.ref(mu)}, {self.ref(sigma)}"
+            self.w(f"float s{j}[{D}];")
+            self.w(f"if ({fl} & GJB_SITE_SAMPLE) gjb::GmmDiag::sample<{K}, {D}>(rng, {j + 1}u, {a}, s{j}); else {{ for (int k = 0; k < {D}; ++k) s{j}[k] = in_s{j}[k]; }}")
+            self.w(f"if {need} {{ const float lp = gjb::GmmDiag::logpdf<{K}, {D}>(s{j}, {a}); score += lp; if ({fl} & GJB_SITE_WEIGHT) weight += lp; }}")
+            return
         if d.name != "mv_normal_diag":
             raise NotImplementedError(d.name)
         loc, scale = s.args
@@ -379,20 +391,23 @@ def _shared_decls(ir: ModelIR) -> tuple[list[str], list[str]]:
     return decl, stage
 
 
-def generate(ir: ModelIR, pf_obs: tuple | None = None) -> str:
+def generate(ir: ModelIR, pf_obs: tuple | None = None, chain=None) -> str:
     """CUDA source for ``ir``.  ``pf_obs`` (site indices observed at every
     filter step) bakes the per-site flags of the persistent filter kernel in at
     compile time, so the paths a bootstrap filter never takes (reading proposed
     sites, scoring unweighted ones) are removed from ``pf_kernel``."""
     G = group_lanes(ir.width)
-    gen = _Generator(ir, G, pf_obs)
+    if any(s.dist.vector and s.dist.name != "mv_normal_diag" for s in ir.sites):
+        G = 0  # lane-group kernels know mv_normal_diag only; other vector primitives run on per-thread arrays
+    gen = _Generator(ir, G, pf_obs, chain)
     return gen.source()
 
 
 class _Generator:
-    def __init__(self, ir: ModelIR, G: int, pf_obs: tuple | None = None):
+    def __init__(self, ir: ModelIR, G: int, pf_obs: tuple | None = None, chain=None):
         self.ir = ir
         self.G = G
+        self.chain = chain
         self.pf_obs = None if pf_obs is None else tuple(sorted(int(j) for j in pf_obs))
         self.group = G > 0
         self.em = _Emitter(ir, group=self.group)
@@ -793,11 +808,17 @@ class _Generator:
         pf = self.pf_supported()
         if pf:
             out.extend(self.pf_kernel())
+        chain_ext = None
+        if self.chain is not None:
+            from . import codegen_chain
+
+            chain_ns, chain_ext = codegen_chain.generate_chain(self.ir, self.chain)
+            out.append(chain_ns)
         out.append("}  // namespace")
-        out.append(self.extern_c(pf))
+        out.append(self.extern_c(pf, chain_ext))
         return "\n".join(out) + "\n"
 
-    def extern_c(self, pf: bool) -> str:
+    def extern_c(self, pf: bool, chain_ext: str | None = None) -> str:
         ir = self.ir
         mapping = "group" if self.group else "quad"
         info = _info_json(ir, mapping, max(self.G, 1)).replace("\\", "\\\\").replace('"', '\\"')
@@ -852,6 +873,10 @@ int gjb_model_pf_run(const gjb_pf_args* a, void* stream) {{
 int gjb_model_pf_grid(int64_t n) { (void)n; return GJB_E_MODE; }
 int gjb_model_pf_run(const gjb_pf_args* a, void* stream) { (void)a; (void)stream; return GJB_E_MODE; }
 """
+        chain_code = chain_ext if chain_ext is not None else """
+int gjb_model_mh_chain(const gjb_chain_args* a, void* stream) { (void)a; (void)stream; return GJB_E_MODE; }
+int gjb_model_hmc_chain(const gjb_chain_args* a, void* stream) { (void)a; (void)stream; return GJB_E_MODE; }
+"""
         return f"""
 extern "C" {{
 const char* gjb_model_info(void) {{ return "{info}"; }}
@@ -867,7 +892,6 @@ int gjb_model_launch(const gjb_model_args* a, void* stream) {{
   return (int)cudaGetLastError();
 }}
 {pf_code}
-int gjb_model_mh_chain(const gjb_chain_args* a, void* stream) {{ (void)a; (void)stream; return GJB_E_MODE; }}
-int gjb_model_hmc_chain(const gjb_chain_args* a, void* stream) {{ (void)a; (void)stream; return GJB_E_MODE; }}
+{chain_code}
 }}
 """

@@ -199,6 +199,90 @@ class _MvNormalDiag(Distribution):
         return F32, (d,)
 
 
+class _RepeatedNormal(_MvNormalDiag):
+    """``normal.repeat(n=N)`` / ``normal.vmap(...)`` over N iid draws sharing (or
+    zipping) loc and scale: one vector site scored like mv_normal_diag
+    (combinators/repeat.py:37-41, vmap.py:180-218: score = sum of the inner scores)."""
+
+    def __init__(self, n: int):
+        self.n = int(n)
+
+    def _canonical(self, args, kwargs):
+        loc, scale = _Normal._canonical(normal, args, kwargs)
+        zeros = Expr("constvec", (), F32, (self.n,), tuple(0.0 for _ in range(self.n)))
+        out = []
+        for a in (loc, scale):
+            a = E.lift(a)
+            if a.ndim == 0:
+                a = a + zeros
+            elif a.shape[0] != self.n:
+                raise TypeError(f"argument of width {a.shape[0]} under repeat/vmap of n={self.n}")
+            out.append(a)
+        return out
+
+
+def _normal_repeat(self, n: int):
+    return _RepeatedNormal(n)
+
+
+def _normal_vmap(self, in_axes=0, axis_size: int | None = None):
+    if axis_size is None:
+        raise TypeError("normal.vmap needs axis_size=N here (shapes are static at capture time)")
+    return _RepeatedNormal(axis_size)
+
+
+_Normal.repeat = _normal_repeat
+_Normal.vmap = _normal_vmap
+
+
+class _GmmDiag(Distribution):
+    """Mixture of K diagonal Gaussians with one scale per component:
+    ``gmm_diag(logits[K], mu[K, D], sigma[K])`` -- the fusable form of the
+    cookbook's custom ``GaussianMixture`` ExactDensity
+    (docs/cookbook/inactive/expressivity/custom_distribution.ipynb cell 9):
+    sample = ancestral (component, then N(mu_k, sigma_k)), logpdf =
+    logsumexp_k(log_softmax(logits)_k + sum_d logN(x_d; mu_kd, sigma_k))."""
+
+    name, cuda, n_args, vector = "gmm_diag", "GmmDiag", 3, True
+    rng_kind = "lane"
+
+    def value_type(self, cargs):
+        logits, mu, sigma = cargs
+        if not (mu.op == "arg" and mu.attr["kind"] == "shared" and mu.ndim == 2):
+            raise TypeError("gmm_diag needs mu as a shared [K, D] argument")
+        if logits.ndim != 1 or sigma.ndim != 1 or logits.shape[0] != mu.shape[0] or sigma.shape[0] != mu.shape[0]:
+            raise TypeError("gmm_diag needs logits [K], mu [K, D], sigma [K]")
+        return F32, (mu.shape[1],)
+
+    def logpdf_expr(self, v, args):
+        import math
+
+        logits, mu, sigma = args
+        K = logits.shape[0]
+        m = logits[0]
+        for k in range(1, K):
+            m = E.binary("max", m, logits[k])
+        tot = None
+        for k in range(K):
+            t = E.unary("exp", logits[k] - m)
+            tot = t if tot is None else tot + t
+        lse = m + E.unary("log", tot)
+        comps = []
+        for k in range(K):
+            sk = sigma[k]
+            z = v / sk - mu[k] / sk
+            lpk = E.vsum(E.const(-0.5) * E.unary("square", z) - (E.const(0.5 * math.log(2.0 * math.pi)) + E.unary("log", sk)))
+            comps.append((logits[k] - lse) + lpk)
+        M = comps[0]
+        for c in comps[1:]:
+            M = E.binary("max", M, c)
+        tot = None
+        for c in comps:
+            t = E.unary("exp", c - M)
+            tot = t if tot is None else tot + t
+        return M + E.unary("log", tot)
+
+
 normal = _Normal()
 uniform = _Uniform()
 exponential = _Exponential()
@@ -209,10 +293,11 @@ flip = _Flip()
 bernoulli = _Bernoulli()
 categorical = _Categorical()
 mv_normal_diag = _MvNormalDiag()
+gmm_diag = _GmmDiag()
 
 REGISTRY: dict[str, Distribution] = {
     d.name: d
-    for d in (normal, uniform, exponential, half_normal, gamma, beta, flip, bernoulli, categorical, mv_normal_diag)
+    for d in (normal, uniform, exponential, half_normal, gamma, beta, flip, bernoulli, categorical, mv_normal_diag, gmm_diag)
 }
 
 
@@ -355,9 +440,28 @@ def _d_sample(self, key, *args, **kwargs):
     return _d_simulate(self, key, a).get_retval()
 
 
+def _auto_batch(self, v, args):
+    """``dist.logpdf(values[n], ...)``: jax broadcasting over a leading axis becomes one batched launch."""
+    import torch
+
+    from .static import Batched
+
+    ev = 1 if self.vector else 0
+    if not (isinstance(v, torch.Tensor) and v.ndim == ev + 1):
+        return v, args
+    n = v.shape[0]
+    out = []
+    for a in args:
+        if isinstance(a, torch.Tensor) and a.ndim >= 1 and a.shape[0] == n and (a.ndim == ev + 1 or not self.vector):
+            a = Batched(a)
+        out.append(a)
+    return Batched(v), tuple(out)
+
+
 def _d_logpdf(self, v, *args, **kwargs):
     from ..core.choice_map import ChoiceMap
 
+    v, args = _auto_batch(self, v, args)
     a = (args, kwargs) if kwargs else args
     score, _ = _d_assess(self, ChoiceMap.choice(v), a)
     return score

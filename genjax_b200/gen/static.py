@@ -111,9 +111,9 @@ class CompiledModel:
 _COMPILED: dict[str, CompiledModel] = {}
 
 
-def compile_ir(ir: ModelIR, pf_obs: tuple | None = None) -> CompiledModel:
+def compile_ir(ir: ModelIR, pf_obs: tuple | None = None, chain=None) -> CompiledModel:
     ir.digest = cap.ir_fingerprint(ir)
-    source = codegen.generate(ir, pf_obs)
+    source = codegen.generate(ir, pf_obs, chain)
     key = build.model_digest(source)
     cm = _COMPILED.get(key)
     if cm is None:

@@ -20,6 +20,8 @@ GJB_MAX_RETS = 8
 SITE_SAMPLE = 1
 SITE_WEIGHT = 2
 SITE_BCAST = 4
+CHAIN_HAVE_LOGP = 1
+CHAIN_NO_ACCEPT = 2
 
 _p = C.c_void_p
 _i64 = C.c_int64
@@ -125,6 +127,9 @@ class ChainArgs(C.Structure):
         ("state", _p),
         ("logp", _p),
         ("accept_count", _p),
+        ("alpha_out", _p),
+        ("state_width", _i32),
+        ("flags", _u32),
         ("n_steps", _i32),
         ("step0", _i32),
         ("step_size", C.c_float),

@@ -227,17 +227,24 @@ int gjb_model_pf_run(const gjb_pf_args* a, void* stream);
  *         reproduces the carried-gradient quirk at hmc.py:186.
  * state: [n_chains, D] latent values (site order), logp: [n_chains].
  */
+#define GJB_CHAIN_HAVE_LOGP 1u  /* logp[] holds the log-density of state[] on entry (MH)      */
+#define GJB_CHAIN_NO_ACCEPT 2u  /* always move: the bare request.edit of the reference, whose
+                                   weight (alpha_out) the caller feeds to its own accept step */
+
 typedef struct gjb_chain_args {
-  int64_t n;
-  uint64_t idx_offset;
+  int64_t n;                 /* chains in this launch                           */
+  uint64_t idx_offset;       /* global index of local chain 0 (RNG lane)        */
   uint32_t key0, key1;
   const void* args[GJB_MAX_ARGS];
   float scalars[GJB_MAX_ARGS];
   const void* site_in[GJB_MAX_SITES];  /* observed (unselected) site values, broadcast or per chain */
   uint32_t site_flags[GJB_MAX_SITES];
-  float* state;              /* in/out [n, D] selected-site values              */
-  float* logp;               /* in/out [n]                                      */
+  float* state;              /* in/out [n, state_width] selected-site values (site order) */
+  float* logp;               /* in/out [n] total log-density of the chain's trace */
   int32_t* accept_count;     /* in/out [n] (nullable)                           */
+  float* alpha_out;          /* nullable [n]: weight of the LAST transition (w + bwd - fwd / HMC alpha) */
+  int32_t state_width;       /* D: must equal the width the kernel was generated for */
+  uint32_t flags;            /* GJB_CHAIN_*                                     */
   int32_t n_steps;           /* transitions per launch                          */
   int32_t step0;             /* global index of the first transition (RNG)      */
   float step_size;           /* MH proposal scale / HMC eps                     */
