@@ -79,7 +79,9 @@ __global__ void __launch_bounds__(256) lse_finalize_kernel(const uint64_t* __res
 
 // ------------------------------------------------------------ systematic
 
-__global__ void __launch_bounds__(kThreads) resample_systematic_kernel(const __grid_constant__ gjb_resample_args R) {
+__global__ void __launch_bounds__(kThreads) resample_systematic_kernel(const __grid_constant__ gjb_resample_args R,
+                                                                       const __grid_constant__ gjb_peers P) {
+  const gjb_peers* peers = P.world > 1 ? &P : nullptr;
   const int64_t n = R.n, n_total = R.n_total, out_lo = R.out_lo, out_n = R.out_n, anc_base = R.anc_base;
   uint32_t key0 = R.key0, key1 = R.key1;
   uint64_t key_index = R.key_index;
@@ -120,13 +122,16 @@ __global__ void __launch_bounds__(kThreads) resample_systematic_kernel(const __g
     for (int k = tid; k < kTile; k += kThreads) {
       const int64_t i = tile_base + k;
       const int64_t j = anc_base + i;
-      if (i < n && j >= out_lo && j < out_lo + out_n) R.ancestors[j - out_lo] = (int32_t)j;
+      if (i < n && j >= out_lo && j < out_lo + out_n) {
+        const AncRoute route{peers ? nullptr : R.ancestors - out_lo, peers};
+        *route.at((int32_t)j) = (int32_t)j;
+      }
     }
     return;
   }
   const float M = ref_max(R.wmax, R.m_global);
   const double u0 = resample_u0(key0, key1, key_index);
-  resample_tile<false>(R.logw, n, tile_base, M, off, S, n_total, u0, out_lo, out_n, anc_base, R.ancestors, sm, heads);
+  resample_tile<false>(R.logw, n, tile_base, M, off, S, n_total, u0, out_lo, out_n, anc_base, R.ancestors, sm, heads, nullptr, peers);
 }
 
 // ----------------------------------------------------------- multinomial
@@ -203,6 +208,69 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const T* __restrict__ 
     dst[k] = __ldg(src + (int64_t)__ldg(anc + row) * w + col);
   }
 }
+
+template <typename T>
+__global__ void __launch_bounds__(256) gather_rows_peers_kernel(const __grid_constant__ gjb_peers P,
+                                                                const int32_t* __restrict__ anc, T* __restrict__ dst,
+                                                                int64_t n_out, int32_t w) {
+  const int64_t total = n_out * w;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = k / w;
+    const int32_t col = (int32_t)(k - row * w);
+    const int64_t g = __ldg(anc + row);
+    const int64_t owner = g / P.n_per_rank;
+    const T* src = reinterpret_cast<const T*>(P.base[owner]);
+    dst[k] = __ldg(src + (g - owner * P.n_per_rank) * w + col);
+  }
+}
+
+// ------------------------------------------------------- cross-rank exchange
+// pad layout on every rank: uint64 [2 slots][GJB_MAX_RANKS sources][2] = {value, tag}
+__global__ void __launch_bounds__(256) exchange_kernel(const __grid_constant__ gjb_xchg_args X) {
+  __shared__ uint64_t red[8];
+  __shared__ uint64_t vals[GJB_MAX_RANKS];
+  const int tid = threadIdx.x;
+  const uint64_t tag = (__ldg(X.epoch) << 32) + X.tag_offset;
+  const int slot = (int)(X.tag_offset & 1);
+  uint64_t mine = 0;
+  if (X.mode == GJB_XCHG_MAX) {
+    mine = (uint64_t)__ldg(X.wmax);
+  } else if (X.mode == GJB_XCHG_MASS) {
+    uint64_t s = 0;
+    for (int t = tid; t < X.n_tiles; t += blockDim.x) s += X.tile_mass[t];
+    s = warp_sum_u64(s);
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    for (int w = 0; w < 8; ++w) mine += red[w];
+  }
+  if (tid < X.world) {
+    // push {value, tag} into slot[rank] of peer `tid`'s pad; value first, system fence, then the tag
+    volatile uint64_t* dst = X.pads[tid] + ((size_t)slot * GJB_MAX_RANKS + X.rank) * 2;
+    dst[0] = mine;
+    __threadfence_system();
+    dst[1] = tag;
+    // wait for rank `tid`'s entry in my own pad
+    volatile uint64_t* src = X.pads[X.rank] + ((size_t)slot * GJB_MAX_RANKS + tid) * 2;
+    while (src[1] != tag) { }
+    __threadfence_system();
+    vals[tid] = src[0];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (X.mode == GJB_XCHG_MAX) {
+      uint32_t m = 0;
+      for (int r = 0; r < X.world; ++r) m = max(m, (uint32_t)vals[r]);
+      *X.m_global = fdec(m);
+    } else if (X.mode == GJB_XCHG_MASS) {
+      uint64_t pre = 0, tot = 0;
+      for (int r = 0; r < X.world; ++r) { if (r < X.rank) pre += vals[r]; tot += vals[r]; }
+      *X.c_offset = pre;
+      *X.s_total = tot;
+    }
+  }
+}
+
+__global__ void epoch_bump_kernel(uint64_t* epoch) { *epoch += 1; }
 
 // ------------------------------------------------------------- RNG hooks
 
@@ -292,7 +360,21 @@ int gjb_resample_systematic(const gjb_resample_args* a, void* stream) {
   if (a->n <= 0 || a->n_total <= 0 || a->out_n < 0 || a->out_lo < 0) return GJB_E_ARG;
   if (a->n_total > 0x7fffffffLL) return GJB_E_RANGE;  // int32 ancestors
   const int64_t tiles = (a->n + kTile - 1) / kTile;
-  resample_systematic_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a);
+  gjb_peers none = {};
+  resample_systematic_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a, none);
+  return launch_status();
+}
+
+int gjb_resample_systematic_peers(const gjb_resample_args* a, const gjb_peers* anc, void* stream) {
+  if (!a || !anc || !a->logw || !a->tile_mass || (!a->wmax && !a->m_global)) return GJB_E_ARG;
+  if (anc->world < 1 || anc->world > GJB_MAX_RANKS || anc->n_per_rank <= 0 || (anc->n_per_rank & 3)) return GJB_E_ARG;
+  if (a->n <= 0 || a->n_total != anc->n_per_rank * anc->world || a->out_lo != 0 || a->out_n != a->n_total) return GJB_E_ARG;
+  if (a->n_total > 0x7fffffffLL) return GJB_E_RANGE;
+  for (int r = 0; r < anc->world; ++r) if (!anc->base[r]) return GJB_E_ARG;
+  const int64_t tiles = (a->n + kTile - 1) / kTile;
+  gjb_peers p = *anc;
+  if (p.world == 1) p.world = 2, p.base[1] = p.base[0];  // keep the routed path even for one rank (tests)
+  resample_systematic_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a, p);
   return launch_status();
 }
 
@@ -326,6 +408,42 @@ int gjb_gather_rows(const void* src, const int32_t* ancestors, void* dst, int64_
     gather_rows_kernel<uint32_t><<<grid_for(n_out * w, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
         (const uint32_t*)src, ancestors, (uint32_t*)dst, n_out, w);
   }
+  return launch_status();
+}
+
+int gjb_gather_rows_peers(const gjb_peers* src, const int32_t* ancestors, void* dst, int64_t n_out, int32_t row_bytes,
+                          void* stream) {
+  if (!src || !ancestors || !dst || n_out < 0 || row_bytes <= 0 || (row_bytes & 3)) return GJB_E_ARG;
+  if (src->world < 1 || src->world > GJB_MAX_RANKS || src->n_per_rank <= 0) return GJB_E_ARG;
+  for (int r = 0; r < src->world; ++r) if (!src->base[r]) return GJB_E_ARG;
+  if (n_out == 0) return 0;
+  const bool v16 = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+  if (v16) {
+    const int w = row_bytes / 16;
+    gather_rows_peers_kernel<uint4><<<grid_for(n_out * w, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+        *src, ancestors, (uint4*)dst, n_out, w);
+  } else {
+    const int w = row_bytes / 4;
+    gather_rows_peers_kernel<uint32_t><<<grid_for(n_out * w, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+        *src, ancestors, (uint32_t*)dst, n_out, w);
+  }
+  return launch_status();
+}
+
+int gjb_exchange(const gjb_xchg_args* a, void* stream) {
+  if (!a || a->world < 1 || a->world > GJB_MAX_RANKS || a->rank < 0 || a->rank >= a->world || !a->epoch) return GJB_E_ARG;
+  if (a->tag_offset == 0 || a->tag_offset >= (1ull << 32)) return GJB_E_ARG;
+  for (int r = 0; r < a->world; ++r) if (!a->pads[r]) return GJB_E_ARG;
+  if (a->mode == GJB_XCHG_MAX) { if (!a->wmax || !a->m_global) return GJB_E_ARG; }
+  else if (a->mode == GJB_XCHG_MASS) { if (!a->tile_mass || a->n_tiles <= 0 || !a->c_offset || !a->s_total) return GJB_E_ARG; }
+  else if (a->mode != GJB_XCHG_BARRIER) return GJB_E_MODE;
+  exchange_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*a);
+  return launch_status();
+}
+
+int gjb_epoch_bump(uint64_t* epoch, void* stream) {
+  if (!epoch) return GJB_E_ARG;
+  epoch_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(epoch);
   return launch_status();
 }
 

@@ -33,16 +33,31 @@ __device__ __forceinline__ T ldx(const T* p) { return kCg ? __ldcg(p) : __ldg(p)
 template <bool kCg>
 __device__ __forceinline__ float ldf(const float* p) { return kCg ? __ldcg(p) : __ldg(p); }
 
+// base pointer and local row of a per-particle argument row that may live on a peer rank
+__device__ __forceinline__ const void* arg_base(const void* local, const gjb_peers* P, int64_t& row) {
+  if (!P) return local;
+  const int64_t owner = row / P->n_per_rank;
+  row -= owner * P->n_per_rank;
+  return P->base[owner];
+}
+
 // 4 consecutive 32-bit words starting at element i0 (elements u in [lo, hi)
 // valid), optionally through a gather index per element or broadcast from
 // element 0.
 template <bool kCg>
 __device__ __forceinline__ void load4(const void* __restrict__ base, int64_t i0, int lo, int hi, const int32_t (&g)[4],
-                                      bool gathered, bool bcast, uint32_t (&w)[4]) {
+                                      bool gathered, bool bcast, uint32_t (&w)[4], const gjb_peers* peers = nullptr) {
   const uint32_t* __restrict__ p = reinterpret_cast<const uint32_t*>(base);
   if (bcast) {
     const uint32_t v = __ldg(p);
     w[0] = w[1] = w[2] = w[3] = v;
+  } else if (gathered && peers) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int64_t row = g[u];
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(arg_base(base, peers, row));
+      w[u] = (u >= lo && u < hi) ? ldx<kCg>(q + row) : 0u;
+    }
   } else if (gathered) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) w[u] = (u >= lo && u < hi) ? ldx<kCg>(p + g[u]) : 0u;

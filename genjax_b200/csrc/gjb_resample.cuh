@@ -14,9 +14,22 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "genjax_b200.h"
 #include "gjb_rng.cuh"
 
 namespace gjb {
+
+// where offspring slot j lives: a local array, or the owning rank's array (peer mapped)
+struct AncRoute {
+  int32_t* local;            // single device: ancestors - out_lo
+  const gjb_peers* peers;    // multi device (kernel parameter space)
+  __device__ __forceinline__ int32_t* at(int32_t j) const {
+    if (!peers) return local + j;
+    const int32_t npr = (int32_t)peers->n_per_rank;
+    const int32_t owner = j / npr;
+    return reinterpret_cast<int32_t*>(const_cast<void*>(peers->base[owner])) + (j - owner * npr);
+  }
+};
 
 constexpr int kTile = 2048;      // particles per tile (fixed: part of the ABI)
 constexpr int kThreads = 256;    // threads per block in tile routines
@@ -138,7 +151,8 @@ template <bool kCg>
 __device__ __forceinline__ uint64_t resample_tile(const float* __restrict__ logw, int64_t n, int64_t tile_base, float M,
                                                   uint64_t off, uint64_t S, int64_t n_total, double u0, int64_t out_lo,
                                                   int64_t out_n, int64_t anc_base, int32_t* __restrict__ ancestors,
-                                                  TileSmem& sm, int32_t* heads, const uint64_t* qin = nullptr) {
+                                                  TileSmem& sm, int32_t* heads, const uint64_t* qin = nullptr,
+                                                  const gjb_peers* peers = nullptr) {
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   uint64_t q[kItems];
@@ -187,7 +201,7 @@ __device__ __forceinline__ uint64_t resample_tile(const float* __restrict__ logw
   if (tid == kThreads - 1) sm.range[1] = cnt[kItems];
   __syncthreads();
   const int32_t r_lo = sm.range[0], r_hi = sm.range[1];
-  int32_t* __restrict__ anc = ancestors - out_lo;
+  const AncRoute anc{peers ? nullptr : ancestors - out_lo, peers};
   const int32_t a0 = (int32_t)(anc_base + tile_base) - 1;  // heads hold local index + 1
   for (int32_t wb = r_lo; wb < r_hi; wb += kWin) {
     const int32_t we = min(wb + kWin, r_hi);
@@ -203,7 +217,7 @@ __device__ __forceinline__ uint64_t resample_tile(const float* __restrict__ logw
     const int32_t fill = sm.fill;
     if (fill) {  // degenerate weights: coalesced constant fill, no scan
       const int32_t a = a0 + fill;
-      for (int32_t j = wb + tid; j < we; j += kThreads) anc[j] = a;
+      for (int32_t j = wb + tid; j < we; j += kThreads) *anc.at(j) = a;
       __syncthreads();
       if (tid == 0) sm.fill = 0;
       __syncthreads();
@@ -245,7 +259,8 @@ __device__ __forceinline__ uint64_t resample_tile(const float* __restrict__ logw
     pre += a0;
     // 4. coalesced write of the window
     const int32_t jb = wb + tid * per;
-    const bool vec = (reinterpret_cast<uintptr_t>(anc + jb) & 15) == 0;
+    // 128-bit stores need slot alignment (peer blocks are multiples of 4 slots, so an aligned group has one owner)
+    const bool vec = peers ? ((jb & 3) == 0) : ((reinterpret_cast<uintptr_t>(anc.local + jb) & 15) == 0);
 #pragma unroll
     for (int c4 = 0; c4 < kPer / 4; ++c4) {
       if (4 * c4 < per) {
@@ -253,12 +268,12 @@ __device__ __forceinline__ uint64_t resample_tile(const float* __restrict__ logw
         const int4 o4 = make_int4(max(a0 + v[4 * c4], pre), max(a0 + v[4 * c4 + 1], pre), max(a0 + v[4 * c4 + 2], pre),
                                   max(a0 + v[4 * c4 + 3], pre));
         if (vec && j + 4 <= we) {
-          *reinterpret_cast<int4*>(anc + j) = o4;
+          *reinterpret_cast<int4*>(anc.at(j)) = o4;
         } else {
-          if (j < we) anc[j] = o4.x;
-          if (j + 1 < we) anc[j + 1] = o4.y;
-          if (j + 2 < we) anc[j + 2] = o4.z;
-          if (j + 3 < we) anc[j + 3] = o4.w;
+          if (j < we) *anc.at(j) = o4.x;
+          if (j + 1 < we) *anc.at(j + 1) = o4.y;
+          if (j + 2 < we) *anc.at(j + 2) = o4.z;
+          if (j + 3 < we) *anc.at(j + 3) = o4.w;
         }
       }
     }

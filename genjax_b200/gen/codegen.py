@@ -459,6 +459,7 @@ class _Generator:
         out.append("struct Io {  // what one launch (or one filter step) reads and writes")
         out.append("  const void* args[NA]; const void* site_in[NS]; void* site_out[NS]; void* ret_out[NR];")
         out.append("  const int32_t* gather; const float* score_in; const float* weight_in; float* score_out; float* weight_out;")
+        out.append("  const gjb_peers* peers;  // nullable device array [NA]: gathered rows may live on peer ranks")
         out.append("};")
         out.append("struct Uni {  // particle-invariant values, computed once per thread per launch")
         out.append("  float sc[NA];")
@@ -492,14 +493,15 @@ class _Generator:
             if a.shape == ():
                 P.append(f"  {ct} a{i};")
                 conv = "(int)w[u]" if a.dtype == I32 else "gjb::as_f(w[u])"
-                pre.append(f"    gjb::load4<kCg>(io.args[{i}], i0, lo, hi, g, io.gather != nullptr, false, w);")
+                pre.append(f"    gjb::load4<kCg>(io.args[{i}], i0, lo, hi, g, io.gather != nullptr, false, w, (io.gather && io.peers) ? io.peers + {i} : nullptr);")
                 pre.append(f"    for (int u = 0; u < 4; ++u) p[u].a{i} = {conv};")
                 bind.append(f"      const {ct} a{i} = p[u].a{i};")
             else:
                 D = a.shape[0]
                 P.append(f"  float a{i}[{D}];")
-                pre.append(f"    for (int u = 0; u < 4; ++u) {{ const int64_t row = io.gather ? (int64_t)g[u] : i0 + u;")
-                pre.append(f"      for (int k = 0; k < {D}; ++k) p[u].a{i}[k] = (u >= lo && u < hi) ? gjb::ldf<kCg>(reinterpret_cast<const float*>(io.args[{i}]) + row * {D} + k) : 0.0f; }}")
+                pre.append(f"    for (int u = 0; u < 4; ++u) {{ int64_t row = io.gather ? (int64_t)g[u] : i0 + u;")
+                pre.append(f"      const float* rb = reinterpret_cast<const float*>(gjb::arg_base(io.args[{i}], (io.gather && io.peers) ? io.peers + {i} : nullptr, row));")
+                pre.append(f"      for (int k = 0; k < {D}; ++k) p[u].a{i}[k] = (u >= lo && u < hi) ? gjb::ldf<kCg>(rb + row * {D} + k) : 0.0f; }}")
                 bind.append(f"      const float* a{i} = p[u].a{i};")
         for s in ir.sites:
             j = s.index
@@ -609,9 +611,11 @@ class _Generator:
             if a.shape == ():
                 ct = "int" if a.dtype == I32 else "float"
                 cast = "const int*" if a.dtype == I32 else "const float*"
-                pre.append(f"      const {ct} a{i} = valid ? gjb::ldx<kCg>(reinterpret_cast<{cast}>(io.args[{i}]) + row) : 0;")
+                pre.append(f"      int64_t row{i} = row; const void* rb{i} = gjb::arg_base(io.args[{i}], (io.gather && io.peers) ? io.peers + {i} : nullptr, row{i});")
+                pre.append(f"      const {ct} a{i} = valid ? gjb::ldx<kCg>(reinterpret_cast<{cast}>(rb{i}) + row{i}) : 0;")
             else:
-                pre.append(f"      const gjb::V4 a{i} = valid ? gjb::v4_ld<kCg>(reinterpret_cast<const float*>(io.args[{i}]) + row * {D} + 4 * lane) : gjb::v4_splat(0.0f);")
+                pre.append(f"      int64_t row{i} = row; const void* rb{i} = gjb::arg_base(io.args[{i}], (io.gather && io.peers) ? io.peers + {i} : nullptr, row{i});")
+                pre.append(f"      const gjb::V4 a{i} = valid ? gjb::v4_ld<kCg>(reinterpret_cast<const float*>(rb{i}) + row{i} * {D} + 4 * lane) : gjb::v4_splat(0.0f);")
         for s in ir.sites:
             j = s.index
             if s.value.ndim == 0:
@@ -685,6 +689,7 @@ class _Generator:
         out.append("  for (int j = 0; j < NS; ++j) { io.site_in[j] = A.site_in[j]; io.site_out[j] = A.site_out[j]; }")
         out.append("  for (int k = 0; k < NR; ++k) io.ret_out[k] = A.ret_out[k];")
         out.append("  io.gather = A.gather; io.score_in = A.score_in; io.weight_in = A.weight_in; io.score_out = A.score_out; io.weight_out = A.weight_out;")
+        out.append("  io.peers = A.peer_args;")
         out.append("  const uint32_t key0 = A.key_dev ? __ldg(A.key_dev) : A.key0, key1 = A.key_dev ? __ldg(A.key_dev + 1) : A.key1;")
         out.append("  float run_max = -INFINITY;")
         if self.group:
@@ -723,7 +728,7 @@ class _Generator:
         out.append("    for (int i = 0; i < NA; ++i) io.args[i] = nullptr;")
         out.append("    for (int j = 0; j < NS; ++j) { io.site_in[j] = nullptr; io.site_out[j] = nullptr; }")
         out.append("    for (int k = 0; k < NR; ++k) io.ret_out[k] = nullptr;")
-        out.append("    io.score_in = nullptr; io.weight_in = nullptr; io.score_out = nullptr;")
+        out.append("    io.score_in = nullptr; io.weight_in = nullptr; io.score_out = nullptr; io.peers = nullptr;")
         for i in range(len(ir.ret_leaves)):
             out.append(f"    io.args[{i}] = t == 0 ? Q.state0[{i}] : (const void*)((const char*)Q.state_buf[{i}] + (int64_t)pslot * Q.state_stride[{i}]);")
         out.append("    io.gather = t == 0 ? nullptr : Q.ancestors + (int64_t)pslot * n;")

@@ -44,6 +44,7 @@ class ModelArgs(C.Structure):
         ("key1", _u32),
         ("key_dev", _p),
         ("gather", _p),
+        ("peer_args", _p),
         ("args", _p * GJB_MAX_ARGS),
         ("scalars", C.c_float * GJB_MAX_ARGS),
         ("site_in", _p * GJB_MAX_SITES),
@@ -55,6 +56,35 @@ class ModelArgs(C.Structure):
         ("score_out", _p),
         ("weight_out", _p),
         ("wmax", _p),
+    ]
+
+
+GJB_MAX_RANKS = 16
+XCHG_MAX, XCHG_MASS, XCHG_BARRIER = 0, 1, 2
+
+
+class Peers(C.Structure):
+    """``gjb_peers`` (include/genjax_b200.h)."""
+
+    _fields_ = [("world", _i32), ("rank", _i32), ("n_per_rank", _i64), ("base", _p * GJB_MAX_RANKS)]
+
+
+class XchgArgs(C.Structure):
+    """``gjb_xchg_args`` (include/genjax_b200.h)."""
+
+    _fields_ = [
+        ("rank", _i32),
+        ("world", _i32),
+        ("mode", _i32),
+        ("n_tiles", _i32),
+        ("pads", _p * GJB_MAX_RANKS),
+        ("epoch", _p),
+        ("tag_offset", _u64),
+        ("wmax", _p),
+        ("tile_mass", _p),
+        ("m_global", _p),
+        ("c_offset", _p),
+        ("s_total", _p),
     ]
 
 
@@ -148,6 +178,10 @@ CORE_PROTOTYPES = {
     "gjb_resample_systematic": (C.c_int, [C.POINTER(ResampleArgs), _p]),
     "gjb_resample_multinomial": (C.c_int, [_p, _i64, _p, _p, _p, _u32, _u32, _u64, _i64, _p, _p]),
     "gjb_gather_rows": (C.c_int, [_p, _p, _p, _i64, _i32, _p]),
+    "gjb_exchange": (C.c_int, [C.POINTER(XchgArgs), _p]),
+    "gjb_epoch_bump": (C.c_int, [_p, _p]),
+    "gjb_resample_systematic_peers": (C.c_int, [C.POINTER(ResampleArgs), C.POINTER(Peers), _p]),
+    "gjb_gather_rows_peers": (C.c_int, [C.POINTER(Peers), _p, _p, _i64, _i32, _p]),
     "gjb_philox_fill": (C.c_int, [_u32, _u32, _u64, _u32, _u32, _i64, _p, _p]),
     "gjb_normal_fill": (C.c_int, [_u32, _u32, _u64, _u32, _i64, _i32, _p, _p]),
 }
@@ -182,7 +216,7 @@ def core():
     if _core is None:
         path = build.build_core()
         _core = _bind(C.CDLL(str(path)), CORE_PROTOTYPES)
-        if _core.gjb_abi_version() != 2:
+        if _core.gjb_abi_version() != 3:
             raise GjbError("libgjb_core.so ABI mismatch")
     return _core
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GJB_ABI_VERSION 2
+#define GJB_ABI_VERSION 3
 
 #define GJB_E_ARG (-1)      /* null / misaligned pointer, negative size          */
 #define GJB_E_RANGE (-2)    /* size beyond what the kernel supports              */
@@ -119,6 +119,56 @@ int gjb_resample_multinomial(const float* logw, int64_t n, const uint32_t* wmax,
 int gjb_gather_rows(const void* src, const int32_t* ancestors, void* dst,
                     int64_t n_out, int32_t row_bytes, void* stream);
 
+/* ----------------------------------------------- 1b. multi-GPU (one process per GPU)
+ *
+ * Global resampling across R ranks: particles are block
+ * partitioned (rank r owns global ids [r*n_per_rank, (r+1)*n_per_rank)), the
+ * CDF is the concatenation of the ranks' exact integer CDFs, and every rank
+ * writes the ancestors of ITS parents' offspring straight into the owning
+ * rank's ancestor buffer over NVLink (peer pointers from a symmetric-memory
+ * rendezvous).  The three per-step exchanges (global max, rank masses, barrier)
+ * are single-CTA kernels that push 16 bytes to every peer's pad and poll their
+ * own -- no NCCL call on the data path.
+ */
+#define GJB_MAX_RANKS 16
+
+typedef struct gjb_peers {
+  int32_t world;             /* 0 or 1: single device, tables ignored           */
+  int32_t rank;
+  int64_t n_per_rank;        /* particles per rank (multiple of 4)              */
+  const void* base[GJB_MAX_RANKS];   /* the same buffer on every rank (peer mapped) */
+} gjb_peers;
+
+#define GJB_XCHG_MAX 0       /* in: wmax (encoded)        out: m_global = max over ranks        */
+#define GJB_XCHG_MASS 1      /* in: tile_mass[n_tiles]    out: c_offset (ranks before), s_total */
+#define GJB_XCHG_BARRIER 2   /* all ranks reached this point; their earlier peer writes are visible */
+
+typedef struct gjb_xchg_args {
+  int32_t rank, world;
+  int32_t mode;              /* GJB_XCHG_*                                       */
+  int32_t n_tiles;           /* MASS: entries of tile_mass                       */
+  uint64_t* pads[GJB_MAX_RANKS];     /* every rank's pad: uint64 [2][GJB_MAX_RANKS][2] = {value, tag} */
+  const uint64_t* epoch;     /* device counter (bumped once per filter run)      */
+  uint64_t tag_offset;       /* tag = *epoch * 2^32 + tag_offset; consecutive exchanges use consecutive offsets >= 1 */
+  const uint32_t* wmax;      /* MAX input                                        */
+  const uint64_t* tile_mass; /* MASS input                                       */
+  float* m_global;           /* MAX output                                       */
+  uint64_t* c_offset;        /* MASS output                                      */
+  uint64_t* s_total;         /* MASS output                                      */
+} gjb_xchg_args;
+
+int gjb_exchange(const gjb_xchg_args* a, void* stream);
+int gjb_epoch_bump(uint64_t* epoch, void* stream);
+
+/* gjb_resample_systematic with every rank's ancestor buffer: offspring j is
+ * written to anc.base[j / n_per_rank][j % n_per_rank].  a->ancestors is ignored,
+ * a->out_lo must be 0 and a->out_n the global particle count. */
+int gjb_resample_systematic_peers(const gjb_resample_args* a, const gjb_peers* anc, void* stream);
+
+/* gjb_gather_rows whose source rows live on the rank that owns the (global) ancestor id. */
+int gjb_gather_rows_peers(const gjb_peers* src, const int32_t* ancestors, void* dst, int64_t n_out,
+                          int32_t row_bytes, void* stream);
+
 /* Raw Philox words / N(0,1) draws for RNG known-answer tests. */
 int gjb_philox_fill(uint32_t key0, uint32_t key1, uint64_t idx_offset,
                     uint32_t site, uint32_t chunk, int64_t n, uint32_t* out4,
@@ -159,6 +209,7 @@ typedef struct gjb_model_args {
   uint32_t key0, key1;       /* batch key words                                 */
   const uint32_t* key_dev;   /* nullable: {key0, key1} read on the device instead (graph replay) */
   const int32_t* gather;     /* nullable: per-particle args are read at gather[i] */
+  const gjb_peers* peer_args; /* nullable DEVICE array [GJB_MAX_ARGS]: per-particle arg i lives on rank gather[i] / n_per_rank */
   const void* args[GJB_MAX_ARGS];      /* model args: per-particle arrays or shared blocks */
   float scalars[GJB_MAX_ARGS];         /* model args passed by value (host scalars)        */
   const void* site_in[GJB_MAX_SITES];  /* constrained / previous values        */

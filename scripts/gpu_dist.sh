@@ -1,0 +1,4 @@
+set -x
+cd $GRAFT_REPO_ROOT
+nvidia-smi -L
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_pf_worker.py 2>&1 | tail -30
