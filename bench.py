@@ -48,7 +48,10 @@ def parse():
     ap.add_argument("--particles", type=int, default=1 << 20, help="particles per GPU")
     ap.add_argument("--T", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="persistent", choices=["persistent", "graph"],
+    ap.add_argument("--multi-gpu", default="global", choices=["global", "independent"],
+                    help="N>1: global = one filter over N*particles with global resampling (peer memory exchange); "
+                         "independent = one filter per rank, no exchange")
+    ap.add_argument("--mode", default="graph", choices=["persistent", "graph"],
                     help="persistent: one cooperative launch per filter; graph: 3 launches per step in a CUDA graph")
     return ap.parse_args()
 
@@ -248,7 +251,13 @@ def run_ours(args):
         shared = (torch.full((d,), LG_Q, device=device), torch.full((d,), LG_R, device=device))
     # weak scaling: every rank filters its own block of n particles; lanes are
     # global particle indices so the streams of different ranks never overlap
-    pf = ParticleFilter(model, n, idx_offset=0, mode=args.mode)
+    global_resample = world > 1 and args.multi_gpu == "global"
+    if global_resample:
+        from genjax_b200.inference.pf_dist import DistributedParticleFilter
+
+        pf = DistributedParticleFilter(model, n)
+    else:
+        pf = ParticleFilter(model, n, idx_offset=0, mode=args.mode)
     obs_dev = gj.C["y"].set(ys_dev)
     obs_host = gj.C["y"].set(ys_host)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
@@ -259,7 +268,7 @@ def run_ours(args):
         torch.cuda.synchronize(device)
 
     def one(step_idx, e2e):
-        key = gj.fold_in(gj.key(314159 + rank), step_idx)
+        key = gj.fold_in(gj.key(314159 + (0 if global_resample else rank)), step_idx)
         if e2e:
             res = pf.run(key, x0_host.to(device, non_blocking=True), obs_host, shared_args=shared)
             return res.log_marginal_likelihood.item()  # D2H read + sync
@@ -364,7 +373,7 @@ def run_ours(args):
     model_bytes = (8 * d + 12) * n  # read ancestor 4 + x_prev 4d, write x 4d + logw 4
     model_gbs = model_bytes / (model_ms * 1e-3) / 1e9
 
-    if plan.persistent:
+    if getattr(plan, "persistent", False):
         pf_ms = time_launches(lambda: plan.cm.lib.gjb_model_pf_run(C.byref(plan.pf_args), stream), 10, 2)
         achieved = step_bytes / (pf_ms * 1e-3) / 1e9
         roofline = {
@@ -414,8 +423,10 @@ def run_ours(args):
                         "systematic resampling every step",
             "particles_per_gpu": n, "T": T, "d": d,
             "l2": "flushed between timed steps (256 MiB write)",
-            "mode": args.mode,
-            "multi_gpu": "independent particle blocks per rank (weak scaling), no data-path collective",
+            "mode": "graph (6 launches/step incl. exchanges)" if global_resample else args.mode,
+            "multi_gpu": ("one filter over all ranks' particles, global systematic resampling: per step 3 push/poll exchanges "
+                          "(max, rank masses, barrier) and ancestor writes / state gathers over NVLink peer memory; weak scaling"
+                          if global_resample else "independent particle blocks per rank (weak scaling), no data-path collective"),
             "logZ_last": logz,
         },
         "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,

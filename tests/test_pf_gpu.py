@@ -294,3 +294,19 @@ def test_hmm_filter_teacher_forced_and_exact(device):
         ll += np.log(alpha.sum())
         alpha /= alpha.sum()
     assert res.log_marginal_likelihood.item() == pytest.approx(ll, abs=0.05)
+
+
+def test_multi_gpu_global_resampling_equals_single_gpu(device):
+    """R-rank filter with global resampling (peer-mapped ancestor writes / state gathers, push-poll
+    exchanges) == single-GPU filter of R*n particles, bit for bit.  Needs >= 2 GPUs (gpurun --gpus 2)."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tests", "dist_pf_worker.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "DIST_PF_OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
