@@ -423,7 +423,7 @@ def run_ours(args):
                         "systematic resampling every step",
             "particles_per_gpu": n, "T": T, "d": d,
             "l2": "flushed between timed steps (256 MiB write)",
-            "mode": "graph (6 launches/step incl. exchanges)" if global_resample else args.mode,
+            "mode": "graph (3 launches/step, cross-rank hand-offs fused into the kernels)" if global_resample else args.mode,
             "multi_gpu": ("one filter over all ranks' particles, global systematic resampling: per step 3 push/poll exchanges "
                           "(max, rank masses, barrier) and ancestor writes / state gathers over NVLink peer memory; weak scaling"
                           if global_resample else "independent particle blocks per rank (weak scaling), no data-path collective"),

@@ -57,6 +57,118 @@ __global__ void __launch_bounds__(kThreads) weight_mass_kernel(const float* __re
   if (threadIdx.x == 0) tile_mass[blockIdx.x] = s;
 }
 
+// multi-GPU: wait for every rank's max, mass relative to the global max, last CTA pushes this rank's mass
+__global__ void __launch_bounds__(kThreads) weight_mass_linked_kernel(const float* __restrict__ logw, int64_t n,
+                                                                      uint64_t* __restrict__ tile_mass,
+                                                                      uint64_t* __restrict__ tile_prefix,
+                                                                      const gjb_link* __restrict__ L, uint64_t wait_max,
+                                                                      uint64_t push_mass) {
+  __shared__ uint64_t sm[kThreads / 32];
+  __shared__ uint64_t vals[GJB_MAX_RANKS];
+  link_wait(L, wait_max, vals);
+  uint32_t me = 0;
+  for (int r = 0; r < L->world; ++r) me = max(me, (uint32_t)vals[r]);
+  const float M = fdec(me);
+  const uint64_t s = tile_mass_of<false>(logw, n, (int64_t)blockIdx.x * kTile, M, sm);
+  if (threadIdx.x == 0) tile_mass[blockIdx.x] = s;
+  if (link_last_block(L)) {
+    const int nt = (int)gridDim.x;
+    uint64_t tot = 0;
+    if (tile_prefix) {
+      // inclusive prefix of the tile masses for the peers' pull resampler: chunks of kThreads tiles
+      uint64_t carry = 0;
+      for (int t0 = 0; t0 < nt; t0 += kThreads) {
+        const int t = t0 + threadIdx.x;
+        const uint64_t v = t < nt ? (uint64_t)__ldcg(reinterpret_cast<const unsigned long long*>(tile_mass) + t) : 0ull;
+        uint64_t inc = v;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint64_t u = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += u;
+        }
+        __syncthreads();
+        if (lane == 31) sm[warp] = inc;
+        __syncthreads();
+        uint64_t wpre = 0, ctot = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) { if (w < warp) wpre += sm[w]; ctot += sm[w]; }
+        if (t < nt) tile_prefix[t] = carry + wpre + inc;
+        carry += ctot;
+      }
+      tot = carry;
+      __syncthreads();  // the prefix stores precede the release store of the tag (cumulative through the barrier)
+    } else {
+      for (int t = threadIdx.x; t < nt; t += kThreads)
+        tot += __ldcg(reinterpret_cast<const unsigned long long*>(tile_mass) + t);
+      tot = block_sum_u64(tot, sm);
+    }
+    link_push(L, push_mass, tot);
+  }
+}
+
+// pull resampler: CTA (b, p) looks at parent tile b of rank p and writes the ancestors of the offspring
+// of that tile that fall into THIS rank's slots [out_lo, out_lo + out_n) -- into the local ancestor array
+__global__ void __launch_bounds__(kThreads) resample_pull_kernel(const __grid_constant__ gjb_resample_args R,
+                                                                 const __grid_constant__ gjb_peers LW,
+                                                                 const __grid_constant__ gjb_peers PF,
+                                                                 const gjb_link* __restrict__ L, uint64_t wait_max,
+                                                                 uint64_t wait_mass) {
+  __shared__ TileSmem sm;
+  __shared__ uint64_t vals[GJB_MAX_RANKS];
+  __shared__ __align__(16) int32_t heads[kWin];
+  const int tid = threadIdx.x;
+  const int p = blockIdx.y;  // rank that owns the parent tile
+  const int64_t npr = LW.n_per_rank;
+  const int64_t n_total = R.n_total, out_lo = R.out_lo, out_n = R.out_n;
+  link_wait(L, wait_max, vals);
+  uint32_t me = 0;
+  for (int r = 0; r < L->world; ++r) me = max(me, (uint32_t)vals[r]);
+  const float M = fdec(me);
+  __syncthreads();
+  link_wait(L, wait_mass, vals);
+  uint64_t base = 0, S = 0;
+  for (int r = 0; r < L->world; ++r) { if (r < p) base += vals[r]; S += vals[r]; }
+  const uint64_t Sp = vals[p];
+  if (blockIdx.x == 0 && p == L->rank && tid == 0) {
+    if (R.lse_out) {
+      R.lse_out[0] = (double)M;
+      R.lse_out[1] = (double)S;
+      R.lse_out[2] = S ? (double)M + log((double)S) - kQLog - log((double)n_total) : -INFINITY;
+    }
+    if (R.wmax_next) *R.wmax_next = GJB_WMAX_NEG_INF;
+  }
+  const int64_t tile_base = (int64_t)blockIdx.x * kTile;
+  if (S == 0) {  // every weight is zero: identity ancestors for my own slots
+    if (p == L->rank)
+      for (int k = tid; k < kTile; k += kThreads) {
+        const int64_t i = tile_base + k;
+        if (i < npr) R.ancestors[i] = (int32_t)(out_lo + i);
+      }
+    return;
+  }
+  uint32_t key0 = R.key0, key1 = R.key1;
+  uint64_t key_index = R.key_index;
+  if (R.key_dev) {
+    key0 = __ldg(R.key_dev);
+    key1 = __ldg(R.key_dev + 1);
+    key_index = (uint64_t)__ldg(R.key_dev + 2) | ((uint64_t)__ldg(R.key_dev + 3) << 32);
+  }
+  const double u0 = resample_u0(key0, key1, key_index);
+  const double scale = __ddiv_rn((double)n_total, (double)S);
+  const int32_t nt = (int32_t)n_total;
+  const int64_t w_lo = out_lo, w_hi = out_lo + out_n;
+  // rank-level reject: offspring range of all of rank p's parents
+  if ((int64_t)offspring_cnt(base + Sp, S, scale, u0, nt) <= w_lo || (int64_t)offspring_cnt(base, S, scale, u0, nt) >= w_hi) return;
+  // tile-level reject from rank p's inclusive tile prefix (2 words, local or over NVLink)
+  const unsigned long long* pf = reinterpret_cast<const unsigned long long*>(PF.base[p]);
+  const uint64_t pre = blockIdx.x ? (uint64_t)__ldcg(pf + blockIdx.x - 1) : 0ull;
+  const uint64_t end = (uint64_t)__ldcg(pf + blockIdx.x);
+  if ((int64_t)offspring_cnt(base + end, S, scale, u0, nt) <= w_lo || (int64_t)offspring_cnt(base + pre, S, scale, u0, nt) >= w_hi) return;
+  const float* lw = reinterpret_cast<const float*>(LW.base[p]);
+  resample_tile<true>(lw, npr, tile_base, M, base + pre, S, n_total, u0, out_lo, out_n, (int64_t)p * npr, R.ancestors, sm, heads);
+}
+
 __global__ void __launch_bounds__(256) lse_finalize_kernel(const uint64_t* __restrict__ tile_mass, int n_tiles,
                                                            const uint32_t* __restrict__ wmax,
                                                            const float* __restrict__ m_global, int64_t n_total,
@@ -80,7 +192,9 @@ __global__ void __launch_bounds__(256) lse_finalize_kernel(const uint64_t* __res
 // ------------------------------------------------------------ systematic
 
 __global__ void __launch_bounds__(kThreads) resample_systematic_kernel(const __grid_constant__ gjb_resample_args R,
-                                                                       const __grid_constant__ gjb_peers P) {
+                                                                       const __grid_constant__ gjb_peers P,
+                                                                       const gjb_link* __restrict__ L, uint64_t wait_max,
+                                                                       uint64_t wait_mass, uint64_t push_barrier) {
   const gjb_peers* peers = P.world > 1 ? &P : nullptr;
   const int64_t n = R.n, n_total = R.n_total, out_lo = R.out_lo, out_n = R.out_n, anc_base = R.anc_base;
   uint32_t key0 = R.key0, key1 = R.key1;
@@ -92,6 +206,7 @@ __global__ void __launch_bounds__(kThreads) resample_systematic_kernel(const __g
   }
   __shared__ TileSmem sm;
   __shared__ uint64_t sm_b[kThreads / 32];
+  __shared__ uint64_t vals[GJB_MAX_RANKS];
   __shared__ __align__(16) int32_t heads[kWin];
   const int tid = threadIdx.x;
   const int n_tiles = gridDim.x;
@@ -105,33 +220,49 @@ __global__ void __launch_bounds__(kThreads) resample_systematic_kernel(const __g
   }
   pre = block_sum_u64(pre, sm.red);
   tot = block_sum_u64(tot, sm_b);
-  const uint64_t S = R.s_total ? __ldg(R.s_total) : tot;
-  const uint64_t off = pre + (R.c_offset ? __ldg(R.c_offset) : 0ull);
+  uint64_t S, off;
+  float M;
+  if (L) {  // multi-GPU, fused hand-offs: global max and every rank's mass come from the pad
+    link_wait(L, wait_max, vals);
+    uint32_t me = 0;
+    for (int r = 0; r < L->world; ++r) me = max(me, (uint32_t)vals[r]);
+    M = fdec(me);
+    __syncthreads();
+    link_wait(L, wait_mass, vals);
+    uint64_t before = 0, all = 0;
+    for (int r = 0; r < L->world; ++r) { if (r < L->rank) before += vals[r]; all += vals[r]; }
+    S = all;
+    off = pre + before;
+  } else {
+    S = R.s_total ? __ldg(R.s_total) : tot;
+    off = pre + (R.c_offset ? __ldg(R.c_offset) : 0ull);
+    M = ref_max(R.wmax, R.m_global);
+  }
   if (blockIdx.x == 0 && tid == 0) {
     if (R.lse_out) {
-      const double Md = (double)ref_max(R.wmax, R.m_global);
-      R.lse_out[0] = Md;
+      R.lse_out[0] = (double)M;
       R.lse_out[1] = (double)S;
-      R.lse_out[2] = S ? Md + log((double)S) - kQLog - log((double)n_total) : -INFINITY;
+      R.lse_out[2] = S ? (double)M + log((double)S) - kQLog - log((double)n_total) : -INFINITY;
     }
     if (R.wmax_next) *R.wmax_next = GJB_WMAX_NEG_INF;
   }
 
   const int64_t tile_base = (int64_t)blockIdx.x * kTile;
   if (S == 0) {  // every weight is zero: identity ancestors (collection invalid)
+    const AncRoute route{peers ? nullptr : R.ancestors - out_lo, peers};
     for (int k = tid; k < kTile; k += kThreads) {
       const int64_t i = tile_base + k;
       const int64_t j = anc_base + i;
-      if (i < n && j >= out_lo && j < out_lo + out_n) {
-        const AncRoute route{peers ? nullptr : R.ancestors - out_lo, peers};
-        *route.at((int32_t)j) = (int32_t)j;
-      }
+      if (i < n && j >= out_lo && j < out_lo + out_n) *route.at((int32_t)j) = (int32_t)j;
     }
-    return;
+  } else {
+    const double u0 = resample_u0(key0, key1, key_index);
+    resample_tile<false>(R.logw, n, tile_base, M, off, S, n_total, u0, out_lo, out_n, anc_base, R.ancestors, sm, heads,
+                         nullptr, peers);
   }
-  const float M = ref_max(R.wmax, R.m_global);
-  const double u0 = resample_u0(key0, key1, key_index);
-  resample_tile<false>(R.logw, n, tile_base, M, off, S, n_total, u0, out_lo, out_n, anc_base, R.ancestors, sm, heads, nullptr, peers);
+  if (L && push_barrier) {
+    if (link_last_block(L)) link_push(L, push_barrier, 0ull);
+  }
 }
 
 // ----------------------------------------------------------- multinomial
@@ -231,7 +362,7 @@ __global__ void __launch_bounds__(256) exchange_kernel(const __grid_constant__ g
   __shared__ uint64_t vals[GJB_MAX_RANKS];
   const int tid = threadIdx.x;
   const uint64_t tag = (__ldg(X.epoch) << 32) + X.tag_offset;
-  const int slot = (int)(X.tag_offset & 1);
+  const int slot = (int)(X.tag_offset % GJB_PAD_SLOTS);
   uint64_t mine = 0;
   if (X.mode == GJB_XCHG_MAX) {
     mine = (uint64_t)__ldg(X.wmax);
@@ -361,7 +492,7 @@ int gjb_resample_systematic(const gjb_resample_args* a, void* stream) {
   if (a->n_total > 0x7fffffffLL) return GJB_E_RANGE;  // int32 ancestors
   const int64_t tiles = (a->n + kTile - 1) / kTile;
   gjb_peers none = {};
-  resample_systematic_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a, none);
+  resample_systematic_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a, none, nullptr, 0, 0, 0);
   return launch_status();
 }
 
@@ -374,7 +505,54 @@ int gjb_resample_systematic_peers(const gjb_resample_args* a, const gjb_peers* a
   const int64_t tiles = (a->n + kTile - 1) / kTile;
   gjb_peers p = *anc;
   if (p.world == 1) p.world = 2, p.base[1] = p.base[0];  // keep the routed path even for one rank (tests)
-  resample_systematic_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a, p);
+  resample_systematic_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a, p, nullptr, 0, 0, 0);
+  return launch_status();
+}
+
+int gjb_resample_systematic_linked(const gjb_resample_args* a, const gjb_peers* anc, const gjb_link* link,
+                                   uint64_t wait_max, uint64_t wait_mass, uint64_t push_barrier, void* stream) {
+  if (!a || !anc || !link || !a->logw || !a->tile_mass || !wait_max || !wait_mass) return GJB_E_ARG;
+  if (anc->world < 2 || anc->world > GJB_MAX_RANKS || anc->n_per_rank <= 0 || (anc->n_per_rank & 3)) return GJB_E_ARG;
+  if (a->n <= 0 || a->n_total != anc->n_per_rank * anc->world || a->out_lo != 0 || a->out_n != a->n_total) return GJB_E_ARG;
+  if (a->n_total > 0x7fffffffLL) return GJB_E_RANGE;
+  const int64_t tiles = (a->n + kTile - 1) / kTile;
+  resample_systematic_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a, *anc, link, wait_max, wait_mass,
+                                                                               push_barrier);
+  return launch_status();
+}
+
+int gjb_weight_mass_linked(const float* logw, int64_t n, uint64_t* tile_mass, const gjb_link* link, uint64_t wait_max,
+                           uint64_t push_mass, void* stream) {
+  if (!logw || !tile_mass || !link || n <= 0 || !wait_max || !push_mass) return GJB_E_ARG;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  if (tiles > 0x7fffffff) return GJB_E_RANGE;
+  weight_mass_linked_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(logw, n, tile_mass, nullptr, link, wait_max, push_mass);
+  return launch_status();
+}
+
+int gjb_weight_mass_prefix_linked(const float* logw, int64_t n, uint64_t* tile_mass, uint64_t* tile_prefix,
+                                  const gjb_link* link, uint64_t wait_max, uint64_t push_mass, void* stream) {
+  if (!logw || !tile_mass || !tile_prefix || !link || n <= 0 || !wait_max || !push_mass) return GJB_E_ARG;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  if (tiles > 0x7fffffff) return GJB_E_RANGE;
+  weight_mass_linked_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(logw, n, tile_mass, tile_prefix, link, wait_max,
+                                                                              push_mass);
+  return launch_status();
+}
+
+int gjb_resample_systematic_pull(const gjb_resample_args* a, const gjb_peers* logw_peers, const gjb_peers* prefix_peers,
+                                 const gjb_link* link, uint64_t wait_max, uint64_t wait_mass, void* stream) {
+  if (!a || !logw_peers || !prefix_peers || !link || !a->ancestors || !wait_max || !wait_mass) return GJB_E_ARG;
+  const int world = logw_peers->world;
+  if (world < 1 || world > GJB_MAX_RANKS || prefix_peers->world != world) return GJB_E_ARG;
+  const int64_t npr = logw_peers->n_per_rank;
+  if (npr <= 0 || (npr & 3) || a->n != npr || a->n_total != npr * world) return GJB_E_ARG;
+  if (a->out_n != npr || a->out_lo != (int64_t)logw_peers->rank * npr) return GJB_E_ARG;
+  if (a->n_total > 0x7fffffffLL) return GJB_E_RANGE;
+  for (int r = 0; r < world; ++r) if (!logw_peers->base[r] || !prefix_peers->base[r]) return GJB_E_ARG;
+  const int64_t tiles = (npr + kTile - 1) / kTile;
+  resample_pull_kernel<<<dim3((unsigned)tiles, (unsigned)world), kThreads, 0, (cudaStream_t)stream>>>(
+      *a, *logw_peers, *prefix_peers, link, wait_max, wait_mass);
   return launch_status();
 }
 

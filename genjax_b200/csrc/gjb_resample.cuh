@@ -19,6 +19,51 @@
 
 namespace gjb {
 
+// ---- fused cross-rank hand-offs (gjb_link): see include/genjax_b200.h
+__device__ __forceinline__ uint64_t link_tag(const gjb_link* L, uint64_t off) {
+  return ((uint64_t)__ldg(reinterpret_cast<const unsigned long long*>(L->epoch)) << 32) + off;
+}
+// every CTA: wait until all ranks' entries of exchange `off` sit in MY pad; vals[r] = rank r's value
+__device__ __forceinline__ void link_wait(const gjb_link* L, uint64_t off, uint64_t* vals /* smem [GJB_MAX_RANKS] */) {
+  if ((int)threadIdx.x < L->world) {
+    const uint64_t tag = link_tag(L, off);
+    const uint64_t* src = L->pads[L->rank] + ((off % GJB_PAD_SLOTS) * GJB_MAX_RANKS + threadIdx.x) * 2;
+    // acquire load of the tag (pairs with the pusher's release store); every CTA polls the line the peers'
+    // NVLink stores must land in, so back off between polls
+    uint64_t seen;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(src + 1) : "memory");
+      if (seen == tag) break;
+      __nanosleep(40);
+    }
+    vals[threadIdx.x] = *reinterpret_cast<const volatile uint64_t*>(src);
+  }
+  __syncthreads();
+}
+// all threads of every CTA call this after the CTA's last global write; true in the CTA that finishes last
+__device__ __forceinline__ bool link_last_block(const gjb_link* L) {
+  __shared__ int gjb_is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();  // cumulative over the CTA's writes ordered by the barrier above
+    const uint32_t total = gridDim.x * gridDim.y * gridDim.z;
+    const uint32_t ticket = atomicAdd(L->counter, 1u);
+    gjb_is_last = ticket == total - 1;
+    if (gjb_is_last) *L->counter = 0u;  // the next kernel on the stream starts from zero
+  }
+  __syncthreads();
+  return gjb_is_last != 0;
+}
+// threads [0, world) of ONE CTA: push {value, tag} into slot[rank] of every peer's pad
+__device__ __forceinline__ void link_push(const gjb_link* L, uint64_t off, uint64_t value) {
+  if ((int)threadIdx.x < L->world) {
+    uint64_t* dst = L->pads[threadIdx.x] + ((off % GJB_PAD_SLOTS) * GJB_MAX_RANKS + L->rank) * 2;
+    *reinterpret_cast<volatile uint64_t*>(dst) = value;
+    const uint64_t tag = link_tag(L, off);
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst + 1), "l"(tag) : "memory");
+  }
+}
+
 // where offspring slot j lives: a local array, or the owning rank's array (peer mapped)
 struct AncRoute {
   int32_t* local;            // single device: ancestors - out_lo

@@ -680,6 +680,10 @@ class _Generator:
     # ------------------------------------------------------------ kernels
     def model_kernel(self) -> list[str]:
         out = ["__global__ void __launch_bounds__(kThreads) model_kernel(const __grid_constant__ gjb_model_args A) {"]
+        out.append("  if (A.link && A.wait_off) {  // multi-GPU: the peers' ancestor writes of the previous step have landed")
+        out.append("    __shared__ uint64_t link_vals[GJB_MAX_RANKS];")
+        out.append("    gjb::link_wait(A.link, A.wait_off, link_vals);")
+        out.append("  }")
         out.extend(self.stage_lines("A.args"))
         out.append("  Uni U; make_uni(U, A.scalars);")
         out.append("  uint32_t fl[NS];")
@@ -698,6 +702,9 @@ class _Generator:
             out.append("  const int64_t nq = (A.n + (int64_t)(A.idx_offset & 3) + 3) >> 2;")
             out.append("  run_quads<false, false>(io, U, fl, A.n, A.idx_offset, key0, key1, blockIdx.x * (int64_t)kThreads + threadIdx.x, nq, (int64_t)gridDim.x * kThreads, run_max);")
         out.append("  if (A.wmax) gjb::block_wmax(run_max, A.wmax);")
+        out.append("  if (A.link && A.push_off) {  // multi-GPU: the CTA that finishes last publishes this rank's max")
+        out.append("    if (gjb::link_last_block(A.link)) gjb::link_push(A.link, A.push_off, (uint64_t)__ldcg(A.wmax));")
+        out.append("  }")
         out.append("}")
         return out
 

@@ -37,7 +37,7 @@ from ..gen.static import StaticGenerativeFunction, _dev_tensor
 from ..runtime import cabi, smc_ops
 from .pf import PFResult
 
-_PAD_WORDS = 2 * cabi.GJB_MAX_RANKS * 2  # uint64 [2][GJB_MAX_RANKS][2]
+_PAD_WORDS = cabi.GJB_PAD_WORDS  # uint64 [GJB_PAD_SLOTS][GJB_MAX_RANKS][2]
 
 
 def shard_bounds(n_total: int, world: int, rank: int) -> tuple[int, int]:
@@ -89,7 +89,16 @@ class DistributedParticleFilter:
     ``ParticleFilter`` over ``world * n_per_rank`` particles with global
     systematic resampling.  ``state0`` / results are this rank's block."""
 
-    def __init__(self, step: StaticGenerativeFunction, n_per_rank: int, group=None):
+    def __init__(self, step: StaticGenerativeFunction, n_per_rank: int, group=None, fused: bool = True,
+                 mode: str = "pull"):
+        """mode "pull" (default): every rank resolves the ancestors of its OWN slots, reading peers'
+        log-weight tiles over NVLink -- 2 fused hand-offs per step, no cross-rank stores, no barrier;
+        mode "push": owners write ancestors into the peers' buffers -- 3 hand-offs per step, fused into
+        the kernels (``fused=True``) or as 3 extra single-CTA launches (``fused=False``)."""
+        if mode not in ("pull", "push"):
+            raise ValueError(mode)
+        self.mode = mode
+        self.fused = bool(fused) or mode == "pull"
         if not dist.is_initialized():
             raise RuntimeError("init torch.distributed first (one process per GPU)")
         self.step = step
@@ -142,7 +151,8 @@ class _DistPlan:
         self.slots = slots
         # ---- symmetric buffers: state ping-pong, ancestors, exchange pad
         row_elems = [int(np.prod(s.shape[1:])) if s.ndim > 1 else 1 for s in state0]
-        need = sum(slots * n * r * 4 + 512 for r in row_elems) + slots * n * 4 + 512 + _PAD_WORDS * 8 + 1024
+        need = (sum(slots * n * r * 4 + 512 for r in row_elems) + 2 * (slots * n * 4 + 512) + _PAD_WORDS * 8 + 1024
+                + 2 * 8 * ((n + smc_ops.TILE - 1) // smc_ops.TILE + 1) + 1024)
         self.arena = SymmArena(need, device, pf.group)
         self.bufs, self.buf_off = [], []
         for s in state0:
@@ -151,6 +161,11 @@ class _DistPlan:
             self.buf_off.append(off)
         self.anc, self.anc_off = self.arena.take((slots, n), torch.int32)
         self.pad, self.pad_off = self.arena.take((_PAD_WORDS,), torch.int64)
+        self.pull = pf.mode == "pull"
+        n_tiles = max(1, (n + smc_ops.TILE - 1) // smc_ops.TILE)
+        if self.pull:  # peers read these: log-weights and inclusive tile prefixes, double buffered across steps
+            self.logw_sym, self.logw_off = self.arena.take((slots, n), torch.float32)
+            self.tpre, self.tpre_off = self.arena.take((2, n_tiles), torch.int64)
         # ---- local buffers
         self.state_in = tuple(torch.empty_like(s) for s in state0)
         self.shared = tuple(torch.empty_like(s) if isinstance(s, torch.Tensor) else s for s in shared)
@@ -164,6 +179,14 @@ class _DistPlan:
         self.c_offset = torch.empty(1, dtype=torch.int64, device=device)
         self.s_total = torch.empty(1, dtype=torch.int64, device=device)
         self.epoch = torch.zeros(1, dtype=torch.int64, device=device)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=device)
+        L = cabi.Link()
+        L.rank, L.world = rank, world
+        for r in range(world):
+            L.pads[r] = self.arena.ptrs[r] + self.pad_off
+        L.epoch = self.epoch.data_ptr()
+        L.counter = self.counter.data_ptr()
+        self.link = torch.from_numpy(np.frombuffer(bytes(L), dtype=np.uint8).copy()).to(device)
         self.final = tuple(torch.empty_like(s) for s in state0)
         # device tables of peer pointers: per slot, gjb_peers[GJB_MAX_ARGS]
         self.peer_tabs = []
@@ -217,10 +240,18 @@ class _DistPlan:
                     A.site_out[r.attr] = out.data_ptr()
                 else:
                     A.ret_out[k] = out.data_ptr()
-            lw = self.logw[t if self.record else 0]
+            lw = self.logw_sym[slot] if self.pull else self.logw[t if self.record else 0]
             A.weight_out = lw.data_ptr()
             wm = self.wmax2[t & 1:]
             A.wmax = wm.data_ptr()
+            if self.pull:
+                A.link = self.link.data_ptr()
+                A.wait_off = 0  # no barrier: peers only READ this rank's buffers
+                A.push_off = 2 * t + 1
+            elif pf.fused:
+                A.link = self.link.data_ptr()
+                A.wait_off = 3 * t if t > 0 else 0  # BARRIER of step t-1 has offset 3(t-1)+3
+                A.push_off = 3 * t + 1
 
             def xchg(mode, off):
                 X = cabi.XchgArgs()
@@ -244,9 +275,16 @@ class _DistPlan:
             )
             R.out_n = pf.n_total
             anc_peers = self.arena.peers(self.anc_off + slot * n * 4, n)
-            self.steps.append(dict(A=A, lw=lw, wm=wm, R=R, anc_peers=anc_peers,
+            lw_peers = pre_peers = None
+            if self.pull:
+                R.out_lo, R.out_n = rank * n, n  # my own slots only
+                lw_peers = self.arena.peers(self.logw_off + slot * n * 4, n)
+                pre_peers = self.arena.peers(self.tpre_off + (t & 1) * self.tpre.shape[1] * 8, n)
+            self.steps.append(dict(A=A, lw=lw, wm=wm, R=R, anc_peers=anc_peers, lw_peers=lw_peers, pre_peers=pre_peers,
                                    x_max=xchg(cabi.XCHG_MAX, 3 * t + 1), x_mass=xchg(cabi.XCHG_MASS, 3 * t + 2),
                                    x_bar=xchg(cabi.XCHG_BARRIER, 3 * t + 3)))
+        self.x_final = xchg(cabi.XCHG_BARRIER, 3 * T + 1)
+        self.x_end = xchg(cabi.XCHG_BARRIER, 3 * T + 2)
         last = (T - 1) if self.record else ((T - 1) & 1)
         self.final_peers = [self.arena.peers(off + last * n * self.row_elems[i] * 4, n) for i, off in enumerate(self.buf_off)]
         self.last = last
@@ -256,8 +294,24 @@ class _DistPlan:
         stream = cabi.stream_ptr(self.device)
         lib = self.cm.lib
         cabi.check(core.gjb_wmax_reset(self.wmax2.data_ptr(), stream), "gjb_wmax_reset")
-        for st in self.steps:
+        for t, st in enumerate(self.steps):
             cabi.check(lib.gjb_model_launch(C.byref(st["A"]), stream), "gjb_model_launch")
+            if self.pull:
+                cabi.check(core.gjb_weight_mass_prefix_linked(st["lw"].data_ptr(), st["lw"].numel(), self.ws.tile_mass.data_ptr(),
+                                                              self.tpre[t & 1].data_ptr(), self.link.data_ptr(), 2 * t + 1,
+                                                              2 * t + 2, stream), "gjb_weight_mass_prefix_linked")
+                cabi.check(core.gjb_resample_systematic_pull(C.byref(st["R"]), C.byref(st["lw_peers"]), C.byref(st["pre_peers"]),
+                                                             self.link.data_ptr(), 2 * t + 1, 2 * t + 2, stream),
+                           "gjb_resample_systematic_pull")
+                continue
+            if self.pf.fused:
+                cabi.check(core.gjb_weight_mass_linked(st["lw"].data_ptr(), st["lw"].numel(), self.ws.tile_mass.data_ptr(),
+                                                       self.link.data_ptr(), 3 * t + 1, 3 * t + 2, stream),
+                           "gjb_weight_mass_linked")
+                cabi.check(core.gjb_resample_systematic_linked(C.byref(st["R"]), C.byref(st["anc_peers"]),
+                                                               self.link.data_ptr(), 3 * t + 1, 3 * t + 2, 3 * t + 3, stream),
+                           "gjb_resample_systematic_linked")
+                continue
             cabi.check(core.gjb_exchange(C.byref(st["x_max"]), stream), "gjb_exchange(max)")
             cabi.check(core.gjb_weight_mass(st["lw"].data_ptr(), st["lw"].numel(), st["wm"].data_ptr(),
                                             self.m_global.data_ptr(), self.ws.tile_mass.data_ptr(), stream), "gjb_weight_mass")
@@ -265,14 +319,18 @@ class _DistPlan:
             cabi.check(core.gjb_resample_systematic_peers(C.byref(st["R"]), C.byref(st["anc_peers"]), stream),
                        "gjb_resample_systematic_peers")
             cabi.check(core.gjb_exchange(C.byref(st["x_bar"]), stream), "gjb_exchange(barrier)")
+        if self.pf.fused and not self.pull:  # all ranks finished their last resample before anyone gathers the final state
+            cabi.check(core.gjb_exchange(C.byref(self.x_final), stream), "gjb_exchange(final barrier)")
         for k in range(len(self.bufs)):
             cabi.check(core.gjb_gather_rows_peers(C.byref(self.final_peers[k]), self.anc[self.last].data_ptr(),
                                                   self.final[k].data_ptr(), self.pf.n, self.row_elems[k] * 4, stream),
                        "gjb_gather_rows_peers")
+        if self.pull:  # nobody overwrites state / log-weights of this run while a peer still gathers from them
+            cabi.check(core.gjb_exchange(C.byref(self.x_end), stream), "gjb_exchange(end of run)")
         cabi.check(core.gjb_epoch_bump(self.epoch.data_ptr(), stream), "gjb_epoch_bump")
 
     def launches_per_run(self) -> int:
-        return 2 + 6 * self.T + len(self.bufs)
+        return (3 + 3 * self.T if self.pf.fused else 2 + 6 * self.T) + len(self.bufs)  # pull: 3/step too, 2 hand-offs
 
     def execute(self, key, state0, shared, obs, use_graph):
         tab = torch.from_numpy(pf_key_table(key, self.T).view(np.int32))
@@ -298,6 +356,6 @@ class _DistPlan:
         else:
             self._enqueue()
         inc = self.lse[:, 2]
-        hist = {"state": tuple(self.bufs), "log_weights": self.logw} if self.record else None
+        hist = {"state": tuple(self.bufs), "log_weights": self.logw_sym if self.pull else self.logw} if self.record else None
         return PFResult(state=self.final, log_marginal_likelihood=inc.sum(), log_increments=inc, lse_terms=self.lse,
                         ancestors=self.anc if self.record else None, history=hist)

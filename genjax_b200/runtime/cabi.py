@@ -45,6 +45,9 @@ class ModelArgs(C.Structure):
         ("key_dev", _p),
         ("gather", _p),
         ("peer_args", _p),
+        ("link", _p),
+        ("wait_off", _u64),
+        ("push_off", _u64),
         ("args", _p * GJB_MAX_ARGS),
         ("scalars", C.c_float * GJB_MAX_ARGS),
         ("site_in", _p * GJB_MAX_SITES),
@@ -67,6 +70,16 @@ class Peers(C.Structure):
     """``gjb_peers`` (include/genjax_b200.h)."""
 
     _fields_ = [("world", _i32), ("rank", _i32), ("n_per_rank", _i64), ("base", _p * GJB_MAX_RANKS)]
+
+
+GJB_PAD_SLOTS = 4
+GJB_PAD_WORDS = GJB_PAD_SLOTS * GJB_MAX_RANKS * 2
+
+
+class Link(C.Structure):
+    """``gjb_link`` (include/genjax_b200.h)."""
+
+    _fields_ = [("rank", _i32), ("world", _i32), ("pads", _p * GJB_MAX_RANKS), ("epoch", _p), ("counter", _p)]
 
 
 class XchgArgs(C.Structure):
@@ -180,6 +193,10 @@ CORE_PROTOTYPES = {
     "gjb_gather_rows": (C.c_int, [_p, _p, _p, _i64, _i32, _p]),
     "gjb_exchange": (C.c_int, [C.POINTER(XchgArgs), _p]),
     "gjb_epoch_bump": (C.c_int, [_p, _p]),
+    "gjb_weight_mass_linked": (C.c_int, [_p, _i64, _p, _p, _u64, _u64, _p]),
+    "gjb_weight_mass_prefix_linked": (C.c_int, [_p, _i64, _p, _p, _p, _u64, _u64, _p]),
+    "gjb_resample_systematic_pull": (C.c_int, [C.POINTER(ResampleArgs), C.POINTER(Peers), C.POINTER(Peers), _p, _u64, _u64, _p]),
+    "gjb_resample_systematic_linked": (C.c_int, [C.POINTER(ResampleArgs), C.POINTER(Peers), _p, _u64, _u64, _u64, _p]),
     "gjb_resample_systematic_peers": (C.c_int, [C.POINTER(ResampleArgs), C.POINTER(Peers), _p]),
     "gjb_gather_rows_peers": (C.c_int, [C.POINTER(Peers), _p, _p, _i64, _i32, _p]),
     "gjb_philox_fill": (C.c_int, [_u32, _u32, _u64, _u32, _u32, _i64, _p, _p]),
@@ -216,7 +233,7 @@ def core():
     if _core is None:
         path = build.build_core()
         _core = _bind(C.CDLL(str(path)), CORE_PROTOTYPES)
-        if _core.gjb_abi_version() != 3:
+        if _core.gjb_abi_version() != 5:
             raise GjbError("libgjb_core.so ABI mismatch")
     return _core
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GJB_ABI_VERSION 3
+#define GJB_ABI_VERSION 5
 
 #define GJB_E_ARG (-1)      /* null / misaligned pointer, negative size          */
 #define GJB_E_RANGE (-2)    /* size beyond what the kernel supports              */
@@ -147,9 +147,9 @@ typedef struct gjb_xchg_args {
   int32_t rank, world;
   int32_t mode;              /* GJB_XCHG_*                                       */
   int32_t n_tiles;           /* MASS: entries of tile_mass                       */
-  uint64_t* pads[GJB_MAX_RANKS];     /* every rank's pad: uint64 [2][GJB_MAX_RANKS][2] = {value, tag} */
+  uint64_t* pads[GJB_MAX_RANKS];     /* every rank's pad: uint64 [GJB_PAD_SLOTS][GJB_MAX_RANKS][2] = {value, tag} */
   const uint64_t* epoch;     /* device counter (bumped once per filter run)      */
-  uint64_t tag_offset;       /* tag = *epoch * 2^32 + tag_offset; consecutive exchanges use consecutive offsets >= 1 */
+  uint64_t tag_offset;       /* tag = *epoch * 2^32 + tag_offset (>= 1); pad slot tag_offset % GJB_PAD_SLOTS */
   const uint32_t* wmax;      /* MAX input                                        */
   const uint64_t* tile_mass; /* MASS input                                       */
   float* m_global;           /* MAX output                                       */
@@ -158,6 +158,44 @@ typedef struct gjb_xchg_args {
 } gjb_xchg_args;
 
 int gjb_exchange(const gjb_xchg_args* a, void* stream);
+
+/*
+ * The same three hand-offs FUSED into the compute kernels (no extra launches):
+ * the last CTA of a producer kernel pushes {value, tag} to every peer's pad,
+ * every CTA of the consumer kernel polls its own pad before it needs the value.
+ *   model kernel   : waits BARRIER(t-1) before gathering, pushes MAX(t)
+ *   mass kernel    : waits MAX(t),  pushes MASS(t)
+ *   resample kernel: waits MAX(t) + MASS(t), pushes BARRIER(t)
+ * Exchange k of a run uses tag = *epoch * 2^32 + k and pad slot k % 4.
+ */
+#define GJB_PAD_SLOTS 4
+#define GJB_PAD_WORDS (GJB_PAD_SLOTS * GJB_MAX_RANKS * 2)   /* uint64 words per rank */
+
+typedef struct gjb_link {      /* lives in DEVICE memory; constant for a plan     */
+  int32_t rank, world;
+  uint64_t* pads[GJB_MAX_RANKS];
+  const uint64_t* epoch;
+  uint32_t* counter;           /* zero-initialised ticket counter (self resetting) */
+} gjb_link;
+
+int gjb_weight_mass_linked(const float* logw, int64_t n, uint64_t* tile_mass, const gjb_link* link,
+                           uint64_t wait_max, uint64_t push_mass, void* stream);
+
+/*
+ * PULL form of the global resample (no cross-rank stores, no barrier): the mass
+ * kernel's last CTA also writes the inclusive prefix of this rank's tile masses
+ * (tile_prefix, read by peers); every rank then resolves the ancestors of ITS
+ * OWN offspring slots by scanning the parent tiles -- local or on a peer --
+ * whose offspring range overlaps its slots.  Per step: 2 hand-offs (MAX, MASS);
+ * log-weights and tile prefixes are double buffered across steps.
+ */
+int gjb_weight_mass_prefix_linked(const float* logw, int64_t n, uint64_t* tile_mass, uint64_t* tile_prefix,
+                                  const gjb_link* link, uint64_t wait_max, uint64_t push_mass, void* stream);
+int gjb_resample_systematic_pull(const gjb_resample_args* a, const gjb_peers* logw_peers,
+                                 const gjb_peers* prefix_peers, const gjb_link* link, uint64_t wait_max,
+                                 uint64_t wait_mass, void* stream);
+int gjb_resample_systematic_linked(const gjb_resample_args* a, const gjb_peers* anc, const gjb_link* link,
+                                   uint64_t wait_max, uint64_t wait_mass, uint64_t push_barrier, void* stream);
 int gjb_epoch_bump(uint64_t* epoch, void* stream);
 
 /* gjb_resample_systematic with every rank's ancestor buffer: offspring j is
@@ -210,6 +248,9 @@ typedef struct gjb_model_args {
   const uint32_t* key_dev;   /* nullable: {key0, key1} read on the device instead (graph replay) */
   const int32_t* gather;     /* nullable: per-particle args are read at gather[i] */
   const gjb_peers* peer_args; /* nullable DEVICE array [GJB_MAX_ARGS]: per-particle arg i lives on rank gather[i] / n_per_rank */
+  const gjb_link* link;      /* nullable: fused cross-rank hand-offs (multi-GPU filter)          */
+  uint64_t wait_off;         /* != 0: poll BARRIER exchange wait_off before reading gathered rows */
+  uint64_t push_off;         /* != 0: last CTA pushes *wmax as MAX exchange push_off              */
   const void* args[GJB_MAX_ARGS];      /* model args: per-particle arrays or shared blocks */
   float scalars[GJB_MAX_ARGS];         /* model args passed by value (host scalars)        */
   const void* site_in[GJB_MAX_SITES];  /* constrained / previous values        */

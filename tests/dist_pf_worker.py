@@ -41,8 +41,8 @@ def main():
             model, shared = lgssm_step_vec, (torch.full((d,), LG_Q), torch.full((d,), LG_R))
         obs = gj.C["y"].set(torch.from_numpy(ys))
         mine = torch.from_numpy(x0[rank * n:(rank + 1) * n])
-        for use_graph in (False, True):
-            dpf = DistributedParticleFilter(model, n)
+        for use_graph, fused, mode in ((False, True, "pull"), (True, True, "pull"), (True, True, "push"), (True, False, "push")):
+            dpf = DistributedParticleFilter(model, n, fused=fused, mode=mode)
             res = dpf.run(gj.key(21), mine, obs, shared_args=shared, record=True, use_graph=use_graph)
             res2 = dpf.run(gj.key(21), mine, obs, shared_args=shared, record=True, use_graph=use_graph)  # replay: epoch tags advance
             torch.cuda.synchronize()
@@ -59,7 +59,7 @@ def main():
             # cross-rank traffic really happened: some ancestors of my slots live on the other rank(s)
             a = res.ancestors[-1]
             remote = int(((a < lo) | (a >= hi)).sum())
-            print(f"[rank {rank}] d={d} graph={use_graph}: OK, logZ={res.log_marginal_likelihood.item():.4f}, "
+            print(f"[rank {rank}] d={d} graph={use_graph} mode={mode} fused={fused}: OK, logZ={res.log_marginal_likelihood.item():.4f}, "
                   f"{remote} of {n} last-step ancestors remote", flush=True)
             del dpf
     dist.barrier()
