@@ -64,7 +64,12 @@ def _is_scalar_number(v) -> bool:
 def _mark(tree, axes):
     """Wrap leaves with ``Batched`` where the in_axes tree says 0."""
     if isinstance(tree, ChoiceMap):
-        return tree.map_leaves(lambda v: Batched(v)) if axes == 0 else tree
+        def wrap(v):
+            if isinstance(v, torch.Tensor) and v.ndim == 0:
+                return v  # a 0-d leaf has no particle axis: shared by all particles
+            return Batched(v)
+
+        return tree.map_leaves(wrap) if axes == 0 else tree
     if isinstance(axes, (tuple, list)) and isinstance(tree, (tuple, list)):
         if len(axes) != len(tree):
             raise ValueError("in_axes structure does not match the argument structure")
@@ -241,6 +246,11 @@ class StaticTrace(Trace):
     def _site_value(self, s):
         v = self.values[s.index]
         v = self._view(v, self.bcast[s.index])
+        if self.bcast[s.index] and self.batched and isinstance(v, torch.Tensor):
+            # a constraint shared by all particles reads back with the particle axis, like every
+            # leaf of a vmapped trace in the reference (zero-copy expand)
+            ev = tuple(s.value.shape)
+            v = v.reshape(ev).expand((self.n,) + ev)
         if getattr(s.dist, "bool_valued", False) and isinstance(v, torch.Tensor):
             v = v.to(torch.bool)
         return v
