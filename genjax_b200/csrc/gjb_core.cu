@@ -107,30 +107,30 @@ __global__ void __launch_bounds__(kThreads) weight_mass_linked_kernel(const floa
   }
 }
 
-// pull resampler: CTA (b, p) looks at parent tile b of rank p and writes the ancestors of the offspring
-// of that tile that fall into THIS rank's slots [out_lo, out_lo + out_n) -- into the local ancestor array
+// pull resampler: CTA b walks over the ranks p and, for every parent tile (p, b) whose offspring overlap
+// THIS rank's slots [out_lo, out_lo + out_n), scans it and writes those ancestors into the local array.
+// With balanced weights only p == rank (plus a neighbour at the block edges) passes the two rejects.
 __global__ void __launch_bounds__(kThreads) resample_pull_kernel(const __grid_constant__ gjb_resample_args R,
                                                                  const __grid_constant__ gjb_peers LW,
                                                                  const __grid_constant__ gjb_peers PF,
                                                                  const gjb_link* __restrict__ L, uint64_t wait_max,
                                                                  uint64_t wait_mass) {
   __shared__ TileSmem sm;
-  __shared__ uint64_t vals[GJB_MAX_RANKS];
+  __shared__ uint64_t vmax[GJB_MAX_RANKS];
+  __shared__ uint64_t vmass[GJB_MAX_RANKS];
   __shared__ __align__(16) int32_t heads[kWin];
   const int tid = threadIdx.x;
-  const int p = blockIdx.y;  // rank that owns the parent tile
+  const int world = L->world;
   const int64_t npr = LW.n_per_rank;
   const int64_t n_total = R.n_total, out_lo = R.out_lo, out_n = R.out_n;
-  link_wait(L, wait_max, vals);
+  link_wait(L, wait_max, vmax);
   uint32_t me = 0;
-  for (int r = 0; r < L->world; ++r) me = max(me, (uint32_t)vals[r]);
+  for (int r = 0; r < world; ++r) me = max(me, (uint32_t)vmax[r]);
   const float M = fdec(me);
-  __syncthreads();
-  link_wait(L, wait_mass, vals);
-  uint64_t base = 0, S = 0;
-  for (int r = 0; r < L->world; ++r) { if (r < p) base += vals[r]; S += vals[r]; }
-  const uint64_t Sp = vals[p];
-  if (blockIdx.x == 0 && p == L->rank && tid == 0) {
+  link_wait(L, wait_mass, vmass);
+  uint64_t S = 0;
+  for (int r = 0; r < world; ++r) S += vmass[r];
+  if (blockIdx.x == 0 && tid == 0) {
     if (R.lse_out) {
       R.lse_out[0] = (double)M;
       R.lse_out[1] = (double)S;
@@ -140,11 +140,10 @@ __global__ void __launch_bounds__(kThreads) resample_pull_kernel(const __grid_co
   }
   const int64_t tile_base = (int64_t)blockIdx.x * kTile;
   if (S == 0) {  // every weight is zero: identity ancestors for my own slots
-    if (p == L->rank)
-      for (int k = tid; k < kTile; k += kThreads) {
-        const int64_t i = tile_base + k;
-        if (i < npr) R.ancestors[i] = (int32_t)(out_lo + i);
-      }
+    for (int k = tid; k < kTile; k += kThreads) {
+      const int64_t i = tile_base + k;
+      if (i < npr) R.ancestors[i] = (int32_t)(out_lo + i);
+    }
     return;
   }
   uint32_t key0 = R.key0, key1 = R.key1;
@@ -158,15 +157,25 @@ __global__ void __launch_bounds__(kThreads) resample_pull_kernel(const __grid_co
   const double scale = __ddiv_rn((double)n_total, (double)S);
   const int32_t nt = (int32_t)n_total;
   const int64_t w_lo = out_lo, w_hi = out_lo + out_n;
-  // rank-level reject: offspring range of all of rank p's parents
-  if ((int64_t)offspring_cnt(base + Sp, S, scale, u0, nt) <= w_lo || (int64_t)offspring_cnt(base, S, scale, u0, nt) >= w_hi) return;
-  // tile-level reject from rank p's inclusive tile prefix (2 words, local or over NVLink)
-  const unsigned long long* pf = reinterpret_cast<const unsigned long long*>(PF.base[p]);
-  const uint64_t pre = blockIdx.x ? (uint64_t)__ldcg(pf + blockIdx.x - 1) : 0ull;
-  const uint64_t end = (uint64_t)__ldcg(pf + blockIdx.x);
-  if ((int64_t)offspring_cnt(base + end, S, scale, u0, nt) <= w_lo || (int64_t)offspring_cnt(base + pre, S, scale, u0, nt) >= w_hi) return;
-  const float* lw = reinterpret_cast<const float*>(LW.base[p]);
-  resample_tile<true>(lw, npr, tile_base, M, base + pre, S, n_total, u0, out_lo, out_n, (int64_t)p * npr, R.ancestors, sm, heads);
+  uint64_t base = 0;
+  for (int p = 0; p < world; ++p) {
+    const uint64_t Sp = vmass[p];
+    // rank-level reject: offspring range of all of rank p's parents
+    const bool rank_hit = (int64_t)offspring_cnt(base + Sp, S, scale, u0, nt) > w_lo &&
+                          (int64_t)offspring_cnt(base, S, scale, u0, nt) < w_hi;
+    if (rank_hit) {
+      // tile-level reject from rank p's inclusive tile prefix (2 words, local or over NVLink)
+      const unsigned long long* pf = reinterpret_cast<const unsigned long long*>(PF.base[p]);
+      const uint64_t pre = blockIdx.x ? (uint64_t)__ldcg(pf + blockIdx.x - 1) : 0ull;
+      const uint64_t end = (uint64_t)__ldcg(pf + blockIdx.x);
+      if ((int64_t)offspring_cnt(base + end, S, scale, u0, nt) > w_lo && (int64_t)offspring_cnt(base + pre, S, scale, u0, nt) < w_hi) {
+        const float* lw = reinterpret_cast<const float*>(LW.base[p]);
+        resample_tile<true>(lw, npr, tile_base, M, base + pre, S, n_total, u0, out_lo, out_n, (int64_t)p * npr, R.ancestors,
+                            sm, heads);
+      }
+    }
+    base += Sp;
+  }
 }
 
 __global__ void __launch_bounds__(256) lse_finalize_kernel(const uint64_t* __restrict__ tile_mass, int n_tiles,
@@ -551,7 +560,7 @@ int gjb_resample_systematic_pull(const gjb_resample_args* a, const gjb_peers* lo
   if (a->n_total > 0x7fffffffLL) return GJB_E_RANGE;
   for (int r = 0; r < world; ++r) if (!logw_peers->base[r] || !prefix_peers->base[r]) return GJB_E_ARG;
   const int64_t tiles = (npr + kTile - 1) / kTile;
-  resample_pull_kernel<<<dim3((unsigned)tiles, (unsigned)world), kThreads, 0, (cudaStream_t)stream>>>(
+  resample_pull_kernel<<<dim3((unsigned)tiles), kThreads, 0, (cudaStream_t)stream>>>(
       *a, *logw_peers, *prefix_peers, link, wait_max, wait_mass);
   return launch_status();
 }

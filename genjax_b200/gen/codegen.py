@@ -678,8 +678,9 @@ class _Generator:
         return out
 
     # ------------------------------------------------------------ kernels
-    def model_kernel(self) -> list[str]:
-        out = ["__global__ void __launch_bounds__(kThreads) model_kernel(const __grid_constant__ gjb_model_args A) {"]
+    def model_kernel(self, static: bool = False) -> list[str]:
+        name = "model_kernel_static" if static else "model_kernel"
+        out = [f"__global__ void __launch_bounds__(kThreads) {name}(const __grid_constant__ gjb_model_args A) {{"]
         out.append("  if (A.link && A.wait_off) {  // multi-GPU: the peers' ancestor writes of the previous step have landed")
         out.append("    __shared__ uint64_t link_vals[GJB_MAX_RANKS];")
         out.append("    gjb::link_wait(A.link, A.wait_off, link_vals);")
@@ -697,10 +698,10 @@ class _Generator:
         out.append("  const uint32_t key0 = A.key_dev ? __ldg(A.key_dev) : A.key0, key1 = A.key_dev ? __ldg(A.key_dev + 1) : A.key1;")
         out.append("  float run_max = -INFINITY;")
         if self.group:
-            out.append("  run_groups<false, false>(io, U, fl, A.n, A.idx_offset, key0, key1, (int64_t)blockIdx.x * kPPB, A.n, (int64_t)gridDim.x * kPPB, run_max);")
+            out.append(f"  run_groups<false, {'true' if static else 'false'}>(io, U, fl, A.n, A.idx_offset, key0, key1, (int64_t)blockIdx.x * kPPB, A.n, (int64_t)gridDim.x * kPPB, run_max);")
         else:
             out.append("  const int64_t nq = (A.n + (int64_t)(A.idx_offset & 3) + 3) >> 2;")
-            out.append("  run_quads<false, false>(io, U, fl, A.n, A.idx_offset, key0, key1, blockIdx.x * (int64_t)kThreads + threadIdx.x, nq, (int64_t)gridDim.x * kThreads, run_max);")
+            out.append(f"  run_quads<false, {'true' if static else 'false'}>(io, U, fl, A.n, A.idx_offset, key0, key1, blockIdx.x * (int64_t)kThreads + threadIdx.x, nq, (int64_t)gridDim.x * kThreads, run_max);")
         out.append("  if (A.wmax) gjb::block_wmax(run_max, A.wmax);")
         out.append("  if (A.link && A.push_off) {  // multi-GPU: the CTA that finishes last publishes this rank's max")
         out.append("    if (gjb::link_last_block(A.link)) gjb::link_push(A.link, A.push_off, (uint64_t)__ldcg(A.wmax));")
@@ -817,6 +818,8 @@ class _Generator:
         out = self.header()
         out.extend(self.run_groups() if self.group else self.run_quads())
         out.extend(self.model_kernel())
+        if self.pf_obs is not None:
+            out.extend(self.model_kernel(static=True))
         pf = self.pf_supported()
         if pf:
             out.extend(self.pf_kernel())
@@ -885,6 +888,17 @@ int gjb_model_pf_run(const gjb_pf_args* a, void* stream) {{
 int gjb_model_pf_grid(int64_t n) { (void)n; return GJB_E_MODE; }
 int gjb_model_pf_run(const gjb_pf_args* a, void* stream) { (void)a; (void)stream; return GJB_E_MODE; }
 """
+        if self.pf_obs is not None:
+            static_dispatch = f"""// a launch whose flags are exactly the baked-in filter flags (and that asks for no score / weight
+  // accumulation, and whose lanes start on a quad boundary) takes the specialised instantiation
+  bool is_static = !a->score_in && !a->weight_in && !a->score_out && (a->idx_offset & 3) == 0;
+  for (int j = 0; j < {self.ns}; ++j) is_static = is_static && a->site_flags[j] == kPfFl_host[j];
+  if (is_static) {{{{
+    model_kernel_static<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(*a);
+    return (int)cudaGetLastError();
+  }}}}"""
+        else:
+            static_dispatch = ""
         chain_code = chain_ext if chain_ext is not None else """
 int gjb_model_mh_chain(const gjb_chain_args* a, void* stream) { (void)a; (void)stream; return GJB_E_MODE; }
 int gjb_model_hmc_chain(const gjb_chain_args* a, void* stream) { (void)a; (void)stream; return GJB_E_MODE; }
@@ -900,6 +914,7 @@ int gjb_model_launch(const gjb_model_args* a, void* stream) {{
   int64_t blocks = (work + {per_block} - 1) / {per_block};
   const int64_t cap = gjb::resident_blocks((const void*)model_kernel, kThreads, 8);  // one full wave, grid-stride inside
   if (blocks > cap) blocks = cap;
+  {static_dispatch}
   model_kernel<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(*a);
   return (int)cudaGetLastError();
 }}

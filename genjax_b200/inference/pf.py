@@ -59,7 +59,7 @@ class ParticleFilter:
     particles).  Every other site is proposed from the model (bootstrap)."""
 
     def __init__(self, step: StaticGenerativeFunction, n_particles: int, *, n_state: int = 1, resampler: str = "systematic",
-                 idx_offset: int = 0, n_total: int | None = None, mode: str = "persistent"):
+                 idx_offset: int = 0, n_total: int | None = None, mode: str = "graph"):
         if resampler != "systematic":
             raise NotImplementedError("the fused filter loop uses systematic resampling; see ParticleCollection.resample")
         if mode not in ("persistent", "graph"):
@@ -122,7 +122,7 @@ class _Plan:
                 specs.append(ArgSpec("shared", "i32" if s.dtype == torch.int32 else "f32", tuple(s.shape)))
             else:
                 specs.append(ArgSpec("scalar", "i32" if isinstance(s, int) else "f32", ()))
-        self.cm = step.prebuild(specs, pf_obs=tuple(obs.keys()) if pf.mode == "persistent" else None)
+        self.cm = step.prebuild(specs, pf_obs=tuple(obs.keys()))  # filter variant: site flags baked in
         ir = self.cm.ir
         self.ir = ir
         # static buffers (graph replays read/write these)

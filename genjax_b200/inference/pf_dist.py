@@ -143,7 +143,7 @@ class _DistPlan:
                 specs.append(ArgSpec("shared", "i32" if s.dtype == torch.int32 else "f32", tuple(s.shape)))
             else:
                 specs.append(ArgSpec("scalar", "i32" if isinstance(s, int) else "f32", ()))
-        self.cm = pf.step.prebuild(specs)
+        self.cm = pf.step.prebuild(specs, pf_obs=tuple(obs.keys()))  # filter variant: site flags baked in
         ir = self.ir = self.cm.ir
         if len(ir.ret_leaves) != len(state0):
             raise ValueError("the step must return one leaf per state leaf")
