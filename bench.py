@@ -389,6 +389,14 @@ def run_ours(args):
             "achieved": model_gbs, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": model_gbs / peak,
             "traffic": None, "kernel_us": model_ms * 1e3, "algorithmic_bytes_per_launch": model_bytes,
         }
+    # DRAM traffic of the dominant kernel per launch from the committed `ncu --set full` capture (profiles/)
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            tr = json.load(f).get(f"d{d}", {})
+        roofline["traffic"] = tr.get("model_kernel_dram_bytes_per_launch")
+        roofline["traffic_source"] = tr.get("source")
+    except Exception:
+        pass
     roofline["working_set_note"] = (
         "L2-resident: %d MB of particle arrays < 126 MB L2, DRAM traffic is only the first touch" % ((8 * d + 12) * n >> 20)
         if (8 * d + 12) * n < (100 << 20) else "HBM-resident: particle arrays exceed the 126 MB L2")

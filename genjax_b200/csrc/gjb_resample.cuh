@@ -167,13 +167,13 @@ struct TileSmem {
   int32_t fill;
 };
 
-// cumulative offspring count of a particle whose inclusive CDF value is C (n_total < 2^31)
+// cumulative offspring count of a particle whose inclusive CDF value is C (n_total < 2^31):
+// clamp(ceil(C * scale - u0), 0, n_total).  0 <= C < S and u0 in (0, 1) put C*scale - u0 inside (-1, n_total),
+// so the clamp is a no-op and ceil + convert is ONE round-up conversion; C == S closes the range exactly.
 __device__ __forceinline__ int32_t offspring_cnt(uint64_t C, uint64_t S, double scale, double u0, int32_t n_total) {
-  if (C == S) return n_total;
-  const double pos = __dsub_rn(__dmul_rn((double)C, scale), u0);
-  double c = ceil(pos);
-  c = fmin(fmax(c, 0.0), (double)n_total);
-  return (int32_t)c;
+  const double pos = __dsub_rn(__dmul_rn((double)(long long)C, scale), u0);  // C < 2^63: signed conversion is exact
+  const int32_t c = __double2int_ru(pos);
+  return C == S ? n_total : c;
 }
 
 // One tile of the systematic resampler: scan the tile's masses on top of
