@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(kThreads) weight_mass_linked_kernel(const floa
         carry += ctot;
       }
       tot = carry;
-      __syncthreads();  // the prefix stores precede the release store of the tag (cumulative through the barrier)
+      __threadfence();  // the prefix stores are at L2 before the flag leaves
+      __syncthreads();
     } else {
       for (int t = threadIdx.x; t < nt; t += kThreads)
         tot += __ldcg(reinterpret_cast<const unsigned long long*>(tile_mass) + t);
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(kThreads) resample_systematic_kernel(const __g
                          nullptr, peers);
   }
   if (L && push_barrier) {
-    if (link_last_block(L)) link_push(L, push_barrier, 0ull);
+    if (link_last_block(L)) link_push_release(L, push_barrier, 0ull);
   }
 }
 
@@ -358,20 +359,21 @@ __global__ void __launch_bounds__(256) gather_rows_peers_kernel(const __grid_con
     const int64_t row = k / w;
     const int32_t col = (int32_t)(k - row * w);
     const int64_t g = __ldg(anc + row);
-    const int64_t owner = g / P.n_per_rank;
+    const int64_t owner = peer_owner(&P, (uint32_t)g);
     const T* src = reinterpret_cast<const T*>(P.base[owner]);
     dst[k] = __ldg(src + (g - owner * P.n_per_rank) * w + col);
   }
 }
 
 // ------------------------------------------------------- cross-rank exchange
-// pad layout on every rank: uint64 [2 slots][GJB_MAX_RANKS sources][2] = {value, tag}
+// stand-alone form of the hand-offs (one CTA; pushes with a system-scope release, so it also orders
+// earlier stores into peer memory): same pad format as the fused form (gjb_resample.cuh)
 __global__ void __launch_bounds__(256) exchange_kernel(const __grid_constant__ gjb_xchg_args X) {
   __shared__ uint64_t red[8];
   __shared__ uint64_t vals[GJB_MAX_RANKS];
   const int tid = threadIdx.x;
-  const uint64_t tag = (__ldg(X.epoch) << 32) + X.tag_offset;
-  const int slot = (int)(X.tag_offset % GJB_PAD_SLOTS);
+  const uint64_t epoch = __ldg(reinterpret_cast<const unsigned long long*>(X.epoch));
+  const uint32_t tag = (uint32_t)(((epoch + 1) << 16) | (X.tag_offset & 0xffffu));
   uint64_t mine = 0;
   if (X.mode == GJB_XCHG_MAX) {
     mine = (uint64_t)__ldg(X.wmax);
@@ -384,16 +386,10 @@ __global__ void __launch_bounds__(256) exchange_kernel(const __grid_constant__ g
     for (int w = 0; w < 8; ++w) mine += red[w];
   }
   if (tid < X.world) {
-    // push {value, tag} into slot[rank] of peer `tid`'s pad; value first, system fence, then the tag
-    volatile uint64_t* dst = X.pads[tid] + ((size_t)slot * GJB_MAX_RANKS + X.rank) * 2;
-    dst[0] = mine;
     __threadfence_system();
-    dst[1] = tag;
-    // wait for rank `tid`'s entry in my own pad
-    volatile uint64_t* src = X.pads[X.rank] + ((size_t)slot * GJB_MAX_RANKS + tid) * 2;
-    while (src[1] != tag) { }
+    pad_store(X.pads[tid], X.tag_offset, X.rank, mine, tag);
+    vals[tid] = pad_poll(X.pads[X.rank], X.tag_offset, tid, tag);
     __threadfence_system();
-    vals[tid] = src[0];
   }
   __syncthreads();
   if (tid == 0) {
@@ -513,6 +509,7 @@ int gjb_resample_systematic_peers(const gjb_resample_args* a, const gjb_peers* a
   for (int r = 0; r < anc->world; ++r) if (!anc->base[r]) return GJB_E_ARG;
   const int64_t tiles = (a->n + kTile - 1) / kTile;
   gjb_peers p = *anc;
+  gjb_peers_set_divisor(&p);
   if (p.world == 1) p.world = 2, p.base[1] = p.base[0];  // keep the routed path even for one rank (tests)
   resample_systematic_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a, p, nullptr, 0, 0, 0);
   return launch_status();
@@ -525,7 +522,9 @@ int gjb_resample_systematic_linked(const gjb_resample_args* a, const gjb_peers* 
   if (a->n <= 0 || a->n_total != anc->n_per_rank * anc->world || a->out_lo != 0 || a->out_n != a->n_total) return GJB_E_ARG;
   if (a->n_total > 0x7fffffffLL) return GJB_E_RANGE;
   const int64_t tiles = (a->n + kTile - 1) / kTile;
-  resample_systematic_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a, *anc, link, wait_max, wait_mass,
+  gjb_peers p = *anc;
+  gjb_peers_set_divisor(&p);
+  resample_systematic_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a, p, link, wait_max, wait_mass,
                                                                                push_barrier);
   return launch_status();
 }
@@ -605,21 +604,35 @@ int gjb_gather_rows_peers(const gjb_peers* src, const int32_t* ancestors, void* 
   for (int r = 0; r < src->world; ++r) if (!src->base[r]) return GJB_E_ARG;
   if (n_out == 0) return 0;
   const bool v16 = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+  gjb_peers p = *src;
+  gjb_peers_set_divisor(&p);
   if (v16) {
     const int w = row_bytes / 16;
     gather_rows_peers_kernel<uint4><<<grid_for(n_out * w, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
-        *src, ancestors, (uint4*)dst, n_out, w);
+        p, ancestors, (uint4*)dst, n_out, w);
   } else {
     const int w = row_bytes / 4;
     gather_rows_peers_kernel<uint32_t><<<grid_for(n_out * w, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
-        *src, ancestors, (uint32_t*)dst, n_out, w);
+        p, ancestors, (uint32_t*)dst, n_out, w);
   }
   return launch_status();
 }
 
+int gjb_peers_set_divisor(gjb_peers* p) {
+  if (!p || p->n_per_rank <= 0 || p->n_per_rank > 0x7fffffffLL) return GJB_E_ARG;
+  const uint64_t d = (uint64_t)p->n_per_rank;
+  if (d == 1) { p->div_mul = 0; p->div_shr = 0; return 0; }
+  unsigned lg = 0;
+  while ((1ull << lg) < d) ++lg;  // ceil(log2 d)
+  const unsigned sh = 31 + lg;
+  p->div_mul = (uint32_t)(((1ull << sh) + d - 1) / d);
+  p->div_shr = sh - 32;
+  return 0;
+}
+
 int gjb_exchange(const gjb_xchg_args* a, void* stream) {
   if (!a || a->world < 1 || a->world > GJB_MAX_RANKS || a->rank < 0 || a->rank >= a->world || !a->epoch) return GJB_E_ARG;
-  if (a->tag_offset == 0 || a->tag_offset >= (1ull << 32)) return GJB_E_ARG;
+  if (a->tag_offset == 0 || a->tag_offset >= (1ull << 16)) return GJB_E_ARG;
   for (int r = 0; r < a->world; ++r) if (!a->pads[r]) return GJB_E_ARG;
   if (a->mode == GJB_XCHG_MAX) { if (!a->wmax || !a->m_global) return GJB_E_ARG; }
   else if (a->mode == GJB_XCHG_MASS) { if (!a->tile_mass || a->n_tiles <= 0 || !a->c_offset || !a->s_total) return GJB_E_ARG; }

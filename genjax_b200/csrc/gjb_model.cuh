@@ -18,6 +18,7 @@
 
 #include "genjax_b200.h"
 #include "gjb_dist.cuh"
+#include "gjb_resample.cuh"
 #include "gjb_rng.cuh"
 
 namespace gjb {
@@ -36,8 +37,8 @@ __device__ __forceinline__ float ldf(const float* p) { return kCg ? __ldcg(p) : 
 // base pointer and local row of a per-particle argument row that may live on a peer rank
 __device__ __forceinline__ const void* arg_base(const void* local, const gjb_peers* P, int64_t& row) {
   if (!P) return local;
-  const int64_t owner = row / P->n_per_rank;
-  row -= owner * P->n_per_rank;
+  const uint32_t owner = peer_owner(P, (uint32_t)row);
+  row -= (int64_t)owner * P->n_per_rank;
   return P->base[owner];
 }
 

@@ -20,24 +20,40 @@
 namespace gjb {
 
 // ---- fused cross-rank hand-offs (gjb_link): see include/genjax_b200.h
-__device__ __forceinline__ uint64_t link_tag(const gjb_link* L, uint64_t off) {
-  return ((uint64_t)__ldg(reinterpret_cast<const unsigned long long*>(L->epoch)) << 32) + off;
+//
+// Pad entry (slot, source rank) = two 64-bit words, each carrying its own copy of the 32-bit tag:
+//     word0 = value[31:0] | tag << 32,   word1 = value[63:32] | tag << 32
+// (the "LL" idea of NCCL: the flag travels inside the 8-byte store it validates, so value and flag need
+// no ordering fence between them).  tag = ((epoch + 1) << 16 | offset) is never 0 and never repeats
+// within the 4-slot reuse distance.
+//
+// Ordering of BULK data (pull mode): everything a peer reads after a hand-off (state rows, log-weights,
+// tile prefixes) was written LOCALLY by the producer kernel; every CTA makes its writes visible at the
+// device's L2 (gpu-scope fence) before it takes its ticket, the last CTA sends the flag after it has seen
+// all tickets, and a peer's NVLink reads are served by this device's L2 -- so no system-scope fence
+// (several microseconds each on this platform) sits on the critical path.  Push mode, which writes
+// ancestors into peer memory, keeps its system-scope release (link_push_release).
+__device__ __forceinline__ uint32_t link_tag(const gjb_link* L, uint64_t off) {
+  const uint64_t epoch = __ldg(reinterpret_cast<const unsigned long long*>(L->epoch));
+  return (uint32_t)(((epoch + 1) << 16) | (off & 0xffffu));
+}
+__device__ __forceinline__ void pad_store(uint64_t* pad, uint64_t off, int src_rank, uint64_t value, uint32_t tag) {
+  volatile uint64_t* dst = pad + ((off % GJB_PAD_SLOTS) * GJB_MAX_RANKS + src_rank) * 2;
+  dst[0] = (value & 0xffffffffull) | ((uint64_t)tag << 32);
+  dst[1] = (value >> 32) | ((uint64_t)tag << 32);
+}
+__device__ __forceinline__ uint64_t pad_poll(const uint64_t* pad, uint64_t off, int src_rank, uint32_t tag) {
+  const volatile uint64_t* src = pad + ((off % GJB_PAD_SLOTS) * GJB_MAX_RANKS + src_rank) * 2;
+  for (;;) {
+    const uint64_t w0 = src[0], w1 = src[1];
+    if ((uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag) return (w0 & 0xffffffffull) | (w1 << 32);
+    __nanosleep(20);
+  }
 }
 // every CTA: wait until all ranks' entries of exchange `off` sit in MY pad; vals[r] = rank r's value
 __device__ __forceinline__ void link_wait(const gjb_link* L, uint64_t off, uint64_t* vals /* smem [GJB_MAX_RANKS] */) {
-  if ((int)threadIdx.x < L->world) {
-    const uint64_t tag = link_tag(L, off);
-    const uint64_t* src = L->pads[L->rank] + ((off % GJB_PAD_SLOTS) * GJB_MAX_RANKS + threadIdx.x) * 2;
-    // acquire load of the tag (pairs with the pusher's release store); every CTA polls the line the peers'
-    // NVLink stores must land in, so back off between polls
-    uint64_t seen;
-    for (;;) {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(src + 1) : "memory");
-      if (seen == tag) break;
-      __nanosleep(40);
-    }
-    vals[threadIdx.x] = *reinterpret_cast<const volatile uint64_t*>(src);
-  }
+  __syncthreads();  // vals may still be read from a previous wait
+  if ((int)threadIdx.x < L->world) vals[threadIdx.x] = pad_poll(L->pads[L->rank], off, threadIdx.x, link_tag(L, off));
   __syncthreads();
 }
 // all threads of every CTA call this after the CTA's last global write; true in the CTA that finishes last
@@ -49,19 +65,29 @@ __device__ __forceinline__ bool link_last_block(const gjb_link* L) {
     const uint32_t total = gridDim.x * gridDim.y * gridDim.z;
     const uint32_t ticket = atomicAdd(L->counter, 1u);
     gjb_is_last = ticket == total - 1;
-    if (gjb_is_last) *L->counter = 0u;  // the next kernel on the stream starts from zero
+    if (gjb_is_last) {
+      *L->counter = 0u;  // the next kernel on the stream starts from zero
+      __threadfence();
+    }
   }
   __syncthreads();
   return gjb_is_last != 0;
 }
-// threads [0, world) of ONE CTA: push {value, tag} into slot[rank] of every peer's pad
+// threads [0, world) of ONE CTA: push the value into slot[rank] of every peer's pad (no fence: see above)
 __device__ __forceinline__ void link_push(const gjb_link* L, uint64_t off, uint64_t value) {
+  if ((int)threadIdx.x < L->world) pad_store(L->pads[threadIdx.x], off, L->rank, value, link_tag(L, off));
+}
+// same after a system-scope release: orders this device's earlier stores into PEER memory before the flag
+__device__ __forceinline__ void link_push_release(const gjb_link* L, uint64_t off, uint64_t value) {
   if ((int)threadIdx.x < L->world) {
-    uint64_t* dst = L->pads[threadIdx.x] + ((off % GJB_PAD_SLOTS) * GJB_MAX_RANKS + L->rank) * 2;
-    *reinterpret_cast<volatile uint64_t*>(dst) = value;
-    const uint64_t tag = link_tag(L, off);
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst + 1), "l"(tag) : "memory");
+    __threadfence_system();
+    pad_store(L->pads[threadIdx.x], off, L->rank, value, link_tag(L, off));
   }
+}
+
+// row / n_per_rank for rows < 2^31 without an integer division (see gjb_peers in include/genjax_b200.h)
+__device__ __forceinline__ uint32_t peer_owner(const gjb_peers* P, uint32_t row) {
+  return P->n_per_rank == 1 ? row : (__umulhi(row, P->div_mul) >> P->div_shr);
 }
 
 // where offspring slot j lives: a local array, or the owning rank's array (peer mapped)
@@ -71,7 +97,7 @@ struct AncRoute {
   __device__ __forceinline__ int32_t* at(int32_t j) const {
     if (!peers) return local + j;
     const int32_t npr = (int32_t)peers->n_per_rank;
-    const int32_t owner = j / npr;
+    const int32_t owner = (int32_t)peer_owner(peers, (uint32_t)j);
     return reinterpret_cast<int32_t*>(const_cast<void*>(peers->base[owner])) + (j - owner * npr);
   }
 };

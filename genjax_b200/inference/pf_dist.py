@@ -81,6 +81,7 @@ class SymmArena:
         P.world, P.rank, P.n_per_rank = self.world, self.rank, int(n_per_rank)
         for r in range(self.world):
             P.base[r] = self.ptrs[r] + off
+        cabi.check(cabi.core().gjb_peers_set_divisor(C.byref(P)), "gjb_peers_set_divisor")
         return P
 
 
@@ -147,6 +148,8 @@ class _DistPlan:
         ir = self.ir = self.cm.ir
         if len(ir.ret_leaves) != len(state0):
             raise ValueError("the step must return one leaf per state leaf")
+        if 3 * T + 3 >= (1 << 16):
+            raise ValueError("at most 21844 filter steps per run (16-bit hand-off offsets)")
         slots = T if record else 2
         self.slots = slots
         # ---- symmetric buffers: state ping-pong, ancestors, exchange pad

@@ -69,7 +69,8 @@ XCHG_MAX, XCHG_MASS, XCHG_BARRIER = 0, 1, 2
 class Peers(C.Structure):
     """``gjb_peers`` (include/genjax_b200.h)."""
 
-    _fields_ = [("world", _i32), ("rank", _i32), ("n_per_rank", _i64), ("base", _p * GJB_MAX_RANKS)]
+    _fields_ = [("world", _i32), ("rank", _i32), ("n_per_rank", _i64), ("base", _p * GJB_MAX_RANKS),
+                ("div_mul", _u32), ("div_shr", _u32)]
 
 
 GJB_PAD_SLOTS = 4
@@ -192,6 +193,7 @@ CORE_PROTOTYPES = {
     "gjb_resample_multinomial": (C.c_int, [_p, _i64, _p, _p, _p, _u32, _u32, _u64, _i64, _p, _p]),
     "gjb_gather_rows": (C.c_int, [_p, _p, _p, _i64, _i32, _p]),
     "gjb_exchange": (C.c_int, [C.POINTER(XchgArgs), _p]),
+    "gjb_peers_set_divisor": (C.c_int, [C.POINTER(Peers)]),
     "gjb_epoch_bump": (C.c_int, [_p, _p]),
     "gjb_weight_mass_linked": (C.c_int, [_p, _i64, _p, _p, _u64, _u64, _p]),
     "gjb_weight_mass_prefix_linked": (C.c_int, [_p, _i64, _p, _p, _p, _u64, _u64, _p]),
@@ -233,7 +235,7 @@ def core():
     if _core is None:
         path = build.build_core()
         _core = _bind(C.CDLL(str(path)), CORE_PROTOTYPES)
-        if _core.gjb_abi_version() != 5:
+        if _core.gjb_abi_version() != 6:
             raise GjbError("libgjb_core.so ABI mismatch")
     return _core
 

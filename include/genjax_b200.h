@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GJB_ABI_VERSION 5
+#define GJB_ABI_VERSION 6
 
 #define GJB_E_ARG (-1)      /* null / misaligned pointer, negative size          */
 #define GJB_E_RANGE (-2)    /* size beyond what the kernel supports              */
@@ -137,7 +137,13 @@ typedef struct gjb_peers {
   int32_t rank;
   int64_t n_per_rank;        /* particles per rank (multiple of 4)              */
   const void* base[GJB_MAX_RANKS];   /* the same buffer on every rank (peer mapped) */
+  uint32_t div_mul, div_shr; /* owner = row / n_per_rank without a division (rows < 2^31):
+                                n_per_rank == 1 ? row : umulhi(row, div_mul) >> div_shr, with p = 31 + ceil(log2 n_per_rank),
+                                div_mul = ceil(2^p / n_per_rank), div_shr = p - 32 (host: gjb_peers_set_divisor) */
 } gjb_peers;
+
+/* Fills div_mul / div_shr for p->n_per_rank (host helper, no GPU work). */
+int gjb_peers_set_divisor(gjb_peers* p);
 
 #define GJB_XCHG_MAX 0       /* in: wmax (encoded)        out: m_global = max over ranks        */
 #define GJB_XCHG_MASS 1      /* in: tile_mass[n_tiles]    out: c_offset (ranks before), s_total */
@@ -147,9 +153,10 @@ typedef struct gjb_xchg_args {
   int32_t rank, world;
   int32_t mode;              /* GJB_XCHG_*                                       */
   int32_t n_tiles;           /* MASS: entries of tile_mass                       */
-  uint64_t* pads[GJB_MAX_RANKS];     /* every rank's pad: uint64 [GJB_PAD_SLOTS][GJB_MAX_RANKS][2] = {value, tag} */
+  uint64_t* pads[GJB_MAX_RANKS];     /* every rank's pad: uint64 [GJB_PAD_SLOTS][GJB_MAX_RANKS][2]; entry = value[31:0] | tag<<32,
+                                        value[63:32] | tag<<32 (the 32-bit tag rides inside each 8-byte store it validates) */
   const uint64_t* epoch;     /* device counter (bumped once per filter run)      */
-  uint64_t tag_offset;       /* tag = *epoch * 2^32 + tag_offset (>= 1); pad slot tag_offset % GJB_PAD_SLOTS */
+  uint64_t tag_offset;       /* 1 <= tag_offset < 2^16; tag = (*epoch + 1) << 16 | tag_offset; pad slot tag_offset % GJB_PAD_SLOTS */
   const uint32_t* wmax;      /* MAX input                                        */
   const uint64_t* tile_mass; /* MASS input                                       */
   float* m_global;           /* MAX output                                       */
@@ -166,7 +173,7 @@ int gjb_exchange(const gjb_xchg_args* a, void* stream);
  *   model kernel   : waits BARRIER(t-1) before gathering, pushes MAX(t)
  *   mass kernel    : waits MAX(t),  pushes MASS(t)
  *   resample kernel: waits MAX(t) + MASS(t), pushes BARRIER(t)
- * Exchange k of a run uses tag = *epoch * 2^32 + k and pad slot k % 4.
+ * Exchange k of a run uses tag = (*epoch + 1) << 16 | k and pad slot k % 4 (k < 2^16).
  */
 #define GJB_PAD_SLOTS 4
 #define GJB_PAD_WORDS (GJB_PAD_SLOTS * GJB_MAX_RANKS * 2)   /* uint64 words per rank */

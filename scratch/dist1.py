@@ -8,7 +8,6 @@ from genjax_b200.inference.pf_dist import DistributedParticleFilter
 from genjax_b200.workloads import lgssm_step
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29555")
 torch.cuda.set_device(0); dev = torch.device("cuda", 0)
-dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
 n, T = 1 << 20, 100
 x0 = torch.randn(n, device=dev); ys = torch.randn(T, device=dev)
 def timeit(pf, reps=10):
@@ -19,7 +18,13 @@ def timeit(pf, reps=10):
     for _ in range(reps): pf.run(gj.key(1), x0, gj.C["y"].set(ys))
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps / T * 1e3
-print("plain graph      us/step", round(timeit(ParticleFilter(lgssm_step, n, mode="graph")), 2))
-for mode, fused in (("pull", True),):
-    print(f"dist world=1 {mode} fused={fused} us/step", round(timeit(DistributedParticleFilter(lgssm_step, n, mode=mode, fused=fused)), 2))
+plain = ParticleFilter(lgssm_step, n, mode="graph")
+print("plain graph (before any process group)   us/step", round(timeit(plain), 2), flush=True)
+dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+print("plain graph (after nccl init)            us/step", round(timeit(plain), 2), flush=True)
+dpf = DistributedParticleFilter(lgssm_step, n, mode="pull")
+print("dist world=1 pull                        us/step", round(timeit(dpf), 2), flush=True)
+print("plain graph (symmetric memory allocated) us/step", round(timeit(plain), 2), flush=True)
+dpf2 = DistributedParticleFilter(lgssm_step, n, mode="push", fused=False)
+print("dist world=1 push unfused                us/step", round(timeit(dpf2), 2), flush=True)
 dist.destroy_process_group()
