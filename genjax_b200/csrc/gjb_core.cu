@@ -5,6 +5,7 @@
 //
 // All kernels are HBM/L2-streaming integer/fp32 work: coalesced 128-bit loads,
 // warp-shuffle reductions and scans, no tensor cores.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -275,6 +276,68 @@ __global__ void __launch_bounds__(kThreads) resample_systematic_kernel(const __g
   }
 }
 
+// mass + systematic resampling in one cooperative launch: phase B (integer masses, kept in registers),
+// grid barrier, phase C (CDF offset, scan, offspring ranges)
+__global__ void __launch_bounds__(kThreads) mass_resample_kernel(const __grid_constant__ gjb_resample_args R) {
+  const int64_t n = R.n, n_total = R.n_total, out_lo = R.out_lo, out_n = R.out_n, anc_base = R.anc_base;
+  __shared__ TileSmem sm;
+  __shared__ uint64_t sm_b[kThreads / 32];
+  __shared__ __align__(16) int32_t heads[kWin];
+  const int tid = threadIdx.x;
+  const int n_tiles = gridDim.x;
+  const int64_t tile_base = (int64_t)blockIdx.x * kTile;
+  const float M = fdec(__ldg(R.wmax));
+  unsigned long long* tm = reinterpret_cast<unsigned long long*>(const_cast<uint64_t*>(R.tile_mass));
+  // ---- phase B
+  uint64_t q[kItems];
+  {
+    float x[kItems];
+    load_items<false>(R.logw, n, tile_base + tid * kItems, x);
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) { q[k] = det_exp_q(__fadd_rn(x[k], -M)); s += q[k]; }
+    s = block_sum_u64(s, sm.red);
+    if (tid == 0) __stcg(tm + blockIdx.x, (unsigned long long)s);
+  }
+  cooperative_groups::this_grid().sync();
+  // ---- phase C
+  uint64_t pre = 0, tot = 0;
+  for (int t = tid; t < n_tiles; t += kThreads) {
+    const uint64_t v = __ldcg(tm + t);
+    tot += v;
+    if (t < (int)blockIdx.x) pre += v;
+  }
+  pre = block_sum_u64(pre, sm.red);
+  tot = block_sum_u64(tot, sm_b);
+  const uint64_t S = tot;
+  if (blockIdx.x == 0 && tid == 0) {
+    if (R.lse_out) {
+      R.lse_out[0] = (double)M;
+      R.lse_out[1] = (double)S;
+      R.lse_out[2] = S ? (double)M + log((double)S) - kQLog - log((double)n_total) : -INFINITY;
+    }
+    if (R.wmax_next) *R.wmax_next = GJB_WMAX_NEG_INF;
+  }
+  if (S == 0) {
+    for (int k = tid; k < kTile; k += kThreads) {
+      const int64_t i = tile_base + k;
+      const int64_t j = anc_base + i;
+      if (i < n && j >= out_lo && j < out_lo + out_n) R.ancestors[j - out_lo] = (int32_t)j;
+    }
+    return;
+  }
+  uint32_t key0 = R.key0, key1 = R.key1;
+  uint64_t key_index = R.key_index;
+  if (R.key_dev) {
+    key0 = __ldg(R.key_dev);
+    key1 = __ldg(R.key_dev + 1);
+    key_index = (uint64_t)__ldg(R.key_dev + 2) | ((uint64_t)__ldg(R.key_dev + 3) << 32);
+  }
+  const double u0 = resample_u0(key0, key1, key_index);
+  resample_tile<false>(R.logw, n, tile_base, M, pre, S, n_total, u0, out_lo, out_n, anc_base, R.ancestors, sm, heads, nullptr,
+                       nullptr, q);
+}
+
 // ----------------------------------------------------------- multinomial
 
 __global__ void __launch_bounds__(kThreads) cdf_kernel(const float* __restrict__ logw, int64_t n,
@@ -498,6 +561,38 @@ int gjb_resample_systematic(const gjb_resample_args* a, void* stream) {
   const int64_t tiles = (a->n + kTile - 1) / kTile;
   gjb_peers none = {};
   resample_systematic_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a, none, nullptr, 0, 0, 0);
+  return launch_status();
+}
+
+static int mass_resample_resident() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0, sms = 0, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mass_resample_kernel, kThreads, 0);
+    cached = sms * occ;
+  }
+  return cached;
+}
+
+int gjb_mass_resample_fits(int64_t n) {
+  if (n <= 0) return 0;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  return tiles <= mass_resample_resident() ? 1 : 0;
+}
+
+int gjb_mass_resample_systematic(const gjb_resample_args* a, void* stream) {
+  if (!a || !a->logw || !a->tile_mass || !a->ancestors || !a->wmax) return GJB_E_ARG;
+  if (a->m_global || a->c_offset || a->s_total) return GJB_E_MODE;  // single-device form
+  if (a->n <= 0 || a->n_total <= 0 || a->out_n < 0 || a->out_lo < 0) return GJB_E_ARG;
+  if (a->n_total > 0x7fffffffLL) return GJB_E_RANGE;
+  if (!gjb_mass_resample_fits(a->n)) return GJB_E_RANGE;
+  const int64_t tiles = (a->n + kTile - 1) / kTile;
+  void* params[1] = {(void*)a};
+  const cudaError_t e = cudaLaunchCooperativeKernel((const void*)mass_resample_kernel, dim3((unsigned)tiles), dim3(kThreads),
+                                                    params, 0, (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
   return launch_status();
 }
 

@@ -223,12 +223,15 @@ __device__ __forceinline__ uint64_t resample_tile(const float* __restrict__ logw
                                                   uint64_t off, uint64_t S, int64_t n_total, double u0, int64_t out_lo,
                                                   int64_t out_n, int64_t anc_base, int32_t* __restrict__ ancestors,
                                                   TileSmem& sm, int32_t* heads, const uint64_t* qin = nullptr,
-                                                  const gjb_peers* peers = nullptr) {
+                                                  const gjb_peers* peers = nullptr, const uint64_t* qthread = nullptr) {
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   uint64_t q[kItems];
   uint64_t tsum = 0;
-  if (qin) {
+  if (qthread) {  // this thread's masses are still in its registers (fused mass + resample kernel)
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) { q[k] = qthread[k]; tsum += q[k]; }
+  } else if (qin) {
 #pragma unroll
     for (int k = 0; k < kItems; ++k) { q[k] = qin[tid * kItems + k]; tsum += q[k]; }
   } else {

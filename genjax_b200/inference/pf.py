@@ -65,6 +65,7 @@ class ParticleFilter:
         if mode not in ("persistent", "graph"):
             raise ValueError(mode)
         self.mode = mode
+        self.fuse_mass_resample = True  # graph mode: gjb_mass_resample_systematic when the particle count fits
         self.step = step
         self.n = int(n_particles)
         self.n_state = n_state
@@ -259,9 +260,16 @@ class _Plan:
                 smc_ops.gather_rows(self.bufs[k][last], self.anc[last], self.final[k])
             return
         cabi.check(core.gjb_wmax_reset(self.wmax2.data_ptr(), stream), "gjb_wmax_reset")
+        fused = getattr(self, "fuse_mass_resample", None)
+        if fused is None:
+            # mass + resample as one cooperative launch when every tile's CTA is resident (2 launches per step)
+            fused = self.fuse_mass_resample = bool(core.gjb_mass_resample_fits(self.pf.n)) and self.pf.fuse_mass_resample
         for t in range(self.T):
             cabi.check(lib.gjb_model_launch(C.byref(self.margs[t]), stream), "gjb_model_launch")
             lw, R = self.rargs[t]
+            if fused:
+                cabi.check(core.gjb_mass_resample_systematic(C.byref(R), stream), "gjb_mass_resample_systematic")
+                continue
             cabi.check(
                 core.gjb_weight_mass(lw.data_ptr(), lw.numel(), self.wmax2[t & 1 :].data_ptr(), None,
                                      self.ws.tile_mass.data_ptr(), stream),
@@ -275,7 +283,7 @@ class _Plan:
     def launches_per_run(self) -> int:
         if self.persistent:
             return 2 + len(self.bufs)  # init + persistent filter kernel + final gather(s)
-        return 1 + 3 * self.T + len(self.bufs)
+        return 1 + (2 if getattr(self, "fuse_mass_resample", False) else 3) * self.T + len(self.bufs)
 
     def execute(self, key, state0, shared, obs, use_graph):
         tab = torch.from_numpy(pf_key_table(key, self.T).view(np.int32))

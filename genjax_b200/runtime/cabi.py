@@ -190,6 +190,8 @@ CORE_PROTOTYPES = {
     "gjb_weight_mass": (C.c_int, [_p, _i64, _p, _p, _p, _p]),
     "gjb_lse_finalize": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _p]),
     "gjb_resample_systematic": (C.c_int, [C.POINTER(ResampleArgs), _p]),
+    "gjb_mass_resample_fits": (C.c_int, [_i64]),
+    "gjb_mass_resample_systematic": (C.c_int, [C.POINTER(ResampleArgs), _p]),
     "gjb_resample_multinomial": (C.c_int, [_p, _i64, _p, _p, _p, _u32, _u32, _u64, _i64, _p, _p]),
     "gjb_gather_rows": (C.c_int, [_p, _p, _p, _i64, _i32, _p]),
     "gjb_exchange": (C.c_int, [C.POINTER(XchgArgs), _p]),
@@ -235,7 +237,7 @@ def core():
     if _core is None:
         path = build.build_core()
         _core = _bind(C.CDLL(str(path)), CORE_PROTOTYPES)
-        if _core.gjb_abi_version() != 6:
+        if _core.gjb_abi_version() != 7:
             raise GjbError("libgjb_core.so ABI mismatch")
     return _core
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GJB_ABI_VERSION 6
+#define GJB_ABI_VERSION 7
 
 #define GJB_E_ARG (-1)      /* null / misaligned pointer, negative size          */
 #define GJB_E_RANGE (-2)    /* size beyond what the kernel supports              */
@@ -100,6 +100,17 @@ typedef struct gjb_resample_args {
 } gjb_resample_args;
 
 int gjb_resample_systematic(const gjb_resample_args* a, void* stream);
+
+/*
+ * gjb_weight_mass + gjb_resample_systematic as ONE cooperative launch (a grid
+ * barrier instead of a kernel boundary; the integer masses stay in registers
+ * between the two phases).  a->tile_mass is scratch written by the kernel.
+ * Needs one resident CTA per 2048-particle tile: gjb_mass_resample_fits(n) says
+ * whether n qualifies on the current device (1) or the two-launch form must be
+ * used (0).  Single-device form (no c_offset / s_total / m_global).
+ */
+int gjb_mass_resample_fits(int64_t n);
+int gjb_mass_resample_systematic(const gjb_resample_args* a, void* stream);
 
 /*
  * Multinomial resampling: offspring j draws r_j (64 bits of its Philox lane,

@@ -310,3 +310,27 @@ def test_multi_gpu_global_resampling_equals_single_gpu(device):
            "--master-port", "29533", os.path.join(root, "tests", "dist_pf_worker.py")]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "DIST_PF_OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_mass_resample_equals_two_launches(device, use_graph):
+    """gjb_mass_resample_systematic (one cooperative launch, masses kept in registers across a grid barrier)
+    == gjb_weight_mass + gjb_resample_systematic, bit for bit; also inside a captured CUDA graph."""
+    gj, step, _ = _models()
+    from genjax_b200.inference.pf import ParticleFilter
+
+    n, T = 200_003, 6
+    ys = osmc.simulate_lgssm(3, T, 1, A_, Q_, C_, R_)[:, 0]
+    x0 = torch.randn(n, generator=torch.Generator().manual_seed(2))
+    outs = []
+    for fuse in (True, False):
+        pf = ParticleFilter(step, n, mode="graph")
+        pf.fuse_mass_resample = fuse
+        res = pf.run(gj.key(8), x0, gj.C["y"].set(torch.from_numpy(ys)), record=True, use_graph=use_graph)
+        res = pf.run(gj.key(8), x0, gj.C["y"].set(torch.from_numpy(ys)), record=True, use_graph=use_graph)  # replay
+        torch.cuda.synchronize()
+        plan = next(iter(pf._plans.values()))
+        assert plan.fuse_mass_resample == fuse
+        outs.append((res.ancestors.clone(), res.log_increments.clone(), res.state[0].clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
