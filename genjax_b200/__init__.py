@@ -51,7 +51,7 @@ from .gen.gfi import (
     Update,
 )
 from .gen.static import Batched, StaticGenerativeFunction, StaticTrace, gen, vmap
-from .inference.sp import Algorithm, SampleDistribution, Target
+from .inference.sp import Algorithm, Marginal, SampleDistribution, Target, marginal
 from . import inference
 
 C = ChoiceMapBuilder

@@ -123,6 +123,15 @@ def split(k: PRNGKey, num: int = 2) -> KeyBatch:
     return KeyBatch(threefry2x32(w[0], w[1], 0x73706C74, 0), num, 0)
 
 
+def key_children(k, num: int = 2) -> list:
+    """``split`` that also works lane-wise on a ``KeyBatch``: child j of a batch is the batch whose words are
+    hashed with j and whose lanes are unchanged (what ``jax.vmap(jax.random.split)`` over the batch gives, one
+    child batch per column).  For a scalar key this is ``list(split(k, num))``."""
+    if isinstance(k, KeyBatch):
+        return [KeyBatch(threefry2x32(k.words[0], k.words[1], 0x73706C74, j + 1), k.n, k.offset) for j in range(num)]
+    return list(split(k, num))
+
+
 def lanes_of(k) -> tuple[tuple[int, int], int, int]:
     """(words, first lane, n lanes) of a PRNGKey (1 lane) or KeyBatch."""
     if isinstance(k, KeyBatch):

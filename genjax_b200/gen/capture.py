@@ -135,6 +135,14 @@ def flatten(tree) -> tuple[list, Any]:
     leaves: list = []
 
     def go(t):
+        from ..core.choice_map import ChoiceMap
+
+        if isinstance(t, ChoiceMap):
+            # a choice map is a pytree of its leaves (the reference's ChoiceMap is a Pytree, choice_map.py:847)
+            return ("chm", [(addr, go(v)) for addr, v in t.leaves()])
+        if type(t).__name__ == "Target" and hasattr(t, "constraint") and hasattr(t, "p"):
+            # Target(p, args, constraint): p is static, args and constraint are traced (sp.py:53-81)
+            return ("target", (t.p, go(t.args), go(t.constraint)))
         if isinstance(t, tuple):
             return ("tuple", [go(x) for x in t])
         if isinstance(t, list):
@@ -151,6 +159,18 @@ def flatten(tree) -> tuple[list, Any]:
 
 def unflatten(tree, leaves):
     kind, payload = tree
+    if kind == "chm":
+        from ..core.choice_map import ChoiceMap
+
+        out = ChoiceMap.empty()
+        for addr, sub in payload:
+            out = out | ChoiceMap.entry(unflatten(sub, leaves), *addr)
+        return out
+    if kind == "target":
+        from ..inference.sp import Target
+
+        p, a, c = payload
+        return Target(p, unflatten(a, leaves), unflatten(c, leaves))
     if kind == "tuple":
         return tuple(unflatten(x, leaves) for x in payload)
     if kind == "list":

@@ -312,6 +312,12 @@ class GenerativeFunction:
         tr = self.simulate(key, args)
         return tr.get_choices(), tr.get_score(), tr.get_retval()
 
+    def marginal(self, *, selection: Selection | None = None, algorithm=None):
+        """``gen_fn.marginal(selection=..., algorithm=...)`` (generative_function.py ``marginal``; sp.py:208-273)."""
+        from ..inference.sp import Marginal
+
+        return Marginal(self, Selection.all() if selection is None else selection, algorithm)
+
     def partial_apply(self, *bound):
         from .static import gen
 

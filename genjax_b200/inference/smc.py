@@ -17,7 +17,7 @@ import math
 import torch
 
 from ..core.choice_map import ChoiceMap
-from ..core.key import KeyBatch, PRNGKey, split
+from ..core.key import KeyBatch, PRNGKey, key_children, split
 from ..gen.static import Batched, StaticTrace, _rebatch
 from ..runtime import smc_ops
 from .sp import Algorithm, SampleDistribution, Target
@@ -109,6 +109,42 @@ class ParticleCollection:
         return ParticleCollection(tr, lw, self.is_valid), anc
 
 
+def _concat_traces(a: StaticTrace, b: StaticTrace) -> StaticTrace:
+    """``tree_map(stack_to_first_dim, a, b)`` (smc.py:317-351): the particles of ``a`` followed by those of ``b``."""
+    assert a.cm is b.cm, "traces of different models"
+    ir = a.cm.ir
+
+    def rows(tr, j, t):
+        ev = tuple(ir.sites[j].value.shape)
+        if tr.bcast[j] or t.ndim == len(ev):
+            return t.reshape((1,) + ev).expand((tr.n,) + ev)
+        return t.reshape((tr.n,) + ev)
+
+    values = {j: torch.cat([rows(a, j, a.values[j]), rows(b, j, b.values[j])]).contiguous() for j in a.values}
+    rets = []
+    for ra, rb in zip(a.ret_leaves, b.ret_leaves):
+        if isinstance(ra, torch.Tensor):
+            rets.append(torch.cat([ra.reshape((a.n,) + tuple(ra.shape[1:])), rb.reshape((b.n,) + tuple(rb.shape[1:]))]))
+        else:
+            rets.append(ra)
+    score = torch.cat([a.score.reshape(a.n), b.score.reshape(b.n)])
+    return StaticTrace(a.gen_fn, a.cm, a.bound if a.bound is not None else b.bound, a.args, a.n + b.n, True, values, score,
+                       rets, {j: False for j in values})
+
+
+def _stack_chm(batch: ChoiceMap, n: int, one: ChoiceMap) -> ChoiceMap:
+    """Batched choice map (n lanes) followed by one more lane holding ``one``."""
+    out = ChoiceMap.empty()
+    single = dict(one.leaves())
+    for addr, v in batch.leaves():
+        v = v.value if isinstance(v, Batched) else v
+        v = torch.as_tensor(v)
+        w = torch.as_tensor(single[addr]).to(v.device).to(v.dtype)
+        ev = tuple(w.shape)
+        out = out | ChoiceMap.entry(Batched(torch.cat([v.reshape((n,) + ev), w.reshape((1,) + ev)])), *addr)
+    return out
+
+
 class SMCAlgorithm(Algorithm):
     """smc.py:117-230."""
 
@@ -153,6 +189,15 @@ class SMCAlgorithm(Algorithm):
         (target,) = args
         w, chm = self.random_weighted(key, target)
         return _SampleTrace(self, args, chm, w)
+
+    # VI hooks (smc.py:204-230)
+    def estimate_normalizing_constant(self, key: PRNGKey, target: Target):
+        algorithm = ChangeTarget(self, target)
+        key, sub_key = key_children(key)
+        return algorithm.run_smc(sub_key).get_log_marginal_likelihood_estimate()
+
+    def estimate_reciprocal_normalizing_constant(self, key: PRNGKey, target: Target, latent_choices: ChoiceMap, w):
+        return ChangeTarget(self, target).run_csmc_for_normalizing_constant(key, latent_choices, w)
 
 
 class _SampleTrace:
@@ -244,7 +289,25 @@ class ImportanceK(SMCAlgorithm):
         return ParticleCollection(trs, lw, True)
 
     def run_csmc(self, key: PRNGKey, retained: ChoiceMap):
-        raise NotImplementedError("conditional SMC is a 'next' row (SURVEY.md 8f-2)")
+        """Conditional importance sampling: K - 1 fresh particles plus the retained one, last (smc.py:317-351)."""
+        kb = split(key)
+        key, sub_key = kb[0], kb[1]
+        k = self.get_num_particles()
+        if k < 2:
+            return Importance(self.target, self.q).run_csmc(key, retained)
+        sub_keys = split(sub_key, k - 1)
+        if self.q is not None:
+            log_scores, choices = self.q.random_weighted(sub_keys, self.target)
+            retained_score = self.q.estimate_logpdf(key, retained, self.target)
+            stacked = _stack_chm(choices, k - 1, retained)
+            stacked_scores = torch.cat([log_scores.reshape(k - 1), torch.as_tensor(retained_score).reshape(1).to(log_scores)])
+            trs, target_scores = self.target.importance(split(key, k), stacked)
+            return ParticleCollection(trs, target_scores - stacked_scores, True)
+        ignored, ignored_scores = self.target.importance(sub_keys, ChoiceMap.empty())
+        retained_tr, retained_score = self.target.importance(key, retained)
+        retained_tr, retained_score = _as_batch(retained_tr, retained_score)
+        trs = _concat_traces(ignored, retained_tr)
+        return ParticleCollection(trs, torch.cat([ignored_scores.reshape(k - 1), retained_score.reshape(1)]), True)
 
 
 class ChangeTarget(SMCAlgorithm):
@@ -261,7 +324,32 @@ class ChangeTarget(SMCAlgorithm):
         return self.target
 
     def run_smc(self, key: PRNGKey) -> ParticleCollection:
-        collection = self.prev.run_smc(key)
+        return self._reweight(self.prev.run_smc(key), key)
+
+    def run_csmc(self, key: PRNGKey, retained: ChoiceMap) -> ParticleCollection:
+        """smc.py:398-425: conditional SMC of the previous algorithm, then the same reweighting."""
+        return self._reweight(self.prev.run_csmc(key, retained), key)
+
+    def run_csmc_for_normalizing_constant(self, key: PRNGKey, latent_choices: ChoiceMap, w):
+        """smc.py:432-465: the retained particle keeps the weight ``w`` it already has under the new target."""
+        kb = split(key)
+        key, sub_key = kb[0], kb[1]
+        collection = self.prev.run_csmc(sub_key, latent_choices)
+        k = self.get_num_particles()
+        particles = collection.get_particles()
+        lw = collection.get_log_weights()
+        retained_score = particles.score[k - 1]
+        retained_weight = lw[k - 1]
+        w = torch.as_tensor(w).to(lw).reshape(())
+        if k > 1:
+            rew = self._reweight(collection, key).get_log_weights()  # lanes 0..k-2 are the rejected particles
+            all_w = torch.cat([rew[: k - 1], (w - retained_score + retained_weight).reshape(1)]).contiguous()
+        else:
+            all_w = (w - retained_score + retained_weight).reshape(1).contiguous()
+        total = ParticleCollection(particles, all_w, True).get_log_marginal_likelihood_estimate()  # logsumexp - log k
+        return retained_score - total
+
+    def _reweight(self, collection: ParticleCollection, key: PRNGKey) -> ParticleCollection:
         particles = collection.get_particles()
         # latents of every particle, batched along the particle axis
         latents = self.prev.get_final_target().filter_to_unconstrained(_rebatch(particles))
@@ -273,6 +361,3 @@ class ChangeTarget(SMCAlgorithm):
             score_in=particles.score, n=particles.n, batched=True
         )
         return ParticleCollection(new_tr, new_w, True)
-
-    def run_csmc(self, key: PRNGKey, retained: ChoiceMap):
-        raise NotImplementedError("conditional SMC is a 'next' row (SURVEY.md 8f-2)")

@@ -256,3 +256,102 @@ def test_readme_quickstart_config0(device):
             ps.append(chm["p"].item())
         se = 0.2 / math.sqrt(50)
         assert abs(np.mean(ps) - exact) < 4 * se
+
+
+def test_custom_proposal_marginal_and_conditional_smc(device):
+    """data-driven proposals ``ImportanceK(target, q=proposal.marginal())`` (smc.py:301-305), conditional
+    SMC ``run_csmc`` (smc.py:268-279, 317-351, 398-425), ``Marginal`` (sp.py:208-252) and the GenSP density
+    estimators.  With the EXACT posterior as proposal every importance weight equals log p(y): zero variance."""
+    gj = _gj()
+    from genjax_b200.inference.smc import ChangeTarget, Importance, ImportanceK
+
+    @gj.gen
+    def model():
+        x = gj.normal(0.0, 1.0) @ "x"
+        gj.normal(x, 1.0) @ "y"
+
+    @gj.gen
+    def proposal(target):
+        y = target["y"]  # the proposal reads the observation out of the target (custom_proposal.ipynb)
+        gj.normal(y / 2.0, math.sqrt(0.5)) @ "x"
+
+    yv = 1.3
+    target = gj.Target(model, (), gj.C["y"].set(yv))
+    exact_logz = float(od.normal_logpdf(F32(yv), F32(0.0), F32(math.sqrt(2.0))))
+    k = 512
+    alg = ImportanceK(target, q=proposal.marginal(), k_particles=k)
+    pc = alg.run_smc(gj.key(1))
+    lw = pc.get_log_weights().cpu().numpy()
+    assert lw.shape == (k,)
+    np.testing.assert_allclose(lw, exact_logz, atol=2e-5)
+    x = pc.get_particles().get_choices()["x"].cpu().numpy()
+    assert abs(x.mean() - yv / 2) < 4 * math.sqrt(0.5 / k) and abs(x.std() - math.sqrt(0.5)) < 0.08
+    assert alg.log_marginal_likelihood_estimate(gj.key(2)).item() == pytest.approx(exact_logz, abs=2e-5)
+    # conditional SMC: K - 1 fresh particles + the retained one in the last slot
+    retained = gj.C["x"].set(0.4)
+    pc2 = alg.run_csmc(gj.key(3), retained)
+    assert len(pc2) == k and pc2.get_particles().get_choices()["x"][-1].item() == pytest.approx(0.4)
+    np.testing.assert_allclose(pc2.get_log_weights().cpu().numpy(), exact_logz, atol=2e-5)
+    # GenSP density estimate of the retained value == the exact posterior density N(0.4; y/2, sqrt(1/2))
+    est = alg.estimate_logpdf(gj.key(4), retained, target)
+    assert est.item() == pytest.approx(float(od.normal_logpdf(F32(0.4), F32(yv / 2), F32(math.sqrt(0.5)))), abs=1e-4)
+    # without a proposal: prior particles, the retained one scored by the likelihood
+    alg0 = ImportanceK(target, k_particles=64)
+    pc3 = alg0.run_csmc(gj.key(5), retained)
+    assert len(pc3) == 64 and pc3.get_particles().get_choices()["x"][-1].item() == pytest.approx(0.4)
+    # (importance with x AND y constrained: both sites are weighted, smc.py:340-342)
+    assert pc3.get_log_weights()[-1].item() == pytest.approx(
+        float(od.normal_logpdf(F32(0.4), F32(0.0), F32(1.0)) + od.normal_logpdf(F32(yv), F32(0.4), F32(1.0))), abs=1e-5)
+    one = Importance(target, q=proposal.marginal()).run_csmc(gj.key(6), retained)
+    assert one.get_log_weights()[0].item() == pytest.approx(exact_logz, abs=2e-5)
+    # ChangeTarget on top of conditional SMC keeps the retained particle and reweights everyone
+    t2 = gj.Target(model, (), gj.C["y"].set(2.0))
+    pc4 = ChangeTarget(alg, t2).run_csmc(gj.key(7), retained)
+    x4 = pc4.get_particles().get_choices()["x"]
+    assert x4[-1].item() == pytest.approx(0.4)
+    want = exact_logz + (gj.normal.logpdf(torch.full_like(x4, 2.0), x4, 1.0) - gj.normal.logpdf(torch.full_like(x4, yv), x4, 1.0))
+    torch.testing.assert_close(pc4.get_log_weights(), want, rtol=1e-4, atol=1e-4)
+    # VI hooks (smc.py:204-230)
+    assert alg.estimate_normalizing_constant(gj.key(8), target).item() == pytest.approx(exact_logz, abs=2e-5)
+    w_ret = float(od.normal_logpdf(F32(0.4), F32(0), F32(1)) + od.normal_logpdf(F32(yv), F32(0.4), F32(1.0))
+                  - od.normal_logpdf(F32(0.4), F32(yv / 2), F32(math.sqrt(0.5))))
+    rz = alg.estimate_reciprocal_normalizing_constant(gj.key(9), target, retained, w_ret)
+    score_ret = float(od.normal_logpdf(F32(0.4), F32(0), F32(1)) + od.normal_logpdf(F32(yv), F32(0.4), F32(1.0)))
+    # smc.py:432-465: K - 1 reweighted particles (each exactly log p(y) here) + the retained one at w - score + weight
+    last = w_ret - score_ret + exact_logz
+    total = math.log(((k - 1) * math.exp(exact_logz) + math.exp(last)) / k)
+    assert rz.item() == pytest.approx(score_ret - total, abs=1e-4)
+
+
+def test_marginal_of_a_generative_function(device):
+    """sp.py:208-252: random_weighted keeps the selected choices and weights by the projection on the rest;
+    estimate_logpdf is the importance weight of the given choices."""
+    gj = _gj()
+
+    @gj.gen
+    def model():
+        x = gj.normal(0.0, 2.0) @ "x"
+        gj.normal(x, 0.5) @ "y"
+
+    n = 4096
+    m = model.marginal(selection=gj.S["y"])
+    kb = gj.split(gj.key(1), n)
+    w, chm = m.random_weighted(kb)
+    assert "y" in chm and "x" not in chm and w.shape == (n,)
+    # the weight is the density of the kept choice y given the simulated x: a Normal(x, 0.5) log-density, so it
+    # is bounded above by -log(0.5) - 0.5 log(2 pi); the reference-compatible form projects on the complement
+    # (the prior density of the discarded x) instead
+    assert (w <= -math.log(0.5) - 0.5 * math.log(2 * math.pi) + 1e-5).all()
+    wc, _ = model.marginal(selection=gj.S["y"]).__class__(model, gj.S["y"], reference_compat=True).random_weighted(kb)
+    assert (wc <= -math.log(2.0) - 0.5 * math.log(2 * math.pi) + 1e-5).all() and not torch.equal(wc, w)
+    yv = chm["y"]
+    est = m.estimate_logpdf(gj.split(gj.key(2), n), gj.vmap(lambda v: gj.C["y"].set(v), in_axes=0)(yv))
+    assert est.shape == (n,) and torch.isfinite(est).all()
+    # importance weight of y given a fresh prior draw of x is log N(y; x', 0.5): on average exp(est) ~ p(y)
+    marg = torch.exp(est.double()).mean().item()
+    exact = torch.exp(gj.normal.logpdf(yv, 0.0, math.sqrt(4.25)).double()).mean().item()
+    assert marg == pytest.approx(exact, rel=0.1)
+    with pytest.raises(TypeError):
+        gj.Target(m, (), gj.C.n())
+    dec = gj.marginal(selection=gj.S["x"])(model)
+    assert isinstance(dec, gj.Marginal)
