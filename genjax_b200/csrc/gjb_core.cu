@@ -307,8 +307,7 @@ __global__ void __launch_bounds__(kThreads) mass_resample_kernel(const __grid_co
     tot += v;
     if (t < (int)blockIdx.x) pre += v;
   }
-  pre = block_sum_u64(pre, sm.red);
-  tot = block_sum_u64(tot, sm_b);
+  block_sum2_u64(pre, tot, sm.red, sm_b);
   const uint64_t S = tot;
   if (blockIdx.x == 0 && tid == 0) {
     if (R.lse_out) {

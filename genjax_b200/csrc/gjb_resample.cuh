@@ -152,6 +152,18 @@ __device__ __forceinline__ uint64_t block_sum_u64(uint64_t v, uint64_t* sm /*[kT
   return tot;
 }
 
+// block-wide sums of two uint64 at once (one barrier pair instead of two); results valid in every thread
+__device__ __forceinline__ void block_sum2_u64(uint64_t& a, uint64_t& b, uint64_t* sm_a, uint64_t* sm_b) {
+  a = warp_sum_u64(a);
+  b = warp_sum_u64(b);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { sm_a[threadIdx.x >> 5] = a; sm_b[threadIdx.x >> 5] = b; }
+  __syncthreads();
+  a = 0; b = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) { a += sm_a[w]; b += sm_b[w]; }
+}
+
 // the 8 consecutive log-weights of this thread (0-mass padding past n);
 // kCg: bypass L1 (data written earlier in the same persistent kernel)
 template <bool kCg>
@@ -271,12 +283,26 @@ __device__ __forceinline__ uint64_t resample_tile(const float* __restrict__ logw
     const int32_t c = min(max(offspring_cnt(C, S, scale, u0, nt), w_lo), w_hi);
     cnt[k + 1] = (i_base + k < n) ? c : cnt[k];  // padding particles own nothing
   }
-  if (tid == 0) { sm.range[0] = cnt[0]; sm.fill = 0; }
-  if (tid == kThreads - 1) sm.range[1] = cnt[kItems];
-  __syncthreads();
-  const int32_t r_lo = sm.range[0], r_hi = sm.range[1];
+  // the tile's offspring range follows from its CDF interval: no exchange needed
+  const int32_t r_lo = min(max(offspring_cnt(off, S, scale, u0, nt), w_lo), w_hi);
+  const int32_t r_hi = min(max(offspring_cnt(off + ttot, S, scale, u0, nt), w_lo), w_hi);
   const AncRoute anc{peers ? nullptr : ancestors - out_lo, peers};
   const int32_t a0 = (int32_t)(anc_base + tile_base) - 1;  // heads hold local index + 1
+  // Balanced tile (every particle has at most kDirect offspring): each thread writes the adjacent offspring
+  // ranges of its kItems particles straight from registers -- no shared-memory pass, one block-wide vote.
+  constexpr int kDirect = 12;
+  int heavy = 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) heavy |= (cnt[k + 1] - cnt[k]) > kDirect;
+  if (tid == 0) sm.fill = 0;
+  if (!__syncthreads_or(heavy)) {
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+      const int32_t a = a0 + 1 + tid * kItems + k;
+      for (int32_t j = cnt[k]; j < cnt[k + 1]; ++j) *anc.at(j) = a;
+    }
+    return ttot;
+  }
   for (int32_t wb = r_lo; wb < r_hi; wb += kWin) {
     const int32_t we = min(wb + kWin, r_hi);
     const int32_t len = we - wb;
