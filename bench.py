@@ -389,6 +389,9 @@ def run_ours(args):
     model_bytes = (8 * d + 12) * n  # read ancestor 4 + x_prev 4d, write x 4d + logw 4
     model_gbs = model_bytes / (model_ms * 1e-3) / 1e9
 
+    kernels = {"model_kernel": {"kernel_us": model_ms * 1e3, "algorithmic_bytes_per_launch": model_bytes,
+                                "achieved": model_gbs, "frac": model_gbs / peak,
+                                "what": "fused ancestor-gather + propose + logpdf + running max (gjb_model_launch)"}}
     if getattr(plan, "persistent", False):
         pf_ms = time_launches(lambda: plan.cm.lib.gjb_model_pf_run(C.byref(plan.pf_args), stream), 10, 2)
         achieved = step_bytes / (pf_ms * 1e-3) / 1e9
@@ -400,16 +403,36 @@ def run_ours(args):
             "algorithmic_bytes_per_particle_step": 8 * d + 24,
         }
     else:
+        dominant = "model_kernel"
+        if not global_resample and getattr(plan, "fuse_mass_resample", False):
+            # the other kernel of the step: integer mass + CDF scan + systematic ancestors in one cooperative launch;
+            # algorithmic bytes: log-weights read once (4) + ancestors written (4) per particle
+            core = cabi.core()
+            core.gjb_wmax_reset(plan.wmax2.data_ptr(), stream)
+            plan.cm.lib.gjb_model_launch(C.byref(plan.margs[0]), stream)  # a valid max + weights to resample
+            mr_ms = time_launches(lambda: core.gjb_mass_resample_systematic(C.byref(plan.rargs[0][1]), stream), 200, 20)
+            mr_bytes = 8 * n
+            mr_gbs = mr_bytes / (mr_ms * 1e-3) / 1e9
+            kernels["mass_resample_kernel"] = {
+                "kernel_us": mr_ms * 1e3, "algorithmic_bytes_per_launch": mr_bytes, "achieved": mr_gbs, "frac": mr_gbs / peak,
+                "what": "exact integer weight mass + grid barrier + CDF scan + systematic offspring ranges (gjb_mass_resample_systematic)"}
+            if mr_ms > model_ms:
+                dominant = "mass_resample_kernel"
+        k = kernels[dominant]
         roofline = {
-            "bound": "hbm", "kernel": "model_kernel (fused ancestor-gather + propose + logpdf + running max)",
-            "achieved": model_gbs, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": model_gbs / peak,
-            "traffic": None, "kernel_us": model_ms * 1e3, "algorithmic_bytes_per_launch": model_bytes,
+            "bound": "hbm", "kernel": f"{dominant}: {k['what']}",
+            "achieved": k["achieved"], "peak": peak, "peak_source": how, "unit": "GB/s", "frac": k["frac"],
+            "traffic": None, "kernel_us": k["kernel_us"], "algorithmic_bytes_per_launch": k["algorithmic_bytes_per_launch"],
+            "note": "dominant = the kernel with the larger measured launch duration of the step; both kernels are listed under "
+                    "'kernels'. At d=1 neither is HBM-bound (working set L2-resident, instruction / barrier-latency bound, see DESIGN.md 6)",
         }
+    roofline["kernels"] = kernels
     # DRAM traffic of the dominant kernel per launch from the committed `ncu --set full` capture (profiles/)
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             tr = json.load(f).get(f"d{d}", {})
-        roofline["traffic"] = tr.get("model_kernel_dram_bytes_per_launch")
+        key_ = "mass_resample_kernel_dram_bytes_per_launch" if "mass_resample" in roofline["kernel"] else "model_kernel_dram_bytes_per_launch"
+        roofline["traffic"] = tr.get(key_)
         roofline["traffic_source"] = tr.get("source")
     except Exception:
         pass
