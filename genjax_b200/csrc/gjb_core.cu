@@ -298,6 +298,7 @@ __global__ void __launch_bounds__(kThreads) mass_resample_kernel(const __grid_co
     for (int k = 0; k < kItems; ++k) { q[k] = det_exp_q(__fadd_rn(x[k], -M)); s += q[k]; }
     s = block_sum_u64(s, sm.red);
     if (tid == 0) __stcg(tm + blockIdx.x, (unsigned long long)s);
+    if (blockIdx.x == 0 && tid == 0 && R.heavy_ws) __stcg(R.heavy_ws, 0u);  // empty heavy list for phase C
   }
   cooperative_groups::this_grid().sync();
   // ---- phase C
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(kThreads) mass_resample_kernel(const __grid_co
       const int64_t j = anc_base + i;
       if (i < n && j >= out_lo && j < out_lo + out_n) R.ancestors[j - out_lo] = (int32_t)j;
     }
-    return;
+    return;  // uniform over the grid: nobody reaches the second barrier
   }
   uint32_t key0 = R.key0, key1 = R.key1;
   uint64_t key_index = R.key_index;
@@ -333,8 +334,31 @@ __global__ void __launch_bounds__(kThreads) mass_resample_kernel(const __grid_co
     key_index = (uint64_t)__ldg(R.key_dev + 2) | ((uint64_t)__ldg(R.key_dev + 3) << 32);
   }
   const double u0 = resample_u0(key0, key1, key_index);
+  // can any particle own a whole window?  the heaviest possible particle has mass 2^36 (weight == max), i.e. at most
+  // n_total * 2^36 / S offspring -- a grid-uniform test, so balanced steps never pay for the second barrier
+  const bool may_heavy = R.heavy_ws != nullptr && (double)n_total * 68719476736.0 >= (double)S * (double)kWin;
   resample_tile<false>(R.logw, n, tile_base, M, pre, S, n_total, u0, out_lo, out_n, anc_base, R.ancestors, sm, heads, nullptr,
-                       nullptr, q);
+                       nullptr, q, may_heavy ? R.heavy_ws : nullptr);
+  if (may_heavy) {
+    cooperative_groups::this_grid().sync();
+    const uint32_t cnt_h = min(__ldcg(R.heavy_ws), (uint32_t)GJB_HEAVY_CAP);
+    const int32_t* e = reinterpret_cast<const int32_t*>(R.heavy_ws) + 4;
+    int32_t* anc = R.ancestors - out_lo;
+    const int64_t gtid = (int64_t)blockIdx.x * kThreads + tid, gsz = (int64_t)gridDim.x * kThreads;
+    for (uint32_t h = 0; h < cnt_h; ++h) {
+      const int32_t lo = __ldcg(e + 3 * h), hi = __ldcg(e + 3 * h + 1), a = __ldcg(e + 3 * h + 2);
+      // 128-bit stores over the aligned body, scalars at the ragged ends
+      const int64_t body_lo = ((int64_t)lo + 3) & ~(int64_t)3, body_hi = (int64_t)hi & ~(int64_t)3;
+      if (body_lo < body_hi && ((reinterpret_cast<uintptr_t>(anc + body_lo) & 15) == 0)) {
+        const int4 v = make_int4(a, a, a, a);
+        for (int64_t j = body_lo + 4 * gtid; j < body_hi; j += 4 * gsz) *reinterpret_cast<int4*>(anc + j) = v;
+        if (gtid < body_lo - lo) anc[lo + gtid] = a;
+        if (gtid < hi - body_hi) anc[body_hi + gtid] = a;
+      } else {
+        for (int64_t j = lo + gtid; j < hi; j += gsz) anc[j] = a;
+      }
+    }
+  }
 }
 
 // ----------------------------------------------------------- multinomial

@@ -203,6 +203,7 @@ struct TileSmem {
   int32_t wred[kThreads / 32];
   int32_t range[2];
   int32_t fill;
+  int32_t fill_hi;
 };
 
 // cumulative offspring count of a particle whose inclusive CDF value is C (n_total < 2^31):
@@ -235,7 +236,8 @@ __device__ __forceinline__ uint64_t resample_tile(const float* __restrict__ logw
                                                   uint64_t off, uint64_t S, int64_t n_total, double u0, int64_t out_lo,
                                                   int64_t out_n, int64_t anc_base, int32_t* __restrict__ ancestors,
                                                   TileSmem& sm, int32_t* heads, const uint64_t* qin = nullptr,
-                                                  const gjb_peers* peers = nullptr, const uint64_t* qthread = nullptr) {
+                                                  const gjb_peers* peers = nullptr, const uint64_t* qthread = nullptr,
+                                                  uint32_t* heavy_ws = nullptr) {
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   uint64_t q[kItems];
@@ -312,11 +314,29 @@ __device__ __forceinline__ uint64_t resample_tile(const float* __restrict__ logw
     for (int j = tid * 4; j < per * kThreads; j += kThreads * 4) *reinterpret_cast<int4*>(heads + j) = make_int4(0, 0, 0, 0);
 #pragma unroll
     for (int k = 0; k < kItems; ++k)
-      if (cnt[k] <= wb && cnt[k + 1] >= we) sm.fill = tid * kItems + k + 1;
+      if (cnt[k] <= wb && cnt[k + 1] >= we) { sm.fill = tid * kItems + k + 1; sm.fill_hi = cnt[k + 1]; }
     __syncthreads();
     const int32_t fill = sm.fill;
-    if (fill) {  // degenerate weights: coalesced constant fill, no scan
+    if (fill) {  // degenerate weights: this window belongs to ONE particle -- constant fill, no scan
       const int32_t a = a0 + fill;
+      if (heavy_ws) {
+        // park the whole run of windows this particle owns; every CTA of the grid fills it after the barrier
+        const int32_t span_end = min(wb + ((sm.fill_hi - wb) / kWin) * kWin, r_hi);
+        __shared__ int gjb_heavy_slot;
+        if (tid == 0) gjb_heavy_slot = (int)atomicAdd(heavy_ws, 1u);
+        __syncthreads();
+        const int slot = gjb_heavy_slot;
+        if (slot < GJB_HEAVY_CAP) {
+          if (tid == 0) {
+            int32_t* e = reinterpret_cast<int32_t*>(heavy_ws) + 4 + 3 * slot;
+            e[0] = wb; e[1] = max(span_end, we); e[2] = a;
+            sm.fill = 0;
+          }
+          __syncthreads();
+          wb = max(span_end, we) - kWin;  // the loop increment lands on the first window not owned by this particle
+          continue;
+        }
+      }
       for (int32_t j = wb + tid; j < we; j += kThreads) *anc.at(j) = a;
       __syncthreads();
       if (tid == 0) sm.fill = 0;

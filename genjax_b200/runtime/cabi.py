@@ -16,6 +16,7 @@ from . import build
 GJB_MAX_SITES = 16
 GJB_MAX_ARGS = 16
 GJB_MAX_RETS = 8
+GJB_HEAVY_WS_WORDS = 4 + 3 * 1024
 
 SITE_SAMPLE = 1
 SITE_WEIGHT = 2
@@ -124,6 +125,7 @@ class ResampleArgs(C.Structure):
         ("ancestors", _p),
         ("lse_out", _p),
         ("wmax_next", _p),
+        ("heavy_ws", _p),
     ]
 
 
@@ -237,7 +239,7 @@ def core():
     if _core is None:
         path = build.build_core()
         _core = _bind(C.CDLL(str(path)), CORE_PROTOTYPES)
-        if _core.gjb_abi_version() != 7:
+        if _core.gjb_abi_version() != 8:
             raise GjbError("libgjb_core.so ABI mismatch")
     return _core
 

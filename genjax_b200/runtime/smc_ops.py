@@ -28,6 +28,7 @@ class WeightWorkspace:
         self.wmax = torch.empty(1, dtype=torch.int32, device=device)  # ordered-uint encoded float
         self.tile_mass = torch.empty(self.tiles, dtype=torch.int64, device=device)
         self.lse = torch.empty(3, dtype=torch.float64, device=device)
+        self.heavy = torch.zeros(cabi.GJB_HEAVY_WS_WORDS, dtype=torch.int32, device=device)
         self.reset_max()
 
     def reset_max(self):
@@ -89,6 +90,7 @@ class WeightWorkspace:
         R.ancestors = ancestors.data_ptr()
         R.lse_out = cabi.ptr(lse_out)
         R.wmax_next = cabi.ptr(wmax_next)
+        R.heavy_ws = self.heavy.data_ptr()
         return R
 
     def systematic(self, logw: torch.Tensor, key: PRNGKey | None, ancestors: torch.Tensor, **kw):

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GJB_ABI_VERSION 7
+#define GJB_ABI_VERSION 8
 
 #define GJB_E_ARG (-1)      /* null / misaligned pointer, negative size          */
 #define GJB_E_RANGE (-2)    /* size beyond what the kernel supports              */
@@ -97,7 +97,14 @@ typedef struct gjb_resample_args {
   int32_t* ancestors;         /* [out_n]                                          */
   double* lse_out;            /* nullable: {M, S, M + log S - 36 log 2 - log n_total} */
   uint32_t* wmax_next;        /* nullable: reset to -inf for the next step        */
+  uint32_t* heavy_ws;         /* nullable scratch, GJB_HEAVY_WS_WORDS uint32: gjb_mass_resample_systematic parks the
+                                 offspring ranges of particles that own whole 4096-slot windows here and, after a
+                                 second grid barrier, ALL CTAs fill them (degenerate weights no longer serialise on
+                                 the one CTA that owns the heavy particle)                                        */
 } gjb_resample_args;
+
+#define GJB_HEAVY_CAP 1024
+#define GJB_HEAVY_WS_WORDS (4 + 3 * GJB_HEAVY_CAP)
 
 int gjb_resample_systematic(const gjb_resample_args* a, void* stream);
 

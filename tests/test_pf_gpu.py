@@ -313,11 +313,21 @@ def test_multi_gpu_global_resampling_equals_single_gpu(device):
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
-def test_fused_mass_resample_equals_two_launches(device, use_graph):
+@pytest.mark.parametrize("obs_sd", [0.5, 0.0001])
+def test_fused_mass_resample_equals_two_launches(device, use_graph, obs_sd):
     """gjb_mass_resample_systematic (one cooperative launch, masses kept in registers across a grid barrier)
     == gjb_weight_mass + gjb_resample_systematic, bit for bit; also inside a captured CUDA graph."""
     gj, step, _ = _models()
     from genjax_b200.inference.pf import ParticleFilter
+
+    if obs_sd != 0.5:
+        # a razor-sharp likelihood: a handful of particles own tens of thousands of offspring each, so the fused
+        # kernel parks whole 4096-slot windows in the heavy list and the grid fills them after the second barrier
+        @gj.gen
+        def step(x_prev):  # noqa: F811
+            x = gj.normal(A_ * x_prev, Q_) @ "x"
+            gj.normal(C_ * x, obs_sd) @ "y"
+            return x
 
     n, T = 200_003, 6
     ys = osmc.simulate_lgssm(3, T, 1, A_, Q_, C_, R_)[:, 0]
@@ -334,3 +344,10 @@ def test_fused_mass_resample_equals_two_launches(device, use_graph):
         outs.append((res.ancestors.clone(), res.log_increments.clone(), res.state[0].clone()))
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+    if obs_sd != 0.5:
+        anc = outs[0][0][-1].cpu().numpy()
+        counts = np.bincount(outs[0][0].cpu().numpy().reshape(-1) + np.repeat(np.arange(T) * n, n))
+        assert counts.max() > 2 * 4096, counts.max()  # really degenerate: some parent owns whole 4096-slot windows
+        lw = res.history["log_weights"][-1].cpu().numpy()
+        _, k_res = osmc.pf_step_keys(orng.key(8), T - 1)
+        assert np.array_equal(anc, osmc.resample_systematic(lw, k_res))
