@@ -319,14 +319,9 @@ class GenerativeFunction:
         return Marginal(self, Selection.all() if selection is None else selection, algorithm)
 
     def partial_apply(self, *bound):
-        from .static import gen
-
-        outer = self
-
-        def inner(*rest):
-            return outer(*bound, *rest) @ "_partial"
-
-        raise NotImplementedError("partial_apply is not on the fused hot path yet")
+        """``gen_fn.partial_apply(*args)`` (generative_function.py ``partial_apply``): the same generative function
+        with its first arguments fixed; the choices keep their addresses."""
+        raise NotImplementedError(f"partial_apply is not available for {type(self).__name__}")
 
     def get_zero_trace(self, *args):
         raise NotImplementedError("zero traces belong to the jaxpr staging machinery (out of scope)")

@@ -334,6 +334,13 @@ class StaticGenerativeFunction(GenerativeFunction):
         bound.__name__ = self.__name__
         return bound
 
+    def partial_apply(self, *bound):
+        """Same model with its first arguments fixed (test_static_gen_fn.py:1116-1163): addresses unchanged."""
+        src = self.source
+        out = StaticGenerativeFunction(lambda *rest: src(*bound, *rest))
+        out.__name__ = f"{self.__name__}_partial"
+        return out
+
     # -- capture ---------------------------------------------------------
     def capture_inline(self, args):
         """Nested call inside another @gen body: inline the sites."""

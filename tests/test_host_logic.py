@@ -188,3 +188,48 @@ def test_new_model_compiles_for_sm100a():
     cm = m.prebuild([ArgSpec("particle", "f32", ()), ArgSpec("scalar", "f32", ())])
     assert cm.path.exists() and cm.info["mapping"] == "quad"
     assert [s["dist"] for s in cm.info["sites"]] == ["exponential", "uniform", "flip", "normal"]
+
+
+def test_partial_apply_keeps_addresses():
+    @gj.gen
+    def m(a, b):
+        x = gj.normal(a, b) @ "x"
+        return gj.normal(x, 1.0) @ "y"
+
+    p = m.partial_apply(0.5)
+    ir = cap.capture(p.source, "p", _specs(("scalar", ())), ("tuple", [("leaf", 0)]))
+    assert [s.addr for s in ir.sites] == [("x",), ("y",)]
+    with pytest.raises(NotImplementedError):
+        gj.normal.partial_apply(0.0)
+
+
+def test_target_and_choice_map_are_pytrees_for_capture():
+    """A custom proposal is a @gen function OF THE TARGET (custom_proposal.ipynb): Target / ChoiceMap arguments are
+    flattened into traced leaves and rebuilt symbolically inside the body."""
+    @gj.gen
+    def model():
+        x = gj.normal(0.0, 1.0) @ "x"
+        gj.normal(x, 1.0) @ "y"
+
+    target = gj.Target(model, (), C["y"].set(1.5))
+    leaves, tree = cap.flatten((target,))
+    assert leaves == [1.5] and tree[0] == "tuple" and tree[1][0][0] == "target"
+    rebuilt = cap.unflatten(tree, ["SYM"])[0]
+    assert isinstance(rebuilt, gj.Target) and rebuilt["y"] == "SYM" and rebuilt.p is model
+
+    @gj.gen
+    def proposal(t):
+        return gj.normal(t["y"] / 2.0, 0.7) @ "x"
+
+    ir = cap.capture(proposal.source, "proposal", [ArgSpec("scalar", "f32", ())], tree)
+    assert [s.addr for s in ir.sites] == [("x",)] and ir.sites[0].args[0].op == "div"
+
+
+def test_key_children_batch_and_scalar():
+    from genjax_b200.core.key import KeyBatch, key_children
+
+    kb = gj.split(gj.key(1), 8)
+    a, b = key_children(kb)
+    assert isinstance(a, KeyBatch) and a.n == b.n == 8 and a.words != b.words != kb.words and a.offset == kb.offset
+    ka, kb2 = key_children(gj.key(1))
+    assert ka == gj.split(gj.key(1))[0] and kb2 == gj.split(gj.key(1))[1]
