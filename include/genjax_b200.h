@@ -15,8 +15,11 @@
  *     validation failure (GJB_E_*);
  *   - particle arrays are row-major [n] or [n, d] float32 / int32;
  *   - RNG: Philox4x32-10, key = (key0, key1), counter =
- *     (idx_lo, idx_hi, chunk, site) with idx = idx_offset + local index, so
- *     results do not depend on how particles are sharded over GPUs.
+ *     (idx_lo, idx_hi, chunk, site) with idx = idx_offset + local index (the
+ *     GLOBAL particle / chain index), so results do not depend on how
+ *     particles are sharded over GPUs.  Scalar sites share one block between
+ *     the 4 particles of global quad idx >> 2 (slot idx & 3); vector sites
+ *     and rejection samplers use one stream per particle (csrc/gjb_rng.cuh).
  *
  * Two libraries export these symbols:
  *   libgjb_core.so          : everything in section 1 (model independent)
@@ -45,7 +48,9 @@ int gjb_abi_version(void);
 int64_t gjb_resample_workspace_bytes(int64_t n);
 
 /*
- * max_i logw_i  ->  *wmax (ordered-uint encoding, see gjb_wmax_decode).
+ * max_i logw_i  ->  *wmax, a float in ordered-uint encoding so that unsigned
+ * atomicMax orders it: b = bits(f); enc = (b >> 31) ? ~b : (b | 0x80000000);
+ * -inf encodes as 0x007FFFFF, which is what gjb_wmax_reset stores.
  * Replaces the max pass of jax.scipy.special.logsumexp at
  * inference/smc.py:97,107.  `wmax` must have been reset with gjb_wmax_reset.
  */
