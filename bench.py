@@ -203,19 +203,42 @@ def cpu_port_rate(n, T_sample, d, seed=314159, threads=None):
     return n * T_sample / dt, dt, logz, threads
 
 
+def cpu_c_port_rate(n, T_sample, d, seed=314159):
+    """particle-steps/s of the C / OpenMP restatement of the same oracle filter (oracle/c/pf_port.c; checked against the
+    NumPy oracle bit for bit in tests/test_oracle_c_port.py) on all host threads; None when gcc is unavailable."""
+    from genjax_b200.core.key import key as pkey, pf_key_table
+    from genjax_b200.workloads import LG_A, LG_C, LG_Q, LG_R
+    from oracle import cport
+
+    if cport.lib() is None:
+        return None
+    cport.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
+    ys = synth_obs(T_sample, d)
+    g = np.random.default_rng(1)
+    x0 = g.standard_normal(n if d == 1 else (n, d)).astype(np.float32)
+    tab = pf_key_table(pkey(seed), T_sample)
+    t0 = time.perf_counter()
+    out = cport.pf_lgssm(x0, ys, LG_A, LG_Q, LG_C, LG_R, tab)
+    dt = time.perf_counter() - t0
+    return n * T_sample / dt, dt, float(out["logz_inc"].sum()), cport.threads()
+
+
 def run_reference(args):
     """Reference arm: the CPU restatement of the path (oracle port; the real reference is not installable)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n, d = args.particles, args.dim
-    T_sample = 4
+    use_c = cpu_c_port_rate(min(n, 4096), 1, d) is not None
+    T_sample = args.T if use_c else 4  # the C port runs the whole T-step filter per timed step; NumPy a 4-step sample
+    port = cpu_c_port_rate if use_c else cpu_port_rate
+    impl_name = "C/OpenMP restatement of the oracle filter (oracle/c/pf_port.c)" if use_c else "NumPy float32 oracle port"
     for _ in range(min(args.warmup, 1)):
-        cpu_port_rate(n, 1, d)
+        port(n, 1, d)
     rates, times = [], []
     threads = os.cpu_count() or 1
     for _ in range(args.steps):
-        r, dt, _, threads = cpu_port_rate(n, T_sample, d)
+        r, dt, _, threads = port(n, T_sample, d)
         rates.append(r)
         times.append(dt)
     total = n * T_sample * args.steps
@@ -237,9 +260,9 @@ def run_reference(args):
         "config": {"workload": f"linear-Gaussian SSM bootstrap SMC, N={n} particles, d={d}", "T_full": args.T,
                    "sample": f"{T_sample} of {args.T} filter steps per timed step"},
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": threads, "kind": "port",
-                         "sample": f"{T_sample} filter steps x {n} particles per timed step, NumPy float32 oracle port, propose+weight "
-                                   f"pass on {threads} threads ({os.cpu_count()} cores visible), resampling serial; the reference "
-                                   "itself (GenJAX on jax[cpu]) is not installable in this image"},
+                         "sample": f"{T_sample} filter steps x {n} particles per timed step, {impl_name}, {threads} threads "
+                                   f"({os.cpu_count()} cores visible); the reference itself (GenJAX on jax[cpu]) is not installable "
+                                   "in this image"},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -475,11 +498,15 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu_baseline:
         T_s = 20 if d == 1 else 2
-        rate, dt, _, thr = cpu_port_rate(n, T_s, d)
+        c_res = cpu_c_port_rate(n, T, d)
+        if c_res is not None:
+            rate, dt, _, thr = c_res
+            what = f"all {T} filter steps x {n} particles in {dt:.1f} s, C/OpenMP restatement of the oracle filter (oracle/c/pf_port.c)"
+        else:
+            rate, dt, _, thr = cpu_port_rate(n, T_s, d)
+            what = f"{T_s} of {T} filter steps x {n} particles in {dt:.1f} s, NumPy float32 oracle port"
         cpu = {"value": rate, "unit": "particle-steps/s", "cores": thr, "kind": "port",
-               "sample": f"{T_s} of {T} filter steps x {n} particles in {dt:.1f} s, NumPy float32 oracle port, propose+weight pass "
-                         f"on {thr} threads ({os.cpu_count()} cores visible), resampling serial; GenJAX jax[cpu] itself is not "
-                         "installable here"}
+               "sample": f"{what}, {thr} threads ({os.cpu_count()} cores visible); GenJAX jax[cpu] itself is not installable here"}
 
     h2d = x0_host.numel() * 4 + ys_host.numel() * 4 + T * 8 * 4
     line = {
