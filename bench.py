@@ -496,7 +496,7 @@ def run_ours(args):
                                       "achieved": model_gbs, "frac": model_gbs / peak}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # the CPU arm is timed at N = 1 only
         T_s = 20 if d == 1 else 2
         c_res = cpu_c_port_rate(n, T, d)
         if c_res is not None:
