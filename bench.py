@@ -41,7 +41,7 @@ import numpy as np
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dim", type=int, default=1, help="state width d (1 = configs[1] shape 2a; 32 = HBM-bound shape 2b)")
@@ -70,59 +70,73 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clocks / throttle reasons sampled DURING the timed region: in-process NVML polling every ~2 ms (the timed
+    region of the default run is only tens of milliseconds), nvidia-smi as a fallback."""
 
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.lines: list[str] = []
+        self.sm: list[float] = []
+        self.mx = None
+        self.bits = 0
+        self.stop_flag = False
+        self.thread = None
+        self.how = None
+
+    def _nvml_loop(self):
+        import pynvml
+
+        try:
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.how = "nvml"
+            while not self.stop_flag:
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                try:
+                    self.bits |= int(reasons(h))
+                except Exception:
+                    pass
+                time.sleep(0.002)
+        except Exception:
+            self.how = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
-            )
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml  # noqa: F401
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            time.sleep(0.02)
+        except Exception:
+            self.thread = None
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        self.proc.terminate()
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if self.how == "nvml" and self.sm:
+            return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx,
+                    "reasons": sorted(n for b, n in self.NAMES.items() if self.bits & b), "samples": len(self.sm), "source": "nvml"}
+        return self._smi_once()
+
+    def _smi_once(self) -> dict:
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc.wait(timeout=2)
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+            parts = [p.strip() for p in out.split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(parts[0]), "sm_max_mhz": float(parts[1]),
+                    "reasons": [n for n, v in zip(names, parts[2:6]) if v.lower().startswith("active")], "samples": 1,
+                    "source": "nvidia-smi (one sample right after the timed region)"}
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 6:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, parts[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {
-            "sm_mhz": float(np.median(sm)) if sm else None,
-            "sm_max_mhz": float(max(mx)) if mx else None,
-            "reasons": sorted(reasons),
-            "samples": len(sm),
-        }
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
 
 
 def synth_obs(T, d, seed=0):
