@@ -6,6 +6,10 @@ the hot path: per-site sample/logpdf, the static-language GFI accumulation,
 ImportanceK / ChangeTarget, the bootstrap particle-filter step with
 resampling, and the MH / HMC chain transitions.
 
+``oracle/c/pf_port.c`` (loaded through ``oracle/cport.py``) restates the bootstrap filter in C / OpenMP,
+operation for operation, so that bench.py's CPU arm can use every host core; it is checked against the NumPy
+code bit for bit (tests/test_oracle_c_port.py).
+
 Rules (the judge checks these):
   * only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
     ``cpu_baseline`` / ``--impl reference`` legs may import this package;
