@@ -31,6 +31,7 @@ from .gen.distributions import (
     gamma,
     gmm_diag,
     half_normal,
+    mv_normal,
     mv_normal_diag,
     normal,
     register_primitive,

@@ -137,6 +137,64 @@ struct GmmDiag {
   }
 };
 
+// ------------------------------------------------------ mv_normal (full covariance)
+// tfd.MultivariateNormalFullCovariance(loc, covariance_matrix): L = chol(cov) once per thread per launch
+// (particle-invariant, lives in the Uni struct), then per particle a forward substitution
+//   z = L^-1 (x - loc),  log_prob = -0.5 |z|^2 - sum_k log L_kk - D/2 log 2pi,   sample = loc + L eps.
+// D <= 16 keeps this on FMA (SURVEY kernel K10); the factor is D*(D+1)/2 floats of per-thread state.
+struct MvNormal {
+  template <int D>
+  __device__ static __forceinline__ float cholesky(const float* __restrict__ cov, float* __restrict__ L) {
+    float logdet = 0.0f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        float s = cov[i * D + j];
+        for (int m = 0; m < j; ++m) s -= L[i * D + m] * L[j * D + m];
+        if (i == j) {
+          const float dgl = sqrtf(s);
+          L[i * D + i] = dgl;
+          logdet += logf(dgl);
+        } else {
+          L[i * D + j] = s / L[j * D + j];
+        }
+      }
+#pragma unroll
+      for (int j = i + 1; j < D; ++j) L[i * D + j] = 0.0f;
+    }
+    return logdet;  // sum_k log L_kk
+  }
+  template <int D>
+  __device__ static __forceinline__ void sample(const Lane& l, uint32_t site, const float* loc, const float* L, float* out) {
+    float eps[(D + 3) / 4 * 4];
+#pragma unroll
+    for (int c = 0; c < (D + 3) / 4; ++c) {
+      const float4 z = normal4(l, site, (uint32_t)c);
+      eps[4 * c] = z.x; eps[4 * c + 1] = z.y; eps[4 * c + 2] = z.z; eps[4 * c + 3] = z.w;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      float s = loc[i];
+      for (int m = 0; m <= i; ++m) s += L[i * D + m] * eps[m];
+      out[i] = s;
+    }
+  }
+  template <int D>
+  __device__ static __forceinline__ float logpdf(const float* v, const float* loc, const float* L, float logdet) {
+    float z[D];
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      float s = v[i] - loc[i];
+      for (int m = 0; m < i; ++m) s -= L[i * D + m] * z[m];
+      z[i] = s / L[i * D + i];
+      q += z[i] * z[i];
+    }
+    return -0.5f * q - logdet - (float)D * kHalfLog2Pi;
+  }
+};
+
 // -------------------------------------------------------------- gamma, beta
 // Marsaglia-Tsang; attempt t uses chunk chunk0+t: words (x,y) -> normal,
 // z -> acceptance uniform, w (attempt 0) -> boost uniform for a < 1.

@@ -342,6 +342,17 @@ class _Emitter:
             self.w(f"if ({fl} & GJB_SITE_SAMPLE) gjb::GmmDiag::sample<{K}, {D}>(rng, {j + 1}u, {a}, s{j}); else {{ for (int k = 0; k < {D}; ++k) s{j}[k] = in_s{j}[k]; }}")
             self.w(f"if {need} {{ const float lp = gjb::GmmDiag::logpdf<{K}, {D}>(s{j}, {a}); score += lp; if ({fl} & GJB_SITE_WEIGHT) weight += lp; }}")
             return
+        if d.name == "mv_normal":
+            loc, cov = s.args
+            D = s.value.shape[0]
+            # Cholesky factor of the shared covariance: particle-invariant, once per thread per launch
+            self.uni_decl.append(f"  float L{j}[{D * D}]; float ld{j};")
+            self.uni_init.append(f"  U.ld{j} = gjb::MvNormal::cholesky<{D}>({self.ref(cov)}, U.L{j});")
+            lc = self.ref(loc)
+            self.w(f"float s{j}[{D}];")
+            self.w(f"if ({fl} & GJB_SITE_SAMPLE) gjb::MvNormal::sample<{D}>(rng, {j + 1}u, {lc}, U.L{j}, s{j}); else {{ for (int k = 0; k < {D}; ++k) s{j}[k] = in_s{j}[k]; }}")
+            self.w(f"if {need} {{ const float lp = gjb::MvNormal::logpdf<{D}>(s{j}, {lc}, U.L{j}, U.ld{j}); score += lp; if ({fl} & GJB_SITE_WEIGHT) weight += lp; }}")
+            return
         if d.name != "mv_normal_diag":
             raise NotImplementedError(d.name)
         loc, scale = s.args

@@ -283,6 +283,35 @@ class _GmmDiag(Distribution):
         return M + E.unary("log", tot)
 
 
+class _MvNormal(Distribution):
+    """tfd.MultivariateNormalFullCovariance(loc, covariance_matrix) (tensorflow_probability/__init__.py:244).
+    ``covariance_matrix`` must be a shared [D, D] argument (D <= 16); its Cholesky factor is computed once per
+    thread per launch, each particle pays one forward substitution."""
+
+    name, cuda, n_args, vector = "mv_normal", "MvNormal", 2, True
+    rng_kind = "lane"
+
+    def value_type(self, cargs):
+        loc, cov = cargs
+        if not (cov.op == "arg" and cov.attr["kind"] == "shared" and cov.ndim == 2 and cov.shape[0] == cov.shape[1]):
+            raise TypeError("mv_normal needs the covariance as a shared [D, D] argument")
+        d = cov.shape[0]
+        if d > 16:
+            raise NotImplementedError("mv_normal on FMA handles D <= 16")
+        if loc.ndim == 1 and loc.shape[0] != d:
+            raise TypeError("mv_normal: loc and covariance disagree on D")
+        return F32, (d,)
+
+    def _canonical(self, args, kwargs):
+        if kwargs:
+            args = tuple(args) + tuple(kwargs[k] for k in ("loc", "covariance_matrix") if k in kwargs)
+        loc, cov = super()._canonical(args, {})
+        loc, cov = E.lift(loc), E.lift(cov)
+        if loc.ndim == 0 and cov.ndim == 2:
+            loc = loc + Expr("constvec", (), F32, (cov.shape[0],), tuple(0.0 for _ in range(cov.shape[0])))
+        return [loc, cov]
+
+
 normal = _Normal()
 uniform = _Uniform()
 exponential = _Exponential()
@@ -294,10 +323,11 @@ bernoulli = _Bernoulli()
 categorical = _Categorical()
 mv_normal_diag = _MvNormalDiag()
 gmm_diag = _GmmDiag()
+mv_normal = _MvNormal()
 
 REGISTRY: dict[str, Distribution] = {
     d.name: d
-    for d in (normal, uniform, exponential, half_normal, gamma, beta, flip, bernoulli, categorical, mv_normal_diag, gmm_diag)
+    for d in (normal, uniform, exponential, half_normal, gamma, beta, flip, bernoulli, categorical, mv_normal_diag, gmm_diag, mv_normal)
 }
 
 

@@ -132,6 +132,60 @@ def mv_normal_diag_logpdf(v, loc, scale_diag):
     return out
 
 
+def _cholesky_f32(cov):
+    """Cholesky factor in float32 with the device's operation order (csrc/gjb_dist.cuh MvNormal::cholesky)."""
+    cov = _f(cov)
+    d = cov.shape[0]
+    L = np.zeros((d, d), dtype=F32)
+    logdet = F32(0.0)
+    for i in range(d):
+        for j in range(i + 1):
+            s = cov[i, j]
+            for m in range(j):
+                s = F32(s - F32(L[i, m] * L[j, m]))
+            if i == j:
+                L[i, i] = np.sqrt(s).astype(F32)
+                logdet = F32(logdet + _log(L[i, i]))
+            else:
+                L[i, j] = F32(s / L[j, j])
+    return L, logdet
+
+
+def mv_normal_logpdf(v, loc, cov):
+    """tfd.MultivariateNormalFullCovariance._log_prob via the Cholesky factor:
+    -0.5 |L^-1 (x - loc)|^2 - sum log L_kk - d/2 log 2pi (forward substitution, float32)."""
+    L, logdet = _cholesky_f32(cov)
+    d = L.shape[0]
+    v = _f(v)
+    if v.ndim == 1:
+        v = v[None]
+    loc = np.broadcast_to(_f(loc), v.shape)
+    z = np.zeros(v.shape, dtype=F32)
+    q = np.zeros(v.shape[0], dtype=F32)
+    for i in range(d):
+        s = (v[:, i] - loc[:, i]).astype(F32)
+        for m in range(i):
+            s = (s - L[i, m] * z[:, m]).astype(F32)
+        z[:, i] = (s / L[i, i]).astype(F32)
+        q = (q + z[:, i] * z[:, i]).astype(F32)
+    return (F32(-0.5) * q - logdet - F32(d) * _HALF_LOG_2PI).astype(F32)
+
+
+def mv_normal_sample(words, idx, site, loc, cov):
+    """loc + L eps with eps_k from chunk k // 4 of the particle's own stream (like mv_normal_diag)."""
+    L, _ = _cholesky_f32(cov)
+    d = L.shape[0]
+    eps = rng.normal_vec(words, idx, site, d)
+    loc = np.broadcast_to(_f(loc), eps.shape)
+    out = np.empty_like(eps)
+    for i in range(d):
+        s = loc[:, i].astype(F32)
+        for m in range(i + 1):
+            s = (s + L[i, m] * eps[:, m]).astype(F32)
+        out[:, i] = s
+    return out
+
+
 def gamma_logpdf(v, concentration, rate):
     """tfd.Gamma._log_prob: xlogy(a-1, x) - rate*x - (lgamma(a) - a*log(rate))."""
     v, a, b = _f(v), _f(concentration), _f(rate)
@@ -289,5 +343,6 @@ DISTS = {
     "mv_normal_diag": (mv_normal_diag_sample, mv_normal_diag_logpdf),
     "half_normal": (half_normal_sample, half_normal_logpdf),
     "gamma": (gamma_sample, gamma_logpdf),
+    "mv_normal": (mv_normal_sample, mv_normal_logpdf),
     "beta": (beta_sample, beta_logpdf),
 }

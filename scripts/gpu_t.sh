@@ -1,2 +1,2 @@
 cd $GRAFT_REPO_ROOT
-timeout 300 python -m pytest tests/test_golden_fixtures.py -x -q -m gpu 2>&1 | tail -25
+timeout 200 python -m pytest tests/test_zz_mv_normal_gpu.py -x -q 2>&1 | tail -25
