@@ -233,3 +233,40 @@ def test_key_children_batch_and_scalar():
     assert isinstance(a, KeyBatch) and a.n == b.n == 8 and a.words != b.words != kb.words and a.offset == kb.offset
     ka, kb2 = key_children(gj.key(1))
     assert ka == gj.split(gj.key(1))[0] and kb2 == gj.split(gj.key(1))[1]
+
+
+def test_chain_kernels_are_generated_and_hmc_degrades_to_e_mode_without_a_gradient():
+    """MH / HMC kernels are generated per (model, latent set).  A model whose log-density has no device gradient
+    (lgamma of a latent) still gets its MH kernel; the HMC entry point then reports GJB_E_MODE instead of a wrong
+    answer.  Argument validation happens before any GPU work, so this runs on the CPU."""
+    from genjax_b200.gen.codegen_chain import ChainSpec
+    from genjax_b200.gen.static import compile_ir
+
+    @gj.gen
+    def ok_model():
+        x = gj.normal(0.0, 1.0) @ "x"
+        gj.normal(x, 0.5) @ "y"
+
+    ir = cap.capture(ok_model.source, "ok_model", [], ("tuple", []))
+    cm = compile_ir(ir, chain=ChainSpec((0,), (None,)))
+    assert cm.lib.gjb_model_mh_chain(None, None) == -1 and cm.lib.gjb_model_hmc_chain(None, None) == -1  # GJB_E_ARG
+
+    @gj.gen
+    def no_grad_model():
+        a = gj.exponential(1.0) @ "a"
+        gj.gamma(a + 1.0, 2.0) @ "g"  # log-density contains lgamma(a + 1): no digamma on the device
+
+    ir = cap.capture(no_grad_model.source, "no_grad_model", [], ("tuple", []))
+    cm = compile_ir(ir, chain=ChainSpec((0,), (None,)))
+    assert cm.lib.gjb_model_mh_chain(None, None) == -1   # MH kernel exists (argument check fires)
+    assert cm.lib.gjb_model_hmc_chain(None, None) == -3  # GJB_E_MODE: no gradient kernel for this model
+    # a chain over an integer-valued site is refused at generation time
+    @gj.gen
+    def discrete():
+        gj.flip(0.3) @ "b"
+
+    from genjax_b200.gen.autodiff import NotDifferentiable
+
+    ir = cap.capture(discrete.source, "discrete", [], ("tuple", []))
+    with pytest.raises(NotDifferentiable):
+        compile_ir(ir, chain=ChainSpec((0,), (None,)))
