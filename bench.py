@@ -15,10 +15,13 @@ over P=1,048,576 particles per GPU, i.e. 1.048e8 particle-steps.
           marginal likelihood read back D2H inside the timed region.
   roofline : the fused gather+propose+logpdf model kernel, algorithmic bytes per
           launch / average launch duration (CUDA events, back-to-back launches).
-  cpu_baseline : the NumPy oracle restatement (oracle/smc.py) timed on the host
-          cores on a bounded sample (the reference itself -- GenJAX on jax[cpu] --
-          is not installable in this image: no jax/tfp wheels, no network).
---impl reference times that same oracle port as the reference arm.
+  cpu_baseline : the C/OpenMP restatement of the oracle filter (oracle/c/pf_port.c;
+          NumPy oracle if it did not build) timed on the host cores on a bounded
+          sample (the reference itself -- GenJAX on jax[cpu] -- is not installable
+          in this image: no jax/tfp wheels, no network).
+--impl reference times that same port as the reference arm; if `import jax, genjax`
+ever succeeds (baseline/_ref populated) it times baseline/run_genjax_cpu.py instead
+(the same filter written against GenJAX's own API) and reports kind "reference".
 """
 
 from __future__ import annotations
@@ -54,7 +57,7 @@ def parse():
                          "global = one filter over N*particles with global systematic resampling every step "
                          "(peer-memory hand-offs, BASELINE configs[3] style)")
     ap.add_argument("--mode", default="graph", choices=["persistent", "graph"],
-                    help="persistent: one cooperative launch per filter; graph: 3 launches per step in a CUDA graph")
+                    help="persistent: one cooperative launch per filter; graph: 2 launches per step in a CUDA graph")
     return ap.parse_args()
 
 
@@ -237,12 +240,47 @@ def cpu_c_port_rate(n, T_sample, d, seed=314159):
     return n * T_sample / dt, dt, float(out["logz_inc"].sum()), cport.threads()
 
 
+def genjax_reference_rate(args):
+    """The real reference (GenJAX on jax[cpu]) through baseline/run_genjax_cpu.py, or None where it cannot be
+    imported -- which is the case in this image (no jax / tfp / genjax wheels, no network)."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(ref_dir) and ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    try:
+        import jax  # noqa: F401
+        import genjax  # noqa: F401
+    except Exception:
+        return None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import run_genjax_cpu
+
+        return run_genjax_cpu.measure(1, args.particles, args.T, args.dim, repeats=max(1, min(args.steps, 3)))
+    except Exception as e:  # an installed but broken reference must not take the arm down
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def run_reference(args):
     """Reference arm: the CPU restatement of the path (oracle port; the real reference is not installable)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n, d = args.particles, args.dim
+    real = genjax_reference_rate(args)
+    if real is not None and "value" in real:
+        line = {
+            "impl": "reference", "metric": "particle-steps/sec", "value": real["value"], "unit": "particle-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * real["seconds"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"linear-Gaussian SSM bootstrap SMC, N={n} particles, d={d}", "T_full": args.T},
+            "cpu_baseline": {"value": real["value"], "unit": "particle-steps/s", "cores": real["cores"], "kind": "reference",
+                             "sample": f"whole {args.T}-step filter, GenJAX {real['genjax']} on jax {real['jax']} [cpu], "
+                                       "baseline/run_genjax_cpu.py"},
+            "e2e": {"value": real["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line), flush=True)
+        return
     use_c = cpu_c_port_rate(min(n, 4096), 1, d) is not None
     T_sample = args.T if use_c else 4  # the C port runs the whole T-step filter per timed step; NumPy a 4-step sample
     port = cpu_c_port_rate if use_c else cpu_port_rate
