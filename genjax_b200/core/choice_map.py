@@ -1,21 +1,26 @@
-"""ChoiceMap / Selection algebra (host-side, static addresses).
+"""ChoiceMap / Selection algebra (host-side).
 
-API mirror of src/genjax/_src/core/generative/choice_map.py for the subset the
+API mirror of src/genjax/_src/core/generative/choice_map.py for the part the
 hot path uses: ``Static`` + ``Choice`` maps (``ChoiceMap:847``, ``Choice:1397``,
-``Static:1535``), the builder ``C[...]`` (``_ChoiceMapBuilder:752``) and the
-``Selection`` algebra (``Selection:124``: all / none / leaf / static / and / or
-/ complement).  In the reference these are pytrees whose leaves are traced
-arrays; here they are plain host objects whose leaves are torch tensors (or
-Python scalars) and they resolve, at capture time, to per-site flags
-{sampled, constrained, selected} for the fused kernels.
+``Static:1535``), vectorised leaves addressed through ``[:, "x"]`` / ``[i, "x"]``
+(``Indexed:1448`` with full slices and static integer indices), the builder
+``C[...]`` (``_ChoiceMapBuilder:752``) and the ``Selection`` algebra
+(``Selection:124``: all / none / leaf / static incl. the ``...`` wildcard / and
+/ or / complement, with the same constructor-time simplifications, so that
+``==`` between selections behaves as in the reference's tests,
+tests/core/test_choice_maps.py).  In the reference these are pytrees whose
+leaves are traced arrays; here they are plain host objects whose leaves are
+torch tensors (or Python scalars) and they resolve, at capture time, to per-site
+flags {sampled, constrained, selected} for the fused kernels.
 
-Dynamic structure (``Indexed``, ``Switch``, ``Or`` with traced flags, masks)
-is out of scope and raises ``NotImplementedError``.
+Dynamic structure (array-valued index addresses, ``Switch``, masks with traced
+flags) is out of scope and raises
+``NotImplementedError``.
 """
 
 from __future__ import annotations
 
-from typing import Any, Iterable
+from typing import Any, Callable, Iterable
 
 __all__ = [
     "ChoiceMap",
@@ -24,6 +29,8 @@ __all__ = [
     "Selection",
     "SelectionBuilder",
 ]
+
+_FULL = slice(None, None, None)
 
 
 class ChoiceMapNoValueAtAddress(Exception):
@@ -34,17 +41,43 @@ class ChoiceMapNoValueAtAddress(Exception):
         super().__init__(addr)
 
 
+def _is_index_array(a) -> bool:
+    return hasattr(a, "shape") and hasattr(a, "dtype") and not isinstance(a, (str, bytes))
+
+
 def _norm_addr(addr) -> tuple:
+    """Flatten nested address tuples into one tuple of components (str / int / slice / Ellipsis)."""
     if isinstance(addr, tuple):
         out = []
         for a in addr:
             out.extend(_norm_addr(a))
         return tuple(out)
-    if addr is Ellipsis or isinstance(addr, slice):
+    if addr is Ellipsis or isinstance(addr, (slice, str)):
         return (addr,)
-    if isinstance(addr, (str, int)):
+    if isinstance(addr, bool):
+        raise TypeError(f"unsupported address component {addr!r}")
+    if isinstance(addr, int):
         return (addr,)
+    if _is_index_array(addr):
+        if tuple(addr.shape) == ():
+            return (int(addr),)  # a concrete 0-d index is a static index here (nothing is traced on the host)
+        raise NotImplementedError("array-valued (dynamic) index addresses are out of scope")
     raise TypeError(f"unsupported address component {addr!r}")
+
+
+def _validate_dynamic(addr: tuple, allow_partial_slice: bool) -> None:
+    """Index components must be scalars first, then (for lookups only) one partial slice, then full slices
+    (choice_map.py:695-749)."""
+    dyn = [c for c in addr if isinstance(c, (slice, int))]
+    k = 0
+    while k < len(dyn) and isinstance(dyn[k], int):
+        k += 1
+    rest = dyn[k:]
+    if rest and allow_partial_slice and rest[0] != _FULL:
+        rest = rest[1:]
+    if not all(isinstance(s, slice) and s == _FULL for s in rest):
+        what = "an optional partial slice, and then only full slices" if allow_partial_slice else "full slices"
+        raise ValueError(f"Address must consist of scalar components, followed by {what}. Found: {dyn}")
 
 
 # ------------------------------------------------------------------ Selection
@@ -52,9 +85,11 @@ def _norm_addr(addr) -> tuple:
 
 class Selection:
     """Set of addresses.  ``sel[addr]`` / ``addr in sel`` test membership;
-    ``sel(addr)`` descends one level (choice_map.py:124-325)."""
+    ``sel(addr)`` descends (choice_map.py:124-325)."""
 
-    # kinds: all, none, static{name->Selection}, and, or, not
+    # kinds: all, none, leaf, static{component -> Selection} (component may be ``...``), and, or, not
+    __slots__ = ("kind", "payload")
+
     def __init__(self, kind: str, payload: Any = None):
         self.kind = kind
         self.payload = payload
@@ -74,60 +109,82 @@ class Selection:
 
     @staticmethod
     def at_addr(addr) -> "Selection":
-        sel = Selection.all()
-        for comp in reversed(_norm_addr(addr)):
-            if comp is Ellipsis or isinstance(comp, slice):
-                continue  # wildcard over an index axis: static models have none
-            sel = Selection("static", {comp: sel})
-        return sel
+        comps = _norm_addr(addr)
+        if comps == ():
+            return Selection.leaf()
+        return Selection.all().extend(*comps)
 
-    class _At:
-        def __getitem__(self, addr) -> "Selection":
-            return Selection.at_addr(addr)
-
-    at = _At()
-
-    # algebra ----------------------------------------------------------
+    # algebra (constructor-time simplifications of AndSel / OrSel / ComplementSel .build) -----------
     def __or__(self, other: "Selection") -> "Selection":
+        if self.kind == "all" or other.kind == "none":
+            return self
+        if other.kind == "all" or self.kind == "none":
+            return other
+        if self == other:
+            return self
         return Selection("or", (self, other))
 
     def __and__(self, other: "Selection") -> "Selection":
+        if self.kind == "all" or other.kind == "none":
+            return other
+        if other.kind == "all" or self.kind == "none":
+            return self
+        if self == other:
+            return self
         return Selection("and", (self, other))
 
     def __invert__(self) -> "Selection":
+        if self.kind == "all":
+            return Selection.none()
+        if self.kind == "none":
+            return Selection.all()
+        if self.kind == "not":
+            return self.payload
         return Selection("not", self)
 
     def complement(self) -> "Selection":
         return ~self
 
     def extend(self, *addr) -> "Selection":
+        """Nest under the given components; ``...`` matches any one component (choice_map.py:283-312)."""
         sel = self
         for comp in reversed(_norm_addr(addr)):
+            if isinstance(comp, slice):
+                continue  # an index axis is transparent to selections (Indexed.filter passes them through)
+            if sel.kind == "none":
+                return sel
             sel = Selection("static", {comp: sel})
         return sel
+
+    def filter(self, sample: "ChoiceMap") -> "ChoiceMap":
+        return sample.filter(self)
 
     # queries ----------------------------------------------------------
     def __call__(self, addr) -> "Selection":
         """Sub-selection under ``addr``."""
         sel = self
         for comp in _norm_addr(addr):
-            sel = sel._descend(comp)
+            sel = sel.get_subselection(comp)
         return sel
 
-    def _descend(self, comp) -> "Selection":
+    def get_subselection(self, comp) -> "Selection":
+        if comp is Ellipsis or isinstance(comp, slice):
+            raise TypeError("wildcards are only allowed when BUILDING a selection, not when querying one")
         k = self.kind
         if k in ("all", "none"):
             return self
         if k == "leaf":
             return Selection.none()
         if k == "static":
+            if Ellipsis in self.payload:
+                return self.payload[Ellipsis]
             return self.payload.get(comp, Selection.none())
         if k == "or":
-            return self.payload[0]._descend(comp) | self.payload[1]._descend(comp)
+            return self.payload[0].get_subselection(comp) | self.payload[1].get_subselection(comp)
         if k == "and":
-            return self.payload[0]._descend(comp) & self.payload[1]._descend(comp)
+            return self.payload[0].get_subselection(comp) & self.payload[1].get_subselection(comp)
         if k == "not":
-            return ~self.payload._descend(comp)
+            return ~self.payload.get_subselection(comp)
         raise AssertionError(k)
 
     def check(self) -> bool:
@@ -151,6 +208,15 @@ class Selection:
     def __contains__(self, addr) -> bool:
         return self(addr).check()
 
+    def __eq__(self, other) -> bool:
+        return isinstance(other, Selection) and self.kind == other.kind and self.payload == other.payload
+
+    def __ne__(self, other) -> bool:
+        return not self == other
+
+    def __hash__(self):
+        return hash(self.kind)
+
     def __repr__(self):
         if self.kind == "static":
             return "Selection{" + ", ".join(f"{k!r}: {v!r}" for k, v in self.payload.items()) + "}"
@@ -163,20 +229,65 @@ class Selection:
 
 
 class _SelectionBuilder:
+    """``S["x", "y"]``, ``S[..., "y"]``, ``S[()]``, ``S.all`` / ``S.none`` / ``S.leaf`` (choice_map.py:75-119)."""
+
+    @property
+    def all(self) -> Selection:
+        return Selection.all()
+
+    @property
+    def none(self) -> Selection:
+        return Selection.none()
+
+    @property
+    def leaf(self) -> Selection:
+        return Selection.leaf()
+
     def __getitem__(self, addr) -> Selection:
         return Selection.at_addr(addr)
 
 
 SelectionBuilder = _SelectionBuilder()
+Selection.at = SelectionBuilder
 
 
 # ------------------------------------------------------------------ ChoiceMap
 
 
+def _leaf_equal(a, b) -> bool:
+    if isinstance(a, ChoiceMap) or isinstance(b, ChoiceMap):
+        return isinstance(a, ChoiceMap) and isinstance(b, ChoiceMap) and a == b
+    ta, tb = hasattr(a, "shape"), hasattr(b, "shape")
+    if ta or tb:
+        try:
+            import numpy as np
+
+            xa = a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a)
+            xb = b.detach().cpu().numpy() if hasattr(b, "detach") else np.asarray(b)
+            return xa.shape == xb.shape and bool((xa == xb).all())
+        except Exception:
+            return False
+    try:
+        return bool(a == b)
+    except Exception:
+        return False
+
+
+def _index_leaf(v, idx):
+    """``v[idx]`` on a vectorised leaf (Choice.get_inner_map with an index component, choice_map.py:1437-1443)."""
+    if isinstance(v, ChoiceMap):
+        return v.get_submap(idx)
+    if hasattr(v, "value") and type(v).__name__ == "Batched":  # genjax_b200.gen.static.Batched marker
+        return type(v)(v.value[idx])
+    if hasattr(v, "__getitem__") and not isinstance(v, (str, bytes)):
+        return v[idx]
+    raise TypeError(f"leaf {v!r} has no index axis")
+
+
 class ChoiceMap:
-    """Immutable tree: either a leaf value (``Choice``) or a dict name -> ChoiceMap
-    (``Static``).  Construct with ``ChoiceMap.d / kw / choice / empty`` or the
-    builder ``C[...]``."""
+    """Immutable tree: either a leaf value (``Choice``) or a dict component -> ChoiceMap
+    (``Static``; integer components are static indices).  Construct with
+    ``ChoiceMap.d / kw / from_mapping / choice / empty`` or the builder ``C[...]``."""
 
     __slots__ = ("_value", "_children", "_has_value")
 
@@ -194,16 +305,23 @@ class ChoiceMap:
     def choice(v) -> "ChoiceMap":
         if isinstance(v, ChoiceMap):
             return v
+        if hasattr(v, "shape") and tuple(v.shape) == (0,):
+            return ChoiceMap()  # an empty array is an empty choice map (Choice.build, choice_map.py:1411-1413)
         return ChoiceMap(value=v, has_value=True)
 
     value = choice
 
     @staticmethod
-    def d(d: dict) -> "ChoiceMap":
+    def from_mapping(pairs: Iterable[tuple]) -> "ChoiceMap":
+        """Address/value pairs; dict values nest; later pairs fill in, earlier ones win (choice_map.py:1043-1073)."""
         out = ChoiceMap.empty()
-        for addr, v in d.items():
+        for addr, v in pairs:
             out = out | ChoiceMap.entry(v, *_norm_addr(addr))
         return out
+
+    @staticmethod
+    def d(d: dict) -> "ChoiceMap":
+        return ChoiceMap.from_mapping(d.items())
 
     @staticmethod
     def kw(**kwargs) -> "ChoiceMap":
@@ -217,17 +335,21 @@ class ChoiceMap:
         return chm.extend(*addr)
 
     @staticmethod
-    def builder():
-        return ChoiceMapBuilder
+    def switch(idx, chms) -> "ChoiceMap":
+        if isinstance(idx, int) and not isinstance(idx, bool):
+            return list(chms)[idx]
+        raise NotImplementedError("switch over a traced index is out of scope")
 
     # structure --------------------------------------------------------
     def extend(self, *addr) -> "ChoiceMap":
         chm = self
         for comp in reversed(_norm_addr(addr)):
-            if comp is Ellipsis or isinstance(comp, slice):
-                continue  # vectorised leading axis: leaves already carry it
-            if not isinstance(comp, str):
-                raise NotImplementedError("indexed (dynamic) choice-map addresses are out of scope")
+            if comp is Ellipsis:
+                raise TypeError("`...` is a Selection wildcard, not a choice-map address")
+            if isinstance(comp, slice):
+                if comp != _FULL and not chm.static_is_empty():
+                    raise ValueError(f"Partial slices not supported: {comp}")
+                continue  # full slice over a vectorised axis: the leaves already carry it (Indexed.build)
             if chm.static_is_empty():
                 return ChoiceMap.empty()
             chm = ChoiceMap(children={comp: chm})
@@ -242,12 +364,26 @@ class ChoiceMap:
     def has_value(self) -> bool:
         return self._has_value
 
+    def get_inner_map(self, comp) -> "ChoiceMap":
+        """One address component down (``get_inner_map`` of Choice / Static / Indexed in the reference)."""
+        if isinstance(comp, str):
+            return self._children.get(comp, _EMPTY)
+        if comp is Ellipsis:
+            raise TypeError("`...` is a Selection wildcard, not a choice-map address")
+        if isinstance(comp, slice):
+            return self if comp == _FULL else self.map_leaves(lambda v: _index_leaf(v, comp))
+        if isinstance(comp, int):
+            if any(isinstance(k, int) for k in self._children):  # static indices: C[0].set(...)
+                return self._children.get(comp, _EMPTY)
+            return self.map_leaves(lambda v: _index_leaf(v, comp))
+        raise TypeError(f"unsupported address component {comp!r}")
+
     def get_submap(self, *addr) -> "ChoiceMap":
+        comps = _norm_addr(addr)
+        _validate_dynamic(comps, allow_partial_slice=True)
         chm = self
-        for comp in _norm_addr(addr):
-            if comp is Ellipsis or isinstance(comp, slice):
-                continue
-            chm = chm._children.get(comp, _EMPTY)
+        for comp in comps:
+            chm = chm.get_inner_map(comp)
         return chm
 
     def __call__(self, *addr) -> "ChoiceMap":
@@ -262,7 +398,7 @@ class ChoiceMap:
     def __contains__(self, addr) -> bool:
         return self.get_submap(addr)._has_value
 
-    def keys(self) -> Iterable[str]:
+    def keys(self) -> Iterable:
         return self._children.keys()
 
     def leaves(self, prefix=()) -> Iterable[tuple[tuple, Any]]:
@@ -277,15 +413,15 @@ class ChoiceMap:
 
     # algebra ----------------------------------------------------------
     def merge(self, other: "ChoiceMap") -> "ChoiceMap":
-        """``self | other``: self wins where both have a value (choice_map.py:1227)."""
+        """``self | other``: self wins where both have a value (Or.build, choice_map.py:1799-1833)."""
         if other is None or other.static_is_empty():
             return self
         if self.static_is_empty():
             return other
-        if self._has_value:
+        if self._has_value and other._has_value:
             return self
-        if other._has_value:
-            return other
+        if self._has_value or other._has_value:
+            raise Exception(f"Choice and non-Choice in Or: {self}, {other}")
         children = dict(self._children)
         for k, c in other._children.items():
             children[k] = children[k].merge(c) if k in children else c
@@ -294,59 +430,81 @@ class ChoiceMap:
     def __or__(self, other):
         return self.merge(other)
 
+    __add__ = __or__
+
     def __xor__(self, other: "ChoiceMap") -> "ChoiceMap":
-        """Disjoint union (deprecated in the reference); raises on overlap."""
-        for addr, _ in other.leaves():
-            if addr in self or (addr == () and self._has_value):
-                raise Exception(f"The two choice maps have an overlapping address {addr!r}.")
+        """Deprecated alias of ``|`` in the reference (choice_map.py:1261-1267)."""
         return self.merge(other)
 
-    def filter(self, selection: Selection) -> "ChoiceMap":
-        """Keep the leaves whose address is in ``selection`` (choice_map.py:896)."""
+    def __and__(self, other: "ChoiceMap") -> "ChoiceMap":
+        """Addresses present in both, values from the right-hand side (choice_map.py:1272-1273)."""
+        return other.filter(self.get_selection())
+
+    def filter(self, selection) -> "ChoiceMap":
+        """Keep the leaves whose address is in ``selection`` (choice_map.py:896); a bool acts as a mask."""
+        if isinstance(selection, bool):
+            return self if selection else _EMPTY
+        if not isinstance(selection, Selection):
+            raise NotImplementedError("masked choice maps with traced flags are out of scope")
         if self._has_value:
             return self if selection.check() else _EMPTY
         children = {}
         for k, c in self._children.items():
-            f = c.filter(selection(k))
+            # a static integer index is transparent to selections, like the reference's Indexed layer
+            f = c.filter(selection if isinstance(k, int) else selection.get_subselection(k))
             if not f.static_is_empty():
                 children[k] = f
         return ChoiceMap(children=children)
 
     def get_selection(self) -> Selection:
+        """Selection of exactly the addresses holding a value (ChmSel, choice_map.py:624-660)."""
         if self._has_value:
-            return Selection.all()
-        if not self._children:
+            return Selection.leaf()
+        if self.static_is_empty():
             return Selection.none()
-        return Selection("static", {k: c.get_selection() for k, c in self._children.items()})
+        sel = Selection.none()
+        for k, c in self._children.items():
+            sub = c.get_selection()
+            sel = sel | (sub if isinstance(k, int) else sub.extend(k))
+        return sel
 
     def mask(self, flag):
-        if isinstance(flag, bool):
-            return self if flag else _EMPTY
-        raise NotImplementedError("masked choice maps with traced flags are out of scope")
+        return self.filter(flag) if isinstance(flag, bool) else self.filter(_not_a_flag(flag))
 
-    class _AtSetter:
-        def __init__(self, chm, addr):
-            self.chm = chm
-            self.addr = addr
+    def simplify(self) -> "ChoiceMap":
+        return self
 
-        def set(self, v) -> "ChoiceMap":
-            return ChoiceMap.entry(v, *self.addr) | self.chm
-
-    class _At:
-        def __init__(self, chm):
-            self.chm = chm
-
-        def __getitem__(self, addr):
-            return ChoiceMap._AtSetter(self.chm, _norm_addr(addr))
+    def invalid_subset(self, gen_fn, args) -> "ChoiceMap | None":
+        """Choices that ``gen_fn(*args)`` can never visit, or None (choice_map.py:1344-1376)."""
+        valid = Selection.none()
+        for addr in gen_fn.get_site_addresses(args):
+            valid = valid | Selection.leaf().extend(*addr)
+        extras = self.filter(~valid)
+        return None if extras.static_is_empty() else extras
 
     @property
-    def at(self):
-        return ChoiceMap._At(self)
+    def at(self) -> "_Builder":
+        return _Builder(self, ())
 
     def map_leaves(self, fn) -> "ChoiceMap":
         if self._has_value:
             return ChoiceMap.choice(fn(self._value))
         return ChoiceMap(children={k: c.map_leaves(fn) for k, c in self._children.items()})
+
+    def __eq__(self, other) -> bool:
+        if not isinstance(other, ChoiceMap):
+            return NotImplemented
+        if self._has_value or other._has_value:
+            return self._has_value and other._has_value and _leaf_equal(self._value, other._value)
+        mine = {k: c for k, c in self._children.items() if not c.static_is_empty()}
+        theirs = {k: c for k, c in other._children.items() if not c.static_is_empty()}
+        return mine.keys() == theirs.keys() and all(mine[k] == theirs[k] for k in mine)
+
+    def __ne__(self, other) -> bool:
+        r = self.__eq__(other)
+        return r if r is NotImplemented else not r
+
+    __hash__ = object.__hash__
 
     def __repr__(self):
         if self._has_value:
@@ -354,26 +512,48 @@ class ChoiceMap:
         return "ChoiceMap{" + ", ".join(f"{k!r}: {c!r}" for k, c in self._children.items()) + "}"
 
 
+def _not_a_flag(flag):
+    raise NotImplementedError(f"masked choice maps with traced flags are out of scope (got {type(flag).__name__})")
+
+
 _EMPTY = ChoiceMap()
 
 
 class _Builder:
-    """``C["x"].set(v)``, ``C["a", "b"].set(v)``, ``C.n()``, ``C.v(v)``, ``C.d({...})``, ``C.kw(...)``."""
+    """``C["x"].set(v)``, ``C["a", "b"].set(v)``, ``C[:, "x"].set(vec)``, ``C.n()``, ``C.v(v)``, ``C.d({...})``,
+    ``C.kw(...)``, ``C.from_mapping(...)``; ``chm.at[addr].set(v)`` / ``.update(fn)`` edit an existing map
+    (_ChoiceMapBuilder, choice_map.py:752-845)."""
 
-    def __init__(self, addr=()):
+    def __init__(self, base: ChoiceMap | None = None, addr=()):
+        self.base = base
         self.addr = addr
 
     def __getitem__(self, addr) -> "_Builder":
-        return _Builder(self.addr + _norm_addr(addr))
+        return _Builder(self.base, self.addr + _norm_addr(addr))
 
     def set(self, v) -> ChoiceMap:
-        return ChoiceMap.entry(v, *self.addr)
+        _validate_dynamic(self.addr, allow_partial_slice=False)
+        new = ChoiceMap.entry(v, *self.addr)
+        if self.base is None:
+            return new
+        return new | self.base  # the new entry wins over what the map held at that address (`chm + old`, :776)
+
+    def update(self, f: Callable) -> ChoiceMap:
+        """Replace what sits at the address by ``f(value)`` (or ``f(submap)`` if there is no value there)."""
+        if self.base is None:
+            return self.set(f(_EMPTY))
+        sub = self.base.get_submap(self.addr)
+        return self.set(f(sub.get_value() if sub.has_value() else sub))
 
     def n(self) -> ChoiceMap:
         return ChoiceMap.empty()
 
     def v(self, v) -> ChoiceMap:
-        return self.set(v)
+        # a ChoiceMap passed to .v is stored AS A VALUE (choice_map.py:813-817: "not advisable", but tested)
+        return self.set(ChoiceMap(value=v, has_value=True) if isinstance(v, ChoiceMap) else ChoiceMap.choice(v))
+
+    def from_mapping(self, mapping) -> ChoiceMap:
+        return self.set(ChoiceMap.from_mapping(mapping))
 
     def d(self, d: dict) -> ChoiceMap:
         return self.set(ChoiceMap.d(d))
@@ -381,5 +561,9 @@ class _Builder:
     def kw(self, **kwargs) -> ChoiceMap:
         return self.set(ChoiceMap.kw(**kwargs))
 
+    def switch(self, idx, chms) -> ChoiceMap:
+        return self.set(ChoiceMap.switch(idx, chms))
+
 
 ChoiceMapBuilder = _Builder()
+ChoiceMap.builder = ChoiceMapBuilder

@@ -357,6 +357,14 @@ class StaticGenerativeFunction(GenerativeFunction):
             self._cache[sig] = cm
         return cm
 
+    def get_site_addresses(self, args) -> list[tuple]:
+        """Addresses the body visits for these arguments, in program order -- the shape information the
+        reference takes from ``get_zero_trace(*args).get_choices()`` (choice_map.py:1372).  Host-only: the body is
+        captured symbolically, nothing is compiled or launched."""
+        bound = _BoundArgs(args if isinstance(args, tuple) else tuple(args), torch.device("cpu"))
+        ir = cap.capture(self.source, self.__name__, bound.specs, bound.tree)
+        return [s.addr for s in ir.sites]
+
     def prebuild(self, specs: list, tree=None, pf_obs: tuple | None = None) -> CompiledModel:
         """Capture + compile for an explicit argument signature (no GPU needed):
         ``specs`` is a list of ``ArgSpec``; used by ``__graft_entry__.build()``.
