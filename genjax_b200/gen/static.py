@@ -42,7 +42,7 @@ from .gfi import (
     Update,
 )
 
-__all__ = ["gen", "StaticGenerativeFunction", "StaticTrace", "vmap", "AddressReuse", "MissingAddress"]
+__all__ = ["gen", "StaticGenerativeFunction", "StaticTrace", "SubTrace", "vmap", "AddressReuse", "MissingAddress"]
 
 
 # --------------------------------------------------------------- batch specs
@@ -222,6 +222,7 @@ class StaticTrace(Trace):
         self.bcast = bcast  # site index -> bool (value shared by all particles)
         self.score = score  # [n]
         self.ret_leaves = ret_leaves
+        self._site_score_cache = None
 
     def _view(self, t, is_bcast=False):
         if t is None or not isinstance(t, torch.Tensor):
@@ -262,11 +263,22 @@ class StaticTrace(Trace):
         return chm
 
     def get_subtrace(self, *addr):
-        raise NotImplementedError("per-site subtraces are fused away; use get_choices()(addr) / site_scores()")
+        """``tr.get_subtrace("x")`` / ``tr.get_subtrace("f", "x")`` (generative_function.py:141-175,
+        static.py:118-127).  The sites are fused into one kernel, so a sub-trace is a VIEW: the value of the site
+        (or the choices under a nested call's prefix) plus its log-density from ``site_scores()``."""
+        a = cap_norm(addr)
+        sites = [s for s in self.cm.ir.sites if s.addr[: len(a)] == a]
+        if not a or not sites:
+            from ..core.choice_map import ChoiceMapNoValueAtAddress
+
+            raise ChoiceMapNoValueAtAddress(a[0] if len(a) == 1 else a)
+        return SubTrace(self, a, sites)
 
     def site_scores(self) -> dict:
-        """Per-site log-densities (recomputed by one assess-mode launch per site set)."""
-        return self.gen_fn._site_scores(self)
+        """Per-site log-densities ``{addr: [n]}`` (one weight-only launch per site, computed once per trace)."""
+        if self._site_score_cache is None:
+            self._site_score_cache = self.gen_fn._site_scores(self)
+        return self._site_score_cache
 
     def take(self, idx) -> "StaticTrace":
         """``tree_map(lambda v: v[idx])`` over the particle axis (smc.py:90-91)."""
@@ -287,6 +299,50 @@ class StaticTrace(Trace):
         args = _take_args(self.args, sel)
         return StaticTrace(self.gen_fn, self.cm, None, args, int(sel.numel()), out_batched, values,
                            self.score.index_select(0, sel), rets, dict(self.bcast))
+
+
+class SubTrace(Trace):
+    """View of one site (``DistributionTrace``, distribution.py:60-87) or of the sites under a nested call's
+    address prefix (the inlined callee's ``StaticTrace``) inside a fused ``StaticTrace``."""
+
+    def __init__(self, parent: StaticTrace, prefix: tuple, sites: list):
+        self.parent = parent
+        self.prefix = prefix
+        self.sites = sites
+        self.is_site = len(sites) == 1 and sites[0].addr == prefix
+
+    def get_gen_fn(self):
+        if self.is_site:
+            return self.sites[0].dist
+        raise NotImplementedError("the callee of an inlined nested call is not kept in the fused trace")
+
+    def get_args(self):
+        raise NotImplementedError("per-site arguments are fused away (they live in registers of the model kernel)")
+
+    def get_score(self):
+        scores = self.parent.site_scores()
+        tot = None
+        for s in self.sites:
+            tot = scores[s.addr] if tot is None else tot + scores[s.addr]
+        return tot if self.parent.batched else tot[0]
+
+    def get_choices(self) -> ChoiceMap:
+        return self.parent.get_choices().get_submap(*self.prefix)
+
+    get_sample = get_choices
+
+    def get_retval(self):
+        if self.is_site:
+            return self.parent._site_value(self.sites[0])
+        raise NotImplementedError("the return value of an inlined nested call is not kept in the fused trace")
+
+    get_value = get_retval
+
+    def get_subtrace(self, *addr):
+        return self.parent.get_subtrace(*self.prefix, *addr)
+
+    def project(self, key, selection: Selection):
+        return self.parent.project(key, selection.extend(*self.prefix))
 
 
 def _unmark(tree):
