@@ -52,6 +52,7 @@ from .gen.gfi import (
     Update,
 )
 from .gen.static import Batched, StaticGenerativeFunction, StaticTrace, gen, vmap
+from .gen.scan import Scan, ScanTrace, accumulate, iterate, iterate_final, reduce, scan
 from .inference.sp import Algorithm, Marginal, SampleDistribution, Target, marginal
 from . import inference
 

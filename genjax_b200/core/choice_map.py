@@ -278,7 +278,7 @@ def _index_leaf(v, idx):
     if isinstance(v, ChoiceMap):
         return v.get_submap(idx)
     if hasattr(v, "value") and type(v).__name__ == "Batched":  # genjax_b200.gen.static.Batched marker
-        return type(v)(v.value[idx])
+        return type(v)(v.value[:, idx])  # the particle axis is invisible to addresses, as under jax.vmap
     if hasattr(v, "__getitem__") and not isinstance(v, (str, bytes)):
         return v[idx]
     raise TypeError(f"leaf {v!r} has no index axis")
@@ -373,9 +373,14 @@ class ChoiceMap:
         if isinstance(comp, slice):
             return self if comp == _FULL else self.map_leaves(lambda v: _index_leaf(v, comp))
         if isinstance(comp, int):
-            if any(isinstance(k, int) for k in self._children):  # static indices: C[0].set(...)
-                return self._children.get(comp, _EMPTY)
-            return self.map_leaves(lambda v: _index_leaf(v, comp))
+            # vectorised leaves are indexed; entries stored under this static index (C[comp, ...].set) win over them
+            if self._has_value:
+                return self.map_leaves(lambda v: _index_leaf(v, comp))
+            rest = ChoiceMap(children={k: c for k, c in self._children.items() if not isinstance(k, int)})
+            out = rest.map_leaves(lambda v: _index_leaf(v, comp))
+            if comp in self._children:
+                out = _prefer(self._children[comp], out)
+            return out
         raise TypeError(f"unsupported address component {comp!r}")
 
     def get_submap(self, *addr) -> "ChoiceMap":
@@ -510,6 +515,20 @@ class ChoiceMap:
         if self._has_value:
             return f"Choice({self._value!r})"
         return "ChoiceMap{" + ", ".join(f"{k!r}: {c!r}" for k, c in self._children.items()) + "}"
+
+
+def _prefer(first: ChoiceMap, second: ChoiceMap) -> ChoiceMap:
+    """``first | second`` where ``first`` also wins structurally (a value over a subtree and vice versa)."""
+    if second.static_is_empty():
+        return first
+    if first.static_is_empty():
+        return second
+    if first._has_value or second._has_value:
+        return first
+    children = dict(second._children)
+    for k, c in first._children.items():
+        children[k] = _prefer(c, children[k]) if k in children else c
+    return ChoiceMap(children=children)
 
 
 def _not_a_flag(flag):

@@ -132,6 +132,18 @@ def key_children(k, num: int = 2) -> list:
     return list(split(k, num))
 
 
+def fold_in_lanes(k, data: int):
+    """``fold_in`` applied lane-wise -- ``jax.vmap(lambda key: jax.random.fold_in(key, data))(keys)``: the words
+    are hashed with ``data`` and every lane keeps its index, for a ``KeyBatch`` and for a single lane alike, so a
+    batched call and a scalar call on lane i of the batch stay in step (the chained key of ``Scan``, scan.py:213)."""
+    w = threefry2x32(k.words[0], k.words[1], 0x666F6C64, int(data) & _M32)
+    if isinstance(k, KeyBatch):
+        return KeyBatch(w, k.n, k.offset)
+    if isinstance(k, PRNGKey):
+        return PRNGKey(w, k.index)
+    raise TypeError(f"expected a PRNGKey or KeyBatch, got {type(k).__name__}")
+
+
 def lanes_of(k) -> tuple[tuple[int, int], int, int]:
     """(words, first lane, n lanes) of a PRNGKey (1 lane) or KeyBatch."""
     if isinstance(k, KeyBatch):

@@ -236,3 +236,116 @@ def regenerate(model, key, trace: OTrace, selected, args=None):
     args = trace.args if args is None else args
     rv = model(h, *args)
     return OTrace(model, args, rv, h.choices, h.scores, h.n), h.weight, h.discard
+
+
+# --------------------------------------------------------------------------
+# Scan combinator (src/genjax/_src/generative_functions/combinators/scan.py)
+# --------------------------------------------------------------------------
+#
+# A scanned kernel is an oracle model ``kernel(h, carry, x) -> (carry, y)``.  The key chain is the reference's
+# (``key_t = fold_in(key_{t-1}, t)``, scan.py:213, 268), applied lane-wise (rng.fold_in_lanes); scores and weights
+# are summed over the steps in step order (``jnp.sum(scores)``, :236, 296); constraints are addressed per step
+# (``constraint.get_submap(idx)``, :270): here ``chm_at(t)`` returns the step's ``{addr: values}`` dict.
+
+
+def _x_at(xs, t):
+    if xs is None:
+        return None
+    if isinstance(xs, (tuple, list)):
+        return type(xs)(_x_at(x, t) for x in xs)
+    if isinstance(xs, dict):
+        return {k: _x_at(v, t) for k, v in xs.items()}
+    return np.asarray(xs)[t]
+
+
+def _scan_len(xs, length):
+    if xs is None:
+        return int(length)
+    leaves = []
+
+    def go(x):
+        if isinstance(x, (tuple, list)):
+            for y in x:
+                go(y)
+        elif isinstance(x, dict):
+            for y in x.values():
+                go(y)
+        elif x is not None:
+            leaves.append(np.asarray(x).shape[0])
+
+    go(xs)
+    assert len(set(leaves)) == 1 and (length is None or leaves[0] == length)
+    return leaves[0]
+
+
+def scan_simulate(kernel, key, carry, xs, length=None):
+    """scan.py:199-238 -> (per-step traces, carry_out, [y_t], score)."""
+    T = _scan_len(xs, length)
+    traces, ys, score, k = [], [], None, key
+    for t in range(T):
+        k = rng.fold_in_lanes(k, t)
+        tr = simulate(kernel, k, (carry, _x_at(xs, t)))
+        carry, y = tr.get_retval()
+        traces.append(tr)
+        ys.append(y)
+        score = tr.get_score() if score is None else (score + tr.get_score()).astype(F32)
+    return traces, carry, ys, score
+
+
+def scan_generate(kernel, key, chm_at, carry, xs, length=None):
+    """scan.py:240-297 -> (per-step traces, carry_out, [y_t], score, weight)."""
+    T = _scan_len(xs, length)
+    traces, ys, score, weight, k = [], [], None, None, key
+    for t in range(T):
+        k = rng.fold_in_lanes(k, t)
+        tr, w = generate(kernel, k, chm_at(t), (carry, _x_at(xs, t)))
+        carry, y = tr.get_retval()
+        traces.append(tr)
+        ys.append(y)
+        score = tr.get_score() if score is None else (score + tr.get_score()).astype(F32)
+        weight = w if weight is None else (weight + w).astype(F32)
+    return traces, carry, ys, score, weight
+
+
+def scan_assess(kernel, chm_at, carry, xs, length=None, n=1):
+    """scan.py:634-660 -> (score, carry_out, [y_t])."""
+    T = _scan_len(xs, length)
+    ys, score = [], None
+    for t in range(T):
+        s, (carry, y) = assess(kernel, chm_at(t), (carry, _x_at(xs, t)), n=n)
+        ys.append(y)
+        score = s if score is None else (score + s).astype(F32)
+    return score, carry, ys
+
+
+def scan_update(kernel, key, traces, chm_at, carry, xs, length=None):
+    """scan.py:509-602: every step is re-visited with ``Update(constraint(t))`` and the new carry
+    -> (per-step traces, carry_out, [y_t], score, weight, {t: discard})."""
+    T = _scan_len(xs, length)
+    new, ys, score, weight, k, discard = [], [], None, None, key, {}
+    for t in range(T):
+        k = rng.fold_in_lanes(k, t)
+        tr, w, d = update(kernel, k, traces[t], chm_at(t), (carry, _x_at(xs, t)))
+        carry, y = tr.get_retval()
+        new.append(tr)
+        ys.append(y)
+        score = tr.get_score() if score is None else (score + tr.get_score()).astype(F32)
+        weight = w if weight is None else (weight + w).astype(F32)
+        if d:
+            discard[t] = d
+    return new, carry, ys, score, weight, discard
+
+
+def scan_regenerate(kernel, key, traces, selected, carry, xs, length=None):
+    """scan.py:417-507: ``Regenerate(selection)`` at every step."""
+    T = _scan_len(xs, length)
+    new, ys, score, weight, k = [], [], None, None, key
+    for t in range(T):
+        k = rng.fold_in_lanes(k, t)
+        tr, w, _ = regenerate(kernel, k, traces[t], selected, (carry, _x_at(xs, t)))
+        carry, y = tr.get_retval()
+        new.append(tr)
+        ys.append(y)
+        score = tr.get_score() if score is None else (score + tr.get_score()).astype(F32)
+        weight = w if weight is None else (weight + w).astype(F32)
+    return new, carry, ys, score, weight

@@ -186,6 +186,17 @@ def split(k: Key, n: int = 2) -> KeyBatch:
     return KeyBatch((int(out[0]), int(out[1])), n, 0)
 
 
+def fold_in_lanes(k, data: int):
+    """``fold_in`` applied lane-wise (``jax.vmap(lambda key: fold_in(key, data))``): the words are hashed with
+    ``data``, every lane keeps its index (mirrors genjax_b200/core/key.py ``fold_in_lanes``; the chained key of the
+    Scan combinator, scan.py:213, 268)."""
+    out = threefry2x32(np.array(k.words, dtype=U32), np.array([0x666F6C64, int(data) & _M32], dtype=U32))
+    w = (int(out[0]), int(out[1]))
+    if isinstance(k, KeyBatch):
+        return KeyBatch(w, k.n, k.offset)
+    return Key(w, k.index)
+
+
 def lanes(k) -> tuple[tuple[int, int], np.ndarray]:
     """(words, uint64 lane indices) for a Key (1 lane) or KeyBatch (n lanes)."""
     if isinstance(k, KeyBatch):

@@ -1,0 +1,348 @@
+"""TEST INFRASTRUCTURE ONLY -- a CPU emulation of the per-model C-ABI entry point ``gjb_model_launch``.
+
+Purpose: exercise the HOST side (argument binding, per-site flags, pointer tables, choice-map / trace plumbing, the
+``Scan`` combinator, ``get_subtrace`` ...) in the CPU suite, where no CUDA device exists.  The emulator reads the very
+``gjb_model_args`` structure the host fills (through the raw pointers, like the kernel does), interprets the captured
+model IR with the oracle's samplers / log-densities (oracle/dists.py, oracle/rng.py) and writes the outputs back
+through the pointers.
+
+What a green run proves: the host code fills the ABI consistently with the documented contract
+(include/genjax_b200.h).  What it does NOT prove: anything about the CUDA kernels -- those are only ever checked on a
+real B200 by the ``-m gpu`` tests.  Nothing under genjax_b200/ imports this file; it is installed by monkeypatching
+inside tests (``install(monkeypatch)``), and the product keeps failing loudly without CUDA.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import json
+
+import numpy as np
+import torch
+
+from oracle import dists as od
+
+F32, I32 = np.float32, np.int32
+
+_UN = {
+    "neg": np.negative, "exp": np.exp, "log": np.log, "sqrt": np.sqrt, "abs": np.abs, "tanh": np.tanh,
+    "sigmoid": lambda x: F32(1) / (F32(1) + np.exp(-x)), "log1p": np.log1p, "expm1": np.expm1, "square": np.square,
+    "floor": np.floor, "sin": np.sin, "cos": np.cos, "softplus": lambda x: np.logaddexp(F32(0), x),
+    "reciprocal": lambda x: F32(1) / x, "logical_not": lambda x: (x == 0).astype(I32),
+}
+_BIN = {
+    "add": np.add, "sub": np.subtract, "mul": np.multiply, "div": np.divide, "pow": np.power, "min": np.minimum,
+    "max": np.maximum, "lt": np.less, "le": np.less_equal, "gt": np.greater, "ge": np.greater_equal,
+    "eq": np.equal, "ne": np.not_equal, "and": lambda a, b: (a != 0) & (b != 0), "or": lambda a, b: (a != 0) | (b != 0),
+}
+
+
+def _typed(v, dtype):
+    return np.asarray(v).astype(F32 if dtype == "f32" else I32)
+
+
+def evaluate(e, env, cache):
+    """Vectorised float32 / int32 interpreter of the captured DAG; values carry a leading particle axis or broadcast."""
+    if e._id in cache:
+        return cache[e._id]
+    ins = [evaluate(i, env, cache) for i in e.ins]
+    op = e.op
+    if op == "const":
+        v = F32(e.attr) if e.dtype == "f32" else I32(e.attr)
+    elif op == "constvec":
+        v = _typed(e.attr, e.dtype)
+    elif op == "site":
+        v = env[("site", e.attr)]
+    elif op == "arg":
+        v = env[("arg", e.attr["index"])]
+    elif op in ("row", "gather1"):
+        v = ins[0][np.asarray(ins[1]).astype(np.int64)]
+    elif op == "elem":
+        v = ins[0][..., int(e.attr)]
+    elif op == "sum":
+        v = np.sum(ins[0], axis=-1, dtype=F32)
+    elif op == "cast":
+        v = _typed(ins[0], e.dtype)
+    elif op == "where":
+        v = np.where(np.asarray(ins[0]) != 0, ins[1], ins[2])
+    elif op in _UN:
+        with np.errstate(all="ignore"):
+            v = _UN[op](ins[0])
+    elif op in _BIN:
+        with np.errstate(all="ignore"):
+            v = _BIN[op](ins[0], ins[1])
+        if op in ("lt", "le", "gt", "ge", "eq", "ne", "and", "or"):
+            v = np.asarray(v).astype(I32)
+    else:
+        raise NotImplementedError(f"emulator: op {op}")
+    if isinstance(v, np.ndarray) and v.dtype == np.float64:
+        v = v.astype(F32)
+    cache[e._id] = v
+    return v
+
+
+def _view(ptr, count, dtype):
+    if not ptr or count == 0:
+        return None
+    ct = C.c_float if dtype == F32 else C.c_int32
+    return np.ctypeslib.as_array((ct * count).from_address(ptr))
+
+
+def _prod(shape):
+    out = 1
+    for d in shape:
+        out *= d
+    return out
+
+
+class EmulatedModelLib:
+    """Stands in for ``ctypes.CDLL(model_<digest>.so)``: ``gjb_model_info`` and ``gjb_model_launch`` only."""
+
+    def __init__(self, ir):
+        self.ir = ir
+        self.launches = 0
+
+    def gjb_model_info(self):
+        sites = [{"addr": list(s.addr), "dist": s.dist.name} for s in self.ir.sites]
+        return json.dumps({"name": self.ir.name, "sites": sites, "emulated": True}).encode()
+
+    def gjb_model_launch(self, a_ref, stream):
+        A = a_ref._obj
+        ir = self.ir
+        n = int(A.n)
+        if n < 0:
+            return -1
+        if n == 0:
+            return 0
+        self.launches += 1
+        if A.peer_args or A.link or A.key_dev or A.wmax:
+            raise NotImplementedError("emulator: multi-GPU links / device keys / running max are GPU-only paths")
+        words = (int(A.key0), int(A.key1))
+        idx = np.uint64(A.idx_offset) + np.arange(n, dtype=np.uint64)
+        gather = _view(A.gather, n, I32)
+        env = {}
+        for i, spec in enumerate(ir.args):
+            dt = F32 if spec.dtype == "f32" else I32
+            if spec.kind == "scalar":
+                env[("arg", i)] = dt(A.scalars[i])
+            elif spec.kind == "shared":
+                env[("arg", i)] = _view(A.args[i], max(_prod(spec.shape), 1), dt).reshape(spec.shape).copy()
+            else:
+                row = _prod(spec.shape)
+                if gather is not None:  # rows of a LARGER source array, picked by ancestor index
+                    rows = int(gather.max()) + 1
+                    src = _view(A.args[i], rows * row, dt).reshape((rows,) + tuple(spec.shape))
+                    env[("arg", i)] = src[gather].copy()
+                else:
+                    env[("arg", i)] = _view(A.args[i], n * row, dt).reshape((n,) + tuple(spec.shape)).copy()
+        cache = {}
+        score = np.zeros(n, dtype=F32)
+        weight = np.zeros(n, dtype=F32)
+        need_score = bool(A.score_out)
+        for s in ir.sites:
+            j = s.index
+            fl = int(A.site_flags[j])
+            ev = tuple(s.value.shape)
+            dt = F32 if s.value.dtype == "f32" else I32
+            args = [evaluate(e, env, cache) for e in s.args]
+            sample, logpdf = od.DISTS[s.dist.name]
+            if fl & 1:
+                v = np.asarray(sample(words, idx, j + 1, *args))
+                v = np.broadcast_to(v.astype(dt), (n,) + ev).copy()
+            else:
+                if not A.site_in[j]:
+                    return -1
+                if fl & 4:
+                    v = _view(A.site_in[j], max(_prod(ev), 1), dt).reshape(ev).copy()
+                    v = np.broadcast_to(v, (n,) + ev)
+                else:
+                    v = _view(A.site_in[j], n * _prod(ev), dt).reshape((n,) + ev).copy()
+            if need_score or (fl & 2):
+                vv = v.astype(bool) if getattr(s.dist, "bool_valued", False) else v
+                lp = np.broadcast_to(np.asarray(logpdf(vv, *args), dtype=F32), (n,))
+                score = (score + lp).astype(F32)
+                if fl & 2:
+                    weight = (weight + lp).astype(F32)
+            env[("site", j)] = v
+            out = _view(A.site_out[j], n * _prod(ev), dt)
+            if out is not None:
+                out[:] = np.ascontiguousarray(v).reshape(-1)
+        for k, r in enumerate(ir.ret_leaves):
+            if not A.ret_out[k]:
+                continue
+            val = evaluate(r, env, cache)
+            dt = F32 if r.dtype == "f32" else I32
+            full = np.broadcast_to(np.asarray(val).astype(dt), (n,) + tuple(r.shape))
+            _view(A.ret_out[k], n * _prod(r.shape), dt)[:] = np.ascontiguousarray(full).reshape(-1)
+        if A.score_out:
+            _view(A.score_out, n, F32)[:] = score
+        if A.weight_out:
+            t = weight
+            if A.weight_in:
+                t = (_view(A.weight_in, n, F32) + t).astype(F32)
+            if A.score_in:
+                t = (t - _view(A.score_in, n, F32)).astype(F32)
+            _view(A.weight_out, n, F32)[:] = t
+        return 0
+
+
+# ------------------------------------------------------------------ libgjb_core.so (single-device entry points)
+
+_TILE = 2048
+
+
+def _enc(f) -> int:
+    u = int(np.asarray(f, dtype=F32).view(np.uint32))
+    return (u ^ 0xFFFFFFFF) & 0xFFFFFFFF if u >> 31 else u ^ 0x80000000
+
+
+def _dec(u: int):
+    u = int(u)
+    b = u ^ 0x80000000 if u >> 31 else (u ^ 0xFFFFFFFF) & 0xFFFFFFFF
+    return np.asarray(b, dtype=np.uint32).view(F32)[()]
+
+
+def _arr(ptr, count, ct, dtype):
+    if not ptr or count == 0:
+        return None
+    return np.ctypeslib.as_array((ct * count).from_address(ptr)).view(dtype)
+
+
+class EmulatedCore:
+    """The model-independent entry points the single-device SMC drivers use (runtime/smc_ops.py), restated with
+    oracle/smc.py.  Multi-GPU, fused cooperative and filter entry points are GPU-only and absent on purpose."""
+
+    def gjb_abi_version(self):
+        return 8
+
+    def gjb_mass_resample_fits(self, n):
+        return 0
+
+    def gjb_wmax_reset(self, wmax, stream):
+        _arr(wmax, 1, C.c_uint32, np.uint32)[0] = 0x007FFFFF
+        return 0
+
+    def gjb_weight_max(self, logw, n, wmax, stream):
+        w = _arr(wmax, 1, C.c_uint32, np.uint32)
+        if n > 0:
+            x = _view(logw, n, F32)
+            with np.errstate(invalid="ignore"):
+                m = np.fmax.reduce(x)
+            if not np.isnan(m):
+                w[0] = max(int(w[0]), _enc(m))
+        return 0
+
+    @staticmethod
+    def _max(wmax, m_global):
+        if m_global:
+            return _view(m_global, 1, F32)[0]
+        return _dec(_arr(wmax, 1, C.c_uint32, np.uint32)[0])
+
+    def gjb_weight_mass(self, logw, n, wmax, m_global, tile_mass, stream):
+        from oracle import smc as osmc
+
+        M = self._max(wmax, m_global)
+        x = _view(logw, n, F32)
+        with np.errstate(invalid="ignore"):
+            q = osmc.det_exp_q((x - M).astype(F32))
+        tiles = max(1, (n + _TILE - 1) // _TILE)
+        out = _arr(tile_mass, tiles, C.c_uint64, np.uint64)
+        for b in range(tiles):
+            out[b] = q[b * _TILE:(b + 1) * _TILE].sum(dtype=np.uint64)
+        return 0
+
+    def gjb_lse_finalize(self, tile_mass, n, wmax, m_global, n_total, lse_out, stream):
+        import math
+
+        tiles = max(1, (n + _TILE - 1) // _TILE)
+        S = int(_arr(tile_mass, tiles, C.c_uint64, np.uint64).sum(dtype=np.uint64))
+        M = float(self._max(wmax, m_global))
+        out = _arr(lse_out, 3, C.c_double, np.float64)
+        out[0], out[1] = M, float(S)
+        out[2] = M + math.log(S) - 36 * math.log(2.0) - math.log(n_total) if S else -math.inf
+        return 0
+
+    def gjb_resample_systematic(self, r_ref, stream):
+        from oracle import rng as orng
+        from oracle import smc as osmc
+
+        R = r_ref._obj
+        if R.key_dev or R.c_offset or R.s_total or R.m_global:
+            raise NotImplementedError("emulator: sharded / device-key resampling is a GPU-only path")
+        n = int(R.n)
+        logw = _view(R.logw, n, F32)
+        M = self._max(R.wmax, None)
+        tiles = max(1, (n + _TILE - 1) // _TILE)
+        S = int(_arr(R.tile_mass, tiles, C.c_uint64, np.uint64).sum(dtype=np.uint64))
+        anc = _view(R.ancestors, int(R.out_n), I32)
+        lo = int(R.out_lo)
+        if S == 0:
+            anc[:] = np.arange(lo, lo + int(R.out_n), dtype=I32)
+        else:
+            u0 = osmc.resample_u0(orng.Key((R.key0, R.key1), int(R.key_index)))
+            cnt, _ = osmc.systematic_counts(logw, u0, n_out=int(R.n_total), M=M, S=S)
+            prev = np.concatenate([[0], cnt[:-1]])
+            full = np.repeat(np.arange(n, dtype=np.int64) + int(R.anc_base), (cnt - prev).astype(np.int64))
+            anc[:] = full[lo:lo + int(R.out_n)].astype(I32)
+        if R.lse_out:
+            self.gjb_lse_finalize(R.tile_mass, n, R.wmax, None, int(R.n_total), R.lse_out, stream)
+        if R.wmax_next:
+            _arr(R.wmax_next, 1, C.c_uint32, np.uint32)[0] = 0x007FFFFF
+        return 0
+
+    def gjb_resample_multinomial(self, logw, n, wmax, tile_mass, cdf, key0, key1, idx_offset, n_out, ancestors, stream):
+        from oracle import rng as orng
+        from oracle import smc as osmc
+
+        x = _view(logw, n, F32)
+        M = self._max(wmax, None)
+        with np.errstate(invalid="ignore"):
+            q = osmc.det_exp_q((x - M).astype(F32))
+        Cq = np.cumsum(q, dtype=np.uint64)
+        S = int(Cq[-1]) if n else 0
+        anc = _view(ancestors, n_out, I32)
+        if S == 0:
+            anc[:] = np.arange(n_out, dtype=I32)
+            return 0
+        idx = np.arange(n_out, dtype=np.uint64) + np.uint64(idx_offset)
+        w0, w1, _, _ = orng.site_words((key0, key1), idx, 0, 1)
+        r = (w0.astype(np.uint64) << np.uint64(32)) | w1.astype(np.uint64)
+        anc[:] = np.searchsorted(Cq, osmc._mulhi64(r, np.uint64(S)), side="right").astype(I32)
+        return 0
+
+    def gjb_gather_rows(self, src, ancestors, dst, n_out, row_bytes, stream):
+        words = row_bytes // 4
+        anc = _view(ancestors, n_out, I32)
+        rows = int(anc.max()) + 1 if n_out else 0
+        s = _view(src, rows * words, I32).reshape(rows, words)
+        _view(dst, n_out * words, I32).reshape(n_out, words)[:] = s[anc]
+        return 0
+
+
+class _EmulatedCompiledModel:
+    def __init__(self, ir):
+        self.ir = ir
+        self.lib = EmulatedModelLib(ir)
+        self.path = None
+        self.info = json.loads(self.lib.gjb_model_info().decode())
+
+
+def install(monkeypatch):
+    """Route the host through the emulator for the duration of one test."""
+    from genjax_b200.gen import capture as cap
+    from genjax_b200.gen import static
+    from genjax_b200.runtime import cabi
+
+    cpu = torch.device("cpu")
+    monkeypatch.setattr(cabi, "require_cuda", lambda: cpu)
+    monkeypatch.setattr(cabi, "stream_ptr", lambda device=None: 0)
+    monkeypatch.setattr(cabi, "ptr", lambda t: None if t is None else t.data_ptr())
+
+    def compile_ir(ir, pf_obs=None, chain=None):
+        ir.digest = cap.ir_fingerprint(ir)
+        return _EmulatedCompiledModel(ir)
+
+    monkeypatch.setattr(static, "compile_ir", compile_ir)
+    core = EmulatedCore()
+    monkeypatch.setattr(cabi, "core", lambda: core)
+    return cpu

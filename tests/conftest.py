@@ -33,6 +33,16 @@ def pytest_collection_modifyitems(config, items):
 def device():
     import torch
 
+    if os.environ.get("GJB_EMULATE") == "1" and not torch.cuda.is_available():
+        # HOST-LOGIC dry run of the GPU tests on a CPU box: gjb_model_launch is emulated with the oracle
+        # (tests/abi_emulator.py); tests that reach any other entry point fail.  Proves nothing about the kernels.
+        import abi_emulator
+
+        mp = pytest.MonkeyPatch()
+        dev = abi_emulator.install(mp)
+        yield dev
+        mp.undo()
+        return
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    return torch.device("cuda", 0)
+    yield torch.device("cuda", 0)

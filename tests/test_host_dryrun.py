@@ -1,0 +1,22 @@
+"""HOST-LOGIC dry run of GPU test files on CPU: GJB_EMULATE=1 makes the `device` fixture install
+tests/abi_emulator.py (the oracle behind the real gjb_model_args / gjb_resample_args structures), so every host path
+those tests walk -- argument binding, flags, choice maps, traces, SMC drivers, Scan, get_subtrace -- is exercised
+without a device.  Proves nothing about the CUDA kernels (the -m gpu run on a B200 does); catches host regressions
+between GPU runs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("files", [["tests/test_gfi_gpu.py"], ["tests/test_zzz_unverified_gpu.py"]])
+def test_gpu_tests_host_paths_under_emulation(files):
+    env = dict(os.environ, GJB_EMULATE="1", GJB_RUN_UNVERIFIED="1", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-m", "pytest", *files, "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and "skipped" not in r.stdout.splitlines()[-1], tail

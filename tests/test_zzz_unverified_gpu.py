@@ -55,3 +55,120 @@ def test_get_subtrace_scores_and_project(device):
 
     one = f.simulate(gj.key(3), ())  # scalar trace: 0-d views
     assert one.get_subtrace("x").get_score().shape == ()
+
+
+# ------------------------------------------------------------------ Scan combinator (genjax_b200/gen/scan.py)
+
+from oracle import gfi as ogfi  # noqa: E402
+from oracle import rng  # noqa: E402
+
+F32 = np.float32
+STDS = np.array([2.0, 4.0, 3.0, 5.0, 1.0], dtype=F32)
+
+
+def _walk(gj):
+    @gj.gen
+    def walk(x, std):
+        nx = gj.normal(x, std) @ "x"
+        y = gj.normal(2.0 * nx, 0.5) @ "y"
+        return nx, nx + y
+
+    return walk
+
+
+def _o_walk(h, x, std):
+    nx = h.normal("x", x, std)
+    y = h.normal("y", (F32(2.0) * nx).astype(F32), F32(0.5))
+    return nx, (nx + y).astype(F32)
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("n", [None, 1, 1000])
+def test_scan_simulate_and_importance_match_oracle(device, n):
+    """scan.py:199-297 against oracle/gfi.py scan_simulate / scan_generate (same scenarios as tests/test_scan_host.py,
+    which runs them through the CPU emulation of the launch)."""
+    gj = _gj()
+    model = _walk(gj).scan(n=5)
+    key = gj.key(314159) if n is None else gj.split(gj.key(314159), n)
+    okey = rng.key(314159) if n is None else rng.split(rng.key(314159), n)
+    stds = torch.tensor(STDS, device=device)
+    tr = model.simulate(key, (0.25, stds))
+    otr, ocarry, oys, oscore = ogfi.scan_simulate(_o_walk, okey, F32(0.25), STDS)
+    lead = () if n is None else (n,)
+    xs = tr.get_choices()[:, "x"]
+    assert tuple(xs.shape) == lead + (5,)
+    np.testing.assert_allclose(_np(xs).reshape(-1, 5), np.stack([t.choices["x"] for t in otr], 1), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(_np(tr.get_score()).reshape(-1), oscore, rtol=1e-5, atol=5e-5)
+    carry, ys = tr.get_retval()
+    np.testing.assert_allclose(_np(carry).reshape(-1), np.broadcast_to(ocarry, (n or 1,)), rtol=1e-5, atol=2e-6)
+    assert tuple(ys.shape) == lead + (5,)
+    sub = tr.get_subtrace("y").get_score()
+    assert tuple(sub.shape) == lead + (5,)
+
+    yobs = np.array([0.5, -1.0, 2.0, 0.0, 1.0], dtype=F32)
+    tr2, w = model.importance(key, gj.C[:, "y"].set(torch.tensor(yobs, device=device)), (0.1, stds))
+    _, _, _, osc2, ow = ogfi.scan_generate(_o_walk, okey, lambda t: {"y": yobs[t]}, F32(0.1), STDS)
+    np.testing.assert_allclose(_np(w).reshape(-1), ow, rtol=1e-5, atol=5e-5)
+    np.testing.assert_allclose(_np(tr2.get_score()).reshape(-1), osc2, rtol=1e-5, atol=5e-5)
+
+
+def test_scan_lane_consistency_update_regenerate(device):
+    gj = _gj()
+    model = _walk(gj).scan()
+    n = 64
+    stds = torch.tensor(STDS, device=device)
+    args = (0.3, stds)
+    kb = gj.split(gj.key(11), n)
+    tr = model.simulate(kb, args)
+    one = model.simulate(kb[3], args)
+    assert torch.equal(tr.get_choices()[:, "x"][3], one.get_choices()[:, "x"])
+    otr, _, _, _ = ogfi.scan_simulate(_o_walk, rng.split(rng.key(11), n), F32(0.3), STDS)
+
+    new, w, _, bwd = model.update(gj.split(gj.key(12), n), tr, gj.C[1, "x"].set(9.0), gj.Diff.no_change(args))
+    _, _, _, oscore, ow, _ = ogfi.scan_update(_o_walk, rng.split(rng.key(12), n), otr,
+                                              lambda t: {"x": F32(9.0)} if t == 1 else {}, F32(0.3), STDS)
+    np.testing.assert_allclose(_np(w), ow, rtol=2e-4, atol=5e-4)
+    np.testing.assert_allclose(_np(new.get_score()), oscore, rtol=1e-5, atol=5e-5)
+    xs_new, xs_old = new.get_choices()[:, "x"], tr.get_choices()[:, "x"]
+    assert (xs_new[:, 1] == 9.0).all() and torch.equal(xs_new[:, [0, 2, 3, 4]], xs_old[:, [0, 2, 3, 4]])
+    assert torch.equal(bwd[1, "x"], xs_old[:, 1])
+    back, wb, _, _ = model.update(gj.split(gj.key(13), n), new, bwd, gj.Diff.no_change(args))
+    torch.testing.assert_close(w + wb, torch.zeros(n, device=device), rtol=0, atol=2e-3)
+    assert torch.equal(back.get_choices()[:, "x"], xs_old)
+
+    reg, wr, _, _ = model.edit(gj.split(gj.key(14), n), tr, gj.Regenerate(gj.S["x"]), gj.Diff.no_change(args))
+    oreg, _, _, _, owr = ogfi.scan_regenerate(_o_walk, rng.split(rng.key(14), n), otr, {"x"}, F32(0.3), STDS)
+    np.testing.assert_allclose(_np(wr), owr, rtol=2e-4, atol=5e-4)
+    np.testing.assert_allclose(_np(reg.get_choices()[:, "x"]), np.stack([t.choices["x"] for t in oreg], 1), rtol=1e-5, atol=2e-6)
+    assert torch.equal(reg.get_choices()[:, "y"], tr.get_choices()[:, "y"])
+
+    chm = gj.vmap(lambda c: c, in_axes=0)(tr.get_choices())
+    score, _ = model.assess(chm, args)
+    torch.testing.assert_close(score, tr.get_score(), rtol=1e-5, atol=5e-5)
+
+
+def test_iterate_and_accumulate(device):
+    gj = _gj()
+
+    @gj.gen
+    def step(x):
+        return gj.normal(x, 1.0) @ "z"
+
+    it = step.iterate(n=10)
+    tr, w = it.importance(gj.key(314159), gj.C[3, "z"].set(0.5), (0.01,))
+    zs = tr.get_choices()[:, "z"]
+    assert zs[3] == 0.5
+    assert w.item() == pytest.approx(float(od.normal_logpdf(F32(0.5), F32(zs[2].item()), F32(1.0))), rel=1e-5, abs=2e-5)
+    out = tr.get_retval()
+    assert out.shape == (11,) and torch.equal(out[1:], zs)
+
+    @gj.gen
+    def add(acc, x):
+        return acc + x + 0.0 * (gj.normal(0.0, 1.0) @ "eps")
+
+    res = add.accumulate().simulate(gj.key(0), (0.0, torch.ones(4))).get_retval()
+    assert torch.equal(res.cpu(), torch.tensor([0.0, 1.0, 2.0, 3.0, 4.0]))
+    assert add.reduce().simulate(gj.key(0), (0.0, torch.ones(10))).get_retval().item() == 10.0
