@@ -53,6 +53,7 @@ from .gen.gfi import (
 )
 from .gen.static import Batched, StaticGenerativeFunction, StaticTrace, gen, vmap
 from .gen.scan import Scan, ScanTrace, accumulate, iterate, iterate_final, reduce, scan
+from .gen.vmap_combinator import Vmap, VmapTrace, repeat, vmap_combinator
 from .inference.sp import Algorithm, Marginal, SampleDistribution, Target, marginal
 from . import inference
 

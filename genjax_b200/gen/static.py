@@ -87,11 +87,20 @@ def _mark(tree, axes):
     raise NotImplementedError("only in_axes of 0 / None are supported (particles live on the leading axis)")
 
 
-def vmap(fn: Callable, in_axes=0):
+def vmap(fn: Callable | None = None, in_axes=0):
     """``jax.vmap`` for GFI calls: ``vmap(model.importance, in_axes=(0, None, (0,)))(keys, chm, (x_prev,))``.
 
     The batch is not unrolled: the call runs ONE fused kernel over all lanes
-    of the ``KeyBatch`` / all rows of the ``in_axes=0`` arguments."""
+    of the ``KeyBatch`` / all rows of the ``in_axes=0`` arguments.
+
+    ``vmap(in_axes=...)`` without a function is the reference's combinator decorator ``@genjax.vmap(in_axes=...)``
+    (vmap.py:384): applied to an ``@gen`` function it returns a ``Vmap`` generative function."""
+    if fn is None or isinstance(fn, StaticGenerativeFunction):
+        from .vmap_combinator import Vmap
+
+        if fn is not None:
+            return Vmap(fn, in_axes)
+        return lambda f: Vmap(f, in_axes) if isinstance(f, StaticGenerativeFunction) else vmap(f, in_axes)
 
     def wrapped(*args):
         axes = in_axes if isinstance(in_axes, (tuple, list)) else (in_axes,) * len(args)

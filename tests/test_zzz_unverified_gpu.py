@@ -172,3 +172,49 @@ def test_iterate_and_accumulate(device):
     res = add.accumulate().simulate(gj.key(0), (0.0, torch.ones(4))).get_retval()
     assert torch.equal(res.cpu(), torch.tensor([0.0, 1.0, 2.0, 3.0, 4.0]))
     assert add.reduce().simulate(gj.key(0), (0.0, torch.ones(10))).get_retval().item() == 10.0
+
+
+# ------------------------------------------------------------------ Vmap / repeat (genjax_b200/gen/vmap_combinator.py)
+
+
+def test_vmap_combinator_and_repeat(device):
+    """vmap.py:180-275, 363-375 and repeat.py:25-41 (scenarios of tests/test_vmap_host.py on the device)."""
+    gj = _gj()
+
+    @gj.gen
+    def kernel(x):
+        z = gj.normal(x, 1.0) @ "z"
+        return z
+
+    def o_kernel(h, x):
+        return h.normal("z", x, F32(1.0))
+
+    def lp(v, mu):
+        return float(od.normal_logpdf(F32(v), F32(mu), F32(1.0)))
+
+    model = gj.vmap(in_axes=(0,))(kernel)
+    over = torch.arange(0, 50, dtype=torch.float32, device=device)
+    tr = model.simulate(gj.key(314159), (over,))
+    otr = ogfi.simulate(o_kernel, rng.split(rng.key(314159), 50), (np.arange(50, dtype=F32),))
+    np.testing.assert_allclose(_np(tr.get_choices()[:, "z"]), otr.choices["z"], rtol=1e-5, atol=2e-6)
+    assert tr.get_score().shape == () and tr.get_score().item() == pytest.approx(float(otr.get_score().sum()), rel=1e-5)
+    assert tr.project(gj.key(1), gj.Selection.all()).item() == pytest.approx(tr.get_score().item(), rel=1e-5)
+    score, ret = model.assess(tr.get_choices(), (over,))
+    assert score.item() == pytest.approx(tr.get_score().item(), rel=1e-5) and torch.equal(ret, tr.get_retval())
+
+    over3 = torch.arange(0, 3, dtype=torch.float32, device=device)
+    _, w = model.importance(gj.key(314159), gj.C[:, "z"].set(torch.tensor([3.0, 2.0, 3.0], device=device)), (over3,))
+    assert w.item() == pytest.approx(lp(3.0, 0.0) + lp(2.0, 1.0) + lp(3.0, 2.0), rel=1e-5)
+    tr1, w1 = model.importance(gj.key(1), gj.C[1, "z"].set(5.0), (over3,))  # three launches: lanes [0,1), {1}, [2,3)
+    assert tr1.get_choices()[1, "z"] == 5.0 and w1.item() == pytest.approx(lp(5.0, 1.0), rel=1e-5)
+    free = model.simulate(gj.key(1), (over3,)).get_choices()[:, "z"]
+    assert torch.equal(tr1.get_choices()[:, "z"][[0, 2]], free[[0, 2]])
+
+    old = tr1.get_choices()[:, "z"]
+    new, wu, _, bwd = model.update(gj.key(6), tr1, gj.C[2, "z"].set(1.0), gj.Diff.no_change((over3,)))
+    assert new.get_choices()[2, "z"] == 1.0 and bwd[2, "z"] == old[2]
+    assert wu.item() == pytest.approx(lp(1.0, 2.0) - lp(old[2].item(), 2.0), rel=1e-4, abs=2e-5)
+
+    rep = kernel.repeat(n=3).simulate(gj.key(314159), (0.0,))
+    vm = kernel.vmap().simulate(gj.key(314159), (torch.zeros(3, device=device),))
+    assert rep.get_retval().shape == (3,) and torch.equal(vm.get_choices()[:, "z"], rep.get_choices()[:, "z"])
