@@ -203,6 +203,8 @@ class Vmap(GenerativeFunction):
             inner = tr if inner is None else _concat_traces(inner, tr)
             if w is not None:
                 weight.append(w)
+        if len(runs) > 1:
+            inner.args = marked  # the concatenation kept the first run's slice; the trace spans all lanes
         return inner, (torch.cat(weight).sum() if weight else None), discard
 
     # -- GFI ---------------------------------------------------------------

@@ -86,6 +86,12 @@ def test_vmap_update_and_regenerate(emu):
     allnew, w2, _, bwd2 = model.update(gj.key(7), tr, C[:, "z"].set(torch.zeros(4)), gj.Diff.no_change((over,)))
     assert torch.equal(bwd2[:, "z"], old) and (allnew.get_choices()[:, "z"] == 0).all()
     assert w2.item() == pytest.approx(allnew.get_score().item() - tr.get_score().item(), rel=1e-4, abs=1e-4)
+    # a trace that was itself assembled from several runs can be updated again
+    part, _ = model.importance(gj.key(9), C[1, "z"].set(5.0), (over,))
+    again, w4, _, bwd4 = model.update(gj.key(10), part, C[3, "z"].set(-1.0), gj.Diff.no_change((over,)))
+    assert again.get_choices()[1, "z"] == 5.0 and again.get_choices()[3, "z"] == -1.0
+    assert bwd4[3, "z"] == part.get_choices()[3, "z"]
+    assert w4.item() == pytest.approx(_lp(-1.0, 3.0) - _lp(part.get_choices()[3, "z"].item(), 3.0), rel=1e-4, abs=1e-5)
     reg, w3, _, _ = model.edit(gj.key(8), tr, gj.Regenerate(gj.S["z"]), gj.Diff.no_change((over,)))
     assert not torch.equal(reg.get_choices()[:, "z"], old)
     assert w3.item() == pytest.approx(reg.get_score().item() - tr.get_score().item(), rel=1e-4, abs=1e-4)
