@@ -16,7 +16,7 @@ from __future__ import annotations
 import math
 
 from . import expr as E
-from .expr import Expr, F32, I32
+from .expr import Expr, F32
 
 _HALF_LOG_2PI = 0.5 * math.log(2.0 * math.pi)
 

@@ -13,7 +13,7 @@ from __future__ import annotations
 import contextvars
 import hashlib
 import json
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Any, Callable
 
 from . import expr as E

@@ -13,7 +13,6 @@ a primitive can be fused only if it has device code registered under its name
 from __future__ import annotations
 
 import warnings
-from typing import Any
 
 from . import expr as E
 from .expr import Expr, F32, I32

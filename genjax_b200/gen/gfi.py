@@ -11,7 +11,6 @@ incremental.py (``Diff:89``, ``NoChange``, ``UnknownChange``).
 
 from __future__ import annotations
 
-from typing import Any
 
 from ..core.choice_map import ChoiceMap, Selection
 

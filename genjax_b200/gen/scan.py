@@ -23,7 +23,7 @@ capture pass fuses static bodies only).
 
 from __future__ import annotations
 
-from typing import Any, Callable
+from typing import Callable
 
 import numpy as np
 import torch

@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import json
-from typing import Any, Callable
+from typing import Callable
 
 import numpy as np
 import torch

@@ -24,7 +24,6 @@ import torch
 
 from ..core.choice_map import ChoiceMap, Selection, _norm_addr
 from ..core.key import lanes_of
-from ..gen import capture as cap
 from ..gen.codegen_chain import ChainSpec
 from ..gen.gfi import Diff, EditRequest, Update
 from ..gen.static import StaticTrace, _rebatch, compile_ir

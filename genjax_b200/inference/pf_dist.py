@@ -32,7 +32,7 @@ import torch.distributed as dist
 from ..core.choice_map import ChoiceMap
 from ..core.key import PRNGKey, pf_key_table
 from ..gen.capture import ArgSpec
-from ..gen.expr import Expr, I32
+from ..gen.expr import Expr
 from ..gen.static import StaticGenerativeFunction, _dev_tensor
 from ..runtime import cabi, smc_ops
 from .pf import PFResult

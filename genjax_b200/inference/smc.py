@@ -12,12 +12,10 @@ over the lanes of a ``KeyBatch``.
 
 from __future__ import annotations
 
-import math
-
 import torch
 
 from ..core.choice_map import ChoiceMap
-from ..core.key import KeyBatch, PRNGKey, key_children, split
+from ..core.key import PRNGKey, key_children, split
 from ..gen.static import Batched, StaticTrace, _rebatch
 from ..runtime import smc_ops
 from .sp import Algorithm, SampleDistribution, Target
