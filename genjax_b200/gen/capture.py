@@ -13,6 +13,7 @@ from __future__ import annotations
 import contextvars
 import hashlib
 import json
+import dataclasses
 from dataclasses import dataclass
 from typing import Any, Callable
 
@@ -143,6 +144,9 @@ def flatten(tree) -> tuple[list, Any]:
         if type(t).__name__ == "Target" and hasattr(t, "constraint") and hasattr(t, "p"):
             # Target(p, args, constraint): p is static, args and constraint are traced (sp.py:53-81)
             return ("target", (t.p, go(t.args), go(t.constraint)))
+        if dataclasses.is_dataclass(t) and not isinstance(t, type):
+            # user pytrees (the reference's Pytree.dataclass): fields are children, the class is static
+            return ("dataclass", (type(t), [(f.name, go(getattr(t, f.name))) for f in dataclasses.fields(t)]))
         if isinstance(t, tuple):
             return ("tuple", [go(x) for x in t])
         if isinstance(t, list):
@@ -171,6 +175,9 @@ def unflatten(tree, leaves):
 
         p, a, c = payload
         return Target(p, unflatten(a, leaves), unflatten(c, leaves))
+    if kind == "dataclass":
+        cls, fields = payload
+        return cls(**{name: unflatten(sub, leaves) for name, sub in fields})
     if kind == "tuple":
         return tuple(unflatten(x, leaves) for x in payload)
     if kind == "list":

@@ -241,7 +241,9 @@ class Trace:
 
 
 class GenerativeFunctionClosure:
-    """``gen_fn(*args)``; ``closure @ "addr"`` traces it (generative_function.py:1568-1583)."""
+    """``gen_fn(*args, **kwargs)`` (generative_function.py:1558-1690): ``closure @ "addr"`` traces it inside a
+    ``@gen`` body; ``closure(key)`` runs it and returns the return value; the GFI methods take the REMAINING
+    arguments.  Keyword arguments go through ``gen_fn.handle_kwargs()``, whose arguments are ``(args, kwargs)``."""
 
     def __init__(self, gen_fn, args: tuple, kwargs: dict):
         self.gen_fn = gen_fn
@@ -256,22 +258,45 @@ class GenerativeFunctionClosure:
 
         return trace_site(addr, self.gen_fn, self._packed_args())
 
+    def _target(self, args=(), kwargs=None):
+        """(generative function to run, its argument tuple)."""
+        full = self.args + tuple(args)
+        kw = {**self.kwargs, **(kwargs or {})}
+        if kw:
+            return self.gen_fn.handle_kwargs(), (full, kw)
+        return self.gen_fn, full
+
+    def __call__(self, key, *args, **kwargs):
+        fn, full = self._target(args, kwargs)
+        return fn.simulate(key, full).get_retval()
+
+    def handle_kwargs(self):
+        return self
+
     # direct GFI use: genjax.normal(0., 1.).simulate(key, ())
     def simulate(self, key, args=()):
-        return self.gen_fn.simulate(key, self._full(args))
+        fn, full = self._target(args)
+        return fn.simulate(key, full)
 
-    def importance(self, key, constraint, args=()):
-        return self.gen_fn.importance(key, constraint, self._full(args))
+    def generate(self, key, constraint, args=()):
+        fn, full = self._target(args)
+        return fn.generate(key, constraint, full)
+
+    importance = generate
 
     def assess(self, sample, args=()):
-        return self.gen_fn.assess(sample, self._full(args))
+        fn, full = self._target(args)
+        return fn.assess(sample, full)
 
     def propose(self, key, args=()):
-        return self.gen_fn.propose(key, self._full(args))
+        fn, full = self._target(args)
+        return fn.propose(key, full)
+
+    def project(self, key, trace, selection):
+        return self.gen_fn.project(key, trace, selection)
 
     def _full(self, args):
-        full = self.args + tuple(args)
-        return (full, self.kwargs) if self.kwargs else full
+        return self._target(args)[1]
 
 
 class GenerativeFunction:
@@ -322,5 +347,9 @@ class GenerativeFunction:
         with its first arguments fixed; the choices keep their addresses."""
         raise NotImplementedError(f"partial_apply is not available for {type(self).__name__}")
 
+    def handle_kwargs(self):
+        """A version of this function whose arguments are ``(args, kwargs)`` (generative_function.py:1466-1480)."""
+        return self
+
     def get_zero_trace(self, *args):
-        raise NotImplementedError("zero traces belong to the jaxpr staging machinery (out of scope)")
+        raise NotImplementedError(f"get_zero_trace is not available for {type(self).__name__}")

@@ -310,6 +310,38 @@ class StaticTrace(Trace):
                            self.score.index_select(0, sel), rets, dict(self.bcast))
 
 
+class ZeroTrace(Trace):
+    """``gen_fn.get_zero_trace(*args)``: addresses, shapes and dtypes of a trace, all values zero."""
+
+    def __init__(self, gen_fn, args, ir: ModelIR):
+        self.gen_fn, self.args, self.ir = gen_fn, args, ir
+
+    @staticmethod
+    def _zero(e):
+        if not isinstance(e, Expr):
+            return e
+        dt = torch.int32 if e.dtype == I32 else torch.float32
+        return torch.zeros(tuple(e.shape), dtype=dt) if e.shape else (0 if e.dtype == I32 else 0.0)
+
+    def get_gen_fn(self):
+        return self.gen_fn
+
+    def get_args(self):
+        return self.args
+
+    def get_score(self):
+        return 0.0
+
+    def get_retval(self):
+        return cap.unflatten(self.ir.ret_tree, [self._zero(r) for r in self.ir.ret_leaves])
+
+    def get_choices(self) -> ChoiceMap:
+        chm = ChoiceMap.empty()
+        for s in self.ir.sites:
+            chm = chm | ChoiceMap.entry(self._zero(s.value), *s.addr)
+        return chm
+
+
 class SubTrace(Trace):
     """View of one site (``DistributionTrace``, distribution.py:60-87) or of the sites under a nested call's
     address prefix (the inlined callee's ``StaticTrace``) inside a fused ``StaticTrace``."""
@@ -382,11 +414,18 @@ def _take_args(tree, sel):
 
 
 class StaticGenerativeFunction(GenerativeFunction):
-    def __init__(self, source: Callable):
+    def __init__(self, source: Callable, partial_args: tuple = ()):
         self.source = source
+        # functools.wraps-style metadata (static.py:1044-1062; test_static_gen_fn.py:38-79)
         self.__name__ = getattr(source, "__name__", "model")
         self.__doc__ = getattr(source, "__doc__", None)
+        self.__module__ = getattr(source, "__module__", self.__module__)
+        self.__qualname__ = getattr(source, "__qualname__", self.__name__)
+        self.__annotations__ = dict(getattr(source, "__annotations__", {}))
+        self.__wrapped__ = source
+        self.partial_args = tuple(partial_args)  # arguments fixed by partial_apply / method binding
         self._cache: dict = {}
+        self._kwarged = None
 
     def __repr__(self):
         return f"StaticGenerativeFunction({self.__name__})"
@@ -395,16 +434,41 @@ class StaticGenerativeFunction(GenerativeFunction):
         # @gen on methods (static.py:757-763): bind `self` as the first argument
         if instance is None:
             return self
-        bound = StaticGenerativeFunction(lambda *a: self.source(instance, *a))
+        bound = StaticGenerativeFunction(lambda *a, **kw: self.source(instance, *a, **kw), self.partial_args + (instance,))
         bound.__name__ = self.__name__
         return bound
 
     def partial_apply(self, *bound):
-        """Same model with its first arguments fixed (test_static_gen_fn.py:1116-1163): addresses unchanged."""
+        """Same model with its first arguments fixed (test_static_gen_fn.py:1116-1163): addresses unchanged, the
+        fixed values stay readable as ``partial_args``."""
         src = self.source
-        out = StaticGenerativeFunction(lambda *rest: src(*bound, *rest))
+        out = StaticGenerativeFunction(lambda *rest, **kw: src(*bound, *rest, **kw), self.partial_args + tuple(bound))
         out.__name__ = f"{self.__name__}_partial"
         return out
+
+    def handle_kwargs(self) -> "StaticGenerativeFunction":
+        """The same model taking ``(args, kwargs)`` as its two arguments (static.py ``handle_kwargs``;
+        generative_function.py:1563-1565): what a closure with keyword arguments runs."""
+        if self._kwarged is None:
+            src = self.source
+            out = StaticGenerativeFunction(lambda args, kwargs: src(*args, **kwargs), self.partial_args)
+            out.__name__ = f"{self.__name__}_kwargs"
+            out._kwarged = out
+            self._kwarged = out
+        return self._kwarged
+
+    def inline(self, *args):
+        """``callee.inline(*args)`` inside an ``@gen`` body: the callee's choices are recorded at the CALLER's
+        address level (static.py ``inline``; test_static_gen_fn.py:949-1087)."""
+        if cap.current_capture() is None:
+            raise RuntimeError("`gen_fn.inline(*args)` can only be used inside a @gen function body")
+        return self.source(*args)
+
+    def get_zero_trace(self, *args):
+        """A trace-shaped object with zeros everywhere (generative_function.py ``get_zero_trace``): the SHAPE of what
+        the model visits for these arguments.  Host-only, nothing is launched."""
+        bound = _BoundArgs(args, torch.device("cpu"))
+        return ZeroTrace(self, args, cap.capture(self.source, self.__name__, bound.specs, bound.tree))
 
     # -- capture ---------------------------------------------------------
     def capture_inline(self, args):
@@ -687,38 +751,57 @@ def _rebatch_constraint(chm: ChoiceMap, trace: StaticTrace) -> ChoiceMap:
     return chm.map_leaves(mark)
 
 
-def _edit_static_request(gf, key, trace, request: StaticRequest, argdiffs):
-    """StaticRequest (static.py:512-566, 867-904): per-address sub-requests.
-    Update / Regenerate sub-requests fuse into ONE launch; other sub-requests
-    (Rejuvenate, HMC) are delegated to their own batched drivers."""
-    constraint = ChoiceMap.empty()
-    selected = []
-    custom = []
-    for addr, sub in request.addressed.items():
-        from ..core.choice_map import _norm_addr
+def _collect_static_request(request: StaticRequest, prefix: tuple, out: dict) -> None:
+    """Flatten (possibly nested) per-address sub-requests into one constraint, one selection list and the rest."""
+    from ..core.choice_map import _norm_addr
 
-        a = _norm_addr(addr)
+    for addr, sub in request.addressed.items():
+        a = prefix + _norm_addr(addr)
         if isinstance(sub, Update):
-            constraint = constraint | ChoiceMap.entry(sub.constraint, *a)
+            out["constraint"] = out["constraint"] | ChoiceMap.entry(sub.constraint, *a)
         elif isinstance(sub, Regenerate):
-            selected.append(Selection.all().extend(*a) if sub.selection.check() else sub.selection.extend(*a))
+            out["selected"].append(Selection.all().extend(*a) if sub.selection.check() else sub.selection.extend(*a))
         elif isinstance(sub, EmptyRequest):
             pass
+        elif isinstance(sub, StaticRequest):
+            _collect_static_request(sub, a, out)
         else:
-            custom.append((a, sub))
+            out["custom"].append((a, sub))
+
+
+def _edit_static_request(gf, key, trace, request: StaticRequest, argdiffs):
+    """StaticRequest (static.py:512-566, 867-904): per-address sub-requests, nested ones included.
+    Update / Regenerate sub-requests fuse into ONE launch (constrained sites read, selected sites resampled, every
+    site re-scored); other sub-requests (Rejuvenate, HMC) are delegated to their own batched drivers."""
+    out = {"constraint": ChoiceMap.empty(), "selected": [], "custom": []}
+    _collect_static_request(request, (), out)
+    constraint, selected, custom = out["constraint"], out["selected"], out["custom"]
     if custom:
         if len(custom) > 1 or selected or not constraint.static_is_empty():
             raise NotSupportedEditRequest(request)
         a, sub = custom[0]
         return sub.edit_at(key, trace, a, argdiffs)
-    if selected and not constraint.static_is_empty():
-        raise NotSupportedEditRequest(request)
-    if selected:
-        sel = selected[0]
-        for s in selected[1:]:
-            sel = sel | s
+    sel = Selection.none()
+    for s in selected:
+        sel = sel | s
+    if not selected:
+        return gf.edit(key, trace, Update(constraint), argdiffs)
+    if constraint.static_is_empty():
         return gf.edit(key, trace, Regenerate(sel), argdiffs)
-    return gf.edit(key, trace, Update(constraint), argdiffs)
+    # both kinds at once: the backward request restores every touched site (distribution.py:179-300)
+    new_args = Diff.tree_primal(argdiffs) if argdiffs is not None and argdiffs != () else trace.args
+    if new_args == () and trace.args != ():
+        new_args = trace.args
+    new_args = _carry_batch_marks(new_args, trace.args)
+    sites = trace.cm.ir.sites
+    sel_addrs = {s.addr for s in sites if sel(s.addr).check() and not constraint.get_submap(*s.addr).has_value()}
+    tr, w = gf._run(key, new_args, _rebatch_constraint(constraint, trace), prev=trace, sample_addrs=sel_addrs,
+                    weight_mode="delta", n=trace.n, batched=trace.batched)
+    discard = ChoiceMap.empty()
+    for s in sites:
+        if s.addr in sel_addrs or constraint.get_submap(*s.addr).has_value():
+            discard = discard | ChoiceMap.entry(trace._site_value(s), *s.addr)
+    return tr, gf._w(tr, w), Diff.unknown_change(tr.get_retval()), Update(discard)
 
 
 def gen(source: Callable) -> StaticGenerativeFunction:

@@ -19,6 +19,7 @@ _MODEL_LAUNCH_ONLY = ("test_step_importance_matches_oracle or test_assess_kat or
 @pytest.mark.parametrize("files", [
     ["tests/test_gfi_gpu.py"],
     ["tests/test_zzz_unverified_gpu.py"],
+    ["tests/test_zzz_static_reference_gpu.py"],
     # the filter, chain and core-kernel tests reach entry points that exist on the GPU only; these do not
     ["tests/test_pf_gpu.py", "tests/test_mcmc_gpu.py", "tests/test_zz_mv_normal_gpu.py", "-k", _MODEL_LAUNCH_ONLY],
 ])

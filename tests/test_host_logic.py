@@ -270,3 +270,36 @@ def test_chain_kernels_are_generated_and_hmc_degrades_to_e_mode_without_a_gradie
     ir = cap.capture(discrete.source, "discrete", [], ("tuple", []))
     with pytest.raises(NotDifferentiable):
         compile_ir(ir, chain=ChainSpec((0,), (None,)))
+
+
+def test_gen_transfers_function_metadata():
+    """test_static_gen_fn.py:38-79 (TestStaticGenFnMetadata)."""
+    import genjax_b200 as gj
+
+    def original_function(x: float, y: float) -> float:
+        """This is a test function that adds two numbers."""
+        return x + y
+
+    wrapped = gj.gen(original_function)
+    assert wrapped.__doc__ == original_function.__doc__ and wrapped.__name__ == original_function.__name__
+    assert wrapped.__module__ == original_function.__module__ and wrapped.__qualname__ == original_function.__qualname__
+    assert wrapped.__wrapped__ is original_function
+    assert wrapped.__annotations__ == {"x": float, "y": float, "return": float}
+    assert gj.gen(original_function).partial_apply(1.0).partial_apply(2.0).partial_args == (1.0, 2.0)
+
+
+def test_zero_trace_and_site_addresses_need_no_device():
+    import genjax_b200 as gj
+
+    @gj.gen
+    def model(x):
+        y = gj.normal(x, 1.0) @ "y"
+        z = gj.bernoulli(probs=0.7) @ ("z", "inner")
+        return y + z
+
+    zt = model.get_zero_trace(0.0)
+    assert zt.get_args() == (0.0,) and zt.get_retval() == 0.0 and zt.get_score() == 0.0
+    assert zt.get_choices()["y"] == 0.0 and zt.get_choices()["z", "inner"] == 0
+    assert model.get_site_addresses((0.0,)) == [("y",), ("z", "inner")]
+    with pytest.raises(RuntimeError):
+        model.inline(0.0)  # only inside an @gen body
