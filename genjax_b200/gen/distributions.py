@@ -23,10 +23,11 @@ class NotFusable(NotImplementedError):
     pass
 
 
-def implicit_logit_warning():
-    """distribution.py:479-500: bare positional arg to categorical/bernoulli = logits."""
+def implicit_logit_warning(name: str = "distribution"):
+    """distribution.py:479-500: a bare positional argument to categorical / bernoulli means logits, and warns."""
     warnings.warn(
-        "You are using the implicit logits argument; use the explicit `logits=` or `probs=` keyword instead.",
+        f"The use of a bare argument to genjax.{name} is deprecated. Please specify `logits=` or `probs=` for the "
+        "parameters. The default, which will be used in this case, is logits.",
         DeprecationWarning,
         stacklevel=3,
     )
@@ -81,7 +82,7 @@ class Distribution(GenerativeFunction):
         return f"gjb::{self.cuda}::logpdf({v}, {', '.join(a)})"
 
     def __repr__(self):
-        return f"genjax_b200.{self.name}"
+        return f"genjax.{self.name}()"  # what the reference prints (test_distributions.py:476-489)
 
 
 def _split_kwargs(args):
@@ -150,7 +151,7 @@ class _Bernoulli(Distribution):
         if "logits" in kwargs:
             return [kwargs["logits"]]
         if len(args) == 1:
-            implicit_logit_warning()
+            implicit_logit_warning("bernoulli")
             return [args[0]]
         raise TypeError("bernoulli expects logits= or probs=")
 
@@ -167,7 +168,7 @@ class _Categorical(Distribution):
         if "logits" in kwargs:
             return [kwargs["logits"]]
         if len(args) == 1:
-            implicit_logit_warning()
+            implicit_logit_warning("categorical")
             return [args[0]]
         raise TypeError("categorical expects logits= or probs=")
 

@@ -425,3 +425,78 @@ def test_project_and_tupled_addresses(device):
     px, py = tr.project(gj.key(1), gj.S["x"]), tr.project(gj.key(1), gj.S["y"])
     assert px == tr.get_subtrace("x", "x0").get_score() and py == tr.get_subtrace("y").get_score()
     assert tr.get_score().item() == pytest.approx((px + py).item(), abs=1e-5)
+
+
+# ------------------------------------------------------------------ tests/generative_functions/test_distributions.py
+
+
+def test_distribution_gfi(device):
+    """TestDistributions.test_simulate / test_importance / test_update (mask cases with concrete flags only)."""
+    gj = _gj()
+    NoChange, UnknownChange, Diff, C = gj.NoChange, gj.UnknownChange, gj.Diff, gj.C
+    key = gj.key(314159)
+    tr = gj.normal(0.0, 1.0).simulate(key, ())
+    assert tr.get_score() == gj.normal(0.0, 1.0).assess(tr.get_choices(), ())[0]
+
+    tr, w = gj.normal.importance(key, C.n(), (0.0, 1.0))
+    assert w == 0.0
+    tr, w = gj.normal.importance(key, C.v(1.0), (0.0, 1.0))
+    assert w == gj.normal(0.0, 1.0).assess(tr.get_choices(), ())[0]
+    tr, w = gj.normal.importance(key, C.v(1.0).mask(True), (0.0, 1.0))
+    assert tr.get_choices().get_value() == 1.0 and w == gj.normal.assess(C.v(1.0), (0.0, 1.0))[0]
+    tr, w = gj.normal.importance(key, C.v(1.0).mask(False), (0.0, 1.0))
+    assert tr.get_choices().get_value() != 1.0 and w == 0.0
+
+    tr = gj.normal.simulate(gj.key(1), (0.0, 1.0))
+    old = tr.get_choices()
+
+    def lp(chm, *args):
+        return gj.normal.assess(chm, args)[0].item()
+
+    cases = [  # (constraint, argdiffs, new value is 1.0?, new args)
+        (C.n(), (Diff(0.0, NoChange), Diff(1.0, NoChange)), False, (0.0, 1.0)),
+        (C.v(1.0), (Diff(0.0, NoChange), Diff(1.0, NoChange)), True, (0.0, 1.0)),
+        (C.n(), (Diff(1.0, UnknownChange), Diff(1.0, NoChange)), False, (1.0, 1.0)),
+        (C.v(1.0), (Diff(1.0, UnknownChange), Diff(2.0, UnknownChange)), True, (1.0, 2.0)),
+        (C.v(1.0).mask(True), (Diff(1.0, UnknownChange), Diff(1.0, NoChange)), True, (1.0, 1.0)),
+        (C.v(1.0).mask(False), (Diff(0.0, NoChange), Diff(1.0, NoChange)), False, (0.0, 1.0)),
+        (C.v(1.0).mask(False), (Diff(1.0, UnknownChange), Diff(1.0, NoChange)), False, (1.0, 1.0)),
+    ]
+    for i, (chm, argdiffs, moved, new_args) in enumerate(cases):
+        new_tr, w, _, _ = gj.normal.update(gj.key(10 + i), tr, chm, argdiffs)
+        want = C.v(1.0) if moved else old
+        assert new_tr.get_choices().get_value() == want.get_value()
+        assert new_tr.get_score().item() == pytest.approx(lp(want, *new_args), abs=1e-5)
+        assert w.item() == pytest.approx(lp(want, *new_args) - lp(old, 0.0, 1.0), abs=1e-5)
+
+
+def test_distribution_repr_kwargs_and_warnings(device):
+    """test_distribution_repr / test_distribution_kwargs / test_deprecation_warnings."""
+    gj = _gj()
+
+    @gj.gen
+    def model():
+        x = gj.normal(0.0, 1.0) @ "x"
+        y = gj.bernoulli(logits=0.0) @ "y"
+        z = gj.flip(0.5) @ "z"
+        t = gj.categorical(logits=[0.0, 0.0]) @ "t"
+        n = gj.normal(loc=0.0, scale=0.1) @ "n"
+        return x, y, z, t, n
+
+    tr = model.simulate(gj.key(0), ())
+    for addr, name in (("x", "normal"), ("y", "bernoulli"), ("z", "flip"), ("t", "categorical")):
+        assert str(tr.get_subtrace(addr).get_gen_fn()) == f"genjax.{name}()"
+    assert abs(tr.get_choices()["n"].item()) < 1.0
+
+    @gj.gen
+    def f():
+        return gj.categorical([-0.3, -0.5]) @ "c"
+
+    @gj.gen
+    def g():
+        return gj.bernoulli(-0.4) @ "b"
+
+    with pytest.warns(DeprecationWarning, match="bare argument to genjax.categorical"):
+        f.simulate(gj.key(0), ())
+    with pytest.warns(DeprecationWarning, match="bare argument to genjax.bernoulli"):
+        g.simulate(gj.key(0), ())
