@@ -1,4 +1,6 @@
-"""TEST INFRASTRUCTURE ONLY -- a CPU emulation of the per-model C-ABI entry point ``gjb_model_launch``.
+"""TEST INFRASTRUCTURE ONLY -- a CPU emulation of the C-ABI entry points the single-device host code reaches:
+``gjb_model_launch``, ``gjb_model_mh_chain`` / ``gjb_model_hmc_chain`` and the LSE / resampling / gather calls of
+libgjb_core.
 
 Purpose: exercise the HOST side (argument binding, per-site flags, pointer tables, choice-map / trace plumbing, the
 ``Scan`` combinator, ``get_subtrace`` ...) in the CPU suite, where no CUDA device exists.  The emulator reads the very
@@ -47,6 +49,9 @@ def evaluate(e, env, cache):
         return cache[e._id]
     ins = [evaluate(i, env, cache) for i in e.ins]
     op = e.op
+    if e.shape != () and op not in ("row", "gather1", "elem", "sum"):
+        # a scalar-shaped operand that carries the particle axis broadcasts against the event axis of the result
+        ins = [v[..., None] if (i.shape == () and np.ndim(v) >= 1) else v for i, v in zip(e.ins, ins)]
     if op == "const":
         v = F32(e.attr) if e.dtype == "f32" else I32(e.attr)
     elif op == "constvec":
@@ -55,6 +60,12 @@ def evaluate(e, env, cache):
         v = env[("site", e.attr)]
     elif op == "arg":
         v = env[("arg", e.attr["index"])]
+    elif op == "chain_step":
+        v = env["step_size"]
+    elif op == "lgamma":
+        from scipy.special import gammaln
+
+        v = gammaln(ins[0]).astype(F32)
     elif op in ("row", "gather1"):
         v = ins[0][np.asarray(ins[1]).astype(np.int64)]
     elif op == "elem":
@@ -98,8 +109,9 @@ def _prod(shape):
 class EmulatedModelLib:
     """Stands in for ``ctypes.CDLL(model_<digest>.so)``: ``gjb_model_info`` and ``gjb_model_launch`` only."""
 
-    def __init__(self, ir):
+    def __init__(self, ir, chain=None):
         self.ir = ir
+        self.chain = chain
         self.launches = 0
 
     def gjb_model_info(self):
@@ -145,8 +157,13 @@ class EmulatedModelLib:
             ev = tuple(s.value.shape)
             dt = F32 if s.value.dtype == "f32" else I32
             args = [evaluate(e, env, cache) for e in s.args]
-            sample, logpdf = od.DISTS[s.dist.name]
+            if s.dist.name in od.DISTS:
+                sample, logpdf = od.DISTS[s.dist.name]
+            else:  # no oracle sampler: score through the symbolic log-density (gen/autodiff.py), refuse to sample
+                sample, logpdf = None, None
             if fl & 1:
+                if sample is None:
+                    raise NotImplementedError(f"emulator: no oracle sampler for {s.dist.name}")
                 v = np.asarray(sample(words, idx, j + 1, *args))
                 v = np.broadcast_to(v.astype(dt), (n,) + ev).copy()
             else:
@@ -159,7 +176,13 @@ class EmulatedModelLib:
                     v = _view(A.site_in[j], n * _prod(ev), dt).reshape((n,) + ev).copy()
             if need_score or (fl & 2):
                 vv = v.astype(bool) if getattr(s.dist, "bool_valued", False) else v
-                lp = np.broadcast_to(np.asarray(logpdf(vv, *args), dtype=F32), (n,))
+                if logpdf is None:
+                    from genjax_b200.gen import autodiff as AD
+
+                    env[("site", j)] = v
+                    lp = np.broadcast_to(np.asarray(evaluate(AD.logpdf_expr(s.dist, s.value, s.args), env, {}), dtype=F32), (n,))
+                else:
+                    lp = np.broadcast_to(np.asarray(logpdf(vv, *args), dtype=F32), (n,))
                 score = (score + lp).astype(F32)
                 if fl & 2:
                     weight = (weight + lp).astype(F32)
@@ -184,6 +207,127 @@ class EmulatedModelLib:
                 t = (t - _view(A.score_in, n, F32)).astype(F32)
             _view(A.weight_out, n, F32)[:] = t
         return 0
+
+
+# ------------------------------------------------------------------ chain entry points (gjb_model_mh_chain / _hmc_chain)
+
+
+def _chain_common(lib, A):
+    """(n, layout, env builder) of a chain launch: per-chain arguments and the unselected sites are constants, the
+    selected sites are columns of the state row (gen/codegen_chain.py Ctx / _layout)."""
+    ir, spec = lib.ir, lib.chain
+    n = int(A.n)
+    offs, off = {}, 0
+    for j in spec.latent:
+        sv = ir.sites[j].value
+        w = sv.shape[0] if sv.ndim else 1
+        offs[j] = (off, w)
+        off += w
+    base = {"step_size": F32(A.step_size)}
+    for i, a in enumerate(ir.args):
+        dt = F32 if a.dtype == "f32" else I32
+        if a.kind == "scalar":
+            base[("arg", i)] = dt(A.scalars[i])
+        elif a.kind == "shared":
+            base[("arg", i)] = _view(A.args[i], max(_prod(a.shape), 1), dt).reshape(a.shape).copy()
+        else:
+            base[("arg", i)] = _view(A.args[i], n * _prod(a.shape), dt).reshape((n,) + tuple(a.shape)).copy()
+    for s in ir.sites:
+        j = s.index
+        if j in spec.latent:
+            continue
+        ev = tuple(s.value.shape)
+        dt = F32 if s.value.dtype == "f32" else I32
+        if int(A.site_flags[j]) & 4:
+            base[("site", j)] = np.broadcast_to(_view(A.site_in[j], max(_prod(ev), 1), dt).reshape(ev), (n,) + ev).copy()
+        else:
+            base[("site", j)] = _view(A.site_in[j], n * _prod(ev), dt).reshape((n,) + ev).copy()
+
+    def env_of(q):
+        env = dict(base)
+        for j, (o, w) in offs.items():
+            env[("site", j)] = q[:, o] if ir.sites[j].value.ndim == 0 else q[:, o:o + w]
+        return env
+
+    return n, offs, off, env_of
+
+
+def _emulated_chain(lib, a_ref, kind):
+    from genjax_b200.gen import autodiff as AD
+    from genjax_b200.gen import expr as E
+    from oracle import mcmc as omcmc
+    from oracle import rng as orng
+
+    A = a_ref._obj
+    ir, spec = lib.ir, lib.chain
+    if spec is None:
+        return -3
+    n, offs, dtot, env_of = _chain_common(lib, A)
+    if int(A.state_width) != dtot:
+        return -1
+    logp_e = AD.model_logp(ir)
+    lat_vals = [ir.sites[j].value for j in spec.latent]
+
+    def full(v):
+        return np.broadcast_to(np.asarray(v, dtype=F32), (n,)).astype(F32)
+
+    def logp(q):
+        return full(evaluate(logp_e, env_of(np.asarray(q, dtype=F32)), {}))
+
+    state = _view(A.state, n * dtot, F32).reshape(n, dtot)
+    key = orng.KeyBatch((int(A.key0), int(A.key1)), n, int(A.idx_offset))
+    accept = not (int(A.flags) & 2)
+    if kind == "mh":
+        props = []
+        for k, j in enumerate(spec.latent):
+            mapping = spec.proposals[k] if k < len(spec.proposals) else None
+            cur = ir.sites[j].value
+            props.append((cur, E.Expr("chain_step", (), "f32", ())) if mapping is None else tuple(E.lift(x) for x in mapping(cur)))
+
+        def proposal(q):
+            env, cache = env_of(np.asarray(q, dtype=F32)), {}
+            loc, scale = np.empty((n, dtot), dtype=F32), np.empty((n, dtot), dtype=F32)
+            for (le, se), j in zip(props, spec.latent):
+                o, w = offs[j]
+                for dst, ex in ((loc, le), (scale, se)):
+                    val = np.asarray(evaluate(ex, env, cache), dtype=F32)
+                    if val.ndim >= 1 and val.shape[0] == n and ex.shape == ():
+                        val = val[:, None]
+                    dst[:, o:o + w] = np.broadcast_to(val, (n, w))
+            return loc, scale
+
+        q, lp, acc, alpha = omcmc.mh_chain(logp, state.copy(), key, int(A.n_steps), float(A.step_size), proposal, accept,
+                                           int(A.step0))
+    else:
+        try:
+            grads = AD.grad(logp_e, lat_vals)
+        except AD.NotDifferentiable:
+            return -3
+
+        def logp_grad(q):
+            env, cache = env_of(np.asarray(q, dtype=F32)), {}
+            lp = full(evaluate(logp_e, env, cache))
+            g = np.empty((n, dtot), dtype=F32)
+            for ge, j in zip(grads, spec.latent):
+                o, w = offs[j]
+                val = np.asarray(evaluate(ge, env, cache), dtype=F32)
+                if val.ndim >= 1 and val.shape[0] == n and ge.shape == ():
+                    val = val[:, None]
+                g[:, o:o + w] = np.broadcast_to(val, (n, w))
+            return lp, g
+
+        q, lp, acc, alpha = omcmc.hmc_chain(logp_grad, state.copy(), key, int(A.n_steps), float(A.step_size),
+                                            int(A.n_leapfrog), bool(A.compat_stale_grad), accept, int(A.step0))
+    state[:] = q
+    _view(A.logp, n, F32)[:] = lp
+    _view(A.accept_count, n, I32)[:] += acc.astype(I32)
+    if A.alpha_out:
+        _view(A.alpha_out, n, F32)[:] = alpha
+    return 0
+
+
+EmulatedModelLib.gjb_model_mh_chain = lambda self, a_ref, stream: _emulated_chain(self, a_ref, "mh")
+EmulatedModelLib.gjb_model_hmc_chain = lambda self, a_ref, stream: _emulated_chain(self, a_ref, "hmc")
 
 
 # ------------------------------------------------------------------ libgjb_core.so (single-device entry points)
@@ -320,9 +464,9 @@ class EmulatedCore:
 
 
 class _EmulatedCompiledModel:
-    def __init__(self, ir):
+    def __init__(self, ir, chain=None):
         self.ir = ir
-        self.lib = EmulatedModelLib(ir)
+        self.lib = EmulatedModelLib(ir, chain)
         self.path = None
         self.info = json.loads(self.lib.gjb_model_info().decode())
 
@@ -340,9 +484,12 @@ def install(monkeypatch):
 
     def compile_ir(ir, pf_obs=None, chain=None):
         ir.digest = cap.ir_fingerprint(ir)
-        return _EmulatedCompiledModel(ir)
+        return _EmulatedCompiledModel(ir, chain)
 
     monkeypatch.setattr(static, "compile_ir", compile_ir)
+    from genjax_b200.inference import mcmc
+
+    monkeypatch.setattr(mcmc, "compile_ir", compile_ir)
     core = EmulatedCore()
     monkeypatch.setattr(cabi, "core", lambda: core)
     return cpu

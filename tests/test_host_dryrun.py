@@ -13,7 +13,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 _MODEL_LAUNCH_ONLY = ("test_step_importance_matches_oracle or test_assess_kat or test_step_vec_importance_matches_oracle "
-                      "or test_regenerate_mh_convergence or test_mv_normal_simulate_importance_assess")
+                      "or test_mv_normal_simulate_importance_assess")
+# chain entry points are emulated with oracle/mcmc.py over the symbolic log-density and its reverse-mode gradient
+# (gen/autodiff.py); the 8-schools run passes too but takes a minute in NumPy, and the mixture has no oracle sampler
+_MCMC = "not eight_schools and not gmm"
 
 
 @pytest.mark.parametrize("files", [
@@ -21,7 +24,8 @@ _MODEL_LAUNCH_ONLY = ("test_step_importance_matches_oracle or test_assess_kat or
     ["tests/test_zzz_unverified_gpu.py"],
     ["tests/test_zzz_static_reference_gpu.py"],
     # the filter, chain and core-kernel tests reach entry points that exist on the GPU only; these do not
-    ["tests/test_pf_gpu.py", "tests/test_mcmc_gpu.py", "tests/test_zz_mv_normal_gpu.py", "-k", _MODEL_LAUNCH_ONLY],
+    ["tests/test_pf_gpu.py", "tests/test_zz_mv_normal_gpu.py", "-k", _MODEL_LAUNCH_ONLY],
+    ["tests/test_mcmc_gpu.py", "-k", _MCMC],
 ])
 def test_gpu_tests_host_paths_under_emulation(files):
     env = dict(os.environ, GJB_EMULATE="1", GJB_RUN_UNVERIFIED="1", CUDA_VISIBLE_DEVICES="")
