@@ -72,6 +72,7 @@ class ModelIR:
     ret_tree: Any  # structure to rebuild the retval
     width: int = 0  # vector event width D (0 = all scalar)
     digest: str = ""
+    subcalls: dict = dataclasses.field(default_factory=dict)  # address prefix of a nested @gen call -> (arg leaves, ret leaves)
 
     def site_index(self, addr: tuple) -> int:
         for s in self.sites:
@@ -91,6 +92,7 @@ class _Capture:
         self.sites: list[SiteSpec] = []
         self.prefix: tuple = ()
         self.addrs: set = set()
+        self.subcalls: dict = {}
 
     def record(self, addr, dist, args) -> Expr:
         full = self.prefix + addr
@@ -122,9 +124,12 @@ def trace_site(addr, gen_fn, args):
         old = cap.prefix
         cap.prefix = old + addr
         try:
-            return gen_fn.capture_inline(args)
+            ret = gen_fn.capture_inline(args)
         finally:
             cap.prefix = old
+        # what flows into and out of the callee: change propagation for edit requests addressed at it
+        cap.subcalls[old + addr] = (flatten(args)[0], flatten(ret)[0])
+        return ret
     return cap.record(addr, gen_fn, args)
 
 
@@ -214,7 +219,8 @@ def capture(source: Callable, name: str, arg_specs: list, arg_tree) -> ModelIR:
             widths.add(r.shape[0])
     if len(widths) > 1:
         raise NotImplementedError(f"all vector-valued choices/arguments of one model must share one width, got {widths}")
-    ir = ModelIR(name, list(arg_specs), arg_exprs, cap.sites, ret_leaves, ret_tree, width=(widths.pop() if widths else 0))
+    ir = ModelIR(name, list(arg_specs), arg_exprs, cap.sites, ret_leaves, ret_tree, width=(widths.pop() if widths else 0),
+                 subcalls=cap.subcalls)
     if len(ir.sites) > 16:
         raise NotImplementedError("more than 16 random-choice sites in one static model")
     return ir

@@ -28,6 +28,7 @@ from ..runtime import build, cabi
 from . import capture as cap
 from . import codegen
 from .capture import AddressReuse, ArgSpec, MissingAddress, ModelIR
+from . import expr as E
 from .expr import Expr, F32, I32
 from .gfi import (
     Diff,
@@ -35,10 +36,12 @@ from .gfi import (
     EditRequest,
     EmptyRequest,
     GenerativeFunction,
+    NoChange,
     NotSupportedEditRequest,
     Regenerate,
     StaticRequest,
     Trace,
+    UnknownChange,
     Update,
 )
 
@@ -751,12 +754,53 @@ def _rebatch_constraint(chm: ChoiceMap, trace: StaticTrace) -> ChoiceMap:
     return chm.map_leaves(mark)
 
 
+def _depends(exprs, moved_sites: set, changed_args: set) -> bool:
+    """Does any of ``exprs`` read a site whose value moves or a model argument that changed?"""
+    roots = [e for e in exprs if isinstance(e, Expr)]
+    for node in E.topo(roots):
+        if node.op == "site" and node.attr in moved_sites:
+            return True
+        if node.op == "arg" and node.attr["index"] in changed_args:
+            return True
+    return False
+
+
+def _changed_arg_leaves(argdiffs) -> set:
+    """Indices of the flattened model-argument leaves whose ``Diff`` tangent is not NoChange."""
+    if argdiffs is None or argdiffs == ():
+        return set()
+    leaves, _ = cap.flatten(Diff._map(argdiffs, lambda v: v if isinstance(v, Diff) else Diff(v, UnknownChange)))
+    return {i for i, v in enumerate(leaves) if isinstance(v, Diff) and v.tangent is not NoChange}
+
+
+def _callee_diffs(ir: ModelIR, addr: tuple, moved: set, changed_args: set):
+    """(argdiffs, retdiff) of the callee at ``addr`` -- a distribution site or a nested @gen call -- as trees of
+    ``Diff(None, tangent)``: the static change propagation the reference does with ``Diff`` values
+    (core/compiler/interpreters/incremental.py) restricted to changed / unchanged."""
+
+    def d(flag):
+        return Diff(None, UnknownChange if flag else NoChange)
+
+    for s in ir.sites:
+        if s.addr == addr:
+            return tuple(d(_depends([a], moved, changed_args)) for a in s.args), d(s.index in moved)
+    if addr in ir.subcalls:
+        args, rets = ir.subcalls[addr]
+        return (tuple(d(_depends([a], moved, changed_args)) for a in args),
+                tuple(d(_depends([r], moved, changed_args)) for r in rets))
+    raise MissingAddress(addr[0] if len(addr) == 1 else addr)
+
+
 def _collect_static_request(request: StaticRequest, prefix: tuple, out: dict) -> None:
-    """Flatten (possibly nested) per-address sub-requests into one constraint, one selection list and the rest."""
+    """Flatten (possibly nested) per-address sub-requests into one constraint, one selection list, the custom
+    requests and the ``DiffAnnotate`` callbacks addressed along the way."""
     from ..core.choice_map import _norm_addr
 
     for addr, sub in request.addressed.items():
         a = prefix + _norm_addr(addr)
+        while isinstance(sub, DiffAnnotate):
+            out["annot"].append((a, sub.argdiff_fn, sub.retdiff_fn))
+            sub = sub.request
         if isinstance(sub, Update):
             out["constraint"] = out["constraint"] | ChoiceMap.entry(sub.constraint, *a)
         elif isinstance(sub, Regenerate):
@@ -772,36 +816,59 @@ def _collect_static_request(request: StaticRequest, prefix: tuple, out: dict) ->
 def _edit_static_request(gf, key, trace, request: StaticRequest, argdiffs):
     """StaticRequest (static.py:512-566, 867-904): per-address sub-requests, nested ones included.
     Update / Regenerate sub-requests fuse into ONE launch (constrained sites read, selected sites resampled, every
-    site re-scored); other sub-requests (Rejuvenate, HMC) are delegated to their own batched drivers."""
-    out = {"constraint": ChoiceMap.empty(), "selected": [], "custom": []}
+    site re-scored); Rejuvenate / HMC sub-requests run on their own batched drivers, in the order given, before
+    it; ``DiffAnnotate`` callbacks see the changed / unchanged pattern of their callee's arguments and return value."""
+    out = {"constraint": ChoiceMap.empty(), "selected": [], "custom": [], "annot": []}
     _collect_static_request(request, (), out)
-    constraint, selected, custom = out["constraint"], out["selected"], out["custom"]
-    if custom:
-        if len(custom) > 1 or selected or not constraint.static_is_empty():
-            raise NotSupportedEditRequest(request)
-        a, sub = custom[0]
-        return sub.edit_at(key, trace, a, argdiffs)
+    constraint, selected, custom, annot = out["constraint"], out["selected"], out["custom"], out["annot"]
+    ir = trace.cm.ir
     sel = Selection.none()
     for s in selected:
         sel = sel | s
+
+    if annot:
+        moved = {s.index for s in ir.sites if sel(s.addr).check() or constraint.get_submap(*s.addr).has_value()}
+        for a, sub in custom:
+            moved |= set(sub.moved_sites(trace, a))
+        changed_args = _changed_arg_leaves(argdiffs)
+        for a, argdiff_fn, retdiff_fn in annot:
+            adiff, rdiff = _callee_diffs(ir, a, moved, changed_args)
+            argdiff_fn(adiff)
+            retdiff_fn(rdiff[0] if isinstance(rdiff, tuple) and len(rdiff) == 1 else rdiff)
+
+    weight, bwd = None, ChoiceMap.empty()
+    for a, sub in custom:
+        if not hasattr(sub, "edit_at"):
+            raise NotSupportedEditRequest(request)
+        trace, w, _, b = sub.edit_at(key, trace, a, argdiffs)
+        weight = w if weight is None else weight + w
+        bwd = bwd | b.constraint  # the oldest discarded value wins: undoing goes back to the start
+        argdiffs = ()  # the following steps start from the arguments the first one installed
+    if custom and not selected and constraint.static_is_empty():
+        return trace, weight, Diff.unknown_change(trace.get_retval()), Update(bwd)
+
     if not selected:
-        return gf.edit(key, trace, Update(constraint), argdiffs)
-    if constraint.static_is_empty():
-        return gf.edit(key, trace, Regenerate(sel), argdiffs)
-    # both kinds at once: the backward request restores every touched site (distribution.py:179-300)
-    new_args = Diff.tree_primal(argdiffs) if argdiffs is not None and argdiffs != () else trace.args
-    if new_args == () and trace.args != ():
-        new_args = trace.args
-    new_args = _carry_batch_marks(new_args, trace.args)
-    sites = trace.cm.ir.sites
-    sel_addrs = {s.addr for s in sites if sel(s.addr).check() and not constraint.get_submap(*s.addr).has_value()}
-    tr, w = gf._run(key, new_args, _rebatch_constraint(constraint, trace), prev=trace, sample_addrs=sel_addrs,
-                    weight_mode="delta", n=trace.n, batched=trace.batched)
-    discard = ChoiceMap.empty()
-    for s in sites:
-        if s.addr in sel_addrs or constraint.get_submap(*s.addr).has_value():
-            discard = discard | ChoiceMap.entry(trace._site_value(s), *s.addr)
-    return tr, gf._w(tr, w), Diff.unknown_change(tr.get_retval()), Update(discard)
+        tr, w, rd, b = gf.edit(key, trace, Update(constraint), argdiffs)
+    elif constraint.static_is_empty():
+        tr, w, rd, b = gf.edit(key, trace, Regenerate(sel), argdiffs)
+    else:
+        # both kinds at once: the backward request restores every touched site (distribution.py:179-300)
+        new_args = Diff.tree_primal(argdiffs) if argdiffs is not None and argdiffs != () else trace.args
+        if new_args == () and trace.args != ():
+            new_args = trace.args
+        new_args = _carry_batch_marks(new_args, trace.args)
+        sel_addrs = {s.addr for s in ir.sites if sel(s.addr).check() and not constraint.get_submap(*s.addr).has_value()}
+        tr, w = gf._run(key, new_args, _rebatch_constraint(constraint, trace), prev=trace, sample_addrs=sel_addrs,
+                        weight_mode="delta", n=trace.n, batched=trace.batched)
+        discard = ChoiceMap.empty()
+        for s in ir.sites:
+            if s.addr in sel_addrs or constraint.get_submap(*s.addr).has_value():
+                discard = discard | ChoiceMap.entry(trace._site_value(s), *s.addr)
+        w, rd, b = gf._w(tr, w), Diff.unknown_change(tr.get_retval()), Update(discard)
+    if weight is not None:
+        w = weight + w
+        b = Update(bwd | b.constraint)
+    return tr, w, rd, b
 
 
 def gen(source: Callable) -> StaticGenerativeFunction:

@@ -229,6 +229,9 @@ class Rejuvenate(EditRequest):
             self._mapped = mapping
         return self._mapped
 
+    def moved_sites(self, trace: StaticTrace, addr: tuple) -> tuple:
+        return _selected_sites(trace, Selection.all().extend(*addr))
+
     def edit_at(self, key, trace: StaticTrace, addr: tuple, argdiffs):
         if not Diff.static_check_no_change(argdiffs if argdiffs not in (None, ()) else ()):
             raise NotImplementedError("Rejuvenate with changed arguments")
@@ -257,10 +260,14 @@ class HMC(EditRequest):
         self.eps = float(eps)
         self.L = int(L)
 
-    def edit(self, key, tr: StaticTrace, argdiffs):
+    def moved_sites(self, trace: StaticTrace, addr: tuple = ()) -> tuple:
+        return _selected_sites(trace, self.selection.extend(*addr))
+
+    def edit_at(self, key, tr: StaticTrace, addr: tuple, argdiffs):
+        """The move on the callee at ``addr`` (``StaticRequest({addr: HMC(...)})``): the selection is relative to it."""
         assert Diff.static_check_no_change(argdiffs if argdiffs not in (None, ()) else ()), \
             "HMC needs unchanged arguments (hmc.py:163)"
-        latent = _selected_sites(tr, self.selection)
+        latent = self.moved_sites(tr, addr)
         res = _run_chain("hmc", key, tr, latent, (), n_steps=1, step_size=self.eps, n_leapfrog=self.L,
                          compat_stale_grad=True, accept=False)
         old = ChoiceMap.empty()
@@ -268,14 +275,23 @@ class HMC(EditRequest):
             s = tr.cm.ir.sites[j]
             old = old | ChoiceMap.entry(tr._site_value(s), *s.addr)
         w = res.alpha if tr.batched else res.alpha[0]
-        return res.trace, w, Diff.no_change(res.trace.get_retval()), Update(old)
+        # the return value changes exactly when it reads a moved choice (the retdiff HMC's inner Update reports)
+        from ..gen.static import _depends
 
-
-class SafeHMC(HMC):
-    """hmc.py:214-223: HMC that first checks the selection only addresses float choices."""
+        ret = res.trace.get_retval()
+        changed = _depends(tr.cm.ir.ret_leaves, set(latent), set())
+        return res.trace, w, (Diff.unknown_change(ret) if changed else Diff.no_change(ret)), Update(old)
 
     def edit(self, key, tr: StaticTrace, argdiffs):
-        for j in _selected_sites(tr, self.selection):
-            if tr.cm.ir.sites[j].value.dtype != "f32":
-                raise TypeError(f"SafeHMC: address {tr.cm.ir.sites[j].addr} is not float valued")
-        return super().edit(key, tr, argdiffs)
+        return self.edit_at(key, tr, (), argdiffs)
+
+
+def SafeHMC(selection: Selection, eps, L: int = 10):
+    """hmc.py:214-223: ``HMC(...).map(retdiff_assertion)`` -- an HMC move that asserts the return value of the
+    generative function it is addressed at does not change (it must not read a moved choice)."""
+
+    def retdiff_assertion(retdiff):
+        assert Diff.static_check_no_change(retdiff), "SafeHMC: the return value depends on a moved choice"
+        return retdiff
+
+    return HMC(selection, eps, L).map(retdiff_assertion)

@@ -500,3 +500,77 @@ def test_distribution_repr_kwargs_and_warnings(device):
         f.simulate(gj.key(0), ())
     with pytest.warns(DeprecationWarning, match="bare argument to genjax.bernoulli"):
         g.simulate(gj.key(0), ())
+
+
+# ------------------------------------------------------------------ tests/inference/test_requests.py (composition)
+
+
+def test_safe_hmc_and_composed_requests(device):
+    """TestHMC.test_safe_hmc: HMC addressed at a nested call, composed with Regenerate / Update, and the retdiff
+    assertion when the callee's return value is moved."""
+    gj = _gj()
+    from genjax_b200.inference.requests import SafeHMC
+
+    @gj.gen
+    def submodel():
+        x = gj.normal(0.0, 1.0) @ "x"
+        y = gj.normal(x, 0.01) @ "y"
+        return y
+
+    @gj.gen
+    def model():
+        submodel() @ "x"
+        submodel() @ "y"
+
+    tr, _ = model.importance(gj.key(0), gj.ChoiceMap.kw(y=3.0), ())
+    request = gj.StaticRequest({"x": SafeHMC(gj.Selection.at["x"], 1e-2)})
+    new_tr, w, *_ = request.edit(gj.key(1), tr, ())
+    assert new_tr.get_choices()["x", "x"] != tr.get_choices()["x", "x"] and w != 0.0
+    assert new_tr.get_choices()["x", "y"] == tr.get_choices()["x", "y"]
+
+    request = gj.StaticRequest({
+        "x": SafeHMC(gj.Selection.at["x"], 1e-2),
+        "y": gj.StaticRequest({"x": gj.Regenerate(gj.Selection.all()), "y": gj.Update(gj.ChoiceMap.choice(3.0))}),
+    })
+    new_tr, w, _, bwd = request.edit(gj.key(2), tr, ())
+    assert new_tr.get_choices()["x", "x"] != tr.get_choices()["x", "x"]
+    assert new_tr.get_choices()["y", "x"] != tr.get_choices()["y", "x"]
+    assert new_tr.get_choices()["y", "y"] == 3.0 and w != 0.0
+    back, _, _, _ = bwd.edit(gj.key(3), new_tr, ())
+    assert back.get_choices() == tr.get_choices()
+
+    with pytest.raises(Exception):  # moving "y" moves the return value of the callee at "x"
+        gj.StaticRequest({"x": SafeHMC(gj.Selection.at["y"], 1e-2)}).edit(gj.key(4), tr, ())
+
+
+def test_diff_annotate_inside_static_requests(device):
+    """TestDiffCoercion.test_diff_coercion: DiffAnnotate callbacks see the change pattern of their callee."""
+    gj = _gj()
+
+    @gj.gen
+    def simple_normal():
+        y1 = gj.normal(0.0, 1.0) @ "y1"
+        y2 = gj.normal(y1, 1.0) @ "y2"
+        return y1 + y2
+
+    tr = simple_normal.simulate(gj.key(314159), ())
+
+    def assert_no_change(v):
+        assert gj.Diff.static_check_no_change(v)
+        return v
+
+    request = gj.StaticRequest({
+        "y1": gj.Regenerate(gj.Selection.all()),
+        "y2": gj.DiffAnnotate(gj.EmptyRequest(), argdiff_fn=assert_no_change),
+    })
+    with pytest.raises(AssertionError):  # y2's argument reads the regenerated y1
+        request.edit(gj.key(1), tr, ())
+
+    unwrapped = gj.StaticRequest({"y1": gj.Regenerate(gj.Selection.all())})
+    wrapped = gj.StaticRequest({
+        "y1": gj.Regenerate(gj.Selection.all()).contramap(assert_no_change),
+        "y2": gj.EmptyRequest().map(assert_no_change),
+    })
+    _, w, _, _ = unwrapped.edit(gj.key(1), tr, ())
+    _, w_, _, _ = wrapped.edit(gj.key(1), tr, ())
+    assert w == w_
