@@ -460,6 +460,28 @@ class StaticGenerativeFunction(GenerativeFunction):
             self._kwarged = out
         return self._kwarged
 
+    def dimap(self, *, pre: Callable = lambda *args: args, post: Callable = lambda _args, _xformed, retval: retval):
+        """``gen_fn.dimap(pre=, post=)`` (generative_function.py:1339-1389; combinators/dimap.py): ``pre`` maps the
+        arguments (and must return a tuple), ``post(args, transformed_args, retval)`` maps the return value.  Both
+        are traced into the fused kernel with the body; the choices keep their addresses."""
+        src = self.source
+
+        def wrapped(*args):
+            xformed = tuple(pre(*args))
+            return post(args, xformed, src(*xformed))
+
+        out = StaticGenerativeFunction(wrapped, self.partial_args)
+        out.__name__ = f"{self.__name__}_dimap"
+        return out
+
+    def map(self, f: Callable):
+        """``gen_fn.map(f)``: post-process the return value (generative_function.py:1391-1427)."""
+        return self.dimap(post=lambda _args, _xformed, retval: f(retval))
+
+    def contramap(self, f: Callable):
+        """``gen_fn.contramap(f)``: pre-process the arguments; ``f`` returns a tuple (generative_function.py:1429-1467)."""
+        return self.dimap(pre=f)
+
     def inline(self, *args):
         """``callee.inline(*args)`` inside an ``@gen`` body: the callee's choices are recorded at the CALLER's
         address level (static.py ``inline``; test_static_gen_fn.py:949-1087)."""

@@ -574,3 +574,44 @@ def test_diff_annotate_inside_static_requests(device):
     _, w, _, _ = unwrapped.edit(gj.key(1), tr, ())
     _, w_, _, _ = wrapped.edit(gj.key(1), tr, ())
     assert w == w_
+
+
+# ------------------------------------------------------------------ tests/generative_functions/test_dimap_combinator.py
+
+
+def test_dimap_map_contramap(device):
+    """TestDimap.test_dimap_update_retval."""
+    gj = _gj()
+
+    def pre_process(x, y):
+        return (x + 1, y * 2, y * 3)
+
+    def post_process(_args, _xformed, retval):
+        assert len(_args) == 2 and len(_xformed) == 3
+        return retval + 2
+
+    @gj.gen
+    def model(x, y, _):
+        return gj.normal(x, y) @ "z"
+
+    dm = model.dimap(pre=pre_process, post=post_process)
+    tr = dm.simulate(gj.key(0), (2.0, 3.0))
+    z = tr.get_choices()["z"]
+    assert tr.get_retval().item() == pytest.approx(z.item() + 2.0, abs=1e-6)
+    score, ret = dm.assess(tr.get_choices(), (2.0, 3.0))
+    assert score.item() == pytest.approx(tr.get_score().item(), abs=1e-6) and ret == tr.get_retval()
+    assert tr.get_score().item() == pytest.approx(_lp(z, 3.0, 6.0), abs=1e-5)  # pre-processing is seen by the score
+    up, _, _, _ = tr.update(gj.key(1), gj.C["z"].set(-2.0))
+    assert up.get_retval() == 0.0
+    imp, _ = dm.importance(gj.key(2), up.get_choices(), (1.0, 2.0))
+    assert imp.get_retval() == up.get_retval()
+    assert imp.get_score().item() == pytest.approx(_lp(-2.0, 2.0, 4.0), abs=1e-5)
+
+    @gj.gen
+    def one(x):
+        return gj.normal(x, 1.0) @ "z"
+
+    sq = one.map(lambda r: r * r).simulate(gj.key(3), (0.5,))
+    assert sq.get_retval().item() == pytest.approx(sq.get_choices()["z"].item() ** 2, rel=1e-6)
+    shifted = one.contramap(lambda x: (x + 1,)).importance(gj.key(4), gj.C["z"].set(0.0), (0.5,))[1]
+    assert shifted.item() == pytest.approx(_lp(0.0, 1.5, 1.0), abs=1e-6)
