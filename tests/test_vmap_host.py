@@ -134,3 +134,29 @@ def test_vmap_validation(emu):  # test_vmap_validation
         foo.vmap(in_axes=0).simulate(gj.key(0), (torch.arange(2.0), torch.arange(3.0)))
     with pytest.raises(NotImplementedError):
         foo.vmap(in_axes=(0, None)).simulate(gj.split(gj.key(0), 4), (torch.arange(2.0), 1.0))
+
+
+def test_closure_call_zero_length_and_repeat_importance(emu):
+    """test_repeat_combinator_importance / test_repeat_matches_vmap (with one choice per call) / test_zero_length_vmap."""
+    @gj.gen
+    def model():
+        return gj.normal(0.0, 1.0) @ "x"
+
+    tr, w = model.repeat(n=10).importance(gj.key(314), C[1, "x"].set(3.0), ())
+    assert w.item() == pytest.approx(_lp(tr.get_choices()[1, "x"].item(), 0.0), rel=1e-6) and tr.get_choices()[1, "x"] == 3.0
+
+    @gj.gen
+    def noisy_square(x):
+        return x * x + 0.0 * (gj.normal(0.0, 1.0) @ "eps")
+
+    rep = noisy_square.repeat(n=10)(2.0)(gj.key(314))
+    assert rep.shape == (10,) and torch.equal(rep, torch.full((10,), 4.0))
+    assert torch.equal(noisy_square.vmap()(torch.full((10,), 2.0))(gj.key(314)), rep)
+
+    @gj.gen
+    def step(state, sigma):
+        new_x = gj.normal(state, sigma) @ "x"
+        return new_x, new_x + 1
+
+    empty = step.vmap(in_axes=(None, 0)).simulate(gj.key(20), (2.0, torch.zeros(0)))
+    assert empty.get_choices().static_is_empty() and empty.get_score().item() == 0.0
