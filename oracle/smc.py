@@ -133,6 +133,39 @@ def resample_systematic(logw, key: rng.Key):
     return np.repeat(np.arange(n, dtype=np.int32), (cnt - prev).astype(np.int64))
 
 
+def resample_systematic_pull(logw, key: rng.Key, M=None, out_lo=0, out_n=None):
+    """The same ancestors as ``resample_systematic``, resolved per OUTPUT slot: slot j takes the first particle i
+    whose cumulative count exceeds j (``cnt_i > j``).  This is the formulation in which a CTA owns a range of
+    offspring slots (and can go on to propagate them) instead of a range of parents; ``M`` may be any reference
+    >= max(logw) known before the weights are (an analytic upper bound of the incremental weight) -- the masses,
+    hence the ancestors, are then a deterministic function of (logw, M) and the max pass disappears."""
+    logw = np.asarray(logw, dtype=F32)
+    n = len(logw)
+    out_n = n - out_lo if out_n is None else out_n
+    u0 = resample_u0(key)
+    if M is None:
+        M, S = lse_terms(logw)
+    else:
+        with np.errstate(invalid="ignore"):
+            S = int(det_exp_q((logw - F32(M)).astype(F32)).sum(dtype=U64))
+    cnt, _ = systematic_counts(logw, u0, M=M, S=S)
+    j = np.arange(out_lo, out_lo + out_n, dtype=np.int64)
+    if cnt is None:
+        return j.astype(np.int32)
+    return np.searchsorted(cnt, j, side="right").astype(np.int32)
+
+
+def log_mean_exp_ref(logw, M, n_total=None):
+    """``log_mean_exp`` with the masses taken relative to a given reference ``M >= max(logw)``."""
+    logw = np.asarray(logw, dtype=F32)
+    with np.errstate(invalid="ignore"):
+        S = int(det_exp_q((logw - F32(M)).astype(F32)).sum(dtype=U64))
+    n = len(logw) if n_total is None else n_total
+    if S == 0:
+        return -math.inf
+    return float(F32(M)) + math.log(S) - Q_BITS * math.log(2.0) - math.log(n)
+
+
 def _mulhi64(a, b):
     """floor(a*b / 2^64) for uint64 arrays / scalars (32-bit limbs)."""
     a = np.asarray(a, dtype=U64)
