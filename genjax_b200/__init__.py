@@ -43,6 +43,7 @@ from .gen.gfi import (
     EditRequest,
     EmptyRequest,
     GenerativeFunction,
+    IndexRequest,
     NoChange,
     NotSupportedEditRequest,
     Regenerate,

@@ -172,6 +172,18 @@ class Regenerate(PrimitiveEditRequest):
         return f"Regenerate({self.selection!r})"
 
 
+class IndexRequest(EditRequest):
+    """``IndexRequest(index, request)`` (generative_function.py ``IndexRequest``): apply ``request`` to ONE index of a
+    vectorised trace (``Vmap`` lane, ``Scan`` step); handled by those combinators' ``edit``."""
+
+    def __init__(self, index, request: EditRequest):
+        self.index = int(index)
+        self.request = request
+
+    def __repr__(self):
+        return f"IndexRequest({self.index}, {self.request!r})"
+
+
 class StaticRequest(EditRequest):
     """static.py:130-131: per-address sub-requests."""
 

@@ -36,12 +36,13 @@ from .gfi import (
     Diff,
     EditRequest,
     GenerativeFunction,
+    IndexRequest,
     NotSupportedEditRequest,
     Regenerate,
     Trace,
     Update,
 )
-from .static import Batched, StaticGenerativeFunction, _dev_tensor, _is_scalar_number, cap_norm
+from .static import Batched, StaticGenerativeFunction, _depends, _dev_tensor, _is_scalar_number, cap_norm
 
 __all__ = ["Scan", "ScanTrace", "scan", "accumulate", "reduce", "iterate", "iterate_final"]
 
@@ -345,7 +346,49 @@ class Scan(GenerativeFunction):
             tot = torch.zeros_like(trace.score)
         return tot if trace.batched else tot[0]
 
+    def _edit_index(self, key, trace: ScanTrace, request: IndexRequest, argdiffs):
+        """scan.py:329-415: the sub-request runs on step ``index`` with unchanged arguments; the next step is
+        re-visited with the new carry, and -- like the reference -- the edit is only allowed when the carry LEAVING
+        the kernel does not read the carry entering it (otherwise every later step would have to move)."""
+        if not Diff.static_check_no_change(argdiffs if argdiffs not in (None, ()) else ()):
+            raise AssertionError("IndexRequest needs unchanged arguments (scan.py:339)")
+        idx = request.index
+        T = trace.scan_length
+        if not 0 <= idx < T:
+            raise AssertionError(f"index {idx} is outside the scan of length {T}")
+        device = cabi.require_cuda()
+        n = trace.n
+        old = trace.inner[idx]
+        ir = old.cm.ir
+        n_carry = len(cap.flatten(old.args[0])[0])
+        ret_carry = cap.flatten(cap.unflatten(ir.ret_tree, list(ir.ret_leaves))[0])[0]
+        assert not _depends(ret_carry, set(), set(range(n_carry))), \
+            "IndexRequest on a scan needs a kernel whose outgoing carry does not read the incoming one (scan.py:368-372)"
+        new_step, w, _, bwd = self.kernel_gen_fn.edit(key, old, request.request, Diff.no_change(old.args))
+        inner = list(trace.inner)
+        ys = list(trace.ys)
+        inner[idx] = new_step
+        carry, ys[idx] = new_step.get_retval()
+        carry = _carry_next(carry, n, device)
+        score = trace.score - old.score + new_step.score
+        w = w.reshape(-1) if isinstance(w, torch.Tensor) else w
+        if idx + 1 < T:
+            nxt = trace.inner[idx + 1]
+            nxt_args = (carry, nxt.args[1])
+            new_next, w2, _, _ = self.kernel_gen_fn.edit(key, nxt, Update(ChoiceMap.empty()), Diff.unknown_change(nxt_args))
+            inner[idx + 1] = new_next
+            _, ys[idx + 1] = new_next.get_retval()
+            score = score - nxt.score + new_next.score
+            w = w + w2.reshape(-1)
+            carry_out = trace.carry_out  # unchanged by the assertion above
+        else:
+            carry_out = carry
+        new = ScanTrace(self, inner, trace.args, carry_out, ys, score, n, trace.batched)
+        return new, (w if trace.batched else w[0]), Diff.unknown_change(new.get_retval()), IndexRequest(idx, bwd)
+
     def edit(self, key, trace: ScanTrace, request: EditRequest, argdiffs):
+        if isinstance(request, IndexRequest):
+            return self._edit_index(key, trace, request, argdiffs)
         if not isinstance(request, (Update, Regenerate)):
             if hasattr(request, "edit") and type(request).edit is not EditRequest.edit:
                 return request.edit(key, trace, argdiffs)

@@ -26,8 +26,8 @@ from ..core.choice_map import ChoiceMap, Selection
 from ..core.key import KeyBatch, PRNGKey, split
 from ..runtime import cabi
 from . import capture as cap
-from .gfi import Diff, EditRequest, GenerativeFunction, NotSupportedEditRequest, Regenerate, Trace, Update
-from .static import Batched, StaticGenerativeFunction, _dev_tensor
+from .gfi import Diff, EditRequest, GenerativeFunction, IndexRequest, NotSupportedEditRequest, Regenerate, Trace, Update
+from .static import Batched, StaticGenerativeFunction, StaticTrace, _dev_tensor
 
 __all__ = ["Vmap", "VmapTrace", "vmap_combinator", "repeat"]
 
@@ -76,6 +76,34 @@ def _mark_arg(tree, axes, sizes: list, device):
 def _slice_args(tree, lo: int, hi: int):
     leaves, shape = cap.flatten(tree)
     return cap.unflatten(shape, [Batched(v.value[lo:hi].contiguous()) if isinstance(v, Batched) else v for v in leaves])
+
+
+def replace_lane(inner: StaticTrace, idx: int, one: StaticTrace) -> StaticTrace:
+    """``tree_map(lambda v, v_: v.at[idx].set(v_), inner, one)`` (vmap.py:330-332): a copy of ``inner`` whose lane
+    ``idx`` holds the one-lane trace ``one``; traces are immutable, so every leaf is cloned."""
+    ir = inner.cm.ir
+    n = inner.n
+    values = {}
+    for s in ir.sites:
+        j = s.index
+        ev = tuple(s.value.shape)
+        full = inner.values[j]
+        full = full.reshape(ev).expand((n,) + ev) if inner.bcast[j] else full
+        full = full.clone()
+        full[idx] = one.values[j].reshape((-1,) + ev)[0]
+        values[j] = full
+    rets = []
+    for ra, rb in zip(inner.ret_leaves, one.ret_leaves):
+        if isinstance(ra, torch.Tensor):
+            r = ra.clone()
+            r[idx] = rb.reshape((-1,) + tuple(ra.shape[1:]))[0]
+            rets.append(r)
+        else:
+            rets.append(ra)
+    score = inner.score.clone()
+    score[idx] = one.score.reshape(-1)[0]
+    return StaticTrace(inner.gen_fn, inner.cm, inner.bound, inner.args, n, True, values, score, rets,
+                       {j: False for j in values})
 
 
 class VmapTrace(Trace):
@@ -227,7 +255,24 @@ class Vmap(GenerativeFunction):
     def project(self, key, trace: VmapTrace, selection: Selection):
         return self.gen_fn.project(key, trace.inner, selection).sum()
 
+    def _edit_index(self, key, trace: VmapTrace, request: IndexRequest, argdiffs):
+        """vmap.py:277-336: the sub-request runs on lane ``index`` alone, with ``key`` itself."""
+        if not Diff.static_check_no_change(argdiffs if argdiffs not in (None, ()) else ()):
+            raise AssertionError("IndexRequest needs unchanged arguments (vmap.py:285)")
+        idx = request.index
+        if not 0 <= idx < trace.dim_length:
+            raise AssertionError(f"index {idx} is outside the mapped axis of length {trace.dim_length}")
+        _, marked, n = self._bind(None, trace.args)
+        lane = trace.inner.take(torch.tensor([idx], device=trace.inner.score.device))
+        new_lane, w, _, bwd = self.gen_fn.edit(key, lane, request.request, Diff.no_change(_slice_args(marked, idx, idx + 1)))
+        inner = replace_lane(trace.inner, idx, new_lane)
+        inner.args = marked
+        new = VmapTrace(self, inner, trace.args, n)
+        return new, w.reshape(-1)[0], Diff.unknown_change(new.get_retval()), IndexRequest(idx, bwd)
+
     def edit(self, key, trace: VmapTrace, request: EditRequest, argdiffs):
+        if isinstance(request, IndexRequest):
+            return self._edit_index(key, trace, request, argdiffs)
         if not isinstance(request, (Update, Regenerate)):
             if hasattr(request, "edit") and type(request).edit is not EditRequest.edit:
                 return request.edit(key, trace, argdiffs)

@@ -160,3 +160,56 @@ def test_closure_call_zero_length_and_repeat_importance(emu):
 
     empty = step.vmap(in_axes=(None, 0)).simulate(gj.key(20), (2.0, torch.zeros(0)))
     assert empty.get_choices().static_is_empty() and empty.get_score().item() == 0.0
+
+
+def test_index_request_on_vmap_and_scan(emu):
+    """TestVmapIndexRequest / TestScanIndexRequest (top-level form): the sub-request touches one index only."""
+    @gj.gen
+    def cell(mu):
+        return gj.normal(mu, 1.0) @ "z"
+
+    model = cell.vmap()
+    over = torch.zeros(6)
+    tr = model.simulate(gj.key(314159), (over,))
+    old = tr.get_choices()[:, "z"]
+    for idx in range(6):
+        new, w, _, bwd = model.edit(gj.key(7), tr, gj.IndexRequest(idx, gj.Regenerate(gj.S["z"])), gj.Diff.no_change((over,)))
+        z = new.get_choices()[:, "z"]
+        keep = [i for i in range(6) if i != idx]
+        assert z[idx] != old[idx] and torch.equal(z[keep], old[keep])
+        assert w.item() == pytest.approx(_lp(z[idx].item(), 0.0) - _lp(old[idx].item(), 0.0), rel=1e-4, abs=1e-5)
+        assert isinstance(bwd, gj.IndexRequest) and bwd.index == idx
+        back, wb, _, _ = model.edit(gj.key(8), new, bwd, gj.Diff.no_change((over,)))
+        assert torch.equal(back.get_choices()[:, "z"], old) and (w + wb).item() == pytest.approx(0.0, abs=1e-5)
+        upd, wu, _, _ = model.edit(gj.key(9), tr, gj.IndexRequest(idx, gj.Update(C["z"].set(idx + 7.0))), gj.Diff.no_change((over,)))
+        assert upd.get_choices()[idx, "z"] == idx + 7.0
+        assert wu.item() == pytest.approx(_lp(idx + 7.0, 0.0) - _lp(old[idx].item(), 0.0), rel=1e-4, abs=1e-4)
+    with pytest.raises(AssertionError):
+        model.edit(gj.key(7), tr, gj.IndexRequest(11, gj.Regenerate(gj.S["z"])), gj.Diff.no_change((over,)))
+
+    @gj.gen
+    def kernel(carry, _):
+        z = gj.normal(0.0, 1.0) @ "z"
+        return z, None
+
+    chain = kernel.scan(n=10)
+    tr = chain.simulate(gj.key(1), (0.0, None))
+    old = tr.get_choices()[:, "z"]
+    for idx in (0, 4, 9):
+        new, w, _, _ = chain.edit(gj.key(2), tr, gj.IndexRequest(idx, gj.Regenerate(gj.S["z"])), gj.Diff.no_change((0.0, None)))
+        z = new.get_choices()[:, "z"]
+        keep = [i for i in range(10) if i != idx]
+        assert z[idx] != old[idx] and torch.equal(z[keep], old[keep])
+        assert w.item() == pytest.approx(_lp(z[idx].item(), 0.0) - _lp(old[idx].item(), 0.0), rel=1e-4, abs=1e-5)
+        assert new.get_score().item() == pytest.approx(sum(_lp(v.item(), 0.0) for v in z), rel=1e-5)
+    with pytest.raises(AssertionError):
+        chain.edit(gj.key(2), tr, gj.IndexRequest(11, gj.Regenerate(gj.S["z"])), gj.Diff.no_change((0.0, None)))
+
+    @gj.gen
+    def walk(carry, _):
+        z = gj.normal(carry, 1.0) @ "z"
+        return z + carry, None  # the outgoing carry reads the incoming one: every later step would move
+
+    wtr = walk.scan(n=4).simulate(gj.key(3), (0.0, None))
+    with pytest.raises(AssertionError):
+        walk.scan(n=4).edit(gj.key(4), wtr, gj.IndexRequest(1, gj.Regenerate(gj.S["z"])), gj.Diff.no_change((0.0, None)))
