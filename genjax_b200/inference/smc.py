@@ -72,6 +72,54 @@ class ParticleCollection:
         w = torch.exp(lw)
         return w.sum() ** 2 / (w * w).sum()
 
+    # -- checkpointing (the on-disk side of a resumable run) ----
+    def state_dict(self) -> dict:
+        """Everything needed to rebuild this collection, as CPU tensors and plain Python values: the log-weights
+        and, per address, the particles' choices.  The trace itself (score, return value, per-site log-densities)
+        is NOT stored: ``load_state_dict`` recomputes it from the choices with one assess-mode launch of the model
+        kernel, so a checkpoint stays valid across kernel / layout changes."""
+        tr = self.particles
+        choices = {}
+        for s in tr.cm.ir.sites:
+            v = tr.values[s.index]
+            choices["/".join(str(a) for a in s.addr)] = {"value": v.detach().cpu(), "shared": bool(tr.bcast[s.index])}
+        lse = self.lse_terms().detach().cpu()
+        return {
+            "format": "genjax_b200.ParticleCollection/1",
+            "n": int(self.log_weights.numel()),
+            "model": tr.get_gen_fn().__name__,
+            "addresses": [list(s.addr) for s in tr.cm.ir.sites],
+            "log_weights": self.log_weights.detach().cpu(),
+            "choices": choices,
+            "is_valid": bool(self.is_valid) if not isinstance(self.is_valid, torch.Tensor) else bool(self.is_valid.item()),
+            "diagnostics": {"log_marginal_likelihood": float(lse[2]), "ess": float(self.effective_sample_size().item())},
+        }
+
+    @staticmethod
+    def load_state_dict(gen_fn, args: tuple, state: dict) -> "ParticleCollection":
+        """Rebuild a collection saved by ``state_dict`` for the model ``gen_fn`` called with ``args`` (per-particle
+        arguments marked as in the original run, e.g. ``gj.Batched(x_prev)``)."""
+        from ..runtime import cabi
+
+        if state.get("format") != "genjax_b200.ParticleCollection/1":
+            raise ValueError("not a genjax_b200 ParticleCollection checkpoint")
+        device = cabi.require_cuda()
+        n = int(state["n"])
+        chm = ChoiceMap.empty()
+        for addr in state["addresses"]:
+            entry = state["choices"]["/".join(str(a) for a in addr)]
+            v = entry["value"].to(device)
+            chm = chm | ChoiceMap.entry(v if entry["shared"] else Batched(v), *addr)
+        tr, _ = gen_fn._run(None, args, chm, weight_mode="none", n=n, batched=True)
+        return ParticleCollection(tr, state["log_weights"].to(device), state["is_valid"])
+
+    def save(self, path) -> None:
+        torch.save(self.state_dict(), path)
+
+    @staticmethod
+    def load(path, gen_fn, args: tuple) -> "ParticleCollection":
+        return ParticleCollection.load_state_dict(gen_fn, args, torch.load(path, map_location="cpu", weights_only=True))
+
     def sample_particle_index(self, key: PRNGKey) -> torch.Tensor:
         """One categorical draw over the normalised weights (smc.py:105-108)."""
         ws = self._workspace()

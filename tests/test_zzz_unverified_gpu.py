@@ -218,3 +218,34 @@ def test_vmap_combinator_and_repeat(device):
     rep = kernel.repeat(n=3).simulate(gj.key(314159), (0.0,))
     vm = kernel.vmap().simulate(gj.key(314159), (torch.zeros(3, device=device),))
     assert rep.get_retval().shape == (3,) and torch.equal(vm.get_choices()[:, "z"], rep.get_choices()[:, "z"])
+
+
+# ------------------------------------------------------------------ ParticleCollection checkpoints
+
+
+def test_particle_collection_checkpoint_round_trip(device, tmp_path):
+    gj = _gj()
+    from genjax_b200.inference.smc import ImportanceK, ParticleCollection
+
+    @gj.gen
+    def model(mu):
+        x = gj.normal(mu, 2.0) @ "x"
+        gj.normal(x, 0.5) @ "y"
+        return x
+
+    target = gj.Target(model, (0.3,), gj.C["y"].set(1.0))
+    pc = ImportanceK(target, k_particles=500).run_smc(gj.key(5))
+    path = tmp_path / "pc.pt"
+    pc.save(path)
+    back = ParticleCollection.load(path, model, (0.3,))
+    assert torch.equal(back.get_log_weights(), pc.get_log_weights())
+    assert back.get_particles().get_choices() == pc.get_particles().get_choices()
+    torch.testing.assert_close(back.get_particles().get_score(), pc.get_particles().get_score(), rtol=1e-6, atol=1e-6)
+    assert back.get_log_marginal_likelihood_estimate() == pc.get_log_marginal_likelihood_estimate()
+    sd = pc.state_dict()
+    assert sd["diagnostics"]["ess"] == pytest.approx(pc.effective_sample_size().item())
+    assert 1.0 <= sd["diagnostics"]["ess"] <= 500.0
+    # the same key picks the same particle from the restored collection
+    assert back.sample_particle(gj.key(9)).get_choices() == pc.sample_particle(gj.key(9)).get_choices()
+    with pytest.raises(ValueError):
+        ParticleCollection.load_state_dict(model, (0.3,), {"format": "something else"})
