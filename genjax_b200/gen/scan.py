@@ -425,7 +425,9 @@ class Scan(GenerativeFunction):
             score = self._acc(score, tr.score)
             weight = self._acc(weight, w)
             if not bwd.constraint.static_is_empty():
-                discard = discard | bwd.constraint.extend(t)
+                d = bwd.constraint if batched else bwd.constraint.map_leaves(
+                    lambda v: v[0] if isinstance(v, torch.Tensor) and v.ndim >= 1 else v)  # scalar call: no particle axis
+                discard = discard | d.extend(t)
         if weight is None:
             weight = torch.zeros(n, dtype=torch.float32, device=device)
         new_tr, w = self._finish(inner, args, carry, ys, score, weight, n, batched, device)

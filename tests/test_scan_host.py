@@ -173,6 +173,17 @@ def test_scan_update_and_regenerate(emu):
     assert torch.equal(reg.get_choices()[:, "y"], tr.get_choices()[:, "y"])
 
 
+def test_scalar_call_update_has_no_particle_axis(emu):
+    model = walk.scan()
+    args = (0.3, torch.tensor(STDS))
+    tr = model.simulate(gj.key(11), args)
+    new, w, _, bwd = model.update(gj.key(12), tr, C[1, "x"].set(9.0), gj.Diff.no_change(args))
+    assert w.shape == () and new.get_choices()[:, "x"].shape == (5,) and new.get_choices()[1, "x"] == 9.0
+    assert bwd[1, "x"].shape == () and bwd[1, "x"] == tr.get_choices()[1, "x"]
+    back, wb, _, _ = model.update(gj.key(13), new, bwd, gj.Diff.no_change(args))
+    assert torch.equal(back.get_choices()[:, "x"], tr.get_choices()[:, "x"]) and (w + wb).abs().item() < 5e-4
+
+
 def test_iterate_accumulate_reduce(emu):
     """test_iterate_simple_normal_importance / test_iterate / test_accumulate / test_reduce, with one random choice per
     step (kernels without any choice have no fused kernel to launch)."""
