@@ -127,9 +127,12 @@ class EmulatedModelLib:
         if n == 0:
             return 0
         self.launches += 1
-        if A.peer_args or A.link or A.key_dev or A.wmax:
-            raise NotImplementedError("emulator: multi-GPU links / device keys / running max are GPU-only paths")
+        if A.peer_args or A.link:
+            raise NotImplementedError("emulator: multi-GPU links are a GPU-only path")
         words = (int(A.key0), int(A.key1))
+        if A.key_dev:  # filter steps read their key words from the device key table
+            kd = _arr(A.key_dev, 2, C.c_uint32, np.uint32)
+            words = (int(kd[0]), int(kd[1]))
         idx = np.uint64(A.idx_offset) + np.arange(n, dtype=np.uint64)
         gather = _view(A.gather, n, I32)
         env = {}
@@ -206,6 +209,14 @@ class EmulatedModelLib:
             if A.score_in:
                 t = (t - _view(A.score_in, n, F32)).astype(F32)
             _view(A.weight_out, n, F32)[:] = t
+            if A.wmax:  # running maximum of the weights in the order-preserving integer encoding (atomicMax)
+                w = _arr(A.wmax, 1, C.c_uint32, np.uint32)
+                with np.errstate(invalid="ignore"):
+                    m = np.fmax.reduce(t)
+                if not np.isnan(m):
+                    w[0] = max(int(w[0]), _enc(m))
+        elif A.wmax:
+            raise NotImplementedError("emulator: wmax without weight_out")
         return 0
 
 
@@ -326,6 +337,68 @@ def _emulated_chain(lib, a_ref, kind):
     return 0
 
 
+def _emulated_pf_run(lib, q_ref):
+    """``gjb_model_pf_run``: the T-step bootstrap filter of the persistent kernel, as the same three phases per step
+    (propose + weight + max, exact mass, systematic resampling) run through the emulated single-step entry points."""
+    from genjax_b200.runtime import cabi
+
+    Q = q_ref._obj
+    ir = lib.ir
+    n, T, rec = int(Q.n), int(Q.T), bool(Q.record)
+    if n <= 0 or T <= 0 or int(Q.idx_offset) & 3:
+        return -1
+    keys = _arr(Q.keys, T * 8, C.c_uint32, np.uint32).reshape(T, 8)
+    core = EmulatedCore()
+    wmax = np.zeros(1, dtype=np.uint32)
+    tiles = max(1, (n + _TILE - 1) // _TILE)
+    tile_mass = np.zeros(tiles, dtype=np.uint64)
+    n_state = int(Q.n_state)
+    for t in range(T):
+        slot, pslot = (t, t - 1) if rec else (t & 1, (t - 1) & 1)
+        A = cabi.ModelArgs()
+        A.n, A.idx_offset = n, int(Q.idx_offset)
+        A.key0, A.key1 = int(keys[t, 0]), int(keys[t, 1])
+        for i, a in enumerate(ir.args):
+            if i < n_state:
+                A.args[i] = Q.state0[i] if t == 0 else Q.state_buf[i] + pslot * int(Q.state_stride[i])
+            elif a.kind == "scalar":
+                A.scalars[i] = Q.scalars[i]
+            else:
+                A.args[i] = Q.shared[i]
+        if t > 0:
+            A.gather = Q.ancestors + pslot * n * 4
+        for s_ in ir.sites:
+            j = s_.index
+            A.site_flags[j] = Q.site_flags[j]
+            if Q.obs[j]:
+                A.site_in[j] = Q.obs[j] + t * int(Q.obs_stride[j])
+        for k, r in enumerate(ir.ret_leaves):
+            buf = Q.state_buf[k] + slot * int(Q.state_stride[k])
+            if r.op == "site" and (int(Q.site_flags[r.attr]) & 1):
+                A.site_out[r.attr] = buf
+            else:
+                A.ret_out[k] = buf
+        lw = Q.logw + (t * n * 4 if rec else 0)
+        A.weight_out = lw
+        wmax[0] = 0x007FFFFF
+        A.wmax = wmax.ctypes.data
+        rc = lib.gjb_model_launch(C.byref(A), 0)
+        if rc:
+            return rc
+        core.gjb_weight_mass(lw, n, wmax.ctypes.data, None, tile_mass.ctypes.data, 0)
+        R = cabi.ResampleArgs()
+        R.logw, R.n, R.wmax, R.tile_mass = lw, n, wmax.ctypes.data, tile_mass.ctypes.data
+        R.n_total, R.out_lo, R.out_n, R.anc_base = int(Q.n_total), 0, n, 0
+        R.key0, R.key1 = int(keys[t, 2]), int(keys[t, 3])
+        R.key_index = int(keys[t, 4]) | (int(keys[t, 5]) << 32)
+        R.ancestors = Q.ancestors + slot * n * 4
+        R.lse_out = Q.lse + t * 24
+        core.gjb_resample_systematic(C.byref(R), 0)
+    return 0
+
+
+EmulatedModelLib.gjb_model_pf_grid = lambda self, n: -1 if n < 0 else 4
+EmulatedModelLib.gjb_model_pf_run = lambda self, q_ref, stream: _emulated_pf_run(self, q_ref)
 EmulatedModelLib.gjb_model_mh_chain = lambda self, a_ref, stream: _emulated_chain(self, a_ref, "mh")
 EmulatedModelLib.gjb_model_hmc_chain = lambda self, a_ref, stream: _emulated_chain(self, a_ref, "hmc")
 
@@ -411,8 +484,12 @@ class EmulatedCore:
         from oracle import smc as osmc
 
         R = r_ref._obj
-        if R.key_dev or R.c_offset or R.s_total or R.m_global:
-            raise NotImplementedError("emulator: sharded / device-key resampling is a GPU-only path")
+        if R.c_offset or R.s_total or R.m_global:
+            raise NotImplementedError("emulator: sharded resampling is a GPU-only path")
+        key0, key1, key_index = int(R.key0), int(R.key1), int(R.key_index)
+        if R.key_dev:
+            kd = _arr(R.key_dev, 4, C.c_uint32, np.uint32)
+            key0, key1, key_index = int(kd[0]), int(kd[1]), int(kd[2]) | (int(kd[3]) << 32)
         n = int(R.n)
         logw = _view(R.logw, n, F32)
         M = self._max(R.wmax, None)
@@ -421,9 +498,9 @@ class EmulatedCore:
         anc = _view(R.ancestors, int(R.out_n), I32)
         lo = int(R.out_lo)
         if S == 0:
-            anc[:] = np.arange(lo, lo + int(R.out_n), dtype=I32)
+            anc[:] = np.arange(lo, lo + int(R.out_n), dtype=I32) - lo + int(R.anc_base)
         else:
-            u0 = osmc.resample_u0(orng.Key((R.key0, R.key1), int(R.key_index)))
+            u0 = osmc.resample_u0(orng.Key((key0, key1), key_index))
             cnt, _ = osmc.systematic_counts(logw, u0, n_out=int(R.n_total), M=M, S=S)
             prev = np.concatenate([[0], cnt[:-1]])
             full = np.repeat(np.arange(n, dtype=np.int64) + int(R.anc_base), (cnt - prev).astype(np.int64))
@@ -492,4 +569,10 @@ def install(monkeypatch):
     monkeypatch.setattr(mcmc, "compile_ir", compile_ir)
     core = EmulatedCore()
     monkeypatch.setattr(cabi, "core", lambda: core)
+    # CUDA graphs are a device feature: under emulation the filter enqueues its launches eagerly on every run
+    from genjax_b200.inference import pf
+
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    eager = pf._Plan.execute
+    monkeypatch.setattr(pf._Plan, "execute", lambda self, key, state0, shared, obs, use_graph: eager(self, key, state0, shared, obs, False))
     return cpu

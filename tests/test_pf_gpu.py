@@ -186,12 +186,15 @@ def test_particle_filter_vec_matches_kalman(device):
     x0 = torch.randn(n, d, generator=torch.Generator().manual_seed(0))
     q = torch.full((d,), Q_)
     r = torch.full((d,), r_obs)
+    # one run of this 8-D bootstrap filter has sd(log Z-hat) = 0.24 (8 seeds through the oracle-backed emulation,
+    # tests/abi_emulator.py; the Jensen bias is -0.03): the mean of 8 seeds has sd 0.084, tolerance = 4 sd
     ests = []
-    for seed in (5, 6):
-        pf = ParticleFilter(step_vec, n)
+    pf = ParticleFilter(step_vec, n)
+    for seed in range(5, 13):
         res = pf.run(gj.key(seed), x0, gj.C["y"].set(torch.from_numpy(ys)), shared_args=(q, r))
         ests.append(res.log_marginal_likelihood.item())
-    assert np.mean(ests) == pytest.approx(exact, abs=0.15)
+    assert np.mean(ests) == pytest.approx(exact, abs=0.34)
+    assert np.std(ests, ddof=1) < 0.6
 
 
 @pytest.mark.parametrize("n", [1, 7, 2049, 300_001, 3_000_000])
