@@ -144,8 +144,9 @@ def test_particle_filter_matches_kalman(device):
         pf = ParticleFilter(step, n)
         res = pf.run(gj.key(seed), x0, gj.C["y"].set(torch.from_numpy(ys)))
         ests.append(res.log_marginal_likelihood.item())
+    # sd(log Z-hat) of one run = 0.029 (8 seeds through tests/abi_emulator.py): the mean of 4 runs has sd 0.015
     assert np.mean(ests) == pytest.approx(exact, abs=0.05)
-    assert np.std(ests) < 0.05
+    assert np.std(ests) < 0.08
 
 
 def test_particle_filter_vec_teacher_forced_vs_oracle(device):
