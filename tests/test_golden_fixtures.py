@@ -60,3 +60,61 @@ def test_cuda_matches_committed_fixtures(device):
     assert res.log_increments[0].item() == pytest.approx(FIX["pf_logz_inc"][0], abs=1e-5)
     same = (res.ancestors[0].cpu().numpy() == FIX["pf_ancestors"][0]).mean()
     assert same > 0.99  # a 1-ulp weight difference can move a count boundary by one slot
+
+
+# ------------------------------------------------------------------ combinators and the output-slot resampler
+
+FIX2 = np.load(os.path.join(HERE, "golden", "combinator_fixtures.npz"))
+
+
+def test_oracle_reproduces_combinator_fixtures():
+    spec = importlib.util.spec_from_file_location("make_combinator_fixtures",
+                                                  os.path.join(HERE, "golden", "make_combinator_fixtures.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    now = mod.build()
+    assert set(now) == set(FIX2.files)
+    for k in FIX2.files:
+        a, b = now[k], FIX2[k]
+        assert a.shape == b.shape and a.dtype == b.dtype, k
+        if a.dtype.kind in "iub":
+            assert np.array_equal(a, b), k
+        else:
+            np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-6, err_msg=k)
+    # the push form (what the kernels compute today) gives the same ancestors as the frozen pull form
+    from oracle import rng, smc
+
+    key = rng.split(rng.key(11))[1]
+    assert np.array_equal(smc.resample_systematic(FIX2["pull_logw"], key), FIX2["pull_ancestors_true_max"])
+
+
+@pytest.mark.gpu
+@pytest.mark.unverified
+def test_cuda_combinators_match_committed_fixtures(device):
+    import torch
+
+    import genjax_b200 as gj
+
+    @gj.gen
+    def walk(x, std):
+        nx = gj.normal(x, std) @ "x"
+        y = gj.normal(2.0 * nx, 0.5) @ "y"
+        return nx, nx + y
+
+    @gj.gen
+    def cell(x):
+        return gj.normal(x, 1.0) @ "z"
+
+    stds = torch.from_numpy(FIX2["scan_stds"]).to(device)
+    tr = walk.scan(n=5).simulate(gj.split(gj.key(314159), 6), (0.25, stds))
+    np.testing.assert_allclose(tr.get_choices()[:, "x"].cpu().numpy(), FIX2["scan_x"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(tr.get_choices()[:, "y"].cpu().numpy(), FIX2["scan_y"], rtol=1e-5, atol=4e-6)
+    np.testing.assert_allclose(tr.get_score().cpu().numpy(), FIX2["scan_score"], rtol=1e-5, atol=5e-5)
+    np.testing.assert_allclose(tr.get_retval()[0].cpu().numpy(), FIX2["scan_carry"], rtol=1e-5, atol=2e-6)
+    yobs = torch.from_numpy(FIX2["scan_yobs"]).to(device)
+    tr, w = walk.scan().importance(gj.split(gj.key(2), 6), gj.C[:, "y"].set(yobs), (0.1, stds))
+    np.testing.assert_allclose(tr.get_choices()[:, "x"].cpu().numpy(), FIX2["scan_imp_x"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(w.cpu().numpy(), FIX2["scan_imp_weight"], rtol=1e-5, atol=5e-5)
+    vt = cell.vmap().simulate(gj.key(314159), (torch.arange(50, dtype=torch.float32, device=device),))
+    np.testing.assert_allclose(vt.get_choices()[:, "z"].cpu().numpy(), FIX2["vmap_z"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(vt.inner.get_score().cpu().numpy(), FIX2["vmap_score_lanes"], rtol=1e-5, atol=2e-5)
