@@ -78,3 +78,99 @@ float32 = _torch.float32
 int32 = _torch.int32
 pi = _math.pi
 inf = _math.inf
+
+
+# ---- composites of the traced operations above (no new kernel-side operations) --------------------------------
+
+
+def _is_traced(*xs) -> bool:
+    return any(isinstance(x, _Expr) for x in xs)
+
+
+def negative(x):
+    return -x
+
+
+def reciprocal(x):
+    if isinstance(x, _Expr):
+        return _E.unary("reciprocal", x)
+    return 1.0 / x
+
+
+def add(a, b):
+    return a + b
+
+
+def subtract(a, b):
+    return a - b
+
+
+def multiply(a, b):
+    return a * b
+
+
+def divide(a, b):
+    return a / b
+
+
+def clip(x, a_min=None, a_max=None):
+    """``jnp.clip``: ``minimum(maximum(x, a_min), a_max)``."""
+    if a_min is not None:
+        x = maximum(x, a_min)
+    if a_max is not None:
+        x = minimum(x, a_max)
+    return x
+
+
+def logaddexp(a, b):
+    """``log(exp(a) + exp(b))`` without overflow: ``max(a, b) + log1p(exp(-|a - b|))``."""
+    if not _is_traced(a, b):
+        return _torch.logaddexp(_torch.as_tensor(a, dtype=_torch.float32), _torch.as_tensor(b, dtype=_torch.float32))
+    return maximum(a, b) + log1p(exp(-abs(a - b)))
+
+
+def mean(x, axis=None):
+    if isinstance(x, _Expr):
+        return _E.vsum(x) / float(x.shape[0]) if x.ndim else x
+    t = _torch.as_tensor(x, dtype=_torch.float32)
+    return _torch.mean(t) if axis is None else _torch.mean(t, dim=axis)
+
+
+def dot(a, b):
+    """Inner product of two vectors (``sum(a * b)``)."""
+    if _is_traced(a, b):
+        return _E.vsum(a * b)
+    return _torch.dot(_torch.as_tensor(a, dtype=_torch.float32), _torch.as_tensor(b, dtype=_torch.float32))
+
+
+def logical_and(a, b):
+    if _is_traced(a, b):
+        return _E.binary("and", a, b)
+    return _torch.logical_and(_torch.as_tensor(a), _torch.as_tensor(b))
+
+
+def logical_or(a, b):
+    if _is_traced(a, b):
+        return _E.binary("or", a, b)
+    return _torch.logical_or(_torch.as_tensor(a), _torch.as_tensor(b))
+
+
+def logical_not(a):
+    if isinstance(a, _Expr):
+        return _E.unary("logical_not", a)
+    return _torch.logical_not(_torch.as_tensor(a))
+
+
+def zeros(shape, dtype=None):
+    return _torch.zeros(shape, dtype=dtype or _torch.float32)
+
+
+def ones(shape, dtype=None):
+    return _torch.ones(shape, dtype=dtype or _torch.float32)
+
+
+def arange(*args, dtype=None):
+    return _torch.arange(*args, dtype=dtype)
+
+
+e = _math.e

@@ -229,3 +229,29 @@ def test_scan_validation_and_zero_length(emu):  # test_scan_validation / test_ze
     walk.scan().importance(gj.key(1), empty.get_choices(), (2.0, torch.zeros(0)))
     with pytest.raises(TypeError):
         gj.Scan(gj.normal)  # only @gen kernels can be scanned
+
+
+def test_numpy_api_composites_inside_a_model(emu):
+    """gj.numpy composites (clip, logaddexp, mean, dot, logical ops) are traced into the model and agree with NumPy."""
+    jnp = gj.numpy
+
+    @gj.gen
+    def model(x, w):
+        a = gj.normal(jnp.clip(x, -1.0, 1.0), 1.0) @ "a"
+        b = gj.normal(jnp.logaddexp(a, x), jnp.reciprocal(2.0 + jnp.square(x))) @ "b"
+        inside = jnp.logical_and(a > -5.0, jnp.logical_not(a > 5.0))
+        return jnp.where(inside, jnp.dot(w, w) * a + jnp.mean(w), jnp.negative(b)), jnp.divide(jnp.subtract(b, a), jnp.add(1.0, jnp.abs(x)))
+
+    n = 64
+    xs = torch.linspace(-3, 3, n)
+    w = torch.tensor([0.5, -1.0, 2.0, 0.25])
+    tr = model.simulate(gj.split(gj.key(3), n), (gj.Batched(xs), w))
+    a, b = _np(tr.get_choices()["a"]), _np(tr.get_choices()["b"])
+    x = xs.numpy()
+    r0, r1 = tr.get_retval()
+    np.testing.assert_allclose(_np(r0), float((w * w).sum()) * a + float(w.mean()), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(_np(r1), (b - a) / (1 + np.abs(x)), rtol=1e-5, atol=1e-5)
+    want = od.normal_logpdf(a, np.clip(x, -1, 1).astype(F32), F32(1.0)) + od.normal_logpdf(
+        b, np.logaddexp(a, x).astype(F32), (1.0 / (2.0 + x * x)).astype(F32))
+    np.testing.assert_allclose(_np(tr.get_score()), want, rtol=2e-5, atol=2e-5)
+    assert float(jnp.logaddexp(0.0, 0.0)) == pytest.approx(np.log(2.0)) and float(jnp.clip(torch.tensor(3.0), 0.0, 1.0)) == 1.0
