@@ -162,6 +162,12 @@ class _Categorical(Distribution):
     name, cuda, n_args, value_dtype = "categorical", "Categorical", 1, I32
 
     def _canonical(self, args, kwargs):
+        shape = kwargs.get("sample_shape", ())
+        shape = getattr(shape, "value", shape)  # genjax.Const((...)) wraps the static shape
+        if shape not in ((), None):
+            # tfd.Categorical(...).sample(sample_shape=n) draws n iid values into ONE choice (tfp __init__.py:53-55);
+            # silently returning a single draw would be wrong -- use categorical.vmap / repeat once they exist
+            raise NotImplementedError("categorical(..., sample_shape=n) is not supported: one choice holds one draw")
         kwargs = {k: v for k, v in kwargs.items() if k != "sample_shape"}
         if "probs" in kwargs:
             return [E.unary("log", E.lift(kwargs["probs"]))]
