@@ -85,6 +85,20 @@ class Distribution(GenerativeFunction):
         return f"genjax.{self.name}()"  # what the reference prints (test_distributions.py:476-489)
 
 
+def _check_kwargs(name: str, kwargs: dict, allowed: tuple) -> dict:
+    """Reject what this build cannot honour instead of dropping it: unknown keywords, and ``sample_shape=n``
+    (tfp draws n iid values into one choice, tensorflow_probability/__init__.py:53-55; here one choice is one draw)."""
+    shape = kwargs.get("sample_shape", ())
+    shape = getattr(shape, "value", shape)  # genjax.Const((...)) wraps the static shape
+    if shape not in ((), None):
+        raise NotImplementedError(f"{name}(..., sample_shape=...) is not supported: one choice holds one draw")
+    rest = {k: v for k, v in kwargs.items() if k != "sample_shape"}
+    unknown = [k for k in rest if k not in allowed]
+    if unknown:
+        raise TypeError(f"{name} got unexpected keyword argument(s) {unknown}; accepted: {list(allowed)}")
+    return rest
+
+
 def _split_kwargs(args):
     """Unpack the reference's ``(args, kwargs_dict)`` convention (distribution.py:448-462)."""
     if isinstance(args, tuple) and len(args) == 2 and isinstance(args[1], dict) and isinstance(args[0], tuple):
@@ -97,6 +111,7 @@ class _Normal(Distribution):
     rng_kind = "normal"
 
     def _canonical(self, args, kwargs):
+        kwargs = _check_kwargs("normal", kwargs, ("loc", "scale"))
         if kwargs:
             args = tuple(args) + tuple(kwargs[k] for k in ("loc", "scale") if k in kwargs)
         return super()._canonical(args, {})
@@ -106,6 +121,7 @@ class _Uniform(Distribution):
     name, cuda, n_args = "uniform", "Uniform", 2
 
     def _canonical(self, args, kwargs):
+        kwargs = _check_kwargs("uniform", kwargs, ("low", "high"))
         if kwargs:
             args = tuple(args) + tuple(kwargs[k] for k in ("low", "high") if k in kwargs)
         if len(args) == 0:
@@ -145,6 +161,7 @@ class _Bernoulli(Distribution):
     name, cuda, n_args, value_dtype = "bernoulli", "Bernoulli", 1, I32
 
     def _canonical(self, args, kwargs):
+        kwargs = _check_kwargs("bernoulli", kwargs, ("probs", "logits"))
         if "probs" in kwargs:
             p = E.lift(kwargs["probs"])
             return [E.unary("log", p) - E.unary("log1p", -p)]
@@ -162,13 +179,7 @@ class _Categorical(Distribution):
     name, cuda, n_args, value_dtype = "categorical", "Categorical", 1, I32
 
     def _canonical(self, args, kwargs):
-        shape = kwargs.get("sample_shape", ())
-        shape = getattr(shape, "value", shape)  # genjax.Const((...)) wraps the static shape
-        if shape not in ((), None):
-            # tfd.Categorical(...).sample(sample_shape=n) draws n iid values into ONE choice (tfp __init__.py:53-55);
-            # silently returning a single draw would be wrong -- use categorical.vmap / repeat once they exist
-            raise NotImplementedError("categorical(..., sample_shape=n) is not supported: one choice holds one draw")
-        kwargs = {k: v for k, v in kwargs.items() if k != "sample_shape"}
+        kwargs = _check_kwargs("categorical", kwargs, ("probs", "logits"))
         if "probs" in kwargs:
             return [E.unary("log", E.lift(kwargs["probs"]))]
         if "logits" in kwargs:

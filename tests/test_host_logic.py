@@ -303,3 +303,25 @@ def test_zero_trace_and_site_addresses_need_no_device():
     assert model.get_site_addresses((0.0,)) == [("y",), ("z", "inner")]
     with pytest.raises(RuntimeError):
         model.inline(0.0)  # only inside an @gen body
+
+
+def test_distributions_reject_what_they_cannot_honour():
+    """Unknown keywords and sample_shape=n fail at capture time instead of being dropped silently."""
+    import genjax_b200 as gj
+
+    def addresses(make):
+        @gj.gen
+        def m():
+            return make() @ "v"
+
+        return m.get_site_addresses(())
+
+    for make in (lambda: gj.normal(0.0, 1.0, sample_shape=(2, 2)), lambda: gj.bernoulli(probs=0.3, sample_shape=2),
+                 lambda: gj.categorical(logits=[0.0, 0.0], sample_shape=3)):
+        with pytest.raises(NotImplementedError, match="sample_shape"):
+            addresses(make)
+    with pytest.raises(TypeError, match="unexpected keyword"):
+        addresses(lambda: gj.uniform(0.0, 1.0, foo=1))
+    for make in (lambda: gj.normal(loc=0.0, scale=1.0), lambda: gj.categorical(probs=[0.5, 0.5]),
+                 lambda: gj.uniform(low=0.0, high=2.0), lambda: gj.categorical(logits=[0.0, 0.0], sample_shape=())):
+        assert addresses(make) == [("v",)]
