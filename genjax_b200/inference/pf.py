@@ -73,6 +73,34 @@ class ParticleFilter:
         self.n_total = int(n_total) if n_total is not None else self.n
         self._plans: dict = {}
 
+    def weight_upper_bound(self, state0, observations: ChoiceMap, shared_args: tuple = ()):
+        """Analytic supremum over particles of ONE step's incremental log-weight (the sum of the observed sites'
+        log-densities), or None when it cannot be derived from the model (``gen/bounds.py``).  Host-only: the step
+        is captured symbolically, nothing is launched.  A reference maximum of this kind is what the single-pass
+        filter step of DESIGN.md section 10 needs; today it is a diagnostic (``lse_terms[:, 0] <= bound``)."""
+        from ..gen import bounds
+        from ..gen import capture as cap_
+
+        state0 = state0 if isinstance(state0, (tuple, list)) else (state0,)
+        specs, values = [], {}
+        for i, s in enumerate(state0):
+            t = torch.as_tensor(s)
+            specs.append(ArgSpec("particle", "i32" if t.dtype in (torch.int32, torch.int64) else "f32", tuple(t.shape[1:])))
+        for k, s in enumerate(shared_args):
+            i = len(state0) + k
+            if isinstance(s, (int, float)):
+                specs.append(ArgSpec("scalar", "i32" if isinstance(s, int) else "f32", ()))
+                values[i] = s
+            else:
+                t = torch.as_tensor(s).detach().cpu()
+                specs.append(ArgSpec("shared", "i32" if t.dtype in (torch.int32, torch.int64) else "f32", tuple(t.shape)))
+                values[i] = t.numpy()
+        tree = ("tuple", [("leaf", i) for i in range(len(specs))])
+        ir = cap_.capture(self.step.source, self.step.__name__, specs, tree)
+        sites = [ir.site_index(addr) for addr, _ in observations.leaves()]
+        b = bounds.log_weight_upper_bound(ir, sites)
+        return None if b is None else bounds.evaluate_invariant(b, values)
+
     # ------------------------------------------------------------------ plan
     def _plan(self, state0: tuple, shared: tuple, obs: dict, T: int, record: bool, device):
         sig = (tuple((tuple(s.shape[1:]), s.dtype) for s in state0),

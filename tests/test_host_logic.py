@@ -325,3 +325,46 @@ def test_distributions_reject_what_they_cannot_honour():
     for make in (lambda: gj.normal(loc=0.0, scale=1.0), lambda: gj.categorical(probs=[0.5, 0.5]),
                  lambda: gj.uniform(low=0.0, high=2.0), lambda: gj.categorical(logits=[0.0, 0.0], sample_shape=())):
         assert addresses(make) == [("v",)]
+
+
+def test_weight_upper_bounds_from_the_model():
+    """gen/bounds.py: the analytic supremum of a filter step's incremental weight."""
+    import math
+
+    import torch
+
+    import genjax_b200 as gj
+    from genjax_b200.inference.pf import ParticleFilter
+    from genjax_b200.workloads import LG_R, hmm_step, lgssm_step, lgssm_step_vec
+
+    half = 0.5 * math.log(2 * math.pi)
+    b = ParticleFilter(lgssm_step, 8).weight_upper_bound(torch.zeros(8), gj.C["y"].set(torch.zeros(3)))
+    assert b == pytest.approx(-(half + math.log(LG_R)), rel=1e-6)
+    r = torch.tensor([0.5, 1.0, 2.0, 4.0])
+    b = ParticleFilter(lgssm_step_vec, 8).weight_upper_bound(torch.zeros(8, 4), gj.C["y"].set(torch.zeros(3, 4)),
+                                                             (torch.ones(4), r))
+    assert b == pytest.approx(-(4 * half + float(torch.log(r).sum())), rel=1e-6)
+    b = ParticleFilter(hmm_step, 8).weight_upper_bound(torch.zeros(8, dtype=torch.int32), gj.C["y"].set(torch.zeros(3, dtype=torch.int32)),
+                                                       (torch.zeros(16, 16), torch.zeros(16, 16)))
+    assert b == 0.0
+
+    @gj.gen
+    def hetero(x_prev):  # the observation noise depends on the particle: no particle-free bound
+        x = gj.normal(x_prev, 1.0) @ "x"
+        gj.normal(x, gj.numpy.exp(0.1 * x)) @ "y"
+        return x
+
+    assert ParticleFilter(hetero, 8).weight_upper_bound(torch.zeros(8), gj.C["y"].set(torch.zeros(3))) is None
+
+    # the bound really bounds: oracle weights of the scalar model never exceed it
+    from oracle import gfi as ogfi
+    from oracle import rng
+
+    def o_step(h, x_prev):
+        x = h.normal("x", np.float32(0.9) * x_prev, np.float32(1.0))
+        h.normal("y", x, np.float32(LG_R))
+        return x
+
+    _, w = ogfi.generate(o_step, rng.split(rng.key(0), 4096), {"y": np.float32(0.3)}, (np.zeros(4096, dtype=np.float32),))
+    bound = ParticleFilter(lgssm_step, 8).weight_upper_bound(torch.zeros(8), gj.C["y"].set(torch.zeros(3)))
+    assert w.max() <= bound + 1e-6 and w.max() > bound - 1e-3
