@@ -249,3 +249,22 @@ def test_particle_collection_checkpoint_round_trip(device, tmp_path):
     assert back.sample_particle(gj.key(9)).get_choices() == pc.sample_particle(gj.key(9)).get_choices()
     with pytest.raises(ValueError):
         ParticleCollection.load_state_dict(model, (0.3,), {"format": "something else"})
+
+
+# ------------------------------------------------------------------ analytic weight bound (gen/bounds.py)
+
+
+def test_filter_maxima_stay_below_the_analytic_bound(device):
+    gj = _gj()
+    from genjax_b200.inference.pf import ParticleFilter
+    from genjax_b200.workloads import lgssm_step
+    from oracle import smc as osmc
+
+    n, T = 20_000, 12
+    ys = torch.from_numpy(osmc.simulate_lgssm(0, T, 1, 0.9, 1.0, 1.0, 0.5)[:, 0])
+    x0 = torch.randn(n, generator=torch.Generator().manual_seed(0))
+    pf = ParticleFilter(lgssm_step, n)
+    bound = pf.weight_upper_bound(x0, gj.C["y"].set(ys))
+    res = pf.run(gj.key(1), x0, gj.C["y"].set(ys))
+    m = res.lse_terms[:, 0].cpu().numpy()
+    assert (m <= bound + 1e-6).all() and (m > bound - 0.01).all()  # 20 000 particles: some particle sits on the mode
