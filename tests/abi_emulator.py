@@ -540,16 +540,73 @@ class EmulatedCore:
         return 0
 
 
+class HostKernelModelLib(EmulatedModelLib):
+    """Same stand-in, but the model launch and the chain launches execute the GENERATED CUDA source compiled for the
+    host (tests/host_kernels.py) instead of interpreting the IR; the filter run reuses the per-step launch."""
+
+    def __init__(self, ir, chain, hostlib):
+        super().__init__(ir, chain)
+        self.h = hostlib
+
+    def gjb_model_launch(self, a_ref, stream):
+        A = a_ref._obj
+        n = int(A.n)
+        if n < 0:
+            return -1
+        if n == 0:
+            return 0
+        if A.peer_args or A.link:
+            raise NotImplementedError("host kernels: multi-GPU links are a GPU-only path")
+        self.launches += 1
+        wmax = A.wmax
+        A.wmax = None  # the block-level max reduction needs a real thread block; redone below from the weights
+        try:
+            rc = self.h.host_model_launch(a_ref)
+        finally:
+            A.wmax = wmax
+        if rc == 0 and wmax:
+            if not A.weight_out:
+                raise NotImplementedError("host kernels: wmax without weight_out")
+            t = _view(A.weight_out, n, F32)
+            w = _arr(wmax, 1, C.c_uint32, np.uint32)
+            with np.errstate(invalid="ignore"):
+                m = np.fmax.reduce(t)
+            if not np.isnan(m):
+                w[0] = max(int(w[0]), _enc(m))
+        return rc
+
+    def gjb_model_mh_chain(self, a_ref, stream):
+        return self.h.host_mh_chain(a_ref) if hasattr(self.h, "host_mh_chain") else -3
+
+    def gjb_model_hmc_chain(self, a_ref, stream):
+        return self.h.host_hmc_chain(a_ref) if hasattr(self.h, "host_hmc_chain") else -3
+
+
 class _EmulatedCompiledModel:
-    def __init__(self, ir, chain=None):
+    def __init__(self, ir, chain=None, pf_obs=None, host_kernels=False):
         self.ir = ir
-        self.lib = EmulatedModelLib(ir, chain)
+        self.lib = None
+        if host_kernels:
+            import host_kernels as hk
+            from genjax_b200.gen import codegen
+
+            source = codegen.generate(ir, pf_obs, chain)
+            if hk.is_host_runnable(source):
+                self.lib = HostKernelModelLib(ir, chain, hk.build(source))
+        if self.lib is None:
+            self.lib = EmulatedModelLib(ir, chain)
         self.path = None
         self.info = json.loads(self.lib.gjb_model_info().decode())
 
 
-def install(monkeypatch):
-    """Route the host through the emulator for the duration of one test."""
+def install(monkeypatch, host_kernels=None):
+    """Route the host through the emulator for the duration of one test.  ``host_kernels=True`` (or
+    GJB_EMULATE_KERNELS=host) executes the generated CUDA source compiled for the host where that is possible
+    (tests/host_kernels.py) instead of interpreting the IR."""
+    import os
+
+    if host_kernels is None:
+        host_kernels = os.environ.get("GJB_EMULATE_KERNELS") == "host"
     from genjax_b200.gen import capture as cap
     from genjax_b200.gen import static
     from genjax_b200.runtime import cabi
@@ -561,7 +618,7 @@ def install(monkeypatch):
 
     def compile_ir(ir, pf_obs=None, chain=None):
         ir.digest = cap.ir_fingerprint(ir)
-        return _EmulatedCompiledModel(ir, chain)
+        return _EmulatedCompiledModel(ir, chain, pf_obs, host_kernels)
 
     monkeypatch.setattr(static, "compile_ir", compile_ir)
     from genjax_b200.inference import mcmc

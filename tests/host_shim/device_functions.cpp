@@ -1,0 +1,66 @@
+// Host build of the exact-arithmetic device functions (see cuda_runtime.h in this directory).
+#include "gjb_resample.cuh"
+
+extern "C" {
+void h_philox(const uint32_t* ctr, uint32_t k0, uint32_t k1, uint32_t* out) {
+  const uint4 r = gjb::philox4x32_10(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]), k0, k1);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+void h_quad_words(uint32_t k0, uint32_t k1, uint64_t quad, uint32_t site, uint32_t chunk, uint32_t* out) {
+  const uint4 r = gjb::quad_words(k0, k1, quad, site, chunk);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+void h_lane_words(uint32_t k0, uint32_t k1, uint64_t idx, uint32_t site, uint32_t chunk, uint32_t* out) {
+  const uint4 r = gjb::make_lane(k0, k1, idx).words(site, chunk);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+void h_u01(const uint32_t* bits, int n, float* out) { for (int i = 0; i < n; ++i) out[i] = gjb::u01(bits[i]); }
+void h_box_muller(const uint32_t* b0, const uint32_t* b1, int n, float* out) {
+  for (int i = 0; i < n; ++i) { const float2 z = gjb::box_muller(b0[i], b1[i]); out[2 * i] = z.x; out[2 * i + 1] = z.y; }
+}
+void h_fenc(const float* f, int n, uint32_t* out) { for (int i = 0; i < n; ++i) out[i] = gjb::fenc(f[i]); }
+void h_fdec(const uint32_t* e, int n, float* out) { for (int i = 0; i < n; ++i) out[i] = gjb::fdec(e[i]); }
+void h_det_exp_q(const float* x, int n, uint64_t* out) { for (int i = 0; i < n; ++i) out[i] = gjb::det_exp_q(x[i]); }
+void h_offspring_cnt(const uint64_t* C, int n, uint64_t S, int32_t n_total, double u0, int32_t* out) {
+  const double scale = __ddiv_rn((double)n_total, (double)S);
+  for (int i = 0; i < n; ++i) out[i] = gjb::offspring_cnt(C[i], S, scale, u0, n_total);
+}
+double h_resample_u0(uint32_t k0, uint32_t k1, uint64_t key_index) { return gjb::resample_u0(k0, k1, key_index); }
+}
+
+// ---- distribution device library (gjb_dist.cuh): log-densities and the lane-stream samplers
+#include "gjb_dist.cuh"
+
+extern "C" {
+// which: 0 normal(v, loc, scale)  1 uniform(v, lo, hi)  2 exponential(v, rate)  3 half_normal(v, scale)
+//        4 gamma(v, a, rate)  5 beta(v, a, b)  6 flip(v, p)  7 bernoulli(v, logit)  8 normal logpdf_r(v, loc, 1/scale, lc)
+void h_logpdf(int which, const float* v, const float* a, const float* b, int n, float* out) {
+  for (int i = 0; i < n; ++i) {
+    switch (which) {
+      case 0: out[i] = gjb::Normal::logpdf(v[i], a[i], b[i]); break;
+      case 1: out[i] = gjb::Uniform::logpdf(v[i], a[i], b[i]); break;
+      case 2: out[i] = gjb::Exponential::logpdf(v[i], a[i]); break;
+      case 3: out[i] = gjb::HalfNormal::logpdf(v[i], a[i]); break;
+      case 4: out[i] = gjb::Gamma::logpdf(v[i], a[i], b[i]); break;
+      case 5: out[i] = gjb::Beta::logpdf(v[i], a[i], b[i]); break;
+      case 6: out[i] = gjb::Flip::logpdf((int)v[i], a[i]); break;
+      case 7: out[i] = gjb::Bernoulli::logpdf((int)v[i], a[i]); break;
+      case 8: out[i] = gjb::Normal::logpdf_r(v[i], a[i], 1.0f / b[i], gjb::kHalfLog2Pi + logf(b[i])); break;
+    }
+  }
+}
+void h_categorical(const float* logits, int K, const float* u, int n, int32_t* draws, float* logpdf_of_draw) {
+  for (int i = 0; i < n; ++i) {
+    draws[i] = gjb::Categorical::sample(u[i], logits, K);
+    logpdf_of_draw[i] = gjb::Categorical::logpdf(draws[i], logits, K);
+  }
+}
+// lane-stream rejection samplers: lane = (key, global index), site as in the kernels
+void h_gamma_beta(uint32_t k0, uint32_t k1, uint64_t idx0, int n, uint32_t site, float a, float b, float* gamma_out, float* beta_out) {
+  for (int i = 0; i < n; ++i) {
+    const gjb::Lane l = gjb::make_lane(k0, k1, idx0 + (uint64_t)i);
+    gamma_out[i] = gjb::Gamma::sample(l, site, a, b);
+    beta_out[i] = gjb::Beta::sample(l, site, a, b);
+  }
+}
+}

@@ -30,7 +30,9 @@ _MCMC = "not eight_schools and not gmm"
     ["tests/test_mcmc_gpu.py", "-k", _MCMC],
 ])
 def test_gpu_tests_host_paths_under_emulation(files):
-    env = dict(os.environ, GJB_EMULATE="1", GJB_RUN_UNVERIFIED="1", CUDA_VISIBLE_DEVICES="")
+    # GJB_EMULATE_KERNELS=host: scalar-site models and chain kernels execute their GENERATED CUDA source compiled for
+    # the host (tests/host_kernels.py); vector-site models fall back to the IR interpreter
+    env = dict(os.environ, GJB_EMULATE="1", GJB_EMULATE_KERNELS="host", GJB_RUN_UNVERIFIED="1", CUDA_VISIBLE_DEVICES="")
     r = subprocess.run([sys.executable, "-m", "pytest", *files, "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider"],
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     tail = (r.stdout + r.stderr)[-3000:]

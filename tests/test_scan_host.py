@@ -20,9 +20,11 @@ from oracle import rng
 F32 = np.float32
 
 
-@pytest.fixture
-def emu(monkeypatch):
-    return abi_emulator.install(monkeypatch)
+@pytest.fixture(params=["ir", "host"])
+def emu(monkeypatch, request):
+    """"ir": the captured IR interpreted with the oracle; "host": the generated CUDA source compiled for the host
+    (tests/host_kernels.py) -- the same scenarios on both."""
+    return abi_emulator.install(monkeypatch, host_kernels=request.param == "host")
 
 
 @gj.gen
