@@ -56,6 +56,9 @@ def parse():
                          "per-shard log-marginal-likelihood terms are combined by ONE NCCL all-reduce per run; "
                          "global = one filter over N*particles with global systematic resampling every step "
                          "(peer-memory hand-offs, BASELINE configs[3] style)")
+    ap.add_argument("--reference-max", default="running", choices=["running", "analytic"],
+                    help="running (default): max + mass passes; analytic: masses relative to an analytic bound, accumulated "
+                         "in the model kernel (graph mode, d = 1; DESIGN.md section 10 -- not yet measured on a device)")
     ap.add_argument("--mode", default="graph", choices=["persistent", "graph"],
                     help="persistent: one cooperative launch per filter; graph: 2 launches per step in a CUDA graph")
     return ap.parse_args()
@@ -363,7 +366,7 @@ def run_ours(args):
 
         pf = DistributedParticleFilter(model, n)
     else:
-        pf = ParticleFilter(model, n, idx_offset=0, mode=args.mode)
+        pf = ParticleFilter(model, n, idx_offset=0, mode=args.mode, reference_max=args.reference_max)
     obs_dev = gj.C["y"].set(ys_dev)
     obs_host = gj.C["y"].set(ys_host)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
@@ -522,6 +525,23 @@ def run_ours(args):
                 "what": "exact integer weight mass + grid barrier + CDF scan + systematic offspring ranges (gjb_mass_resample_systematic)"}
             if mr_ms > model_ms:
                 dominant = "mass_resample_kernel"
+        if not global_resample and getattr(plan, "analytic", False):
+            # reference-maximum step: the model kernel also accumulates the masses; the resampler takes them as given
+            core = cabi.core()
+            plan.tm2.zero_()
+            mm_ms = time_launches(lambda: plan.cm.lib.gjb_model_launch(C.byref(plan.margs[0]), stream), 200, 20)
+            kernels["model_kernel_static_mass"] = {
+                "kernel_us": mm_ms * 1e3, "algorithmic_bytes_per_launch": model_bytes, "achieved": model_bytes / (mm_ms * 1e-3) / 1e9,
+                "frac": model_bytes / (mm_ms * 1e-3) / 1e9 / peak,
+                "what": "gather + propose + logpdf + exact integer masses relative to the analytic bound (gjb_model_launch)"}
+            plan.tm2.zero_()
+            plan.cm.lib.gjb_model_launch(C.byref(plan.margs[0]), stream)
+            rs_ms = time_launches(lambda: core.gjb_resample_systematic(C.byref(plan.rargs[0][1]), stream), 200, 20)
+            kernels["resample_systematic_kernel"] = {
+                "kernel_us": rs_ms * 1e3, "algorithmic_bytes_per_launch": 8 * n, "achieved": 8 * n / (rs_ms * 1e-3) / 1e9,
+                "frac": 8 * n / (rs_ms * 1e-3) / 1e9 / peak,
+                "what": "CDF scan + systematic offspring ranges on given tile masses (gjb_resample_systematic)"}
+            dominant = "resample_systematic_kernel" if rs_ms > mm_ms else "model_kernel_static_mass"
         k = kernels[dominant]
         roofline = {
             "bound": "hbm", "kernel": f"{dominant}: {k['what']}",
@@ -587,6 +607,7 @@ def run_ours(args):
                           "on 8 bytes) per run, inside the timed region; weak scaling. --multi-gpu global times the "
                           "global-resampling filter instead"),
             "logZ_last": logz,
+            "reference_max": args.reference_max,
         },
         "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                 "logZ_last": logz_e2e},

@@ -471,6 +471,7 @@ class _Generator:
         out.append("  const void* args[NA]; const void* site_in[NS]; void* site_out[NS]; void* ret_out[NR];")
         out.append("  const int32_t* gather; const float* score_in; const float* weight_in; float* score_out; float* weight_out;")
         out.append("  const gjb_peers* peers;  // nullable device array [NA]: gathered rows may live on peer ranks")
+        out.append("  const float* m_ref; unsigned long long* tile_mass;  // reference-maximum step (kMass instantiation only)")
         out.append("};")
         out.append("struct Uni {  // particle-invariant values, computed once per thread per launch")
         out.append("  float sc[NA];")
@@ -562,10 +563,11 @@ class _Generator:
 
         out = list(P)
         out.append("// quads [ql_begin, ql_end) step ql_stride of the launch; local particle i0 = 4*ql - (idx_offset & 3)")
-        out.append("template <bool kCg, bool kSt>")
+        out.append("template <bool kCg, bool kSt, bool kMass = false>")
         out.append("__device__ __forceinline__ void run_quads(const Io& io, const Uni& U, const uint32_t (&fl)[NS], int64_t n,")
         out.append("    uint64_t idx_offset, uint32_t key0, uint32_t key1, int64_t ql_begin, int64_t ql_end, int64_t ql_stride, float& run_max) {")
         out.append("  const bool need_score = !kSt && io.score_out != nullptr;")
+        out.append("  const float mref = kMass ? __ldg(io.m_ref) : 0.0f;  // reference maximum known before the launch")
         out.append("  const int shift = kSt ? 0 : (int)(idx_offset & 3);")
         out.append("  const uint64_t quad0 = idx_offset >> 2;")
         out.append("  const int32_t g0[4] = {0, 0, 0, 0};")
@@ -605,6 +607,11 @@ class _Generator:
         out.append("        if (u >= lo && u < hi) run_max = fmaxf(run_max, t);")
         out.append("      }")
         out.append("      if (io.weight_out) gjb::store4(io.weight_out, i0, lo, hi, w);")
+        out.append("      if (kMass) {  // exact integer mass of the quad, added to its tile (a quad never straddles a tile)")
+        out.append("        unsigned long long qs = 0ull;")
+        out.append("        for (int u = 0; u < 4; ++u) if (u >= lo && u < hi) qs += gjb::det_exp_q(__fadd_rn(gjb::as_f(w[u]), -mref));")
+        out.append("        if (qs) atomicAdd(io.tile_mass + ((i0 + lo) / gjb::kTile), qs);")
+        out.append("      }")
         out.append("    }")
         out.append("  }")
         out.append("}")
@@ -689,9 +696,13 @@ class _Generator:
         return out
 
     # ------------------------------------------------------------ kernels
-    def model_kernel(self, static: bool = False) -> list[str]:
-        name = "model_kernel_static" if static else "model_kernel"
+    def model_kernel(self, static: bool = False, mass: bool = False) -> list[str]:
+        name = ("model_kernel_static_mass" if mass else "model_kernel_static") if static else "model_kernel"
         out = [f"__global__ void __launch_bounds__(kThreads) {name}(const __grid_constant__ gjb_model_args A) {{"]
+        if mass:
+            out.append("  // the tile masses of the NEXT step's buffer are zeroed here (nobody reads them during this launch)")
+            out.append("  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < A.tile_mass_clear_n; i += (int64_t)gridDim.x * kThreads)")
+            out.append("    if (A.tile_mass_clear) A.tile_mass_clear[i] = 0ull;")
         out.append("  if (A.link && A.wait_off) {  // multi-GPU: the peers' ancestor writes of the previous step have landed")
         out.append("    __shared__ uint64_t link_vals[GJB_MAX_RANKS];")
         out.append("    gjb::link_wait(A.link, A.wait_off, link_vals);")
@@ -706,13 +717,15 @@ class _Generator:
         out.append("  for (int k = 0; k < NR; ++k) io.ret_out[k] = A.ret_out[k];")
         out.append("  io.gather = A.gather; io.score_in = A.score_in; io.weight_in = A.weight_in; io.score_out = A.score_out; io.weight_out = A.weight_out;")
         out.append("  io.peers = A.peer_args;")
+        out.append("  io.m_ref = A.m_ref; io.tile_mass = A.tile_mass;" if mass else "  io.m_ref = nullptr; io.tile_mass = nullptr;")
         out.append("  const uint32_t key0 = A.key_dev ? __ldg(A.key_dev) : A.key0, key1 = A.key_dev ? __ldg(A.key_dev + 1) : A.key1;")
         out.append("  float run_max = -INFINITY;")
         if self.group:
             out.append(f"  run_groups<false, {'true' if static else 'false'}>(io, U, fl, A.n, A.idx_offset, key0, key1, (int64_t)blockIdx.x * kPPB, A.n, (int64_t)gridDim.x * kPPB, run_max);")
         else:
             out.append("  const int64_t nq = (A.n + (int64_t)(A.idx_offset & 3) + 3) >> 2;")
-            out.append(f"  run_quads<false, {'true' if static else 'false'}>(io, U, fl, A.n, A.idx_offset, key0, key1, blockIdx.x * (int64_t)kThreads + threadIdx.x, nq, (int64_t)gridDim.x * kThreads, run_max);")
+            targs = "false, true, true" if mass else f"false, {'true' if static else 'false'}"
+            out.append(f"  run_quads<{targs}>(io, U, fl, A.n, A.idx_offset, key0, key1, blockIdx.x * (int64_t)kThreads + threadIdx.x, nq, (int64_t)gridDim.x * kThreads, run_max);")
         out.append("  if (A.wmax) gjb::block_wmax(run_max, A.wmax);")
         out.append("  if (A.link && A.push_off) {  // multi-GPU: the CTA that finishes last publishes this rank's max")
         out.append("    if (gjb::link_last_block(A.link)) gjb::link_push(A.link, A.push_off, (uint64_t)__ldcg(A.wmax));")
@@ -747,7 +760,7 @@ class _Generator:
         out.append("    for (int i = 0; i < NA; ++i) io.args[i] = nullptr;")
         out.append("    for (int j = 0; j < NS; ++j) { io.site_in[j] = nullptr; io.site_out[j] = nullptr; }")
         out.append("    for (int k = 0; k < NR; ++k) io.ret_out[k] = nullptr;")
-        out.append("    io.score_in = nullptr; io.weight_in = nullptr; io.score_out = nullptr; io.peers = nullptr;")
+        out.append("    io.score_in = nullptr; io.weight_in = nullptr; io.score_out = nullptr; io.peers = nullptr; io.m_ref = nullptr; io.tile_mass = nullptr;")
         for i in range(len(ir.ret_leaves)):
             out.append(f"    io.args[{i}] = t == 0 ? Q.state0[{i}] : (const void*)((const char*)Q.state_buf[{i}] + (int64_t)pslot * Q.state_stride[{i}]);")
         out.append("    io.gather = t == 0 ? nullptr : Q.ancestors + (int64_t)pslot * n;")
@@ -831,6 +844,8 @@ class _Generator:
         out.extend(self.model_kernel())
         if self.pf_obs is not None:
             out.extend(self.model_kernel(static=True))
+            if not self.group:
+                out.extend(self.model_kernel(static=True, mass=True))
         pf = self.pf_supported()
         if pf:
             out.extend(self.pf_kernel())
@@ -904,12 +919,17 @@ int gjb_model_pf_run(const gjb_pf_args* a, void* stream) { (void)a; (void)stream
   // accumulation, and whose lanes start on a quad boundary) takes the specialised instantiation
   bool is_static = !a->score_in && !a->weight_in && !a->score_out && (a->idx_offset & 3) == 0;
   for (int j = 0; j < {self.ns}; ++j) is_static = is_static && a->site_flags[j] == kPfFl_host[j];
+  if (a->tile_mass || a->m_ref) {{{{  // reference-maximum step: masses accumulated while the weights are in registers
+    if (!is_static || !a->tile_mass || !a->m_ref || !a->weight_out || {'true' if self.group else 'false'}) return GJB_E_MODE;
+    {'return GJB_E_MODE;' if self.group else 'model_kernel_static_mass<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(*a);'}
+    return (int)cudaGetLastError();
+  }}}}
   if (is_static) {{{{
     model_kernel_static<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(*a);
     return (int)cudaGetLastError();
   }}}}"""
         else:
-            static_dispatch = ""
+            static_dispatch = "if (a->tile_mass || a->m_ref) return GJB_E_MODE;  // needs the filter-flag instantiation"
         chain_code = chain_ext if chain_ext is not None else """
 int gjb_model_mh_chain(const gjb_chain_args* a, void* stream) { (void)a; (void)stream; return GJB_E_MODE; }
 int gjb_model_hmc_chain(const gjb_chain_args* a, void* stream) { (void)a; (void)stream; return GJB_E_MODE; }

@@ -59,11 +59,22 @@ class ParticleFilter:
     particles).  Every other site is proposed from the model (bootstrap)."""
 
     def __init__(self, step: StaticGenerativeFunction, n_particles: int, *, n_state: int = 1, resampler: str = "systematic",
-                 idx_offset: int = 0, n_total: int | None = None, mode: str = "graph"):
+                 idx_offset: int = 0, n_total: int | None = None, mode: str = "graph", reference_max: str = "running"):
+        """``reference_max``: what the exact integer weight masses are taken relative to.  "running" (default): the
+        maximum of the step's weights, found by a running max in the model kernel, masses in the resampling launch.
+        "analytic" (graph mode, scalar-site models): an upper bound of the incremental weight derived from the model
+        (``gen/bounds.py``); the masses are then accumulated in the model kernel itself and the step needs neither
+        the max nor the mass pass.  Same estimator, ancestors differ in the last bits of the
+        masses; a bound so loose that every mass underflows shows up as ``lse_terms[:, 1] == 0``."""
         if resampler != "systematic":
             raise NotImplementedError("the fused filter loop uses systematic resampling; see ParticleCollection.resample")
         if mode not in ("persistent", "graph"):
             raise ValueError(mode)
+        if reference_max not in ("running", "analytic"):
+            raise ValueError(reference_max)
+        if reference_max == "analytic" and mode != "graph":
+            raise ValueError("reference_max='analytic' needs mode='graph'")
+        self.reference_max = reference_max
         self.mode = mode
         self.fuse_mass_resample = True  # graph mode: gjb_mass_resample_systematic when the particle count fits
         self.step = step
@@ -184,6 +195,22 @@ class _Plan:
             self.obs_sites[ir.site_index(addr)] = addr
         self.graph = None
         self.persistent = pf.mode == "persistent"
+        self.analytic = pf.reference_max == "analytic"
+        if self.analytic:
+            from ..gen import bounds
+
+            from ..gen import codegen
+
+            if codegen.group_lanes(ir.width):
+                raise NotImplementedError("reference_max='analytic' exists for scalar-site (quad-mapped) models only: "
+                                          "the lane-group kernels of vector-site models have no mass instantiation yet")
+            self.bound_expr = bounds.log_weight_upper_bound(ir, sorted(self.obs_sites))
+            if self.bound_expr is None:
+                raise ValueError("reference_max='analytic': no particle-free bound of the observed sites' log-density "
+                                 "can be derived for this model (gen/bounds.py)")
+            self.m_ref = torch.empty(1, dtype=torch.float32, device=device)
+            self.tm2 = torch.zeros((2, self.ws.tiles), dtype=torch.int64, device=device)
+            self._m_ref_value = None
         if self.persistent:
             self._build_pf_args()
         else:
@@ -268,6 +295,21 @@ class _Plan:
                     A.ret_out[k] = out.data_ptr()
             lw = self.logw_hist[t] if self.record else self.logw
             A.weight_out = lw.data_ptr()
+            if self.analytic:
+                # masses relative to the analytic bound, accumulated by the model kernel into this step's tile buffer;
+                # the other buffer (next step's) is zeroed by the same launch
+                A.m_ref = self.m_ref.data_ptr()
+                A.tile_mass = self.tm2[t & 1].data_ptr()
+                A.tile_mass_clear = self.tm2[(t + 1) & 1].data_ptr()
+                A.tile_mass_clear_n = self.ws.tiles
+                self.margs.append(A)
+                R = self.ws.systematic_args(
+                    lw, None, self.anc[slot], n_total=pf.n_total, out_lo=pf.idx_offset, anc_base=pf.idx_offset,
+                    key_dev=self.keys[t][2:], lse_out=self.lse[t], m_global=self.m_ref,
+                )
+                R.tile_mass = self.tm2[t & 1].data_ptr()
+                self.rargs.append((lw, R))
+                continue
             A.wmax = self.wmax2[t & 1 :].data_ptr()
             self.margs.append(A)
             R = self.ws.systematic_args(
@@ -283,6 +325,15 @@ class _Plan:
         lib = self.cm.lib
         if self.persistent:
             cabi.check(lib.gjb_model_pf_run(C.byref(self.pf_args), stream), "gjb_model_pf_run")
+            last = (self.T - 1) if self.record else ((self.T - 1) & 1)
+            for k in range(len(self.bufs)):
+                smc_ops.gather_rows(self.bufs[k][last], self.anc[last], self.final[k])
+            return
+        if self.analytic:  # 2 launches per step: model kernel (weights + masses), resampler on the given masses
+            self.tm2.zero_()
+            for t in range(self.T):
+                cabi.check(lib.gjb_model_launch(C.byref(self.margs[t]), stream), "gjb_model_launch")
+                cabi.check(core.gjb_resample_systematic(C.byref(self.rargs[t][1]), stream), "gjb_resample_systematic")
             last = (self.T - 1) if self.record else ((self.T - 1) & 1)
             for k in range(len(self.bufs)):
                 smc_ops.gather_rows(self.bufs[k][last], self.anc[last], self.final[k])
@@ -311,6 +362,8 @@ class _Plan:
     def launches_per_run(self) -> int:
         if self.persistent:
             return 2 + len(self.bufs)  # init + persistent filter kernel + final gather(s)
+        if self.analytic:
+            return 2 * self.T + len(self.bufs)  # (+ one memset node)
         return 1 + (2 if getattr(self, "fuse_mass_resample", False) else 3) * self.T + len(self.bufs)
 
     def execute(self, key, state0, shared, obs, use_graph):
@@ -325,6 +378,16 @@ class _Plan:
         for a in self.obs:
             if self.obs[a].data_ptr() != obs[a].data_ptr():
                 self.obs[a].copy_(obs[a], non_blocking=True)
+        if self.analytic:
+            from ..gen import bounds
+
+            values = {}
+            for k, sh in enumerate(shared):
+                values[len(self.state_in) + k] = sh.detach().cpu().numpy() if isinstance(sh, torch.Tensor) else sh
+            m = bounds.evaluate_invariant(self.bound_expr, values)
+            if m != self._m_ref_value:
+                self.m_ref.copy_(torch.tensor([m], dtype=torch.float32), non_blocking=True)
+                self._m_ref_value = m
         if use_graph and not self.persistent:
             if self.graph is None:
                 # warm-up launch outside capture (module load), then capture once

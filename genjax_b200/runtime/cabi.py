@@ -13,6 +13,7 @@ import torch
 
 from . import build
 
+ABI_VERSION = 9  # GJB_ABI_VERSION of include/genjax_b200.h this binding mirrors (tests/test_abi.py keeps them equal)
 GJB_MAX_SITES = 16
 GJB_MAX_ARGS = 16
 GJB_MAX_RETS = 8
@@ -60,6 +61,10 @@ class ModelArgs(C.Structure):
         ("score_out", _p),
         ("weight_out", _p),
         ("wmax", _p),
+        ("m_ref", _p),
+        ("tile_mass", _p),
+        ("tile_mass_clear", _p),
+        ("tile_mass_clear_n", _i64),
     ]
 
 
@@ -239,8 +244,8 @@ def core():
     if _core is None:
         path = build.build_core()
         _core = _bind(C.CDLL(str(path)), CORE_PROTOTYPES)
-        if _core.gjb_abi_version() != 8:
-            raise GjbError("libgjb_core.so ABI mismatch")
+        if _core.gjb_abi_version() != ABI_VERSION:
+            raise GjbError(f"libgjb_core.so reports ABI {_core.gjb_abi_version()}, this binding is for {ABI_VERSION}")
     return _core
 
 

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GJB_ABI_VERSION 8
+#define GJB_ABI_VERSION 9
 
 #define GJB_E_ARG (-1)      /* null / misaligned pointer, negative size          */
 #define GJB_E_RANGE (-2)    /* size beyond what the kernel supports              */
@@ -292,6 +292,16 @@ typedef struct gjb_model_args {
   float* score_out;          /* nullable                                        */
   float* weight_out;         /* nullable                                        */
   uint32_t* wmax;            /* nullable: atomic max of weight_out (ordered-uint) */
+  /* Reference-maximum filter step (filter-flag instantiation only, idx_offset % 4 == 0): with a reference
+   * *m_ref >= every weight of this launch known BEFORE the launch (an analytic bound of the incremental weight,
+   * gen/bounds.py), the exact integer masses round(2^36 exp(w - *m_ref)) are accumulated per 2048-particle tile while
+   * the weights are still in registers, so the step needs neither the max pass nor the mass pass:
+   * gjb_resample_systematic(m_global = m_ref, tile_mass) follows directly.  tile_mass must be zero on entry;
+   * tile_mass_clear[0 .. tile_mass_clear_n) (the buffer of the NEXT step) is zeroed by this launch.            */
+  const float* m_ref;                  /* nullable */
+  unsigned long long* tile_mass;       /* nullable; [ceil(n / 2048)] */
+  unsigned long long* tile_mass_clear; /* nullable */
+  int64_t tile_mass_clear_n;
 } gjb_model_args;
 
 /* JSON description of the captured model (sites, args, layouts); static storage. */

@@ -255,7 +255,7 @@ def pf_step_keys(key: rng.Key, t: int):
 
 
 def particle_filter(step_model, key: rng.Key, state0, observations, shared_args=(), resampler="systematic",
-                    record=False):
+                    record=False, m_ref=None):
     """Bootstrap PF.  ``step_model(h, *state, *shared_args)`` returns the new
     state (array or tuple of arrays); ``observations`` is a list of dicts
     addr -> value constrained at each step.
@@ -273,11 +273,13 @@ def particle_filter(step_model, key: rng.Key, state0, observations, shared_args=
         k_prop, k_res = pf_step_keys(key, t)
         keys = rng.split(k_prop, n)
         tr, w = gfi.generate(step_model, keys, obs, state + tuple(shared_args))
-        inc = log_mean_exp(w)
+        # m_ref: a reference maximum known before the weights are (an analytic bound of the incremental weight);
+        # the integer masses, hence ancestors and estimate, are then taken relative to it instead of max(w)
+        inc = log_mean_exp(w) if m_ref is None else log_mean_exp_ref(w, m_ref)
         incs.append(inc)
         logz += inc
         if resampler == "systematic":
-            anc = resample_systematic(w, k_res)
+            anc = resample_systematic(w, k_res) if m_ref is None else resample_systematic_pull(w, k_res, M=F32(m_ref))
         else:
             anc = resample_multinomial(w, rng.split(k_res, n))
         rv = tr.retval if isinstance(tr.retval, tuple) else (tr.retval,)

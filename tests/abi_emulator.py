@@ -92,6 +92,26 @@ def evaluate(e, env, cache):
     return v
 
 
+def _accumulate_tile_mass(A, n, t):
+    """Reference-maximum step (gjb_model_args.m_ref / tile_mass): exact integer masses of the weights relative to
+    *m_ref, added per 2048-particle tile; the next step's buffer is zeroed."""
+    if not (A.tile_mass or A.m_ref):
+        return
+    from oracle import smc as osmc
+
+    if not (A.tile_mass and A.m_ref) or int(A.idx_offset) & 3:
+        raise ValueError("emulator: m_ref and tile_mass come together, on a quad-aligned launch")
+    if A.tile_mass_clear and A.tile_mass_clear_n > 0:
+        _arr(A.tile_mass_clear, int(A.tile_mass_clear_n), C.c_uint64, np.uint64)[:] = 0
+    mref = _view(A.m_ref, 1, F32)[0]
+    with np.errstate(invalid="ignore"):
+        q = osmc.det_exp_q((np.asarray(t, dtype=F32) - mref).astype(F32))
+    tiles = (n + 2047) // 2048
+    tm = _arr(A.tile_mass, tiles, C.c_uint64, np.uint64)
+    for b in range(tiles):
+        tm[b] += q[b * 2048:(b + 1) * 2048].sum(dtype=np.uint64)
+
+
 def _view(ptr, count, dtype):
     if not ptr or count == 0:
         return None
@@ -209,6 +229,7 @@ class EmulatedModelLib:
             if A.score_in:
                 t = (t - _view(A.score_in, n, F32)).astype(F32)
             _view(A.weight_out, n, F32)[:] = t
+            _accumulate_tile_mass(A, n, t)
             if A.wmax:  # running maximum of the weights in the order-preserving integer encoding (atomicMax)
                 w = _arr(A.wmax, 1, C.c_uint32, np.uint32)
                 with np.errstate(invalid="ignore"):
@@ -430,7 +451,7 @@ class EmulatedCore:
     oracle/smc.py.  Multi-GPU, fused cooperative and filter entry points are GPU-only and absent on purpose."""
 
     def gjb_abi_version(self):
-        return 8
+        return 9
 
     def gjb_mass_resample_fits(self, n):
         return 0
@@ -484,7 +505,7 @@ class EmulatedCore:
         from oracle import smc as osmc
 
         R = r_ref._obj
-        if R.c_offset or R.s_total or R.m_global:
+        if R.c_offset or R.s_total:
             raise NotImplementedError("emulator: sharded resampling is a GPU-only path")
         key0, key1, key_index = int(R.key0), int(R.key1), int(R.key_index)
         if R.key_dev:
@@ -492,7 +513,7 @@ class EmulatedCore:
             key0, key1, key_index = int(kd[0]), int(kd[1]), int(kd[2]) | (int(kd[3]) << 32)
         n = int(R.n)
         logw = _view(R.logw, n, F32)
-        M = self._max(R.wmax, None)
+        M = self._max(R.wmax, R.m_global)
         tiles = max(1, (n + _TILE - 1) // _TILE)
         S = int(_arr(R.tile_mass, tiles, C.c_uint64, np.uint64).sum(dtype=np.uint64))
         anc = _view(R.ancestors, int(R.out_n), I32)
@@ -506,7 +527,7 @@ class EmulatedCore:
             full = np.repeat(np.arange(n, dtype=np.int64) + int(R.anc_base), (cnt - prev).astype(np.int64))
             anc[:] = full[lo:lo + int(R.out_n)].astype(I32)
         if R.lse_out:
-            self.gjb_lse_finalize(R.tile_mass, n, R.wmax, None, int(R.n_total), R.lse_out, stream)
+            self.gjb_lse_finalize(R.tile_mass, n, R.wmax, R.m_global, int(R.n_total), R.lse_out, stream)
         if R.wmax_next:
             _arr(R.wmax_next, 1, C.c_uint32, np.uint32)[0] = 0x007FFFFF
         return 0
@@ -561,7 +582,12 @@ class HostKernelModelLib(EmulatedModelLib):
         wmax = A.wmax
         A.wmax = None  # the block-level max reduction needs a real thread block; redone below from the weights
         try:
-            rc = self.h.host_model_launch(a_ref)
+            if A.tile_mass or A.m_ref:  # the launcher's dispatch: the filter-flag instantiation with masses
+                if not hasattr(self.h, "host_model_launch_mass") or not (A.tile_mass and A.m_ref and A.weight_out):
+                    return -3
+                rc = self.h.host_model_launch_mass(a_ref)
+            else:
+                rc = self.h.host_model_launch(a_ref)
         finally:
             A.wmax = wmax
         if rc == 0 and wmax:
@@ -621,6 +647,24 @@ def install(monkeypatch, host_kernels=None):
         return _EmulatedCompiledModel(ir, chain, pf_obs, host_kernels)
 
     monkeypatch.setattr(static, "compile_ir", compile_ir)
+
+    # module-level @gen functions (genjax_b200.workloads) keep their compiled models in a per-object cache that other
+    # tests may have filled with REAL libraries: under emulation every generative function uses a cache of its own
+    cache_name = "_emu_cache_host" if host_kernels else "_emu_cache_ir"
+
+    def with_private_cache(method):
+        def wrapped(self, *args, **kwargs):
+            saved = self._cache
+            self._cache = self.__dict__.setdefault(cache_name, {})
+            try:
+                return method(self, *args, **kwargs)
+            finally:
+                self._cache = saved
+
+        return wrapped
+
+    for name in ("compiled_for", "prebuild"):
+        monkeypatch.setattr(static.StaticGenerativeFunction, name, with_private_cache(getattr(static.StaticGenerativeFunction, name)))
     from genjax_b200.inference import mcmc
 
     monkeypatch.setattr(mcmc, "compile_ir", compile_ir)

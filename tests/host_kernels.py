@@ -29,6 +29,13 @@ extern "C" int host_model_launch(const gjb_model_args* a) {
   return 0;
 }
 '''
+_MASS_DRIVER = r'''
+extern "C" int host_model_launch_mass(const gjb_model_args* a) {
+  gridDim.x = 1; gridDim.y = 1; gridDim.z = 1; blockDim.x = 1; blockIdx.x = 0;
+  for (unsigned t = 0; t < (unsigned)kThreads; ++t) { threadIdx.x = t; model_kernel_static_mass(*a); }
+  return 0;
+}
+'''
 _CHAIN_DRIVER = r'''
 extern "C" int host_%(kind)s_chain(const gjb_chain_args* a) {
   gridDim.x = 1; gridDim.y = 1; gridDim.z = 1; blockDim.x = 1; blockIdx.x = 0; threadIdx.x = 0;
@@ -51,6 +58,8 @@ def build(source: str):
     cut = source.index('extern "C" {')
     body = source[:cut].replace("extern __shared__ __align__(16) unsigned char dyn_smem[];", "static unsigned char dyn_smem[1 << 16];")
     text = body + _DRIVER
+    if "model_kernel_static_mass(" in body:
+        text += _MASS_DRIVER
     for kind in ("mh", "hmc"):
         if f"{kind}_chain_kernel(" in body:
             text += _CHAIN_DRIVER % {"kind": kind}

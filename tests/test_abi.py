@@ -50,6 +50,9 @@ def test_core_library_exports_every_declared_symbol(libs):
     assert set(cabi.CORE_PROTOTYPES) == set(core), "ctypes prototypes and the header disagree"
     version = int(re.search(r"#define GJB_ABI_VERSION (\d+)", open(HEADER).read()).group(1))
     assert core_lib.gjb_abi_version() == version
+    from genjax_b200.runtime import cabi
+
+    assert cabi.ABI_VERSION == version  # the ctypes binding mirrors the same header revision
 
 
 def test_model_libraries_export_every_declared_symbol(libs):

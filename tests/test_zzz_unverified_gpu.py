@@ -269,3 +269,47 @@ def test_filter_maxima_stay_below_the_analytic_bound(device):
     res = pf.run(gj.key(1), x0, gj.C["y"].set(ys))
     m = res.lse_terms[:, 0].cpu().numpy()
     assert (m <= bound + 1e-6).all() and (m > bound - 0.01).all()  # 20 000 particles: some particle sits on the mode
+
+
+# ------------------------------------------------------------------ reference-maximum filter step
+
+
+@pytest.mark.parametrize("n", [7, 2048, 100_001])
+def test_analytic_reference_filter_matches_oracle(device, n):
+    """ParticleFilter(reference_max="analytic"): masses accumulated by model_kernel_static_mass relative to the
+    analytic bound, resampler on those masses (same scenario as tests/test_pf_reference_max_host.py)."""
+    gj = _gj()
+    from genjax_b200.inference.pf import ParticleFilter
+    from genjax_b200.workloads import LG_A, LG_C, LG_Q, LG_R, lgssm_step
+    from oracle import smc as osmc
+
+    def o_step(h, x_prev):
+        x = h.normal("x", F32(LG_A) * x_prev, F32(LG_Q))
+        h.normal("y", F32(LG_C) * x, F32(LG_R))
+        return x
+
+    T = 6
+    ys = osmc.simulate_lgssm(1, T, 1, LG_A, LG_Q, LG_C, LG_R)[:, 0]
+    x0 = np.random.default_rng(n).standard_normal(n).astype(F32)
+    pf = ParticleFilter(lgssm_step, n, reference_max="analytic")
+    bound = pf.weight_upper_bound(torch.from_numpy(x0), gj.C["y"].set(torch.from_numpy(ys)))
+    for use_graph in (False, True):
+        res = pf.run(gj.key(17), torch.from_numpy(x0), gj.C["y"].set(torch.from_numpy(ys)), record=True, use_graph=use_graph)
+        anc, lws, xs = res.ancestors.cpu().numpy(), res.history["log_weights"].cpu().numpy(), res.history["state"][0].cpu().numpy()
+        x_in, okey = x0, rng.key(17)
+        for t in range(T):
+            kp, kr = osmc.pf_step_keys(okey, t)
+            otr, ow = ogfi.generate(o_step, rng.split(kp, n), {"y": F32(ys[t])}, (x_in,))
+            np.testing.assert_allclose(xs[t], otr.choices["x"], rtol=1e-5, atol=2e-6)
+            np.testing.assert_allclose(lws[t], ow, rtol=1e-5, atol=2e-5)
+            assert lws[t].max() <= bound + 1e-6
+            assert np.array_equal(anc[t], osmc.resample_systematic_pull(lws[t], kr, M=F32(bound)))
+            M, S, inc = res.lse_terms[t].cpu().numpy()
+            assert M == float(F32(bound))
+            assert S == float(int(osmc.det_exp_q((lws[t] - F32(bound)).astype(F32)).sum(dtype=np.uint64)))
+            assert inc == pytest.approx(osmc.log_mean_exp(lws[t]), abs=2e-7)
+            x_in = xs[t][anc[t]]
+        np.testing.assert_array_equal(res.state[0].cpu().numpy(), x_in)
+    plain = ParticleFilter(lgssm_step, n).run(gj.key(17), torch.from_numpy(x0), gj.C["y"].set(torch.from_numpy(ys)), record=True)
+    assert torch.equal(plain.history["log_weights"][0], res.history["log_weights"][0])
+    assert plain.log_increments[0].item() == pytest.approx(res.log_increments[0].item(), abs=2e-7)
