@@ -418,8 +418,20 @@ def _emulated_pf_run(lib, q_ref):
     return 0
 
 
-EmulatedModelLib.gjb_model_pf_grid = lambda self, n: -1 if n < 0 else 4
-EmulatedModelLib.gjb_model_pf_run = lambda self, q_ref, stream: _emulated_pf_run(self, q_ref)
+def _pf_run(lib, q_ref):
+    """Small filters run the REAL persistent kernel as a grid of one block under the SIMT shim (when the generated
+    source is at hand); larger ones use the per-step emulation above."""
+    source = getattr(lib, "source", None)
+    Q = q_ref._obj
+    if source is not None and "pf_kernel(" in source and int(Q.n) <= 20000:
+        import simt_kernels
+
+        return simt_kernels.model(source).s_pf_run(q_ref)
+    return _emulated_pf_run(lib, q_ref)
+
+
+EmulatedModelLib.gjb_model_pf_grid = lambda self, n: -1 if n < 0 else 1
+EmulatedModelLib.gjb_model_pf_run = lambda self, q_ref, stream: _pf_run(self, q_ref)
 EmulatedModelLib.gjb_model_mh_chain = lambda self, a_ref, stream: _emulated_chain(self, a_ref, "mh")
 EmulatedModelLib.gjb_model_hmc_chain = lambda self, a_ref, stream: _emulated_chain(self, a_ref, "hmc")
 
@@ -608,6 +620,85 @@ class HostKernelModelLib(EmulatedModelLib):
         return self.h.host_hmc_chain(a_ref) if hasattr(self.h, "host_hmc_chain") else -3
 
 
+class SimtKernelModelLib(EmulatedModelLib):
+    """The generated source of a lane-group (vector-site) model run with real block semantics (tests/simt_kernels.py):
+    slower than the thread-at-a-time host build, so only used where that one cannot run."""
+
+    def __init__(self, ir, chain, source):
+        super().__init__(ir, chain)
+        import simt_kernels
+
+        self.s = simt_kernels.model(source)
+        from genjax_b200.gen import codegen
+
+        self.ppb = 256 // max(codegen.group_lanes(ir.width), 1)
+
+    def gjb_model_launch(self, a_ref, stream):
+        A = a_ref._obj
+        n = int(A.n)
+        if n < 0:
+            return -1
+        if n == 0:
+            return 0
+        if A.peer_args or A.link:
+            raise NotImplementedError("SIMT kernels: multi-GPU links are a GPU-only path")
+        if A.tile_mass or A.m_ref:
+            return -3
+        self.launches += 1
+        return self.s.s_model_launch(a_ref, C.c_int(max(1, min(4, (n + self.ppb - 1) // self.ppb))))
+
+    def gjb_model_mh_chain(self, a_ref, stream):
+        return self.s.s_mh_chain(a_ref) if hasattr(self.s, "s_mh_chain") else -3
+
+    def gjb_model_hmc_chain(self, a_ref, stream):
+        return self.s.s_hmc_chain(a_ref) if hasattr(self.s, "s_hmc_chain") else -3
+
+
+class SimtCore(EmulatedCore):
+    """libgjb_core's single-device entry points on their REAL kernels, run with block semantics on the CPU
+    (tests/simt_kernels.py) for inputs small enough to stay quick; larger ones fall back to the oracle restatement."""
+
+    LIMIT = 40_000
+
+    def __init__(self):
+        import simt_kernels
+
+        self.k = simt_kernels.core()
+
+    def gjb_weight_max(self, logw, n, wmax, stream):
+        if n > self.LIMIT or n <= 0:
+            return super().gjb_weight_max(logw, n, wmax, stream)
+        return self.k.s_weight_max(C.c_void_p(logw), C.c_int64(n), C.c_void_p(wmax), C.c_int(max(1, min(4, (n + 255) // 256))))
+
+    def gjb_weight_mass(self, logw, n, wmax, m_global, tile_mass, stream):
+        if n > self.LIMIT or n <= 0:
+            return super().gjb_weight_mass(logw, n, wmax, m_global, tile_mass, stream)
+        return self.k.s_weight_mass(C.c_void_p(logw), C.c_int64(n), C.c_void_p(wmax), C.c_void_p(m_global), C.c_void_p(tile_mass))
+
+    def gjb_lse_finalize(self, tile_mass, n, wmax, m_global, n_total, lse_out, stream):
+        tiles = max(1, (n + _TILE - 1) // _TILE)
+        return self.k.s_lse_finalize(C.c_void_p(tile_mass), C.c_int(tiles), C.c_void_p(wmax), C.c_void_p(m_global),
+                                     C.c_int64(n_total), C.c_void_p(lse_out))
+
+    def gjb_resample_systematic(self, r_ref, stream):
+        R = r_ref._obj
+        if int(R.n) > self.LIMIT or int(R.n) <= 0 or int(R.out_n) <= 0:
+            return super().gjb_resample_systematic(r_ref, stream)
+        return self.k.s_resample_systematic(r_ref)
+
+    def gjb_resample_multinomial(self, logw, n, wmax, tile_mass, cdf, key0, key1, idx_offset, n_out, ancestors, stream):
+        if n > self.LIMIT or n <= 0 or n_out <= 0:
+            return super().gjb_resample_multinomial(logw, n, wmax, tile_mass, cdf, key0, key1, idx_offset, n_out, ancestors, stream)
+        return self.k.s_multinomial(C.c_void_p(logw), C.c_int64(n), C.c_void_p(wmax), C.c_void_p(tile_mass), C.c_void_p(cdf),
+                                    C.c_uint32(key0), C.c_uint32(key1), C.c_uint64(idx_offset), C.c_int64(n_out), C.c_void_p(ancestors))
+
+    def gjb_gather_rows(self, src, ancestors, dst, n_out, row_bytes, stream):
+        if n_out > self.LIMIT or n_out <= 0:
+            return super().gjb_gather_rows(src, ancestors, dst, n_out, row_bytes, stream)
+        return self.k.s_gather_rows(C.c_void_p(src), C.c_void_p(ancestors), C.c_void_p(dst), C.c_int64(n_out), C.c_int(row_bytes // 4),
+                                    C.c_int(max(1, min(4, (n_out * (row_bytes // 4) + 255) // 256))))
+
+
 class _EmulatedCompiledModel:
     def __init__(self, ir, chain=None, pf_obs=None, host_kernels=False):
         self.ir = ir
@@ -619,6 +710,9 @@ class _EmulatedCompiledModel:
             source = codegen.generate(ir, pf_obs, chain)
             if hk.is_host_runnable(source):
                 self.lib = HostKernelModelLib(ir, chain, hk.build(source))
+            else:
+                self.lib = SimtKernelModelLib(ir, chain, source)
+            self.lib.source = source
         if self.lib is None:
             self.lib = EmulatedModelLib(ir, chain)
         self.path = None
@@ -668,7 +762,7 @@ def install(monkeypatch, host_kernels=None):
     from genjax_b200.inference import mcmc
 
     monkeypatch.setattr(mcmc, "compile_ir", compile_ir)
-    core = EmulatedCore()
+    core = SimtCore() if host_kernels else EmulatedCore()
     monkeypatch.setattr(cabi, "core", lambda: core)
     # CUDA graphs are a device feature: under emulation the filter enqueues its launches eagerly on every run
     from genjax_b200.inference import pf

@@ -97,10 +97,31 @@ extern "C" int s_model_launch(const gjb_model_args* a, int grid) {
   return 0;
 }
 '''
+PF_DRIVER = r'''
+extern "C" int s_pf_run(const gjb_pf_args* q) {  // the persistent cooperative filter as a grid of ONE block
+  const gjb_pf_args Q = *q;
+  simt::launch(1, 32, [=] { pf_init_kernel(Q.wmax, Q.barrier); });
+  simt::launch(1, kThreads, [=] { pf_kernel(Q); });
+  return 0;
+}
+'''
+CHAIN_DRIVER = r'''
+extern "C" int s_%(kind)s_chain(const gjb_chain_args* a) {
+  const gjb_chain_args A = *a;
+  simt::launch(1, 128, [=] { %(kind)s_chain_kernel(A); });
+  return 0;
+}
+'''
 
 
 def model(source: str):
     """A generated model source (quad- or lane-group-mapped) with a SIMT driver for its generic model_kernel."""
     body = source[: source.index('extern "C" {')].replace(
         "extern __shared__ __align__(16) unsigned char dyn_smem[];", "static unsigned char dyn_smem[1 << 16];")
-    return _compile(body + MODEL_DRIVER, "model")
+    text = body + MODEL_DRIVER
+    if "pf_kernel(" in body:
+        text += PF_DRIVER
+    for kind in ("mh", "hmc"):
+        if f"{kind}_chain_kernel(" in body:
+            text += CHAIN_DRIVER % {"kind": kind}
+    return _compile(text, "model")

@@ -15,9 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # the fused cooperative resampler and the multi-GPU links have no emulation; the Kalman comparisons and the 3M-particle
 # case pass too but take a minute in NumPy
 _PF = "not fused_mass_resample and not multi_gpu and not matches_kalman and not 3000000"
-# chain entry points are emulated with oracle/mcmc.py over the symbolic log-density and its reverse-mode gradient
-# (gen/autodiff.py); the 8-schools run passes too but takes a minute in NumPy, and the mixture has no oracle sampler
-_MCMC = "not eight_schools and not gmm"
+_MCMC = "not gmm"  # the mixture has no oracle sampler; everything else runs its generated chain kernels on the host
 
 
 @pytest.mark.parametrize("files", [
@@ -30,8 +28,9 @@ _MCMC = "not eight_schools and not gmm"
     ["tests/test_mcmc_gpu.py", "-k", _MCMC],
 ])
 def test_gpu_tests_host_paths_under_emulation(files):
-    # GJB_EMULATE_KERNELS=host: scalar-site models and chain kernels execute their GENERATED CUDA source compiled for
-    # the host (tests/host_kernels.py); vector-site models fall back to the IR interpreter
+    # GJB_EMULATE_KERNELS=host: every model launch, chain launch and small filter runs the GENERATED CUDA source on the
+    # host -- thread by thread for scalar-site models (tests/host_kernels.py), with real block semantics for vector-site
+    # models, the persistent filter kernel and the kernels of libgjb_core (tests/simt_kernels.py)
     env = dict(os.environ, GJB_EMULATE="1", GJB_EMULATE_KERNELS="host", GJB_RUN_UNVERIFIED="1", CUDA_VISIBLE_DEVICES="")
     r = subprocess.run([sys.executable, "-m", "pytest", *files, "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider"],
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
