@@ -517,8 +517,8 @@ class EmulatedCore:
         from oracle import smc as osmc
 
         R = r_ref._obj
-        if R.c_offset or R.s_total:
-            raise NotImplementedError("emulator: sharded resampling is a GPU-only path")
+        c_off = int(_arr(R.c_offset, 1, C.c_uint64, np.uint64)[0]) if R.c_offset else 0
+        s_tot = int(_arr(R.s_total, 1, C.c_uint64, np.uint64)[0]) if R.s_total else None
         key0, key1, key_index = int(R.key0), int(R.key1), int(R.key_index)
         if R.key_dev:
             kd = _arr(R.key_dev, 4, C.c_uint32, np.uint32)
@@ -527,17 +527,22 @@ class EmulatedCore:
         logw = _view(R.logw, n, F32)
         M = self._max(R.wmax, R.m_global)
         tiles = max(1, (n + _TILE - 1) // _TILE)
-        S = int(_arr(R.tile_mass, tiles, C.c_uint64, np.uint64).sum(dtype=np.uint64))
+        S = int(_arr(R.tile_mass, tiles, C.c_uint64, np.uint64).sum(dtype=np.uint64)) if s_tot is None else s_tot
         anc = _view(R.ancestors, int(R.out_n), I32)
         lo = int(R.out_lo)
         if S == 0:
             anc[:] = np.arange(lo, lo + int(R.out_n), dtype=I32) - lo + int(R.anc_base)
         else:
             u0 = osmc.resample_u0(orng.Key((key0, key1), key_index))
-            cnt, _ = osmc.systematic_counts(logw, u0, n_out=int(R.n_total), M=M, S=S)
-            prev = np.concatenate([[0], cnt[:-1]])
-            full = np.repeat(np.arange(n, dtype=np.int64) + int(R.anc_base), (cnt - prev).astype(np.int64))
-            anc[:] = full[lo:lo + int(R.out_n)].astype(I32)
+            cnt, _ = osmc.systematic_counts(logw, u0, n_out=int(R.n_total), M=M, S=S, c_offset=c_off)
+            scale = np.float64(int(R.n_total)) / np.float64(S)
+            start = 0 if c_off == 0 else int(np.clip(np.ceil(np.float64(c_off) * scale - np.float64(u0)), 0, int(R.n_total)))
+            prev = np.concatenate([[start], cnt[:-1]])
+            # a shard writes only the offspring of ITS parents that fall inside the window; other slots are untouched
+            for i in np.nonzero(cnt > prev)[0]:
+                a, b = max(int(prev[i]), lo), min(int(cnt[i]), lo + int(R.out_n))
+                if b > a:
+                    anc[a - lo:b - lo] = i + int(R.anc_base)
         if R.lse_out:
             self.gjb_lse_finalize(R.tile_mass, n, R.wmax, R.m_global, int(R.n_total), R.lse_out, stream)
         if R.wmax_next:
@@ -562,6 +567,21 @@ class EmulatedCore:
         w0, w1, _, _ = orng.site_words((key0, key1), idx, 0, 1)
         r = (w0.astype(np.uint64) << np.uint64(32)) | w1.astype(np.uint64)
         anc[:] = np.searchsorted(Cq, osmc._mulhi64(r, np.uint64(S)), side="right").astype(I32)
+        return 0
+
+    def gjb_philox_fill(self, key0, key1, idx_offset, site, chunk, n, out4, stream):
+        from oracle import rng as orng
+
+        idx = np.arange(n, dtype=np.uint64) + np.uint64(idx_offset)
+        w = np.stack(orng.site_words((key0, key1), idx, site, chunk), axis=1).astype(np.uint32)
+        _arr(out4, 4 * n, C.c_uint32, np.uint32)[:] = w.reshape(-1)
+        return 0
+
+    def gjb_normal_fill(self, key0, key1, idx_offset, site, n, d, out, stream):
+        from oracle import rng as orng
+
+        idx = np.arange(n, dtype=np.uint64) + np.uint64(idx_offset)
+        _view(out, n * d, F32)[:] = orng.normal_vec((key0, key1), idx, site, d).reshape(-1)
         return 0
 
     def gjb_gather_rows(self, src, ancestors, dst, n_out, row_bytes, stream):
@@ -691,6 +711,18 @@ class SimtCore(EmulatedCore):
             return super().gjb_resample_multinomial(logw, n, wmax, tile_mass, cdf, key0, key1, idx_offset, n_out, ancestors, stream)
         return self.k.s_multinomial(C.c_void_p(logw), C.c_int64(n), C.c_void_p(wmax), C.c_void_p(tile_mass), C.c_void_p(cdf),
                                     C.c_uint32(key0), C.c_uint32(key1), C.c_uint64(idx_offset), C.c_int64(n_out), C.c_void_p(ancestors))
+
+    def gjb_philox_fill(self, key0, key1, idx_offset, site, chunk, n, out4, stream):
+        if n > self.LIMIT or n <= 0:
+            return super().gjb_philox_fill(key0, key1, idx_offset, site, chunk, n, out4, stream)
+        return self.k.s_philox_fill(C.c_uint32(key0), C.c_uint32(key1), C.c_uint64(idx_offset), C.c_uint32(site), C.c_uint32(chunk),
+                                    C.c_int64(n), C.c_void_p(out4))
+
+    def gjb_normal_fill(self, key0, key1, idx_offset, site, n, d, out, stream):
+        if n * d > 4 * self.LIMIT or n <= 0:
+            return super().gjb_normal_fill(key0, key1, idx_offset, site, n, d, out, stream)
+        return self.k.s_normal_fill(C.c_uint32(key0), C.c_uint32(key1), C.c_uint64(idx_offset), C.c_uint32(site), C.c_int64(n),
+                                    C.c_int(d), C.c_void_p(out))
 
     def gjb_gather_rows(self, src, ancestors, dst, n_out, row_bytes, stream):
         if n_out > self.LIMIT or n_out <= 0:

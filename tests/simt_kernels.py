@@ -54,6 +54,14 @@ int s_multinomial(const float* logw, int64_t n, const uint32_t* wmax, const uint
   simt::launch((int)((n_out + 255) / 256), 256, [=] { gjb::multinomial_search_kernel(cdf, n, k0, k1, idx_offset, n_out, anc); });
   return 0;
 }
+int s_philox_fill(uint32_t k0, uint32_t k1, uint64_t off, uint32_t site, uint32_t chunk, int64_t n, uint4* out) {
+  simt::launch((int)((n + 255) / 256 < 4 ? (n + 255) / 256 : 4), 256, [=] { gjb::philox_fill_kernel(k0, k1, off, site, chunk, n, out); });
+  return 0;
+}
+int s_normal_fill(uint32_t k0, uint32_t k1, uint64_t off, uint32_t site, int64_t n, int d, float* out) {
+  simt::launch(4, 256, [=] { gjb::normal_fill_kernel(k0, k1, off, site, n, d, out); });
+  return 0;
+}
 int s_gather_rows(const uint32_t* src, const int32_t* anc, uint32_t* dst, int64_t n_out, int w, int grid) {
   simt::launch(grid, 256, [=] { gjb::gather_rows_kernel<uint32_t>(src, anc, dst, n_out, w); });
   return 0;

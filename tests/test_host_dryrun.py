@@ -19,6 +19,7 @@ _MCMC = "not gmm"  # the mixture has no oracle sampler; everything else runs its
 
 
 @pytest.mark.parametrize("files", [
+    ["tests/test_core_gpu.py"],
     ["tests/test_gfi_gpu.py"],
     ["tests/test_zzz_unverified_gpu.py"],
     ["tests/test_zzz_static_reference_gpu.py"],
