@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--reference-max", default="running", choices=["running", "analytic"],
                     help="running (default): max + mass passes; analytic: masses relative to an analytic bound, accumulated "
                          "in the model kernel (graph mode, d = 1; DESIGN.md section 10 -- not yet measured on a device)")
+    ap.add_argument("--single-pass", action="store_true",
+                    help="with --reference-max analytic: ONE launch per step (output-slot resampling of the previous step fused "
+                         "into the model kernel, model_kernel_static_pull; DESIGN.md section 10 -- not yet measured on a device)")
     ap.add_argument("--mode", default="graph", choices=["persistent", "graph"],
                     help="persistent: one cooperative launch per filter; graph: 2 launches per step in a CUDA graph")
     return ap.parse_args()
@@ -366,7 +369,8 @@ def run_ours(args):
 
         pf = DistributedParticleFilter(model, n)
     else:
-        pf = ParticleFilter(model, n, idx_offset=0, mode=args.mode, reference_max=args.reference_max)
+        pf = ParticleFilter(model, n, idx_offset=0, mode=args.mode, reference_max=args.reference_max,
+                            single_pass=args.single_pass)
     obs_dev = gj.C["y"].set(ys_dev)
     obs_host = gj.C["y"].set(ys_host)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
@@ -525,7 +529,21 @@ def run_ours(args):
                 "what": "exact integer weight mass + grid barrier + CDF scan + systematic offspring ranges (gjb_mass_resample_systematic)"}
             if mr_ms > model_ms:
                 dominant = "mass_resample_kernel"
-        if not global_resample and getattr(plan, "analytic", False):
+        if not global_resample and getattr(plan, "single_pass", False):
+            # single-pass step: step 0 leaves weights + tile masses; step 1's launch (pull-resample them into the CTA's
+            # own slots, gather, propose, score, masses) is the kernel every later step repeats.  Re-launching it adds
+            # to the same tile masses again, which nothing reads here.
+            plan.tm3.zero_()
+            plan.cm.lib.gjb_model_launch(C.byref(plan.margs[0]), stream)
+            sp_ms = time_launches(lambda: plan.cm.lib.gjb_model_launch(C.byref(plan.margs[1]), stream), 200, 20)
+            sp_bytes = model_bytes + 4 * n  # + the previous step's log-weights; the ancestors are written AND read back
+            kernels["model_kernel_static_pull"] = {
+                "kernel_us": sp_ms * 1e3, "algorithmic_bytes_per_launch": sp_bytes, "achieved": sp_bytes / (sp_ms * 1e-3) / 1e9,
+                "frac": sp_bytes / (sp_ms * 1e-3) / 1e9 / peak,
+                "what": "output-slot systematic resampling of the previous step + gather + propose + logpdf + exact integer "
+                        "masses relative to the analytic bound, one launch per filter step (gjb_model_launch)"}
+            dominant = "model_kernel_static_pull"
+        elif not global_resample and getattr(plan, "analytic", False):
             # reference-maximum step: the model kernel also accumulates the masses; the resampler takes them as given
             core = cabi.core()
             plan.tm2.zero_()
@@ -607,7 +625,7 @@ def run_ours(args):
                           "on 8 bytes) per run, inside the timed region; weak scaling. --multi-gpu global times the "
                           "global-resampling filter instead"),
             "logZ_last": logz,
-            "reference_max": args.reference_max,
+            "reference_max": args.reference_max, "single_pass": bool(args.single_pass),
         },
         "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                 "logZ_last": logz_e2e},

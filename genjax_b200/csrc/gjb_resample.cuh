@@ -407,4 +407,65 @@ __device__ __forceinline__ double resample_u0(uint32_t key0, uint32_t key1, uint
   return (double)u01(philox4x32_10(make_uint4((uint32_t)key_index, (uint32_t)(key_index >> 32), 0u, 0u), key0, key1).x);
 }
 
+// Output-slot ("pull") resampling for ONE CTA: the ancestors of the offspring slots [w_lo, w_lo + w_n) it owns.
+// The inclusive prefix of all tile masses is built in shared memory (`pre`, n_tiles <= kPullMaxTiles), the first
+// parent tile whose offspring reach the window is found by bisection, and every parent tile overlapping the window
+// is scanned by resample_tile restricted to the window (anc[j - w_lo] = parent of slot j).  Under balanced weights
+// that is the tile with the same index and a neighbour.  Returns the total mass S (0: identity ancestors written).
+// oracle: oracle/smc.py resample_systematic_pull.  All kThreads threads must call.
+constexpr int kPullMaxTiles = 2048;
+template <bool kCg>
+__device__ __forceinline__ uint64_t pull_ancestors(const float* __restrict__ logw, int64_t n,
+                                                   const unsigned long long* __restrict__ tile_mass, int n_tiles, float M,
+                                                   int64_t n_total, double u0, int64_t w_lo, int64_t w_n,
+                                                   int32_t* __restrict__ anc, TileSmem& sm, int32_t* heads, uint64_t* pre) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (n_tiles + kThreads - 1) / kThreads;
+  uint64_t run = 0;
+  for (int k = 0; k < per; ++k) {
+    const int t = tid * per + k;
+    if (t < n_tiles) { run += (uint64_t)(kCg ? __ldcg(tile_mass + t) : tile_mass[t]); pre[t] = run; }
+  }
+  uint64_t inc = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  __syncthreads();
+  if (lane == 31) sm.red[warp] = inc;
+  __syncthreads();
+  uint64_t wpre = 0, S = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const uint64_t v = sm.red[w];
+    if (w < warp) wpre += v;
+    S += v;
+  }
+  const uint64_t excl = wpre + inc - run;
+  for (int k = 0; k < per; ++k) {
+    const int t = tid * per + k;
+    if (t < n_tiles) pre[t] += excl;
+  }
+  __syncthreads();
+  if (S == 0) {
+    for (int64_t j = tid; j < w_n; j += kThreads) anc[j] = (int32_t)(w_lo + j);
+    return 0;
+  }
+  const double scale = __ddiv_rn((double)n_total, (double)S);
+  const int32_t nt = (int32_t)n_total;
+  int lo = 0, hi = n_tiles;  // smallest p whose cumulative offspring count exceeds w_lo
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((int64_t)offspring_cnt(pre[mid], S, scale, u0, nt) > w_lo) hi = mid; else lo = mid + 1;
+  }
+  for (int p = lo; p < n_tiles; ++p) {
+    const uint64_t off = p ? pre[p - 1] : 0ull;
+    if ((int64_t)offspring_cnt(off, S, scale, u0, nt) >= w_lo + w_n) break;
+    if (pre[p] == off) continue;  // a tile without mass has no offspring
+    resample_tile<kCg>(logw, n, (int64_t)p * kTile, M, off, S, n_total, u0, w_lo, w_n, 0, anc, sm, heads);
+  }
+  return S;
+}
+
 }  // namespace gjb

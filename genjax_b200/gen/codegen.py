@@ -733,6 +733,44 @@ class _Generator:
         out.append("}")
         return out
 
+    def pull_kernel(self) -> list[str]:
+        """Single-pass filter step: pull-resample the previous step into this CTA's own slots, then gather + propose +
+        logpdf + masses for exactly those slots (include/genjax_b200.h, gjb_model_args.pull_*)."""
+        out = ["__global__ void __launch_bounds__(kThreads) model_kernel_static_pull(const __grid_constant__ gjb_model_args A) {"]
+        out.append("  __shared__ gjb::TileSmem tsm;")
+        out.append("  __shared__ __align__(16) int32_t heads[gjb::kWin];")
+        out.append("  __shared__ uint64_t pre[gjb::kPullMaxTiles];")
+        out.append("  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < A.tile_mass_clear_n; i += (int64_t)gridDim.x * kThreads)")
+        out.append("    if (A.tile_mass_clear) A.tile_mass_clear[i] = 0ull;")
+        out.extend(self.stage_lines("A.args"))
+        out.append("  Uni U; make_uni(U, A.scalars);")
+        out.append("  uint32_t fl[NS];")
+        out.append(f"  for (int j = 0; j < {self.ns}; ++j) fl[j] = A.site_flags[j];")
+        out.append("  Io io;")
+        out.append("  for (int i = 0; i < NA; ++i) io.args[i] = A.args[i];")
+        out.append("  for (int j = 0; j < NS; ++j) { io.site_in[j] = A.site_in[j]; io.site_out[j] = A.site_out[j]; }")
+        out.append("  for (int k = 0; k < NR; ++k) io.ret_out[k] = A.ret_out[k];")
+        out.append("  io.gather = nullptr; io.score_in = nullptr; io.weight_in = nullptr; io.score_out = nullptr; io.weight_out = A.weight_out;")
+        out.append("  io.peers = nullptr; io.m_ref = A.m_ref; io.tile_mass = A.tile_mass;")
+        out.append("  const int64_t w_lo = (int64_t)blockIdx.x * gjb::kTile;")
+        out.append("  const int64_t w_n = (A.n - w_lo) < gjb::kTile ? (A.n - w_lo) : gjb::kTile;")
+        out.append("  if (A.pull_logw) {  // ancestors of MY slots from the previous step's weights and tile masses")
+        out.append("    const float Mp = __ldg(A.pull_m_ref);")
+        out.append("    const double u0 = gjb::resample_u0(__ldg(A.pull_key), __ldg(A.pull_key + 1), (uint64_t)__ldg(A.pull_key + 2) | ((uint64_t)__ldg(A.pull_key + 3) << 32));")
+        out.append("    const uint64_t S = gjb::pull_ancestors<false>(A.pull_logw, A.n, A.pull_tile_mass, (int)gridDim.x, Mp, A.pull_n_total, u0, w_lo, w_n, A.pull_ancestors + w_lo, tsm, heads, pre);")
+        out.append("    if (blockIdx.x == 0 && threadIdx.x == 0 && A.pull_lse) {")
+        out.append("      A.pull_lse[0] = (double)Mp; A.pull_lse[1] = (double)S;")
+        out.append("      A.pull_lse[2] = S ? (double)Mp + log((double)S) - gjb::kQLog - log((double)A.pull_n_total) : -INFINITY;")
+        out.append("    }")
+        out.append("    __syncthreads();  // the CTA's own ancestor stores are visible to all of its threads (read back through L2)")
+        out.append("    io.gather = A.pull_ancestors;")
+        out.append("  }")
+        out.append("  const uint32_t key0 = A.key_dev ? __ldg(A.key_dev) : A.key0, key1 = A.key_dev ? __ldg(A.key_dev + 1) : A.key1;")
+        out.append("  float run_max = -INFINITY;")
+        out.append("  run_quads<true, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, (w_lo >> 2) + threadIdx.x, (w_lo + w_n + 3) >> 2, kThreads, run_max);")
+        out.append("}")
+        return out
+
     def pf_kernel(self) -> list[str]:
         """The persistent particle-filter kernel (None when the model's return
         leaves cannot feed back as its leading particle arguments)."""
@@ -846,6 +884,7 @@ class _Generator:
             out.extend(self.model_kernel(static=True))
             if not self.group:
                 out.extend(self.model_kernel(static=True, mass=True))
+                out.extend(self.pull_kernel())
         pf = self.pf_supported()
         if pf:
             out.extend(self.pf_kernel())
@@ -921,6 +960,13 @@ int gjb_model_pf_run(const gjb_pf_args* a, void* stream) { (void)a; (void)stream
   for (int j = 0; j < {self.ns}; ++j) is_static = is_static && a->site_flags[j] == kPfFl_host[j];
   if (a->tile_mass || a->m_ref) {{{{  // reference-maximum step: masses accumulated while the weights are in registers
     if (!is_static || !a->tile_mass || !a->m_ref || !a->weight_out || {'true' if self.group else 'false'}) return GJB_E_MODE;
+    if (a->pull_ancestors) {{{{  // single-pass step: one CTA per 2048 offspring slots
+      const int64_t tiles = (a->n + gjb::kTile - 1) / gjb::kTile;
+      if (tiles > gjb::kPullMaxTiles || a->idx_offset != 0 || a->gather) return GJB_E_RANGE;
+      if (a->pull_logw && (!a->pull_tile_mass || !a->pull_m_ref || !a->pull_key || a->pull_n_total <= 0 || a->pull_n_total > 0x7fffffffLL)) return GJB_E_ARG;
+      {'return GJB_E_MODE;' if self.group else 'model_kernel_static_pull<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a);'}
+      return (int)cudaGetLastError();
+    }}}}
     {'return GJB_E_MODE;' if self.group else 'model_kernel_static_mass<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(*a);'}
     return (int)cudaGetLastError();
   }}}}

@@ -59,7 +59,8 @@ class ParticleFilter:
     particles).  Every other site is proposed from the model (bootstrap)."""
 
     def __init__(self, step: StaticGenerativeFunction, n_particles: int, *, n_state: int = 1, resampler: str = "systematic",
-                 idx_offset: int = 0, n_total: int | None = None, mode: str = "graph", reference_max: str = "running"):
+                 idx_offset: int = 0, n_total: int | None = None, mode: str = "graph", reference_max: str = "running",
+                 single_pass: bool = False):
         """``reference_max``: what the exact integer weight masses are taken relative to.  "running" (default): the
         maximum of the step's weights, found by a running max in the model kernel, masses in the resampling launch.
         "analytic" (graph mode, scalar-site models): an upper bound of the incremental weight derived from the model
@@ -74,6 +75,12 @@ class ParticleFilter:
             raise ValueError(reference_max)
         if reference_max == "analytic" and mode != "graph":
             raise ValueError("reference_max='analytic' needs mode='graph'")
+        if single_pass and (reference_max != "analytic" or idx_offset != 0):
+            raise ValueError("single_pass=True needs reference_max='analytic' on one device")
+        # single_pass: ONE launch per step -- every CTA first resolves the ancestors of its own 2048 offspring slots
+        # from the previous step's weights (output-slot resampling), then gathers, proposes, scores and accumulates
+        # the masses of exactly those slots; a final resampling launch closes the run
+        self.single_pass = bool(single_pass)
         self.reference_max = reference_max
         self.mode = mode
         self.fuse_mass_resample = True  # graph mode: gjb_mass_resample_systematic when the particle count fits
@@ -211,6 +218,12 @@ class _Plan:
             self.m_ref = torch.empty(1, dtype=torch.float32, device=device)
             self.tm2 = torch.zeros((2, self.ws.tiles), dtype=torch.int64, device=device)
             self._m_ref_value = None
+            self.single_pass = pf.single_pass
+            if self.single_pass:
+                if self.ws.tiles > 2048:
+                    raise NotImplementedError("single_pass handles up to 2048 tiles (4 194 304 particles) per device")
+                self.tm3 = torch.zeros((3, self.ws.tiles), dtype=torch.int64, device=device)  # accumulate / read / clear
+                self.logw2 = torch.empty((2, n), dtype=torch.float32, device=device)
         if self.persistent:
             self._build_pf_args()
         else:
@@ -295,6 +308,34 @@ class _Plan:
                     A.ret_out[k] = out.data_ptr()
             lw = self.logw_hist[t] if self.record else self.logw
             A.weight_out = lw.data_ptr()
+            if self.analytic and self.single_pass:
+                lw = self.logw_hist[t] if self.record else self.logw2[t & 1]
+                A.weight_out = lw.data_ptr()
+                A.gather = None  # the kernel gathers through the ancestors it resolves itself
+                A.m_ref = self.m_ref.data_ptr()
+                A.tile_mass = self.tm3[t % 3].data_ptr()
+                A.tile_mass_clear = self.tm3[(t + 1) % 3].data_ptr()
+                A.tile_mass_clear_n = self.ws.tiles
+                A.pull_n_total = pf.n_total
+                if t == 0:
+                    A.pull_ancestors = self.anc[slot].data_ptr()  # selects the single-pass kernel; nothing to resample yet
+                else:
+                    lw_prev = self.logw_hist[t - 1] if self.record else self.logw2[(t - 1) & 1]
+                    A.pull_logw = lw_prev.data_ptr()
+                    A.pull_tile_mass = self.tm3[(t - 1) % 3].data_ptr()
+                    A.pull_m_ref = self.m_ref.data_ptr()
+                    A.pull_key = self.keys[t - 1][2:].data_ptr()
+                    A.pull_ancestors = self.anc[prev_slot].data_ptr()
+                    A.pull_lse = self.lse[t - 1].data_ptr()
+                self.margs.append(A)
+                if t == T - 1:  # the run ends with a plain resampling of the last step's weights
+                    R = self.ws.systematic_args(
+                        lw, None, self.anc[slot], n_total=pf.n_total, out_lo=pf.idx_offset, anc_base=pf.idx_offset,
+                        key_dev=self.keys[t][2:], lse_out=self.lse[t], m_global=self.m_ref,
+                    )
+                    R.tile_mass = self.tm3[t % 3].data_ptr()
+                    self.rargs.append((lw, R))
+                continue
             if self.analytic:
                 # masses relative to the analytic bound, accumulated by the model kernel into this step's tile buffer;
                 # the other buffer (next step's) is zeroed by the same launch
@@ -325,6 +366,15 @@ class _Plan:
         lib = self.cm.lib
         if self.persistent:
             cabi.check(lib.gjb_model_pf_run(C.byref(self.pf_args), stream), "gjb_model_pf_run")
+            last = (self.T - 1) if self.record else ((self.T - 1) & 1)
+            for k in range(len(self.bufs)):
+                smc_ops.gather_rows(self.bufs[k][last], self.anc[last], self.final[k])
+            return
+        if self.analytic and self.single_pass:  # 1 launch per step + one closing resampling launch
+            self.tm3.zero_()
+            for t in range(self.T):
+                cabi.check(lib.gjb_model_launch(C.byref(self.margs[t]), stream), "gjb_model_launch")
+            cabi.check(core.gjb_resample_systematic(C.byref(self.rargs[-1][1]), stream), "gjb_resample_systematic")
             last = (self.T - 1) if self.record else ((self.T - 1) & 1)
             for k in range(len(self.bufs)):
                 smc_ops.gather_rows(self.bufs[k][last], self.anc[last], self.final[k])
@@ -362,6 +412,8 @@ class _Plan:
     def launches_per_run(self) -> int:
         if self.persistent:
             return 2 + len(self.bufs)  # init + persistent filter kernel + final gather(s)
+        if self.analytic and self.single_pass:
+            return self.T + 1 + len(self.bufs)  # (+ one memset node)
         if self.analytic:
             return 2 * self.T + len(self.bufs)  # (+ one memset node)
         return 1 + (2 if getattr(self, "fuse_mass_resample", False) else 3) * self.T + len(self.bufs)

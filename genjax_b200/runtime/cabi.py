@@ -13,7 +13,7 @@ import torch
 
 from . import build
 
-ABI_VERSION = 9  # GJB_ABI_VERSION of include/genjax_b200.h this binding mirrors (tests/test_abi.py keeps them equal)
+ABI_VERSION = 10  # GJB_ABI_VERSION of include/genjax_b200.h this binding mirrors (tests/test_abi.py keeps them equal)
 GJB_MAX_SITES = 16
 GJB_MAX_ARGS = 16
 GJB_MAX_RETS = 8
@@ -65,6 +65,13 @@ class ModelArgs(C.Structure):
         ("tile_mass", _p),
         ("tile_mass_clear", _p),
         ("tile_mass_clear_n", _i64),
+        ("pull_logw", _p),
+        ("pull_tile_mass", _p),
+        ("pull_m_ref", _p),
+        ("pull_key", _p),
+        ("pull_ancestors", _p),
+        ("pull_lse", _p),
+        ("pull_n_total", _i64),
     ]
 
 

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GJB_ABI_VERSION 9
+#define GJB_ABI_VERSION 10
 
 #define GJB_E_ARG (-1)      /* null / misaligned pointer, negative size          */
 #define GJB_E_RANGE (-2)    /* size beyond what the kernel supports              */
@@ -302,7 +302,20 @@ typedef struct gjb_model_args {
   unsigned long long* tile_mass;       /* nullable; [ceil(n / 2048)] */
   unsigned long long* tile_mass_clear; /* nullable */
   int64_t tile_mass_clear_n;
+  /* Single-pass filter step (with the reference-maximum fields above; one CTA per 2048 offspring slots, n <= 2048 *
+   * GJB_PULL_MAX_TILES): before proposing, every CTA resolves the ancestors of ITS OWN slots from the PREVIOUS step's
+   * weights -- output-slot ("pull") systematic resampling over the tile masses that step accumulated -- writes them to
+   * pull_ancestors and gathers the previous state through them, so a step is ONE launch: resample(t-1) + gather +
+   * propose + logpdf + masses(t).  pull_logw == NULL (first step): no resampling, args are read in place.          */
+  const float* pull_logw;                  /* nullable: previous step's log-weights [n]                  */
+  const unsigned long long* pull_tile_mass; /* previous step's tile masses (relative to *pull_m_ref)      */
+  const float* pull_m_ref;                 /* previous step's reference maximum                          */
+  const uint32_t* pull_key;                /* {key0, key1, index_lo, index_hi} of that resampling        */
+  int32_t* pull_ancestors;                 /* [n] out: ancestors of this step's particles                */
+  double* pull_lse;                        /* nullable out: {M, S, log-mean-exp} of the previous step    */
+  int64_t pull_n_total;                    /* particle count the offspring counts are scaled to          */
 } gjb_model_args;
+#define GJB_PULL_MAX_TILES 2048
 
 /* JSON description of the captured model (sites, args, layouts); static storage. */
 const char* gjb_model_info(void);

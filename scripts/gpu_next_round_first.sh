@@ -9,3 +9,4 @@ GJB_RUN_UNVERIFIED=1 timeout 900 python -m pytest tests -m gpu -q -k "unverified
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 400 python bench.py > gpurun_out/next_bench_d1.json 2> gpurun_out/next_bench_d1.err; tail -2 gpurun_out/next_bench_d1.err; cat gpurun_out/next_bench_d1.json
 timeout 400 python bench.py --reference-max analytic --no-cpu-baseline > gpurun_out/next_bench_d1_analytic.json 2> gpurun_out/next_bench_d1_analytic.err; tail -2 gpurun_out/next_bench_d1_analytic.err; cat gpurun_out/next_bench_d1_analytic.json
+timeout 400 python bench.py --reference-max analytic --single-pass --no-cpu-baseline > gpurun_out/next_bench_d1_single_pass.json 2> gpurun_out/next_bench_d1_single_pass.err; tail -2 gpurun_out/next_bench_d1_single_pass.err; cat gpurun_out/next_bench_d1_single_pass.json

@@ -149,12 +149,30 @@ class EmulatedModelLib:
         self.launches += 1
         if A.peer_args or A.link:
             raise NotImplementedError("emulator: multi-GPU links are a GPU-only path")
+        gather_ptr = A.gather
+        if A.pull_ancestors and A.pull_logw:  # single-pass step: output-slot resampling of the previous step first
+            from oracle import rng as orng
+            from oracle import smc as osmc
+
+            lwp = _view(A.pull_logw, n, F32)
+            mp = _view(A.pull_m_ref, 1, F32)[0]
+            kd = _arr(A.pull_key, 4, C.c_uint32, np.uint32)
+            key = orng.Key((int(kd[0]), int(kd[1])), int(kd[2]) | (int(kd[3]) << 32))
+            anc = osmc.resample_systematic_pull(lwp, key, M=mp)
+            _view(A.pull_ancestors, n, I32)[:] = anc
+            if A.pull_lse:
+                tiles = (n + 2047) // 2048
+                S = int(_arr(A.pull_tile_mass, tiles, C.c_uint64, np.uint64).sum(dtype=np.uint64))
+                out = _arr(A.pull_lse, 3, C.c_double, np.float64)
+                out[0], out[1] = float(mp), float(S)
+                out[2] = float(mp) + np.log(float(S)) - 36 * np.log(2.0) - np.log(float(A.pull_n_total)) if S else -np.inf
+            gather_ptr = A.pull_ancestors
         words = (int(A.key0), int(A.key1))
         if A.key_dev:  # filter steps read their key words from the device key table
             kd = _arr(A.key_dev, 2, C.c_uint32, np.uint32)
             words = (int(kd[0]), int(kd[1]))
         idx = np.uint64(A.idx_offset) + np.arange(n, dtype=np.uint64)
-        gather = _view(A.gather, n, I32)
+        gather = _view(gather_ptr, n, I32)
         env = {}
         for i, spec in enumerate(ir.args):
             dt = F32 if spec.dtype == "f32" else I32
@@ -463,7 +481,7 @@ class EmulatedCore:
     oracle/smc.py.  Multi-GPU, fused cooperative and filter entry points are GPU-only and absent on purpose."""
 
     def gjb_abi_version(self):
-        return 9
+        return 10
 
     def gjb_mass_resample_fits(self, n):
         return 0
@@ -614,7 +632,13 @@ class HostKernelModelLib(EmulatedModelLib):
         wmax = A.wmax
         A.wmax = None  # the block-level max reduction needs a real thread block; redone below from the weights
         try:
-            if A.tile_mass or A.m_ref:  # the launcher's dispatch: the filter-flag instantiation with masses
+            if A.pull_ancestors:  # single-pass step: a block-level kernel, run with real block semantics
+                import simt_kernels
+
+                if not (A.tile_mass and A.m_ref and A.weight_out) or A.gather or int(A.idx_offset):
+                    return -3
+                rc = simt_kernels.model(self.source).s_model_launch_pull(a_ref)
+            elif A.tile_mass or A.m_ref:  # the launcher's dispatch: the filter-flag instantiation with masses
                 if not hasattr(self.h, "host_model_launch_mass") or not (A.tile_mass and A.m_ref and A.weight_out):
                     return -3
                 rc = self.h.host_model_launch_mass(a_ref)

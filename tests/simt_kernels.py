@@ -105,6 +105,14 @@ extern "C" int s_model_launch(const gjb_model_args* a, int grid) {
   return 0;
 }
 '''
+PULL_DRIVER = r'''
+extern "C" int s_model_launch_pull(const gjb_model_args* a) {
+  const gjb_model_args A = *a;
+  const int tiles = (int)((A.n + gjb::kTile - 1) / gjb::kTile);
+  simt::launch(tiles, kThreads, [=] { model_kernel_static_pull(A); });
+  return 0;
+}
+'''
 PF_DRIVER = r'''
 extern "C" int s_pf_run(const gjb_pf_args* q) {  // the persistent cooperative filter as a grid of ONE block
   const gjb_pf_args Q = *q;
@@ -127,6 +135,8 @@ def model(source: str):
     body = source[: source.index('extern "C" {')].replace(
         "extern __shared__ __align__(16) unsigned char dyn_smem[];", "static unsigned char dyn_smem[1 << 16];")
     text = body + MODEL_DRIVER
+    if "model_kernel_static_pull(" in body:
+        text += PULL_DRIVER
     if "pf_kernel(" in body:
         text += PF_DRIVER
     for kind in ("mh", "hmc"):

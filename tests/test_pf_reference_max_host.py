@@ -102,3 +102,26 @@ def test_analytic_reference_needs_a_derivable_bound_and_graph_mode(emu):
     assert (res.lse_terms[:, 0] == 0).all() and (res.lse_terms[:, 1] > 0).all()
     ref = ParticleFilter(hmm_step, n).run(gj.key(2), z0, gj.C["y"].set(ys), shared_args=(tl, ol), record=True)
     assert res.log_increments[0].item() == pytest.approx(ref.log_increments[0].item(), abs=2e-7)
+
+
+@pytest.mark.parametrize("n", [7, 2048, 6000])
+def test_single_pass_filter_matches_oracle(emu, n):
+    """ParticleFilter(reference_max="analytic", single_pass=True): ONE launch per step (pull-resample the previous step
+    into the CTA's own slots, gather, propose, score, accumulate masses) + one closing resampling launch.  Same
+    ancestors, weights, estimate as the two-launch analytic filter and as the oracle with the same reference."""
+    T = 5
+    ys = osmc.simulate_lgssm(1, T, 1, LG_A, LG_Q, LG_C, LG_R)[:, 0]
+    x0 = np.random.default_rng(n).standard_normal(n).astype(F32)
+    obs = gj.C["y"].set(torch.from_numpy(ys))
+    one = ParticleFilter(lgssm_step, n, reference_max="analytic", single_pass=True).run(gj.key(17), torch.from_numpy(x0), obs, record=True)
+    two = ParticleFilter(lgssm_step, n, reference_max="analytic").run(gj.key(17), torch.from_numpy(x0), obs, record=True)
+    assert torch.equal(one.ancestors, two.ancestors)
+    assert torch.equal(one.history["log_weights"], two.history["log_weights"])
+    assert torch.equal(one.history["state"][0], two.history["state"][0])
+    assert torch.equal(one.lse_terms, two.lse_terms) and torch.equal(one.state[0], two.state[0])
+    ores = osmc.particle_filter(o_step, orng.key(17), x0, [{"y": F32(y)} for y in ys],
+                                m_ref=F32(ParticleFilter(lgssm_step, n).weight_upper_bound(torch.from_numpy(x0), obs)))
+    assert one.log_marginal_likelihood.item() == pytest.approx(ores["logz"], abs=2e-4)
+    # ping-pong buffers (no history)
+    plain = ParticleFilter(lgssm_step, n, reference_max="analytic", single_pass=True).run(gj.key(17), torch.from_numpy(x0), obs)
+    assert torch.equal(plain.log_increments, one.log_increments) and torch.equal(plain.state[0], one.state[0])

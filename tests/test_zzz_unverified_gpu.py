@@ -313,3 +313,31 @@ def test_analytic_reference_filter_matches_oracle(device, n):
     plain = ParticleFilter(lgssm_step, n).run(gj.key(17), torch.from_numpy(x0), gj.C["y"].set(torch.from_numpy(ys)), record=True)
     assert torch.equal(plain.history["log_weights"][0], res.history["log_weights"][0])
     assert plain.log_increments[0].item() == pytest.approx(res.log_increments[0].item(), abs=2e-7)
+
+
+@pytest.mark.parametrize("n", [7, 2048, 100_001, 1 << 20])
+def test_single_pass_filter_equals_the_two_launch_filter(device, n):
+    """ParticleFilter(reference_max="analytic", single_pass=True): model_kernel_static_pull resolves the ancestors of
+    its own 2048 slots from the previous step (output-slot resampling), gathers, proposes, scores and accumulates the
+    masses in ONE launch per step.  Bit-identical ancestors, weights, states and estimate terms to the two-launch
+    analytic filter (which the test above pins to the oracle); same scenario as tests/test_pf_reference_max_host.py."""
+    gj = _gj()
+    from genjax_b200.inference.pf import ParticleFilter
+    from genjax_b200.workloads import LG_A, LG_C, LG_Q, LG_R, lgssm_step
+    from oracle import smc as osmc
+
+    T = 6
+    ys = torch.from_numpy(osmc.simulate_lgssm(1, T, 1, LG_A, LG_Q, LG_C, LG_R)[:, 0])
+    x0 = torch.from_numpy(np.random.default_rng(n % 1000).standard_normal(n).astype(F32))
+    obs = gj.C["y"].set(ys)
+    two = ParticleFilter(lgssm_step, n, reference_max="analytic").run(gj.key(17), x0, obs, record=True)
+    for use_graph in (False, True):
+        one = ParticleFilter(lgssm_step, n, reference_max="analytic", single_pass=True).run(gj.key(17), x0, obs, record=True, use_graph=use_graph)
+        assert torch.equal(one.ancestors, two.ancestors)
+        assert torch.equal(one.history["log_weights"], two.history["log_weights"])
+        assert torch.equal(one.history["state"][0], two.history["state"][0])
+        assert torch.equal(one.lse_terms, two.lse_terms) and torch.equal(one.state[0], two.state[0])
+    plain = ParticleFilter(lgssm_step, n, reference_max="analytic", single_pass=True).run(gj.key(17), x0, obs)
+    assert torch.equal(plain.log_increments, two.log_increments) and torch.equal(plain.state[0], two.state[0])
+    with pytest.raises(NotImplementedError):  # the tile prefix lives in shared memory: up to 2048 tiles per device
+        ParticleFilter(lgssm_step, (1 << 22) + 1, reference_max="analytic", single_pass=True).run(gj.key(0), torch.zeros((1 << 22) + 1), obs)
