@@ -25,17 +25,23 @@ from .gen.distributions import (
     bernoulli,
     beta,
     categorical,
+    cauchy,
     exact_density,
     exponential,
     flip,
     gamma,
     gmm_diag,
+    gumbel,
+    half_cauchy,
     half_normal,
+    laplace,
+    log_normal,
     mv_normal,
     mv_normal_diag,
     normal,
     register_primitive,
     uniform,
+    weibull,
 )
 from .gen.gfi import (
     Diff,

@@ -49,6 +49,65 @@ struct HalfNormal {
   }
 };
 
+// ------------------------------------------- long-tail scalar wrappers
+// tensorflow_probability/__init__.py:110 (cauchy), :179 (half_cauchy), :214 (laplace), :219 (log_normal), :174 (gumbel),
+// :309 (weibull).  Inverse-CDF samplers on one u01 word (u in [2^-25, 1)); log-densities in TFP 0.23's operation order
+// as restated in oracle/dists.py.
+constexpr float kPi = 3.14159265358979323846f;
+constexpr float kLogPi = 1.14472988584940017414f;
+constexpr float kLog2OverPi = -0.45158270528945486473f;  // log(2/pi)
+constexpr float kLog2 = 0.69314718055994530942f;
+
+struct Cauchy {
+  __device__ static __forceinline__ float sample(float u, float loc, float scale) { return loc + scale * tanf(kPi * (u - 0.5f)); }
+  __device__ static __forceinline__ float logpdf(float v, float loc, float scale) {
+    const float z = (v - loc) / scale;
+    return -log1pf(z * z) - (kLogPi + logf(scale));
+  }
+};
+
+struct HalfCauchy {
+  __device__ static __forceinline__ float sample(float u, float loc, float scale) { return loc + scale * fabsf(tanf(kPi * (u - 0.5f))); }
+  __device__ static __forceinline__ float logpdf(float v, float loc, float scale) {
+    const float z = (v - loc) / scale;
+    return v < loc ? -INFINITY : kLog2OverPi - logf(scale) - log1pf(z * z);
+  }
+};
+
+struct Laplace {
+  __device__ static __forceinline__ float sample(float u, float loc, float scale) {
+    const float w = 2.0f * u - 1.0f;  // (-1, 1): |w| <= 1 - 2^-24, the logarithm stays finite
+    return loc - scale * copysignf(log1pf(-fabsf(w)), w);
+  }
+  __device__ static __forceinline__ float logpdf(float v, float loc, float scale) {
+    return -fabsf((v - loc) / scale) - kLog2 - logf(scale);
+  }
+};
+
+struct LogNormal {  // exp of a Normal(loc, scale): Normal log-density of log v, minus the log-Jacobian log v
+  __device__ static __forceinline__ float sample(float z, float loc, float scale) { return expf(loc + scale * z); }
+  __device__ static __forceinline__ float logpdf(float v, float loc, float scale) {
+    const float lv = logf(v);
+    return v > 0.0f ? Normal::logpdf(lv, loc, scale) - lv : -INFINITY;
+  }
+};
+
+struct Gumbel {
+  __device__ static __forceinline__ float sample(float u, float loc, float scale) { return loc - scale * logf(-logf(u)); }
+  __device__ static __forceinline__ float logpdf(float v, float loc, float scale) {
+    const float z = (v - loc) / scale;
+    return -(z + expf(-z)) - logf(scale);
+  }
+};
+
+struct Weibull {  // (concentration k, scale s): x = s (-log(1 - u))^(1/k)
+  __device__ static __forceinline__ float sample(float u, float k, float s) { return s * expf(logf(-log1pf(-u)) / k); }
+  __device__ static __forceinline__ float logpdf(float v, float k, float s) {
+    const float t = logf(v) - logf(s);
+    return v < 0.0f ? -INFINITY : logf(k) - logf(s) + (k - 1.0f) * t - expf(k * t);
+  }
+};
+
 // --------------------------------------------------------- flip / bernoulli
 __device__ __forceinline__ float softplusf(float x) { return fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x))); }
 

@@ -48,6 +48,31 @@ def logpdf_expr(dist, v: Expr, args: list) -> Expr:
         z = v / scale
         lp = E.const(0.5 * math.log(2.0 / math.pi)) - E.unary("log", scale) - E.const(0.5) * E.unary("square", z)
         return E.where(v < 0.0, E.const(-math.inf), lp)
+    if name in ("cauchy", "half_cauchy"):
+        loc, scale = args
+        z = (v - loc) / scale
+        if name == "cauchy":
+            return -E.unary("log1p", E.unary("square", z)) - (E.const(math.log(math.pi)) + E.unary("log", scale))
+        lp = E.const(math.log(2.0 / math.pi)) - E.unary("log", scale) - E.unary("log1p", E.unary("square", z))
+        return E.where(v < loc, E.const(-math.inf), lp)
+    if name == "laplace":
+        loc, scale = args
+        return -E.unary("abs", (v - loc) / scale) - E.const(math.log(2.0)) - E.unary("log", scale)
+    if name == "log_normal":
+        loc, scale = args
+        lv = E.unary("log", v)
+        z = lv / scale - loc / scale
+        lp = E.const(-0.5) * E.unary("square", z) - (E.const(_HALF_LOG_2PI) + E.unary("log", scale)) - lv
+        return E.where(v > 0.0, lp, E.const(-math.inf))
+    if name == "gumbel":
+        loc, scale = args
+        z = (v - loc) / scale
+        return -(z + E.unary("exp", -z)) - E.unary("log", scale)
+    if name == "weibull":
+        k, scale = args
+        t = E.unary("log", v) - E.unary("log", scale)
+        lp = E.unary("log", k) - E.unary("log", scale) + (k - 1.0) * t - E.unary("exp", k * t)
+        return E.where(v < 0.0, E.const(-math.inf), lp)
     if name == "exponential":
         (rate,) = args
         return E.where(v < 0.0, E.const(-math.inf), E.unary("log", rate) - rate * v)

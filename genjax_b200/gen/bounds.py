@@ -8,6 +8,7 @@ is a function of the shared / scalar arguments alone:
     half_normal            :   1/2 log(2 / pi) - log scale
     exponential            :   log rate
     uniform                :  -log(high - low)
+    cauchy / half_cauchy / laplace / gumbel :  -log(pi s) / log(2 / (pi s)) / -log(2 s) / -1 - log s
     flip, bernoulli, categorical : 0
 
 Such a bound is a valid reference maximum for the exact integer weight masses (any ``M >= max w`` that every CTA and
@@ -54,6 +55,13 @@ def _site_bound(site, width: int) -> Expr | None:
         return per * float(width) if width else per  # a scalar scale shared by every element of a vector site
     if name == "half_normal":
         return E.const(0.5 * math.log(2.0 / math.pi)) - E.unary("log", a[0]) if is_particle_invariant(a[0]) else None
+    if name in ("cauchy", "half_cauchy", "laplace"):  # the mode sits at loc: -log(pi s), log(2 / (pi s)), -log(2 s)
+        if not is_particle_invariant(a[1]):
+            return None
+        c = {"cauchy": -math.log(math.pi), "half_cauchy": math.log(2.0 / math.pi), "laplace": -math.log(2.0)}[name]
+        return E.const(c) - E.unary("log", a[1])
+    if name == "gumbel":  # mode at loc: -1 - log s
+        return E.const(-1.0) - E.unary("log", a[1]) if is_particle_invariant(a[1]) else None
     if name == "exponential":
         return E.unary("log", a[0]) if is_particle_invariant(a[0]) else None
     if name == "uniform":

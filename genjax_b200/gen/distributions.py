@@ -138,6 +138,48 @@ class _HalfNormal(Distribution):
     rng_kind = "normal"
 
 
+class _LocScale(Distribution):
+    """Long-tail scalar wrappers with ``(loc, scale)`` parameters (tensorflow_probability/__init__.py:110, 174, 179,
+    214, 219): one inverse-CDF draw per site, keyword spelling as TFP's."""
+
+    n_args = 2
+    kw_names = ("loc", "scale")
+
+    def _canonical(self, args, kwargs):
+        kwargs = _check_kwargs(self.name, kwargs, self.kw_names)
+        if kwargs:
+            args = tuple(args) + tuple(kwargs[k] for k in self.kw_names if k in kwargs)
+        return super()._canonical(args, {})
+
+
+class _Cauchy(_LocScale):
+    name, cuda = "cauchy", "Cauchy"
+
+
+class _HalfCauchy(_LocScale):
+    name, cuda = "half_cauchy", "HalfCauchy"
+
+
+class _Laplace(_LocScale):
+    name, cuda = "laplace", "Laplace"
+
+
+class _LogNormal(_LocScale):
+    name, cuda = "log_normal", "LogNormal"
+    rng_kind = "normal"
+
+
+class _Gumbel(_LocScale):
+    name, cuda = "gumbel", "Gumbel"
+
+
+class _Weibull(_LocScale):
+    """tfd.Weibull(concentration, scale) (tensorflow_probability/__init__.py:309)."""
+
+    name, cuda = "weibull", "Weibull"
+    kw_names = ("concentration", "scale")
+
+
 class _Gamma(Distribution):
     name, cuda, n_args = "gamma", "Gamma", 2
     rng_kind = "lane"
@@ -333,6 +375,12 @@ normal = _Normal()
 uniform = _Uniform()
 exponential = _Exponential()
 half_normal = _HalfNormal()
+cauchy = _Cauchy()
+half_cauchy = _HalfCauchy()
+laplace = _Laplace()
+log_normal = _LogNormal()
+gumbel = _Gumbel()
+weibull = _Weibull()
 gamma = _Gamma()
 beta = _Beta()
 flip = _Flip()
@@ -344,7 +392,7 @@ mv_normal = _MvNormal()
 
 REGISTRY: dict[str, Distribution] = {
     d.name: d
-    for d in (normal, uniform, exponential, half_normal, gamma, beta, flip, bernoulli, categorical, mv_normal_diag, gmm_diag, mv_normal)
+    for d in (normal, uniform, exponential, half_normal, cauchy, half_cauchy, laplace, log_normal, gumbel, weibull, gamma, beta, flip, bernoulli, categorical, mv_normal_diag, gmm_diag, mv_normal)
 }
 
 

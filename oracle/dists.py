@@ -210,6 +210,56 @@ def half_normal_logpdf(v, scale):
     return np.where(v < 0, F32(-np.inf), lp).astype(F32)
 
 
+def cauchy_logpdf(v, loc, scale):
+    """tfd.Cauchy._log_prob: -log1p(z^2) - (log pi + log s), z = (x - loc) / s
+    (tensorflow_probability/__init__.py:110)."""
+    v, m, s = _f(v), _f(loc), _f(scale)
+    z = ((v - m) / s).astype(F32)
+    return (-_log1p((z * z).astype(F32)) - (F32(math.log(math.pi)) + _log(s))).astype(F32)
+
+
+def half_cauchy_logpdf(v, loc, scale):
+    """tfd.HalfCauchy._log_prob: log(2/pi) - log s - log1p(z^2) for x >= loc
+    (tensorflow_probability/__init__.py:179)."""
+    v, m, s = _f(v), _f(loc), _f(scale)
+    z = ((v - m) / s).astype(F32)
+    lp = (F32(math.log(2.0 / math.pi)) - _log(s) - _log1p((z * z).astype(F32))).astype(F32)
+    return np.where(v < m, F32(-np.inf), lp).astype(F32)
+
+
+def laplace_logpdf(v, loc, scale):
+    """tfd.Laplace._log_prob: -|z| - log 2 - log s (tensorflow_probability/__init__.py:214)."""
+    v, m, s = _f(v), _f(loc), _f(scale)
+    return (-np.abs(((v - m) / s).astype(F32)) - F32(math.log(2.0)) - _log(s)).astype(F32)
+
+
+def log_normal_logpdf(v, loc, scale):
+    """tfd.LogNormal = Exp(Normal): Normal log-density of log x minus log x, x > 0
+    (tensorflow_probability/__init__.py:219)."""
+    v = _f(v)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lv = _log(v)
+        lp = (normal_logpdf(lv, loc, scale) - lv).astype(F32)
+    return np.where(v > 0, lp, F32(-np.inf)).astype(F32)
+
+
+def gumbel_logpdf(v, loc, scale):
+    """tfd.Gumbel._log_prob: -(z + exp(-z)) - log s (tensorflow_probability/__init__.py:174)."""
+    v, m, s = _f(v), _f(loc), _f(scale)
+    z = ((v - m) / s).astype(F32)
+    return (-(z + _exp(-z)) - _log(s)).astype(F32)
+
+
+def weibull_logpdf(v, concentration, scale):
+    """tfd.Weibull (inverse WeibullCDF bijector on Uniform): log k - log s + (k-1) t - exp(k t), t = log x - log s,
+    x >= 0 (tensorflow_probability/__init__.py:309)."""
+    v, k, s = _f(v), _f(concentration), _f(scale)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = (_log(v) - _log(s)).astype(F32)
+        lp = (_log(k) - _log(s) + (k - F32(1)) * t - _exp((k * t).astype(F32))).astype(F32)
+    return np.where(v < 0, F32(-np.inf), lp).astype(F32)
+
+
 # ---------------------------------------------------------------- samplers
 # sampler(words, idx, site, *args) -> values for the lanes in idx
 
@@ -266,6 +316,37 @@ def categorical_sample(words, idx, site, logits):
 
 def exponential_sample(words, idx, site, rate):
     return (-_log(rng.quad_u01(words, idx, site)) / _f(rate)).astype(F32)
+
+
+def _tan_centered(words, idx, site):
+    u = rng.quad_u01(words, idx, site)
+    return np.tan((F32(math.pi) * (u - F32(0.5)).astype(F32)).astype(F32).astype(np.float64)).astype(F32)
+
+
+def cauchy_sample(words, idx, site, loc, scale):
+    return (_f(loc) + _f(scale) * _tan_centered(words, idx, site)).astype(F32)
+
+
+def half_cauchy_sample(words, idx, site, loc, scale):
+    return (_f(loc) + _f(scale) * np.abs(_tan_centered(words, idx, site))).astype(F32)
+
+
+def laplace_sample(words, idx, site, loc, scale):
+    w = (F32(2) * rng.quad_u01(words, idx, site) - F32(1)).astype(F32)
+    return (_f(loc) - _f(scale) * np.copysign(_log1p(-np.abs(w)), w).astype(F32)).astype(F32)
+
+
+def log_normal_sample(words, idx, site, loc, scale):
+    return _exp((_f(loc) + _f(scale) * rng.quad_normal(words, idx, site)).astype(F32))
+
+
+def gumbel_sample(words, idx, site, loc, scale):
+    return (_f(loc) - _f(scale) * _log(-_log(rng.quad_u01(words, idx, site)))).astype(F32)
+
+
+def weibull_sample(words, idx, site, concentration, scale):
+    e = (-_log1p(-rng.quad_u01(words, idx, site))).astype(F32)
+    return (_f(scale) * _exp((_log(e) / _f(concentration)).astype(F32))).astype(F32)
 
 
 def mv_normal_diag_sample(words, idx, site, loc, scale_diag):
@@ -345,4 +426,10 @@ DISTS = {
     "gamma": (gamma_sample, gamma_logpdf),
     "mv_normal": (mv_normal_sample, mv_normal_logpdf),
     "beta": (beta_sample, beta_logpdf),
+    "cauchy": (cauchy_sample, cauchy_logpdf),
+    "half_cauchy": (half_cauchy_sample, half_cauchy_logpdf),
+    "laplace": (laplace_sample, laplace_logpdf),
+    "log_normal": (log_normal_sample, log_normal_logpdf),
+    "gumbel": (gumbel_sample, gumbel_logpdf),
+    "weibull": (weibull_sample, weibull_logpdf),
 }

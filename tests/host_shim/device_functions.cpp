@@ -34,6 +34,7 @@ double h_resample_u0(uint32_t k0, uint32_t k1, uint64_t key_index) { return gjb:
 extern "C" {
 // which: 0 normal(v, loc, scale)  1 uniform(v, lo, hi)  2 exponential(v, rate)  3 half_normal(v, scale)
 //        4 gamma(v, a, rate)  5 beta(v, a, b)  6 flip(v, p)  7 bernoulli(v, logit)  8 normal logpdf_r(v, loc, 1/scale, lc)
+//        9 cauchy  10 half_cauchy  11 laplace  12 log_normal  13 gumbel (v, loc, scale)  14 weibull(v, k, scale)
 void h_logpdf(int which, const float* v, const float* a, const float* b, int n, float* out) {
   for (int i = 0; i < n; ++i) {
     switch (which) {
@@ -46,6 +47,25 @@ void h_logpdf(int which, const float* v, const float* a, const float* b, int n, 
       case 6: out[i] = gjb::Flip::logpdf((int)v[i], a[i]); break;
       case 7: out[i] = gjb::Bernoulli::logpdf((int)v[i], a[i]); break;
       case 8: out[i] = gjb::Normal::logpdf_r(v[i], a[i], 1.0f / b[i], gjb::kHalfLog2Pi + logf(b[i])); break;
+      case 9: out[i] = gjb::Cauchy::logpdf(v[i], a[i], b[i]); break;
+      case 10: out[i] = gjb::HalfCauchy::logpdf(v[i], a[i], b[i]); break;
+      case 11: out[i] = gjb::Laplace::logpdf(v[i], a[i], b[i]); break;
+      case 12: out[i] = gjb::LogNormal::logpdf(v[i], a[i], b[i]); break;
+      case 13: out[i] = gjb::Gumbel::logpdf(v[i], a[i], b[i]); break;
+      case 14: out[i] = gjb::Weibull::logpdf(v[i], a[i], b[i]); break;
+    }
+  }
+}
+// inverse-CDF samplers on a given draw d (a u01 value; a standard normal for log_normal); numbering as h_logpdf
+void h_sample(int which, const float* d, const float* a, const float* b, int n, float* out) {
+  for (int i = 0; i < n; ++i) {
+    switch (which) {
+      case 9: out[i] = gjb::Cauchy::sample(d[i], a[i], b[i]); break;
+      case 10: out[i] = gjb::HalfCauchy::sample(d[i], a[i], b[i]); break;
+      case 11: out[i] = gjb::Laplace::sample(d[i], a[i], b[i]); break;
+      case 12: out[i] = gjb::LogNormal::sample(d[i], a[i], b[i]); break;
+      case 13: out[i] = gjb::Gumbel::sample(d[i], a[i], b[i]); break;
+      case 14: out[i] = gjb::Weibull::sample(d[i], a[i], b[i]); break;
     }
   }
 }

@@ -125,12 +125,27 @@ def test_distribution_log_densities_and_samplers(lib):
         (2, pos, b, b, od.exponential_logpdf(pos, b)), (3, pos, b, b, od.half_normal_logpdf(pos, b)),
         (4, pos, b + 0.5, pos, od.gamma_logpdf(pos, b + 0.5, pos)), (5, unit, b + 0.5, pos, od.beta_logpdf(unit, b + 0.5, pos)),
         (6, bits, unit, unit, od.flip_logpdf(bits.astype(bool), unit)), (7, bits, a, a, od.bernoulli_logpdf(bits.astype(bool), a)),
+        (9, v, a, b, od.cauchy_logpdf(v, a, b)), (10, a + pos, a, b, od.half_cauchy_logpdf(a + pos, a, b)),
+        (10, a - pos, a, b, od.half_cauchy_logpdf(a - pos, a, b)), (11, v, a, b, od.laplace_logpdf(v, a, b)),
+        (12, pos, a, b, od.log_normal_logpdf(pos, a, b)), (12, -pos, a, b, od.log_normal_logpdf(-pos, a, b)),
+        (13, v, a, b, od.gumbel_logpdf(v, a, b)), (14, pos, b + 0.3, b, od.weibull_logpdf(pos, b + 0.3, b)),
     ]
     for which, x, p, q, want in cases:
         out = np.zeros(n, dtype=F32)
         x, p, q = (np.ascontiguousarray(t, dtype=F32) for t in (x, p, q))
         lib.h_logpdf(C.c_int(which), _p(x), _p(p), _p(q), C.c_int(n), _p(out))
         np.testing.assert_allclose(out, want, rtol=3e-6, atol=3e-6, err_msg=f"logpdf case {which}")
+    # the inverse-CDF samplers of the long-tail wrappers on the oracle's own draws of lanes 77.. at site 2
+    words, idx = (0x12345678, 0x9ABCDEF0), np.arange(n, dtype=np.uint64) + np.uint64(77)
+    u_q, z_q = rng.quad_u01(words, idx, 2), rng.quad_normal(words, idx, 2)
+    for which, name, p, q in ((9, "cauchy", a, b), (10, "half_cauchy", a, b), (11, "laplace", a, b), (12, "log_normal", a / 4, b / 3),
+                              (13, "gumbel", a, b), (14, "weibull", b + 0.3, b)):
+        out = np.zeros(n, dtype=F32)
+        draw = np.ascontiguousarray(z_q if name == "log_normal" else u_q, dtype=F32)
+        p, q = np.ascontiguousarray(p, dtype=F32), np.ascontiguousarray(q, dtype=F32)
+        lib.h_sample(C.c_int(which), _p(draw), _p(p), _p(q), C.c_int(n), _p(out))
+        want = od.DISTS[name][0](words, idx, 2, p, q)
+        np.testing.assert_allclose(out, want, rtol=2e-5, atol=2e-6, err_msg=name)  # libm tanf / expf vs rounded float64
     logits = np.array([0.1, -0.4, 1.3, 0.0, -2.0], dtype=F32)
     u = np.ascontiguousarray(g.random(n), dtype=F32)
     draws, lp = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=F32)

@@ -356,6 +356,20 @@ def test_weight_upper_bounds_from_the_model():
 
     assert ParticleFilter(hetero, 8).weight_upper_bound(torch.zeros(8), gj.C["y"].set(torch.zeros(3))) is None
 
+    @gj.gen
+    def tails(x_prev, s):  # long-tail observation sites: the mode of each sits at its loc
+        x = gj.normal(x_prev, 1.0) @ "x"
+        gj.cauchy(x, s) @ "y"
+        gj.laplace(x, 2.0) @ "y2"
+        gj.gumbel(x, s) @ "y3"
+        gj.half_cauchy(x, s) @ "y4"
+        return x
+
+    obs = gj.C["y"].set(torch.zeros(3)).at["y2"].set(torch.zeros(3)).at["y3"].set(torch.zeros(3)).at["y4"].set(torch.zeros(3))
+    b = ParticleFilter(tails, 8).weight_upper_bound(torch.zeros(8), obs, (0.5,))
+    ls = math.log(0.5)
+    assert b == pytest.approx((-math.log(math.pi) - ls) + (-math.log(2.0) - math.log(2.0)) + (-1.0 - ls) + (math.log(2 / math.pi) - ls), rel=1e-6)
+
     # the bound really bounds: oracle weights of the scalar model never exceed it
     from oracle import gfi as ogfi
     from oracle import rng

@@ -59,6 +59,27 @@ def test_logpdfs_against_scipy():
     assert dists.half_normal_logpdf(np.float32(-1.0), 1.0) == -np.inf
 
 
+def test_long_tail_scalar_logpdfs_match_scipy():
+    """cauchy, half_cauchy, laplace, log_normal, gumbel, weibull (tensorflow_probability/__init__.py:110-309) against
+    scipy's float64 densities."""
+    n = 2000
+    v = (RNG.standard_normal(n) * 3).astype(np.float32)
+    loc = RNG.standard_normal(n).astype(np.float32)
+    sc = (0.3 + 2 * RNG.random(n)).astype(np.float32)
+    k = (0.5 + 3 * RNG.random(n)).astype(np.float32)
+    pv = np.exp(v / 3).astype(np.float32)
+    hv = (loc + np.abs(v)).astype(np.float32)
+    f = lambda x: x.astype(np.float64)  # noqa: E731
+    _close(dists.cauchy_logpdf(v, loc, sc), stats.cauchy.logpdf(f(v), f(loc), f(sc)), rtol=1e-5, atol=1e-5)
+    _close(dists.half_cauchy_logpdf(hv, loc, sc), stats.halfcauchy.logpdf(f(hv), f(loc), f(sc)), rtol=1e-5, atol=1e-5)
+    _close(dists.laplace_logpdf(v, loc, sc), stats.laplace.logpdf(f(v), f(loc), f(sc)), rtol=1e-5, atol=1e-5)
+    _close(dists.log_normal_logpdf(pv, loc, sc), stats.lognorm.logpdf(f(pv), f(sc), scale=np.exp(f(loc))), rtol=1e-5, atol=1e-5)
+    _close(dists.gumbel_logpdf(v, loc, sc), stats.gumbel_r.logpdf(f(v), f(loc), f(sc)), rtol=1e-5, atol=1e-5)
+    _close(dists.weibull_logpdf(pv, k, sc), stats.weibull_min.logpdf(f(pv), f(k), scale=f(sc)), rtol=1e-5, atol=1e-5)
+    for fn, args in ((dists.half_cauchy_logpdf, (0.0, 1.0)), (dists.log_normal_logpdf, (0.0, 1.0)), (dists.weibull_logpdf, (1.5, 1.0))):
+        assert fn(np.float32(-1.0), *args) == -np.inf  # outside the support
+
+
 def test_categorical_and_mvn_logpdf():
     logits = RNG.standard_normal((50, 16)).astype(np.float32) * 2
     k = RNG.integers(0, 16, 50)
@@ -82,6 +103,12 @@ def test_categorical_and_mvn_logpdf():
         ("gamma", (0.4, 1.0), lambda x: stats.gamma.cdf(x, 0.4)),
         ("beta", (2.0, 2.0), lambda x: stats.beta.cdf(x, 2.0, 2.0)),
         ("beta", (0.5, 3.0), lambda x: stats.beta.cdf(x, 0.5, 3.0)),
+        ("cauchy", (1.0, 2.0), lambda x: stats.cauchy.cdf(x, 1.0, 2.0)),
+        ("half_cauchy", (1.0, 2.0), lambda x: stats.halfcauchy.cdf(x, 1.0, 2.0)),
+        ("laplace", (-1.0, 0.5), lambda x: stats.laplace.cdf(x, -1.0, 0.5)),
+        ("log_normal", (0.3, 0.8), lambda x: stats.lognorm.cdf(x, 0.8, scale=math.exp(0.3))),
+        ("gumbel", (0.5, 1.5), lambda x: stats.gumbel_r.cdf(x, 0.5, 1.5)),
+        ("weibull", (1.7, 2.0), lambda x: stats.weibull_min.cdf(x, 1.7, scale=2.0)),
     ],
 )
 def test_continuous_samplers_ks(name, args, cdf):
