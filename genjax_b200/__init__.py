@@ -26,16 +26,21 @@ from .gen.distributions import (
     beta,
     categorical,
     cauchy,
+    chi2,
     exact_density,
     exponential,
     flip,
     gamma,
+    geometric,
     gmm_diag,
     gumbel,
     half_cauchy,
     half_normal,
+    inverse_gamma,
+    kumaraswamy,
     laplace,
     log_normal,
+    logit_normal,
     mv_normal,
     mv_normal_diag,
     normal,

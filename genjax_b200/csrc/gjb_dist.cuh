@@ -51,7 +51,7 @@ struct HalfNormal {
 
 // ------------------------------------------- long-tail scalar wrappers
 // tensorflow_probability/__init__.py:110 (cauchy), :179 (half_cauchy), :214 (laplace), :219 (log_normal), :174 (gumbel),
-// :309 (weibull).  Inverse-CDF samplers on one u01 word (u in [2^-25, 1)); log-densities in TFP 0.23's operation order
+// :309 (weibull), :204 (kumaraswamy), :224 (logit_normal), :169 (geometric), :194 (inverse_gamma), :120 (chi2).  Inverse-CDF samplers on one u01 word (u in [2^-25, 1)); log-densities in TFP 0.23's operation order
 // as restated in oracle/dists.py.
 constexpr float kPi = 3.14159265358979323846f;
 constexpr float kLogPi = 1.14472988584940017414f;
@@ -105,6 +105,34 @@ struct Weibull {  // (concentration k, scale s): x = s (-log(1 - u))^(1/k)
   __device__ static __forceinline__ float logpdf(float v, float k, float s) {
     const float t = logf(v) - logf(s);
     return v < 0.0f ? -INFINITY : logf(k) - logf(s) + (k - 1.0f) * t - expf(k * t);
+  }
+};
+
+struct Kumaraswamy {  // (concentration1 a, concentration0 b): x = (1 - (1 - u)^(1/b))^(1/a)
+  __device__ static __forceinline__ float sample(float u, float a, float b) {
+    return expf(logf(-expm1f(log1pf(-u) / b)) / a);
+  }
+  __device__ static __forceinline__ float logpdf(float v, float a, float b) {
+    const float lv = logf(v);
+    const float t1 = ((a - 1.0f) == 0.0f) ? 0.0f : (a - 1.0f) * lv;
+    const float t2 = ((b - 1.0f) == 0.0f) ? 0.0f : (b - 1.0f) * log1pf(-expf(a * lv));
+    return (v < 0.0f || v > 1.0f) ? -INFINITY : logf(a) + logf(b) + t1 + t2;
+  }
+};
+
+struct LogitNormal {  // sigmoid of a Normal(loc, scale): Normal log-density of logit v, minus the log-Jacobian
+  __device__ static __forceinline__ float sample(float z, float loc, float scale) { return 1.0f / (1.0f + expf(-(loc + scale * z))); }
+  __device__ static __forceinline__ float logpdf(float v, float loc, float scale) {
+    const float lv = logf(v), l1 = log1pf(-v);
+    return (v > 0.0f && v < 1.0f) ? Normal::logpdf(lv - l1, loc, scale) - lv - l1 : -INFINITY;
+  }
+};
+
+struct Geometric {  // tfd.Geometric(probs=p): failures before the first success, a float-valued count as in TFP
+  __device__ static __forceinline__ float sample(float u, float p) { return floorf(logf(u) / log1pf(-p)); }
+  __device__ static __forceinline__ float logpdf(float v, float p) {
+    const float t = (v == 0.0f) ? 0.0f : v * log1pf(-p);
+    return v < 0.0f ? -INFINITY : t + logf(p);
   }
 };
 
@@ -283,6 +311,18 @@ struct Gamma {
     const float t = ((a - 1.0f) == 0.0f) ? 0.0f : (a - 1.0f) * logf(v);
     return t - rate * v - (lgammaf(a) - a * logf(rate));
   }
+};
+
+struct InverseGamma {  // (concentration a, scale b): b / Gamma(a, 1)
+  __device__ static __forceinline__ float sample(const Lane& l, uint32_t site, float a, float b) { return b / gamma_mt(l, site, a, 0); }
+  __device__ static __forceinline__ float logpdf(float v, float a, float b) {
+    return v > 0.0f ? a * logf(b) - lgammaf(a) - (a + 1.0f) * logf(v) - b / v : -INFINITY;
+  }
+};
+
+struct Chi2 {  // (df): Gamma(df / 2, rate 1/2)
+  __device__ static __forceinline__ float sample(const Lane& l, uint32_t site, float df) { return gamma_mt(l, site, 0.5f * df, 0) / 0.5f; }
+  __device__ static __forceinline__ float logpdf(float v, float df) { return Gamma::logpdf(v, 0.5f * df, 0.5f); }
 };
 
 struct Beta {

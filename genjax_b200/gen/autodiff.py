@@ -73,6 +73,28 @@ def logpdf_expr(dist, v: Expr, args: list) -> Expr:
         t = E.unary("log", v) - E.unary("log", scale)
         lp = E.unary("log", k) - E.unary("log", scale) + (k - 1.0) * t - E.unary("exp", k * t)
         return E.where(v < 0.0, E.const(-math.inf), lp)
+    if name == "kumaraswamy":
+        a, b = args
+        lv = E.unary("log", v)
+        lp = E.unary("log", a) + E.unary("log", b) + (a - 1.0) * lv + (b - 1.0) * E.unary("log1p", -E.unary("exp", a * lv))
+        return E.where((v < 0.0) | (v > 1.0), E.const(-math.inf), lp)
+    if name == "logit_normal":
+        loc, scale = args
+        lv, l1 = E.unary("log", v), E.unary("log1p", -v)
+        z = (lv - l1) / scale - loc / scale
+        lp = E.const(-0.5) * E.unary("square", z) - (E.const(_HALF_LOG_2PI) + E.unary("log", scale)) - lv - l1
+        return E.where((v > 0.0) & (v < 1.0), lp, E.const(-math.inf))
+    if name == "geometric":
+        (p,) = args
+        return E.where(v < 0.0, E.const(-math.inf), v * E.unary("log1p", -p) + E.unary("log", p))
+    if name == "inverse_gamma":
+        a, b = args
+        lp = a * E.unary("log", b) - E.unary("lgamma", a) - (a + 1.0) * E.unary("log", v) - b / v
+        return E.where(v > 0.0, lp, E.const(-math.inf))
+    if name == "chi2":
+        (df,) = args
+        a = 0.5 * df
+        return (a - 1.0) * E.unary("log", v) - 0.5 * v - (E.unary("lgamma", a) - a * E.const(math.log(0.5)))
     if name == "exponential":
         (rate,) = args
         return E.where(v < 0.0, E.const(-math.inf), E.unary("log", rate) - rate * v)
@@ -138,6 +160,10 @@ def grad(out: Expr, wrt: list) -> list:
         raise ValueError("grad needs a scalar output")
     order = E.topo([out])
     adj: dict[int, Expr] = {out._id: E.const(1.0)}
+    dep = {w._id for w in wrt}  # nodes whose value moves with a differentiated variable
+    for e in order:
+        if any(x._id in dep for x in e.ins):
+            dep.add(e._id)
 
     def acc(node: Expr, g):
         if node.dtype != F32 or node.op in ("const", "constvec"):
@@ -212,6 +238,8 @@ def grad(out: Expr, wrt: list) -> list:
         elif op in ("floor", "lt", "le", "gt", "ge", "eq", "ne", "and", "or", "logical_not", "row", "gather1"):
             pass  # piecewise constant / integer / table lookups of non-differentiated data
         elif op == "lgamma":
+            if i[0]._id not in dep:
+                continue  # a shape parameter fed by arguments / non-differentiated sites only: constant here
             raise NotDifferentiable("gradient through lgamma (needs digamma) is not available on the device")
         else:
             raise NotDifferentiable(f"no derivative rule for op {op!r}")

@@ -180,6 +180,41 @@ class _Weibull(_LocScale):
     kw_names = ("concentration", "scale")
 
 
+class _Kumaraswamy(_LocScale):
+    """tfd.Kumaraswamy(concentration1, concentration0) (tensorflow_probability/__init__.py:204)."""
+
+    name, cuda = "kumaraswamy", "Kumaraswamy"
+    kw_names = ("concentration1", "concentration0")
+
+
+class _LogitNormal(_LocScale):
+    name, cuda = "logit_normal", "LogitNormal"
+    rng_kind = "normal"
+
+
+class _Geometric(_LocScale):
+    """tfd.Geometric(probs=p) (tensorflow_probability/__init__.py:169): float-valued count of failures."""
+
+    name, cuda, n_args = "geometric", "Geometric", 1
+    kw_names = ("probs",)
+
+
+class _InverseGamma(_LocScale):
+    """tfd.InverseGamma(concentration, scale) (tensorflow_probability/__init__.py:194)."""
+
+    name, cuda = "inverse_gamma", "InverseGamma"
+    kw_names = ("concentration", "scale")
+    rng_kind = "lane"
+
+
+class _Chi2(_LocScale):
+    """tfd.Chi2(df) (tensorflow_probability/__init__.py:120)."""
+
+    name, cuda, n_args = "chi2", "Chi2", 1
+    kw_names = ("df",)
+    rng_kind = "lane"
+
+
 class _Gamma(Distribution):
     name, cuda, n_args = "gamma", "Gamma", 2
     rng_kind = "lane"
@@ -381,6 +416,11 @@ laplace = _Laplace()
 log_normal = _LogNormal()
 gumbel = _Gumbel()
 weibull = _Weibull()
+kumaraswamy = _Kumaraswamy()
+logit_normal = _LogitNormal()
+geometric = _Geometric()
+inverse_gamma = _InverseGamma()
+chi2 = _Chi2()
 gamma = _Gamma()
 beta = _Beta()
 flip = _Flip()
@@ -392,7 +432,8 @@ mv_normal = _MvNormal()
 
 REGISTRY: dict[str, Distribution] = {
     d.name: d
-    for d in (normal, uniform, exponential, half_normal, cauchy, half_cauchy, laplace, log_normal, gumbel, weibull, gamma, beta, flip, bernoulli, categorical, mv_normal_diag, gmm_diag, mv_normal)
+    for d in (normal, uniform, exponential, half_normal, cauchy, half_cauchy, laplace, log_normal, gumbel, weibull, kumaraswamy, logit_normal, geometric,
+              inverse_gamma, chi2, gamma, beta, flip, bernoulli, categorical, mv_normal_diag, gmm_diag, mv_normal)
 }
 
 

@@ -260,6 +260,49 @@ def weibull_logpdf(v, concentration, scale):
     return np.where(v < 0, F32(-np.inf), lp).astype(F32)
 
 
+def kumaraswamy_logpdf(v, concentration1, concentration0):
+    """tfd.Kumaraswamy (inverse KumaraswamyCDF bijector on Uniform): log a + log b + xlogy(a-1, x) + xlog1py(b-1, -x^a),
+    0 <= x <= 1 (tensorflow_probability/__init__.py:204)."""
+    v, a, b = _f(v), _f(concentration1), _f(concentration0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lv = _log(v)
+        t1 = np.where((a - F32(1)) == 0, F32(0), (a - F32(1)) * lv).astype(F32)
+        t2 = np.where((b - F32(1)) == 0, F32(0), (b - F32(1)) * _log1p(-_exp((a * lv).astype(F32)))).astype(F32)
+        lp = (_log(a) + _log(b) + t1 + t2).astype(F32)
+    return np.where((v < 0) | (v > 1), F32(-np.inf), lp).astype(F32)
+
+
+def logit_normal_logpdf(v, loc, scale):
+    """tfd.LogitNormal = Sigmoid(Normal): Normal log-density of logit x minus log x + log(1 - x), 0 < x < 1
+    (tensorflow_probability/__init__.py:224)."""
+    v = _f(v)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lv, l1 = _log(v), _log1p(-v)
+        lp = (normal_logpdf((lv - l1).astype(F32), loc, scale) - lv - l1).astype(F32)
+    return np.where((v > 0) & (v < 1), lp, F32(-np.inf)).astype(F32)
+
+
+def geometric_logpdf(v, probs):
+    """tfd.Geometric._log_prob: xlog1py(x, -p) + log p, x >= 0 (tensorflow_probability/__init__.py:169)."""
+    v, p = _f(v), _f(probs)
+    t = np.where(v == 0, F32(0), v * _log1p(-p)).astype(F32)
+    return np.where(v < 0, F32(-np.inf), (t + _log(p)).astype(F32)).astype(F32)
+
+
+def inverse_gamma_logpdf(v, concentration, scale):
+    """tfd.InverseGamma._log_prob: a log b - lgamma(a) - (a + 1) log x - b / x, x > 0
+    (tensorflow_probability/__init__.py:194)."""
+    v, a, b = _f(v), _f(concentration), _f(scale)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lp = (a * _log(b) - _lgamma(a) - (a + F32(1)) * _log(v) - b / v).astype(F32)
+    return np.where(v > 0, lp, F32(-np.inf)).astype(F32)
+
+
+def chi2_logpdf(v, df):
+    """tfd.Chi2(df) = Gamma(df / 2, rate 1/2) (tensorflow_probability/__init__.py:120)."""
+    return gamma_logpdf(v, (F32(0.5) * _f(df)).astype(F32), F32(0.5))
+
+
 # ---------------------------------------------------------------- samplers
 # sampler(words, idx, site, *args) -> values for the lanes in idx
 
@@ -349,6 +392,21 @@ def weibull_sample(words, idx, site, concentration, scale):
     return (_f(scale) * _exp((_log(e) / _f(concentration)).astype(F32))).astype(F32)
 
 
+def kumaraswamy_sample(words, idx, site, concentration1, concentration0):
+    u = rng.quad_u01(words, idx, site)
+    t = (-np.expm1((_log1p(-u) / _f(concentration0)).astype(F32).astype(np.float64))).astype(F32)
+    return _exp((_log(t) / _f(concentration1)).astype(F32))
+
+
+def logit_normal_sample(words, idx, site, loc, scale):
+    x = (_f(loc) + _f(scale) * rng.quad_normal(words, idx, site)).astype(F32)
+    return (F32(1) / (F32(1) + _exp(-x))).astype(F32)
+
+
+def geometric_sample(words, idx, site, probs):
+    return np.floor((_log(rng.quad_u01(words, idx, site)) / _log1p(-_f(probs))).astype(F32)).astype(F32)
+
+
 def mv_normal_diag_sample(words, idx, site, loc, scale_diag):
     loc = _f(loc)
     scale_diag = _f(scale_diag)
@@ -406,6 +464,14 @@ def gamma_sample(words, idx, site, concentration, rate):
     return (g / _f(rate)).astype(F32)
 
 
+def inverse_gamma_sample(words, idx, site, concentration, scale):
+    return (_f(scale) / _gamma_mt(words, idx, site, concentration, 0)).astype(F32)
+
+
+def chi2_sample(words, idx, site, df):
+    return (_gamma_mt(words, idx, site, (F32(0.5) * _f(df)).astype(F32), 0) / F32(0.5)).astype(F32)
+
+
 def beta_sample(words, idx, site, a, b):
     """X = Ga / (Ga + Gb) with Ga ~ Gamma(a,1) on chunks [0,64), Gb on [64,128)."""
     ga = _gamma_mt(words, idx, site, a, 0)
@@ -432,4 +498,9 @@ DISTS = {
     "log_normal": (log_normal_sample, log_normal_logpdf),
     "gumbel": (gumbel_sample, gumbel_logpdf),
     "weibull": (weibull_sample, weibull_logpdf),
+    "kumaraswamy": (kumaraswamy_sample, kumaraswamy_logpdf),
+    "logit_normal": (logit_normal_sample, logit_normal_logpdf),
+    "geometric": (geometric_sample, geometric_logpdf),
+    "inverse_gamma": (inverse_gamma_sample, inverse_gamma_logpdf),
+    "chi2": (chi2_sample, chi2_logpdf),
 }

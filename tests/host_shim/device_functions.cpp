@@ -35,6 +35,7 @@ extern "C" {
 // which: 0 normal(v, loc, scale)  1 uniform(v, lo, hi)  2 exponential(v, rate)  3 half_normal(v, scale)
 //        4 gamma(v, a, rate)  5 beta(v, a, b)  6 flip(v, p)  7 bernoulli(v, logit)  8 normal logpdf_r(v, loc, 1/scale, lc)
 //        9 cauchy  10 half_cauchy  11 laplace  12 log_normal  13 gumbel (v, loc, scale)  14 weibull(v, k, scale)
+//        15 kumaraswamy(v, a, b)  16 logit_normal(v, loc, scale)  17 geometric(v, p)  18 inverse_gamma(v, a, scale)  19 chi2(v, df)
 void h_logpdf(int which, const float* v, const float* a, const float* b, int n, float* out) {
   for (int i = 0; i < n; ++i) {
     switch (which) {
@@ -53,6 +54,11 @@ void h_logpdf(int which, const float* v, const float* a, const float* b, int n, 
       case 12: out[i] = gjb::LogNormal::logpdf(v[i], a[i], b[i]); break;
       case 13: out[i] = gjb::Gumbel::logpdf(v[i], a[i], b[i]); break;
       case 14: out[i] = gjb::Weibull::logpdf(v[i], a[i], b[i]); break;
+      case 15: out[i] = gjb::Kumaraswamy::logpdf(v[i], a[i], b[i]); break;
+      case 16: out[i] = gjb::LogitNormal::logpdf(v[i], a[i], b[i]); break;
+      case 17: out[i] = gjb::Geometric::logpdf(v[i], a[i]); break;
+      case 18: out[i] = gjb::InverseGamma::logpdf(v[i], a[i], b[i]); break;
+      case 19: out[i] = gjb::Chi2::logpdf(v[i], a[i]); break;
     }
   }
 }
@@ -66,6 +72,9 @@ void h_sample(int which, const float* d, const float* a, const float* b, int n, 
       case 12: out[i] = gjb::LogNormal::sample(d[i], a[i], b[i]); break;
       case 13: out[i] = gjb::Gumbel::sample(d[i], a[i], b[i]); break;
       case 14: out[i] = gjb::Weibull::sample(d[i], a[i], b[i]); break;
+      case 15: out[i] = gjb::Kumaraswamy::sample(d[i], a[i], b[i]); break;
+      case 16: out[i] = gjb::LogitNormal::sample(d[i], a[i], b[i]); break;
+      case 17: out[i] = gjb::Geometric::sample(d[i], a[i]); break;
     }
   }
 }
@@ -76,6 +85,13 @@ void h_categorical(const float* logits, int K, const float* u, int n, int32_t* d
   }
 }
 // lane-stream rejection samplers: lane = (key, global index), site as in the kernels
+void h_inverse_gamma_chi2(uint32_t k0, uint32_t k1, uint64_t idx0, int n, uint32_t site, float a, float b, float* ig_out, float* chi2_out) {
+  for (int i = 0; i < n; ++i) {
+    const gjb::Lane l = gjb::make_lane(k0, k1, idx0 + (uint64_t)i);
+    ig_out[i] = gjb::InverseGamma::sample(l, site, a, b);
+    chi2_out[i] = gjb::Chi2::sample(l, site, 2.0f * a);
+  }
+}
 void h_gamma_beta(uint32_t k0, uint32_t k1, uint64_t idx0, int n, uint32_t site, float a, float b, float* gamma_out, float* beta_out) {
   for (int i = 0; i < n; ++i) {
     const gjb::Lane l = gjb::make_lane(k0, k1, idx0 + (uint64_t)i);

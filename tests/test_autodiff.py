@@ -119,3 +119,35 @@ def test_long_tail_logp_and_grad():
         y = x.copy()
         y[j] = bad
         assert float(evaluate(logp, env(y))) == -np.inf
+
+
+def test_second_slice_logp_and_grad():
+    """kumaraswamy, logit_normal, geometric, inverse_gamma, chi2: symbolic log-densities against the oracle, gradients
+    in the continuous sites against central finite differences."""
+    import genjax_b200 as gj
+
+    def model(s):
+        a = gj.kumaraswamy(2.0, s) @ "a"
+        b = gj.logit_normal(a, 0.5) @ "b"
+        k = gj.geometric(0.1 + 0.8 * b) @ "k"
+        g = gj.inverse_gamma(2.0 + k, s + a) @ "g"
+        c = gj.chi2(1.0 + s) @ "c"  # a df that depends on a continuous site would need digamma
+        return g + c
+
+    ir = cap.capture(model, "s2", [ArgSpec("scalar", "f32", ())], ("tuple", [("leaf", 0)]))
+    logp = AD.model_logp(ir)
+    cont = [0, 1, 3, 4]
+    grads = AD.grad(logp, [ir.sites[j].value for j in cont])
+    s, k = 1.5, 3.0
+    x = np.array([0.35, 0.6, 0.9, 2.5])
+
+    def env(x):
+        return {0: x[0], 1: x[1], 2: k, 3: x[2], 4: x[3], ("arg", 0): s}
+
+    a, b, g, c = x
+    want = (dists.kumaraswamy_logpdf(a, 2.0, s).astype(np.float64) + dists.logit_normal_logpdf(b, a, 0.5)
+            + dists.geometric_logpdf(k, 0.1 + 0.8 * b) + dists.inverse_gamma_logpdf(g, 2.0 + k, s + a) + dists.chi2_logpdf(c, 1.0 + s))
+    assert float(evaluate(logp, env(x))) == pytest.approx(float(want), rel=2e-6)
+    cache = {}
+    got = np.array([float(evaluate(gr, env(x), cache)) for gr in grads])
+    np.testing.assert_allclose(got, _fd(lambda v: float(evaluate(logp, env(v))), x), rtol=1e-5, atol=1e-7)

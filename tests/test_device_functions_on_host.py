@@ -129,6 +129,10 @@ def test_distribution_log_densities_and_samplers(lib):
         (10, a - pos, a, b, od.half_cauchy_logpdf(a - pos, a, b)), (11, v, a, b, od.laplace_logpdf(v, a, b)),
         (12, pos, a, b, od.log_normal_logpdf(pos, a, b)), (12, -pos, a, b, od.log_normal_logpdf(-pos, a, b)),
         (13, v, a, b, od.gumbel_logpdf(v, a, b)), (14, pos, b + 0.3, b, od.weibull_logpdf(pos, b + 0.3, b)),
+        (15, unit, b + 0.3, pos, od.kumaraswamy_logpdf(unit, b + 0.3, pos)), (15, unit + 1, b, b, od.kumaraswamy_logpdf(unit + 1, b, b)),
+        (16, unit, a, b, od.logit_normal_logpdf(unit, a, b)), (16, -unit, a, b, od.logit_normal_logpdf(-unit, a, b)),
+        (17, np.floor(pos * 3), unit, unit, od.geometric_logpdf(np.floor(pos * 3), unit)),
+        (18, pos, b + 0.5, pos[::-1], od.inverse_gamma_logpdf(pos, b + 0.5, pos[::-1])), (19, pos, b + 0.5, b, od.chi2_logpdf(pos, b + 0.5)),
     ]
     for which, x, p, q, want in cases:
         out = np.zeros(n, dtype=F32)
@@ -139,12 +143,17 @@ def test_distribution_log_densities_and_samplers(lib):
     words, idx = (0x12345678, 0x9ABCDEF0), np.arange(n, dtype=np.uint64) + np.uint64(77)
     u_q, z_q = rng.quad_u01(words, idx, 2), rng.quad_normal(words, idx, 2)
     for which, name, p, q in ((9, "cauchy", a, b), (10, "half_cauchy", a, b), (11, "laplace", a, b), (12, "log_normal", a / 4, b / 3),
-                              (13, "gumbel", a, b), (14, "weibull", b + 0.3, b)):
+                              (13, "gumbel", a, b), (14, "weibull", b + 0.3, b), (15, "kumaraswamy", b + 0.3, pos),
+                              (16, "logit_normal", a, b), (17, "geometric", unit, None)):
         out = np.zeros(n, dtype=F32)
-        draw = np.ascontiguousarray(z_q if name == "log_normal" else u_q, dtype=F32)
-        p, q = np.ascontiguousarray(p, dtype=F32), np.ascontiguousarray(q, dtype=F32)
-        lib.h_sample(C.c_int(which), _p(draw), _p(p), _p(q), C.c_int(n), _p(out))
-        want = od.DISTS[name][0](words, idx, 2, p, q)
+        draw = np.ascontiguousarray(z_q if name in ("log_normal", "logit_normal") else u_q, dtype=F32)
+        p = np.ascontiguousarray(p, dtype=F32)
+        params = (p,) if q is None else (p, np.ascontiguousarray(q, dtype=F32))
+        lib.h_sample(C.c_int(which), _p(draw), _p(p), _p(params[-1]), C.c_int(n), _p(out))
+        want = od.DISTS[name][0](words, idx, 2, *params)
+        if name == "geometric":  # floor of a quotient: an ulp can move a draw sitting on an integer boundary
+            assert np.mean(out != want) < 0.002 and np.abs(out - want).max() <= 1
+            continue
         np.testing.assert_allclose(out, want, rtol=2e-5, atol=2e-6, err_msg=name)  # libm tanf / expf vs rounded float64
     logits = np.array([0.1, -0.4, 1.3, 0.0, -2.0], dtype=F32)
     u = np.ascontiguousarray(g.random(n), dtype=F32)
@@ -162,3 +171,7 @@ def test_distribution_log_densities_and_samplers(lib):
         # a one-ulp libm difference can flip a rejection: allow a handful of lanes to take a different attempt
         assert np.mean(~np.isclose(ga, want_g, rtol=2e-5, atol=1e-6)) < 0.002
         assert np.mean(~np.isclose(be, want_b, rtol=2e-5, atol=1e-6)) < 0.002
+        lib.h_inverse_gamma_chi2(C.c_uint32(words[0]), C.c_uint32(words[1]), C.c_uint64(77), C.c_int(n), C.c_uint32(3), C.c_float(aa),
+                                 C.c_float(bb), _p(ga), _p(be))
+        assert np.mean(~np.isclose(ga, od.inverse_gamma_sample(words, idx, 3, F32(aa), F32(bb)), rtol=2e-5, atol=1e-6)) < 0.002
+        assert np.mean(~np.isclose(be, od.chi2_sample(words, idx, 3, F32(2 * aa)), rtol=2e-5, atol=1e-6)) < 0.002

@@ -80,6 +80,32 @@ def test_long_tail_scalar_logpdfs_match_scipy():
         assert fn(np.float32(-1.0), *args) == -np.inf  # outside the support
 
 
+def test_second_slice_logpdfs_match_scipy():
+    """kumaraswamy, logit_normal, geometric, inverse_gamma, chi2 (tensorflow_probability/__init__.py:204, 224, 169, 194,
+    120) against float64 closed forms / scipy; the geometric sampler's frequencies."""
+    n = 2000
+    f = lambda x: x.astype(np.float64)  # noqa: E731
+    a = (0.4 + 3 * RNG.random(n)).astype(np.float32)
+    b = (0.4 + 3 * RNG.random(n)).astype(np.float32)
+    unit = (0.01 + 0.98 * RNG.random(n)).astype(np.float32)
+    pos = (0.05 + 4 * RNG.random(n)).astype(np.float32)
+    loc = RNG.standard_normal(n).astype(np.float32)
+    kref = np.log(f(a)) + np.log(f(b)) + (f(a) - 1) * np.log(f(unit)) + (f(b) - 1) * np.log1p(-f(unit) ** f(a))
+    _close(dists.kumaraswamy_logpdf(unit, a, b), kref, rtol=1e-5, atol=1e-5)
+    lref = stats.norm.logpdf(np.log(f(unit)) - np.log1p(-f(unit)), f(loc), f(b)) - np.log(f(unit)) - np.log1p(-f(unit))
+    _close(dists.logit_normal_logpdf(unit, loc, b), lref, rtol=1e-5, atol=1e-5)
+    k = RNG.integers(0, 20, n).astype(np.float32)
+    _close(dists.geometric_logpdf(k, unit), stats.geom.logpmf(f(k) + 1, f(unit)), rtol=1e-5, atol=1e-5)  # scipy counts trials
+    _close(dists.inverse_gamma_logpdf(pos, a, b), stats.invgamma.logpdf(f(pos), f(a), scale=f(b)), rtol=1e-5, atol=1e-5)
+    _close(dists.chi2_logpdf(pos, 2 * a), stats.chi2.logpdf(f(pos), f(2 * a)), rtol=1e-5, atol=1e-5)
+    for fn, v, args in ((dists.kumaraswamy_logpdf, 1.5, (2.0, 2.0)), (dists.logit_normal_logpdf, 1.0, (0.0, 1.0)),
+                        (dists.geometric_logpdf, -1.0, (0.3,)), (dists.inverse_gamma_logpdf, 0.0, (2.0, 1.0))):
+        assert fn(np.float32(v), *args) == -np.inf
+    x = dists.geometric_sample((11, 22), np.arange(100_000, dtype=np.uint64), 1, np.float32(0.3))
+    assert x.dtype == np.float32 and x.min() == 0 and (x == np.floor(x)).all()
+    np.testing.assert_allclose(np.bincount(x.astype(int))[:4] / x.size, 0.3 * 0.7 ** np.arange(4), atol=5e-3)
+
+
 def test_categorical_and_mvn_logpdf():
     logits = RNG.standard_normal((50, 16)).astype(np.float32) * 2
     k = RNG.integers(0, 16, 50)
@@ -109,6 +135,11 @@ def test_categorical_and_mvn_logpdf():
         ("log_normal", (0.3, 0.8), lambda x: stats.lognorm.cdf(x, 0.8, scale=math.exp(0.3))),
         ("gumbel", (0.5, 1.5), lambda x: stats.gumbel_r.cdf(x, 0.5, 1.5)),
         ("weibull", (1.7, 2.0), lambda x: stats.weibull_min.cdf(x, 1.7, scale=2.0)),
+        ("kumaraswamy", (2.0, 3.0), lambda x: 1 - (1 - x**2.0) ** 3.0),
+        ("logit_normal", (0.3, 0.8), lambda x: stats.norm.cdf(np.log(x) - np.log1p(-x), 0.3, 0.8)),
+        ("inverse_gamma", (3.0, 2.0), lambda x: stats.invgamma.cdf(x, 3.0, scale=2.0)),
+        ("chi2", (3.5,), lambda x: stats.chi2.cdf(x, 3.5)),
+        ("chi2", (0.8,), lambda x: stats.chi2.cdf(x, 0.8)),
     ],
 )
 def test_continuous_samplers_ks(name, args, cdf):

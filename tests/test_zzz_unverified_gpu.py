@@ -350,7 +350,8 @@ def test_single_pass_filter_equals_the_two_launch_filter(device, n):
 # ------------------------------------------------------------------ long-tail scalar wrappers
 
 _LONG_TAIL = [("cauchy", (1.0, 2.0)), ("half_cauchy", (1.0, 2.0)), ("laplace", (-1.0, 0.5)), ("log_normal", (0.3, 0.8)),
-              ("gumbel", (0.5, 1.5)), ("weibull", (1.7, 2.0))]
+              ("gumbel", (0.5, 1.5)), ("weibull", (1.7, 2.0)), ("kumaraswamy", (2.0, 3.0)), ("logit_normal", (0.3, 0.8)),
+              ("geometric", (0.3,)), ("inverse_gamma", (3.0, 2.0)), ("chi2", (3.5,)), ("chi2", (0.8,))]
 
 
 @pytest.mark.parametrize("name,args", _LONG_TAIL)
@@ -364,8 +365,9 @@ def test_long_tail_primitive_sample_and_logpdf_match_oracle(device, name, args):
     v = tr.get_retval().cpu().numpy()
     words, idx = rng.lanes(rng.split(rng.key(11), n))
     ov = od.DISTS[name][0](words, idx, 1, *[F32(a) for a in args])
-    # tanf / expf of the device against a rounded float64 evaluation; the Cauchy tails amplify an ulp of the argument
-    assert (~np.isclose(v, ov, rtol=1e-4, atol=1e-5)).mean() < 1e-4, name
+    # tanf / expf of the device against a rounded float64 evaluation; the Cauchy tails amplify an ulp of the argument, an
+    # ulp can flip a rejection of the gamma samplers or move a geometric draw across an integer
+    assert (~np.isclose(v, ov, rtol=1e-4, atol=1e-5)).mean() < (2e-3 if name in ("inverse_gamma", "chi2", "geometric") else 1e-4), name
     np.testing.assert_allclose(tr.get_score().cpu().numpy(), od.DISTS[name][1](v, *[F32(a) for a in args]), rtol=2e-5, atol=2e-5)
     kw = dict(zip(getattr(gj, name).kw_names, args))  # TFP's keyword spelling
     tr2 = getattr(gj, name).simulate(gj.split(gj.key(11), 64), ((), kw))
@@ -403,4 +405,37 @@ def test_long_tail_sites_inside_a_model(device):
         np.testing.assert_array_equal(c2[k], ch[k])
     ww = od.gumbel_logpdf(F32(0.3), c2["c"], c2["d"]) + od.weibull_logpdf(F32(1.1), F32(1) + c2["d"], F32(s))
     assert not np.isnan(ww).any()  # -inf where the Cauchy tail of c pushes the observed e out of the Gumbel's reach
+    np.testing.assert_allclose(w.cpu().numpy(), ww, rtol=1e-4, atol=1e-4)
+
+
+def test_second_slice_sites_inside_a_model(device):
+    """kumaraswamy, logit_normal, geometric, inverse_gamma, chi2 as sites of one model (quad-block and lane-stream
+    samplers mixed): scores and importance weights equal the oracle's log-densities."""
+    gj = _gj()
+
+    @gj.gen
+    def model(s):
+        a = gj.kumaraswamy(2.0, s) @ "a"
+        b = gj.logit_normal(a, 0.5) @ "b"
+        k = gj.geometric(0.1 + 0.8 * b) @ "k"
+        g = gj.inverse_gamma(2.0 + k, s) @ "g"
+        c = gj.chi2(1.0 + a) @ "c"
+        return g + c
+
+    n, s = 4096, 1.5
+    tr = model.simulate(gj.split(gj.key(6), n), (s,))
+    ch = {k: tr.get_choices()[k].cpu().numpy() for k in "abkgc"}
+    assert ((ch["a"] > 0) & (ch["a"] < 1)).all() and ((ch["b"] > 0) & (ch["b"] < 1)).all()
+    assert (ch["k"] >= 0).all() and (ch["k"] == np.floor(ch["k"])).all() and (ch["g"] > 0).all() and (ch["c"] > 0).all()
+    want = (od.kumaraswamy_logpdf(ch["a"], F32(2), F32(s)) + od.logit_normal_logpdf(ch["b"], ch["a"], F32(0.5))
+            + od.geometric_logpdf(ch["k"], F32(0.1) + F32(0.8) * ch["b"]) + od.inverse_gamma_logpdf(ch["g"], F32(2) + ch["k"], F32(s))
+            + od.chi2_logpdf(ch["c"], F32(1) + ch["a"]))
+    assert np.isfinite(want).all()
+    np.testing.assert_allclose(tr.get_score().cpu().numpy(), want, rtol=1e-4, atol=1e-4)
+    obs = gj.C["g"].set(0.9).at["c"].set(2.5)
+    tr2, w = model.importance(gj.split(gj.key(6), n), obs, (s,))
+    c2 = {k: tr2.get_choices()[k].cpu().numpy() for k in "abk"}
+    for k in "abk":
+        np.testing.assert_array_equal(c2[k], ch[k])
+    ww = od.inverse_gamma_logpdf(F32(0.9), F32(2) + c2["k"], F32(s)) + od.chi2_logpdf(F32(2.5), F32(1) + c2["a"])
     np.testing.assert_allclose(w.cpu().numpy(), ww, rtol=1e-4, atol=1e-4)
