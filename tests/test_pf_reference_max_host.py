@@ -125,3 +125,19 @@ def test_single_pass_filter_matches_oracle(emu, n):
     # ping-pong buffers (no history)
     plain = ParticleFilter(lgssm_step, n, reference_max="analytic", single_pass=True).run(gj.key(17), torch.from_numpy(x0), obs)
     assert torch.equal(plain.log_increments, one.log_increments) and torch.equal(plain.state[0], one.state[0])
+
+
+def test_single_pass_when_every_mass_underflows(emu):
+    """An observation so far out that every weight sits more than the 25-nat range of the integer masses below the
+    analytic bound (S == 0): both the two-launch and the single-pass filter leave that step unresampled (identity
+    ancestors, log-increment -inf) and agree on every later step."""
+    n, T = 3000, 4
+    ys = np.array([0.2, 90.0, -0.4, 0.1], dtype=F32)  # y_1 = 90: weights near -16 000
+    x0 = np.random.default_rng(3).standard_normal(n).astype(F32)
+    obs = gj.C["y"].set(torch.from_numpy(ys))
+    one = ParticleFilter(lgssm_step, n, reference_max="analytic", single_pass=True).run(gj.key(5), torch.from_numpy(x0), obs, record=True)
+    two = ParticleFilter(lgssm_step, n, reference_max="analytic").run(gj.key(5), torch.from_numpy(x0), obs, record=True)
+    assert one.lse_terms[1, 1].item() == 0.0 and one.log_increments[1].item() == -np.inf
+    assert torch.equal(one.ancestors[1], torch.arange(n, dtype=torch.int32))
+    assert torch.equal(one.ancestors, two.ancestors) and torch.equal(one.lse_terms, two.lse_terms)
+    assert torch.equal(one.history["log_weights"], two.history["log_weights"]) and torch.equal(one.state[0], two.state[0])
