@@ -45,6 +45,7 @@ from .gen.distributions import (
     mv_normal_diag,
     normal,
     register_primitive,
+    student_t,
     uniform,
     weibull,
 )

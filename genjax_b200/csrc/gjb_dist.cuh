@@ -51,7 +51,7 @@ struct HalfNormal {
 
 // ------------------------------------------- long-tail scalar wrappers
 // tensorflow_probability/__init__.py:110 (cauchy), :179 (half_cauchy), :214 (laplace), :219 (log_normal), :174 (gumbel),
-// :309 (weibull), :204 (kumaraswamy), :224 (logit_normal), :169 (geometric), :194 (inverse_gamma), :120 (chi2).  Inverse-CDF samplers on one u01 word (u in [2^-25, 1)); log-densities in TFP 0.23's operation order
+// :309 (weibull), :204 (kumaraswamy), :224 (logit_normal), :169 (geometric), :194 (inverse_gamma), :120 (chi2), :279 (student_t).  Inverse-CDF samplers on one u01 word (u in [2^-25, 1)); log-densities in TFP 0.23's operation order
 // as restated in oracle/dists.py.
 constexpr float kPi = 3.14159265358979323846f;
 constexpr float kLogPi = 1.14472988584940017414f;
@@ -323,6 +323,19 @@ struct InverseGamma {  // (concentration a, scale b): b / Gamma(a, 1)
 struct Chi2 {  // (df): Gamma(df / 2, rate 1/2)
   __device__ static __forceinline__ float sample(const Lane& l, uint32_t site, float df) { return gamma_mt(l, site, 0.5f * df, 0) / 0.5f; }
   __device__ static __forceinline__ float logpdf(float v, float df) { return Gamma::logpdf(v, 0.5f * df, 0.5f); }
+};
+
+struct StudentT {  // (df, loc, scale): loc + scale * z * rsqrt(g / df), g ~ Gamma(df / 2, rate 1/2), z ~ N(0, 1) on chunk 128
+  __device__ static __forceinline__ float sample(const Lane& l, uint32_t site, float df, float loc, float scale) {
+    const float g = gamma_mt(l, site, 0.5f * df, 0) / 0.5f;
+    const uint4 w = l.words(site, 128u);
+    return loc + scale * (box_muller(w.x, w.y).x / sqrtf(g / df));
+  }
+  __device__ static __forceinline__ float logpdf(float v, float df, float loc, float scale) {
+    const float y = (v - loc) / scale;
+    const float norm = logf(fabsf(scale)) + 0.5f * logf(df) + 0.5f * kLogPi + lgammaf(0.5f * df) - lgammaf(0.5f * (df + 1.0f));
+    return -0.5f * (df + 1.0f) * log1pf(y * y / df) - norm;
+  }
 };
 
 struct Beta {

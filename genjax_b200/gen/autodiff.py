@@ -95,6 +95,12 @@ def logpdf_expr(dist, v: Expr, args: list) -> Expr:
         (df,) = args
         a = 0.5 * df
         return (a - 1.0) * E.unary("log", v) - 0.5 * v - (E.unary("lgamma", a) - a * E.const(math.log(0.5)))
+    if name == "student_t":
+        df, loc, scale = args
+        y = (v - loc) / scale
+        norm = (E.unary("log", E.unary("abs", scale)) + 0.5 * E.unary("log", df) + E.const(0.5 * math.log(math.pi))
+                + E.unary("lgamma", 0.5 * df) - E.unary("lgamma", 0.5 * (df + 1.0)))
+        return -0.5 * (df + 1.0) * E.unary("log1p", E.unary("square", y) / df) - norm
     if name == "exponential":
         (rate,) = args
         return E.where(v < 0.0, E.const(-math.inf), E.unary("log", rate) - rate * v)

@@ -215,6 +215,14 @@ class _Chi2(_LocScale):
     rng_kind = "lane"
 
 
+class _StudentT(_LocScale):
+    """tfd.StudentT(df, loc, scale) (tensorflow_probability/__init__.py:279)."""
+
+    name, cuda, n_args = "student_t", "StudentT", 3
+    kw_names = ("df", "loc", "scale")
+    rng_kind = "lane"
+
+
 class _Gamma(Distribution):
     name, cuda, n_args = "gamma", "Gamma", 2
     rng_kind = "lane"
@@ -421,6 +429,7 @@ logit_normal = _LogitNormal()
 geometric = _Geometric()
 inverse_gamma = _InverseGamma()
 chi2 = _Chi2()
+student_t = _StudentT()
 gamma = _Gamma()
 beta = _Beta()
 flip = _Flip()
@@ -433,7 +442,7 @@ mv_normal = _MvNormal()
 REGISTRY: dict[str, Distribution] = {
     d.name: d
     for d in (normal, uniform, exponential, half_normal, cauchy, half_cauchy, laplace, log_normal, gumbel, weibull, kumaraswamy, logit_normal, geometric,
-              inverse_gamma, chi2, gamma, beta, flip, bernoulli, categorical, mv_normal_diag, gmm_diag, mv_normal)
+              inverse_gamma, chi2, student_t, gamma, beta, flip, bernoulli, categorical, mv_normal_diag, gmm_diag, mv_normal)
 }
 
 

@@ -303,6 +303,16 @@ def chi2_logpdf(v, df):
     return gamma_logpdf(v, (F32(0.5) * _f(df)).astype(F32), F32(0.5))
 
 
+def student_t_logpdf(v, df, loc, scale):
+    """tfd.StudentT._log_prob: -0.5 (df + 1) log1p(y^2 / df) - (log|s| + 0.5 log df + 0.5 log pi + lgamma(df / 2)
+    - lgamma((df + 1) / 2)), y = (x - loc) / s (tensorflow_probability/__init__.py:279)."""
+    v, df, m, s = _f(v), _f(df), _f(loc), _f(scale)
+    y = ((v - m) / s).astype(F32)
+    norm = (_log(np.abs(s)) + F32(0.5) * _log(df) + F32(0.5) * F32(math.log(math.pi)) + _lgamma((F32(0.5) * df).astype(F32))
+            - _lgamma((F32(0.5) * (df + F32(1))).astype(F32))).astype(F32)
+    return (F32(-0.5) * (df + F32(1)) * _log1p((y * y / df).astype(F32)) - norm).astype(F32)
+
+
 # ---------------------------------------------------------------- samplers
 # sampler(words, idx, site, *args) -> values for the lanes in idx
 
@@ -472,6 +482,15 @@ def chi2_sample(words, idx, site, df):
     return (_gamma_mt(words, idx, site, (F32(0.5) * _f(df)).astype(F32), 0) / F32(0.5)).astype(F32)
 
 
+def student_t_sample(words, idx, site, df, loc, scale):
+    """loc + scale * z / sqrt(g / df): g ~ Gamma(df / 2, rate 1/2) on chunks [0, 64), z from chunk 128 of the lane."""
+    df = _f(df)
+    g = (_gamma_mt(words, idx, site, (F32(0.5) * df).astype(F32), 0) / F32(0.5)).astype(F32)
+    w = rng.site_words(words, idx, site, 128)
+    z = rng.box_muller(w[0], w[1])[0]
+    return (_f(loc) + _f(scale) * (z / np.sqrt((g / df).astype(F32)).astype(F32)).astype(F32)).astype(F32)
+
+
 def beta_sample(words, idx, site, a, b):
     """X = Ga / (Ga + Gb) with Ga ~ Gamma(a,1) on chunks [0,64), Gb on [64,128)."""
     ga = _gamma_mt(words, idx, site, a, 0)
@@ -503,4 +522,5 @@ DISTS = {
     "geometric": (geometric_sample, geometric_logpdf),
     "inverse_gamma": (inverse_gamma_sample, inverse_gamma_logpdf),
     "chi2": (chi2_sample, chi2_logpdf),
+    "student_t": (student_t_sample, student_t_logpdf),
 }

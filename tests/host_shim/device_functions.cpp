@@ -92,6 +92,13 @@ void h_inverse_gamma_chi2(uint32_t k0, uint32_t k1, uint64_t idx0, int n, uint32
     chi2_out[i] = gjb::Chi2::sample(l, site, 2.0f * a);
   }
 }
+void h_student_t(uint32_t k0, uint32_t k1, uint64_t idx0, int n, uint32_t site, float df, float loc, float scale, float* draw, float* logpdf_of_draw) {
+  for (int i = 0; i < n; ++i) {
+    const gjb::Lane l = gjb::make_lane(k0, k1, idx0 + (uint64_t)i);
+    draw[i] = gjb::StudentT::sample(l, site, df, loc, scale);
+    logpdf_of_draw[i] = gjb::StudentT::logpdf(draw[i], df, loc, scale);
+  }
+}
 void h_gamma_beta(uint32_t k0, uint32_t k1, uint64_t idx0, int n, uint32_t site, float a, float b, float* gamma_out, float* beta_out) {
   for (int i = 0; i < n; ++i) {
     const gjb::Lane l = gjb::make_lane(k0, k1, idx0 + (uint64_t)i);

@@ -151,3 +151,23 @@ def test_second_slice_logp_and_grad():
     cache = {}
     got = np.array([float(evaluate(gr, env(x), cache)) for gr in grads])
     np.testing.assert_allclose(got, _fd(lambda v: float(evaluate(logp, env(v))), x), rtol=1e-5, atol=1e-7)
+
+
+def test_student_t_logp_and_grad():
+    import genjax_b200 as gj
+
+    def model(s):
+        m = gj.normal(0.0, 2.0) @ "m"
+        t = gj.student_t(3.0 + s, m, s) @ "t"
+        return t
+
+    ir = cap.capture(model, "st", [ArgSpec("scalar", "f32", ())], ("tuple", [("leaf", 0)]))
+    logp = AD.model_logp(ir)
+    grads = AD.grad(logp, [s_.value for s_ in ir.sites])
+    s, x = 0.7, np.array([0.4, -1.3])
+    env = lambda x: {0: x[0], 1: x[1], ("arg", 0): s}  # noqa: E731
+    want = dists.normal_logpdf(x[0], 0.0, 2.0).astype(np.float64) + dists.student_t_logpdf(x[1], 3.0 + s, x[0], s)
+    assert float(evaluate(logp, env(x))) == pytest.approx(float(want), rel=2e-6)
+    cache = {}
+    got = np.array([float(evaluate(g, env(x), cache)) for g in grads])
+    np.testing.assert_allclose(got, _fd(lambda v: float(evaluate(logp, env(v))), x), rtol=1e-5, atol=1e-7)

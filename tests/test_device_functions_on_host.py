@@ -175,3 +175,7 @@ def test_distribution_log_densities_and_samplers(lib):
                                  C.c_float(bb), _p(ga), _p(be))
         assert np.mean(~np.isclose(ga, od.inverse_gamma_sample(words, idx, 3, F32(aa), F32(bb)), rtol=2e-5, atol=1e-6)) < 0.002
         assert np.mean(~np.isclose(be, od.chi2_sample(words, idx, 3, F32(2 * aa)), rtol=2e-5, atol=1e-6)) < 0.002
+        lib.h_student_t(C.c_uint32(words[0]), C.c_uint32(words[1]), C.c_uint64(77), C.c_int(n), C.c_uint32(3), C.c_float(2 * aa),
+                        C.c_float(0.5), C.c_float(bb), _p(ga), _p(be))
+        assert np.mean(~np.isclose(ga, od.student_t_sample(words, idx, 3, F32(2 * aa), F32(0.5), F32(bb)), rtol=5e-5, atol=5e-6)) < 0.002
+        np.testing.assert_allclose(be, od.student_t_logpdf(ga, F32(2 * aa), F32(0.5), F32(bb)), rtol=3e-6, atol=3e-6)

@@ -98,6 +98,8 @@ def test_second_slice_logpdfs_match_scipy():
     _close(dists.geometric_logpdf(k, unit), stats.geom.logpmf(f(k) + 1, f(unit)), rtol=1e-5, atol=1e-5)  # scipy counts trials
     _close(dists.inverse_gamma_logpdf(pos, a, b), stats.invgamma.logpdf(f(pos), f(a), scale=f(b)), rtol=1e-5, atol=1e-5)
     _close(dists.chi2_logpdf(pos, 2 * a), stats.chi2.logpdf(f(pos), f(2 * a)), rtol=1e-5, atol=1e-5)
+    tv = (3 * RNG.standard_normal(n)).astype(np.float32)
+    _close(dists.student_t_logpdf(tv, 2 * a, loc, b), stats.t.logpdf(f(tv), f(2 * a), f(loc), f(b)), rtol=1e-5, atol=1e-5)
     for fn, v, args in ((dists.kumaraswamy_logpdf, 1.5, (2.0, 2.0)), (dists.logit_normal_logpdf, 1.0, (0.0, 1.0)),
                         (dists.geometric_logpdf, -1.0, (0.3,)), (dists.inverse_gamma_logpdf, 0.0, (2.0, 1.0))):
         assert fn(np.float32(v), *args) == -np.inf
@@ -140,6 +142,8 @@ def test_categorical_and_mvn_logpdf():
         ("inverse_gamma", (3.0, 2.0), lambda x: stats.invgamma.cdf(x, 3.0, scale=2.0)),
         ("chi2", (3.5,), lambda x: stats.chi2.cdf(x, 3.5)),
         ("chi2", (0.8,), lambda x: stats.chi2.cdf(x, 0.8)),
+        ("student_t", (4.0, 1.0, 2.0), lambda x: stats.t.cdf(x, 4.0, 1.0, 2.0)),
+        ("student_t", (0.9, 0.0, 1.0), lambda x: stats.t.cdf(x, 0.9)),
     ],
 )
 def test_continuous_samplers_ks(name, args, cdf):
