@@ -23,6 +23,8 @@ ap.add_argument("--particles", type=int, default=1 << 20)
 ap.add_argument("--T", type=int, default=8)
 ap.add_argument("--graph", action="store_true")
 ap.add_argument("--mode", default="persistent")
+ap.add_argument("--reference-max", default="running")
+ap.add_argument("--single-pass", action="store_true")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 n, d, T = a.particles, a.dim, a.T
@@ -33,7 +35,7 @@ if d == 1:
     model, shared = lgssm_step, ()
 else:
     model, shared = lgssm_step_vec, (torch.full((d,), LG_Q, device=dev), torch.full((d,), LG_R, device=dev))
-pf = ParticleFilter(model, n, mode=a.mode)
+pf = ParticleFilter(model, n, mode=a.mode, reference_max=a.reference_max, single_pass=a.single_pass)
 res = pf.run(gj.key(1), x0, gj.C["y"].set(torch.from_numpy(ys).to(dev)), shared_args=shared, use_graph=a.graph)
 torch.cuda.synchronize()
 print("logZ", res.log_marginal_likelihood.item())
