@@ -44,6 +44,7 @@ from .gen.distributions import (
     mv_normal,
     mv_normal_diag,
     normal,
+    poisson,
     register_primitive,
     student_t,
     uniform,

@@ -51,7 +51,7 @@ struct HalfNormal {
 
 // ------------------------------------------- long-tail scalar wrappers
 // tensorflow_probability/__init__.py:110 (cauchy), :179 (half_cauchy), :214 (laplace), :219 (log_normal), :174 (gumbel),
-// :309 (weibull), :204 (kumaraswamy), :224 (logit_normal), :169 (geometric), :194 (inverse_gamma), :120 (chi2), :279 (student_t).  Inverse-CDF samplers on one u01 word (u in [2^-25, 1)); log-densities in TFP 0.23's operation order
+// :309 (weibull), :204 (kumaraswamy), :224 (logit_normal), :169 (geometric), :194 (inverse_gamma), :120 (chi2), :279 (student_t), :264 (poisson).  Inverse-CDF samplers on one u01 word (u in [2^-25, 1)); log-densities in TFP 0.23's operation order
 // as restated in oracle/dists.py.
 constexpr float kPi = 3.14159265358979323846f;
 constexpr float kLogPi = 1.14472988584940017414f;
@@ -335,6 +335,40 @@ struct StudentT {  // (df, loc, scale): loc + scale * z * rsqrt(g / df), g ~ Gam
     const float y = (v - loc) / scale;
     const float norm = logf(fabsf(scale)) + 0.5f * logf(df) + 0.5f * kLogPi + lgammaf(0.5f * df) - lgammaf(0.5f * (df + 1.0f));
     return -0.5f * (df + 1.0f) * log1pf(y * y / df) - norm;
+  }
+};
+
+struct Poisson {  // tfd.Poisson(rate): a float-valued count as in TFP
+  // rate < 10: inversion by sequential search on one uniform (chunk 0, word x).  Otherwise PTRS (Hormann 1993,
+  // transformed rejection with squeeze): attempt t draws (U, V) from words (x, y) of chunk t.
+  __device__ static __forceinline__ float sample(const Lane& l, uint32_t site, float rate) {
+    if (rate < 10.0f) {
+      const float u = u01(l.words(site, 0u).x);
+      float p = expf(-rate), s = p, k = 0.0f;
+      while (u > s && k < 128.0f) {
+        k += 1.0f;
+        p *= rate / k;
+        s += p;
+      }
+      return k;
+    }
+    const float b = 0.931f + 2.53f * sqrtf(rate), a = -0.059f + 0.02483f * b;
+    const float lia = logf(1.1239f + 1.1328f / (b - 3.4f)), vr = 0.9277f - 3.6224f / (b - 2.0f), llam = logf(rate);
+    float k = 0.0f;
+    for (uint32_t t = 0; t < 64u; ++t) {
+      const uint4 w = l.words(site, t);
+      const float U = u01(w.x) - 0.5f, V = u01(w.y);
+      const float us = 0.5f - fabsf(U);
+      k = floorf((2.0f * a / us + b) * U + rate + 0.43f);
+      if (us >= 0.07f && V <= vr) break;
+      if (k < 0.0f || (us < 0.013f && V > us)) continue;
+      if (logf(V) + lia - logf(a / (us * us) + b) <= -rate + k * llam - lgammaf(k + 1.0f)) break;
+    }
+    return fmaxf(k, 0.0f);
+  }
+  __device__ static __forceinline__ float logpdf(float v, float rate) {
+    const float t = (v == 0.0f) ? 0.0f : v * logf(rate);
+    return v < 0.0f ? -INFINITY : t - lgammaf(v + 1.0f) - rate;
   }
 };
 

@@ -101,6 +101,9 @@ def logpdf_expr(dist, v: Expr, args: list) -> Expr:
         norm = (E.unary("log", E.unary("abs", scale)) + 0.5 * E.unary("log", df) + E.const(0.5 * math.log(math.pi))
                 + E.unary("lgamma", 0.5 * df) - E.unary("lgamma", 0.5 * (df + 1.0)))
         return -0.5 * (df + 1.0) * E.unary("log1p", E.unary("square", y) / df) - norm
+    if name == "poisson":
+        (rate,) = args
+        return E.where(v < 0.0, E.const(-math.inf), v * E.unary("log", rate) - E.unary("lgamma", v + 1.0) - rate)
     if name == "exponential":
         (rate,) = args
         return E.where(v < 0.0, E.const(-math.inf), E.unary("log", rate) - rate * v)

@@ -223,6 +223,14 @@ class _StudentT(_LocScale):
     rng_kind = "lane"
 
 
+class _Poisson(_LocScale):
+    """tfd.Poisson(rate) (tensorflow_probability/__init__.py:264): float-valued count."""
+
+    name, cuda, n_args = "poisson", "Poisson", 1
+    kw_names = ("rate",)
+    rng_kind = "lane"
+
+
 class _Gamma(Distribution):
     name, cuda, n_args = "gamma", "Gamma", 2
     rng_kind = "lane"
@@ -430,6 +438,7 @@ geometric = _Geometric()
 inverse_gamma = _InverseGamma()
 chi2 = _Chi2()
 student_t = _StudentT()
+poisson = _Poisson()
 gamma = _Gamma()
 beta = _Beta()
 flip = _Flip()
@@ -442,7 +451,7 @@ mv_normal = _MvNormal()
 REGISTRY: dict[str, Distribution] = {
     d.name: d
     for d in (normal, uniform, exponential, half_normal, cauchy, half_cauchy, laplace, log_normal, gumbel, weibull, kumaraswamy, logit_normal, geometric,
-              inverse_gamma, chi2, student_t, gamma, beta, flip, bernoulli, categorical, mv_normal_diag, gmm_diag, mv_normal)
+              inverse_gamma, chi2, student_t, poisson, gamma, beta, flip, bernoulli, categorical, mv_normal_diag, gmm_diag, mv_normal)
 }
 
 

@@ -313,6 +313,15 @@ def student_t_logpdf(v, df, loc, scale):
     return (F32(-0.5) * (df + F32(1)) * _log1p((y * y / df).astype(F32)) - norm).astype(F32)
 
 
+def poisson_logpdf(v, rate):
+    """tfd.Poisson._log_prob: xlogy(x, rate) - lgamma(x + 1) - rate, x >= 0 (tensorflow_probability/__init__.py:264)."""
+    v, r = _f(v), _f(rate)
+    t = np.where(v == 0, F32(0), v * _log(r)).astype(F32)
+    with np.errstate(invalid="ignore"):
+        lp = (t - _lgamma((v + F32(1)).astype(F32)) - r).astype(F32)
+    return np.where(v < 0, F32(-np.inf), lp).astype(F32)
+
+
 # ---------------------------------------------------------------- samplers
 # sampler(words, idx, site, *args) -> values for the lanes in idx
 
@@ -491,6 +500,59 @@ def student_t_sample(words, idx, site, df, loc, scale):
     return (_f(loc) + _f(scale) * (z / np.sqrt((g / df).astype(F32)).astype(F32)).astype(F32)).astype(F32)
 
 
+def poisson_sample(words, idx, site, rate):
+    """rate < 10: inversion by sequential search on one uniform (chunk 0, word 0).  Otherwise PTRS (Hormann 1993):
+    attempt t draws (U, V) from words (0, 1) of chunk t; float32 operation order of gjb_dist.cuh: Poisson."""
+    idx = np.asarray(idx, dtype=np.uint64)
+    n = idx.shape[0]
+    r = np.broadcast_to(_f(rate), (n,)).astype(F32)
+    out = np.zeros(n, dtype=F32)
+    small = r < F32(10)
+    if small.any():
+        rs = r[small]
+        u = rng.u01(rng.site_words(words, idx[small], site, 0)[0])
+        p = _exp(-rs)
+        s = p.copy()
+        k = np.zeros(rs.shape, dtype=F32)
+        for _ in range(128):
+            go = (u > s) & (k < F32(128))
+            if not go.any():
+                break
+            k = np.where(go, k + F32(1), k).astype(F32)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                p = np.where(go, (p * (rs / k).astype(F32)).astype(F32), p)
+            s = np.where(go, (s + p).astype(F32), s)
+        out[small] = k
+    big = ~small
+    if big.any():
+        rb, ib = r[big], idx[big]
+        b = (F32(0.931) + F32(2.53) * np.sqrt(rb)).astype(F32)
+        a = (F32(-0.059) + F32(0.02483) * b).astype(F32)
+        lia = _log((F32(1.1239) + F32(1.1328) / (b - F32(3.4))).astype(F32))
+        vr = (F32(0.9277) - F32(3.6224) / (b - F32(2))).astype(F32)
+        llam = _log(rb)
+        k = np.zeros(rb.shape, dtype=F32)
+        done = np.zeros(rb.shape, dtype=bool)
+        for t in range(64):
+            if done.all():
+                break
+            w = rng.site_words(words, ib, site, t)
+            U = (rng.u01(w[0]) - F32(0.5)).astype(F32)
+            V = rng.u01(w[1])
+            us = (F32(0.5) - np.abs(U)).astype(F32)
+            kt = np.floor(((F32(2) * a / us + b) * U + rb + F32(0.43)).astype(F32)).astype(F32)
+            k = np.where(done, k, kt)
+            acc1 = (us >= F32(0.07)) & (V <= vr)
+            rej = (kt < 0) | ((us < F32(0.013)) & (V > us))
+            with np.errstate(invalid="ignore"):
+                lhs = (_log(V) + lia - _log((a / (us * us).astype(F32) + b).astype(F32))).astype(F32)
+                rhs = (-rb + kt * llam - _lgamma((kt + F32(1)).astype(F32))).astype(F32)
+            acc2 = ~rej & (lhs <= rhs)
+            done |= ~done & (acc1 | acc2)
+        out[big] = np.maximum(k, F32(0))
+    return out
+
+
 def beta_sample(words, idx, site, a, b):
     """X = Ga / (Ga + Gb) with Ga ~ Gamma(a,1) on chunks [0,64), Gb on [64,128)."""
     ga = _gamma_mt(words, idx, site, a, 0)
@@ -523,4 +585,5 @@ DISTS = {
     "inverse_gamma": (inverse_gamma_sample, inverse_gamma_logpdf),
     "chi2": (chi2_sample, chi2_logpdf),
     "student_t": (student_t_sample, student_t_logpdf),
+    "poisson": (poisson_sample, poisson_logpdf),
 }

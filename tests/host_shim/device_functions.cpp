@@ -99,6 +99,13 @@ void h_student_t(uint32_t k0, uint32_t k1, uint64_t idx0, int n, uint32_t site, 
     logpdf_of_draw[i] = gjb::StudentT::logpdf(draw[i], df, loc, scale);
   }
 }
+void h_poisson(uint32_t k0, uint32_t k1, uint64_t idx0, int n, uint32_t site, const float* rate, float* draw, float* logpdf_of_draw) {
+  for (int i = 0; i < n; ++i) {
+    const gjb::Lane l = gjb::make_lane(k0, k1, idx0 + (uint64_t)i);
+    draw[i] = gjb::Poisson::sample(l, site, rate[i]);
+    logpdf_of_draw[i] = gjb::Poisson::logpdf(draw[i], rate[i]);
+  }
+}
 void h_gamma_beta(uint32_t k0, uint32_t k1, uint64_t idx0, int n, uint32_t site, float a, float b, float* gamma_out, float* beta_out) {
   for (int i = 0; i < n; ++i) {
     const gjb::Lane l = gjb::make_lane(k0, k1, idx0 + (uint64_t)i);

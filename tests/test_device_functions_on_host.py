@@ -164,6 +164,11 @@ def test_distribution_log_densities_and_samplers(lib):
     np.testing.assert_allclose(freq, np.exp(logits) / np.exp(logits).sum(), atol=0.03)
     words, idx = (0x12345678, 0x9ABCDEF0), np.arange(n, dtype=np.uint64) + np.uint64(77)
     ga, be = np.zeros(n, dtype=F32), np.zeros(n, dtype=F32)
+    rates = np.ascontiguousarray(np.where(np.arange(n) % 3 == 0, 0.2 + pos, 10 + 30 * pos), dtype=F32)  # both sampler branches
+    lib.h_poisson(C.c_uint32(words[0]), C.c_uint32(words[1]), C.c_uint64(77), C.c_int(n), C.c_uint32(4), _p(rates), _p(ga), _p(be))
+    want_k = od.poisson_sample(words, idx, 4, rates)
+    assert np.mean(ga != want_k) < 0.002  # an ulp of expf / logf can move a draw sitting on an acceptance boundary
+    np.testing.assert_allclose(be, od.poisson_logpdf(ga, rates), rtol=1e-5, atol=2e-4)  # k log(rate) - lgamma(k + 1): terms near 600, one ulp is 6e-5
     for aa, bb in ((2.5, 1.5), (0.4, 2.0)):
         lib.h_gamma_beta(C.c_uint32(words[0]), C.c_uint32(words[1]), C.c_uint64(77), C.c_int(n), C.c_uint32(3), C.c_float(aa),
                          C.c_float(bb), _p(ga), _p(be))

@@ -108,6 +108,26 @@ def test_second_slice_logpdfs_match_scipy():
     np.testing.assert_allclose(np.bincount(x.astype(int))[:4] / x.size, 0.3 * 0.7 ** np.arange(4), atol=5e-3)
 
 
+@pytest.mark.parametrize("rate", [0.3, 4.0, 9.9, 10.0, 37.5, 400.0])
+def test_poisson_sampler_and_logpmf(rate):
+    """tfd.Poisson (tensorflow_probability/__init__.py:264): inversion below rate 10, PTRS above; chi-square of the
+    draws against the exact pmf, log-pmf against scipy."""
+    n = 100_000
+    x = dists.poisson_sample((11, 22), np.arange(n, dtype=np.uint64), 2, np.float32(rate))
+    assert x.dtype == np.float32 and (x == np.floor(x)).all() and x.min() >= 0
+    m = int(x.max()) + 1
+    obs = np.bincount(x.astype(int), minlength=m)
+    exp = stats.poisson.pmf(np.arange(m), rate) * n
+    keep = exp > 5
+    chi = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum()
+    assert stats.chi2.sf(chi, keep.sum() - 1) > 1e-3
+    k = RNG.integers(0, int(3 * rate) + 5, 500).astype(np.float32)
+    # float32 cancellation of k log(rate) - lgamma(k + 1) (TFP's own formula): a few ulps of the larger term
+    _close(dists.poisson_logpdf(k, rate), stats.poisson.logpmf(k.astype(np.float64), rate), rtol=2e-5,
+           atol=2e-5 + 2e-6 * rate * max(1.0, math.log(rate)))
+    assert dists.poisson_logpdf(np.float32(-1.0), rate) == -np.inf
+
+
 def test_categorical_and_mvn_logpdf():
     logits = RNG.standard_normal((50, 16)).astype(np.float32) * 2
     k = RNG.integers(0, 16, 50)

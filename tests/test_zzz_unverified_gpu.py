@@ -352,7 +352,7 @@ def test_single_pass_filter_equals_the_two_launch_filter(device, n):
 _LONG_TAIL = [("cauchy", (1.0, 2.0)), ("half_cauchy", (1.0, 2.0)), ("laplace", (-1.0, 0.5)), ("log_normal", (0.3, 0.8)),
               ("gumbel", (0.5, 1.5)), ("weibull", (1.7, 2.0)), ("kumaraswamy", (2.0, 3.0)), ("logit_normal", (0.3, 0.8)),
               ("geometric", (0.3,)), ("inverse_gamma", (3.0, 2.0)), ("chi2", (3.5,)), ("chi2", (0.8,)),
-              ("student_t", (4.0, 1.0, 2.0))]
+              ("student_t", (4.0, 1.0, 2.0)), ("poisson", (3.5,)), ("poisson", (42.0,))]
 
 
 @pytest.mark.parametrize("name,args", _LONG_TAIL)
@@ -368,8 +368,9 @@ def test_long_tail_primitive_sample_and_logpdf_match_oracle(device, name, args):
     ov = od.DISTS[name][0](words, idx, 1, *[F32(a) for a in args])
     # tanf / expf of the device against a rounded float64 evaluation; the Cauchy tails amplify an ulp of the argument, an
     # ulp can flip a rejection of the gamma samplers or move a geometric draw across an integer
-    assert (~np.isclose(v, ov, rtol=1e-4, atol=1e-5)).mean() < (2e-3 if name in ("inverse_gamma", "chi2", "geometric", "student_t") else 1e-4), name
-    np.testing.assert_allclose(tr.get_score().cpu().numpy(), od.DISTS[name][1](v, *[F32(a) for a in args]), rtol=2e-5, atol=2e-5)
+    assert (~np.isclose(v, ov, rtol=1e-4, atol=1e-5)).mean() < (2e-3 if name in ("inverse_gamma", "chi2", "geometric", "student_t", "poisson") else 1e-4), name
+    np.testing.assert_allclose(tr.get_score().cpu().numpy(), od.DISTS[name][1](v, *[F32(a) for a in args]), rtol=2e-5,
+                               atol=2e-4 if name == "poisson" else 2e-5)  # k log(rate) - lgamma(k + 1) cancels in float32
     kw = dict(zip(getattr(gj, name).kw_names, args))  # TFP's keyword spelling
     tr2 = getattr(gj, name).simulate(gj.split(gj.key(11), 64), ((), kw))
     assert torch.equal(tr2.get_retval(), tr.get_retval()[:64])
@@ -422,16 +423,19 @@ def test_second_slice_sites_inside_a_model(device):
         g = gj.inverse_gamma(2.0 + k, s) @ "g"
         c = gj.chi2(1.0 + a) @ "c"
         t = gj.student_t(2.0 + c, a, s) @ "t"
-        return g + c + t
+        p = gj.poisson(0.5 + 20.0 * b) @ "p"  # rates on both sides of the inversion / PTRS switch
+        return g + c + t + p
 
     n, s = 4096, 1.5
     tr = model.simulate(gj.split(gj.key(6), n), (s,))
-    ch = {k: tr.get_choices()[k].cpu().numpy() for k in "abkgct"}
+    ch = {k: tr.get_choices()[k].cpu().numpy() for k in "abkgctp"}
     assert ((ch["a"] > 0) & (ch["a"] < 1)).all() and ((ch["b"] > 0) & (ch["b"] < 1)).all()
     assert (ch["k"] >= 0).all() and (ch["k"] == np.floor(ch["k"])).all() and (ch["g"] > 0).all() and (ch["c"] > 0).all()
     want = (od.kumaraswamy_logpdf(ch["a"], F32(2), F32(s)) + od.logit_normal_logpdf(ch["b"], ch["a"], F32(0.5))
             + od.geometric_logpdf(ch["k"], F32(0.1) + F32(0.8) * ch["b"]) + od.inverse_gamma_logpdf(ch["g"], F32(2) + ch["k"], F32(s))
-            + od.chi2_logpdf(ch["c"], F32(1) + ch["a"]) + od.student_t_logpdf(ch["t"], F32(2) + ch["c"], ch["a"], F32(s)))
+            + od.chi2_logpdf(ch["c"], F32(1) + ch["a"]) + od.student_t_logpdf(ch["t"], F32(2) + ch["c"], ch["a"], F32(s))
+            + od.poisson_logpdf(ch["p"], F32(0.5) + F32(20) * ch["b"]))
+    assert (ch["p"] >= 0).all() and (ch["p"] == np.floor(ch["p"])).all()
     assert np.isfinite(want).all()
     np.testing.assert_allclose(tr.get_score().cpu().numpy(), want, rtol=1e-4, atol=1e-4)
     obs = gj.C["g"].set(0.9).at["c"].set(2.5)
