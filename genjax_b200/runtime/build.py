@@ -32,6 +32,7 @@ NVCC_FLAGS = [
 ]
 
 _lock = threading.Lock()
+_model_locks: dict[str, threading.Lock] = {}
 
 
 class BuildError(RuntimeError):
@@ -85,6 +86,8 @@ def build_model(source: str, force: bool = False) -> Path:
     digest = model_digest(source)
     out = LIB / f"model_{digest}.so"
     with _lock:
+        lock = _model_locks.setdefault(digest, threading.Lock())
+    with lock:  # per model: distinct models compile concurrently
         if out.exists() and not force:
             return out
         LIB.mkdir(exist_ok=True)

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import json
+import os
 
 import numpy as np
 import torch
@@ -755,10 +756,45 @@ class SimtCore(EmulatedCore):
                                     C.c_int(max(1, min(4, (n_out * (row_bytes // 4) + 255) // 256))))
 
 
+class _PrebuildPool:
+    """Background nvcc jobs of the prebuild pass (joined at interpreter exit)."""
+
+    def __init__(self):
+        self._ex = None
+        self._futs = []
+
+    def submit(self, fn, *a):
+        import atexit
+        from concurrent.futures import ThreadPoolExecutor
+
+        if self._ex is None:
+            self._ex = ThreadPoolExecutor(max_workers=int(os.environ.get("GJB_PREBUILD_JOBS", "4")))
+            atexit.register(self.join)
+        self._futs.append(self._ex.submit(fn, *a))
+
+    def join(self):
+        for f in self._futs:
+            try:
+                f.result()
+            except Exception as e:  # a model that does not compile must fail the GPU test, not the prebuild pass
+                print(f"[prebuild] {type(e).__name__}: {str(e)[-400:]}")
+        self._futs.clear()
+
+
+_PREBUILD_POOL = _PrebuildPool()
+
+
 class _EmulatedCompiledModel:
     def __init__(self, ir, chain=None, pf_obs=None, host_kernels=False):
         self.ir = ir
         self.lib = None
+        if os.environ.get("GJB_PREBUILD") == "1":
+            # scripts/prebuild_test_models.py: also cross-compile the sm_100a library of every model the GPU tests
+            # will ask for, so the GPU box loads genjax_b200/_lib/model_*.so instead of spending its minutes in nvcc
+            from genjax_b200.gen import codegen as _cg
+            from genjax_b200.runtime import build as _gb
+
+            _PREBUILD_POOL.submit(_gb.build_model, _cg.generate(ir, pf_obs, chain))
         if host_kernels:
             import host_kernels as hk
             from genjax_b200.gen import codegen
