@@ -348,11 +348,12 @@ class GenerativeFunction:
         tr = self.simulate(key, args)
         return tr.get_choices(), tr.get_score(), tr.get_retval()
 
-    def marginal(self, *, selection: Selection | None = None, algorithm=None):
-        """``gen_fn.marginal(selection=..., algorithm=...)`` (generative_function.py ``marginal``; sp.py:208-273)."""
+    def marginal(self, *, selection: Selection | None = None, algorithm=None, reference_compat: bool = True):
+        """``gen_fn.marginal(selection=..., algorithm=...)`` (generative_function.py ``marginal``; sp.py:208-273).
+        ``reference_compat=False`` opts into the corrected ``random_weighted`` weight (see ``Marginal``)."""
         from ..inference.sp import Marginal
 
-        return Marginal(self, Selection.all() if selection is None else selection, algorithm)
+        return Marginal(self, Selection.all() if selection is None else selection, algorithm, reference_compat)
 
     def partial_apply(self, *bound):
         """``gen_fn.partial_apply(*args)`` (generative_function.py ``partial_apply``): the same generative function

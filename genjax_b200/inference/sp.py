@@ -67,18 +67,20 @@ class Marginal(SampleDistribution):
     """The marginal of a generative function over a selection of addresses (sp.py:208-252).
 
     ``random_weighted(key, *args)``: simulate, keep the selected choices, weight = projection of the trace on
-    the selection (see ``reference_compat`` for the reference's literal behaviour).  ``estimate_logpdf(key, v, *args)``: importance weight of
-    ``v``.  With an ``algorithm`` the unselected choices are marginalised by (conditional) SMC -- available
+    the COMPLEMENT of the selection, exactly as sp.py:227-228 (``reference_compat=False`` opts into the
+    projection on the selection itself).  ``estimate_logpdf(key, v, *args)``: importance weight of ``v``.  With an ``algorithm`` the unselected choices are marginalised by (conditional) SMC -- available
     for scalar keys (the nested particle batch is not flattened into the outer one)."""
 
     def __init__(self, gen_fn: GenerativeFunction, selection: Selection | None = None, algorithm=None,
-                 reference_compat: bool = False):
-        """``reference_compat=True`` reproduces sp.py:227-228 literally: the weight is the projection of the
-        trace on the COMPLEMENT of the selection.  That is 0 for a full selection, so a proposal wrapped as
-        ``q = proposal.marginal()`` would contribute no density to ``ImportanceK``'s ``target_scores -
-        log_weights`` (smc.py:301-315).  The default projects on the selection itself -- the same quantity
-        ``estimate_logpdf`` (sp.py:244-246) assigns to those choices -- which makes the p / q weights of a
-        custom proposal correct (verified against the closed-form evidence in tests/test_gfi_gpu.py)."""
+                 reference_compat: bool = True):
+        """``reference_compat=True`` (default) is sp.py:227-228 to the letter: the weight is the projection of the
+        trace on the COMPLEMENT of the selection, also when it is handed on to
+        ``algorithm.estimate_reciprocal_normalizing_constant`` (sp.py:232-236).  That is 0 for a full selection,
+        so a proposal wrapped as ``q = proposal.marginal()`` contributes no density to ``ImportanceK``'s
+        ``target_scores - log_weights`` (smc.py:301-315) -- the reference's behaviour, reproduced here.
+        ``reference_compat=False`` is the opt-in corrected estimator: it projects on the selection itself -- the
+        quantity ``estimate_logpdf`` (sp.py:244-246) assigns to those choices -- which makes the p / q weights
+        of a custom proposal the importance weights (closed-form check in tests/test_gfi_gpu.py)."""
         self.gen_fn = gen_fn
         self.selection = Selection.all() if selection is None else selection
         self.algorithm = algorithm
@@ -117,10 +119,10 @@ class Marginal(SampleDistribution):
         return _SampleTrace(self, args, chm, w)
 
 
-def marginal(selection: Selection | None = None, algorithm=None):
+def marginal(selection: Selection | None = None, algorithm=None, reference_compat: bool = True):
     """``@marginal(selection, algorithm)`` decorator (sp.py:260-273)."""
 
     def decorator(gen_fn: GenerativeFunction) -> Marginal:
-        return Marginal(gen_fn, selection, algorithm)
+        return Marginal(gen_fn, selection, algorithm, reference_compat)
 
     return decorator

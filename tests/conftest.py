@@ -13,20 +13,9 @@ if HERE not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line(
-        "markers",
-        "unverified: GPU test of host-side code written after the round's GPU budget was spent; it has never run "
-        "on a device, so it is skipped unless GJB_RUN_UNVERIFIED=1 (first GPU call of the next round)",
-    )
-
-
-def pytest_collection_modifyitems(config, items):
-    if os.environ.get("GJB_RUN_UNVERIFIED") == "1":
-        return
-    skip = pytest.mark.skip(reason="never run on a GPU yet; set GJB_RUN_UNVERIFIED=1 (see DESIGN.md section 9)")
-    for item in items:
-        if "unverified" in item.keywords:
-            item.add_marker(skip)
+    # `unverified` used to auto-skip tests that had never run on a device; every one of them ran green on a B200 in
+    # round 2 (profiles/r2_call1_gpu_tests.log), so the marker is now informational only
+    config.addinivalue_line("markers", "unverified: written in round 1 after the GPU budget was spent; first device run in round 2 (green)")
 
 
 @pytest.fixture(scope="session")

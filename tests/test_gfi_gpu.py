@@ -279,7 +279,14 @@ def test_custom_proposal_marginal_and_conditional_smc(device):
     target = gj.Target(model, (), gj.C["y"].set(yv))
     exact_logz = float(od.normal_logpdf(F32(yv), F32(0.0), F32(math.sqrt(2.0))))
     k = 512
-    alg = ImportanceK(target, q=proposal.marginal(), k_particles=k)
+    # the reference's own weight (sp.py:227-228: projection on the complement of the selection, 0 for a full
+    # selection) is the default: ImportanceK's weights are then the joint score of each particle (smc.py:301-315)
+    pc_ref = ImportanceK(target, q=proposal.marginal(), k_particles=k).run_smc(gj.key(1))
+    x_ref = pc_ref.get_particles().get_choices()["x"]
+    joint = gj.normal.logpdf(x_ref, 0.0, 1.0) + gj.normal.logpdf(torch.full_like(x_ref, yv), x_ref, 1.0)
+    torch.testing.assert_close(pc_ref.get_log_weights(), joint, rtol=1e-5, atol=2e-5)
+    # the corrected estimator is the opt-in: q's own density enters the weights
+    alg = ImportanceK(target, q=proposal.marginal(reference_compat=False), k_particles=k)
     pc = alg.run_smc(gj.key(1))
     lw = pc.get_log_weights().cpu().numpy()
     assert lw.shape == (k,)
@@ -302,7 +309,7 @@ def test_custom_proposal_marginal_and_conditional_smc(device):
     # (importance with x AND y constrained: both sites are weighted, smc.py:340-342)
     assert pc3.get_log_weights()[-1].item() == pytest.approx(
         float(od.normal_logpdf(F32(0.4), F32(0.0), F32(1.0)) + od.normal_logpdf(F32(yv), F32(0.4), F32(1.0))), abs=1e-5)
-    one = Importance(target, q=proposal.marginal()).run_csmc(gj.key(6), retained)
+    one = Importance(target, q=proposal.marginal(reference_compat=False)).run_csmc(gj.key(6), retained)
     assert one.get_log_weights()[0].item() == pytest.approx(exact_logz, abs=2e-5)
     # ChangeTarget on top of conditional SMC keeps the retained particle and reweights everyone
     t2 = gj.Target(model, (), gj.C["y"].set(2.0))
@@ -335,15 +342,16 @@ def test_marginal_of_a_generative_function(device):
 
     n = 4096
     m = model.marginal(selection=gj.S["y"])
+    assert m.reference_compat  # the reference's weight is the default
     kb = gj.split(gj.key(1), n)
-    w, chm = m.random_weighted(kb)
-    assert "y" in chm and "x" not in chm and w.shape == (n,)
-    # the weight is the density of the kept choice y given the simulated x: a Normal(x, 0.5) log-density, so it
-    # is bounded above by -log(0.5) - 0.5 log(2 pi); the reference-compatible form projects on the complement
-    # (the prior density of the discarded x) instead
-    assert (w <= -math.log(0.5) - 0.5 * math.log(2 * math.pi) + 1e-5).all()
-    wc, _ = model.marginal(selection=gj.S["y"]).__class__(model, gj.S["y"], reference_compat=True).random_weighted(kb)
-    assert (wc <= -math.log(2.0) - 0.5 * math.log(2 * math.pi) + 1e-5).all() and not torch.equal(wc, w)
+    wc, chm = m.random_weighted(kb)
+    assert "y" in chm and "x" not in chm and wc.shape == (n,)
+    # sp.py:227-228: the weight is the projection on the COMPLEMENT of the selection, the prior density of the
+    # discarded x: a Normal(0, 2) log-density, bounded above by -log(2) - 0.5 log(2 pi).  The opt-in corrected form
+    # weights by the density of the kept choice y given the simulated x, a Normal(x, 0.5) log-density
+    assert (wc <= -math.log(2.0) - 0.5 * math.log(2 * math.pi) + 1e-5).all()
+    w, _ = model.marginal(selection=gj.S["y"], reference_compat=False).random_weighted(kb)
+    assert (w <= -math.log(0.5) - 0.5 * math.log(2 * math.pi) + 1e-5).all() and not torch.equal(wc, w)
     yv = chm["y"]
     est = m.estimate_logpdf(gj.split(gj.key(2), n), gj.vmap(lambda v: gj.C["y"].set(v), in_axes=0)(yv))
     assert est.shape == (n,) and torch.isfinite(est).all()
