@@ -62,8 +62,10 @@ def parse():
     ap.add_argument("--single-pass", action="store_true",
                     help="with --reference-max analytic: ONE launch per step (output-slot resampling of the previous step fused "
                          "into the model kernel, model_kernel_static_pull; DESIGN.md section 10 -- not yet measured on a device)")
-    ap.add_argument("--mode", default="graph", choices=["persistent", "graph"],
-                    help="persistent: one cooperative launch per filter; graph: 2 launches per step in a CUDA graph")
+    ap.add_argument("--mode", default="graph", choices=["persistent", "graph", "step"],
+                    help="step: ONE launch per filter step (pf_step_kernel: output-slot resampling of the previous step + gather + "
+                         "propose + logpdf + tile-exponent masses), captured in a CUDA graph; graph: round 1's 2 launches per step; "
+                         "persistent: one cooperative launch per filter")
     return ap.parse_args()
 
 
@@ -503,7 +505,24 @@ def run_ours(args):
     kernels = {"model_kernel": {"kernel_us": model_ms * 1e3, "algorithmic_bytes_per_launch": model_bytes,
                                 "achieved": model_gbs, "frac": model_gbs / peak,
                                 "what": "fused ancestor-gather + propose + logpdf + running max (gjb_model_launch)"}}
-    if getattr(plan, "persistent", False):
+    if getattr(plan, "stepmode", False):
+        # the step IS one kernel: launch t = 1 (reads step 0's CDF / tile records, writes its own) is what every later
+        # step repeats; re-launching it is idempotent
+        plan.cm.lib.gjb_model_pf_step(C.byref(plan.sargs[0]), stream)
+        st_ms = time_launches(lambda: plan.cm.lib.gjb_model_pf_step(C.byref(plan.sargs[1]), stream), 200, 20)
+        st_bytes = (8 * d + 24) * n
+        st_gbs = st_bytes / (st_ms * 1e-3) / 1e9
+        kernels["pf_step_kernel"] = {
+            "kernel_us": st_ms * 1e3, "algorithmic_bytes_per_launch": st_bytes, "achieved": st_gbs, "frac": st_gbs / peak,
+            "what": "the whole filter step in one launch: output-slot systematic resampling of the previous step (tile-exponent "
+                    "CDF) + ancestor gather + propose + logpdf + within-tile CDF / tile record of the new weights (gjb_model_pf_step)"}
+        roofline = {
+            "bound": "hbm", "kernel": "pf_step_kernel: " + kernels["pf_step_kernel"]["what"],
+            "achieved": st_gbs, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": st_gbs / peak, "traffic": None,
+            "kernel_us": st_ms * 1e3, "algorithmic_bytes_per_launch": st_bytes, "algorithmic_bytes_per_particle_step": 8 * d + 24,
+            "note": "algorithmic bytes = SURVEY 8d's whole-step figure (8d + 24 per particle-step): this kernel is the whole step",
+        }
+    elif getattr(plan, "persistent", False):
         pf_ms = time_launches(lambda: plan.cm.lib.gjb_model_pf_run(C.byref(plan.pf_args), stream), 10, 2)
         achieved = step_bytes / (pf_ms * 1e-3) / 1e9
         roofline = {

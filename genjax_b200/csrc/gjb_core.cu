@@ -13,6 +13,7 @@
 #include "../../include/genjax_b200.h"
 #include "gjb_resample.cuh"
 #include "gjb_rng.cuh"
+#include "gjb_step.cuh"
 
 namespace gjb {
 
@@ -531,6 +532,44 @@ static inline int launch_status() {
   return (int)e;
 }
 
+
+// ---------------------------------------------------------------- tile-exponent masses (section 1c)
+
+// one CTA per 2048-particle tile: logw -> within-tile CDF + tile record (the stand-alone form of what pf_step_kernel
+// does with the weights it has just computed)
+__global__ void __launch_bounds__(kThreads) te_mass_kernel(const float* __restrict__ logw, int64_t n,
+                                                           uint64_t* __restrict__ cdf, gjb_tile_rec* __restrict__ recs) {
+  __shared__ TeSmem sm;
+  const int64_t base = (int64_t)blockIdx.x * kTeTile + threadIdx.x * kTeItems;
+  float lw[kTeItems];
+  load_items<false>(logw, n, base, lw);
+  te_publish(lw, cdf + (int64_t)blockIdx.x * kTeTile, recs + blockIdx.x, sm);
+}
+
+// one CTA per window of 2048 offspring slots: ancestors of [out_lo, out_lo + out_n) from the tile-exponent CDF
+__global__ void __launch_bounds__(kThreads) te_resample_kernel(const __grid_constant__ gjb_te_resample_args A) {
+  __shared__ TeSmem sm;
+  const int64_t w_lo = A.out_lo + (int64_t)blockIdx.x * kTeTile;
+  const int64_t left = A.out_lo + A.out_n - w_lo;
+  const int w_n = left < kTeTile ? (int)left : kTeTile;
+  const double u0 = resample_u0(__ldg(A.key_dev), __ldg(A.key_dev + 1),
+                                (uint64_t)__ldg(A.key_dev + 2) | ((uint64_t)__ldg(A.key_dev + 3) << 32));
+  int32_t anc[kTeItems];
+  int E;
+  const uint64_t S = A.cdf_peers ? te_pull<true>(A.recs, A.n_tiles_total, A.cdf, A.cdf_peers, A.n_total, u0, w_lo, w_n, sm, anc, &E)
+                                 : te_pull<false>(A.recs, A.n_tiles_total, A.cdf, nullptr, A.n_total, u0, w_lo, w_n, sm, anc, &E);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && A.lse_out) te_write_lse(A.lse_out, E, S, A.n_total);
+  int32_t* out = A.ancestors + (int64_t)blockIdx.x * kTeTile + threadIdx.x * kTeItems;
+  const int j0 = threadIdx.x * kTeItems;
+  if (j0 + kTeItems <= w_n && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+    reinterpret_cast<int4*>(out)[0] = make_int4(anc[0], anc[1], anc[2], anc[3]);
+    reinterpret_cast<int4*>(out)[1] = make_int4(anc[4], anc[5], anc[6], anc[7]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < kTeItems; ++k) if (j0 + k < w_n) out[k] = anc[k];
+  }
+}
+
 }  // namespace gjb
 
 using namespace gjb;
@@ -564,7 +603,7 @@ int gjb_weight_mass(const float* logw, int64_t n, const uint32_t* wmax, const fl
   if (!logw || !tile_mass || (!wmax && !m_global) || n < 0) return GJB_E_ARG;
   if (n == 0) return 0;
   const int64_t tiles = (n + kTile - 1) / kTile;
-  if (tiles > 0x7fffffff) return GJB_E_RANGE;
+  if (n >= GJB_MASS_MAX_PARTICLES) return GJB_E_RANGE;  // a shard alone may not exceed what the total may
   weight_mass_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(logw, n, wmax, m_global, tile_mass);
   return launch_status();
 }
@@ -572,6 +611,7 @@ int gjb_weight_mass(const float* logw, int64_t n, const uint32_t* wmax, const fl
 int gjb_lse_finalize(const uint64_t* tile_mass, int64_t n, const uint32_t* wmax, const float* m_global,
                      int64_t n_total, double* lse_out, void* stream) {
   if (!tile_mass || !lse_out || (!wmax && !m_global) || n <= 0 || n_total <= 0) return GJB_E_ARG;
+  if (n_total >= GJB_MASS_MAX_PARTICLES || n >= GJB_MASS_MAX_PARTICLES) return GJB_E_RANGE;
   const int64_t tiles = (n + kTile - 1) / kTile;
   lse_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(tile_mass, (int)tiles, wmax, m_global, n_total, lse_out);
   return launch_status();
@@ -580,7 +620,7 @@ int gjb_lse_finalize(const uint64_t* tile_mass, int64_t n, const uint32_t* wmax,
 int gjb_resample_systematic(const gjb_resample_args* a, void* stream) {
   if (!a || !a->logw || !a->tile_mass || !a->ancestors || (!a->wmax && !a->m_global)) return GJB_E_ARG;
   if (a->n <= 0 || a->n_total <= 0 || a->out_n < 0 || a->out_lo < 0) return GJB_E_ARG;
-  if (a->n_total > 0x7fffffffLL) return GJB_E_RANGE;  // int32 ancestors
+  if (a->n_total >= GJB_MASS_MAX_PARTICLES) return GJB_E_RANGE;  // S = sum of masses <= 2^36 each must stay < 2^63
   const int64_t tiles = (a->n + kTile - 1) / kTile;
   gjb_peers none = {};
   resample_systematic_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a, none, nullptr, 0, 0, 0);
@@ -609,7 +649,7 @@ int gjb_mass_resample_systematic(const gjb_resample_args* a, void* stream) {
   if (!a || !a->logw || !a->tile_mass || !a->ancestors || !a->wmax) return GJB_E_ARG;
   if (a->m_global || a->c_offset || a->s_total) return GJB_E_MODE;  // single-device form
   if (a->n <= 0 || a->n_total <= 0 || a->out_n < 0 || a->out_lo < 0) return GJB_E_ARG;
-  if (a->n_total > 0x7fffffffLL) return GJB_E_RANGE;
+  if (a->n_total >= GJB_MASS_MAX_PARTICLES) return GJB_E_RANGE;
   if (!gjb_mass_resample_fits(a->n)) return GJB_E_RANGE;
   const int64_t tiles = (a->n + kTile - 1) / kTile;
   void* params[1] = {(void*)a};
@@ -623,7 +663,7 @@ int gjb_resample_systematic_peers(const gjb_resample_args* a, const gjb_peers* a
   if (!a || !anc || !a->logw || !a->tile_mass || (!a->wmax && !a->m_global)) return GJB_E_ARG;
   if (anc->world < 1 || anc->world > GJB_MAX_RANKS || anc->n_per_rank <= 0 || (anc->n_per_rank & 3)) return GJB_E_ARG;
   if (a->n <= 0 || a->n_total != anc->n_per_rank * anc->world || a->out_lo != 0 || a->out_n != a->n_total) return GJB_E_ARG;
-  if (a->n_total > 0x7fffffffLL) return GJB_E_RANGE;
+  if (a->n_total >= GJB_MASS_MAX_PARTICLES) return GJB_E_RANGE;
   for (int r = 0; r < anc->world; ++r) if (!anc->base[r]) return GJB_E_ARG;
   const int64_t tiles = (a->n + kTile - 1) / kTile;
   gjb_peers p = *anc;
@@ -638,7 +678,7 @@ int gjb_resample_systematic_linked(const gjb_resample_args* a, const gjb_peers* 
   if (!a || !anc || !link || !a->logw || !a->tile_mass || !wait_max || !wait_mass) return GJB_E_ARG;
   if (anc->world < 2 || anc->world > GJB_MAX_RANKS || anc->n_per_rank <= 0 || (anc->n_per_rank & 3)) return GJB_E_ARG;
   if (a->n <= 0 || a->n_total != anc->n_per_rank * anc->world || a->out_lo != 0 || a->out_n != a->n_total) return GJB_E_ARG;
-  if (a->n_total > 0x7fffffffLL) return GJB_E_RANGE;
+  if (a->n_total >= GJB_MASS_MAX_PARTICLES) return GJB_E_RANGE;
   const int64_t tiles = (a->n + kTile - 1) / kTile;
   gjb_peers p = *anc;
   gjb_peers_set_divisor(&p);
@@ -651,7 +691,7 @@ int gjb_weight_mass_linked(const float* logw, int64_t n, uint64_t* tile_mass, co
                            uint64_t push_mass, void* stream) {
   if (!logw || !tile_mass || !link || n <= 0 || !wait_max || !push_mass) return GJB_E_ARG;
   const int64_t tiles = (n + kTile - 1) / kTile;
-  if (tiles > 0x7fffffff) return GJB_E_RANGE;
+  if (n >= GJB_MASS_MAX_PARTICLES) return GJB_E_RANGE;
   weight_mass_linked_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(logw, n, tile_mass, nullptr, link, wait_max, push_mass);
   return launch_status();
 }
@@ -660,7 +700,7 @@ int gjb_weight_mass_prefix_linked(const float* logw, int64_t n, uint64_t* tile_m
                                   const gjb_link* link, uint64_t wait_max, uint64_t push_mass, void* stream) {
   if (!logw || !tile_mass || !tile_prefix || !link || n <= 0 || !wait_max || !push_mass) return GJB_E_ARG;
   const int64_t tiles = (n + kTile - 1) / kTile;
-  if (tiles > 0x7fffffff) return GJB_E_RANGE;
+  if (n >= GJB_MASS_MAX_PARTICLES) return GJB_E_RANGE;
   weight_mass_linked_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(logw, n, tile_mass, tile_prefix, link, wait_max,
                                                                               push_mass);
   return launch_status();
@@ -674,7 +714,7 @@ int gjb_resample_systematic_pull(const gjb_resample_args* a, const gjb_peers* lo
   const int64_t npr = logw_peers->n_per_rank;
   if (npr <= 0 || (npr & 3) || a->n != npr || a->n_total != npr * world) return GJB_E_ARG;
   if (a->out_n != npr || a->out_lo != (int64_t)logw_peers->rank * npr) return GJB_E_ARG;
-  if (a->n_total > 0x7fffffffLL) return GJB_E_RANGE;
+  if (a->n_total >= GJB_MASS_MAX_PARTICLES) return GJB_E_RANGE;
   for (int r = 0; r < world; ++r) if (!logw_peers->base[r] || !prefix_peers->base[r]) return GJB_E_ARG;
   const int64_t tiles = (npr + kTile - 1) / kTile;
   resample_pull_kernel<<<dim3((unsigned)tiles), kThreads, 0, (cudaStream_t)stream>>>(
@@ -682,11 +722,32 @@ int gjb_resample_systematic_pull(const gjb_resample_args* a, const gjb_peers* lo
   return launch_status();
 }
 
+int gjb_te_masses(const float* logw, int64_t n, uint64_t* cdf, gjb_tile_rec* recs, void* stream) {
+  if (!logw || !cdf || !recs || n <= 0) return GJB_E_ARG;
+  if ((reinterpret_cast<uintptr_t>(cdf) & 15) || (reinterpret_cast<uintptr_t>(recs) & 15)) return GJB_E_ARG;
+  const int64_t tiles = (n + kTeTile - 1) / kTeTile;
+  if (n >= GJB_MASS_MAX_PARTICLES) return GJB_E_RANGE;
+  te_mass_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(logw, n, cdf, recs);
+  return launch_status();
+}
+
+int gjb_te_resample(const gjb_te_resample_args* a, void* stream) {
+  if (!a || !a->cdf || !a->recs || !a->key_dev || !a->ancestors || a->out_n < 0 || a->out_lo < 0) return GJB_E_ARG;
+  if (a->n_tiles_total <= 0 || a->n_total <= 0 || a->out_lo + a->out_n > a->n_total) return GJB_E_ARG;
+  // S <= n_total * (2^36 + 1) must stay below 2^63 (signed conversion in offspring_cnt): n_total <= 2^26
+  if (a->n_tiles_total > kTeMaxTiles || a->n_total > (1LL << 26)) return GJB_E_RANGE;
+  if ((int64_t)a->n_tiles_total * kTeTile < a->n_total) return GJB_E_ARG;
+  if (a->out_n == 0) return 0;
+  const int64_t ctas = (a->out_n + kTeTile - 1) / kTeTile;
+  te_resample_kernel<<<(int)ctas, kThreads, 0, (cudaStream_t)stream>>>(*a);
+  return launch_status();
+}
+
 int gjb_resample_multinomial(const float* logw, int64_t n, const uint32_t* wmax, const uint64_t* tile_mass,
                              uint64_t* cdf, uint32_t key0, uint32_t key1, uint64_t idx_offset, int64_t n_out,
                              int32_t* ancestors, void* stream) {
   if (!logw || !wmax || !tile_mass || !cdf || !ancestors || n <= 0 || n_out < 0) return GJB_E_ARG;
-  if (n > 0x7fffffffLL) return GJB_E_RANGE;
+  if (n >= GJB_MASS_MAX_PARTICLES) return GJB_E_RANGE;
   const int64_t tiles = (n + kTile - 1) / kTile;
   cdf_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(logw, n, wmax, tile_mass, cdf);
   int e = launch_status();

@@ -20,6 +20,7 @@
 #include "gjb_dist.cuh"
 #include "gjb_resample.cuh"
 #include "gjb_rng.cuh"
+#include "gjb_step.cuh"
 
 namespace gjb {
 
@@ -83,6 +84,21 @@ __device__ __forceinline__ void load4_idx(const int32_t* __restrict__ gather, in
   } else {
 #pragma unroll
     for (int u = 0; u < 4; ++u) g[u] = (u >= lo && u < hi) ? ldx<kCg>(gather + i0 + u) : 0;
+  }
+}
+
+// the same through a generic pointer (the single-launch filter step keeps the ancestors of its window in shared memory)
+__device__ __forceinline__ void load4_idx_gen(const int32_t* gather, int64_t i0, int lo, int hi, int32_t (&g)[4]) {
+  if (!gather) {
+    g[0] = g[1] = g[2] = g[3] = 0;
+    return;
+  }
+  if (lo == 0 && hi == 4 && ((reinterpret_cast<uintptr_t>(gather + i0) & 15) == 0)) {
+    const int4 v = *reinterpret_cast<const int4*>(gather + i0);
+    g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) g[u] = (u >= lo && u < hi) ? gather[i0 + u] : 0;
   }
 }
 

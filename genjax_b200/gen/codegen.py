@@ -32,6 +32,8 @@ from __future__ import annotations
 
 import json
 
+import numpy as np
+
 from . import expr as E
 from .capture import ModelIR
 from .expr import Expr, F32, I32
@@ -371,8 +373,9 @@ class _Emitter:
             self.w(f"if {need} {{ float lp = -{lc}; for (int k = 0; k < {D}; ++k) {{ const float z = s{j}[k] * {inv}[k] - {self.elem_ref(loc, 'k')} * {inv}[k]; lp -= 0.5f * (z * z); }} score += lp; if ({fl} & GJB_SITE_WEIGHT) weight += lp; }}")
 
 
-def _info_json(ir: ModelIR, mapping: str, G: int) -> str:
+def _info_json(ir: ModelIR, mapping: str, G: int, pf_step: bool = False) -> str:
     info = {
+        "pf_step": bool(pf_step),
         "name": ir.name,
         "digest": ir.digest,
         "mapping": mapping,
@@ -472,6 +475,7 @@ class _Generator:
         out.append("  const int32_t* gather; const float* score_in; const float* weight_in; float* score_out; float* weight_out;")
         out.append("  const gjb_peers* peers;  // nullable device array [NA]: gathered rows may live on peer ranks")
         out.append("  const float* m_ref; unsigned long long* tile_mass;  // reference-maximum step (kMass instantiation only)")
+        out.append("  float* te_w;  // nullable (generic pointer): the weights also go here (single-launch step: shared memory)")
         out.append("};")
         out.append("struct Uni {  // particle-invariant values, computed once per thread per launch")
         out.append("  float sc[NA];")
@@ -563,7 +567,7 @@ class _Generator:
 
         out = list(P)
         out.append("// quads [ql_begin, ql_end) step ql_stride of the launch; local particle i0 = 4*ql - (idx_offset & 3)")
-        out.append("template <bool kCg, bool kSt, bool kMass = false>")
+        out.append("template <bool kCg, bool kSt, bool kMass = false, bool kSm = false>  // kSm: io.gather points to shared memory")
         out.append("__device__ __forceinline__ void run_quads(const Io& io, const Uni& U, const uint32_t (&fl)[NS], int64_t n,")
         out.append("    uint64_t idx_offset, uint32_t key0, uint32_t key1, int64_t ql_begin, int64_t ql_end, int64_t ql_stride, float& run_max) {")
         out.append("  const bool need_score = !kSt && io.score_out != nullptr;")
@@ -577,7 +581,7 @@ class _Generator:
         out.append("    const int hi = (n - i0) < 4 ? (int)(n - i0) : 4;")
         out.append("    P p[4];")
         out.append("    int32_t g[4];")
-        out.append("    gjb::load4_idx<kCg>(io.gather, i0, lo, hi, g);")
+        out.append("    if (kSm) gjb::load4_idx_gen(io.gather, i0, lo, hi, g); else gjb::load4_idx<kCg>(io.gather, i0, lo, hi, g);")
         out.append("    uint32_t w[4];")
         out.append("    (void)g0; (void)w; (void)quad0;")
         out.extend(pre)
@@ -607,6 +611,7 @@ class _Generator:
         out.append("        if (u >= lo && u < hi) run_max = fmaxf(run_max, t);")
         out.append("      }")
         out.append("      if (io.weight_out) gjb::store4(io.weight_out, i0, lo, hi, w);")
+        out.append("      if (kSm) gjb::store4(io.te_w, i0, lo, hi, w);")
         out.append("      if (kMass) {  // exact integer mass of the quad, added to its tile (a quad never straddles a tile)")
         out.append("        unsigned long long qs = 0ull;")
         out.append("        for (int u = 0; u < 4; ++u) if (u >= lo && u < hi) qs += gjb::det_exp_q(__fadd_rn(gjb::as_f(w[u]), -mref));")
@@ -662,7 +667,7 @@ class _Generator:
 
         out: list[str] = []
         out.append("// particles [p_begin, p_end): block-iteration base steps by p_stride; G lanes per particle")
-        out.append("template <bool kCg, bool kSt>")
+        out.append("template <bool kCg, bool kSt, bool kSm = false>  // kSm: io.gather points to shared memory")
         out.append("__device__ __forceinline__ void run_groups(const Io& io, const Uni& U, const uint32_t (&fl)[NS], int64_t n,")
         out.append("    uint64_t idx_offset, uint32_t key0, uint32_t key1, int64_t p_begin, int64_t p_end, int64_t p_stride, float& run_max) {")
         out.append("  const bool need_score = !kSt && io.score_out != nullptr;")
@@ -672,7 +677,7 @@ class _Generator:
         out.append("    {")
         out.append("      const int64_t i = base + sub_p;")
         out.append("      const bool valid = i < p_end && i < n;")
-        out.append("      const int64_t row = valid ? (io.gather ? (int64_t)gjb::ldx<kCg>(io.gather + i) : i) : 0;")
+        out.append("      const int64_t row = valid ? (io.gather ? (int64_t)(kSm ? io.gather[i] : gjb::ldx<kCg>(io.gather + i)) : i) : 0;")
         out.append("      (void)row;")
         out.append("      const int sub = (int)((idx_offset + (uint64_t)i) & 3); (void)sub;")
         out.append("      const gjb::Lane rng = gjb::make_lane(key0, key1, idx_offset + (uint64_t)i); (void)rng;")
@@ -688,6 +693,7 @@ class _Generator:
         out.append("        if (!kSt && io.weight_in) t = __ldg(io.weight_in + i) + t;")
         out.append("        if (!kSt && io.score_in) t = t - __ldg(io.score_in + i);")
         out.append("        if (io.weight_out && lane == 0) io.weight_out[i] = t;")
+        out.append("        if (kSm && lane == 0) io.te_w[i] = t;")
         out.append("        run_max = fmaxf(run_max, t);")
         out.append("      }")
         out.append("    }")
@@ -718,6 +724,7 @@ class _Generator:
         out.append("  io.gather = A.gather; io.score_in = A.score_in; io.weight_in = A.weight_in; io.score_out = A.score_out; io.weight_out = A.weight_out;")
         out.append("  io.peers = A.peer_args;")
         out.append("  io.m_ref = A.m_ref; io.tile_mass = A.tile_mass;" if mass else "  io.m_ref = nullptr; io.tile_mass = nullptr;")
+        out.append("  io.te_w = nullptr;")
         out.append("  const uint32_t key0 = A.key_dev ? __ldg(A.key_dev) : A.key0, key1 = A.key_dev ? __ldg(A.key_dev + 1) : A.key1;")
         out.append("  float run_max = -INFINITY;")
         if self.group:
@@ -751,7 +758,7 @@ class _Generator:
         out.append("  for (int j = 0; j < NS; ++j) { io.site_in[j] = A.site_in[j]; io.site_out[j] = A.site_out[j]; }")
         out.append("  for (int k = 0; k < NR; ++k) io.ret_out[k] = A.ret_out[k];")
         out.append("  io.gather = nullptr; io.score_in = nullptr; io.weight_in = nullptr; io.score_out = nullptr; io.weight_out = A.weight_out;")
-        out.append("  io.peers = nullptr; io.m_ref = A.m_ref; io.tile_mass = A.tile_mass;")
+        out.append("  io.peers = nullptr; io.m_ref = A.m_ref; io.tile_mass = A.tile_mass; io.te_w = nullptr;")
         out.append("  const int64_t w_lo = (int64_t)blockIdx.x * gjb::kTile;")
         out.append("  const int64_t w_n = (A.n - w_lo) < gjb::kTile ? (A.n - w_lo) : gjb::kTile;")
         out.append("  if (A.pull_logw) {  // ancestors of MY slots from the previous step's weights and tile masses")
@@ -768,6 +775,77 @@ class _Generator:
         out.append("  const uint32_t key0 = A.key_dev ? __ldg(A.key_dev) : A.key0, key1 = A.key_dev ? __ldg(A.key_dev + 1) : A.key1;")
         out.append("  float run_max = -INFINITY;")
         out.append("  run_quads<true, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, (w_lo >> 2) + threadIdx.x, (w_lo + w_n + 3) >> 2, kThreads, run_max);")
+        out.append("}")
+        return out
+
+    def step_kernel(self) -> list[str]:
+        """The single-launch filter step (include/genjax_b200.h ``gjb_model_pf_step``): one CTA per 2048 offspring
+        slots -- te_pull (ancestors of the CTA's slots from the previous step's tile-exponent CDF) -> gather +
+        propose + logpdf through the generated body -> te_publish (within-tile CDF + tile record of the new
+        weights).  Block-level synchronisation only; csrc/gjb_step.cuh."""
+        ir = self.ir
+        out = ["__global__ void __launch_bounds__(kThreads, 4) pf_step_kernel(const __grid_constant__ gjb_step_args A) {"]
+        out.append("  __shared__ gjb::TeSmem sm;")
+        out.extend(self.stage_lines("A.args"))
+        out.append("  Uni U; make_uni(U, A.scalars);")
+        out.append("  uint32_t fl[NS];")
+        out.append(f"  for (int j = 0; j < {self.ns}; ++j) fl[j] = kPfFl[j];")
+        out.append("  const int tid = threadIdx.x;")
+        out.append("  const int64_t w_loc = (int64_t)blockIdx.x * gjb::kTeTile;  // first (local) slot of this CTA's window")
+        out.append("  const int w_n = (A.n - w_loc) < gjb::kTeTile ? (int)(A.n - w_loc) : gjb::kTeTile;")
+        out.append("  Io io;")
+        out.append("  for (int i = 0; i < NA; ++i) io.args[i] = A.args[i];")
+        out.append("  for (int j = 0; j < NS; ++j) { io.site_in[j] = A.site_in[j]; io.site_out[j] = nullptr; }")
+        out.append("  for (int k = 0; k < NR; ++k) io.ret_out[k] = nullptr;")
+        for k, r in enumerate(ir.ret_leaves):
+            if isinstance(r, Expr) and r.op == "site" and r.attr not in (self.pf_obs or ()):
+                out.append(f"  io.site_out[{r.attr}] = A.state_out[{k}];  // a sampled site that is the next state: written once")
+            else:
+                out.append(f"  io.ret_out[{k}] = A.state_out[{k}];")
+        out.append("  io.gather = nullptr; io.score_in = nullptr; io.weight_in = nullptr; io.score_out = nullptr; io.weight_out = A.weight_out;")
+        out.append("  io.peers = nullptr; io.m_ref = nullptr; io.tile_mass = nullptr;")
+        wbuf = "reinterpret_cast<float*>(sm.pre)" if self.group else "reinterpret_cast<float*>(sm.heads)"
+        out.append(f"  float* const wbuf = {wbuf};  // this window's new weights (block-shared)")
+        out.append("  io.te_w = wbuf - w_loc;")
+        out.append("  if (A.prev_cdf) {  // ancestors of MY slots: output-slot systematic resampling of the previous step")
+        out.append("    const double u0 = gjb::resample_u0(__ldg(A.prev_key), __ldg(A.prev_key + 1), (uint64_t)__ldg(A.prev_key + 2) | ((uint64_t)__ldg(A.prev_key + 3) << 32));")
+        out.append("    int32_t anc[gjb::kTeItems];")
+        out.append("    int E;")
+        out.append("    const uint64_t S = A.cdf_peers")
+        out.append("        ? gjb::te_pull<true>(A.prev_recs, A.n_tiles_total, A.prev_cdf, A.cdf_peers, A.n_total, u0, A.slot_offset + w_loc, w_n, sm, anc, &E)")
+        out.append("        : gjb::te_pull<false>(A.prev_recs, A.n_tiles_total, A.prev_cdf, nullptr, A.n_total, u0, A.slot_offset + w_loc, w_n, sm, anc, &E);")
+        out.append("    if (blockIdx.x == 0 && tid == 0 && A.prev_lse) gjb::te_write_lse(A.prev_lse, E, S, A.n_total);")
+        out.append("    const int4 a0 = make_int4(anc[0], anc[1], anc[2], anc[3]), a1 = make_int4(anc[4], anc[5], anc[6], anc[7]);")
+        out.append("    *reinterpret_cast<int4*>(sm.heads + tid * gjb::kTeItems) = a0;  // (a thread's own slots: no hazard with the scan)")
+        out.append("    *reinterpret_cast<int4*>(sm.heads + tid * gjb::kTeItems + 4) = a1;")
+        out.append("    if (A.ancestors_out) {")
+        out.append("      int32_t* o = A.ancestors_out + w_loc + tid * gjb::kTeItems;")
+        out.append("      if (tid * gjb::kTeItems + gjb::kTeItems <= w_n) { reinterpret_cast<int4*>(o)[0] = a0; reinterpret_cast<int4*>(o)[1] = a1; }")
+        out.append("      else for (int k = 0; k < gjb::kTeItems; ++k) if (tid * gjb::kTeItems + k < w_n) o[k] = anc[k];")
+        out.append("    }")
+        out.append("    io.gather = sm.heads - w_loc;")
+        out.append("    io.peers = A.peer_args;")
+        out.append("  }")
+        out.append("  const uint32_t key0 = __ldg(A.key_dev), key1 = __ldg(A.key_dev + 1);")
+        out.append("  float run_max = -INFINITY;")
+        if self.group:
+            out.append("  __syncthreads();  // every group reads ancestors other threads resolved")
+            out.append("  if (A.cdf_peers) run_groups<true, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, w_loc, w_loc + w_n, kPPB, run_max);")
+            out.append("  else run_groups<false, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, w_loc, w_loc + w_n, kPPB, run_max);")
+            out.append("  __syncthreads();  // the window's weights are complete")
+        else:
+            out.append("  // the thread's own 8 slots = 2 global quads: ancestors and weights never leave the thread")
+            out.append("  const int64_t q0 = (w_loc >> 2) + tid * 2;")
+            out.append("  const int64_t qw = (w_loc + w_n + 3) >> 2;")
+            out.append("  const int64_t qe = q0 + 2 < qw ? q0 + 2 : qw;")
+            out.append("  if (A.cdf_peers) run_quads<true, true, false, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0, qe, 1, run_max);")
+            out.append("  else run_quads<false, true, false, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0, qe, 1, run_max);")
+        out.append("  float lw[gjb::kTeItems];")
+        out.append("#pragma unroll")
+        out.append("  for (int k = 0; k < gjb::kTeItems; ++k) lw[k] = (tid * gjb::kTeItems + k < w_n) ? wbuf[tid * gjb::kTeItems + k] : -INFINITY;")
+        if self.group:
+            out.append("  __syncthreads();  // wbuf aliases sm.pre: everyone has its weights before te_publish reuses the scratch")
+        out.append("  gjb::te_publish(lw, A.cdf_out + w_loc, A.recs_out + blockIdx.x, sm);")
         out.append("}")
         return out
 
@@ -798,7 +876,7 @@ class _Generator:
         out.append("    for (int i = 0; i < NA; ++i) io.args[i] = nullptr;")
         out.append("    for (int j = 0; j < NS; ++j) { io.site_in[j] = nullptr; io.site_out[j] = nullptr; }")
         out.append("    for (int k = 0; k < NR; ++k) io.ret_out[k] = nullptr;")
-        out.append("    io.score_in = nullptr; io.weight_in = nullptr; io.score_out = nullptr; io.peers = nullptr; io.m_ref = nullptr; io.tile_mass = nullptr;")
+        out.append("    io.score_in = nullptr; io.weight_in = nullptr; io.score_out = nullptr; io.peers = nullptr; io.m_ref = nullptr; io.tile_mass = nullptr; io.te_w = nullptr;")
         for i in range(len(ir.ret_leaves)):
             out.append(f"    io.args[{i}] = t == 0 ? Q.state0[{i}] : (const void*)((const char*)Q.state_buf[{i}] + (int64_t)pslot * Q.state_stride[{i}]);")
         out.append("    io.gather = t == 0 ? nullptr : Q.ancestors + (int64_t)pslot * n;")
@@ -888,6 +966,11 @@ class _Generator:
         pf = self.pf_supported()
         if pf:
             out.extend(self.pf_kernel())
+        # (static shared memory: TeSmem is 45 KB of the 48 KB a kernel may declare; large staged argument blocks do not fit)
+        staged = sum(max(1, int(np.prod(a.shape))) for a in self.ir.args if a.kind == "shared")
+        self.has_step = pf and self.pf_obs is not None and staged <= 640
+        if self.has_step:
+            out.extend(self.step_kernel())
         chain_ext = None
         if self.chain is not None:
             from . import codegen_chain
@@ -901,7 +984,7 @@ class _Generator:
     def extern_c(self, pf: bool, chain_ext: str | None = None) -> str:
         ir = self.ir
         mapping = "group" if self.group else "quad"
-        info = _info_json(ir, mapping, max(self.G, 1)).replace("\\", "\\\\").replace('"', '\\"')
+        info = _info_json(ir, mapping, max(self.G, 1), getattr(self, "has_step", False)).replace("\\", "\\\\").replace('"', '\\"')
         if self.group:
             work = "a->n"
             per_block = "kPPB"
@@ -931,7 +1014,7 @@ int gjb_model_pf_run(const gjb_pf_args* a, void* stream) {{
     return GJB_E_ARG;
   if (a->n_state != {len(ir.ret_leaves)}) return GJB_E_ARG;
   if ((a->idx_offset & 3) != 0) return GJB_E_ARG;  // quads must align with the global quad streams
-  if (a->n_total > 0x7fffffffLL || a->n > 0x7fffffffLL) return GJB_E_RANGE;
+  if (a->n_total >= GJB_MASS_MAX_PARTICLES || a->n >= GJB_MASS_MAX_PARTICLES) return GJB_E_RANGE;
   for (int i = 0; i < a->n_state; ++i) if (!a->state0[i] || !a->state_buf[i]) return GJB_E_ARG;
   if (kPfStatic) for (int j = 0; j < {self.ns}; ++j) if (a->site_flags[j] != kPfFl_host[j]) return GJB_E_MODE;  // flags are baked in
   const int grid = pf_grid_for(a->n);
@@ -963,7 +1046,7 @@ int gjb_model_pf_run(const gjb_pf_args* a, void* stream) { (void)a; (void)stream
     if (a->pull_ancestors) {{{{  // single-pass step: one CTA per 2048 offspring slots
       const int64_t tiles = (a->n + gjb::kTile - 1) / gjb::kTile;
       if (tiles > gjb::kPullMaxTiles || a->idx_offset != 0 || a->gather) return GJB_E_RANGE;
-      if (a->pull_logw && (!a->pull_tile_mass || !a->pull_m_ref || !a->pull_key || a->pull_n_total <= 0 || a->pull_n_total > 0x7fffffffLL)) return GJB_E_ARG;
+      if (a->pull_logw && (!a->pull_tile_mass || !a->pull_m_ref || !a->pull_key || a->pull_n_total <= 0 || a->pull_n_total >= GJB_MASS_MAX_PARTICLES)) return GJB_E_ARG;
       {'return GJB_E_MODE;' if self.group else 'model_kernel_static_pull<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a);'}
       return (int)cudaGetLastError();
     }}}}
@@ -976,6 +1059,30 @@ int gjb_model_pf_run(const gjb_pf_args* a, void* stream) { (void)a; (void)stream
   }}}}"""
         else:
             static_dispatch = "if (a->tile_mass || a->m_ref) return GJB_E_MODE;  // needs the filter-flag instantiation"
+        if getattr(self, "has_step", False):
+            step_code = """
+int gjb_model_pf_step(const gjb_step_args* a, void* stream) {
+  if (!a || a->n <= 0 || a->n_total < a->n || !a->key_dev || !a->cdf_out || !a->recs_out) return GJB_E_ARG;
+  if ((a->idx_offset & 3) != 0 || a->slot_offset < 0 || (a->slot_offset % gjb::kTeTile) != 0) return GJB_E_ARG;
+  if ((reinterpret_cast<uintptr_t>(a->cdf_out) & 15) || (reinterpret_cast<uintptr_t>(a->recs_out) & 15)) return GJB_E_ARG;
+  for (int k = 0; k < NR; ++k) if (!a->state_out[k]) return GJB_E_ARG;
+  // S <= n_total * (2^36 + 1) must stay below 2^63 (signed conversion in offspring_cnt)
+  if (a->n_total > (1LL << 26)) return GJB_E_RANGE;
+  if (a->prev_cdf) {
+    if (!a->prev_recs || !a->prev_key || a->n_tiles_total <= 0) return GJB_E_ARG;
+    if (a->n_tiles_total > gjb::kTeMaxTiles) return GJB_E_RANGE;
+    if ((int64_t)a->n_tiles_total * gjb::kTeTile < a->n_total) return GJB_E_ARG;
+    if ((reinterpret_cast<uintptr_t>(a->prev_cdf) & 15) || (reinterpret_cast<uintptr_t>(a->prev_recs) & 15)) return GJB_E_ARG;
+  }
+  const int64_t tiles = (a->n + gjb::kTeTile - 1) / gjb::kTeTile;
+  pf_step_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a);
+  return (int)cudaGetLastError();
+}
+"""
+        else:
+            step_code = """
+int gjb_model_pf_step(const gjb_step_args* a, void* stream) { (void)a; (void)stream; return GJB_E_MODE; }
+"""
         chain_code = chain_ext if chain_ext is not None else """
 int gjb_model_mh_chain(const gjb_chain_args* a, void* stream) { (void)a; (void)stream; return GJB_E_MODE; }
 int gjb_model_hmc_chain(const gjb_chain_args* a, void* stream) { (void)a; (void)stream; return GJB_E_MODE; }
@@ -996,6 +1103,7 @@ int gjb_model_launch(const gjb_model_args* a, void* stream) {{
   return (int)cudaGetLastError();
 }}
 {pf_code}
+{step_code}
 {chain_code}
 }}
 """

@@ -69,8 +69,10 @@ class ParticleFilter:
         masses; a bound so loose that every mass underflows shows up as ``lse_terms[:, 1] == 0``."""
         if resampler != "systematic":
             raise NotImplementedError("the fused filter loop uses systematic resampling; see ParticleCollection.resample")
-        if mode not in ("persistent", "graph"):
+        if mode not in ("persistent", "graph", "step"):
             raise ValueError(mode)
+        if mode == "step" and reference_max != "running":
+            raise ValueError("mode='step' forms its masses per tile (tile-exponent CDF); it takes no reference_max")
         if reference_max not in ("running", "analytic"):
             raise ValueError(reference_max)
         if reference_max == "analytic" and mode != "graph":
@@ -202,6 +204,17 @@ class _Plan:
             self.obs_sites[ir.site_index(addr)] = addr
         self.graph = None
         self.persistent = pf.mode == "persistent"
+        self.stepmode = pf.mode == "step"
+        if self.stepmode:
+            tiles = (n + cabi.TE_TILE - 1) // cabi.TE_TILE
+            if tiles > cabi.TE_MAX_TILES or pf.n_total > (1 << 26):
+                raise NotImplementedError(f"mode='step' resamples over at most {cabi.TE_MAX_TILES} tiles of {cabi.TE_TILE} "
+                                          "particles; use mode='graph' beyond that")
+            if not self.cm.info.get("pf_step", False):
+                raise NotImplementedError("mode='step': this model's return value does not feed back as its state")
+            self.te_tiles = tiles
+            self.te_cdf = torch.empty((2, tiles * cabi.TE_TILE), dtype=torch.int64, device=device)
+            self.te_recs = torch.empty((2, tiles, 2), dtype=torch.int64, device=device)
         self.analytic = pf.reference_max == "analytic"
         if self.analytic:
             from ..gen import bounds
@@ -226,6 +239,8 @@ class _Plan:
                 self.logw2 = torch.empty((2, n), dtype=torch.float32, device=device)
         if self.persistent:
             self._build_pf_args()
+        elif self.stepmode:
+            self._build_step_args()
         else:
             self._build_args()
 
@@ -270,6 +285,55 @@ class _Plan:
         Q.cta_mass = self.cta_mass.data_ptr()
         Q.barrier = self.barrier.data_ptr()
         self.pf_args = Q
+
+    def _build_step_args(self):
+        """One ``gjb_step_args`` per step (ONE launch each) + the closing ``gjb_te_resample_args``."""
+        pf, ir, T, n = self.pf, self.ir, self.T, self.pf.n
+        if pf.idx_offset % 4:
+            raise ValueError("mode='step' needs idx_offset % 4 == 0 (quad RNG streams)")
+        self.sargs = []
+        for t in range(T):
+            A = cabi.StepArgs()
+            A.n, A.n_total, A.idx_offset, A.slot_offset = n, n, pf.idx_offset, 0
+            A.key_dev = self.keys[t].data_ptr()
+            slot = t if self.record else (t & 1)
+            prev_slot = (t - 1) if self.record else ((t - 1) & 1)
+            for i in range(len(self.state_in)):
+                A.args[i] = self.state_in[i].data_ptr() if t == 0 else self.bufs[i][prev_slot].data_ptr()
+                A.state_out[i] = self.bufs[i][slot].data_ptr()
+            for k, s in enumerate(self.shared):
+                i = len(self.state_in) + k
+                if isinstance(s, torch.Tensor):
+                    A.args[i] = s.data_ptr()
+                else:
+                    A.scalars[i] = float(s)
+            for j, addr in self.obs_sites.items():
+                A.site_in[j] = self.obs[addr][t].data_ptr()
+            # the log-weights only leave the kernel when somebody reads them: every step when recording, else the last
+            if self.record:
+                A.weight_out = self.logw_hist[t].data_ptr()
+            elif t == T - 1:
+                A.weight_out = self.logw.data_ptr()
+            if t > 0:
+                A.prev_cdf = self.te_cdf[(t - 1) & 1].data_ptr()
+                A.prev_recs = self.te_recs[(t - 1) & 1].data_ptr()
+                A.n_tiles_total = self.te_tiles
+                A.prev_key = self.keys[t - 1][2:].data_ptr()
+                A.prev_lse = self.lse[t - 1].data_ptr()
+                if self.record:
+                    A.ancestors_out = self.anc[t - 1].data_ptr()
+            A.cdf_out = self.te_cdf[t & 1].data_ptr()
+            A.recs_out = self.te_recs[t & 1].data_ptr()
+            self.sargs.append(A)
+        last = (T - 1) if self.record else ((T - 1) & 1)
+        R = cabi.TeResampleArgs()
+        R.cdf = self.te_cdf[(T - 1) & 1].data_ptr()
+        R.recs = self.te_recs[(T - 1) & 1].data_ptr()
+        R.n_tiles_total, R.n_total, R.out_lo, R.out_n = self.te_tiles, n, 0, n
+        R.key_dev = self.keys[T - 1][2:].data_ptr()
+        R.ancestors = self.anc[last].data_ptr()
+        R.lse_out = self.lse[T - 1].data_ptr()
+        self.te_close = R
 
     def _build_args(self):
         pf, ir, T, n = self.pf, self.ir, self.T, self.pf.n
@@ -370,6 +434,14 @@ class _Plan:
             for k in range(len(self.bufs)):
                 smc_ops.gather_rows(self.bufs[k][last], self.anc[last], self.final[k])
             return
+        if self.stepmode:  # ONE launch per step, the closing resampling of the last step, the final gather(s)
+            for t in range(self.T):
+                cabi.check(lib.gjb_model_pf_step(C.byref(self.sargs[t]), stream), "gjb_model_pf_step")
+            cabi.check(core.gjb_te_resample(C.byref(self.te_close), stream), "gjb_te_resample")
+            last = (self.T - 1) if self.record else ((self.T - 1) & 1)
+            for k in range(len(self.bufs)):
+                smc_ops.gather_rows(self.bufs[k][last], self.anc[last], self.final[k])
+            return
         if self.analytic and self.single_pass:  # 1 launch per step + one closing resampling launch
             self.tm3.zero_()
             for t in range(self.T):
@@ -412,6 +484,8 @@ class _Plan:
     def launches_per_run(self) -> int:
         if self.persistent:
             return 2 + len(self.bufs)  # init + persistent filter kernel + final gather(s)
+        if self.stepmode:
+            return self.T + 1 + len(self.bufs)
         if self.analytic and self.single_pass:
             return self.T + 1 + len(self.bufs)  # (+ one memset node)
         if self.analytic:

@@ -13,11 +13,14 @@ import torch
 
 from . import build
 
-ABI_VERSION = 10  # GJB_ABI_VERSION of include/genjax_b200.h this binding mirrors (tests/test_abi.py keeps them equal)
+ABI_VERSION = 11  # GJB_ABI_VERSION of include/genjax_b200.h this binding mirrors (tests/test_abi.py keeps them equal)
 GJB_MAX_SITES = 16
 GJB_MAX_ARGS = 16
 GJB_MAX_RETS = 8
 GJB_HEAVY_WS_WORDS = 4 + 3 * 1024
+TE_TILE = 2048
+TE_MAX_TILES = 4096
+MASS_MAX_PARTICLES = 1 << 27
 
 SITE_SAMPLE = 1
 SITE_WEIGHT = 2
@@ -170,6 +173,58 @@ class PfArgs(C.Structure):
     ]
 
 
+class TileRec(C.Structure):
+    """``gjb_tile_rec`` (include/genjax_b200.h section 1c)."""
+
+    _fields_ = [("mass", _u64), ("e", _i32), ("reserved", _i32)]
+
+
+class TeResampleArgs(C.Structure):
+    """``gjb_te_resample_args`` (include/genjax_b200.h section 1c)."""
+
+    _fields_ = [
+        ("cdf", _p),
+        ("recs", _p),
+        ("cdf_peers", _p),
+        ("n_tiles_total", _i32),
+        ("reserved", _i32),
+        ("n_total", _i64),
+        ("out_lo", _i64),
+        ("out_n", _i64),
+        ("key_dev", _p),
+        ("ancestors", _p),
+        ("lse_out", _p),
+    ]
+
+
+class StepArgs(C.Structure):
+    """``gjb_step_args`` (include/genjax_b200.h section 2)."""
+
+    _fields_ = [
+        ("n", _i64),
+        ("n_total", _i64),
+        ("idx_offset", _u64),
+        ("slot_offset", _i64),
+        ("key_dev", _p),
+        ("args", _p * GJB_MAX_ARGS),
+        ("scalars", C.c_float * GJB_MAX_ARGS),
+        ("peer_args", _p),
+        ("site_in", _p * GJB_MAX_SITES),
+        ("state_out", _p * GJB_MAX_RETS),
+        ("weight_out", _p),
+        ("prev_cdf", _p),
+        ("prev_recs", _p),
+        ("cdf_peers", _p),
+        ("n_tiles_total", _i32),
+        ("reserved", _i32),
+        ("prev_key", _p),
+        ("ancestors_out", _p),
+        ("prev_lse", _p),
+        ("cdf_out", _p),
+        ("recs_out", _p),
+    ]
+
+
 class ChainArgs(C.Structure):
     """``gjb_chain_args`` (include/genjax_b200.h)."""
 
@@ -217,6 +272,8 @@ CORE_PROTOTYPES = {
     "gjb_resample_systematic_linked": (C.c_int, [C.POINTER(ResampleArgs), C.POINTER(Peers), _p, _u64, _u64, _u64, _p]),
     "gjb_resample_systematic_peers": (C.c_int, [C.POINTER(ResampleArgs), C.POINTER(Peers), _p]),
     "gjb_gather_rows_peers": (C.c_int, [C.POINTER(Peers), _p, _p, _i64, _i32, _p]),
+    "gjb_te_masses": (C.c_int, [_p, _i64, _p, _p, _p]),
+    "gjb_te_resample": (C.c_int, [C.POINTER(TeResampleArgs), _p]),
     "gjb_philox_fill": (C.c_int, [_u32, _u32, _u64, _u32, _u32, _i64, _p, _p]),
     "gjb_normal_fill": (C.c_int, [_u32, _u32, _u64, _u32, _i64, _i32, _p, _p]),
 }
@@ -226,6 +283,7 @@ MODEL_PROTOTYPES = {
     "gjb_model_launch": (C.c_int, [C.POINTER(ModelArgs), _p]),
     "gjb_model_pf_grid": (C.c_int, [_i64]),
     "gjb_model_pf_run": (C.c_int, [C.POINTER(PfArgs), _p]),
+    "gjb_model_pf_step": (C.c_int, [C.POINTER(StepArgs), _p]),
     "gjb_model_mh_chain": (C.c_int, [C.POINTER(ChainArgs), _p]),
     "gjb_model_hmc_chain": (C.c_int, [C.POINTER(ChainArgs), _p]),
 }

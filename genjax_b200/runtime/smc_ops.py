@@ -114,6 +114,43 @@ class WeightWorkspace:
         return ancestors
 
 
+class TeWorkspace:
+    """Tile-exponent CDF of n log-weights (include/genjax_b200.h section 1c): ``masses(logw)`` then
+    ``resample(key, ancestors)`` -- the stand-alone form of what the single-launch filter step does in flight."""
+
+    def __init__(self, n: int, device):
+        self.n = int(n)
+        self.device = device
+        self.tiles = (self.n + cabi.TE_TILE - 1) // cabi.TE_TILE
+        if self.tiles > cabi.TE_MAX_TILES:
+            raise cabi.GjbError(f"tile-exponent resampling spans at most {cabi.TE_MAX_TILES} tiles")
+        self.cdf = torch.empty(self.tiles * cabi.TE_TILE, dtype=torch.int64, device=device)
+        self.recs = torch.empty((self.tiles, 2), dtype=torch.int64, device=device)
+        self.lse = torch.empty(3, dtype=torch.float64, device=device)
+        self._key = torch.empty(4, dtype=torch.int32, device=device)
+
+    def masses(self, logw: torch.Tensor):
+        cabi.check(cabi.core().gjb_te_masses(cabi.ptr(logw), logw.numel(), self.cdf.data_ptr(), self.recs.data_ptr(),
+                                             cabi.stream_ptr(self.device)), "gjb_te_masses")
+        return self
+
+    def resample(self, key: PRNGKey, ancestors: torch.Tensor, out_lo: int = 0) -> torch.Tensor:
+        """ancestors[j - out_lo] for offspring j in [out_lo, out_lo + len(ancestors)); ``self.lse`` = {E ln 2, S, log-mean-exp}."""
+        import ctypes as C
+
+        import numpy as np
+
+        kd = np.array([key.words[0], key.words[1], key.index & 0xFFFFFFFF, key.index >> 32], dtype=np.uint32).view(np.int32)
+        self._key.copy_(torch.from_numpy(kd))
+        R = cabi.TeResampleArgs()
+        R.cdf, R.recs = self.cdf.data_ptr(), self.recs.data_ptr()
+        R.n_tiles_total, R.n_total = self.tiles, self.n
+        R.out_lo, R.out_n = int(out_lo), ancestors.numel()
+        R.key_dev, R.ancestors, R.lse_out = self._key.data_ptr(), ancestors.data_ptr(), self.lse.data_ptr()
+        cabi.check(cabi.core().gjb_te_resample(C.byref(R), cabi.stream_ptr(self.device)), "gjb_te_resample")
+        return ancestors
+
+
 def gather_rows(src: torch.Tensor, ancestors: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     """out[j] = src[ancestors[j]] over the leading axis (4-byte element types)."""
     if src.element_size() != 4:

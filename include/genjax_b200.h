@@ -34,11 +34,15 @@
 extern "C" {
 #endif
 
-#define GJB_ABI_VERSION 10
+#define GJB_ABI_VERSION 11
 
 #define GJB_E_ARG (-1)      /* null / misaligned pointer, negative size          */
 #define GJB_E_RANGE (-2)    /* size beyond what the kernel supports              */
 #define GJB_E_MODE (-3)     /* unknown mode / flag                               */
+
+/* Every particle's integer mass is at most 2^36 and the total S is summed in uint64 and converted as a signed
+ * 64-bit value: resampling / log-sum-exp entry points return GJB_E_RANGE for n_total >= 2^27 particles. */
+#define GJB_MASS_MAX_PARTICLES (1LL << 27)
 
 /* ------------------------------------------------------------------ 1. core */
 
@@ -237,6 +241,48 @@ int gjb_resample_systematic_peers(const gjb_resample_args* a, const gjb_peers* a
 int gjb_gather_rows_peers(const gjb_peers* src, const int32_t* ancestors, void* dst, int64_t n_out,
                           int32_t row_bytes, void* stream);
 
+/* ------------------------------------------- 1c. tile-exponent masses (single-launch filter step)
+ *
+ * The filter step that is ONE launch (section 2, gjb_model_pf_step) cannot spend a pass on the global maximum
+ * before it forms the integer masses.  Each tile of GJB_TE_TILE consecutive particles (tile = global index / 2048:
+ * a constant of the algorithm, not of the launch) takes its masses relative to its own power-of-two reference
+ * 2^e, e = ceil(max_tile(logw * log2 e)); whoever consumes the tiles aligns them with exact right shifts:
+ *     q_i = round(2^36 * 2^(logw_i * log2e - e)),  cdf[i] = inclusive prefix of q inside the tile,
+ *     rec[p] = {mass = cdf of the tile's last particle, e}
+ *     E = max_p e_p;  s_p = min(E - e_p, 63);  P_p = inclusive prefix of (mass_p >> s_p);  S = P_last
+ *     C_i = P_{p-1} + (cdf[i] >> s_p)   (a monotone integer CDF: any CTA / GPU partition gives the same bits)
+ *     offspring counts / ancestors exactly as gjb_resample_systematic; log-mean-exp = E ln 2 + log S - 36 ln 2 - log n_total.
+ * CPU restatement: oracle/smc.py (te_tile_masses, te_cdf, resample_systematic_te).  Replaces, like section 1, the
+ * logsumexp + categorical-per-offspring idiom (inference/smc.py:96-109; mapping_tutorial.ipynb cell 37).
+ */
+#define GJB_TE_TILE 2048
+#define GJB_TE_MAX_TILES 4096         /* global tiles one resampling can span (8 388 608 particles) */
+#define GJB_TE_E_NONE (-2147483647 - 1) /* exponent of a tile without a finite weight */
+
+typedef struct gjb_tile_rec {
+  uint64_t mass;             /* sum of the tile's masses, relative to 2^e       */
+  int32_t e;                 /* the tile's reference exponent (GJB_TE_E_NONE: no finite weight) */
+  int32_t reserved;
+} gjb_tile_rec;
+
+/* logw[n] -> cdf[ceil(n / 2048) * 2048] (padding repeats the last value), recs[ceil(n / 2048)]. */
+int gjb_te_masses(const float* logw, int64_t n, uint64_t* cdf, gjb_tile_rec* recs, void* stream);
+
+typedef struct gjb_te_resample_args {
+  const uint64_t* cdf;       /* [n_tiles_local * 2048] this device's within-tile CDFs */
+  const gjb_tile_rec* recs;  /* [n_tiles_total] tile records of ALL ranks, in global tile order */
+  const gjb_peers* cdf_peers; /* nullable DEVICE pointer: cdf of every rank (n_per_rank = particles per rank) */
+  int32_t n_tiles_total;
+  int32_t reserved;
+  int64_t n_total;           /* global particle count (offspring slots)          */
+  int64_t out_lo, out_n;     /* resolve offspring j in [out_lo, out_lo + out_n) into ancestors[j - out_lo] */
+  const uint32_t* key_dev;   /* {key0, key1, index_lo, index_hi}: u0 = u01(Philox(idx = index, site 0, chunk 0).x) */
+  int32_t* ancestors;        /* [out_n] global parent ids (identity when no weight has mass) */
+  double* lse_out;           /* nullable: {E ln 2, S, log-mean-exp}              */
+} gjb_te_resample_args;
+
+int gjb_te_resample(const gjb_te_resample_args* a, void* stream);
+
 /* Raw Philox words / N(0,1) draws for RNG known-answer tests. */
 int gjb_philox_fill(uint32_t key0, uint32_t key1, uint64_t idx_offset,
                     uint32_t site, uint32_t chunk, int64_t n, uint32_t* out4,
@@ -362,6 +408,41 @@ typedef struct gjb_pf_args {
 /* CTAs the persistent kernel uses for n particles (sizes cta_mass). */
 int gjb_model_pf_grid(int64_t n);
 int gjb_model_pf_run(const gjb_pf_args* a, void* stream);
+
+/*
+ * ONE launch per filter step (the default of inference/pf.py): every CTA owns GJB_TE_TILE offspring slots; it
+ * resolves their ancestors from the PREVIOUS step's tile-exponent CDF (section 1c; systematic, output-slot form),
+ * gathers the previous state through them, proposes, scores the observed sites, and publishes the within-tile CDF
+ * and tile record of ITS OWN new weights -- resample(t-1) + gather + propose + logpdf + masses(t) with only
+ * block-level synchronisation.  Batched form of the same user idiom as gjb_model_pf_run.  Filter-flag instantiation
+ * only (observed sites weighted + broadcast, every other site sampled); the model's return leaves are the next
+ * state.  prev_cdf == NULL (first step): no resampling, the state is read in place.
+ */
+typedef struct gjb_step_args {
+  int64_t n;                 /* particles on this device                          */
+  int64_t n_total;           /* particles the resampling spans (== n unless ranks resample globally) */
+  uint64_t idx_offset;       /* RNG lane of local particle 0 (multiple of 4)      */
+  int64_t slot_offset;       /* global offspring slot / parent id of local particle 0 (multiple of 2048; 0 on one device) */
+  const uint32_t* key_dev;   /* {key0, key1} of this step's proposals             */
+  const void* args[GJB_MAX_ARGS];      /* state leaves of the PREVIOUS step (pre-resampling) then shared blocks */
+  float scalars[GJB_MAX_ARGS];
+  const gjb_peers* peer_args; /* nullable DEVICE array [GJB_MAX_ARGS]: state leaf i of every rank */
+  const void* site_in[GJB_MAX_SITES];  /* observed values of this step (one value shared by all particles) */
+  void* state_out[GJB_MAX_RETS];       /* next state leaves [n(, d)]               */
+  float* weight_out;         /* nullable: this step's incremental log-weights [n]  */
+  const uint64_t* prev_cdf;  /* nullable: previous step's within-tile CDFs (this device) */
+  const gjb_tile_rec* prev_recs;       /* previous step's tile records, all ranks  */
+  const gjb_peers* cdf_peers; /* nullable DEVICE pointer: prev_cdf of every rank   */
+  int32_t n_tiles_total;
+  int32_t reserved;
+  const uint32_t* prev_key;  /* {key0, key1, index_lo, index_hi} of the previous step's resampling */
+  int32_t* ancestors_out;    /* nullable [n]: the ancestors this launch resolved (previous step's) */
+  double* prev_lse;          /* nullable: {E ln 2, S, log-mean-exp} of the previous step */
+  uint64_t* cdf_out;         /* [ceil(n / 2048) * 2048] this step's within-tile CDFs */
+  gjb_tile_rec* recs_out;    /* [ceil(n / 2048)] this step's tile records          */
+} gjb_step_args;
+
+int gjb_model_pf_step(const gjb_step_args* a, void* stream);
 
 /*
  * Batched MCMC drivers generated for the same model (one chain per lane).

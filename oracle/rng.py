@@ -212,6 +212,30 @@ F32 = np.float32
 _TWO_NEG23 = F32(2.0**-23)
 
 
+
+def fma32(a, b, c):
+    """Correctly rounded float32 fused multiply-add ``round32(a * b + c)`` (CUDA ``__fmaf_rn``, C ``fmaf``).
+
+    NumPy has no fma.  The product of two float32 is exact in float64; the float64 sum ``p + c`` may round, and
+    rounding that once more to float32 could double-round.  The sum is therefore re-rounded TO ODD (Boldo &
+    Melquiond, "Emulation of FMA and correctly rounded sums", 2008): with the exact error of the float64 addition
+    from TwoSum, an inexact sum whose last mantissa bit is even is moved to its neighbour on the error's side,
+    which is the odd one; rounding a 53-bit round-to-odd value to 24 bits is then the correctly rounded result.
+    Checked against glibc ``fmaf`` in tests/test_oracle_rng.py."""
+    a = np.asarray(a, dtype=F32).astype(np.float64)
+    b = np.asarray(b, dtype=F32).astype(np.float64)
+    c = np.asarray(c, dtype=F32).astype(np.float64)
+    with np.errstate(invalid="ignore", over="ignore"):
+        p = a * b
+        s = p + c
+        bb = s - p
+        err = (p - (s - bb)) + (c - bb)
+        even = (s.view(np.int64) & np.int64(1)) == 0
+        fix = np.isfinite(s) & (err != 0.0) & even
+        s = np.where(fix, np.nextafter(s, np.where(err > 0.0, np.inf, -np.inf)), s)
+    return s.astype(F32)
+
+
 def site_words(words, idx, site, chunk=0):
     """The 4 Philox words of (lane idx, site, chunk)."""
     idx = np.asarray(idx, dtype=np.uint64)

@@ -166,6 +166,118 @@ def log_mean_exp_ref(logw, M, n_total=None):
     return float(F32(M)) + math.log(S) - Q_BITS * math.log(2.0) - math.log(n)
 
 
+# ------------------------------------------------- tile-exponent masses
+#
+# The single-launch filter step (csrc/gjb_step.cuh, gen/codegen.py ``pf_step_kernel``) cannot afford a pass for the
+# global maximum before the masses are formed.  Each tile of TE_TILE consecutive particles (tile = global index //
+# 2048, a constant of the ALGORITHM, not of the launch) therefore takes its masses relative to its own power-of-two
+# reference 2^e_p, e_p = ceil(max_tile(lw * log2 e)); the consumer aligns the tiles with exact right shifts:
+#
+#     t_i = fl32(lw_i * log2e)  (non-finite -> mass 0);  n_i = floor(t_i);  sh_i = min(e_p - n_i, 63)
+#     q_i = round-half-up(m_i / 2^sh_i),  m_i = uint64(fl32(2^36 * 2^(t_i - n_i)))   (fp32 fma polynomial, te_exp2_m)
+#     c_i = inclusive prefix of q inside the tile (uint64),  T_p = the tile's mass
+#     e   = max_p e_p (tiles with mass);  s_p = min(e - e_p, 63);  P_p = inclusive prefix of (T_p >> s_p);  S = P_last
+#     C_i = P_{p-1} + (c_i >> s_p)        -- a monotone integer CDF: any CTA / GPU partition gives the same bits
+#     cnt_i, ancestors as in systematic_counts;  log-mean-exp = e ln 2 + log S - 36 ln 2 - log N.
+#
+# A particle's effective mass floor(c_i / 2^s) - floor(c_{i-1} / 2^s) is within one unit (2^-36 of the heaviest
+# particle's weight) of its exact share.  Same estimator; "parity unpinned" against the reference like every
+# resampling index stream (module docstring).
+
+TE_TILE = 2048
+TE_E_NONE = -(2**31)
+_TE_CLAMP = F32(2.0**29)
+# minimax-free choice: Taylor coefficients of 2^g, g in [-0.5, 0.5), degree 7, evaluated with fp32 FMAs (Horner)
+_TE_COEF = _EXP2_COEF
+
+
+def te_exp2_m(frac):
+    """uint64(fl32(2^36 * 2^frac)) for float32 frac in [0, 1): Horner with correctly rounded fp32 FMAs
+    (``__fmaf_rn`` on the device), times sqrt 2, times 2^36, truncated."""
+    g = (np.asarray(frac, dtype=F32) - F32(0.5)).astype(F32)
+    p = np.full(g.shape, _TE_COEF[7], dtype=F32)
+    for k in range(6, -1, -1):
+        p = rng.fma32(p, g, _TE_COEF[k])
+    p = (p * _SQRT2).astype(F32)
+    return (p * F32(2.0**Q_BITS)).astype(F32).astype(U64)
+
+
+def te_tile_masses(logw):
+    """(q uint64 [n], e_p int64 [tiles]) of tile-exponent masses; tiles are TE_TILE consecutive particles."""
+    logw = np.asarray(logw, dtype=F32)
+    n = len(logw)
+    tiles = max(1, -(-n // TE_TILE))
+    with np.errstate(invalid="ignore", over="ignore"):
+        t = (logw * _LOG2E).astype(F32)
+        ok = np.isfinite(t)
+        t = np.clip(np.where(ok, t, F32(0.0)), -_TE_CLAMP, _TE_CLAMP).astype(F32)
+        tp = np.full(tiles * TE_TILE, -np.inf, dtype=F32)
+        tp[:n] = np.where(ok, t, F32(-np.inf))
+        tmax = tp.reshape(tiles, TE_TILE).max(axis=1)
+        live = np.isfinite(tmax)
+        e_p = np.where(live, np.ceil(np.where(live, tmax, 0.0)), TE_E_NONE).astype(np.int64)
+        nfl = np.floor(t).astype(F32)
+        m = te_exp2_m((t - nfl).astype(F32))
+        sh = np.clip(e_p[np.arange(n) // TE_TILE] - nfl.astype(np.int64), 0, 63).astype(U64)
+        half = np.where(sh > 0, U64(1) << (np.maximum(sh, U64(1)) - U64(1)), U64(0)).astype(U64)
+        q = np.where(ok, (m + half) >> sh, U64(0)).astype(U64)
+    return q, e_p
+
+
+def te_cdf(logw):
+    """(C uint64 [n] global inclusive CDF, S int, e int or None): the tile-exponent CDF of the header comment."""
+    q, e_p = te_tile_masses(logw)
+    n = len(q)
+    tiles = len(e_p)
+    qp = np.zeros(tiles * TE_TILE, dtype=U64)
+    qp[:n] = q
+    c = np.cumsum(qp.reshape(tiles, TE_TILE), axis=1, dtype=U64)
+    T = c[:, -1]
+    livemass = T > 0
+    if not livemass.any():
+        return np.zeros(n, dtype=U64), 0, None
+    e = int(e_p[livemass].max())
+    s_p = np.where(livemass, np.minimum(e - np.where(livemass, e_p, e), 63), 63).astype(U64)
+    Tp = T >> s_p
+    P = np.cumsum(Tp, dtype=U64)
+    base = np.concatenate([[U64(0)], P[:-1]]).astype(U64)
+    C = (base[:, None] + (c >> s_p[:, None])).reshape(-1)[:n]
+    return C, int(P[-1]), e
+
+
+def te_log_mean_exp(logw, n_total=None):
+    _, S, e = te_cdf(logw)
+    n = len(logw) if n_total is None else n_total
+    if S == 0:
+        return -math.inf
+    return e * math.log(2.0) + math.log(S) - Q_BITS * math.log(2.0) - math.log(n)
+
+
+def te_counts(logw, u0, n_out=None):
+    """Cumulative offspring counts under the tile-exponent CDF (None when no weight has mass)."""
+    C, S, _ = te_cdf(logw)
+    n_out = len(logw) if n_out is None else n_out
+    if S == 0:
+        return None
+    scale = np.float64(n_out) / np.float64(S)
+    pos = C.astype(np.float64) * scale - np.float64(u0)
+    cnt = np.clip(np.ceil(pos), 0, n_out).astype(np.int64)
+    cnt[C == U64(S)] = n_out
+    return cnt
+
+
+def resample_systematic_te(logw, key: rng.Key, out_lo=0, out_n=None):
+    """Systematic ancestors of the offspring slots [out_lo, out_lo + out_n) under the tile-exponent CDF: slot j takes
+    the first particle whose cumulative count exceeds j.  Identity when no weight has mass."""
+    n = len(logw)
+    out_n = n - out_lo if out_n is None else out_n
+    j = np.arange(out_lo, out_lo + out_n, dtype=np.int64)
+    cnt = te_counts(logw, resample_u0(key))
+    if cnt is None:
+        return j.astype(np.int32)
+    return np.searchsorted(cnt, j, side="right").astype(np.int32)
+
+
 def _mulhi64(a, b):
     """floor(a*b / 2^64) for uint64 arrays / scalars (32-bit limbs)."""
     a = np.asarray(a, dtype=U64)
@@ -255,7 +367,7 @@ def pf_step_keys(key: rng.Key, t: int):
 
 
 def particle_filter(step_model, key: rng.Key, state0, observations, shared_args=(), resampler="systematic",
-                    record=False, m_ref=None):
+                    record=False, m_ref=None, masses="exact_max"):
     """Bootstrap PF.  ``step_model(h, *state, *shared_args)`` returns the new
     state (array or tuple of arrays); ``observations`` is a list of dicts
     addr -> value constrained at each step.
@@ -275,10 +387,16 @@ def particle_filter(step_model, key: rng.Key, state0, observations, shared_args=
         tr, w = gfi.generate(step_model, keys, obs, state + tuple(shared_args))
         # m_ref: a reference maximum known before the weights are (an analytic bound of the incremental weight);
         # the integer masses, hence ancestors and estimate, are then taken relative to it instead of max(w)
-        inc = log_mean_exp(w) if m_ref is None else log_mean_exp_ref(w, m_ref)
+        # masses="tile_exponent": the single-launch step's CDF (tile-exponent masses, see above)
+        if masses == "tile_exponent":
+            inc = te_log_mean_exp(w)
+        else:
+            inc = log_mean_exp(w) if m_ref is None else log_mean_exp_ref(w, m_ref)
         incs.append(inc)
         logz += inc
-        if resampler == "systematic":
+        if resampler == "systematic" and masses == "tile_exponent":
+            anc = resample_systematic_te(w, k_res)
+        elif resampler == "systematic":
             anc = resample_systematic(w, k_res) if m_ref is None else resample_systematic_pull(w, k_res, M=F32(m_ref))
         else:
             anc = resample_multinomial(w, rng.split(k_res, n))

@@ -137,7 +137,25 @@ class EmulatedModelLib:
 
     def gjb_model_info(self):
         sites = [{"addr": list(s.addr), "dist": s.dist.name} for s in self.ir.sites]
-        return json.dumps({"name": self.ir.name, "sites": sites, "emulated": True}).encode()
+        return json.dumps({"name": self.ir.name, "sites": sites, "emulated": True, "pf_step": True}).encode()
+
+    def gjb_model_pf_step(self, a_ref, stream):
+        """The single-launch filter step is a block-level kernel: always the GENERATED source with real block semantics
+        (tests/simt_kernels.py), also when the other launches of this library interpret the IR."""
+        import simt_kernels
+        from genjax_b200.gen import codegen
+
+        A = a_ref._obj
+        if A.peer_args or A.cdf_peers:
+            raise NotImplementedError("emulator: multi-GPU links are a GPU-only path")
+        if int(A.n) > 60_000:
+            raise NotImplementedError("emulator: the SIMT host run of pf_step_kernel is kept to small filters")
+        source = getattr(self, "source", None) or codegen.generate(self.ir, getattr(self, "pf_obs", None), self.chain)
+        lib = simt_kernels.model(source)
+        if not hasattr(lib, "s_pf_step"):
+            return -3
+        self.launches += 1
+        return lib.s_pf_step(a_ref)
 
     def gjb_model_launch(self, a_ref, stream):
         A = a_ref._obj
@@ -482,10 +500,21 @@ class EmulatedCore:
     oracle/smc.py.  Multi-GPU, fused cooperative and filter entry points are GPU-only and absent on purpose."""
 
     def gjb_abi_version(self):
-        return 10
+        return 11
 
     def gjb_mass_resample_fits(self, n):
         return 0
+
+    # the tile-exponent kernels (include/genjax_b200.h section 1c) always run as written (tests/simt_kernels.py)
+    def gjb_te_masses(self, logw, n, cdf, recs, stream):
+        import simt_kernels
+
+        return simt_kernels.core().s_te_masses(C.c_void_p(logw), C.c_int64(n), C.c_void_p(cdf), C.c_void_p(recs))
+
+    def gjb_te_resample(self, a_ref, stream):
+        import simt_kernels
+
+        return simt_kernels.core().s_te_resample(a_ref)
 
     def gjb_wmax_reset(self, wmax, stream):
         _arr(wmax, 1, C.c_uint32, np.uint32)[0] = 0x007FFFFF
@@ -807,6 +836,7 @@ class _EmulatedCompiledModel:
             self.lib.source = source
         if self.lib is None:
             self.lib = EmulatedModelLib(ir, chain)
+        self.lib.pf_obs = pf_obs
         self.path = None
         self.info = json.loads(self.lib.gjb_model_info().decode())
 

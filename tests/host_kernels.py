@@ -22,6 +22,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 _CACHE: dict = {}
 
+
+def _deps_digest() -> str:
+    """Headers the host build includes: a cached library is stale when any of them changed."""
+    h = hashlib.sha256()
+    import glob
+
+    for f in sorted(glob.glob(os.path.join(ROOT, "genjax_b200", "csrc", "*.cuh")) + glob.glob(os.path.join(HERE, "host_shim", "*.h"))
+                    + [os.path.join(ROOT, "include", "genjax_b200.h")]):
+        h.update(open(f, "rb").read())
+    return h.hexdigest() + os.environ.get("GJB_SIMT_FLAGS", "")
+
 _DRIVER = r'''
 extern "C" int host_model_launch(const gjb_model_args* a) {
   gridDim.x = 1; gridDim.y = 1; gridDim.z = 1; blockDim.x = 1; blockIdx.x = 0;
@@ -51,7 +62,7 @@ def is_host_runnable(source: str) -> bool:
 
 def build(source: str):
     """ctypes library of the host build of one generated model source (cached by content)."""
-    digest = hashlib.sha256(source.encode()).hexdigest()[:20]
+    digest = hashlib.sha256((source + _deps_digest()).encode()).hexdigest()[:20]
     lib = _CACHE.get(digest)
     if lib is not None:
         return lib

@@ -20,6 +20,8 @@
 
 struct uint4 { uint32_t x, y, z, w; };
 struct int4 { int32_t x, y, z, w; };
+struct ulonglong2 { unsigned long long x, y; };
+static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct dim3 { unsigned x, y, z; };
@@ -32,6 +34,9 @@ static dim3 threadIdx, blockIdx, blockDim, gridDim;
 // IEEE round-to-nearest single operations: compile this TU with -ffp-contract=off so that they stay unfused
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }  // glibc fmaf: correctly rounded
+static inline int __float2int_ru(float x) { return (int)ceilf(x); }
+static inline int __float2int_rd(float x) { return (int)floorf(x); }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
@@ -46,6 +51,7 @@ static inline void sincospif(float x, float* s, float* c) { *s = sinf(3.14159265
 template <class T> static inline T __shfl_up_sync(unsigned, T v, int) { return v; }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
 template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+static inline int __reduce_max_sync(unsigned, int v) { return v; }
 static inline void __syncthreads() {}
 static inline int __syncthreads_or(int p) { return p; }
 static inline void __threadfence() {}
@@ -56,6 +62,7 @@ template <class T> static inline T __ldcg(const T* p) { return *p; }
 template <class T> static inline void __stcg(T* p, T v) { *p = v; }
 template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p += v; return o; }
 template <class T> static inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <class T> static inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }

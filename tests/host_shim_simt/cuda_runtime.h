@@ -30,6 +30,8 @@
 
 struct uint4 { uint32_t x, y, z, w; };
 struct int4 { int32_t x, y, z, w; };
+struct ulonglong2 { unsigned long long x, y; };
+static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3() {} dim3(unsigned a, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
@@ -83,6 +85,9 @@ static inline T exchange(T v, int src_lane) {  // every lane of the warp publish
 
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }  // glibc fmaf: correctly rounded
+static inline int __float2int_ru(float x) { return (int)ceilf(x); }
+static inline int __float2int_rd(float x) { return (int)floorf(x); }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
@@ -99,6 +104,10 @@ template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) { const 
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) { const int l = threadIdx.x & 31; return simt::exchange(v, l + d < 32 ? l + d : l); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return simt::exchange(v, (int)((threadIdx.x & 31) ^ (unsigned)m)); }
 template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return simt::exchange(v, src & 31); }
+static inline int __reduce_max_sync(unsigned, int v) {
+  for (int o = 16; o > 0; o >>= 1) { const int t = simt::exchange(v, (int)((threadIdx.x & 31) ^ (unsigned)o)); v = t > v ? t : v; }
+  return v;
+}
 static inline void __syncthreads() { simt::block_barrier.arrive(); }
 static inline int __syncthreads_or(int p) { return simt::block_barrier.arrive(p != 0); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { simt::warp_barrier[threadIdx.x >> 5].arrive(); }
@@ -112,6 +121,11 @@ template <class T> static inline T atomicAdd(T* p, T v) { return __atomic_fetch_
 template <class T> static inline T atomicMax(T* p, T v) {
   T o = __atomic_load_n(p, __ATOMIC_SEQ_CST);
   while (o < v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return o;
+}
+template <class T> static inline T atomicMin(T* p, T v) {
+  T o = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (o > v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
   return o;
 }
 static inline int min(int a, int b) { return a < b ? a : b; }

@@ -19,6 +19,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 _CACHE: dict = {}
 
+
+def _deps_digest() -> str:
+    """Headers the host build includes: a cached library is stale when any of them changed."""
+    h = hashlib.sha256()
+    import glob
+
+    for f in sorted(glob.glob(os.path.join(ROOT, "genjax_b200", "csrc", "*.cuh")) + glob.glob(os.path.join(HERE, "host_shim_simt", "*.h"))
+                    + [os.path.join(ROOT, "include", "genjax_b200.h")]):
+        h.update(open(f, "rb").read())
+    return h.hexdigest() + os.environ.get("GJB_SIMT_FLAGS", "")
+
 CORE_DRIVERS = r'''
 extern "C" {
 int s_weight_max(const float* logw, int64_t n, uint32_t* wmax, int grid) {
@@ -62,6 +73,17 @@ int s_normal_fill(uint32_t k0, uint32_t k1, uint64_t off, uint32_t site, int64_t
   simt::launch(4, 256, [=] { gjb::normal_fill_kernel(k0, k1, off, site, n, d, out); });
   return 0;
 }
+int s_te_masses(const float* logw, int64_t n, uint64_t* cdf, gjb_tile_rec* recs) {
+  const int tiles = (int)((n + gjb::kTeTile - 1) / gjb::kTeTile);
+  simt::launch(tiles, gjb::kThreads, [=] { gjb::te_mass_kernel(logw, n, cdf, recs); });
+  return 0;
+}
+int s_te_resample(const gjb_te_resample_args* a) {
+  const gjb_te_resample_args A = *a;
+  const int ctas = (int)((A.out_n + gjb::kTeTile - 1) / gjb::kTeTile);
+  simt::launch(ctas, gjb::kThreads, [=] { gjb::te_resample_kernel(A); });
+  return 0;
+}
 int s_gather_rows(const uint32_t* src, const int32_t* anc, uint32_t* dst, int64_t n_out, int w, int grid) {
   simt::launch(grid, 256, [=] { gjb::gather_rows_kernel<uint32_t>(src, anc, dst, n_out, w); });
   return 0;
@@ -71,7 +93,7 @@ int s_gather_rows(const uint32_t* src, const int32_t* anc, uint32_t* dst, int64_
 
 
 def _compile(text: str, tag: str):
-    digest = hashlib.sha256(text.encode()).hexdigest()[:20]
+    digest = hashlib.sha256((text + _deps_digest()).encode()).hexdigest()[:20]
     lib = _CACHE.get(digest)
     if lib is not None:
         return lib
@@ -81,7 +103,7 @@ def _compile(text: str, tag: str):
     if not os.path.exists(so):
         with open(cpp, "w") as f:
             f.write(text)
-        cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-pthread",
+        cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-pthread", *os.environ.get("GJB_SIMT_FLAGS", "").split(),
                f"-I{HERE}/host_shim_simt", f"-I{ROOT}/genjax_b200/csrc", f"-I{ROOT}/include", "-o", so + ".tmp", cpp]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -113,6 +135,14 @@ extern "C" int s_model_launch_pull(const gjb_model_args* a) {
   return 0;
 }
 '''
+STEP_DRIVER = r'''
+extern "C" int s_pf_step(const gjb_step_args* a) {
+  const gjb_step_args A = *a;
+  const int tiles = (int)((A.n + gjb::kTeTile - 1) / gjb::kTeTile);
+  simt::launch(tiles, kThreads, [=] { pf_step_kernel(A); });
+  return 0;
+}
+'''
 PF_DRIVER = r'''
 extern "C" int s_pf_run(const gjb_pf_args* q) {  // the persistent cooperative filter as a grid of ONE block
   const gjb_pf_args Q = *q;
@@ -139,6 +169,8 @@ def model(source: str):
         text += PULL_DRIVER
     if "pf_kernel(" in body:
         text += PF_DRIVER
+    if "pf_step_kernel(" in body:
+        text += STEP_DRIVER
     for kind in ("mh", "hmc"):
         if f"{kind}_chain_kernel(" in body:
             text += CHAIN_DRIVER % {"kind": kind}

@@ -113,3 +113,56 @@ def test_multinomial_and_gather_kernels(core):
     dst = np.zeros((n, 3), dtype=np.uint32)
     core.s_gather_rows(_p(src), _p(anc), _p(dst), C.c_int64(n), C.c_int(3), C.c_int(4))
     assert np.array_equal(dst, src[anc])
+
+
+@pytest.mark.parametrize("n,scale,kind", [(1, 1.0, "n"), (7, 1.0, "n"), (2048, 1.0, "n"), (2049, 2.0, "n"), (6000, 0.3, "n"),
+                                           (9000, 30.0, "n"), (12_345, 300.0, "n"), (5000, 1.0, "one"), (5000, 1.0, "dead"),
+                                           (7000, 1.0, "deadtile"), (4100, 1.0, "nan")])
+def test_tile_exponent_masses_and_pull_resampling(core, n, scale, kind):
+    """te_mass_kernel (te_publish) and te_resample_kernel (te_pull): within-tile CDFs, tile records, ancestors and the
+    log-mean-exp terms of the tile-exponent pipeline, bit for bit against oracle/smc.py -- balanced and degenerate
+    weights, dead particles, a dead tile, NaN / +inf weights, partial last tile, output windows."""
+    r = np.random.default_rng(n)
+    lw = (r.standard_normal(n) * scale - 3.0).astype(F32)
+    if kind == "one":
+        lw[:] = -np.inf
+        lw[n - 3] = 1.5
+    elif kind == "dead":
+        lw[:] = -np.inf
+    elif kind == "deadtile":
+        lw[2048:4096] = -np.inf
+        lw[5] = np.nan
+    elif kind == "nan":
+        lw[::7] = np.nan
+        lw[3] = np.inf
+    tiles = (n + 2047) // 2048
+    cdf = np.zeros(tiles * 2048, dtype=np.uint64)
+    recs = np.zeros(tiles, dtype=[("mass", np.uint64), ("e", np.int32), ("pad", np.int32)])
+    core.s_te_masses(_p(lw), C.c_int64(n), _p(cdf), _p(recs))
+    q, e_p = smc.te_tile_masses(lw)
+    qp = np.zeros(tiles * 2048, dtype=np.uint64)
+    qp[:n] = q
+    want_cdf = np.cumsum(qp.reshape(tiles, 2048), axis=1, dtype=np.uint64).reshape(-1)
+    assert np.array_equal(cdf, want_cdf)
+    assert np.array_equal(recs["mass"], want_cdf.reshape(tiles, 2048)[:, -1])
+    live = recs["mass"] > 0
+    assert np.array_equal(recs["e"][live], e_p[live].astype(np.int32))
+    key = rng.Key((0x1234 + n, 77), 5)
+    kd = np.array([key.words[0], key.words[1], key.index & 0xFFFFFFFF, key.index >> 32], dtype=np.uint32)
+    for out_lo, out_n in ((0, n), (n // 3, n - n // 3 - n // 5)):
+        if out_n <= 0:
+            continue
+        anc = np.full(out_n, -7, dtype=np.int32)
+        lse = np.zeros(3, dtype=np.float64)
+        A = cabi.TeResampleArgs()
+        A.cdf, A.recs, A.n_tiles_total, A.n_total = cdf.ctypes.data, recs.ctypes.data, tiles, n
+        A.out_lo, A.out_n, A.key_dev, A.ancestors, A.lse_out = out_lo, out_n, kd.ctypes.data, anc.ctypes.data, lse.ctypes.data
+        core.s_te_resample(C.byref(A))
+        want = smc.resample_systematic_te(lw, key, out_lo, out_n)
+        assert np.array_equal(anc, want), (np.flatnonzero(anc != want)[:5], anc[:8], want[:8])
+        lme = smc.te_log_mean_exp(lw)
+        if np.isfinite(lme):
+            assert lse[2] == pytest.approx(lme, abs=1e-12, rel=1e-13)
+            assert lse[1] == float(smc.te_cdf(lw)[1])
+        else:
+            assert lse[1] == 0.0 and lse[2] == -np.inf
