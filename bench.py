@@ -163,6 +163,30 @@ def synth_obs(T, d, seed=0):
     return ys if d > 1 else ys[:, 0]
 
 
+def workload_string(n, T, d):
+    """config.workload: the SAME string on both arms (the driver compares them)."""
+    return (f"linear-Gaussian SSM bootstrap SMC (BASELINE configs[1]): T={T}, N={n} particles/GPU, d={d}, "
+            "systematic resampling every step")
+
+
+def kalman_logz(ys, d):
+    """Exact log p(y_1:T) of the (diagonal) linear-Gaussian model by the Kalman filter, float64 -- the ground truth the
+    filter's estimate is checked against inside this script (accept within 4 sigma)."""
+    from genjax_b200.workloads import LG_A, LG_C, LG_Q, LG_R
+
+    ys = np.asarray(ys, dtype=np.float64).reshape(len(ys), -1)
+    total = 0.0
+    for j in range(ys.shape[1]):
+        m, p = 0.0, 1.0
+        for y in ys[:, j]:
+            m, p = LG_A * m, LG_A * LG_A * p + LG_Q * LG_Q
+            s = LG_C * LG_C * p + LG_R * LG_R
+            total += -0.5 * (np.log(2 * np.pi * s) + (y - LG_C * m) ** 2 / s)
+            k = p * LG_C / s
+            m, p = m + k * (y - LG_C * m), (1 - k * LG_C) * p
+    return float(total)
+
+
 # ---------------------------------------------------------------- CPU legs
 
 
@@ -228,24 +252,26 @@ def cpu_port_rate(n, T_sample, d, seed=314159, threads=None):
     return n * T_sample / dt, dt, logz, threads
 
 
-def cpu_c_port_rate(n, T_sample, d, seed=314159):
-    """particle-steps/s of the C / OpenMP restatement of the same oracle filter (oracle/c/pf_port.c; checked against the
-    NumPy oracle bit for bit in tests/test_oracle_c_port.py) on all host threads; None when gcc is unavailable."""
+def cpu_c_port_rate(n, T_sample, d, seed=314159, fast=True):
+    """particle-steps/s of the C / OpenMP restatement of the same filter on all host threads; None when gcc is
+    unavailable.  fast=True (the CPU arm): oracle/c/pf_port_fast.c, written for speed (one Philox block per quad, float
+    libm, -O3 -march=native, gather fused into the resampling); fast=False: oracle/c/pf_port.c, the bit-compatible
+    restatement the tests use (tests/test_oracle_c_port.py), several times slower by construction."""
     from genjax_b200.core.key import key as pkey, pf_key_table
     from genjax_b200.workloads import LG_A, LG_C, LG_Q, LG_R
     from oracle import cport
 
-    if cport.lib() is None:
+    if (cport.fast_lib() if fast else cport.lib()) is None:
         return None
-    cport.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
+    threads = os.cpu_count() or 1  # torchrun exports OMP_NUM_THREADS=1: ask for the cores explicitly
     ys = synth_obs(T_sample, d)
     g = np.random.default_rng(1)
     x0 = g.standard_normal(n if d == 1 else (n, d)).astype(np.float32)
     tab = pf_key_table(pkey(seed), T_sample)
     t0 = time.perf_counter()
-    out = cport.pf_lgssm(x0, ys, LG_A, LG_Q, LG_C, LG_R, tab)
+    out = cport.pf_lgssm(x0, ys, LG_A, LG_Q, LG_C, LG_R, tab, fast=fast, threads_=threads)
     dt = time.perf_counter() - t0
-    return n * T_sample / dt, dt, float(out["logz_inc"].sum()), cport.threads()
+    return n * T_sample / dt, dt, float(out["logz_inc"].sum()), threads
 
 
 def genjax_reference_rate(args):
@@ -280,7 +306,7 @@ def run_reference(args):
             "impl": "reference", "metric": "particle-steps/sec", "value": real["value"], "unit": "particle-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * real["seconds"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"linear-Gaussian SSM bootstrap SMC, N={n} particles, d={d}", "T_full": args.T},
+            "config": {"workload": workload_string(n, args.T, d), "particles_per_gpu": n, "T": args.T, "d": d},
             "cpu_baseline": {"value": real["value"], "unit": "particle-steps/s", "cores": real["cores"], "kind": "reference",
                              "sample": f"whole {args.T}-step filter, GenJAX {real['genjax']} on jax {real['jax']} [cpu], "
                                        "baseline/run_genjax_cpu.py"},
@@ -292,7 +318,8 @@ def run_reference(args):
     use_c = cpu_c_port_rate(min(n, 4096), 1, d) is not None
     T_sample = args.T if use_c else 4  # the C port runs the whole T-step filter per timed step; NumPy a 4-step sample
     port = cpu_c_port_rate if use_c else cpu_port_rate
-    impl_name = "C/OpenMP restatement of the oracle filter (oracle/c/pf_port.c)" if use_c else "NumPy float32 oracle port"
+    impl_name = ("performance C/OpenMP restatement of the filter (oracle/c/pf_port_fast.c: one Philox block per quad, float libm, "
+                 "-O3 -march=native)" if use_c else "NumPy float32 oracle port")
     for _ in range(min(args.warmup, 1)):
         port(n, 1, d)
     rates, times = [], []
@@ -317,7 +344,7 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"linear-Gaussian SSM bootstrap SMC, N={n} particles, d={d}", "T_full": args.T,
+        "config": {"workload": workload_string(n, args.T, d), "particles_per_gpu": n, "T": args.T, "d": d,
                    "sample": f"{T_sample} of {args.T} filter steps per timed step"},
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": threads, "kind": "port",
                          "sample": f"{T_sample} filter steps x {n} particles per timed step, {impl_name}, {threads} threads "
@@ -358,6 +385,7 @@ def run_ours(args):
     ys_host = torch.from_numpy(ys_np).pin_memory()
     x0_dev = x0_host.to(device)
     ys_dev = ys_host.to(device)
+    state_host = torch.empty_like(x0_host).pin_memory()
     if d == 1:
         model, shared = lgssm_step, ()
     else:
@@ -399,6 +427,7 @@ def run_ours(args):
         key = gj.fold_in(gj.key(314159 + (0 if global_resample else rank)), step_idx)
         if e2e:
             res = pf.run(key, x0_host.to(device, non_blocking=True), obs_host, shared_args=shared)
+            state_host.copy_(res.state[0], non_blocking=True)  # the filter's product: final particle cloud, pinned D2H
             return combine(res.log_marginal_likelihood).item()  # (all-reduce of the shard terms +) D2H read + sync
         res = pf.run(key, x0_dev, obs_dev, shared_args=shared)
         res.combined = combine(res.log_marginal_likelihood)
@@ -608,15 +637,34 @@ def run_ours(args):
     if not args.no_cpu_baseline and world == 1:  # the CPU arm is timed at N = 1 only
         T_s = 20 if d == 1 else 2
         c_res = cpu_c_port_rate(n, T, d)
+        exact_res = None
         if c_res is not None:
-            rate, dt, _, thr = c_res
-            what = f"all {T} filter steps x {n} particles in {dt:.1f} s, C/OpenMP restatement of the oracle filter (oracle/c/pf_port.c)"
+            cpu_c_port_rate(n, 2, d)  # (first touch of the buffers / thread pool outside the timed sample)
+            c_res = cpu_c_port_rate(n, T, d)
+            rate, dt, cpu_logz, thr = c_res
+            what = (f"all {T} filter steps x {n} particles in {dt:.2f} s, performance C/OpenMP restatement of the filter "
+                    "(oracle/c/pf_port_fast.c: one Philox block per quad, float libm, -O3 -march=native)")
+            exact_res = cpu_c_port_rate(n, max(T // 5, 1), d, fast=False)
         else:
             rate, dt, _, thr = cpu_port_rate(n, T_s, d)
             what = f"{T_s} of {T} filter steps x {n} particles in {dt:.1f} s, NumPy float32 oracle port"
         cpu = {"value": rate, "unit": "particle-steps/s", "cores": thr, "kind": "port",
                "sample": f"{what}, {thr} threads ({os.cpu_count()} cores visible); GenJAX jax[cpu] itself is not installable here"}
+        if exact_res is not None:
+            cpu["bit_compatible_port"] = {"value": exact_res[0], "unit": "particle-steps/s", "cores": exact_res[3],
+                                          "what": "oracle/c/pf_port.c, the operation-for-operation restatement the parity tests use "
+                                                  f"({max(T // 5, 1)} filter steps)"}
 
+    # the estimate of the last timed run against the exact Kalman log-likelihood (sd of one d = 1 run measured at N = 2^18,
+    # T = 50: 0.029, tests/test_pf_gpu.py; variance scales with T / N; R island estimates average)
+    logz_exact = kalman_logz(ys_np, d)
+    logz_sigma = 0.029 * float(np.sqrt((T / 50.0) * ((1 << 18) / float(n)) / world)) if d == 1 else None
+    if logz_sigma is None:
+        logz_check = "not checked (d > 1 with r = 0.5 is a degenerate bootstrap filter: see --obs-sd)"
+    else:
+        ok = abs(logz - logz_exact) <= 4 * logz_sigma and abs(logz_e2e - logz_exact) <= 4 * logz_sigma
+        logz_check = "pass: |logZ - exact| <= 4 sigma (device-resident and e2e runs)" if ok else \
+            f"FAIL: logZ {logz} / {logz_e2e} vs exact {logz_exact}, 4 sigma = {4 * logz_sigma}"
     h2d = x0_host.numel() * 4 + ys_host.numel() * 4 + T * 8 * 4
     line = {
         "metric": "particle-steps/sec",
@@ -632,8 +680,7 @@ def run_ours(args):
         "dtype": "f32",
         "data": "synthetic",
         "config": {
-            "workload": f"linear-Gaussian SSM bootstrap SMC (BASELINE configs[1]): T={T}, N={n} particles/GPU, d={d}, "
-                        "systematic resampling every step",
+            "workload": workload_string(n, T, d),
             "particles_per_gpu": n, "T": T, "d": d,
             "l2": "flushed between timed steps (256 MiB write)",
             "mode": "graph (3 launches/step, cross-rank hand-offs fused into the kernels)" if global_resample else args.mode,
@@ -643,11 +690,11 @@ def run_ours(args):
                           "differ by key), the shard log-marginal-likelihood terms are combined by one NCCL all-reduce (max + sum-exp "
                           "on 8 bytes) per run, inside the timed region; weak scaling. --multi-gpu global times the "
                           "global-resampling filter instead"),
-            "logZ_last": logz,
+            "logZ_last": logz, "logZ_exact_kalman": logz_exact, "logZ_sigma": logz_sigma, "logZ_check": logz_check,
             "reference_max": args.reference_max, "single_pass": bool(args.single_pass),
         },
-        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
-                "logZ_last": logz_e2e},
+        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 + state_host.numel() * 4,
+                "logZ_last": logz_e2e, "d2h": "log-marginal-likelihood estimate (8 B) + the final particle state"},
         "gpu_launches": plan.launches_per_run() * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
@@ -656,6 +703,8 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if logz_check.startswith("FAIL"):
+        raise SystemExit("bench.py: the filter's log-marginal-likelihood estimate is outside 4 sigma of the exact value: " + logz_check)
 
 
 def main():

@@ -556,8 +556,8 @@ __global__ void __launch_bounds__(kThreads) te_resample_kernel(const __grid_cons
                                 (uint64_t)__ldg(A.key_dev + 2) | ((uint64_t)__ldg(A.key_dev + 3) << 32));
   int32_t anc[kTeItems];
   int E;
-  const uint64_t S = A.cdf_peers ? te_pull<true>(A.recs, A.n_tiles_total, A.cdf, A.cdf_peers, A.n_total, u0, w_lo, w_n, sm, anc, &E)
-                                 : te_pull<false>(A.recs, A.n_tiles_total, A.cdf, nullptr, A.n_total, u0, w_lo, w_n, sm, anc, &E);
+  const uint64_t S = A.cdf_peers ? te_pull<true, false>(A.recs, A.n_tiles_total, A.cdf, A.cdf_peers, A.n_total, u0, w_lo, w_n, sm, anc, &E)
+                                 : te_pull<false, false>(A.recs, A.n_tiles_total, A.cdf, nullptr, A.n_total, u0, w_lo, w_n, sm, anc, &E);
   if (blockIdx.x == 0 && threadIdx.x == 0 && A.lse_out) te_write_lse(A.lse_out, E, S, A.n_total);
   int32_t* out = A.ancestors + (int64_t)blockIdx.x * kTeTile + threadIdx.x * kTeItems;
   const int j0 = threadIdx.x * kTeItems;

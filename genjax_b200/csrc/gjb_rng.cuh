@@ -42,19 +42,53 @@ __device__ __forceinline__ Lane make_lane(uint32_t k0, uint32_t k1, uint64_t idx
   return l;
 }
 
-// uint32 -> float in (0,1): ((bits >> 9) + 0.5) * 2^-23, exact in fp32.
+// uint32 -> float in (0,1): ((bits >> 9) + 0.5) * 2^-23, exact in fp32.  Formed without the conversion pipe:
+// as_float(0x3F800000 | k) = 1 + k 2^-23, minus (1 - 2^-24) -- an exact subtraction giving the same value.
 __device__ __forceinline__ float u01(uint32_t bits) {
-  return ((float)(bits >> 9) + 0.5f) * 1.1920928955078125e-07f;
+  return __fadd_rn(__uint_as_float(0x3F800000u | (bits >> 9)), -0x1.fffffep-1f);
 }
 
-// Two N(0,1) from two words: r = sqrt(-2 log u1); (s,c) = sincospi(2 u2).
+// Two N(0,1) from two words: r = sqrt(-2 ln u1), (z0, z1) = r (cos, sin)(2 pi u2), on fp32 polynomials evaluated with
+// correctly rounded FMAs -- every line is ONE IEEE operation restated in oracle/rng.py box_muller, so the sampled normals
+// are bit-exact against the CPU oracle (coefficients: scratch/fit_box_muller.py; |error| of each kernel < 3e-8).
 __device__ __forceinline__ float2 box_muller(uint32_t b0, uint32_t b1) {
   const float u1 = u01(b0);
   const float u2 = u01(b1);
-  const float r = sqrtf(-2.0f * logf(u1));
-  float s, c;
-  sincospif(2.0f * u2, &s, &c);
-  return make_float2(r * c, r * s);
+  // -2 ln u1: u1 = 2^e m, m in [sqrt(1/2), sqrt(2)), f = m - 1 (exact); -2 log1p(f) = -2 f + f^2 R(f)
+  const int tb = __float_as_int(u1) - 0x3F3504F3;
+  const int e = tb >> 23;
+  const float f = __fadd_rn(__int_as_float((tb & 0x007FFFFF) + 0x3F3504F3), -1.0f);
+  const float ef = __fadd_rn(__int_as_float(e + 0x4B400000), -12582912.0f);  // (float)e without the conversion pipe
+  const float f2 = __fmul_rn(f, f);
+  float R = 0x1.4237fep-3f;
+  R = __fmaf_rn(R, f, -0x1.0696e4p-2f);
+  R = __fmaf_rn(R, f, 0x1.0c524cp-2f);
+  R = __fmaf_rn(R, f, -0x1.22973ap-2f);
+  R = __fmaf_rn(R, f, 0x1.548882p-2f);
+  R = __fmaf_rn(R, f, -0x1.99a3ecp-2f);
+  R = __fmaf_rn(R, f, 0x1.000206p-1f);
+  R = __fmaf_rn(R, f, -0x1.55554ep-1f);
+  R = __fmaf_rn(R, f, 0x1.fffffep-1f);
+  const float L = __fmaf_rn(ef, -0x1.62e43p+0f, __fmaf_rn(f2, R, __fmul_rn(-2.0f, f)));
+  const float r = __fsqrt_rn(L);
+  // 2 pi u2 = j pi/2 + 2 pi rr: j = rint(4 u2) sits in the low mantissa bits of tm, rr in [-1/8, 1/8] is exact
+  const float tm = __fmaf_rn(u2, 4.0f, 12582912.0f);
+  const int q = __float_as_int(tm) & 3;
+  const float rr = __fmaf_rn(__fadd_rn(tm, -12582912.0f), -0.25f, u2);
+  const float z = __fmul_rn(rr, rr);
+  float ps = __fmaf_rn(z, -0x1.2d9b7cp+6f, 0x1.465ec4p+6f);
+  ps = __fmaf_rn(z, ps, -0x1.4abbbap+5f);
+  ps = __fmaf_rn(z, ps, 0x1.921fb6p+2f);
+  const float sn = __fmul_rn(rr, ps);
+  float pc = __fmaf_rn(z, 0x1.db6578p+5f, -0x1.55cb9ap+6f);
+  pc = __fmaf_rn(z, pc, 0x1.03c1eap+6f);
+  pc = __fmaf_rn(z, pc, -0x1.3bd3ccp+4f);
+  const float cs = __fmaf_rn(z, pc, 1.0f);
+  const bool swap = (q & 1) != 0;
+  const float a = swap ? sn : cs, b = swap ? cs : sn;
+  const float ca = __int_as_float(__float_as_int(a) ^ (((q + 1) & 2) << 30));  // quadrants 1, 2: cos < 0
+  const float sb = __int_as_float(__float_as_int(b) ^ ((q & 2) << 30));        // quadrants 2, 3: sin < 0
+  return make_float2(__fmul_rn(r, ca), __fmul_rn(r, sb));
 }
 
 __device__ __forceinline__ float normal1(const Lane& l, uint32_t site, uint32_t chunk = 0) {

@@ -5,7 +5,7 @@
 // reference (inference/smc.py:96-109; docs/cookbook/inactive/inference/mapping_tutorial.ipynb cell 37).
 //
 //   producer (te_publish), per tile of 2048 particles -- block-level synchronisation only:
-//     t_i = fl32(lw_i * log2e);  e = ceil(max_tile t);  q_i = round(2^36 * 2^(t_i - e));
+//     t_i = fl32(lw_i * log2e);  e = ceil(max_tile t);  q_i = rint(2^36 * 2^(t_i - e))  (te_q);
 //     cdf[i] = inclusive prefix of q inside the tile (uint64);  rec = {cdf[last], e}
 //   consumer (te_pull), per CTA = per window of <= 2048 offspring slots:
 //     E = max e_p;  s_p = min(E - e_p, 63);  P = inclusive prefix of (mass_p >> s_p);  S = P_last
@@ -31,15 +31,26 @@ struct TeSmem {
   uint64_t pre[kTeMaxTiles];               // inclusive prefix of the aligned tile masses
   __align__(16) int32_t heads[kTeTile];    // window slots: parent id + 1 at first slots, then ancestors, then weights
   uint8_t shf[kTeMaxTiles];                // s_p
-  uint64_t red[kThreads / 32];
-  int32_t ired[kThreads / 32];
-  float fred[kThreads / 32];
+  __align__(16) uint64_t red[kThreads / 32];
+  __align__(16) int32_t ired[kThreads / 32];
+  __align__(16) float fred[kThreads / 32];
   int32_t p_lo, p_hi;
 };
 
-// uint64(fl32(2^36 * 2^frac)), frac in [0, 1): fp32 FMA Horner (oracle/smc.py te_exp2_m)
-__device__ __forceinline__ uint64_t te_exp2_m(float frac) {
-  const float g = __fadd_rn(frac, -0.5f);
+// t = fl32(lw * log2e) clamped to +-2^20, or -inf when lw is not finite (NaN, +-inf: mass 0)
+__device__ __forceinline__ float te_t(float lw) {
+  const float t = __fmul_rn(lw, 0x1.715476p+0f);
+  return (fabsf(t) < INFINITY) ? fminf(fmaxf(t, -1048576.0f), 1048576.0f) : -INFINITY;
+}
+
+// Mass of a particle with scaled log-weight t (te_t) relative to the tile exponent e >= rint(t), kc = 163 - e - 0x4B400000:
+// rint(2^g * 2^(36 - (e - r))), r = rint(t) taken from the low mantissa bits of t + 1.5 * 2^23, g = t - r, 2^g by fp32 FMA
+// Horner (Taylor, degree 7).  No conversion-pipe instruction except the final float -> uint64.  oracle/smc.py te_q.
+__device__ __forceinline__ uint64_t te_q(float t, int kc) {
+  const bool ok = t > -INFINITY;
+  const float tv = ok ? t : 0.0f;
+  const float tm = __fadd_rn(tv, 12582912.0f);
+  const float g = __fadd_rn(tv, -__fadd_rn(tm, -12582912.0f));
   float p = 0x1.ffcbfcp-17f;               // ln2^7/7!
   p = __fmaf_rn(p, g, 0x1.430912p-13f);    // ln2^6/6!
   p = __fmaf_rn(p, g, 0x1.5d87fep-10f);    // ln2^5/5!
@@ -48,23 +59,9 @@ __device__ __forceinline__ uint64_t te_exp2_m(float frac) {
   p = __fmaf_rn(p, g, 0x1.ebfbep-3f);      // ln2^2/2!
   p = __fmaf_rn(p, g, 0x1.62e43p-1f);      // ln2
   p = __fmaf_rn(p, g, 1.0f);
-  p = __fmul_rn(p, 0x1.6a09e6p+0f);        // sqrt(2)
-  return (uint64_t)__fmul_rn(p, 68719476736.0f);  // 2^36; p in [1, 2] so the product is an exact integer
-}
-
-// t = fl32(lw * log2e) clamped to +-2^29, or -inf when lw is not finite (NaN, +-inf: mass 0)
-__device__ __forceinline__ float te_t(float lw) {
-  const float t = __fmul_rn(lw, 0x1.715476p+0f);
-  return (fabsf(t) < INFINITY) ? fminf(fmaxf(t, -536870912.0f), 536870912.0f) : -INFINITY;
-}
-
-// mass of a particle with scaled log-weight t (te_t) relative to the tile exponent e >= t
-__device__ __forceinline__ uint64_t te_q(float t, int e) {
-  if (!(t > -INFINITY)) return 0ull;
-  const float nf = floorf(t);
-  const uint64_t m = te_exp2_m(__fadd_rn(t, -nf));
-  const int sh = min(e - (int)nf, 63);
-  return sh > 0 ? ((m + (1ull << (sh - 1))) >> sh) : m;
+  const int ex = max(__float_as_int(tm) + kc, 63);  // biased exponent of 2^(36 - (e - r)), floor 2^-64 (mass 0)
+  const float scale = ok ? __int_as_float(ex << 23) : 0.0f;
+  return __float2ull_rn(__fmul_rn(p, scale));
 }
 
 // Producer: the 8 consecutive weights of this thread (slot base tid * 8 of the tile; lw = -inf past the end) ->
@@ -79,14 +76,16 @@ __device__ __forceinline__ void te_publish(const float (&lw)[kTeItems], uint64_t
   tm = warp_max(tm);
   if (lane == 0) sm.fred[warp] = tm;
   __syncthreads();
-  tm = sm.fred[0];
-#pragma unroll
-  for (int w = 1; w < kThreads / 32; ++w) tm = fmaxf(tm, sm.fred[w]);
+  {
+    const float4 a = *reinterpret_cast<const float4*>(sm.fred), b = *reinterpret_cast<const float4*>(sm.fred + 4);
+    tm = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+  }
   const int e = tm > -INFINITY ? __float2int_ru(tm) : GJB_TE_E_NONE;
+  const int kc = tm > -INFINITY ? 163 - e - 0x4B400000 : 0;
   uint64_t c[kTeItems];
   uint64_t run = 0;
 #pragma unroll
-  for (int k = 0; k < kTeItems; ++k) { run += te_q(t[k], e); c[k] = run; }
+  for (int k = 0; k < kTeItems; ++k) { run += te_q(t[k], kc); c[k] = run; }
   uint64_t inc = run;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -97,7 +96,11 @@ __device__ __forceinline__ void te_publish(const float (&lw)[kTeItems], uint64_t
   __syncthreads();
   uint64_t excl = inc - run;
 #pragma unroll
-  for (int w = 0; w < kThreads / 32; ++w) if (w < warp) excl += sm.red[w];
+  for (int w = 0; w < kThreads / 32; w += 2) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(sm.red + w);
+    if (w < warp) excl += v.x;
+    if (w + 1 < warp) excl += v.y;
+  }
   ulonglong2* dst = reinterpret_cast<ulonglong2*>(cdf_tile + tid * kTeItems);
 #pragma unroll
   for (int k = 0; k < kTeItems; k += 2) dst[k >> 1] = make_ulonglong2(c[k] + excl, c[k + 1] + excl);
@@ -118,23 +121,59 @@ __device__ __forceinline__ gjb_tile_rec te_ld_rec(const gjb_tile_rec* p) {
   return r;
 }
 
+// The tile records of tiles 2 tid and 2 tid + 1, loaded EARLY (n_tiles <= 512: the common single-device case): the
+// caller issues these loads, does unrelated ALU work (the step kernel draws its random numbers), and only then enters
+// te_pull, which finds the records in registers instead of re-reading them.  Tiles past n_tiles read as empty.
+struct TeRecs2 {
+  gjb_tile_rec r[2];
+};
+template <bool kCg>
+__device__ __forceinline__ TeRecs2 te_load_recs2(const gjb_tile_rec* __restrict__ recs, int n_tiles) {
+  TeRecs2 o;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int t = 2 * threadIdx.x + k;
+    if (t < n_tiles) {
+      o.r[k] = te_ld_rec<kCg>(recs + t);
+    } else {
+      o.r[k].mass = 0; o.r[k].e = GJB_TE_E_NONE; o.r[k].reserved = 0;
+    }
+  }
+  return o;
+}
+
+// the 8 within-tile CDF values of this thread's parents in tile `ct` (+ the value just before them)
+template <bool kCg>
+__device__ __forceinline__ void te_ld_row(const uint64_t* __restrict__ ct, uint64_t (&c)[kTeItems], uint64_t& c_prev) {
+  c_prev = threadIdx.x ? (kCg ? __ldcg(ct - 1) : __ldg(ct - 1)) : 0ull;
+  const ulonglong2* c2 = reinterpret_cast<const ulonglong2*>(ct);
+#pragma unroll
+  for (int k = 0; k < kTeItems / 2; ++k) {
+    const ulonglong2 v = kCg ? __ldcg(c2 + k) : __ldg(c2 + k);
+    c[2 * k] = v.x; c[2 * k + 1] = v.y;
+  }
+}
+
 // Consumer: global parent ids of the offspring slots [w_lo, w_lo + w_n) (w_n <= 2048) of this CTA, in blocked layout
 // anc[k] = parent of slot w_lo + tid * 8 + k (junk past w_n).  Returns S (0: no weight has mass, identity written);
 // *e_out = E.  `cdf` is this device's array, `cdf_peers` (nullable) every rank's, tile p living on rank p /
-// (n_per_rank / 2048).  All kThreads threads call; sm.heads is left in use (ancestors are NOT stored there).
-template <bool kCg>
+// (n_per_rank / 2048).  kFast: n_tiles <= 512 and *pre2 holds this thread's two records (te_load_recs2).
+// All kThreads threads call; sm.heads is left in use (ancestors are NOT stored there).
+template <bool kCg, bool kFast>
 __device__ __forceinline__ uint64_t te_pull(const gjb_tile_rec* __restrict__ recs, int n_tiles,
                                             const uint64_t* __restrict__ cdf, const gjb_peers* cdf_peers, int64_t n_total,
-                                            double u0, int64_t w_lo, int w_n, TeSmem& sm, int32_t (&anc)[kTeItems], int* e_out) {
+                                            double u0, int64_t w_lo, int w_n, TeSmem& sm, int32_t (&anc)[kTeItems], int* e_out,
+                                            const TeRecs2* pre2 = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int per = (n_tiles + kThreads - 1) / kThreads;
+  const int per = kFast ? 2 : (n_tiles + kThreads - 1) / kThreads;
   const int t0 = tid * per;
   // ---- E = max exponent over tiles with mass
   int emax = GJB_TE_E_NONE;
+#pragma unroll
   for (int k = 0; k < per; ++k) {
     const int t = t0 + k;
-    if (t < n_tiles) {
-      const gjb_tile_rec r = te_ld_rec<kCg>(recs + t);
+    if (kFast || t < n_tiles) {
+      const gjb_tile_rec r = kFast ? pre2->r[k] : te_ld_rec<kCg>(recs + t);
       if (r.mass) emax = max(emax, r.e);
     }
   }
@@ -142,19 +181,23 @@ __device__ __forceinline__ uint64_t te_pull(const gjb_tile_rec* __restrict__ rec
   if (lane == 0) sm.ired[warp] = emax;
   if (tid == 0) { sm.p_lo = 0x7fffffff; sm.p_hi = -1; }
   __syncthreads();
-  int E = sm.ired[0];
-#pragma unroll
-  for (int w = 1; w < kThreads / 32; ++w) E = max(E, sm.ired[w]);
+  int E;
+  {
+    const int4 a = *reinterpret_cast<const int4*>(sm.ired), b = *reinterpret_cast<const int4*>(sm.ired + 4);
+    E = max(max(max(a.x, a.y), max(a.z, a.w)), max(max(b.x, b.y), max(b.z, b.w)));
+  }
   *e_out = E;
   // ---- aligned tile masses, their inclusive prefix
   uint64_t run = 0;
+  uint64_t mine[2] = {0ull, 0ull};  // kFast: this thread's two running sums
+#pragma unroll
   for (int k = 0; k < per; ++k) {
     const int t = t0 + k;
-    if (t < n_tiles) {
-      const gjb_tile_rec r = te_ld_rec<kCg>(recs + t);
+    if (kFast || t < n_tiles) {
+      const gjb_tile_rec r = kFast ? pre2->r[k] : te_ld_rec<kCg>(recs + t);
       const int s = r.mass ? min(E - r.e, 63) : 63;
       run += r.mass >> s;
-      sm.pre[t] = run;
+      if (kFast) mine[k] = run; else sm.pre[t] = run;
       sm.shf[t] = (uint8_t)s;
     }
   }
@@ -171,10 +214,11 @@ __device__ __forceinline__ uint64_t te_pull(const gjb_tile_rec* __restrict__ rec
   __syncthreads();
   uint64_t excl = inc - run, S = 0;
 #pragma unroll
-  for (int w = 0; w < kThreads / 32; ++w) {
-    const uint64_t v = sm.red[w];
-    if (w < warp) excl += v;
-    S += v;
+  for (int w = 0; w < kThreads / 32; w += 2) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(sm.red + w);
+    if (w < warp) excl += v.x;
+    if (w + 1 < warp) excl += v.y;
+    S += v.x + v.y;
   }
   if (S == 0) {
 #pragma unroll
@@ -188,56 +232,60 @@ __device__ __forceinline__ uint64_t te_pull(const gjb_tile_rec* __restrict__ rec
   {
     int lo = 0x7fffffff, hi = -1;
     uint64_t prev = excl;
+    int32_t cnt_prev = offspring_cnt(prev, S, scale, u0, nt);
+#pragma unroll
     for (int k = 0; k < per; ++k) {
       const int t = t0 + k;
-      if (t < n_tiles) {
-        const uint64_t cur = sm.pre[t] + excl;
-        sm.pre[t] = cur;
-        if (cur != prev && offspring_cnt(cur, S, scale, u0, nt) > wl && offspring_cnt(prev, S, scale, u0, nt) < wh) {
+      if (kFast || t < n_tiles) {
+        const uint64_t cur = (kFast ? mine[k] : sm.pre[t]) + excl;
+        if (!kFast || t < n_tiles) sm.pre[t] = cur;
+        const int32_t cnt_cur = offspring_cnt(cur, S, scale, u0, nt);
+        if (cur != prev && cnt_cur > wl && cnt_prev < wh) {
           lo = min(lo, t);
           hi = max(hi, t);
         }
         prev = cur;
+        cnt_prev = cnt_cur;
       }
     }
     if (hi >= 0) { atomicMin(&sm.p_lo, lo); atomicMax(&sm.p_hi, hi); }
   }
   __syncthreads();
   const int p_lo = sm.p_lo, p_hi = sm.p_hi;
-  // ---- every parent with offspring in the window drops its id (+1) at its first slot
+  // ---- every parent with offspring in the window drops its id (+1) at its first slot.  The rows of tile p + 1 are
+  // requested before tile p is processed (one exposed load latency for the whole loop instead of one per tile).
   const int tiles_per_rank = cdf_peers ? (int)(cdf_peers->n_per_rank / kTeTile) : 0;
-  for (int p = p_lo; p <= p_hi; ++p) {
-    const uint64_t base = p ? sm.pre[p - 1] : 0ull;
-    if (sm.pre[p] == base) continue;  // a tile without (aligned) mass
-    const int s = sm.shf[p];
-    const uint64_t* ct;
+  auto row_of = [&](int p) -> const uint64_t* {
     if (cdf_peers) {
       const int owner = p / tiles_per_rank;
-      ct = reinterpret_cast<const uint64_t*>(cdf_peers->base[owner]) + (int64_t)(p - owner * tiles_per_rank) * kTeTile;
-    } else {
-      ct = cdf + (int64_t)p * kTeTile;
+      return reinterpret_cast<const uint64_t*>(cdf_peers->base[owner]) + (int64_t)(p - owner * tiles_per_rank) * kTeTile + tid * kTeItems;
     }
-    ct += tid * kTeItems;
-    const uint64_t c_prev = tid ? (kCg ? __ldcg(ct - 1) : __ldg(ct - 1)) : 0ull;
-    const ulonglong2* c2 = reinterpret_cast<const ulonglong2*>(ct);
-    const ulonglong2 c67 = kCg ? __ldcg(c2 + 3) : __ldg(c2 + 3);
-    int32_t prev = min(max(offspring_cnt(base + (c_prev >> s), S, scale, u0, nt), wl), wh);
-    const int32_t last = min(max(offspring_cnt(base + (c67.y >> s), S, scale, u0, nt), wl), wh);
-    if (last > prev) {  // this thread's 8 parents own slots of the window
-      uint64_t c[kTeItems];
+    return cdf + (int64_t)p * kTeTile + tid * kTeItems;
+  };
+  uint64_t c[kTeItems], c_prev = 0;
+  if (p_lo <= p_hi) te_ld_row<kCg>(row_of(p_lo), c, c_prev);
+  for (int p = p_lo; p <= p_hi; ++p) {
+    uint64_t cn[kTeItems], cn_prev = 0;
+    if (p < p_hi) te_ld_row<kCg>(row_of(p + 1), cn, cn_prev);
+    const uint64_t base = p ? sm.pre[p - 1] : 0ull;
+    if (sm.pre[p] != base) {  // (a tile without aligned mass owns nothing)
+      const int s = sm.shf[p];
+      int32_t prev = min(max(offspring_cnt(base + (c_prev >> s), S, scale, u0, nt), wl), wh);
+      const int32_t last = min(max(offspring_cnt(base + (c[kTeItems - 1] >> s), S, scale, u0, nt), wl), wh);
+      if (last > prev) {  // this thread's 8 parents own slots of the window
+        const int32_t id1 = p * kTeTile + tid * kTeItems + 1;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const ulonglong2 v = kCg ? __ldcg(c2 + k) : __ldg(c2 + k);
-        c[2 * k] = v.x; c[2 * k + 1] = v.y;
+        for (int k = 0; k < kTeItems; ++k) {
+          const int32_t cur = (k == kTeItems - 1) ? last : min(max(offspring_cnt(base + (c[k] >> s), S, scale, u0, nt), wl), wh);
+          if (cur > prev) sm.heads[prev - wl] = id1 + k;
+          prev = cur;
+        }
       }
-      c[6] = c67.x; c[7] = c67.y;
-      const int32_t id1 = p * kTeTile + tid * kTeItems + 1;
+    }
+    if (p < p_hi) {
 #pragma unroll
-      for (int k = 0; k < kTeItems; ++k) {
-        const int32_t cur = (k == kTeItems - 1) ? last : min(max(offspring_cnt(base + (c[k] >> s), S, scale, u0, nt), wl), wh);
-        if (cur > prev) sm.heads[prev - wl] = id1 + k;
-        prev = cur;
-      }
+      for (int k = 0; k < kTeItems; ++k) c[k] = cn[k];
+      c_prev = cn_prev;
     }
   }
   __syncthreads();
@@ -259,8 +307,12 @@ __device__ __forceinline__ uint64_t te_pull(const gjb_tile_rec* __restrict__ rec
   const int32_t wexc = __shfl_up_sync(0xffffffffu, incm, 1);
   __syncthreads();
   int32_t pre = lane ? wexc : 0;
+  {
+    const int4 a = *reinterpret_cast<const int4*>(sm.ired), b = *reinterpret_cast<const int4*>(sm.ired + 4);
+    const int32_t wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-  for (int w = 0; w < kThreads / 32; ++w) if (w < warp) pre = max(pre, sm.ired[w]);
+    for (int w = 0; w < kThreads / 32; ++w) if (w < warp) pre = max(pre, wv[w]);
+  }
 #pragma unroll
   for (int k = 0; k < kTeItems; ++k) anc[k] = max(v[k], pre) - 1;
   return S;

@@ -553,23 +553,45 @@ class _Generator:
         P.append("  float score, weight;")
         P.append("};")
 
-        rngpre: list[str] = []
+        # RNG of one quad: the Philox block (and its Box-Muller normals) of every scalar site that may be sampled from the
+        # quad stream.  Emitted as its own function so that the single-launch filter step can run it BEFORE it resolves its
+        # ancestors (pure ALU work that overlaps the tile-record loads), and as a struct the body reads.
+        qrng_decl: list[str] = ["struct QRng {  // quad-stream random words / normals of one quad, per scalar site"]
+        qrng_fill: list[str] = []
+        rngpre: list[str] = ["    QRng R;",
+                             "    if (kPre) R = *pre_rng; else quad_rng<kSt>(fl, key0, key1, quad0 + (uint64_t)ql, R);"]
+        n_q = 0
         for s in ir.sites:
             j = s.index
             kind = s.dist.rng_kind
             if s.dist.vector or kind == "lane":
                 continue
-            rngpre.append(f"    uint4 W{j} = make_uint4(0u, 0u, 0u, 0u); (void)W{j};")
+            n_q += 1
+            qrng_decl.append(f"  uint4 W{j};")
+            qrng_fill.append(f"  R.W{j} = make_uint4(0u, 0u, 0u, 0u);")
+            rngpre.append(f"    const uint4& W{j} = R.W{j}; (void)W{j};")
             if kind == "normal":
-                rngpre.append(f"    float4 Z{j} = make_float4(0.f, 0.f, 0.f, 0.f); (void)Z{j};")
-            rngpre.append(f"    if (FL({j}) & GJB_SITE_SAMPLE) {{ W{j} = gjb::quad_words(key0, key1, quad0 + (uint64_t)ql, {j + 1}u);"
-                          + (f" Z{j} = gjb::normal4_of(W{j});" if kind == "normal" else "") + " }")
+                qrng_decl.append(f"  float4 Z{j};")
+                qrng_fill.append(f"  R.Z{j} = make_float4(0.f, 0.f, 0.f, 0.f);")
+                rngpre.append(f"    const float4& Z{j} = R.Z{j}; (void)Z{j};")
+            qrng_fill.append(f"  if (FL({j}) & GJB_SITE_SAMPLE) {{ R.W{j} = gjb::quad_words(key0, key1, quad, {j + 1}u);"
+                             + (f" R.Z{j} = gjb::normal4_of(R.W{j});" if kind == "normal" else "") + " }")
+        if n_q == 0:
+            qrng_decl.append("  int unused;")
+        qrng_decl.append("};")
+        qrng_fn = ["template <bool kSt>",
+                   "__device__ __forceinline__ void quad_rng(const uint32_t (&fl)[NS], uint32_t key0, uint32_t key1, uint64_t quad, QRng& R) {",
+                   "  (void)fl; (void)key0; (void)key1; (void)quad; (void)R;"] + qrng_fill + ["}"]
 
         out = list(P)
+        out.extend(qrng_decl)
+        out.extend(qrng_fn)
         out.append("// quads [ql_begin, ql_end) step ql_stride of the launch; local particle i0 = 4*ql - (idx_offset & 3)")
-        out.append("template <bool kCg, bool kSt, bool kMass = false, bool kSm = false>  // kSm: io.gather points to shared memory")
+        out.append("// kSm: io.gather points to shared memory and the weights also go to io.te_w; kPre: the quad's RNG was drawn by the caller")
+        out.append("template <bool kCg, bool kSt, bool kMass = false, bool kSm = false, bool kPre = false>")
         out.append("__device__ __forceinline__ void run_quads(const Io& io, const Uni& U, const uint32_t (&fl)[NS], int64_t n,")
-        out.append("    uint64_t idx_offset, uint32_t key0, uint32_t key1, int64_t ql_begin, int64_t ql_end, int64_t ql_stride, float& run_max) {")
+        out.append("    uint64_t idx_offset, uint32_t key0, uint32_t key1, int64_t ql_begin, int64_t ql_end, int64_t ql_stride, float& run_max,")
+        out.append("    const QRng* pre_rng = nullptr) {")
         out.append("  const bool need_score = !kSt && io.score_out != nullptr;")
         out.append("  const float mref = kMass ? __ldg(io.m_ref) : 0.0f;  // reference maximum known before the launch")
         out.append("  const int shift = kSt ? 0 : (int)(idx_offset & 3);")
@@ -807,26 +829,42 @@ class _Generator:
         wbuf = "reinterpret_cast<float*>(sm.pre)" if self.group else "reinterpret_cast<float*>(sm.heads)"
         out.append(f"  float* const wbuf = {wbuf};  // this window's new weights (block-shared)")
         out.append("  io.te_w = wbuf - w_loc;")
+        out.append("  const uint32_t key0 = __ldg(A.key_dev), key1 = __ldg(A.key_dev + 1);")
+        out.append("  // the tile records are requested first; everything up to te_pull is independent ALU work that hides their latency")
+        out.append("  const bool fast = A.prev_cdf && A.n_tiles_total <= 2 * kThreads;")
+        out.append("  gjb::TeRecs2 recs2;")
+        out.append("  if (fast) recs2 = A.cdf_peers ? gjb::te_load_recs2<true>(A.prev_recs, A.n_tiles_total) : gjb::te_load_recs2<false>(A.prev_recs, A.n_tiles_total);")
+        if not self.group:
+            out.append("  // the thread's own 8 slots = 2 global quads: their random numbers do not depend on the ancestors")
+            out.append("  const int64_t q0 = (w_loc >> 2) + tid * 2;")
+            out.append("  const int64_t qw = (w_loc + w_n + 3) >> 2;")
+            out.append("  QRng R0, R1;")
+            out.append("  quad_rng<true>(fl, key0, key1, (A.idx_offset >> 2) + (uint64_t)q0, R0);")
+            out.append("  quad_rng<true>(fl, key0, key1, (A.idx_offset >> 2) + (uint64_t)q0 + 1, R1);")
         out.append("  if (A.prev_cdf) {  // ancestors of MY slots: output-slot systematic resampling of the previous step")
         out.append("    const double u0 = gjb::resample_u0(__ldg(A.prev_key), __ldg(A.prev_key + 1), (uint64_t)__ldg(A.prev_key + 2) | ((uint64_t)__ldg(A.prev_key + 3) << 32));")
         out.append("    int32_t anc[gjb::kTeItems];")
         out.append("    int E;")
-        out.append("    const uint64_t S = A.cdf_peers")
-        out.append("        ? gjb::te_pull<true>(A.prev_recs, A.n_tiles_total, A.prev_cdf, A.cdf_peers, A.n_total, u0, A.slot_offset + w_loc, w_n, sm, anc, &E)")
-        out.append("        : gjb::te_pull<false>(A.prev_recs, A.n_tiles_total, A.prev_cdf, nullptr, A.n_total, u0, A.slot_offset + w_loc, w_n, sm, anc, &E);")
+        out.append("    uint64_t S;")
+        out.append("    const int64_t w_glob = A.slot_offset + w_loc;")
+        out.append("    if (fast) S = A.cdf_peers")
+        out.append("        ? gjb::te_pull<true, true>(A.prev_recs, A.n_tiles_total, A.prev_cdf, A.cdf_peers, A.n_total, u0, w_glob, w_n, sm, anc, &E, &recs2)")
+        out.append("        : gjb::te_pull<false, true>(A.prev_recs, A.n_tiles_total, A.prev_cdf, nullptr, A.n_total, u0, w_glob, w_n, sm, anc, &E, &recs2);")
+        out.append("    else S = A.cdf_peers")
+        out.append("        ? gjb::te_pull<true, false>(A.prev_recs, A.n_tiles_total, A.prev_cdf, A.cdf_peers, A.n_total, u0, w_glob, w_n, sm, anc, &E)")
+        out.append("        : gjb::te_pull<false, false>(A.prev_recs, A.n_tiles_total, A.prev_cdf, nullptr, A.n_total, u0, w_glob, w_n, sm, anc, &E);")
         out.append("    if (blockIdx.x == 0 && tid == 0 && A.prev_lse) gjb::te_write_lse(A.prev_lse, E, S, A.n_total);")
         out.append("    const int4 a0 = make_int4(anc[0], anc[1], anc[2], anc[3]), a1 = make_int4(anc[4], anc[5], anc[6], anc[7]);")
         out.append("    *reinterpret_cast<int4*>(sm.heads + tid * gjb::kTeItems) = a0;  // (a thread's own slots: no hazard with the scan)")
         out.append("    *reinterpret_cast<int4*>(sm.heads + tid * gjb::kTeItems + 4) = a1;")
         out.append("    if (A.ancestors_out) {")
         out.append("      int32_t* o = A.ancestors_out + w_loc + tid * gjb::kTeItems;")
-        out.append("      if (tid * gjb::kTeItems + gjb::kTeItems <= w_n) { reinterpret_cast<int4*>(o)[0] = a0; reinterpret_cast<int4*>(o)[1] = a1; }")
+        out.append("      if (tid * gjb::kTeItems + gjb::kTeItems <= w_n && (reinterpret_cast<uintptr_t>(o) & 15) == 0) { reinterpret_cast<int4*>(o)[0] = a0; reinterpret_cast<int4*>(o)[1] = a1; }")
         out.append("      else for (int k = 0; k < gjb::kTeItems; ++k) if (tid * gjb::kTeItems + k < w_n) o[k] = anc[k];")
         out.append("    }")
         out.append("    io.gather = sm.heads - w_loc;")
         out.append("    io.peers = A.peer_args;")
         out.append("  }")
-        out.append("  const uint32_t key0 = __ldg(A.key_dev), key1 = __ldg(A.key_dev + 1);")
         out.append("  float run_max = -INFINITY;")
         if self.group:
             out.append("  __syncthreads();  // every group reads ancestors other threads resolved")
@@ -834,12 +872,13 @@ class _Generator:
             out.append("  else run_groups<false, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, w_loc, w_loc + w_n, kPPB, run_max);")
             out.append("  __syncthreads();  // the window's weights are complete")
         else:
-            out.append("  // the thread's own 8 slots = 2 global quads: ancestors and weights never leave the thread")
-            out.append("  const int64_t q0 = (w_loc >> 2) + tid * 2;")
-            out.append("  const int64_t qw = (w_loc + w_n + 3) >> 2;")
-            out.append("  const int64_t qe = q0 + 2 < qw ? q0 + 2 : qw;")
-            out.append("  if (A.cdf_peers) run_quads<true, true, false, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0, qe, 1, run_max);")
-            out.append("  else run_quads<false, true, false, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0, qe, 1, run_max);")
+            out.append("  if (A.cdf_peers) {")
+            out.append("    if (q0 < qw) run_quads<true, true, false, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0, q0 + 1, 1, run_max, &R0);")
+            out.append("    if (q0 + 1 < qw) run_quads<true, true, false, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0 + 1, q0 + 2, 1, run_max, &R1);")
+            out.append("  } else {")
+            out.append("    if (q0 < qw) run_quads<false, true, false, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0, q0 + 1, 1, run_max, &R0);")
+            out.append("    if (q0 + 1 < qw) run_quads<false, true, false, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0 + 1, q0 + 2, 1, run_max, &R1);")
+            out.append("  }")
         out.append("  float lw[gjb::kTeItems];")
         out.append("#pragma unroll")
         out.append("  for (int k = 0; k < gjb::kTeItems; ++k) lw[k] = (tid * gjb::kTeItems + k < w_n) ? wbuf[tid * gjb::kTeItems + k] : -INFINITY;")

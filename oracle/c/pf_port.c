@@ -34,14 +34,37 @@ static inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t
 
 static inline float u01(uint32_t bits) { return ((float)(bits >> 9) + 0.5f) * 1.1920928955078125e-07f; }
 
-/* oracle/rng.py box_muller: log / cos / sin in double, rounded once */
+/* oracle/rng.py box_muller: fp32 polynomials with correctly rounded FMAs (fmaf), operation for operation */
+static inline float as_f(int32_t i) { float f; memcpy(&f, &i, 4); return f; }
+static inline int32_t as_i(float f) { int32_t i; memcpy(&i, &f, 4); return i; }
 static inline void box_muller(uint32_t b0, uint32_t b1, float* z0, float* z1) {
   const float u1 = u01(b0), u2 = u01(b1);
-  const float lg = (float)log((double)u1);
-  const float r = sqrtf(-2.0f * lg);
-  const double ang = 2.0 * (double)u2 * 3.141592653589793;
-  *z0 = r * (float)cos(ang);
-  *z1 = r * (float)sin(ang);
+  const int32_t tb = as_i(u1) - 0x3F3504F3;
+  const int32_t e = tb >> 23;
+  const float f = as_f((tb & 0x007FFFFF) + 0x3F3504F3) - 1.0f;
+  const float ef = (float)e;
+  const float f2 = f * f;
+  float R = 0x1.4237fep-3f;
+  R = fmaf(R, f, -0x1.0696e4p-2f); R = fmaf(R, f, 0x1.0c524cp-2f); R = fmaf(R, f, -0x1.22973ap-2f);
+  R = fmaf(R, f, 0x1.548882p-2f); R = fmaf(R, f, -0x1.99a3ecp-2f); R = fmaf(R, f, 0x1.000206p-1f);
+  R = fmaf(R, f, -0x1.55554ep-1f); R = fmaf(R, f, 0x1.fffffep-1f);
+  const float L = fmaf(ef, -0x1.62e43p+0f, fmaf(f2, R, -2.0f * f));
+  const float r = sqrtf(L);
+  const float tm = fmaf(u2, 4.0f, 12582912.0f);
+  const int32_t q = as_i(tm) & 3;
+  const float rr = fmaf(tm - 12582912.0f, -0.25f, u2);
+  const float z = rr * rr;
+  float ps = fmaf(z, -0x1.2d9b7cp+6f, 0x1.465ec4p+6f);
+  ps = fmaf(z, ps, -0x1.4abbbap+5f); ps = fmaf(z, ps, 0x1.921fb6p+2f);
+  const float sn = rr * ps;
+  float pc = fmaf(z, 0x1.db6578p+5f, -0x1.55cb9ap+6f);
+  pc = fmaf(z, pc, 0x1.03c1eap+6f); pc = fmaf(z, pc, -0x1.3bd3ccp+4f);
+  const float cs = fmaf(z, pc, 1.0f);
+  float a = (q & 1) ? sn : cs, b = (q & 1) ? cs : sn;
+  if ((q + 1) & 2) a = -a;
+  if (q & 2) b = -b;
+  *z0 = r * a;
+  *z1 = r * b;
 }
 
 /* oracle/dists.py normal_logpdf */

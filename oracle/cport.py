@@ -10,13 +10,17 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_build", "liboracle_pf.so")
+FAST_LIB = os.path.join(HERE, "_build", "liboracle_pf_fast.so")
 _lib = None
+_fast = None
 
 
 def build(force: bool = False) -> str | None:
     """Compile oracle/c/pf_port.c with gcc (OpenMP when available); returns the library path or None."""
     src = os.path.join(HERE, "c", "pf_port.c")
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(src):
+    fsrc = os.path.join(HERE, "c", "pf_port_fast.c")
+    if (not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(src)
+            and os.path.exists(FAST_LIB) and os.path.getmtime(FAST_LIB) >= os.path.getmtime(fsrc)):
         return LIB
     try:
         subprocess.run(["make", "-C", os.path.join(HERE, "c"), "-B"], check=True, capture_output=True)
@@ -39,6 +43,23 @@ def lib():
     return _lib
 
 
+_SIG = [C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_float,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+
+
+def fast_lib():
+    """The performance build (oracle/c/pf_port_fast.c: quad-wise Philox, float libm, -O3 -march=native), or None."""
+    global _fast
+    if _fast is None:
+        if build() is None or not os.path.exists(FAST_LIB):
+            return None
+        _fast = C.CDLL(FAST_LIB)
+        _fast.pf_lgssm_fast.restype = C.c_int
+        _fast.pf_lgssm_fast.argtypes = _SIG
+        _fast.pf_fast_threads.restype = C.c_int
+    return _fast
+
+
 def threads() -> int:
     lb = lib()
     return int(lb.pf_port_threads()) if lb is not None else 0
@@ -50,12 +71,15 @@ def set_threads(n: int) -> None:
         lb.pf_port_set_threads(int(n))
 
 
-def pf_lgssm(x0, ys, a, q, c, r, key_table):
+def pf_lgssm(x0, ys, a, q, c, r, key_table, fast: bool = False, threads_: int | None = None):
     """Runs the filter; returns dict(state, logz_inc, logw_last, ancestors_last).  x0: [n] or [n, d] float32;
-    ys: [T] or [T, d]; q, r: [d]; key_table: uint32 [T, 8] (genjax_b200.core.key.pf_key_table)."""
-    lb = lib()
+    ys: [T] or [T, d]; q, r: [d]; key_table: uint32 [T, 8] (genjax_b200.core.key.pf_key_table).
+    ``fast=True``: the performance build (same algorithm and streams; proposals agree to float32 rounding)."""
+    lb = fast_lib() if fast else lib()
     if lb is None:
         raise RuntimeError("oracle C port is not built (gcc missing?)")
+    if threads_:
+        (lb.pf_fast_set_threads if fast else lb.pf_port_set_threads)(int(threads_))
     x = np.array(x0, dtype=np.float32, copy=True, order="C")
     n = x.shape[0]
     d = 1 if x.ndim == 1 else x.shape[1]
@@ -67,7 +91,7 @@ def pf_lgssm(x0, ys, a, q, c, r, key_table):
     inc = np.empty(T, dtype=np.float64)
     lw = np.empty(n, dtype=np.float32)
     anc = np.empty(n, dtype=np.int32)
-    rc = lb.pf_lgssm(n, T, d, x.ctypes.data, ys.ctypes.data, float(a), q.ctypes.data, float(c), r.ctypes.data,
+    rc = (lb.pf_lgssm_fast if fast else lb.pf_lgssm)(n, T, d, x.ctypes.data, ys.ctypes.data, float(a), q.ctypes.data, float(c), r.ctypes.data,
                      keys.ctypes.data, inc.ctypes.data, lw.ctypes.data, anc.ctypes.data)
     if rc != 0:
         raise MemoryError("pf_lgssm failed")

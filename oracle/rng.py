@@ -250,21 +250,54 @@ def u01(bits):
     return ((bits >> U32(9)).astype(F32) + F32(0.5)) * _TWO_NEG23
 
 
-def box_muller(b0, b1):
-    """Two N(0,1) float32 from two uint32 words.
+# Box-Muller on fp32 polynomials with correctly rounded FMAs (scratch/fit_box_muller.py fitted the coefficients): every
+# operation below is one IEEE fp32 operation of csrc/gjb_rng.cuh box_muller, so sampled normals are BIT-EXACT between
+# this oracle and the device (round 1 used libm log / sincospi on the device: rtol 1e-5 only).
+_BM_LOG = [F32(float.fromhex(h)) for h in (
+    "0x1.fffffep-1", "-0x1.55554ep-1", "0x1.000206p-1", "-0x1.99a3ecp-2", "0x1.548882p-2", "-0x1.22973ap-2",
+    "0x1.0c524cp-2", "-0x1.0696e4p-2", "0x1.4237fep-3")]          # -2 log1p(f) = -2 f + f^2 R(f)
+_BM_SIN = [F32(float.fromhex(h)) for h in ("0x1.921fb6p+2", "-0x1.4abbbap+5", "0x1.465ec4p+6", "-0x1.2d9b7cp+6")]  # sin(2 pi r) = r S(r^2)
+_BM_COS = [F32(float.fromhex(h)) for h in ("-0x1.3bd3ccp+4", "0x1.03c1eap+6", "-0x1.55cb9ap+6", "0x1.db6578p+5")]  # cos(2 pi r) = 1 + r^2 C(r^2)
+_BM_NEG_2LN2 = F32(float.fromhex("-0x1.62e43p+0"))
+_MAGIC = F32(12582912.0)  # 1.5 * 2^23: adding it rounds to the nearest integer, which lands in the low mantissa bits
 
-    r = sqrtf(-2 logf(u1)); (s, c) = sincospif(2 u2); z0 = r c; z1 = r s.
-    log / sin / cos are evaluated in float64 and rounded once (the CUDA
-    library functions are within 1-2 ulp of that).
-    """
-    u1 = u01(b0)
-    u2 = u01(b1)
-    lg = np.log(u1.astype(np.float64)).astype(F32)
-    r = np.sqrt(F32(-2.0) * lg).astype(F32)
-    ang = np.float64(2.0) * u2.astype(np.float64) * np.pi
-    c = np.cos(ang).astype(F32)
-    s = np.sin(ang).astype(F32)
-    return (r * c).astype(F32), (r * s).astype(F32)
+
+def box_muller(b0, b1):
+    """Two N(0,1) float32 from two uint32 words: r = sqrt(-2 ln u1), (z0, z1) = r (cos, sin)(2 pi u2)."""
+    u1 = np.asarray(u01(b0), dtype=F32)
+    u2 = np.asarray(u01(b1), dtype=F32)
+    # -2 ln u1: u1 = 2^e m, m in [sqrt(1/2), sqrt(2)), f = m - 1 (exact)
+    tb = u1.view(np.int32) - np.int32(0x3F3504F3)
+    e = tb >> np.int32(23)
+    m = ((tb & np.int32(0x007FFFFF)) + np.int32(0x3F3504F3)).view(F32)
+    f = (m - F32(1.0)).astype(F32)
+    ef = e.astype(F32)
+    f2 = (f * f).astype(F32)
+    R = np.full(f.shape, _BM_LOG[8], dtype=F32)
+    for k in range(7, -1, -1):
+        R = fma32(R, f, _BM_LOG[k])
+    L = fma32(ef, _BM_NEG_2LN2, fma32(f2, R, (F32(-2.0) * f).astype(F32)))
+    r = np.sqrt(L).astype(F32)
+    # angle 2 pi u2 = j pi/2 + 2 pi rr, j = rint(4 u2), rr in [-1/8, 1/8] (exact)
+    tm = fma32(u2, F32(4.0), _MAGIC)
+    q = tm.view(np.int32) & np.int32(3)
+    jf = (tm - _MAGIC).astype(F32)
+    rr = fma32(jf, F32(-0.25), u2)
+    z = (rr * rr).astype(F32)
+    ps = fma32(z, _BM_SIN[3], _BM_SIN[2])
+    ps = fma32(z, ps, _BM_SIN[1])
+    ps = fma32(z, ps, _BM_SIN[0])
+    sn = (rr * ps).astype(F32)
+    pc = fma32(z, _BM_COS[3], _BM_COS[2])
+    pc = fma32(z, pc, _BM_COS[1])
+    pc = fma32(z, pc, _BM_COS[0])
+    cs = fma32(z, pc, F32(1.0))
+    swap = (q & 1) != 0
+    a = np.where(swap, sn, cs)
+    b = np.where(swap, cs, sn)
+    a = np.where(((q + 1) & 2) != 0, -a, a).astype(F32)
+    b = np.where((q & 2) != 0, -b, b).astype(F32)
+    return (r * a).astype(F32), (r * b).astype(F32)
 
 
 def normal4(words, idx, site, chunk=0):

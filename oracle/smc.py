@@ -173,8 +173,8 @@ def log_mean_exp_ref(logw, M, n_total=None):
 # 2048, a constant of the ALGORITHM, not of the launch) therefore takes its masses relative to its own power-of-two
 # reference 2^e_p, e_p = ceil(max_tile(lw * log2 e)); the consumer aligns the tiles with exact right shifts:
 #
-#     t_i = fl32(lw_i * log2e)  (non-finite -> mass 0);  n_i = floor(t_i);  sh_i = min(e_p - n_i, 63)
-#     q_i = round-half-up(m_i / 2^sh_i),  m_i = uint64(fl32(2^36 * 2^(t_i - n_i)))   (fp32 fma polynomial, te_exp2_m)
+#     t_i = fl32(lw_i * log2e)  (non-finite -> mass 0);  r_i = rint(t_i);  g_i = t_i - r_i in [-1/2, 1/2]
+#     q_i = rint(fl32(2^g_i) * 2^(36 - (e_p - r_i)))                     (fp32 fma polynomial, te_q)
 #     c_i = inclusive prefix of q inside the tile (uint64),  T_p = the tile's mass
 #     e   = max_p e_p (tiles with mass);  s_p = min(e - e_p, 63);  P_p = inclusive prefix of (T_p >> s_p);  S = P_last
 #     C_i = P_{p-1} + (c_i >> s_p)        -- a monotone integer CDF: any CTA / GPU partition gives the same bits
@@ -186,20 +186,26 @@ def log_mean_exp_ref(logw, M, n_total=None):
 
 TE_TILE = 2048
 TE_E_NONE = -(2**31)
-_TE_CLAMP = F32(2.0**29)
-# minimax-free choice: Taylor coefficients of 2^g, g in [-0.5, 0.5), degree 7, evaluated with fp32 FMAs (Horner)
+_TE_CLAMP = F32(2.0**20)
+_TE_MAGIC = F32(12582912.0)  # 1.5 * 2^23: t + MAGIC rounds t to the nearest integer (ties to even), held in the low mantissa bits
+# Taylor coefficients of 2^g, g in [-0.5, 0.5], degree 7 (|error| < 6e-9 relative), evaluated with fp32 FMAs (Horner)
 _TE_COEF = _EXP2_COEF
 
 
-def te_exp2_m(frac):
-    """uint64(fl32(2^36 * 2^frac)) for float32 frac in [0, 1): Horner with correctly rounded fp32 FMAs
-    (``__fmaf_rn`` on the device), times sqrt 2, times 2^36, truncated."""
-    g = (np.asarray(frac, dtype=F32) - F32(0.5)).astype(F32)
-    p = np.full(g.shape, _TE_COEF[7], dtype=F32)
+def te_q(t, e):
+    """Mass of a particle with scaled log-weight ``t`` (finite float32, |t| <= 2^20) relative to 2^e, e >= rint(t):
+    rint(fl32(p * 2^(36 - (e - r)))) with r = rint(t), g = t - r, p = 2^g by fp32 FMA Horner -- operation for operation
+    csrc/gjb_step.cuh te_q (one FADD for the rounding, no conversion-pipe instruction, one float -> uint64 convert)."""
+    t = np.asarray(t, dtype=F32)
+    tm = (t + _TE_MAGIC).astype(F32)
+    r = tm.view(np.int32).astype(np.int64) - 0x4B400000
+    g = (t - (tm - _TE_MAGIC).astype(F32)).astype(F32)
+    p = np.full(t.shape, _TE_COEF[7], dtype=F32)
     for k in range(6, -1, -1):
         p = rng.fma32(p, g, _TE_COEF[k])
-    p = (p * _SQRT2).astype(F32)
-    return (p * F32(2.0**Q_BITS)).astype(F32).astype(U64)
+    ex = np.maximum(r + 163 - np.asarray(e, dtype=np.int64), 63)  # biased exponent of 2^(36 - (e - r)), at least 2^-64
+    scale = (ex.astype(np.int32) << np.int32(23)).view(F32)
+    return np.rint((p * scale).astype(F32)).astype(U64)
 
 
 def te_tile_masses(logw):
@@ -216,11 +222,8 @@ def te_tile_masses(logw):
         tmax = tp.reshape(tiles, TE_TILE).max(axis=1)
         live = np.isfinite(tmax)
         e_p = np.where(live, np.ceil(np.where(live, tmax, 0.0)), TE_E_NONE).astype(np.int64)
-        nfl = np.floor(t).astype(F32)
-        m = te_exp2_m((t - nfl).astype(F32))
-        sh = np.clip(e_p[np.arange(n) // TE_TILE] - nfl.astype(np.int64), 0, 63).astype(U64)
-        half = np.where(sh > 0, U64(1) << (np.maximum(sh, U64(1)) - U64(1)), U64(0)).astype(U64)
-        q = np.where(ok, (m + half) >> sh, U64(0)).astype(U64)
+        e_i = e_p[np.arange(n) // TE_TILE]
+        q = np.where(ok, te_q(t, np.where(ok, e_i, 0)), U64(0)).astype(U64)
     return q, e_p
 
 

@@ -35,6 +35,8 @@ static dim3 threadIdx, blockIdx, blockDim, gridDim;
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }  // glibc fmaf: correctly rounded
+static inline float __fsqrt_rn(float x) { return sqrtf(x); }
+static inline unsigned long long __float2ull_rn(float x) { return (unsigned long long)rintf(x); }
 static inline int __float2int_ru(float x) { return (int)ceilf(x); }
 static inline int __float2int_rd(float x) { return (int)floorf(x); }
 static inline double __dmul_rn(double a, double b) { return a * b; }
