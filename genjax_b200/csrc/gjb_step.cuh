@@ -20,6 +20,16 @@
 #include "gjb_resample.cuh"
 #include "gjb_rng.cuh"
 
+// Phase timestamps of the step kernel for scratch/trace_step.py (compiled in only with -DGJB_TRACE: build.py adds
+// $GJB_NVCC_EXTRA to the nvcc line).  Slot i of CTA b: SM clock at trace point i; slots 14 / 15: globaltimer at entry / exit.
+#ifdef GJB_TRACE
+__device__ unsigned long long gjb_trace_buf[1024 * 16];
+__device__ __forceinline__ unsigned long long gjb_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define GJB_TP(i) do { if (threadIdx.x == 0 && blockIdx.x < 1024) gjb_trace_buf[blockIdx.x * 16 + (i)] = ((i) >= 14) ? gjb_globaltimer() : (unsigned long long)clock64(); } while (0)
+#else
+#define GJB_TP(i) do {} while (0)
+#endif
+
 namespace gjb {
 
 constexpr int kTeTile = GJB_TE_TILE;
@@ -80,6 +90,7 @@ __device__ __forceinline__ void te_publish(const float (&lw)[kTeItems], uint64_t
     const float4 a = *reinterpret_cast<const float4*>(sm.fred), b = *reinterpret_cast<const float4*>(sm.fred + 4);
     tm = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
   }
+  GJB_TP(9);
   const int e = tm > -INFINITY ? __float2int_ru(tm) : GJB_TE_E_NONE;
   const int kc = tm > -INFINITY ? 163 - e - 0x4B400000 : 0;
   uint64_t c[kTeItems];
@@ -94,6 +105,7 @@ __device__ __forceinline__ void te_publish(const float (&lw)[kTeItems], uint64_t
   }
   if (lane == 31) sm.red[warp] = inc;
   __syncthreads();
+  GJB_TP(10);
   uint64_t excl = inc - run;
 #pragma unroll
   for (int w = 0; w < kThreads / 32; w += 2) {
@@ -187,6 +199,7 @@ __device__ __forceinline__ uint64_t te_pull(const gjb_tile_rec* __restrict__ rec
     E = max(max(max(a.x, a.y), max(a.z, a.w)), max(max(b.x, b.y), max(b.z, b.w)));
   }
   *e_out = E;
+  GJB_TP(2);
   // ---- aligned tile masses, their inclusive prefix
   uint64_t run = 0;
   uint64_t mine[2] = {0ull, 0ull};  // kFast: this thread's two running sums
@@ -225,6 +238,7 @@ __device__ __forceinline__ uint64_t te_pull(const gjb_tile_rec* __restrict__ rec
     for (int k = 0; k < kTeItems; ++k) anc[k] = (int32_t)(w_lo + tid * kTeItems + k);
     return 0;
   }
+  GJB_TP(3);
   const double scale = __ddiv_rn((double)n_total, (double)S);
   const int32_t nt = (int32_t)n_total;
   const int32_t wl = (int32_t)w_lo, wh = (int32_t)(w_lo + w_n);
@@ -252,6 +266,7 @@ __device__ __forceinline__ uint64_t te_pull(const gjb_tile_rec* __restrict__ rec
   }
   __syncthreads();
   const int p_lo = sm.p_lo, p_hi = sm.p_hi;
+  GJB_TP(4);
   // ---- every parent with offspring in the window drops its id (+1) at its first slot.  The rows of tile p + 1 are
   // requested before tile p is processed (one exposed load latency for the whole loop instead of one per tile).
   const int tiles_per_rank = cdf_peers ? (int)(cdf_peers->n_per_rank / kTeTile) : 0;
@@ -289,6 +304,7 @@ __device__ __forceinline__ uint64_t te_pull(const gjb_tile_rec* __restrict__ rec
     }
   }
   __syncthreads();
+  GJB_TP(5);
   // ---- inclusive max-scan over the window: 8 consecutive slots per thread, warp shuffle, block
   int32_t v[kTeItems];
   {
@@ -315,6 +331,7 @@ __device__ __forceinline__ uint64_t te_pull(const gjb_tile_rec* __restrict__ rec
   }
 #pragma unroll
   for (int k = 0; k < kTeItems; ++k) anc[k] = max(v[k], pre) - 1;
+  GJB_TP(6);
   return S;
 }
 

@@ -829,6 +829,7 @@ class _Generator:
         wbuf = "reinterpret_cast<float*>(sm.pre)" if self.group else "reinterpret_cast<float*>(sm.heads)"
         out.append(f"  float* const wbuf = {wbuf};  // this window's new weights (block-shared)")
         out.append("  io.te_w = wbuf - w_loc;")
+        out.append("  GJB_TP(14); GJB_TP(0);")
         out.append("  const uint32_t key0 = __ldg(A.key_dev), key1 = __ldg(A.key_dev + 1);")
         out.append("  // the tile records are requested first; everything up to te_pull is independent ALU work that hides their latency")
         out.append("  const bool fast = A.prev_cdf && A.n_tiles_total <= 2 * kThreads;")
@@ -841,6 +842,7 @@ class _Generator:
             out.append("  QRng R0, R1;")
             out.append("  quad_rng<true>(fl, key0, key1, (A.idx_offset >> 2) + (uint64_t)q0, R0);")
             out.append("  quad_rng<true>(fl, key0, key1, (A.idx_offset >> 2) + (uint64_t)q0 + 1, R1);")
+        out.append("  GJB_TP(1);")
         out.append("  if (A.prev_cdf) {  // ancestors of MY slots: output-slot systematic resampling of the previous step")
         out.append("    const double u0 = gjb::resample_u0(__ldg(A.prev_key), __ldg(A.prev_key + 1), (uint64_t)__ldg(A.prev_key + 2) | ((uint64_t)__ldg(A.prev_key + 3) << 32));")
         out.append("    int32_t anc[gjb::kTeItems];")
@@ -879,12 +881,14 @@ class _Generator:
             out.append("    if (q0 < qw) run_quads<false, true, false, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0, q0 + 1, 1, run_max, &R0);")
             out.append("    if (q0 + 1 < qw) run_quads<false, true, false, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0 + 1, q0 + 2, 1, run_max, &R1);")
             out.append("  }")
+        out.append("  GJB_TP(8);")
         out.append("  float lw[gjb::kTeItems];")
         out.append("#pragma unroll")
         out.append("  for (int k = 0; k < gjb::kTeItems; ++k) lw[k] = (tid * gjb::kTeItems + k < w_n) ? wbuf[tid * gjb::kTeItems + k] : -INFINITY;")
         if self.group:
             out.append("  __syncthreads();  // wbuf aliases sm.pre: everyone has its weights before te_publish reuses the scratch")
         out.append("  gjb::te_publish(lw, A.cdf_out + w_loc, A.recs_out + blockIdx.x, sm);")
+        out.append("  GJB_TP(11); GJB_TP(15);")
         out.append("}")
         return out
 
@@ -1100,6 +1104,12 @@ int gjb_model_pf_run(const gjb_pf_args* a, void* stream) { (void)a; (void)stream
             static_dispatch = "if (a->tile_mass || a->m_ref) return GJB_E_MODE;  // needs the filter-flag instantiation"
         if getattr(self, "has_step", False):
             step_code = """
+#ifdef GJB_TRACE
+int gjb_model_trace_read(unsigned long long* dst, int n) {  // scratch/trace_step.py
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(dst, gjb_trace_buf, sizeof(unsigned long long) * (size_t)(n < 1024 * 16 ? n : 1024 * 16));
+}
+#endif
 int gjb_model_pf_step(const gjb_step_args* a, void* stream) {
   if (!a || a->n <= 0 || a->n_total < a->n || !a->key_dev || !a->cdf_out || !a->recs_out) return GJB_E_ARG;
   if ((a->idx_offset & 3) != 0 || a->slot_offset < 0 || (a->slot_offset % gjb::kTeTile) != 0) return GJB_E_ARG;

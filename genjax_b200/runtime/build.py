@@ -51,11 +51,17 @@ def _header_digest() -> str:
     for p in sorted(list(CSRC.glob("*.cuh")) + [INCLUDE / "genjax_b200.h"]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
+    h.update(" ".join(_extra_flags()).encode())
     return h.hexdigest()
 
 
+def _extra_flags() -> list[str]:
+    """Extra nvcc flags from $GJB_NVCC_EXTRA (diagnostic builds, e.g. -DGJB_TRACE); part of every digest."""
+    return os.environ.get("GJB_NVCC_EXTRA", "").split()
+
+
 def _compile(src: Path, out: Path, log: Path) -> None:
-    cmd = [_nvcc(), *NVCC_FLAGS, f"-I{CSRC}", f"-I{INCLUDE}", "-o", str(out), str(src)]
+    cmd = [_nvcc(), *NVCC_FLAGS, *_extra_flags(), f"-I{CSRC}", f"-I{INCLUDE}", "-o", str(out), str(src)]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log.write_text(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     if proc.returncode != 0:

@@ -10,7 +10,7 @@ from oracle import smc as osmc
 F32 = np.float32
 
 
-def check_against_oracle(res, x0, obs_list, o_model, key, n, T, shared=(), tol=(1e-5, 2e-6, 1e-5, 2e-5), steps=None):
+def check_against_oracle(res, x0, obs_list, o_model, key, n, T, shared=(), tol=(1e-5, 2e-6, 1e-5, 2e-5), steps=None, lme_tol=5e-7):
     anc, lws, xs = res.ancestors.cpu().numpy(), res.history["log_weights"].cpu().numpy(), res.history["state"][0].cpu().numpy()
     lse = res.lse_terms.cpu().numpy()
     x_in, okey = x0, orng.key(key)
@@ -30,6 +30,6 @@ def check_against_oracle(res, x0, obs_list, o_model, key, n, T, shared=(), tol=(
             _, S_o, e_o = osmc.te_cdf(lws[t])
             assert S == float(S_o) and E_ln2 == pytest.approx(e_o * np.log(2.0), abs=1e-12)
             assert inc == pytest.approx(osmc.te_log_mean_exp(lws[t]), abs=1e-11)
-            assert inc == pytest.approx(osmc.log_mean_exp(lws[t]), abs=5e-7)  # same estimate as the exact-max pipeline
+            assert inc == pytest.approx(osmc.log_mean_exp(lws[t]), abs=lme_tol)  # same estimate as the exact-max pipeline
         x_in = xs[t][anc[t]]  # teacher forcing: continue from the kernel's own state
     np.testing.assert_array_equal(res.state[0].cpu().numpy(), x_in)

@@ -122,7 +122,8 @@ def test_step_filter_vector_model(device, d, n):
 
     res = ParticleFilter(wl.lgssm_step_vec, n, mode="step").run(
         gj.key(5), torch.from_numpy(x0), gj.C["y"].set(torch.from_numpy(ys)), (torch.from_numpy(q), torch.from_numpy(r)), record=True)
-    check_against_oracle(res, x0, [{"y": y.astype(F32)} for y in ys], o_vec, 5, n, T, shared=(q, r), tol=(1e-5, 4e-6, 2e-5, 2e-4))
+    # (a 32-D weight vector spans tens of nats: the two pipelines' 2^-36 quantisation steps sit at different references)
+    check_against_oracle(res, x0, [{"y": y.astype(F32)} for y in ys], o_vec, 5, n, T, shared=(q, r), tol=(1e-5, 4e-6, 2e-5, 2e-4), lme_tol=5e-6)
 
 
 def test_step_filter_integer_state_hmm(device):
