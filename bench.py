@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--particles", type=int, default=1 << 20, help="particles per GPU")
     ap.add_argument("--T", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="enqueue the launches every run instead of replaying a CUDA graph")
     ap.add_argument("--multi-gpu", default="islands", choices=["islands", "global"],
                     help="N>1: islands = every rank filters its own block of particles with local resampling and the "
                          "per-shard log-marginal-likelihood terms are combined by ONE NCCL all-reduce per run; "
@@ -426,10 +427,10 @@ def run_ours(args):
     def one(step_idx, e2e):
         key = gj.fold_in(gj.key(314159 + (0 if global_resample else rank)), step_idx)
         if e2e:
-            res = pf.run(key, x0_host.to(device, non_blocking=True), obs_host, shared_args=shared)
+            res = pf.run(key, x0_host.to(device, non_blocking=True), obs_host, shared_args=shared, use_graph=not args.eager)
             state_host.copy_(res.state[0], non_blocking=True)  # the filter's product: final particle cloud, pinned D2H
             return combine(res.log_marginal_likelihood).item()  # (all-reduce of the shard terms +) D2H read + sync
-        res = pf.run(key, x0_dev, obs_dev, shared_args=shared)
+        res = pf.run(key, x0_dev, obs_dev, shared_args=shared, use_graph=not args.eager)
         res.combined = combine(res.log_marginal_likelihood)
         return res
 
@@ -534,7 +535,23 @@ def run_ours(args):
     kernels = {"model_kernel": {"kernel_us": model_ms * 1e3, "algorithmic_bytes_per_launch": model_bytes,
                                 "achieved": model_gbs, "frac": model_gbs / peak,
                                 "what": "fused ancestor-gather + propose + logpdf + running max (gjb_model_launch)"}}
-    if getattr(plan, "stepmode", False):
+    if global_resample:
+        # several devices: the step kernel's last CTA waits for every rank's tile records, so it cannot be re-launched in
+        # isolation on rank 0; the roofline is taken from the step time of the timed region itself (max over ranks)
+        st_ms = ms_per_step / T
+        st_bytes = (8 * d + 24) * n
+        st_gbs = st_bytes / (st_ms * 1e-3) / 1e9
+        kernels["pf_step_kernel"] = {
+            "kernel_us": st_ms * 1e3, "algorithmic_bytes_per_launch": st_bytes, "achieved": st_gbs, "frac": st_gbs / peak,
+            "what": "one filter step per GPU in one launch (global resampling: parent CDF rows / states read over NVLink, tile "
+                    "records mailed to every rank, prefix table built by each rank's last CTA); duration = timed region / T"}
+        roofline = {
+            "bound": "hbm", "kernel": "pf_step_kernel: " + kernels["pf_step_kernel"]["what"],
+            "achieved": st_gbs, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": st_gbs / peak, "traffic": None,
+            "kernel_us": st_ms * 1e3, "algorithmic_bytes_per_launch": st_bytes, "algorithmic_bytes_per_particle_step": 8 * d + 24,
+            "note": "per GPU; algorithmic bytes = SURVEY 8d's whole-step figure (8d + 24 per particle-step)",
+        }
+    elif getattr(plan, "stepmode", False):
         # the step IS one kernel: launch t = 1 (reads step 0's CDF / tile records, writes its own) is what every later
         # step repeats; re-launching it is idempotent
         plan.cm.lib.gjb_model_pf_step(C.byref(plan.sargs[0]), stream)
@@ -683,9 +700,10 @@ def run_ours(args):
             "workload": workload_string(n, T, d),
             "particles_per_gpu": n, "T": T, "d": d,
             "l2": "flushed between timed steps (256 MiB write)",
-            "mode": "graph (3 launches/step, cross-rank hand-offs fused into the kernels)" if global_resample else args.mode,
-            "multi_gpu": ("one filter over all ranks' particles, global systematic resampling: per step 3 push/poll exchanges "
-                          "(max, rank masses, barrier) and ancestor writes / state gathers over NVLink peer memory; weak scaling"
+            "mode": "step (1 launch/step/GPU, one cross-rank hand-off per step inside the kernel)" if global_resample else args.mode,
+            "multi_gpu": ("one filter over all ranks' particles, global systematic resampling: per step every CTA mails its tile record "
+                          "to every rank, each rank's last CTA waits for all of them (the step's one hand-off) and builds the prefix "
+                          "table; parent CDF rows / states are read over NVLink peer memory; weak scaling"
                           if global_resample else "islands: each rank filters its own block (local resampling, global RNG lanes "
                           "differ by key), the shard log-marginal-likelihood terms are combined by one NCCL all-reduce (max + sum-exp "
                           "on 8 bytes) per run, inside the timed region; weak scaling. --multi-gpu global times the "

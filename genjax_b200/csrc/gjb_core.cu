@@ -556,8 +556,13 @@ __global__ void __launch_bounds__(kThreads) te_resample_kernel(const __grid_cons
                                 (uint64_t)__ldg(A.key_dev + 2) | ((uint64_t)__ldg(A.key_dev + 3) << 32));
   int32_t anc[kTeItems];
   int E;
-  const uint64_t S = A.cdf_peers ? te_pull<true, false>(A.recs, A.n_tiles_total, A.cdf, A.cdf_peers, A.n_total, u0, w_lo, w_n, sm, anc, &E)
-                                 : te_pull<false, false>(A.recs, A.n_tiles_total, A.cdf, nullptr, A.n_total, u0, w_lo, w_n, sm, anc, &E);
+  uint64_t S;
+  if (A.table)
+    S = A.cdf_peers ? te_pull_table<true>(A.table, (int)blockIdx.x, A.cdf, A.cdf_peers, A.n_total, u0, w_lo, w_n, sm, anc, &E)
+                    : te_pull_table<false>(A.table, (int)blockIdx.x, A.cdf, nullptr, A.n_total, u0, w_lo, w_n, sm, anc, &E);
+  else
+    S = A.cdf_peers ? te_pull<true, false>(A.recs, A.n_tiles_total, A.cdf, A.cdf_peers, A.n_total, u0, w_lo, w_n, sm, anc, &E)
+                    : te_pull<false, false>(A.recs, A.n_tiles_total, A.cdf, nullptr, A.n_total, u0, w_lo, w_n, sm, anc, &E);
   if (blockIdx.x == 0 && threadIdx.x == 0 && A.lse_out) te_write_lse(A.lse_out, E, S, A.n_total);
   int32_t* out = A.ancestors + (int64_t)blockIdx.x * kTeTile + threadIdx.x * kTeItems;
   const int j0 = threadIdx.x * kTeItems;
@@ -567,6 +572,114 @@ __global__ void __launch_bounds__(kThreads) te_resample_kernel(const __grid_cons
   } else {
 #pragma unroll
     for (int k = 0; k < kTeItems; ++k) if (j0 + k < w_n) out[k] = anc[k];
+  }
+}
+
+// The table of one step as a launch of its own: one CTA of 1024 threads per device, resident beside the step kernel.
+// Polls the mailbox until every tile of every rank carries the step's tag (the cross-rank hand-off), then E, the
+// aligned tile masses, their inclusive prefix, the offspring count at every tile boundary, and the parent-tile range of
+// every local window.  Same arithmetic as te_finish_step's last-CTA path (gjb_step.cuh), four times the threads.
+constexpr int kTabThreads = 1024;
+__global__ void __launch_bounds__(kTabThreads) te_table_kernel(const __grid_constant__ gjb_te_table_args A) {
+  __shared__ int32_t cnt[kTeMaxTiles];
+  __shared__ uint64_t red[kTabThreads / 32];
+  __shared__ int32_t ired[kTabThreads / 32];
+  pdl_launch_dependents();
+  const gjb_step_link* L = A.link;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_tiles = L->world * L->tiles_per_rank;
+  const uint32_t tag = te_tag(L, A.step);
+  const uint64_t* box = te_mail_slot(L->mailbox[L->rank], A.step, 0);
+  constexpr int kPer = kTeMaxTiles / kTabThreads;  // 4 records per thread, blocked
+  uint64_t m[kPer];
+  int e[kPer];
+  int emax = GJB_TE_E_NONE;
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    const int t = tid * kPer + k;
+    m[k] = 0; e[k] = GJB_TE_E_NONE;
+    if (t < n_tiles) {
+      const uint64_t* r = box + (int64_t)t * GJB_TE_LL_WORDS;
+      uint64_t w0, w1, w2;
+      for (;;) {
+        w0 = te_ld_volatile(r); w1 = te_ld_volatile(r + 1); w2 = te_ld_volatile(r + 2);
+        if ((uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag && (uint32_t)(w2 >> 32) == tag) break;
+        __nanosleep(40);
+      }
+      m[k] = (w0 & 0xffffffffull) | (w1 << 32);
+      e[k] = (int)(uint32_t)w2;
+      if (m[k]) emax = max(emax, e[k]);
+    }
+  }
+  emax = __reduce_max_sync(0xffffffffu, emax);
+  if (lane == 0) ired[warp] = emax;
+  __syncthreads();
+  int E = ired[lane];
+  E = __reduce_max_sync(0xffffffffu, E);
+  uint64_t pre[kPer];
+  uint8_t sft[kPer];
+  uint64_t run = 0;
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    sft[k] = (uint8_t)(m[k] ? min(E - e[k], 63) : 63);
+    run += m[k] >> sft[k];
+    pre[k] = run;
+  }
+  uint64_t inc = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) red[warp] = inc;
+  __syncthreads();
+  uint64_t wv = red[lane], winc = wv;  // every warp scans the 32 warp totals
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t v = __shfl_up_sync(0xffffffffu, winc, o);
+    if (lane >= o) winc += v;
+  }
+  const uint64_t S = __shfl_sync(0xffffffffu, winc, 31);
+  const uint64_t wexc = __shfl_sync(0xffffffffu, winc - wv, warp);
+  const uint64_t excl = wexc + inc - run;
+  const double u0 = resample_u0(__ldg(A.reskey), __ldg(A.reskey + 1), (uint64_t)__ldg(A.reskey + 2) | ((uint64_t)__ldg(A.reskey + 3) << 32));
+  const double scale = S ? __ddiv_rn((double)A.n_total, (double)S) : 0.0;
+  const int32_t nt = (int32_t)A.n_total;
+  gjb_step_table* tab = A.table_out;
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    const int t = tid * kPer + k;
+    if (t < n_tiles) {
+      const uint64_t cur = pre[k] + excl;
+      tab->pre[t] = cur;
+      tab->shf[t] = sft[k];
+      cnt[t] = S ? offspring_cnt(cur, S, scale, u0, nt) : 0;
+    }
+  }
+  if (tid == 0) {
+    tab->S = S; tab->E = E; tab->n_tiles_total = n_tiles;
+    if (A.lse_out) te_write_lse(A.lse_out, E, S, A.n_total);
+  }
+  __syncthreads();
+  if (S == 0) return;
+  const int n_win = (int)((A.n_local + kTeTile - 1) / kTeTile);
+  for (int w = tid; w < n_win; w += kTabThreads) {
+    const int64_t ws = A.slot_offset + (int64_t)w * kTeTile;
+    const int64_t left = A.slot_offset + A.n_local - ws;
+    const int64_t we = ws + (left < kTeTile ? left : kTeTile);
+    int lo = 0, hi = n_tiles;  // smallest p with cnt(P_p) > ws
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((int64_t)cnt[mid] > ws) hi = mid; else lo = mid + 1;
+    }
+    const int p_first = lo;
+    hi = n_tiles;                // smallest p with cnt(P_p) >= we
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((int64_t)cnt[mid] >= we) hi = mid; else lo = mid + 1;
+    }
+    tab->win[w][0] = p_first;
+    tab->win[w][1] = lo < n_tiles ? lo : n_tiles - 1;
   }
 }
 
@@ -731,8 +844,26 @@ int gjb_te_masses(const float* logw, int64_t n, uint64_t* cdf, gjb_tile_rec* rec
   return launch_status();
 }
 
+int gjb_te_table(const gjb_te_table_args* a, void* stream) {
+  if (!a || !a->link || !a->reskey || !a->table_out || a->n_local <= 0 || a->n_total < a->n_local || a->slot_offset < 0) return GJB_E_ARG;
+  if (a->step < 0 || a->step >= 65535) return GJB_E_RANGE;
+  if (a->n_total > (1LL << 26) || (a->n_total + kTeTile - 1) / kTeTile > kTeMaxTiles) return GJB_E_RANGE;
+  if (a->flags & GJB_STEP_PDL) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(kTabThreads); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, te_table_kernel, *a);
+  }
+  te_table_kernel<<<1, kTabThreads, 0, (cudaStream_t)stream>>>(*a);
+  return launch_status();
+}
+
 int gjb_te_resample(const gjb_te_resample_args* a, void* stream) {
-  if (!a || !a->cdf || !a->recs || !a->key_dev || !a->ancestors || a->out_n < 0 || a->out_lo < 0) return GJB_E_ARG;
+  if (!a || !a->cdf || (!a->recs && !a->table) || !a->key_dev || !a->ancestors || a->out_n < 0 || a->out_lo < 0) return GJB_E_ARG;
+  if (a->table && (a->out_lo % kTeTile) != 0) return GJB_E_ARG;  // the table's windows are the device's own aligned windows
   if (a->n_tiles_total <= 0 || a->n_total <= 0 || a->out_lo + a->out_n > a->n_total) return GJB_E_ARG;
   // S <= n_total * (2^36 + 1) must stay below 2^63 (signed conversion in offspring_cnt): n_total <= 2^26
   if (a->n_tiles_total > kTeMaxTiles || a->n_total > (1LL << 26)) return GJB_E_RANGE;

@@ -45,7 +45,39 @@ struct TeSmem {
   __align__(16) int32_t ired[kThreads / 32];
   __align__(16) float fred[kThreads / 32];
   int32_t p_lo, p_hi;
+  uint64_t tile_mass;   // te_publish -> te_finish_step
+  int32_t tile_e;
+  int32_t is_last;
 };
+
+// ---- small PTX helpers (plain C++ under the host shims of tests/)
+__device__ __forceinline__ uint64_t te_ld_volatile(const uint64_t* p) {
+#if defined(__CUDACC__)
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+#else
+  return *reinterpret_cast<const volatile uint64_t*>(p);
+#endif
+}
+__device__ __forceinline__ void te_st_volatile(uint64_t* p, uint64_t v) {
+#if defined(__CUDACC__)
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"((unsigned long long)v) : "memory");
+#else
+  *reinterpret_cast<volatile uint64_t*>(p) = v;
+#endif
+}
+// programmatic dependent launch (sm_90+): let the next launch on the stream start early / wait for the previous one
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if defined(__CUDACC__)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDACC__)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
 
 // t = fl32(lw * log2e) clamped to +-2^20, or -inf when lw is not finite (NaN, +-inf: mass 0)
 __device__ __forceinline__ float te_t(float lw) {
@@ -77,7 +109,7 @@ __device__ __forceinline__ uint64_t te_q(float t, int kc) {
 // Producer: the 8 consecutive weights of this thread (slot base tid * 8 of the tile; lw = -inf past the end) ->
 // cdf_tile[tid * 8 + k] (2048 entries, padding repeats the total) and *rec.  All kThreads threads call.
 __device__ __forceinline__ void te_publish(const float (&lw)[kTeItems], uint64_t* __restrict__ cdf_tile,
-                                           gjb_tile_rec* __restrict__ rec, TeSmem& sm) {
+                                           gjb_tile_rec* __restrict__ rec /* nullable */, TeSmem& sm) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float t[kTeItems];
   float tm = -INFINITY;
@@ -117,9 +149,11 @@ __device__ __forceinline__ void te_publish(const float (&lw)[kTeItems], uint64_t
 #pragma unroll
   for (int k = 0; k < kTeItems; k += 2) dst[k >> 1] = make_ulonglong2(c[k] + excl, c[k + 1] + excl);
   if (tid == kThreads - 1) {
+    sm.tile_mass = c[kTeItems - 1] + excl;  // read by te_finish_step after its barrier
+    sm.tile_e = e;
     // one 16-byte store: a consumer never sees a torn record
-    *reinterpret_cast<uint4*>(rec) = make_uint4((uint32_t)(c[kTeItems - 1] + excl), (uint32_t)((c[kTeItems - 1] + excl) >> 32),
-                                                (uint32_t)e, 0u);
+    if (rec) *reinterpret_cast<uint4*>(rec) = make_uint4((uint32_t)(c[kTeItems - 1] + excl), (uint32_t)((c[kTeItems - 1] + excl) >> 32),
+                                                         (uint32_t)e, 0u);
   }
 }
 
@@ -281,7 +315,9 @@ __device__ __forceinline__ uint64_t te_pull(const gjb_tile_rec* __restrict__ rec
   if (p_lo <= p_hi) te_ld_row<kCg>(row_of(p_lo), c, c_prev);
   for (int p = p_lo; p <= p_hi; ++p) {
     uint64_t cn[kTeItems], cn_prev = 0;
+#ifndef GJB_NO_PREFETCH
     if (p < p_hi) te_ld_row<kCg>(row_of(p + 1), cn, cn_prev);
+#endif
     const uint64_t base = p ? sm.pre[p - 1] : 0ull;
     if (sm.pre[p] != base) {  // (a tile without aligned mass owns nothing)
       const int s = sm.shf[p];
@@ -298,6 +334,259 @@ __device__ __forceinline__ uint64_t te_pull(const gjb_tile_rec* __restrict__ rec
       }
     }
     if (p < p_hi) {
+#ifdef GJB_NO_PREFETCH
+      te_ld_row<kCg>(row_of(p + 1), cn, cn_prev);
+#endif
+#pragma unroll
+      for (int k = 0; k < kTeItems; ++k) c[k] = cn[k];
+      c_prev = cn_prev;
+    }
+  }
+  __syncthreads();
+  GJB_TP(5);
+  // ---- inclusive max-scan over the window: 8 consecutive slots per thread, warp shuffle, block
+  int32_t v[kTeItems];
+  {
+    const int4 a = *reinterpret_cast<const int4*>(sm.heads + tid * kTeItems);
+    const int4 b = *reinterpret_cast<const int4*>(sm.heads + tid * kTeItems + 4);
+    v[0] = a.x; v[1] = max(v[0], a.y); v[2] = max(v[1], a.z); v[3] = max(v[2], a.w);
+    v[4] = max(v[3], b.x); v[5] = max(v[4], b.y); v[6] = max(v[5], b.z); v[7] = max(v[6], b.w);
+  }
+  int32_t incm = v[kTeItems - 1];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t t = __shfl_up_sync(0xffffffffu, incm, o);
+    if (lane >= o) incm = max(incm, t);
+  }
+  if (lane == 31) sm.ired[warp] = incm;
+  const int32_t wexc = __shfl_up_sync(0xffffffffu, incm, 1);
+  __syncthreads();
+  int32_t pre = lane ? wexc : 0;
+  {
+    const int4 a = *reinterpret_cast<const int4*>(sm.ired), b = *reinterpret_cast<const int4*>(sm.ired + 4);
+    const int32_t wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) if (w < warp) pre = max(pre, wv[w]);
+  }
+#pragma unroll
+  for (int k = 0; k < kTeItems; ++k) anc[k] = max(v[k], pre) - 1;
+  GJB_TP(6);
+  return S;
+}
+
+// ------------------------------------------------------------------ step table (Design: include/genjax_b200.h)
+
+__device__ __forceinline__ uint32_t te_tag(const gjb_step_link* L, int step) {
+  const uint64_t epoch = __ldg(reinterpret_cast<const unsigned long long*>(L->epoch));
+  return (uint32_t)(((epoch + 1) << 16) | (uint64_t)((step + 1) & 0xffff));
+}
+__device__ __forceinline__ uint64_t* te_mail_slot(uint64_t* mailbox, int step, int tile) {
+  return mailbox + ((int64_t)(step & 1) * kTeMaxTiles + tile) * GJB_TE_LL_WORDS;
+}
+
+// {E ln 2, S, log-mean-exp} of a resampling (one thread)
+__device__ __forceinline__ void te_write_lse(double* out, int E, uint64_t S, int64_t n_total);
+
+// End of a filter-step CTA (all kThreads threads call, after te_publish): mail this tile's record to every rank, take a
+// ticket; the CTA that draws the last ticket of the launch waits for the records of ALL tiles of ALL ranks, and builds
+// the table the next launch consumes: E, S, the inclusive prefix of the aligned tile masses, and per LOCAL window the
+// range of parent tiles with offspring in it.  `reskey` = {key0, key1, index_lo, index_hi} of the resampling of THESE
+// weights.  Uses sm.pre / sm.shf / sm.red / sm.ired (the CTA's window data is dead by now).
+__device__ __forceinline__ void te_finish_step(const gjb_step_link* __restrict__ L, int step, int64_t slot_offset, int64_t n_local,
+                                               int64_t n_total, const uint32_t* __restrict__ reskey, gjb_step_table* __restrict__ tab,
+                                               double* __restrict__ lse_out, TeSmem& sm) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int world = L->world, tpr = L->tiles_per_rank;
+  const uint32_t tag = te_tag(L, step);
+  __syncthreads();  // every bulk store (CDF row, state rows, weights) of this CTA has been issued; tile_mass / tile_e are set
+  if (tid < world) {
+    __threadfence();  // ... and is visible in this device's L2 before the record that announces it leaves
+    const uint64_t hi = (uint64_t)tag << 32, m = sm.tile_mass;
+    uint64_t* dst = te_mail_slot(L->mailbox[tid], step, L->rank * tpr + (int)blockIdx.x);
+    te_st_volatile(dst + 0, (m & 0xffffffffull) | hi);
+    te_st_volatile(dst + 1, (m >> 32) | hi);
+    te_st_volatile(dst + 2, (uint64_t)(uint32_t)sm.tile_e | hi);
+  }
+  if (!tab) return;  // mail only: gjb_te_table builds the table beside this launch
+  if (tid == 0) sm.is_last = atomicAdd(L->ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!sm.is_last) return;
+  // ---------------- the last CTA of this rank
+  const int n_tiles = world * tpr;
+  const int per = (n_tiles + kThreads - 1) / kThreads;
+  const int t0 = tid * per;
+  const uint64_t* box = te_mail_slot(L->mailbox[L->rank], step, 0);
+  constexpr int kKeep = 4;  // records a thread keeps in registers between the two passes (n_tiles <= 1024)
+  uint64_t km[kKeep];
+  int ke[kKeep];
+  // pass 1: wait for every record (this is the cross-rank barrier of the step), E = max exponent over tiles with mass
+  int emax = GJB_TE_E_NONE;
+  auto poll = [&](int t, uint64_t& m, int& e) {
+    const uint64_t* r = box + (int64_t)t * GJB_TE_LL_WORDS;
+    uint64_t w0, w1, w2;
+    for (;;) {
+      w0 = te_ld_volatile(r); w1 = te_ld_volatile(r + 1); w2 = te_ld_volatile(r + 2);
+      if ((uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag && (uint32_t)(w2 >> 32) == tag) break;
+      __nanosleep(40);
+    }
+    m = (w0 & 0xffffffffull) | (w1 << 32);
+    e = (int)(uint32_t)w2;
+    if (m) emax = max(emax, e);
+  };
+#pragma unroll
+  for (int k = 0; k < kKeep; ++k) {
+    km[k] = 0; ke[k] = GJB_TE_E_NONE;
+    if (k < per && t0 + k < n_tiles) poll(t0 + k, km[k], ke[k]);
+  }
+  for (int k = kKeep; k < per; ++k) {
+    uint64_t m; int e;
+    if (t0 + k < n_tiles) poll(t0 + k, m, e);
+  }
+  emax = __reduce_max_sync(0xffffffffu, emax);
+  if (lane == 0) sm.ired[warp] = emax;
+  __syncthreads();
+  int E = sm.ired[0];
+#pragma unroll
+  for (int w = 1; w < kThreads / 32; ++w) E = max(E, sm.ired[w]);
+  // pass 2: aligned masses, inclusive prefix (records beyond the kept ones are re-read: they are complete now)
+  uint64_t run = 0;
+  auto fold = [&](int t, uint64_t m, int e) {
+    const int sft = m ? min(E - e, 63) : 63;
+    run += m >> sft;
+    sm.pre[t] = run;
+    sm.shf[t] = (uint8_t)sft;
+  };
+#pragma unroll
+  for (int k = 0; k < kKeep; ++k)
+    if (k < per && t0 + k < n_tiles) fold(t0 + k, km[k], ke[k]);
+  for (int k = kKeep; k < per; ++k) {
+    const int t = t0 + k;
+    if (t < n_tiles) {
+      const uint64_t* r = box + (int64_t)t * GJB_TE_LL_WORDS;
+      const ulonglong2 w01 = __ldcg(reinterpret_cast<const ulonglong2*>(r));
+      fold(t, (w01.x & 0xffffffffull) | (w01.y << 32), (int)(uint32_t)__ldcg(reinterpret_cast<const unsigned long long*>(r + 2)));
+    }
+  }
+  uint64_t inc = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) sm.red[warp] = inc;
+  __syncthreads();
+  uint64_t excl = inc - run, S = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const uint64_t v = sm.red[w];
+    if (w < warp) excl += v;
+    S += v;
+  }
+  // cumulative offspring count at every tile boundary (shared memory, when it fits the window scratch), the table
+  const bool cnt_in_smem = n_tiles <= kTeTile;
+  const double u0 = resample_u0(__ldg(reskey), __ldg(reskey + 1), (uint64_t)__ldg(reskey + 2) | ((uint64_t)__ldg(reskey + 3) << 32));
+  const double scale = S ? __ddiv_rn((double)n_total, (double)S) : 0.0;
+  const int32_t nt = (int32_t)n_total;
+  for (int k = 0; k < per; ++k) {
+    const int t = t0 + k;
+    if (t < n_tiles) {
+      const uint64_t cur = sm.pre[t] + excl;
+      sm.pre[t] = cur;
+      tab->pre[t] = cur;
+      tab->shf[t] = sm.shf[t];
+      if (cnt_in_smem && S) sm.heads[t] = offspring_cnt(cur, S, scale, u0, nt);
+    }
+  }
+  if (tid == 0) {
+    tab->S = S; tab->E = E; tab->n_tiles_total = n_tiles;
+    if (lse_out) te_write_lse(lse_out, E, S, n_total);
+    *L->ticket = 0u;  // the next launch on the stream starts from zero
+  }
+  __syncthreads();  // sm.pre / sm.heads complete
+  // window table: for each local window the first tile whose offspring reach it and the tile that owns its last slot
+  const int n_win = (int)((n_local + kTeTile - 1) / kTeTile);
+  if (S != 0) {
+    for (int w = tid; w < n_win; w += kThreads) {
+      const int64_t ws = slot_offset + (int64_t)w * kTeTile;
+      const int64_t left = slot_offset + n_local - ws;
+      const int64_t we = ws + (left < kTeTile ? left : kTeTile);
+      int lo = 0, hi = n_tiles;  // smallest p with cnt(P_p) > ws
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const int64_t c = cnt_in_smem ? (int64_t)sm.heads[mid] : (int64_t)offspring_cnt(sm.pre[mid], S, scale, u0, nt);
+        if (c > ws) hi = mid; else lo = mid + 1;
+      }
+      const int p_first = lo;
+      hi = n_tiles;                // smallest p with cnt(P_p) >= we (lo continues from p_first)
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const int64_t c = cnt_in_smem ? (int64_t)sm.heads[mid] : (int64_t)offspring_cnt(sm.pre[mid], S, scale, u0, nt);
+        if (c >= we) hi = mid; else lo = mid + 1;
+      }
+      tab->win[w][0] = p_first;
+      tab->win[w][1] = lo < n_tiles ? lo : n_tiles - 1;
+    }
+  }
+}
+
+// Consumer on the table of the previous launch: global parent ids of the offspring slots [w_lo, w_lo + w_n) of local
+// window `w_local`, blocked layout as te_pull.  No prefix work: S, E, the parent tile range and the tile prefixes are read.
+template <bool kCg>
+__device__ __forceinline__ uint64_t te_pull_table(const gjb_step_table* __restrict__ tab, int w_local,
+                                                  const uint64_t* __restrict__ cdf, const gjb_peers* cdf_peers, int64_t n_total,
+                                                  double u0, int64_t w_lo, int w_n, TeSmem& sm, int32_t (&anc)[kTeItems], int* e_out) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t S = __ldcg(reinterpret_cast<const unsigned long long*>(&tab->S));
+  *e_out = __ldcg(&tab->E);
+  const int2 win = __ldcg(reinterpret_cast<const int2*>(&tab->win[w_local][0]));
+  *reinterpret_cast<int4*>(sm.heads + tid * kTeItems) = make_int4(0, 0, 0, 0);
+  *reinterpret_cast<int4*>(sm.heads + tid * kTeItems + 4) = make_int4(0, 0, 0, 0);
+  if (S == 0) {
+#pragma unroll
+    for (int k = 0; k < kTeItems; ++k) anc[k] = (int32_t)(w_lo + tid * kTeItems + k);
+    return 0;
+  }
+  const int p_lo = win.x, p_hi = win.y;
+  const int tiles_per_rank = cdf_peers ? (int)(cdf_peers->n_per_rank / kTeTile) : 0;
+  auto row_of = [&](int p) -> const uint64_t* {
+    if (cdf_peers) {
+      const int owner = p / tiles_per_rank;
+      return reinterpret_cast<const uint64_t*>(cdf_peers->base[owner]) + (int64_t)(p - owner * tiles_per_rank) * kTeTile + tid * kTeItems;
+    }
+    return cdf + (int64_t)p * kTeTile + tid * kTeItems;
+  };
+  uint64_t c[kTeItems], c_prev = 0;
+  te_ld_row<kCg>(row_of(p_lo), c, c_prev);
+  const double scale = __ddiv_rn((double)n_total, (double)S);
+  const int32_t nt = (int32_t)n_total;
+  const int32_t wl = (int32_t)w_lo, wh = (int32_t)(w_lo + w_n);
+  GJB_TP(4);
+  __syncthreads();  // the window is clear
+  for (int p = p_lo; p <= p_hi; ++p) {
+    uint64_t cn[kTeItems], cn_prev = 0;
+#ifndef GJB_NO_PREFETCH
+    if (p < p_hi) te_ld_row<kCg>(row_of(p + 1), cn, cn_prev);
+#endif
+    const uint64_t base = p ? __ldcg(reinterpret_cast<const unsigned long long*>(tab->pre + p - 1)) : 0ull;
+    const uint64_t top = __ldcg(reinterpret_cast<const unsigned long long*>(tab->pre + p));
+    if (top != base) {  // (a tile without aligned mass owns nothing)
+      const int sft = __ldcg(tab->shf + p);
+      int32_t prev = min(max(offspring_cnt(base + (c_prev >> sft), S, scale, u0, nt), wl), wh);
+      const int32_t last = min(max(offspring_cnt(base + (c[kTeItems - 1] >> sft), S, scale, u0, nt), wl), wh);
+      if (last > prev) {  // this thread's 8 parents own slots of the window
+        const int32_t id1 = p * kTeTile + tid * kTeItems + 1;
+#pragma unroll
+        for (int k = 0; k < kTeItems; ++k) {
+          const int32_t cur = (k == kTeItems - 1) ? last : min(max(offspring_cnt(base + (c[k] >> sft), S, scale, u0, nt), wl), wh);
+          if (cur > prev) sm.heads[prev - wl] = id1 + k;
+          prev = cur;
+        }
+      }
+    }
+    if (p < p_hi) {
+#ifdef GJB_NO_PREFETCH
+      te_ld_row<kCg>(row_of(p + 1), cn, cn_prev);
+#endif
 #pragma unroll
       for (int k = 0; k < kTeItems; ++k) c[k] = cn[k];
       c_prev = cn_prev;

@@ -31,6 +31,7 @@ particle loop into a per-thread ``Uni`` struct computed once per launch.
 from __future__ import annotations
 
 import json
+import os
 
 import numpy as np
 
@@ -451,6 +452,8 @@ class _Generator:
         self.stage = stage
         out = [f"// generated by genjax_b200.gen.codegen -- model '{ir.name}' [{ir.digest}] "
                f"({'group mapping, G=%d' % self.G if self.group else 'quad mapping'})",
+               *(["#define GJB_NO_PREFETCH  // parent rows are loaded tile by tile (prefetching the next tile spills at 64 registers: measured slower)"]
+                 if os.environ.get("GJB_STEP_PREFETCH", "0") == "0" else []),
                '#include "gjb_model.cuh"', '#include "gjb_resample.cuh"', "namespace {"]
         out.extend(em.consts)
         out.append("constexpr int kThreads = 256;")
@@ -829,33 +832,40 @@ class _Generator:
         wbuf = "reinterpret_cast<float*>(sm.pre)" if self.group else "reinterpret_cast<float*>(sm.heads)"
         out.append(f"  float* const wbuf = {wbuf};  // this window's new weights (block-shared)")
         out.append("  io.te_w = wbuf - w_loc;")
+        hoist = (not self.group) and os.environ.get("GJB_STEP_HOIST", "1") != "0"
+        out.append("  gjb::pdl_launch_dependents();  // the next launch of the stream may queue up behind this one right away")
         out.append("  GJB_TP(14); GJB_TP(0);")
         out.append("  const uint32_t key0 = __ldg(A.key_dev), key1 = __ldg(A.key_dev + 1);")
-        out.append("  // the tile records are requested first; everything up to te_pull is independent ALU work that hides their latency")
-        out.append("  const bool fast = A.prev_cdf && A.n_tiles_total <= 2 * kThreads;")
-        out.append("  gjb::TeRecs2 recs2;")
-        out.append("  if (fast) recs2 = A.cdf_peers ? gjb::te_load_recs2<true>(A.prev_recs, A.n_tiles_total) : gjb::te_load_recs2<false>(A.prev_recs, A.n_tiles_total);")
         if not self.group:
-            out.append("  // the thread's own 8 slots = 2 global quads: their random numbers do not depend on the ancestors")
-            out.append("  const int64_t q0 = (w_loc >> 2) + tid * 2;")
+            out.append("  const int64_t q0 = (w_loc >> 2) + tid * 2;  // the thread's own 8 slots = 2 global quads")
             out.append("  const int64_t qw = (w_loc + w_n + 3) >> 2;")
+        if hoist:
+            out.append("  // their random numbers do not depend on the previous launch, so they are drawn BEFORE this launch waits for it")
+            out.append("  // (programmatic dependent launch: this overlaps the previous kernel's tail)")
             out.append("  QRng R0, R1;")
             out.append("  quad_rng<true>(fl, key0, key1, (A.idx_offset >> 2) + (uint64_t)q0, R0);")
             out.append("  quad_rng<true>(fl, key0, key1, (A.idx_offset >> 2) + (uint64_t)q0 + 1, R1);")
         out.append("  GJB_TP(1);")
+        out.append("  gjb::pdl_wait();  // everything the previous launch wrote (state, CDF rows, table / records) is visible from here on")
         out.append("  if (A.prev_cdf) {  // ancestors of MY slots: output-slot systematic resampling of the previous step")
         out.append("    const double u0 = gjb::resample_u0(__ldg(A.prev_key), __ldg(A.prev_key + 1), (uint64_t)__ldg(A.prev_key + 2) | ((uint64_t)__ldg(A.prev_key + 3) << 32));")
         out.append("    int32_t anc[gjb::kTeItems];")
         out.append("    int E;")
-        out.append("    uint64_t S;")
         out.append("    const int64_t w_glob = A.slot_offset + w_loc;")
-        out.append("    if (fast) S = A.cdf_peers")
-        out.append("        ? gjb::te_pull<true, true>(A.prev_recs, A.n_tiles_total, A.prev_cdf, A.cdf_peers, A.n_total, u0, w_glob, w_n, sm, anc, &E, &recs2)")
-        out.append("        : gjb::te_pull<false, true>(A.prev_recs, A.n_tiles_total, A.prev_cdf, nullptr, A.n_total, u0, w_glob, w_n, sm, anc, &E, &recs2);")
-        out.append("    else S = A.cdf_peers")
-        out.append("        ? gjb::te_pull<true, false>(A.prev_recs, A.n_tiles_total, A.prev_cdf, A.cdf_peers, A.n_total, u0, w_glob, w_n, sm, anc, &E)")
-        out.append("        : gjb::te_pull<false, false>(A.prev_recs, A.n_tiles_total, A.prev_cdf, nullptr, A.n_total, u0, w_glob, w_n, sm, anc, &E);")
-        out.append("    if (blockIdx.x == 0 && tid == 0 && A.prev_lse) gjb::te_write_lse(A.prev_lse, E, S, A.n_total);")
+        out.append("    if (A.table_in) {  // the previous launch's last CTA left the prefix table: no prefix work here")
+        out.append("      // (everything the previous launch produced is read through L2: with programmatic dependent launch this CTA may")
+        out.append("      // have become resident before that launch finished, so nothing may come from a possibly stale L1 line)")
+        out.append("      gjb::te_pull_table<true>(A.table_in, (int)blockIdx.x, A.prev_cdf, A.cdf_peers, A.n_total, u0, w_glob, w_n, sm, anc, &E);")
+        out.append("    } else {           // single device, table-free: every CTA forms the tile prefix from the plain records")
+        out.append("      uint64_t S;")
+        out.append("      if (A.n_tiles_total <= 2 * kThreads) {")
+        out.append("        const gjb::TeRecs2 recs2 = gjb::te_load_recs2<true>(A.prev_recs, A.n_tiles_total);")
+        out.append("        S = gjb::te_pull<true, true>(A.prev_recs, A.n_tiles_total, A.prev_cdf, nullptr, A.n_total, u0, w_glob, w_n, sm, anc, &E, &recs2);")
+        out.append("      } else {")
+        out.append("        S = gjb::te_pull<true, false>(A.prev_recs, A.n_tiles_total, A.prev_cdf, nullptr, A.n_total, u0, w_glob, w_n, sm, anc, &E);")
+        out.append("      }")
+        out.append("      if (blockIdx.x == 0 && tid == 0 && A.prev_lse) gjb::te_write_lse(A.prev_lse, E, S, A.n_total);")
+        out.append("    }")
         out.append("    const int4 a0 = make_int4(anc[0], anc[1], anc[2], anc[3]), a1 = make_int4(anc[4], anc[5], anc[6], anc[7]);")
         out.append("    *reinterpret_cast<int4*>(sm.heads + tid * gjb::kTeItems) = a0;  // (a thread's own slots: no hazard with the scan)")
         out.append("    *reinterpret_cast<int4*>(sm.heads + tid * gjb::kTeItems + 4) = a1;")
@@ -870,25 +880,25 @@ class _Generator:
         out.append("  float run_max = -INFINITY;")
         if self.group:
             out.append("  __syncthreads();  // every group reads ancestors other threads resolved")
-            out.append("  if (A.cdf_peers) run_groups<true, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, w_loc, w_loc + w_n, kPPB, run_max);")
-            out.append("  else run_groups<false, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, w_loc, w_loc + w_n, kPPB, run_max);")
+            out.append("  run_groups<true, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, w_loc, w_loc + w_n, kPPB, run_max);")
             out.append("  __syncthreads();  // the window's weights are complete")
         else:
-            out.append("  if (A.cdf_peers) {")
-            out.append("    if (q0 < qw) run_quads<true, true, false, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0, q0 + 1, 1, run_max, &R0);")
-            out.append("    if (q0 + 1 < qw) run_quads<true, true, false, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0 + 1, q0 + 2, 1, run_max, &R1);")
-            out.append("  } else {")
-            out.append("    if (q0 < qw) run_quads<false, true, false, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0, q0 + 1, 1, run_max, &R0);")
-            out.append("    if (q0 + 1 < qw) run_quads<false, true, false, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0 + 1, q0 + 2, 1, run_max, &R1);")
-            out.append("  }")
+            if hoist:
+                out.append("  if (q0 < qw) run_quads<true, true, false, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0, q0 + 1, 1, run_max, &R0);")
+                out.append("  if (q0 + 1 < qw) run_quads<true, true, false, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0 + 1, q0 + 2, 1, run_max, &R1);")
+            else:
+                out.append("  const int64_t qe = q0 + 2 < qw ? q0 + 2 : qw;")
+                out.append("  run_quads<true, true, false, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0, qe, 1, run_max);")
         out.append("  GJB_TP(8);")
         out.append("  float lw[gjb::kTeItems];")
         out.append("#pragma unroll")
         out.append("  for (int k = 0; k < gjb::kTeItems; ++k) lw[k] = (tid * gjb::kTeItems + k < w_n) ? wbuf[tid * gjb::kTeItems + k] : -INFINITY;")
         if self.group:
             out.append("  __syncthreads();  // wbuf aliases sm.pre: everyone has its weights before te_publish reuses the scratch")
-        out.append("  gjb::te_publish(lw, A.cdf_out + w_loc, A.recs_out + blockIdx.x, sm);")
-        out.append("  GJB_TP(11); GJB_TP(15);")
+        out.append("  gjb::te_publish(lw, A.cdf_out + w_loc, A.recs_out ? A.recs_out + blockIdx.x : nullptr, sm);")
+        out.append("  GJB_TP(11);")
+        out.append("  if (A.link) gjb::te_finish_step(A.link, A.step, A.slot_offset, A.n, A.n_total, A.key_dev + 2, A.table_out, A.lse_out, sm);")
+        out.append("  GJB_TP(15);")
         out.append("}")
         return out
 
@@ -1111,19 +1121,31 @@ int gjb_model_trace_read(unsigned long long* dst, int n) {  // scratch/trace_ste
 }
 #endif
 int gjb_model_pf_step(const gjb_step_args* a, void* stream) {
-  if (!a || a->n <= 0 || a->n_total < a->n || !a->key_dev || !a->cdf_out || !a->recs_out) return GJB_E_ARG;
+  if (!a || a->n <= 0 || a->n_total < a->n || !a->key_dev || !a->cdf_out) return GJB_E_ARG;
+  if (!a->link && !a->recs_out) return GJB_E_ARG;  // table-free form needs the plain records (with link: table_out, or NULL = mail only)
+  if (!a->link && (a->cdf_peers || a->peer_args || a->slot_offset != 0 || a->n_total != a->n)) return GJB_E_MODE;  // several devices need the table form
   if ((a->idx_offset & 3) != 0 || a->slot_offset < 0 || (a->slot_offset % gjb::kTeTile) != 0) return GJB_E_ARG;
-  if ((reinterpret_cast<uintptr_t>(a->cdf_out) & 15) || (reinterpret_cast<uintptr_t>(a->recs_out) & 15)) return GJB_E_ARG;
+  if (a->step < 0 || a->step >= 65535) return GJB_E_RANGE;  // 16-bit step field of the record tags
+  if (reinterpret_cast<uintptr_t>(a->cdf_out) & 15) return GJB_E_ARG;
   for (int k = 0; k < NR; ++k) if (!a->state_out[k]) return GJB_E_ARG;
   // S <= n_total * (2^36 + 1) must stay below 2^63 (signed conversion in offspring_cnt)
   if (a->n_total > (1LL << 26)) return GJB_E_RANGE;
+  if ((a->n_total + gjb::kTeTile - 1) / gjb::kTeTile > gjb::kTeMaxTiles) return GJB_E_RANGE;
   if (a->prev_cdf) {
-    if (!a->prev_recs || !a->prev_key || a->n_tiles_total <= 0) return GJB_E_ARG;
-    if (a->n_tiles_total > gjb::kTeMaxTiles) return GJB_E_RANGE;
-    if ((int64_t)a->n_tiles_total * gjb::kTeTile < a->n_total) return GJB_E_ARG;
+    if ((!a->table_in && !a->prev_recs) || !a->prev_key) return GJB_E_ARG;
+    if (!a->table_in && (a->n_tiles_total <= 0 || a->n_tiles_total > gjb::kTeMaxTiles || (int64_t)a->n_tiles_total * gjb::kTeTile < a->n_total)) return GJB_E_ARG;
     if ((reinterpret_cast<uintptr_t>(a->prev_cdf) & 15) || (reinterpret_cast<uintptr_t>(a->prev_recs) & 15)) return GJB_E_ARG;
   }
   const int64_t tiles = (a->n + gjb::kTeTile - 1) / gjb::kTeTile;
+  if (a->flags & GJB_STEP_PDL) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)tiles); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, pf_step_kernel, *a);
+  }
   pf_step_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a);
   return (int)cudaGetLastError();
 }

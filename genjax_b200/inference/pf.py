@@ -213,8 +213,26 @@ class _Plan:
             if not self.cm.info.get("pf_step", False):
                 raise NotImplementedError("mode='step': this model's return value does not feed back as its state")
             self.te_tiles = tiles
-            self.te_cdf = torch.empty((2, tiles * cabi.TE_TILE), dtype=torch.int64, device=device)
+            import os
+
+            # table form: the last CTA of each launch builds the tile-prefix table for the next (the form several devices
+            # need); table-free form: every CTA forms the prefix from the plain tile records (faster on ONE device: B200,
+            # 1 M particles, 19-22 us against 26 us per step -- the serial tail of the last CTA costs more than the
+            # redundant prefix work it saves)
+            self.te_table = os.environ.get("GJB_STEP_TABLE", "0") == "1"
             self.te_recs = torch.empty((2, tiles, 2), dtype=torch.int64, device=device)
+            self.te_cdf = torch.empty((2, tiles * cabi.TE_TILE), dtype=torch.int64, device=device)
+            # what the last CTA of each launch leaves for the next (one table per step parity), the tile-record
+            # mailbox (single device: only this rank mails into it), run epoch and CTA ticket
+            self.te_tables = torch.zeros((2, C.sizeof(cabi.StepTable)), dtype=torch.uint8, device=device)
+            self.te_mailbox = torch.zeros(cabi.TE_MAILBOX_WORDS, dtype=torch.int64, device=device)
+            self.te_epoch = torch.zeros(1, dtype=torch.int64, device=device)
+            self.te_ticket = torch.zeros(1, dtype=torch.int32, device=device)
+            L = cabi.StepLink()
+            L.rank, L.world, L.tiles_per_rank = 0, 1, tiles
+            L.mailbox[0] = self.te_mailbox.data_ptr()
+            L.epoch, L.ticket = self.te_epoch.data_ptr(), self.te_ticket.data_ptr()
+            self.te_link = torch.from_numpy(np.frombuffer(bytes(L), dtype=np.uint8).copy()).to(device)
         self.analytic = pf.reference_max == "analytic"
         if self.analytic:
             from ..gen import bounds
@@ -288,13 +306,23 @@ class _Plan:
 
     def _build_step_args(self):
         """One ``gjb_step_args`` per step (ONE launch each) + the closing ``gjb_te_resample_args``."""
+        import os
+
         pf, ir, T, n = self.pf, self.ir, self.T, self.pf.n
         if pf.idx_offset % 4:
             raise ValueError("mode='step' needs idx_offset % 4 == 0 (quad RNG streams)")
+        if T >= 65535:
+            raise ValueError("mode='step' tags its tile records with a 16-bit step number: at most 65534 steps per run")
+        pdl = os.environ.get("GJB_PDL", "1") != "0"
         self.sargs = []
+        self.targs = []
         for t in range(T):
             A = cabi.StepArgs()
             A.n, A.n_total, A.idx_offset, A.slot_offset = n, n, pf.idx_offset, 0
+            A.step = t
+            # programmatic dependent launch behind the previous step kernel: this launch draws its random numbers while
+            # that one drains (the first step follows copies / other kernels and is launched normally)
+            A.flags = cabi.STEP_PDL if (pdl and t > 0) else 0
             A.key_dev = self.keys[t].data_ptr()
             slot = t if self.record else (t & 1)
             prev_slot = (t - 1) if self.record else ((t - 1) & 1)
@@ -316,23 +344,39 @@ class _Plan:
                 A.weight_out = self.logw.data_ptr()
             if t > 0:
                 A.prev_cdf = self.te_cdf[(t - 1) & 1].data_ptr()
-                A.prev_recs = self.te_recs[(t - 1) & 1].data_ptr()
-                A.n_tiles_total = self.te_tiles
                 A.prev_key = self.keys[t - 1][2:].data_ptr()
-                A.prev_lse = self.lse[t - 1].data_ptr()
+                if self.te_table:
+                    A.table_in = self.te_tables[(t - 1) & 1].data_ptr()
+                else:
+                    A.prev_recs = self.te_recs[(t - 1) & 1].data_ptr()
+                    A.n_tiles_total = self.te_tiles
+                    A.prev_lse = self.lse[t - 1].data_ptr()
                 if self.record:
                     A.ancestors_out = self.anc[t - 1].data_ptr()
             A.cdf_out = self.te_cdf[t & 1].data_ptr()
-            A.recs_out = self.te_recs[t & 1].data_ptr()
+            if self.te_table:
+                A.link = self.te_link.data_ptr()  # (table_out stays NULL: the CTAs mail their records, gjb_te_table does the rest)
+                B = cabi.TeTableArgs()
+                B.link, B.step, B.flags = self.te_link.data_ptr(), t, (cabi.STEP_PDL if pdl else 0)
+                B.slot_offset, B.n_local, B.n_total = 0, n, n
+                B.reskey = self.keys[t][2:].data_ptr()
+                B.table_out = self.te_tables[t & 1].data_ptr()
+                B.lse_out = self.lse[t].data_ptr()
+                self.targs.append(B)
+            else:
+                A.recs_out = self.te_recs[t & 1].data_ptr()
             self.sargs.append(A)
         last = (T - 1) if self.record else ((T - 1) & 1)
         R = cabi.TeResampleArgs()
         R.cdf = self.te_cdf[(T - 1) & 1].data_ptr()
-        R.recs = self.te_recs[(T - 1) & 1].data_ptr()
+        if self.te_table:
+            R.table = self.te_tables[(T - 1) & 1].data_ptr()
+        else:
+            R.recs = self.te_recs[(T - 1) & 1].data_ptr()
+            R.lse_out = self.lse[T - 1].data_ptr()
         R.n_tiles_total, R.n_total, R.out_lo, R.out_n = self.te_tiles, n, 0, n
         R.key_dev = self.keys[T - 1][2:].data_ptr()
         R.ancestors = self.anc[last].data_ptr()
-        R.lse_out = self.lse[T - 1].data_ptr()
         self.te_close = R
 
     def _build_args(self):
@@ -437,10 +481,13 @@ class _Plan:
         if self.stepmode:  # ONE launch per step, the closing resampling of the last step, the final gather(s)
             for t in range(self.T):
                 cabi.check(lib.gjb_model_pf_step(C.byref(self.sargs[t]), stream), "gjb_model_pf_step")
+                if self.te_table:
+                    cabi.check(core.gjb_te_table(C.byref(self.targs[t]), stream), "gjb_te_table")
             cabi.check(core.gjb_te_resample(C.byref(self.te_close), stream), "gjb_te_resample")
             last = (self.T - 1) if self.record else ((self.T - 1) & 1)
             for k in range(len(self.bufs)):
                 smc_ops.gather_rows(self.bufs[k][last], self.anc[last], self.final[k])
+            cabi.check(core.gjb_epoch_bump(self.te_epoch.data_ptr(), stream), "gjb_epoch_bump")  # new record tags next run
             return
         if self.analytic and self.single_pass:  # 1 launch per step + one closing resampling launch
             self.tm3.zero_()
@@ -485,7 +532,7 @@ class _Plan:
         if self.persistent:
             return 2 + len(self.bufs)  # init + persistent filter kernel + final gather(s)
         if self.stepmode:
-            return self.T + 1 + len(self.bufs)
+            return self.T + 2 + len(self.bufs)  # T step kernels, closing resample, final gather(s), epoch bump
         if self.analytic and self.single_pass:
             return self.T + 1 + len(self.bufs)  # (+ one memset node)
         if self.analytic:

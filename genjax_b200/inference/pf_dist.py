@@ -91,12 +91,18 @@ class DistributedParticleFilter:
     systematic resampling.  ``state0`` / results are this rank's block."""
 
     def __init__(self, step: StaticGenerativeFunction, n_per_rank: int, group=None, fused: bool = True,
-                 mode: str = "pull"):
-        """mode "pull" (default): every rank resolves the ancestors of its OWN slots, reading peers'
+                 mode: str = "step"):
+        """mode "step" (default): ONE launch per filter step on every rank (``gjb_model_pf_step``, the single-device
+        default): each CTA resolves the ancestors of its own 2048 offspring slots from the previous step's
+        tile-exponent CDF -- parent rows and parent states are read over NVLink when they live on a peer -- proposes,
+        scores, and mails its tile record to every rank; the CTA that finishes last on a rank waits for the records
+        of ALL ranks (the one cross-rank hand-off of the step) and builds the prefix table the next launch consumes.
+        n_per_rank must be a multiple of 2048.
+        mode "pull" (round 1): every rank resolves the ancestors of its OWN slots, reading peers'
         log-weight tiles over NVLink -- 2 fused hand-offs per step, no cross-rank stores, no barrier;
         mode "push": owners write ancestors into the peers' buffers -- 3 hand-offs per step, fused into
         the kernels (``fused=True``) or as 3 extra single-CTA launches (``fused=False``)."""
-        if mode not in ("pull", "push"):
+        if mode not in ("step", "pull", "push"):
             raise ValueError(mode)
         self.mode = mode
         self.fused = bool(fused) or mode == "pull"
@@ -129,7 +135,7 @@ class DistributedParticleFilter:
                tuple((a, tuple(v.shape[1:])) for a, v in obs.items()), T, record)
         plan = self._plans.get(sig)
         if plan is None:
-            plan = _DistPlan(self, state0, shared, obs, T, record, device)
+            plan = (_DistStepPlan if self.mode == "step" else _DistPlan)(self, state0, shared, obs, T, record, device)
             self._plans[sig] = plan
         return plan.execute(key, state0, shared, obs, use_graph)
 
@@ -360,5 +366,194 @@ class _DistPlan:
             self._enqueue()
         inc = self.lse[:, 2]
         hist = {"state": tuple(self.bufs), "log_weights": self.logw_sym if self.pull else self.logw} if self.record else None
+        return PFResult(state=self.final, log_marginal_likelihood=inc.sum(), log_increments=inc, lse_terms=self.lse,
+                        ancestors=self.anc if self.record else None, history=hist)
+
+
+class _DistStepPlan:
+    """Launch arguments of the global-resampling filter on the single-launch step kernel (mode="step")."""
+
+    def __init__(self, pf: DistributedParticleFilter, state0, shared, obs, T, record, device):
+        import os
+
+        self.pf, self.device, self.T, self.record = pf, device, T, record
+        self.stepmode = True
+        n, world, rank = pf.n, pf.world, pf.rank
+        if n % cabi.TE_TILE:
+            raise ValueError(f"mode='step': particles per rank must be a multiple of {cabi.TE_TILE}")
+        tiles = n // cabi.TE_TILE
+        if tiles * world > cabi.TE_MAX_TILES or pf.n_total > (1 << 26):
+            raise NotImplementedError(f"mode='step' resamples over at most {cabi.TE_MAX_TILES} tiles of {cabi.TE_TILE} particles")
+        if T >= 65535:
+            raise ValueError("at most 65534 filter steps per run (16-bit step field of the record tags)")
+        specs = [ArgSpec("particle", "i32" if s.dtype == torch.int32 else "f32", tuple(s.shape[1:])) for s in state0]
+        for s in shared:
+            if isinstance(s, torch.Tensor):
+                specs.append(ArgSpec("shared", "i32" if s.dtype == torch.int32 else "f32", tuple(s.shape)))
+            else:
+                specs.append(ArgSpec("scalar", "i32" if isinstance(s, int) else "f32", ()))
+        self.cm = pf.step.prebuild(specs, pf_obs=tuple(obs.keys()))
+        ir = self.ir = self.cm.ir
+        if not self.cm.info.get("pf_step", False):
+            raise NotImplementedError("mode='step': this model's return value does not feed back as its state")
+        if len(ir.ret_leaves) != len(state0):
+            raise ValueError("the step must return one leaf per state leaf")
+        slots = T if record else 2
+        self.slots, self.tiles = slots, tiles
+        row_elems = [int(np.prod(s.shape[1:])) if s.ndim > 1 else 1 for s in state0]
+        self.row_elems = row_elems
+        # ---- symmetric buffers: what peers read (state ping-pong, CDF rows) or write (tile-record mailbox, barrier pad)
+        need = (sum(slots * n * r * 4 + 512 for r in row_elems) + 2 * n * 8 + 512 + cabi.TE_MAILBOX_WORDS * 8 + 512
+                + _PAD_WORDS * 8 + 1024)
+        self.arena = SymmArena(need, device, pf.group)
+        self.bufs, self.buf_off = [], []
+        for s in state0:
+            t, off = self.arena.take((slots,) + tuple(s.shape), s.dtype)
+            self.bufs.append(t)
+            self.buf_off.append(off)
+        self.cdf, self.cdf_off = self.arena.take((2, n), torch.int64)
+        self.mailbox, self.mail_off = self.arena.take((cabi.TE_MAILBOX_WORDS,), torch.int64)
+        self.pad, self.pad_off = self.arena.take((_PAD_WORDS,), torch.int64)
+        # ---- local buffers
+        self.state_in = tuple(torch.empty_like(s) for s in state0)
+        self.shared = tuple(torch.empty_like(s) if isinstance(s, torch.Tensor) else s for s in shared)
+        self.obs = {a: torch.empty_like(v) for a, v in obs.items()}
+        self.keys = torch.empty((T, 8), dtype=torch.int32, device=device)
+        self.logw = torch.empty((T if record else 1, n), dtype=torch.float32, device=device)
+        self.anc = torch.empty((slots, n), dtype=torch.int32, device=device)
+        self.lse = torch.empty((T, 3), dtype=torch.float64, device=device)
+        self.tables = torch.zeros((2, C.sizeof(cabi.StepTable)), dtype=torch.uint8, device=device)
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=device)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
+        self.final = tuple(torch.empty_like(s) for s in state0)
+        L = cabi.StepLink()
+        L.rank, L.world, L.tiles_per_rank = rank, world, tiles
+        for r in range(world):
+            L.mailbox[r] = self.arena.ptrs[r] + self.mail_off
+        L.epoch, L.ticket = self.epoch.data_ptr(), self.ticket.data_ptr()
+        self.link = torch.from_numpy(np.frombuffer(bytes(L), dtype=np.uint8).copy()).to(device)
+
+        def dev_bytes(obj):
+            return torch.from_numpy(np.frombuffer(bytes(obj), dtype=np.uint8).copy()).to(device)
+
+        # device tables of peer pointers: per state slot gjb_peers[GJB_MAX_ARGS]; per CDF parity one gjb_peers
+        self.peer_tabs = []
+        for sl in range(slots):
+            arr = (cabi.Peers * cabi.GJB_MAX_ARGS)()
+            for i, off in enumerate(self.buf_off):
+                arr[i] = self.arena.peers(off + sl * n * row_elems[i] * 4, n)
+            self.peer_tabs.append(dev_bytes(arr))
+        self.cdf_peers = [dev_bytes(self.arena.peers(self.cdf_off + par * n * 8, n)) for par in range(2)]
+        self.obs_sites = {ir.site_index(a): a for a in obs}
+        self.graph = None
+        pdl = os.environ.get("GJB_PDL", "1") != "0"
+        dist.barrier(pf.group)  # every rank has zeroed its arena before anyone mails into it
+        # ---- per-step arguments
+        self.sargs = []
+        self.targs = []
+        for t in range(T):
+            A = cabi.StepArgs()
+            A.n, A.n_total, A.idx_offset, A.slot_offset = n, pf.n_total, rank * n, rank * n
+            A.step = t
+            A.flags = cabi.STEP_PDL if (pdl and t > 0) else 0
+            A.key_dev = self.keys[t].data_ptr()
+            slot = t if record else (t & 1)
+            pslot = (t - 1) if record else ((t - 1) & 1)
+            for i in range(len(self.state_in)):
+                A.args[i] = self.state_in[i].data_ptr() if t == 0 else self.bufs[i][pslot].data_ptr()
+                A.state_out[i] = self.bufs[i][slot].data_ptr()
+            for k, s in enumerate(self.shared):
+                i = len(self.state_in) + k
+                if isinstance(s, torch.Tensor):
+                    A.args[i] = s.data_ptr()
+                else:
+                    A.scalars[i] = float(s)
+            for j, addr in self.obs_sites.items():
+                A.site_in[j] = self.obs[addr][t].data_ptr()
+            if record:
+                A.weight_out = self.logw[t].data_ptr()
+            elif t == T - 1:
+                A.weight_out = self.logw[0].data_ptr()
+            if t > 0:
+                A.prev_cdf = self.cdf[(t - 1) & 1].data_ptr()
+                A.cdf_peers = self.cdf_peers[(t - 1) & 1].data_ptr()
+                A.peer_args = self.peer_tabs[pslot].data_ptr()
+                A.table_in = self.tables[(t - 1) & 1].data_ptr()
+                A.prev_key = self.keys[t - 1][2:].data_ptr()
+                if record:
+                    A.ancestors_out = self.anc[t - 1].data_ptr()
+            A.cdf_out = self.cdf[t & 1].data_ptr()
+            A.link = self.link.data_ptr()  # (table_out stays NULL: the CTAs mail their records, gjb_te_table does the rest)
+            self.sargs.append(A)
+            B = cabi.TeTableArgs()
+            B.link, B.step, B.flags = self.link.data_ptr(), t, (cabi.STEP_PDL if pdl else 0)
+            B.slot_offset, B.n_local, B.n_total = rank * n, n, pf.n_total
+            B.reskey = self.keys[t][2:].data_ptr()
+            B.table_out = self.tables[t & 1].data_ptr()
+            B.lse_out = self.lse[t].data_ptr()
+            self.targs.append(B)
+        last = (T - 1) if record else ((T - 1) & 1)
+        self.last = last
+        R = cabi.TeResampleArgs()
+        R.cdf = self.cdf[(T - 1) & 1].data_ptr()
+        R.table = self.tables[(T - 1) & 1].data_ptr()
+        R.cdf_peers = self.cdf_peers[(T - 1) & 1].data_ptr()
+        R.n_tiles_total, R.n_total, R.out_lo, R.out_n = tiles * world, pf.n_total, rank * n, n
+        R.key_dev = self.keys[T - 1][2:].data_ptr()
+        R.ancestors = self.anc[last].data_ptr()
+        self.close = R
+        self.final_peers = [self.arena.peers(off + last * n * row_elems[i] * 4, n) for i, off in enumerate(self.buf_off)]
+        X = cabi.XchgArgs()
+        X.rank, X.world, X.mode = rank, world, cabi.XCHG_BARRIER
+        for r in range(world):
+            X.pads[r] = self.arena.ptrs[r] + self.pad_off
+        X.epoch = self.epoch.data_ptr()
+        X.tag_offset = 1
+        self.x_end = X
+
+    def _enqueue(self):
+        core = cabi.core()
+        stream = cabi.stream_ptr(self.device)
+        lib = self.cm.lib
+        for t in range(self.T):
+            cabi.check(lib.gjb_model_pf_step(C.byref(self.sargs[t]), stream), "gjb_model_pf_step")
+            cabi.check(core.gjb_te_table(C.byref(self.targs[t]), stream), "gjb_te_table")
+        cabi.check(core.gjb_te_resample(C.byref(self.close), stream), "gjb_te_resample")
+        for k in range(len(self.bufs)):
+            cabi.check(core.gjb_gather_rows_peers(C.byref(self.final_peers[k]), self.anc[self.last].data_ptr(),
+                                                  self.final[k].data_ptr(), self.pf.n, self.row_elems[k] * 4, stream),
+                       "gjb_gather_rows_peers")
+        # nobody overwrites state / CDF rows of this run while a peer still reads them
+        cabi.check(core.gjb_exchange(C.byref(self.x_end), stream), "gjb_exchange(end of run)")
+        cabi.check(core.gjb_epoch_bump(self.epoch.data_ptr(), stream), "gjb_epoch_bump")
+
+    def launches_per_run(self) -> int:
+        return 2 * self.T + 3 + len(self.bufs)  # step kernel + table kernel per step, closing resample, gathers, barrier, epoch
+
+    def execute(self, key, state0, shared, obs, use_graph):
+        tab = torch.from_numpy(pf_key_table(key, self.T).view(np.int32))
+        self.keys.copy_(tab, non_blocking=True)
+        for dst, src in zip(self.state_in, state0):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        for dst, src in zip(self.shared, shared):
+            if isinstance(dst, torch.Tensor) and dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        for a in self.obs:
+            if self.obs[a].data_ptr() != obs[a].data_ptr():
+                self.obs[a].copy_(obs[a], non_blocking=True)
+        if use_graph:
+            if self.graph is None:
+                self._enqueue()
+                torch.cuda.current_stream(self.device).synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue()
+                self.graph = g
+            self.graph.replay()
+        else:
+            self._enqueue()
+        inc = self.lse[:, 2]
+        hist = {"state": tuple(self.bufs), "log_weights": self.logw} if self.record else None
         return PFResult(state=self.final, log_marginal_likelihood=inc.sum(), log_increments=inc, lse_terms=self.lse,
                         ancestors=self.anc if self.record else None, history=hist)

@@ -13,13 +13,16 @@ import torch
 
 from . import build
 
-ABI_VERSION = 11  # GJB_ABI_VERSION of include/genjax_b200.h this binding mirrors (tests/test_abi.py keeps them equal)
+ABI_VERSION = 12  # GJB_ABI_VERSION of include/genjax_b200.h this binding mirrors (tests/test_abi.py keeps them equal)
 GJB_MAX_SITES = 16
 GJB_MAX_ARGS = 16
 GJB_MAX_RETS = 8
 GJB_HEAVY_WS_WORDS = 4 + 3 * 1024
 TE_TILE = 2048
 TE_MAX_TILES = 4096
+TE_LL_WORDS = 4
+TE_MAILBOX_WORDS = 2 * TE_MAX_TILES * TE_LL_WORDS
+STEP_PDL = 1
 MASS_MAX_PARTICLES = 1 << 27
 
 SITE_SAMPLE = 1
@@ -179,12 +182,34 @@ class TileRec(C.Structure):
     _fields_ = [("mass", _u64), ("e", _i32), ("reserved", _i32)]
 
 
+class StepTable(C.Structure):
+    """``gjb_step_table`` (include/genjax_b200.h section 1c)."""
+
+    _fields_ = [("S", _u64), ("E", _i32), ("n_tiles_total", _i32), ("pre", _u64 * TE_MAX_TILES),
+                ("win", (_i32 * 2) * TE_MAX_TILES), ("shf", C.c_uint8 * TE_MAX_TILES)]
+
+
+class StepLink(C.Structure):
+    """``gjb_step_link`` (include/genjax_b200.h section 1c)."""
+
+    _fields_ = [("rank", _i32), ("world", _i32), ("tiles_per_rank", _i32), ("reserved", _i32),
+                ("mailbox", _p * GJB_MAX_RANKS), ("epoch", _p), ("ticket", _p)]
+
+
+class TeTableArgs(C.Structure):
+    """``gjb_te_table_args`` (include/genjax_b200.h section 1c)."""
+
+    _fields_ = [("link", _p), ("step", _i32), ("flags", _u32), ("slot_offset", _i64), ("n_local", _i64), ("n_total", _i64),
+                ("reskey", _p), ("table_out", _p), ("lse_out", _p)]
+
+
 class TeResampleArgs(C.Structure):
     """``gjb_te_resample_args`` (include/genjax_b200.h section 1c)."""
 
     _fields_ = [
         ("cdf", _p),
         ("recs", _p),
+        ("table", _p),
         ("cdf_peers", _p),
         ("n_tiles_total", _i32),
         ("reserved", _i32),
@@ -205,6 +230,8 @@ class StepArgs(C.Structure):
         ("n_total", _i64),
         ("idx_offset", _u64),
         ("slot_offset", _i64),
+        ("step", _i32),
+        ("flags", _u32),
         ("key_dev", _p),
         ("args", _p * GJB_MAX_ARGS),
         ("scalars", C.c_float * GJB_MAX_ARGS),
@@ -213,15 +240,19 @@ class StepArgs(C.Structure):
         ("state_out", _p * GJB_MAX_RETS),
         ("weight_out", _p),
         ("prev_cdf", _p),
-        ("prev_recs", _p),
         ("cdf_peers", _p),
+        ("table_in", _p),
+        ("prev_recs", _p),
         ("n_tiles_total", _i32),
         ("reserved", _i32),
+        ("prev_lse", _p),
         ("prev_key", _p),
         ("ancestors_out", _p),
-        ("prev_lse", _p),
         ("cdf_out", _p),
         ("recs_out", _p),
+        ("link", _p),
+        ("table_out", _p),
+        ("lse_out", _p),
     ]
 
 
@@ -274,6 +305,7 @@ CORE_PROTOTYPES = {
     "gjb_gather_rows_peers": (C.c_int, [C.POINTER(Peers), _p, _p, _i64, _i32, _p]),
     "gjb_te_masses": (C.c_int, [_p, _i64, _p, _p, _p]),
     "gjb_te_resample": (C.c_int, [C.POINTER(TeResampleArgs), _p]),
+    "gjb_te_table": (C.c_int, [C.POINTER(TeTableArgs), _p]),
     "gjb_philox_fill": (C.c_int, [_u32, _u32, _u64, _u32, _u32, _i64, _p, _p]),
     "gjb_normal_fill": (C.c_int, [_u32, _u32, _u64, _u32, _i64, _i32, _p, _p]),
 }

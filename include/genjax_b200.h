@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GJB_ABI_VERSION 11
+#define GJB_ABI_VERSION 12
 
 #define GJB_E_ARG (-1)      /* null / misaligned pointer, negative size          */
 #define GJB_E_RANGE (-2)    /* size beyond what the kernel supports              */
@@ -268,9 +268,65 @@ typedef struct gjb_tile_rec {
 /* logw[n] -> cdf[ceil(n / 2048) * 2048] (padding repeats the last value), recs[ceil(n / 2048)]. */
 int gjb_te_masses(const float* logw, int64_t n, uint64_t* cdf, gjb_tile_rec* recs, void* stream);
 
+/*
+ * What the LAST CTA of a filter-step launch leaves for the next launch (one per device and step parity): the global
+ * exponent and mass, the inclusive prefix of the aligned tile masses of ALL ranks, and for every LOCAL window of 2048
+ * offspring slots the range of parent tiles with offspring in it -- so that the consumers (512+ CTAs) do no prefix
+ * work of their own.  On several GPUs every rank builds its own copy from the records all ranks mailed to it.
+ */
+typedef struct gjb_step_table {
+  uint64_t S;                /* total aligned mass (0: no weight has mass)       */
+  int32_t E;                 /* global exponent                                  */
+  int32_t n_tiles_total;
+  uint64_t pre[GJB_TE_MAX_TILES];      /* inclusive prefix of (mass_p >> shf[p]), global tile order */
+  int32_t win[GJB_TE_MAX_TILES][2];    /* local window w: first / last parent tile with offspring in it */
+  uint8_t shf[GJB_TE_MAX_TILES];
+} gjb_step_table;
+
+/* Tile-record mailbox of one rank: uint64 [2 (step parity)][GJB_TE_MAX_TILES][GJB_TE_LL_WORDS]; record of global tile
+ * p = {mass[31:0] | tag << 32, mass[63:32] | tag << 32, (uint32)e | tag << 32, tag << 32}: the 32-bit tag travels inside
+ * each 8-byte store it validates (NCCL-LL style), so a reader needs no fence between flag and payload.  tag =
+ * ((*epoch + 1) << 16 | step + 1) & 0xffffffff.  A record with the right tag also says that the tile's CDF row and
+ * state rows are visible in the owner's L2 (the owner fences before mailing it). */
+#define GJB_TE_LL_WORDS 4
+#define GJB_TE_MAILBOX_WORDS (2 * GJB_TE_MAX_TILES * GJB_TE_LL_WORDS)
+
+typedef struct gjb_step_link {   /* lives in DEVICE memory; constant for a plan */
+  int32_t rank, world;
+  int32_t tiles_per_rank;    /* ceil(n / 2048), the same on every rank          */
+  int32_t reserved;
+  uint64_t* mailbox[GJB_MAX_RANKS];  /* every rank's mailbox (peer mapped); [rank] is the local one */
+  const uint64_t* epoch;     /* device counter, bumped once per filter run (gjb_epoch_bump) */
+  uint32_t* ticket;          /* zero-initialised CTA ticket counter (self resetting) */
+} gjb_step_link;
+
+/*
+ * The table of one step built by a launch of its own (one CTA of 1024 threads per device), running BESIDE the step
+ * kernel: it polls this device's mailbox until the records of all tiles of all ranks carry the step's tag (that wait is
+ * the cross-rank hand-off of the step), then writes the table.  With GJB_STEP_PDL it is launched with programmatic
+ * stream serialization behind the step kernel, and the next step kernel behind it.
+ */
+typedef struct gjb_te_table_args {
+  const gjb_step_link* link;
+  int32_t step;
+  uint32_t flags;            /* GJB_STEP_PDL                                      */
+  int64_t slot_offset;       /* global slot of this device's particle 0           */
+  int64_t n_local, n_total;
+  const uint32_t* reskey;    /* {key0, key1, index_lo, index_hi} of the resampling of this step's weights */
+  gjb_step_table* table_out;
+  double* lse_out;           /* nullable: {E ln 2, S, log-mean-exp}               */
+} gjb_te_table_args;
+
+#define GJB_STEP_PDL 1u      /* launch with programmatic stream serialization: the launch may start while the previous
+                                kernel on the stream drains; a step kernel draws its random numbers, then waits
+                                (griddepcontrol.wait) before it touches anything the previous launch wrote */
+int gjb_te_table(const gjb_te_table_args* a, void* stream);
+
 typedef struct gjb_te_resample_args {
   const uint64_t* cdf;       /* [n_tiles_local * 2048] this device's within-tile CDFs */
-  const gjb_tile_rec* recs;  /* [n_tiles_total] tile records of ALL ranks, in global tile order */
+  const gjb_tile_rec* recs;  /* [n_tiles_total] tile records of ALL ranks, in global tile order (ignored with `table`) */
+  const gjb_step_table* table; /* nullable: the table a filter-step launch left (then out_lo must be this device's
+                                  slot offset, a multiple of 2048, and out_n its particle count) */
   const gjb_peers* cdf_peers; /* nullable DEVICE pointer: cdf of every rank (n_per_rank = particles per rank) */
   int32_t n_tiles_total;
   int32_t reserved;
@@ -423,23 +479,32 @@ typedef struct gjb_step_args {
   int64_t n_total;           /* particles the resampling spans (== n unless ranks resample globally) */
   uint64_t idx_offset;       /* RNG lane of local particle 0 (multiple of 4)      */
   int64_t slot_offset;       /* global offspring slot / parent id of local particle 0 (multiple of 2048; 0 on one device) */
-  const uint32_t* key_dev;   /* {key0, key1} of this step's proposals             */
+  int32_t step;              /* t: tags this launch's tile records, selects the mailbox parity t & 1 */
+  uint32_t flags;            /* GJB_STEP_*                                        */
+  const uint32_t* key_dev;   /* row t of the key table: {prop_k0, prop_k1, res_k0, res_k1, res_idx_lo, res_idx_hi, 0, 0};
+                                the proposals use words 0-1, the last CTA words 2-5 (resampling of THIS step's weights) */
   const void* args[GJB_MAX_ARGS];      /* state leaves of the PREVIOUS step (pre-resampling) then shared blocks */
   float scalars[GJB_MAX_ARGS];
   const gjb_peers* peer_args; /* nullable DEVICE array [GJB_MAX_ARGS]: state leaf i of every rank */
   const void* site_in[GJB_MAX_SITES];  /* observed values of this step (one value shared by all particles) */
   void* state_out[GJB_MAX_RETS];       /* next state leaves [n(, d)]               */
   float* weight_out;         /* nullable: this step's incremental log-weights [n]  */
-  const uint64_t* prev_cdf;  /* nullable: previous step's within-tile CDFs (this device) */
-  const gjb_tile_rec* prev_recs;       /* previous step's tile records, all ranks  */
+  const uint64_t* prev_cdf;  /* nullable (first step): previous step's within-tile CDFs (this device) */
   const gjb_peers* cdf_peers; /* nullable DEVICE pointer: prev_cdf of every rank   */
+  const gjb_step_table* table_in;      /* the table the previous launch left (with prev_cdf), or NULL: */
+  const gjb_tile_rec* prev_recs;       /* ... single device without table: the previous step's plain tile records; every
+                                          CTA then forms the tile prefix itself (n_tiles_total of them)             */
   int32_t n_tiles_total;
   int32_t reserved;
+  double* prev_lse;          /* nullable, with prev_recs: {E ln 2, S, log-mean-exp} of the PREVIOUS step (written by CTA 0) */
   const uint32_t* prev_key;  /* {key0, key1, index_lo, index_hi} of the previous step's resampling */
   int32_t* ancestors_out;    /* nullable [n]: the ancestors this launch resolved (previous step's) */
-  double* prev_lse;          /* nullable: {E ln 2, S, log-mean-exp} of the previous step */
   uint64_t* cdf_out;         /* [ceil(n / 2048) * 2048] this step's within-tile CDFs */
-  gjb_tile_rec* recs_out;    /* [ceil(n / 2048)] this step's tile records          */
+  gjb_tile_rec* recs_out;    /* nullable: this step's plain tile records [ceil(n / 2048)] (the table-free form) */
+  const gjb_step_link* link; /* nullable: mailboxes, epoch, ticket (the table form; required on several devices) */
+  gjb_step_table* table_out; /* with link: built by this launch's last CTA; NULL: the CTAs only mail their records and
+                                gjb_te_table builds the table beside this launch   */
+  double* lse_out;           /* nullable: {E ln 2, S, log-mean-exp} of THIS step's weights (written by the last CTA) */
 } gjb_step_args;
 
 int gjb_model_pf_step(const gjb_step_args* a, void* stream);

@@ -500,9 +500,13 @@ class EmulatedCore:
     oracle/smc.py.  Multi-GPU, fused cooperative and filter entry points are GPU-only and absent on purpose."""
 
     def gjb_abi_version(self):
-        return 11
+        return 12
 
     def gjb_mass_resample_fits(self, n):
+        return 0
+
+    def gjb_epoch_bump(self, epoch, stream):
+        _arr(epoch, 1, C.c_uint64, np.uint64)[0] += np.uint64(1)
         return 0
 
     # the tile-exponent kernels (include/genjax_b200.h section 1c) always run as written (tests/simt_kernels.py)
@@ -510,6 +514,11 @@ class EmulatedCore:
         import simt_kernels
 
         return simt_kernels.core().s_te_masses(C.c_void_p(logw), C.c_int64(n), C.c_void_p(cdf), C.c_void_p(recs))
+
+    def gjb_te_table(self, a_ref, stream):
+        import simt_kernels
+
+        return simt_kernels.core().s_te_table(a_ref)
 
     def gjb_te_resample(self, a_ref, stream):
         import simt_kernels

@@ -41,6 +41,32 @@ def main():
             model, shared = lgssm_step_vec, (torch.full((d,), LG_Q), torch.full((d,), LG_R))
         obs = gj.C["y"].set(torch.from_numpy(ys))
         mine = torch.from_numpy(x0[rank * n:(rank + 1) * n])
+        # ---- the single-launch step kernel (default): R ranks == one device with R * n particles, bit for bit
+        ns = max(2048, (n // 2048) * 2048)
+        x0s = g.standard_normal((world * ns, d) if d > 1 else world * ns).astype(np.float32)
+        mine_s = torch.from_numpy(x0s[rank * ns:(rank + 1) * ns])
+        ref = ParticleFilter(model, world * ns, mode="step").run(gj.key(21), torch.from_numpy(x0s), obs, shared_args=shared,
+                                                                 record=True, use_graph=False)
+        torch.cuda.synchronize()
+        lo, hi = rank * ns, (rank + 1) * ns
+        for use_graph in (False, True):
+            dpf = DistributedParticleFilter(model, ns, mode="step")
+            runs = [dpf.run(gj.key(21), mine_s, obs, shared_args=shared, record=True, use_graph=use_graph) for _ in range(2)]  # (replay: tags advance)
+            torch.cuda.synchronize()
+            for r in runs:
+                assert torch.equal(r.ancestors, ref.ancestors[:, lo:hi]), f"step: ancestors differ (d={d}, rank={rank})"
+                assert torch.equal(r.history["log_weights"], ref.history["log_weights"][:, lo:hi]), "step: log-weights differ"
+                assert torch.equal(r.history["state"][0], ref.history["state"][0][:, lo:hi]), "step: states differ"
+                assert torch.equal(r.log_increments, ref.log_increments), "step: logZ increments differ"
+                assert torch.equal(r.state[0], ref.state[0][lo:hi]), "step: final state differs"
+            nr = DistributedParticleFilter(model, ns, mode="step").run(gj.key(21), mine_s, obs, shared_args=shared, use_graph=use_graph)
+            assert torch.equal(nr.log_increments, ref.log_increments) and torch.equal(nr.state[0], ref.state[0][lo:hi]), "step: non-record run differs"
+            a = runs[0].ancestors[-1]
+            print(f"[rank {rank}] d={d} graph={use_graph} mode=step: OK, logZ={runs[0].log_marginal_likelihood.item():.4f}, "
+                  f"{int(((a < lo) | (a >= hi)).sum())} of {ns} last-step ancestors remote", flush=True)
+            del dpf
+        if os.environ.get("GJB_TEST_STEP_ONLY") == "1":
+            continue
         for use_graph, fused, mode in ((False, True, "pull"), (True, True, "pull"), (True, True, "push"), (True, False, "push")):
             dpf = DistributedParticleFilter(model, n, fused=fused, mode=mode)
             res = dpf.run(gj.key(21), mine, obs, shared_args=shared, record=True, use_graph=use_graph)

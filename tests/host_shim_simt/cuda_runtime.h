@@ -30,6 +30,7 @@
 
 struct uint4 { uint32_t x, y, z, w; };
 struct int4 { int32_t x, y, z, w; };
+struct int2 { int32_t x, y; };
 struct ulonglong2 { unsigned long long x, y; };
 static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }
 struct float2 { float x, y; };

@@ -84,6 +84,11 @@ int s_te_resample(const gjb_te_resample_args* a) {
   simt::launch(ctas, gjb::kThreads, [=] { gjb::te_resample_kernel(A); });
   return 0;
 }
+int s_te_table(const gjb_te_table_args* a) {
+  const gjb_te_table_args A = *a;
+  simt::launch(1, gjb::kTabThreads, [=] { gjb::te_table_kernel(A); });
+  return 0;
+}
 int s_gather_rows(const uint32_t* src, const int32_t* anc, uint32_t* dst, int64_t n_out, int w, int grid) {
   simt::launch(grid, 256, [=] { gjb::gather_rows_kernel<uint32_t>(src, anc, dst, n_out, w); });
   return 0;
