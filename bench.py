@@ -52,18 +52,18 @@ def parse():
     ap.add_argument("--T", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="enqueue the launches every run instead of replaying a CUDA graph")
-    ap.add_argument("--multi-gpu", default="islands", choices=["islands", "global"],
-                    help="N>1: islands = every rank filters its own block of particles with local resampling and the "
-                         "per-shard log-marginal-likelihood terms are combined by ONE NCCL all-reduce per run; "
-                         "global = one filter over N*particles with global systematic resampling every step "
-                         "(peer-memory hand-offs, BASELINE configs[3] style)")
+    ap.add_argument("--multi-gpu", default="global", choices=["islands", "global"],
+                    help="N>1: global (default, the north star's split) = ONE filter over N*particles with global systematic "
+                         "resampling every step (tile records mailed over NVLink peer memory, parents read from peers); the line "
+                         "also carries an 'islands' measurement.  islands = every rank filters its own block of particles with "
+                         "local resampling and the per-shard log-marginal-likelihood terms are combined by ONE NCCL all-gather per run")
     ap.add_argument("--reference-max", default="running", choices=["running", "analytic"],
                     help="running (default): max + mass passes; analytic: masses relative to an analytic bound, accumulated "
                          "in the model kernel (graph mode, d = 1; DESIGN.md section 10 -- not yet measured on a device)")
     ap.add_argument("--single-pass", action="store_true",
                     help="with --reference-max analytic: ONE launch per step (output-slot resampling of the previous step fused "
                          "into the model kernel, model_kernel_static_pull; DESIGN.md section 10 -- not yet measured on a device)")
-    ap.add_argument("--mode", default="graph", choices=["persistent", "graph", "step"],
+    ap.add_argument("--mode", default="step", choices=["persistent", "graph", "step"],
                     help="step: ONE launch per filter step (pf_step_kernel: output-slot resampling of the previous step + gather + "
                          "propose + logpdf + tile-exponent masses), captured in a CUDA graph; graph: round 1's 2 launches per step; "
                          "persistent: one cooperative launch per filter")
@@ -413,25 +413,26 @@ def run_ours(args):
 
     log_world = float(np.log(world))
 
-    def combine(logz):
-        """islands: log-mean-exp over ranks of the per-shard estimates = ONE all-reduce pair on 8 bytes
-        (max, then sum of exp) -- the single NCCL reduction of per-shard log-sum-exp terms of the north star."""
-        if world == 1 or global_resample:
-            return logz
-        m = logz.detach().clone().reshape(1)
-        dist.all_reduce(m, op=dist.ReduceOp.MAX)
-        s = torch.exp(logz.reshape(1) - m)
-        dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        return (m + torch.log(s) - log_world)[0]
+    gathered = torch.empty(max(world, 1), dtype=torch.float64, device=device)
 
-    def one(step_idx, e2e):
-        key = gj.fold_in(gj.key(314159 + (0 if global_resample else rank)), step_idx)
+    def combine(logz, is_global):
+        """islands: log-mean-exp over ranks of the per-shard estimates from ONE collective (an all-gather of 8 bytes per
+        rank) -- the single NCCL reduction of per-shard log-sum-exp terms of the north star."""
+        if world == 1 or is_global:
+            return logz
+        dist.all_gather_into_tensor(gathered, logz.detach().reshape(1))
+        return torch.logsumexp(gathered, 0) - log_world
+
+    def one(step_idx, e2e, pf_=None, is_global=None):
+        pf_ = pf if pf_ is None else pf_
+        is_global = global_resample if is_global is None else is_global
+        key = gj.fold_in(gj.key(314159 + (0 if is_global else rank)), step_idx)
         if e2e:
-            res = pf.run(key, x0_host.to(device, non_blocking=True), obs_host, shared_args=shared, use_graph=not args.eager)
+            res = pf_.run(key, x0_host.to(device, non_blocking=True), obs_host, shared_args=shared, use_graph=not args.eager)
             state_host.copy_(res.state[0], non_blocking=True)  # the filter's product: final particle cloud, pinned D2H
-            return combine(res.log_marginal_likelihood).item()  # (all-reduce of the shard terms +) D2H read + sync
-        res = pf.run(key, x0_dev, obs_dev, shared_args=shared, use_graph=not args.eager)
-        res.combined = combine(res.log_marginal_likelihood)
+            return combine(res.log_marginal_likelihood, is_global).item()  # (all-gather of the shard terms +) D2H read + sync
+        res = pf_.run(key, x0_dev, obs_dev, shared_args=shared, use_graph=not args.eager)
+        res.combined = combine(res.log_marginal_likelihood, is_global)
         return res
 
     # ---- warm-up
@@ -474,6 +475,32 @@ def run_ours(args):
     t_e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
     t_e2e = torch.tensor([t_e2e_ms], dtype=torch.float64, device=device)
     clocks = sampler.stop()
+
+    # ---- N > 1, global default: the islands mode beside it (device-resident timing only, same protocol)
+    islands = None
+    if global_resample:
+        pf_i = ParticleFilter(model, n, idx_offset=0, mode=args.mode)
+        for w in range(3):
+            one(w, False, pf_i, False)
+        barrier()
+        ti = []
+        for k in range(args.steps):
+            flush.fill_(k & 0xFF)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(device)
+            e0.record()
+            r_i = one(300 + k, False, pf_i, False)
+            e1.record()
+            torch.cuda.synchronize(device)
+            ti.append(e0.elapsed_time(e1))
+        barrier()
+        t_isl = torch.tensor([sum(ti)], dtype=torch.float64, device=device)
+        dist.all_reduce(t_isl, op=dist.ReduceOp.MAX)
+        islands = {"value": float(n) * T * args.steps * world / (t_isl.item() * 1e-3), "unit": "particle-steps/s",
+                   "ms_per_step": t_isl.item() / args.steps, "logZ_last": r_i.combined.item(),
+                   "what": "every rank filters its own block (local resampling); the shard log-marginal-likelihood terms are combined "
+                           "by ONE NCCL all-gather per run, inside the timed region"}
 
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
@@ -535,9 +562,10 @@ def run_ours(args):
     kernels = {"model_kernel": {"kernel_us": model_ms * 1e3, "algorithmic_bytes_per_launch": model_bytes,
                                 "achieved": model_gbs, "frac": model_gbs / peak,
                                 "what": "fused ancestor-gather + propose + logpdf + running max (gjb_model_launch)"}}
-    if global_resample:
-        # several devices: the step kernel's last CTA waits for every rank's tile records, so it cannot be re-launched in
-        # isolation on rank 0; the roofline is taken from the step time of the timed region itself (max over ranks)
+    if global_resample or getattr(plan, "te_table", False):
+        # table form (several devices): a step kernel waits for the table kernel of the step before, fed by every rank's tile
+        # records, so it cannot be re-launched in isolation; the roofline is taken from the step time of the timed region
+        # itself (max over ranks)
         st_ms = ms_per_step / T
         st_bytes = (8 * d + 24) * n
         st_gbs = st_bytes / (st_ms * 1e-3) / 1e9
@@ -705,15 +733,16 @@ def run_ours(args):
                           "to every rank, each rank's last CTA waits for all of them (the step's one hand-off) and builds the prefix "
                           "table; parent CDF rows / states are read over NVLink peer memory; weak scaling"
                           if global_resample else "islands: each rank filters its own block (local resampling, global RNG lanes "
-                          "differ by key), the shard log-marginal-likelihood terms are combined by one NCCL all-reduce (max + sum-exp "
-                          "on 8 bytes) per run, inside the timed region; weak scaling. --multi-gpu global times the "
-                          "global-resampling filter instead"),
+                          "differ by key), the shard log-marginal-likelihood terms are combined by one NCCL all-gather (8 bytes per "
+                          "rank) per run, inside the timed region; weak scaling. --multi-gpu global (the default for N > 1) times the "
+                          "global-resampling filter"),
             "logZ_last": logz, "logZ_exact_kalman": logz_exact, "logZ_sigma": logz_sigma, "logZ_check": logz_check,
             "reference_max": args.reference_max, "single_pass": bool(args.single_pass),
         },
         "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 + state_host.numel() * 4,
                 "logZ_last": logz_e2e, "d2h": "log-marginal-likelihood estimate (8 B) + the final particle state"},
         "gpu_launches": plan.launches_per_run() * args.steps,
+        "islands": islands,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks,

@@ -176,10 +176,12 @@ def threefry2x32_np(k0, k1, c0, c1):
 
 
 def pf_key_table(k: PRNGKey, n_steps: int):
-    """uint32 [T, 8] rows {prop_k0, prop_k1, res_k0, res_k1, res_idx_lo, res_idx_hi, 0, 0}.
+    """uint32 [T, 8] rows {prop_k0, prop_k1, res_k0, res_k1, res_idx_lo, res_idx_hi, mn_k0, mn_k1}.
 
     Step t uses ``k_prop, k_res = split(fold_in(key, t))``; the proposal lanes
-    are ``split(k_prop, N)`` and the resampler draws its uniform from ``k_res``.
+    are ``split(k_prop, N)``, the systematic resampler draws its one uniform from
+    ``k_res`` and the multinomial resampler gives offspring j lane j of
+    ``split(k_res, N)`` (words mn_k0, mn_k1).
     """
     import numpy as np
 
@@ -191,4 +193,6 @@ def pf_key_table(k: PRNGKey, n_steps: int):
     tab = np.zeros((n_steps, 8), dtype=np.uint32)
     tab[:, 0], tab[:, 1], tab[:, 2], tab[:, 3] = p0, p1, s0, s1
     tab[:, 4] = 1  # k_res = lane 1 of the split
+    c0, c1 = threefry2x32_np(s0, s1, np.uint32(0x5851F42D), np.uint32(1))  # k_res collapsed (lane 1 folded into the words)
+    tab[:, 6], tab[:, 7] = threefry2x32_np(c0, c1, np.uint32(0x73706C74), np.uint32(0))  # split(k_res, N) words
     return tab

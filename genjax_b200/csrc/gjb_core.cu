@@ -407,7 +407,9 @@ __global__ void __launch_bounds__(kThreads) cdf_kernel(const float* __restrict__
 
 __global__ void __launch_bounds__(256) multinomial_search_kernel(const uint64_t* __restrict__ cdf, int64_t n,
                                                                  uint32_t key0, uint32_t key1, uint64_t idx_offset,
-                                                                 int64_t n_out, int32_t* __restrict__ ancestors) {
+                                                                 int64_t n_out, int32_t* __restrict__ ancestors,
+                                                                 const uint32_t* __restrict__ key_dev = nullptr) {
+  if (key_dev) { key0 = __ldg(key_dev); key1 = __ldg(key_dev + 1); }  // keys read on the device (graph replay)
   const uint64_t S = cdf[n - 1];
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_out; j += (int64_t)gridDim.x * blockDim.x) {
     if (S == 0) { ancestors[j] = (int32_t)(j < n ? j : n - 1); continue; }
@@ -575,11 +577,11 @@ __global__ void __launch_bounds__(kThreads) te_resample_kernel(const __grid_cons
   }
 }
 
-// The table of one step as a launch of its own: one CTA of 1024 threads per device, resident beside the step kernel.
+// The table of one step as a launch of its own: one CTA of 512 threads per device, resident beside the step kernel.
 // Polls the mailbox until every tile of every rank carries the step's tag (the cross-rank hand-off), then E, the
 // aligned tile masses, their inclusive prefix, the offspring count at every tile boundary, and the parent-tile range of
 // every local window.  Same arithmetic as te_finish_step's last-CTA path (gjb_step.cuh), four times the threads.
-constexpr int kTabThreads = 1024;
+constexpr int kTabThreads = 512;  // 16 K registers: fits beside three resident step CTAs
 __global__ void __launch_bounds__(kTabThreads) te_table_kernel(const __grid_constant__ gjb_te_table_args A) {
   __shared__ int32_t cnt[kTeMaxTiles];
   __shared__ uint64_t red[kTabThreads / 32];
@@ -590,7 +592,7 @@ __global__ void __launch_bounds__(kTabThreads) te_table_kernel(const __grid_cons
   const int n_tiles = L->world * L->tiles_per_rank;
   const uint32_t tag = te_tag(L, A.step);
   const uint64_t* box = te_mail_slot(L->mailbox[L->rank], A.step, 0);
-  constexpr int kPer = kTeMaxTiles / kTabThreads;  // 4 records per thread, blocked
+  constexpr int kPer = kTeMaxTiles / kTabThreads;  // 8 records per thread, blocked
   uint64_t m[kPer];
   int e[kPer];
   int emax = GJB_TE_E_NONE;
@@ -604,7 +606,7 @@ __global__ void __launch_bounds__(kTabThreads) te_table_kernel(const __grid_cons
       for (;;) {
         w0 = te_ld_volatile(r); w1 = te_ld_volatile(r + 1); w2 = te_ld_volatile(r + 2);
         if ((uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag && (uint32_t)(w2 >> 32) == tag) break;
-        __nanosleep(40);
+        __nanosleep(250);
       }
       m[k] = (w0 & 0xffffffffull) | (w1 << 32);
       e[k] = (int)(uint32_t)w2;
@@ -614,7 +616,7 @@ __global__ void __launch_bounds__(kTabThreads) te_table_kernel(const __grid_cons
   emax = __reduce_max_sync(0xffffffffu, emax);
   if (lane == 0) ired[warp] = emax;
   __syncthreads();
-  int E = ired[lane];
+  int E = lane < kTabThreads / 32 ? ired[lane] : GJB_TE_E_NONE;
   E = __reduce_max_sync(0xffffffffu, E);
   uint64_t pre[kPer];
   uint8_t sft[kPer];
@@ -633,7 +635,7 @@ __global__ void __launch_bounds__(kTabThreads) te_table_kernel(const __grid_cons
   }
   if (lane == 31) red[warp] = inc;
   __syncthreads();
-  uint64_t wv = red[lane], winc = wv;  // every warp scans the 32 warp totals
+  uint64_t wv = lane < kTabThreads / 32 ? red[lane] : 0ull, winc = wv;  // every warp scans the warp totals
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const uint64_t v = __shfl_up_sync(0xffffffffu, winc, o);
@@ -661,9 +663,8 @@ __global__ void __launch_bounds__(kTabThreads) te_table_kernel(const __grid_cons
     if (A.lse_out) te_write_lse(A.lse_out, E, S, A.n_total);
   }
   __syncthreads();
-  if (S == 0) return;
   const int n_win = (int)((A.n_local + kTeTile - 1) / kTeTile);
-  for (int w = tid; w < n_win; w += kTabThreads) {
+  for (int w = tid; w < (S ? n_win : 0); w += kTabThreads) {
     const int64_t ws = A.slot_offset + (int64_t)w * kTeTile;
     const int64_t left = A.slot_offset + A.n_local - ws;
     const int64_t we = ws + (left < kTeTile ? left : kTeTile);
@@ -680,6 +681,54 @@ __global__ void __launch_bounds__(kTabThreads) te_table_kernel(const __grid_cons
     }
     tab->win[w][0] = p_first;
     tab->win[w][1] = lo < n_tiles ? lo : n_tiles - 1;
+  }
+  __syncthreads();
+  if (tid == 0) {  // the tag goes last: the next step kernel's CTAs are spinning on it
+    __threadfence();
+    te_st_volatile(reinterpret_cast<uint64_t*>(&tab->tag), (uint64_t)tag);
+  }
+}
+
+// ---------------------------------------------------------------- small host-path helpers (no eager torch on the path)
+
+// MH accept: mask[i] = log(u[i]) < w[i]  (tests/inference/test_requests.py:136-137 `jnp.log(uniform) < w`)
+__global__ void __launch_bounds__(256) accept_mask_kernel(const float* __restrict__ u, const float* __restrict__ w, int64_t n,
+                                                          int32_t* __restrict__ mask) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    mask[i] = logf(__ldg(u + i)) < __ldg(w + i) ? 1 : 0;
+}
+
+// out[i, :] = mask[i] ? a[i, :] : b[i, :]  (`jtu.tree_map(lambda v1, v2: jnp.where(check, v1, v2), new, old)`); rows of
+// `words` 32-bit words; a_stride / b_stride = 0 broadcasts one row
+__global__ void __launch_bounds__(256) select_rows_kernel(const int32_t* __restrict__ mask, const uint32_t* __restrict__ a,
+                                                          const uint32_t* __restrict__ b, uint32_t* __restrict__ out, int64_t n,
+                                                          int words, int64_t a_stride, int64_t b_stride) {
+  const int64_t total = n * words;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / words;
+    const int k = (int)(e - i * words);
+    out[e] = __ldg(mask + i) ? __ldg(a + i * a_stride + k) : __ldg(b + i * b_stride + k);
+  }
+}
+
+// effective sample size (sum w)^2 / sum w^2 of w = exp(logw - M): one CTA, fp64 accumulation in a fixed order
+__global__ void __launch_bounds__(1024) ess_kernel(const float* __restrict__ logw, int64_t n, const double* __restrict__ lse3,
+                                                   double* __restrict__ out) {
+  __shared__ double s1[32], s2[32];
+  const float M = (float)lse3[0];
+  double a = 0.0, b = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) {
+    const double w = (double)expf(__ldg(logw + i) - M);
+    a += w; b += w * w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = a; s2[threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0.0, tb = 0.0;
+    for (int w = 0; w < 32; ++w) { ta += s1[w]; tb += s2[w]; }
+    out[0] = tb > 0.0 ? ta * ta / tb : 0.0;
   }
 }
 
@@ -886,6 +935,44 @@ int gjb_resample_multinomial(const float* logw, int64_t n, const uint32_t* wmax,
   if (n_out == 0) return 0;
   multinomial_search_kernel<<<grid_for(n_out, 256), 256, 0, (cudaStream_t)stream>>>(cdf, n, key0, key1, idx_offset,
                                                                                    n_out, ancestors);
+  return launch_status();
+}
+
+int gjb_resample_multinomial_keydev(const float* logw, int64_t n, const uint32_t* wmax, const uint64_t* tile_mass,
+                                    uint64_t* cdf, const uint32_t* key_dev, uint64_t idx_offset, int64_t n_out,
+                                    int32_t* ancestors, void* stream) {
+  if (!logw || !wmax || !tile_mass || !cdf || !ancestors || !key_dev || n <= 0 || n_out < 0) return GJB_E_ARG;
+  if (n >= GJB_MASS_MAX_PARTICLES) return GJB_E_RANGE;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  cdf_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(logw, n, wmax, tile_mass, cdf);
+  int e = launch_status();
+  if (e) return e;
+  if (n_out == 0) return 0;
+  multinomial_search_kernel<<<grid_for(n_out, 256), 256, 0, (cudaStream_t)stream>>>(cdf, n, 0u, 0u, idx_offset, n_out,
+                                                                                   ancestors, key_dev);
+  return launch_status();
+}
+
+int gjb_accept_mask(const float* u, const float* w, int64_t n, int32_t* mask, void* stream) {
+  if (!u || !w || !mask || n < 0) return GJB_E_ARG;
+  if (n == 0) return 0;
+  accept_mask_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(u, w, n, mask);
+  return launch_status();
+}
+
+int gjb_select_rows(const int32_t* mask, const void* a, const void* b, void* out, int64_t n, int32_t row_bytes,
+                    int32_t a_broadcast, int32_t b_broadcast, void* stream) {
+  if (!mask || !a || !b || !out || n < 0 || row_bytes <= 0 || (row_bytes & 3)) return GJB_E_ARG;
+  if (n == 0) return 0;
+  const int words = row_bytes / 4;
+  select_rows_kernel<<<grid_for(n * words, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      mask, (const uint32_t*)a, (const uint32_t*)b, (uint32_t*)out, n, words, a_broadcast ? 0 : words, b_broadcast ? 0 : words);
+  return launch_status();
+}
+
+int gjb_weight_ess(const float* logw, int64_t n, const double* lse3, double* out, void* stream) {
+  if (!logw || !lse3 || !out || n <= 0) return GJB_E_ARG;
+  ess_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logw, n, lse3, out);
   return launch_status();
 }
 

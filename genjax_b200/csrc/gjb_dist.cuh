@@ -15,7 +15,9 @@ constexpr float kLog2OverPiHalf = -0.22579135264472743236f;  // 0.5*log(2/pi)
 
 // ------------------------------------------------------------------ normal
 struct Normal {
-  __device__ static __forceinline__ float sample(float z, float loc, float scale) { return loc + scale * z; }
+  // one correctly rounded FMA (oracle/dists.py normal_sample does the same): with the bit-reproducible Box-Muller of
+  // gjb_rng.cuh the sampled value is bit-exact against the CPU oracle
+  __device__ static __forceinline__ float sample(float z, float loc, float scale) { return __fmaf_rn(scale, z, loc); }
   // logpdf with the particle-invariant pieces precomputed: inv = 1/scale, lc = 0.5 log 2pi + log scale
   __device__ static __forceinline__ float logpdf_r(float v, float loc, float inv, float lc) {
     const float z = v * inv - loc * inv;

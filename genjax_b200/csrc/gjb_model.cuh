@@ -250,8 +250,8 @@ __device__ __forceinline__ float group_sum(float x) {
 __device__ __forceinline__ V4 mvn_diag_sample(const Lane& l, uint32_t site, uint32_t chunk, const V4& loc,
                                               const V4& scale) {
   const float4 z = normal4(l, site, chunk);
-  return V4{{loc.v[0] + scale.v[0] * z.x, loc.v[1] + scale.v[1] * z.y, loc.v[2] + scale.v[2] * z.z,
-             loc.v[3] + scale.v[3] * z.w}};
+  return V4{{__fmaf_rn(scale.v[0], z.x, loc.v[0]), __fmaf_rn(scale.v[1], z.y, loc.v[1]), __fmaf_rn(scale.v[2], z.z, loc.v[2]),
+             __fmaf_rn(scale.v[3], z.w, loc.v[3])}};
 }
 __device__ __forceinline__ float mvn_diag_logpdf4(const V4& v, const V4& loc, const V4& scale) {
   float s = 0.0f;

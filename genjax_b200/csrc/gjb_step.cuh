@@ -427,7 +427,7 @@ __device__ __forceinline__ void te_finish_step(const gjb_step_link* __restrict__
     for (;;) {
       w0 = te_ld_volatile(r); w1 = te_ld_volatile(r + 1); w2 = te_ld_volatile(r + 2);
       if ((uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag && (uint32_t)(w2 >> 32) == tag) break;
-      __nanosleep(40);
+      __nanosleep(250);
     }
     m = (w0 & 0xffffffffull) | (w1 << 32);
     e = (int)(uint32_t)w2;
@@ -527,15 +527,30 @@ __device__ __forceinline__ void te_finish_step(const gjb_step_link* __restrict__
       tab->win[w][1] = lo < n_tiles ? lo : n_tiles - 1;
     }
   }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    te_st_volatile(reinterpret_cast<uint64_t*>(&tab->tag), (uint64_t)tag);
+  }
 }
 
 // Consumer on the table of the previous launch: global parent ids of the offspring slots [w_lo, w_lo + w_n) of local
 // window `w_local`, blocked layout as te_pull.  No prefix work: S, E, the parent tile range and the tile prefixes are read.
+// want_tag != 0: the table is being built by a kernel running beside this one; spin until it carries the tag.
 template <bool kCg>
 __device__ __forceinline__ uint64_t te_pull_table(const gjb_step_table* __restrict__ tab, int w_local,
                                                   const uint64_t* __restrict__ cdf, const gjb_peers* cdf_peers, int64_t n_total,
-                                                  double u0, int64_t w_lo, int w_n, TeSmem& sm, int32_t (&anc)[kTeItems], int* e_out) {
+                                                  double u0, int64_t w_lo, int w_n, TeSmem& sm, int32_t (&anc)[kTeItems], int* e_out,
+                                                  uint32_t want_tag = 0u) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (want_tag) {
+    if (tid == 0) {
+      const uint64_t* tw = reinterpret_cast<const uint64_t*>(&tab->tag);  // {tag, reserved} as one aligned 8-byte word
+      while ((uint32_t)te_ld_volatile(tw) != want_tag) __nanosleep(500);  // (hundreds of CTAs poll one line: keep it light)
+      __threadfence();  // acquire: the table stores that preceded the tag are visible to the loads below
+    }
+    __syncthreads();
+  }
   const uint64_t S = __ldcg(reinterpret_cast<const unsigned long long*>(&tab->S));
   *e_out = __ldcg(&tab->E);
   const int2 win = __ldcg(reinterpret_cast<const int2*>(&tab->win[w_local][0]));

@@ -846,7 +846,13 @@ class _Generator:
             out.append("  quad_rng<true>(fl, key0, key1, (A.idx_offset >> 2) + (uint64_t)q0, R0);")
             out.append("  quad_rng<true>(fl, key0, key1, (A.idx_offset >> 2) + (uint64_t)q0 + 1, R1);")
         out.append("  GJB_TP(1);")
-        out.append("  gjb::pdl_wait();  // everything the previous launch wrote (state, CDF rows, table / records) is visible from here on")
+        out.append("  // table form: the table kernel runs BESIDE the step kernels and flags its table with the step's tag; the CTAs spin on")
+        out.append("  // that flag (te_pull_table) instead of waiting for a kernel boundary -- every record behind the table was mailed after")
+        out.append("  // its tile's data was fenced into L2, so the flag covers the bulk data too.  Table-free form: wait for the previous launch.")
+        out.append("  // (measured on B200: the flag hand-off is SLOWER than the kernel boundary, 30.7 vs 22.5 us per step on one device, so it is")
+        out.append("  // opt-in: GJB_STEP_FLAGWAIT)")
+        out.append("  const bool flagged = A.table_in && A.link && (A.flags & GJB_STEP_FLAGWAIT);")
+        out.append("  if (!flagged) gjb::pdl_wait();")
         out.append("  if (A.prev_cdf) {  // ancestors of MY slots: output-slot systematic resampling of the previous step")
         out.append("    const double u0 = gjb::resample_u0(__ldg(A.prev_key), __ldg(A.prev_key + 1), (uint64_t)__ldg(A.prev_key + 2) | ((uint64_t)__ldg(A.prev_key + 3) << 32));")
         out.append("    int32_t anc[gjb::kTeItems];")
@@ -855,7 +861,8 @@ class _Generator:
         out.append("    if (A.table_in) {  // the previous launch's last CTA left the prefix table: no prefix work here")
         out.append("      // (everything the previous launch produced is read through L2: with programmatic dependent launch this CTA may")
         out.append("      // have become resident before that launch finished, so nothing may come from a possibly stale L1 line)")
-        out.append("      gjb::te_pull_table<true>(A.table_in, (int)blockIdx.x, A.prev_cdf, A.cdf_peers, A.n_total, u0, w_glob, w_n, sm, anc, &E);")
+        out.append("      gjb::te_pull_table<true>(A.table_in, (int)blockIdx.x, A.prev_cdf, A.cdf_peers, A.n_total, u0, w_glob, w_n, sm, anc, &E,")
+        out.append("                               flagged ? gjb::te_tag(A.link, A.step - 1) : 0u);")
         out.append("    } else {           // single device, table-free: every CTA forms the tile prefix from the plain records")
         out.append("      uint64_t S;")
         out.append("      if (A.n_tiles_total <= 2 * kThreads) {")

@@ -303,14 +303,22 @@ class StaticTrace(Trace):
             sel = idx.to(self.score.device).long()
             out_batched = True
 
+        sel32 = sel.to(torch.int32).contiguous()
+
         def g(t, b):
-            return t if b or not isinstance(t, torch.Tensor) else t.index_select(0, sel)
+            if b or not isinstance(t, torch.Tensor):
+                return t
+            if t.element_size() == 4 and t.shape[0] == self.n:  # float32 / int32 leaves: the resampling gather kernel
+                from ..runtime import smc_ops
+
+                return smc_ops.gather_rows(t.contiguous(), sel32)
+            return t.index_select(0, sel)
 
         values = {k: g(v, self.bcast[k]) for k, v in self.values.items()}
         rets = [g(r, False) for r in self.ret_leaves]
         args = _take_args(self.args, sel)
         return StaticTrace(self.gen_fn, self.cm, None, args, int(sel.numel()), out_batched, values,
-                           self.score.index_select(0, sel), rets, dict(self.bcast))
+                           g(self.score, False), rets, dict(self.bcast))
 
 
 class ZeroTrace(Trace):

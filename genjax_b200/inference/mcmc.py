@@ -181,8 +181,11 @@ def mh_accept(key, new_trace: StaticTrace, old_trace: StaticTrace, weight: torch
     from ..gen.distributions import uniform
     from ..gen.static import Batched
 
+    from ..runtime import smc_ops
+
     u = uniform.sample(key, 0.0, 1.0) if old_trace.batched else uniform.sample(key, 0.0, 1.0).reshape(1)
-    check = torch.log(u) < weight.reshape(-1)
+    mask = smc_ops.accept_mask(u, weight.reshape(-1).to(torch.float32))  # log(u) < w, one small kernel
+    check = mask.bool()
     ir = old_trace.cm.ir
     chm = ChoiceMap.empty()
     n = old_trace.n
@@ -193,10 +196,7 @@ def mh_accept(key, new_trace: StaticTrace, old_trace: StaticTrace, weight: torch
             chm = chm | ChoiceMap.entry(a, *s.addr)
             continue
         ev = tuple(s.value.shape)
-        a = a.reshape((-1,) + ev).expand((n,) + ev)
-        b = b.reshape((-1,) + ev).expand((n,) + ev)
-        c = check.reshape((n,) + (1,) * len(ev))
-        chm = chm | ChoiceMap.entry(Batched(torch.where(c, a, b).contiguous()), *s.addr)
+        chm = chm | ChoiceMap.entry(Batched(smc_ops.select_rows(mask, a, b, n, ev)), *s.addr)  # where(check, new, old)
     tr, _ = old_trace.gen_fn._run(None, old_trace.args, chm, weight_mode="none", n=n, batched=old_trace.batched)
     return tr, check
 

@@ -59,7 +59,7 @@ class ParticleFilter:
     particles).  Every other site is proposed from the model (bootstrap)."""
 
     def __init__(self, step: StaticGenerativeFunction, n_particles: int, *, n_state: int = 1, resampler: str = "systematic",
-                 idx_offset: int = 0, n_total: int | None = None, mode: str = "graph", reference_max: str = "running",
+                 idx_offset: int = 0, n_total: int | None = None, mode: str = "auto", reference_max: str = "running",
                  single_pass: bool = False):
         """``reference_max``: what the exact integer weight masses are taken relative to.  "running" (default): the
         maximum of the step's weights, found by a running max in the model kernel, masses in the resampling launch.
@@ -67,10 +67,23 @@ class ParticleFilter:
         (``gen/bounds.py``); the masses are then accumulated in the model kernel itself and the step needs neither
         the max nor the mass pass.  Same estimator, ancestors differ in the last bits of the
         masses; a bound so loose that every mass underflows shows up as ``lse_terms[:, 1] == 0``."""
-        if resampler != "systematic":
-            raise NotImplementedError("the fused filter loop uses systematic resampling; see ParticleCollection.resample")
-        if mode not in ("persistent", "graph", "step"):
+        if resampler not in ("systematic", "multinomial"):
+            raise ValueError(f"resampler must be 'systematic' or 'multinomial', not {resampler!r}")
+        if mode not in ("auto", "persistent", "graph", "step"):
             raise ValueError(mode)
+        if resampler == "multinomial":
+            # the reference idiom itself: N independent categorical draws over the normalised weights per step
+            # (mapping_tutorial.ipynb cell 37; inference/smc.py:102-109), as inverse-CDF draws over the exact integer CDF
+            if mode not in ("auto", "graph") or reference_max != "running" or single_pass or idx_offset or n_total not in (None, n_particles):
+                raise NotImplementedError("resampler='multinomial' runs in mode='graph' on one device (model launch + mass + "
+                                          "CDF + search per step)")
+            mode = "graph"
+        self.resampler = resampler
+        if mode == "auto":
+            # the single-launch step kernel (tile-exponent CDF) wherever it applies -- the fastest verified form (B200, 1 M
+            # particles, d = 1: 17-18 us per step against 21.8 for the two-launch exact-max form); a plan falls back to
+            # "graph" when the model or the particle count is outside what the step kernel handles (see _Plan)
+            mode = "graph" if (reference_max != "running" or single_pass) else "auto"
         if mode == "step" and reference_max != "running":
             raise ValueError("mode='step' forms its masses per tile (tile-exponent CDF); it takes no reference_max")
         if reference_max not in ("running", "analytic"):
@@ -204,9 +217,12 @@ class _Plan:
             self.obs_sites[ir.site_index(addr)] = addr
         self.graph = None
         self.persistent = pf.mode == "persistent"
-        self.stepmode = pf.mode == "step"
+        tiles = (n + cabi.TE_TILE - 1) // cabi.TE_TILE
+        step_ok = (tiles <= cabi.TE_MAX_TILES and pf.n_total == n and n <= (1 << 26) and pf.idx_offset % 4 == 0
+                   and T < 65535 and self.cm.info.get("pf_step", False))
+        self.stepmode = pf.mode == "step" or (pf.mode == "auto" and step_ok)
+        self.mode = "step" if self.stepmode else ("graph" if pf.mode == "auto" else pf.mode)
         if self.stepmode:
-            tiles = (n + cabi.TE_TILE - 1) // cabi.TE_TILE
             if tiles > cabi.TE_MAX_TILES or pf.n_total > (1 << 26):
                 raise NotImplementedError(f"mode='step' resamples over at most {cabi.TE_MAX_TILES} tiles of {cabi.TE_TILE} "
                                           "particles; use mode='graph' beyond that")
@@ -322,7 +338,7 @@ class _Plan:
             A.step = t
             # programmatic dependent launch behind the previous step kernel: this launch draws its random numbers while
             # that one drains (the first step follows copies / other kernels and is launched normally)
-            A.flags = cabi.STEP_PDL if (pdl and t > 0) else 0
+            A.flags = (cabi.STEP_PDL if (pdl and t > 0) else 0) | (cabi.STEP_FLAGWAIT if os.environ.get("GJB_STEP_FLAGWAIT") == "1" else 0)
             A.key_dev = self.keys[t].data_ptr()
             slot = t if self.record else (t & 1)
             prev_slot = (t - 1) if self.record else ((t - 1) & 1)
@@ -461,6 +477,9 @@ class _Plan:
                 continue
             A.wmax = self.wmax2[t & 1 :].data_ptr()
             self.margs.append(A)
+            if pf.resampler == "multinomial":
+                self.rargs.append((lw, None))
+                continue
             R = self.ws.systematic_args(
                 lw, None, self.anc[slot], n_total=pf.n_total, out_lo=pf.idx_offset, anc_base=pf.idx_offset,
                 key_dev=self.keys[t][2:], lse_out=self.lse[t], wmax=self.wmax2[t & 1 :],
@@ -507,6 +526,28 @@ class _Plan:
             for k in range(len(self.bufs)):
                 smc_ops.gather_rows(self.bufs[k][last], self.anc[last], self.final[k])
             return
+        if self.pf.resampler == "multinomial":
+            # per step: model launch (weights + running max) | exact integer tile masses | log-mean-exp | CDF + one
+            # inverse-CDF search per offspring, offspring j on lane j of split(k_res, N)
+            if getattr(self, "mn_cdf", None) is None:
+                self.mn_cdf = torch.empty(self.pf.n, dtype=torch.int64, device=self.device)
+            n = self.pf.n
+            for t in range(self.T):
+                wm = self.wmax2[t & 1 :]
+                cabi.check(core.gjb_wmax_reset(wm.data_ptr(), stream), "gjb_wmax_reset")
+                cabi.check(lib.gjb_model_launch(C.byref(self.margs[t]), stream), "gjb_model_launch")
+                lw = self.rargs[t][0]
+                cabi.check(core.gjb_weight_mass(lw.data_ptr(), n, wm.data_ptr(), None, self.ws.tile_mass.data_ptr(), stream), "gjb_weight_mass")
+                cabi.check(core.gjb_lse_finalize(self.ws.tile_mass.data_ptr(), n, wm.data_ptr(), None, n, self.lse[t].data_ptr(), stream),
+                           "gjb_lse_finalize")
+                slot = t if self.record else (t & 1)
+                cabi.check(core.gjb_resample_multinomial_keydev(lw.data_ptr(), n, wm.data_ptr(), self.ws.tile_mass.data_ptr(),
+                                                                self.mn_cdf.data_ptr(), self.keys[t][6:].data_ptr(), 0, n,
+                                                                self.anc[slot].data_ptr(), stream), "gjb_resample_multinomial_keydev")
+            last = (self.T - 1) if self.record else ((self.T - 1) & 1)
+            for k in range(len(self.bufs)):
+                smc_ops.gather_rows(self.bufs[k][last], self.anc[last], self.final[k])
+            return
         cabi.check(core.gjb_wmax_reset(self.wmax2.data_ptr(), stream), "gjb_wmax_reset")
         fused = getattr(self, "fuse_mass_resample", None)
         if fused is None:
@@ -537,6 +578,8 @@ class _Plan:
             return self.T + 1 + len(self.bufs)  # (+ one memset node)
         if self.analytic:
             return 2 * self.T + len(self.bufs)  # (+ one memset node)
+        if self.pf.resampler == "multinomial":
+            return 6 * self.T + len(self.bufs)
         return 1 + (2 if getattr(self, "fuse_mass_resample", False) else 3) * self.T + len(self.bufs)
 
     def execute(self, key, state0, shared, obs, use_graph):

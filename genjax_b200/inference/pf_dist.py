@@ -455,7 +455,7 @@ class _DistStepPlan:
             A = cabi.StepArgs()
             A.n, A.n_total, A.idx_offset, A.slot_offset = n, pf.n_total, rank * n, rank * n
             A.step = t
-            A.flags = cabi.STEP_PDL if (pdl and t > 0) else 0
+            A.flags = (cabi.STEP_PDL if (pdl and t > 0) else 0) | (cabi.STEP_FLAGWAIT if os.environ.get("GJB_STEP_FLAGWAIT") == "1" else 0)
             A.key_dev = self.keys[t].data_ptr()
             slot = t if record else (t & 1)
             pslot = (t - 1) if record else ((t - 1) & 1)

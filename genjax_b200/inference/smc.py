@@ -68,9 +68,8 @@ class ParticleCollection:
         return bool(self.lse_terms()[1].item() > 0)
 
     def effective_sample_size(self) -> torch.Tensor:
-        lw = self.log_weights - self.lse_terms()[0].to(torch.float32)
-        w = torch.exp(lw)
-        return w.sum() ** 2 / (w * w).sum()
+        """(sum w)^2 / sum w^2 with w = exp(lw - M): one small kernel, fp64 accumulation in a fixed order."""
+        return smc_ops.weight_ess(self.log_weights, self.lse_terms())
 
     # -- checkpointing (SURVEY 8f-4: the on-disk side of a resumable run) ----
     def state_dict(self) -> dict:

@@ -13,7 +13,7 @@ import torch
 
 from . import build
 
-ABI_VERSION = 12  # GJB_ABI_VERSION of include/genjax_b200.h this binding mirrors (tests/test_abi.py keeps them equal)
+ABI_VERSION = 13  # GJB_ABI_VERSION of include/genjax_b200.h this binding mirrors (tests/test_abi.py keeps them equal)
 GJB_MAX_SITES = 16
 GJB_MAX_ARGS = 16
 GJB_MAX_RETS = 8
@@ -23,6 +23,7 @@ TE_MAX_TILES = 4096
 TE_LL_WORDS = 4
 TE_MAILBOX_WORDS = 2 * TE_MAX_TILES * TE_LL_WORDS
 STEP_PDL = 1
+STEP_FLAGWAIT = 2
 MASS_MAX_PARTICLES = 1 << 27
 
 SITE_SAMPLE = 1
@@ -185,7 +186,7 @@ class TileRec(C.Structure):
 class StepTable(C.Structure):
     """``gjb_step_table`` (include/genjax_b200.h section 1c)."""
 
-    _fields_ = [("S", _u64), ("E", _i32), ("n_tiles_total", _i32), ("pre", _u64 * TE_MAX_TILES),
+    _fields_ = [("S", _u64), ("E", _i32), ("n_tiles_total", _i32), ("tag", _u32), ("reserved", _u32), ("pre", _u64 * TE_MAX_TILES),
                 ("win", (_i32 * 2) * TE_MAX_TILES), ("shf", C.c_uint8 * TE_MAX_TILES)]
 
 
@@ -293,6 +294,10 @@ CORE_PROTOTYPES = {
     "gjb_mass_resample_fits": (C.c_int, [_i64]),
     "gjb_mass_resample_systematic": (C.c_int, [C.POINTER(ResampleArgs), _p]),
     "gjb_resample_multinomial": (C.c_int, [_p, _i64, _p, _p, _p, _u32, _u32, _u64, _i64, _p, _p]),
+    "gjb_resample_multinomial_keydev": (C.c_int, [_p, _i64, _p, _p, _p, _p, _u64, _i64, _p, _p]),
+    "gjb_accept_mask": (C.c_int, [_p, _p, _i64, _p, _p]),
+    "gjb_select_rows": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
+    "gjb_weight_ess": (C.c_int, [_p, _i64, _p, _p, _p]),
     "gjb_gather_rows": (C.c_int, [_p, _p, _p, _i64, _i32, _p]),
     "gjb_exchange": (C.c_int, [C.POINTER(XchgArgs), _p]),
     "gjb_peers_set_divisor": (C.c_int, [C.POINTER(Peers)]),

@@ -169,6 +169,38 @@ def gather_rows(src: torch.Tensor, ancestors: torch.Tensor, out: torch.Tensor | 
     return out
 
 
+def accept_mask(u: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """int32 [n]: ``log(u) < w`` (the MH accept test of the reference's tests, test_requests.py:136-137)."""
+    n = u.numel()
+    mask = torch.empty(n, dtype=torch.int32, device=u.device)
+    cabi.check(cabi.core().gjb_accept_mask(cabi.ptr(u.contiguous()), cabi.ptr(w.contiguous()), n, cabi.ptr(mask),
+                                           cabi.stream_ptr(u.device)), "gjb_accept_mask")
+    return mask
+
+
+def select_rows(mask: torch.Tensor, a: torch.Tensor, b: torch.Tensor, n: int, event_shape: tuple) -> torch.Tensor:
+    """out[i] = a[i] if mask[i] else b[i] over the leading axis; ``a`` / ``b`` of event shape only are broadcast."""
+    row = 1
+    for d in event_shape:
+        row *= d
+    a_b = a.numel() == row and n != 1
+    b_b = b.numel() == row and n != 1
+    if a.dtype != b.dtype or a.element_size() != 4:
+        raise cabi.GjbError("select_rows handles equal 4-byte element types")
+    out = torch.empty((n,) + tuple(event_shape), dtype=a.dtype, device=mask.device)
+    cabi.check(cabi.core().gjb_select_rows(cabi.ptr(mask), cabi.ptr(a.contiguous()), cabi.ptr(b.contiguous()), cabi.ptr(out), n,
+                                           row * 4, int(a_b), int(b_b), cabi.stream_ptr(mask.device)), "gjb_select_rows")
+    return out
+
+
+def weight_ess(logw: torch.Tensor, lse3: torch.Tensor) -> torch.Tensor:
+    """Effective sample size of ``logw`` given its lse terms (float64 0-d)."""
+    out = torch.empty(1, dtype=torch.float64, device=logw.device)
+    cabi.check(cabi.core().gjb_weight_ess(cabi.ptr(logw), logw.numel(), cabi.ptr(lse3), cabi.ptr(out),
+                                          cabi.stream_ptr(logw.device)), "gjb_weight_ess")
+    return out[0]
+
+
 def philox_words(words, idx_offset, site, chunk, n, device) -> torch.Tensor:
     out = torch.empty((n, 4), dtype=torch.int32, device=device)
     cabi.check(

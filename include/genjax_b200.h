@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GJB_ABI_VERSION 12
+#define GJB_ABI_VERSION 13
 
 #define GJB_E_ARG (-1)      /* null / misaligned pointer, negative size          */
 #define GJB_E_RANGE (-2)    /* size beyond what the kernel supports              */
@@ -138,6 +138,11 @@ int gjb_resample_multinomial(const float* logw, int64_t n, const uint32_t* wmax,
                              uint32_t key0, uint32_t key1, uint64_t idx_offset,
                              int64_t n_out, int32_t* ancestors, void* stream);
 
+/* The same with {key0, key1} read on the device (the filter loop replays a CUDA graph with a new key table). */
+int gjb_resample_multinomial_keydev(const float* logw, int64_t n, const uint32_t* wmax,
+                                    const uint64_t* tile_mass, uint64_t* cdf, const uint32_t* key_dev,
+                                    uint64_t idx_offset, int64_t n_out, int32_t* ancestors, void* stream);
+
 /*
  * dst[j, :] = src[ancestors[j], :]  (row_bytes per row, multiple of 4).
  * ParticleCollection.get_particle / tree_map(lambda v: v[idx]),
@@ -145,6 +150,19 @@ int gjb_resample_multinomial(const float* logw, int64_t n, const uint32_t* wmax,
  */
 int gjb_gather_rows(const void* src, const int32_t* ancestors, void* dst,
                     int64_t n_out, int32_t row_bytes, void* stream);
+
+/*
+ * The user-side MH accept step (tests/inference/test_requests.py:136-137, 190-191):
+ *   check = log(uniform(key)) < w;  trace = tree_map(lambda new, old: where(check, new, old), new_trace, old_trace)
+ * gjb_accept_mask: mask[i] = log(u[i]) < w[i];  gjb_select_rows: out[i, :] = mask[i] ? a[i, :] : b[i, :] (a / b may
+ * be one broadcast row).
+ */
+int gjb_accept_mask(const float* u, const float* w, int64_t n, int32_t* mask, void* stream);
+int gjb_select_rows(const int32_t* mask, const void* a, const void* b, void* out, int64_t n, int32_t row_bytes,
+                    int32_t a_broadcast, int32_t b_broadcast, void* stream);
+
+/* Effective sample size (sum w)^2 / sum w^2, w = exp(logw - lse3[0]) (lse3 from gjb_lse_finalize); out: 1 double. */
+int gjb_weight_ess(const float* logw, int64_t n, const double* lse3, double* out, void* stream);
 
 /* ----------------------------------------------- 1b. multi-GPU (one process per GPU)
  *
@@ -278,6 +296,9 @@ typedef struct gjb_step_table {
   uint64_t S;                /* total aligned mass (0: no weight has mass)       */
   int32_t E;                 /* global exponent                                  */
   int32_t n_tiles_total;
+  uint32_t tag;              /* the step's record tag, stored LAST (after a fence): consumers of the next launch spin on it
+                                instead of waiting for a kernel boundary           */
+  uint32_t reserved;
   uint64_t pre[GJB_TE_MAX_TILES];      /* inclusive prefix of (mass_p >> shf[p]), global tile order */
   int32_t win[GJB_TE_MAX_TILES][2];    /* local window w: first / last parent tile with offspring in it */
   uint8_t shf[GJB_TE_MAX_TILES];
@@ -320,6 +341,7 @@ typedef struct gjb_te_table_args {
 #define GJB_STEP_PDL 1u      /* launch with programmatic stream serialization: the launch may start while the previous
                                 kernel on the stream drains; a step kernel draws its random numbers, then waits
                                 (griddepcontrol.wait) before it touches anything the previous launch wrote */
+#define GJB_STEP_FLAGWAIT 2u /* step kernel, table form: spin on the table's tag instead of waiting for the kernel boundary */
 int gjb_te_table(const gjb_te_table_args* a, void* stream);
 
 typedef struct gjb_te_resample_args {

@@ -127,7 +127,7 @@ int pf_lgssm(int64_t n, int T, int d, float* x, const float* ys, float a, const 
         box_muller(o[0], o[1], &z[0], &z[1]);
         box_muller(o[2], o[3], &z[2], &z[3]);
         const float loc = a * x[i];
-        const float xv = loc + q[0] * z[i & 3];
+        const float xv = fmaf(q[0], z[i & 3], loc);
         xn[i] = xv;
         w = normal_logpdf(y[0], c * xv, r[0]);
       } else {
@@ -139,7 +139,7 @@ int pf_lgssm(int64_t n, int T, int d, float* x, const float* ys, float a, const 
           box_muller(o[2], o[3], &z[2], &z[3]);
           for (int s = 0; s < 4; ++s) {
             const int j = 4 * ch + s;
-            if (j < d) xn[i * d + j] = a * x[i * d + j] + q[j] * z[s];
+            if (j < d) xn[i * d + j] = fmaf(q[j], z[s], a * x[i * d + j]);
           }
         }
         for (int j = 0; j < d; ++j) w = w + normal_logpdf(y[j], c * xn[i * d + j], r[j]);

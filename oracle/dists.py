@@ -333,7 +333,7 @@ def _bc(a, n):
 
 def normal_sample(words, idx, site, loc, scale):
     z = rng.quad_normal(words, idx, site)
-    return (_f(loc) + _f(scale) * z).astype(F32)
+    return rng.fma32(_f(scale), z, _f(loc))  # one fused multiply-add, as Normal::sample on the device
 
 
 def uniform_sample(words, idx, site, low, high):
@@ -431,7 +431,7 @@ def mv_normal_diag_sample(words, idx, site, loc, scale_diag):
     scale_diag = _f(scale_diag)
     d = max(loc.shape[-1] if loc.ndim else 1, scale_diag.shape[-1] if scale_diag.ndim else 1)
     z = rng.normal_vec(words, idx, site, d)
-    return (loc + scale_diag * z).astype(F32)
+    return rng.fma32(np.broadcast_to(scale_diag, z.shape), z, np.broadcast_to(loc, z.shape))  # one FMA per element (mvn_diag_sample)
 
 
 def half_normal_sample(words, idx, site, scale):

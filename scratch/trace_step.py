@@ -18,8 +18,8 @@ x0 = torch.from_numpy(g.standard_normal(n if d == 1 else (n, d)).astype(np.float
 r_sd = a.obs_sd if a.obs_sd is not None else LG_R
 shared = () if d == 1 else (torch.full((d,), LG_Q), torch.full((d,), r_sd))
 pf = ParticleFilter(lgssm_step if d == 1 else lgssm_step_vec, n, mode="step")
-for rep in range(3):
-    res = pf.run(gj.key(rep), x0, gj.C["y"].set(ys), shared_args=shared, use_graph=False)
+for rep in range(4):
+    res = pf.run(gj.key(rep), x0, gj.C["y"].set(ys), shared_args=shared, use_graph=os.environ.get("GJB_TRACE_GRAPH", "1") == "1")
 torch.cuda.synchronize()
 plan = next(iter(pf._plans.values()))
 lib = plan.cm.lib

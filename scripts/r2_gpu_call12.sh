@@ -1,0 +1,9 @@
+# round 2, GPU call 12 (2 GPUs): table-form tail after optimisation, graph vs eager, the 2-GPU bit-exactness worker, global bench
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+run() { tag=$1; shift; env "$@" > gpurun_out/r2c12_$tag.json 2> gpurun_out/r2c12_$tag.err; tail -2 gpurun_out/r2c12_$tag.err; python -c "
+import json; d=json.loads([l for l in open('gpurun_out/r2c12_$tag.json') if l.startswith('{')][-1]); print('$tag'.ljust(20), 'us/step %.2f' % (d['ms_per_step']*10), 'kernel_us %.2f' % d['roofline']['kernel_us'], 'e2e %.3e' % d['e2e']['value'], 'value %.3e' % d['value'], d['config'].get('logZ_check','')[:40])"; }
+run d1_default CUDA_VISIBLE_DEVICES=0 timeout 120 python bench.py --mode step --no-cpu-baseline --steps 20
+run d1_table CUDA_VISIBLE_DEVICES=0 GJB_STEP_TABLE=1 timeout 120 python bench.py --mode step --no-cpu-baseline --steps 20
+run g2_global timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 2 --mode step --multi-gpu global --no-cpu-baseline --steps 20

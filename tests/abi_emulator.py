@@ -500,7 +500,7 @@ class EmulatedCore:
     oracle/smc.py.  Multi-GPU, fused cooperative and filter entry points are GPU-only and absent on purpose."""
 
     def gjb_abi_version(self):
-        return 12
+        return 13
 
     def gjb_mass_resample_fits(self, n):
         return 0
@@ -626,6 +626,10 @@ class EmulatedCore:
         anc[:] = np.searchsorted(Cq, osmc._mulhi64(r, np.uint64(S)), side="right").astype(I32)
         return 0
 
+    def gjb_resample_multinomial_keydev(self, logw, n, wmax, tile_mass, cdf, key_dev, idx_offset, n_out, ancestors, stream):
+        kd = _arr(key_dev, 2, C.c_uint32, np.uint32)
+        return self.gjb_resample_multinomial(logw, n, wmax, tile_mass, cdf, int(kd[0]), int(kd[1]), idx_offset, n_out, ancestors, stream)
+
     def gjb_philox_fill(self, key0, key1, idx_offset, site, chunk, n, out4, stream):
         from oracle import rng as orng
 
@@ -639,6 +643,27 @@ class EmulatedCore:
 
         idx = np.arange(n, dtype=np.uint64) + np.uint64(idx_offset)
         _view(out, n * d, F32)[:] = orng.normal_vec((key0, key1), idx, site, d).reshape(-1)
+        return 0
+
+    def gjb_accept_mask(self, u, w, n, mask, stream):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            _view(mask, n, I32)[:] = (np.log(_view(u, n, F32)).astype(F32) < _view(w, n, F32)).astype(I32)
+        return 0
+
+    def gjb_select_rows(self, mask, a, b, out, n, row_bytes, a_bcast, b_bcast, stream):
+        words = row_bytes // 4
+        m = _view(mask, n, I32).astype(bool)[:, None]
+        av = _view(a, words if a_bcast else n * words, I32).reshape(-1, words)
+        bv = _view(b, words if b_bcast else n * words, I32).reshape(-1, words)
+        _view(out, n * words, I32).reshape(n, words)[:] = np.where(m, av, bv)
+        return 0
+
+    def gjb_weight_ess(self, logw, n, lse3, out, stream):
+        M = F32(_arr(lse3, 3, C.c_double, np.float64)[0])
+        with np.errstate(invalid="ignore"):
+            w = np.exp((_view(logw, n, F32) - M).astype(F32)).astype(F32).astype(np.float64)
+        s2 = float((w * w).sum())
+        _arr(out, 1, C.c_double, np.float64)[0] = float(w.sum()) ** 2 / s2 if s2 > 0 else 0.0
         return 0
 
     def gjb_gather_rows(self, src, ancestors, dst, n_out, row_bytes, stream):

@@ -53,7 +53,7 @@ def test_cuda_matches_committed_fixtures(device):
     ws.systematic(lw, gj.key(5), anc)
     assert np.array_equal(anc.cpu().numpy(), FIX["resample_systematic"])
     # the 3-step filter: states / log-weights within fp32 tolerance, ancestors given the CUDA weights
-    res = ParticleFilter(lgssm_step, 512).run(gj.key(99), torch.from_numpy(FIX["pf_x0"]),
+    res = ParticleFilter(lgssm_step, 512, mode="graph").run(gj.key(99), torch.from_numpy(FIX["pf_x0"]),
                                                gj.C["y"].set(torch.from_numpy(FIX["pf_ys"])), record=True)
     np.testing.assert_allclose(res.history["log_weights"][0].cpu().numpy(), FIX["pf_logw"][0], rtol=1e-5, atol=2e-5)
     np.testing.assert_allclose(res.history["state"][0][0].cpu().numpy(), FIX["pf_states"][0], rtol=1e-5, atol=2e-6)

@@ -158,7 +158,7 @@ def test_particle_filter_vec_teacher_forced_vs_oracle(device):
     x0 = torch.randn(n, d, generator=torch.Generator().manual_seed(0))
     q = torch.full((d,), Q_)
     r = torch.full((d,), R_)
-    res = ParticleFilter(step_vec, n).run(
+    res = ParticleFilter(step_vec, n, mode="graph").run(
         gj.key(5), x0, gj.C["y"].set(torch.from_numpy(ys)), shared_args=(q, r), record=True
     )
     anc = res.ancestors.cpu().numpy()
@@ -272,7 +272,7 @@ def test_hmm_filter_teacher_forced_and_exact(device):
         z = g.choice(K, p=pt[z])
         ys[t] = g.choice(K, p=po[z])
     z0 = g.integers(0, K, n).astype(np.int32)
-    res = ParticleFilter(hmm_step, n).run(
+    res = ParticleFilter(hmm_step, n, mode="graph").run(
         gj.key(11), torch.from_numpy(z0), gj.C["y"].set(torch.from_numpy(ys)),
         shared_args=(torch.from_numpy(trans), torch.from_numpy(obs)), record=True)
     anc = res.ancestors.cpu().numpy()
@@ -355,3 +355,35 @@ def test_fused_mass_resample_equals_two_launches(device, use_graph, obs_sd):
         lw = res.history["log_weights"][-1].cpu().numpy()
         _, k_res = osmc.pf_step_keys(orng.key(8), T - 1)
         assert np.array_equal(anc, osmc.resample_systematic(lw, k_res))
+
+
+def test_particle_filter_multinomial_resampler(device):
+    """``ParticleFilter(resampler="multinomial")``: the reference idiom's N independent categorical draws per step
+    (mapping_tutorial.ipynb cell 37; inference/smc.py:102-109) -- ancestors bit-exact against the oracle's inverse-CDF
+    multinomial over the same integer CDF, offspring j on lane j of split(k_res, N); CUDA-graph replay with a new key."""
+    gj, step, _ = _models()
+    from genjax_b200.inference.pf import ParticleFilter
+
+    n, T = 20_000, 5
+    ys = osmc.simulate_lgssm(4, T, 1, A_, Q_, C_, R_)[:, 0]
+    x0 = np.random.default_rng(2).standard_normal(n).astype(np.float32)
+    pf = ParticleFilter(step, n, resampler="multinomial")
+    pf.run(gj.key(1), torch.from_numpy(x0), gj.C["y"].set(torch.from_numpy(ys)), record=True)  # captures the graph with another key
+    res = pf.run(gj.key(33), torch.from_numpy(x0), gj.C["y"].set(torch.from_numpy(ys)), record=True)
+    anc = res.ancestors.cpu().numpy()
+    xs = res.history["state"][0].cpu().numpy()
+    lws = res.history["log_weights"].cpu().numpy()
+    x_in, okey = x0, orng.key(33)
+    for t in range(T):
+        kp, kr = osmc.pf_step_keys(okey, t)
+        otr, ow = ogfi.generate(o_step, orng.split(kp, n), {"y": np.float32(ys[t])}, (x_in,))
+        np.testing.assert_allclose(xs[t], otr.choices["x"], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(lws[t], ow, rtol=1e-5, atol=2e-5)
+        assert np.array_equal(anc[t], osmc.resample_multinomial(lws[t], orng.split(kr, n))), f"ancestors step {t}"
+        assert res.log_increments[t].item() == pytest.approx(osmc.log_mean_exp(lws[t]), abs=1e-9)
+        x_in = xs[t][anc[t]]
+    np.testing.assert_array_equal(res.state[0].cpu().numpy(), x_in)
+    # multinomial offspring counts are not sorted-unique like systematic ones: duplicates and gaps both occur
+    assert len(np.unique(anc[-1])) < 0.7 * n
+    with pytest.raises(ValueError):
+        ParticleFilter(step, n, resampler="stratified")

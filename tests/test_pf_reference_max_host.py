@@ -67,7 +67,7 @@ def test_analytic_reference_and_running_max_are_the_same_estimator(emu):
     ys = torch.from_numpy(osmc.simulate_lgssm(3, T, 1, LG_A, LG_Q, LG_C, LG_R)[:, 0])
     x0 = torch.randn(n, generator=torch.Generator().manual_seed(1))
     a = ParticleFilter(lgssm_step, n, reference_max="analytic").run(gj.key(5), x0, gj.C["y"].set(ys), record=True)
-    b = ParticleFilter(lgssm_step, n).run(gj.key(5), x0, gj.C["y"].set(ys), record=True)
+    b = ParticleFilter(lgssm_step, n, mode="graph").run(gj.key(5), x0, gj.C["y"].set(ys), record=True)
     # step 0 sees identical inputs: identical weights, estimate equal to fp64 rounding; ancestors may differ in a few
     # slots (masses are quantised relative to a different reference), after which the runs are different draws
     assert torch.equal(a.history["log_weights"][0], b.history["log_weights"][0])
@@ -100,7 +100,7 @@ def test_analytic_reference_needs_a_derivable_bound_and_graph_mode(emu):
     z0 = torch.from_numpy(g.integers(0, 16, n).astype(np.int32))
     res = ParticleFilter(hmm_step, n, reference_max="analytic").run(gj.key(2), z0, gj.C["y"].set(ys), shared_args=(tl, ol), record=True)
     assert (res.lse_terms[:, 0] == 0).all() and (res.lse_terms[:, 1] > 0).all()
-    ref = ParticleFilter(hmm_step, n).run(gj.key(2), z0, gj.C["y"].set(ys), shared_args=(tl, ol), record=True)
+    ref = ParticleFilter(hmm_step, n, mode="graph").run(gj.key(2), z0, gj.C["y"].set(ys), shared_args=(tl, ol), record=True)
     assert res.log_increments[0].item() == pytest.approx(ref.log_increments[0].item(), abs=2e-7)
 
 

@@ -264,7 +264,7 @@ def test_filter_maxima_stay_below_the_analytic_bound(device):
     n, T = 20_000, 12
     ys = torch.from_numpy(osmc.simulate_lgssm(0, T, 1, 0.9, 1.0, 1.0, 0.5)[:, 0])
     x0 = torch.randn(n, generator=torch.Generator().manual_seed(0))
-    pf = ParticleFilter(lgssm_step, n)
+    pf = ParticleFilter(lgssm_step, n, mode="graph")  # (lse_terms[:, 0] is the running max M in this mode)
     bound = pf.weight_upper_bound(x0, gj.C["y"].set(ys))
     res = pf.run(gj.key(1), x0, gj.C["y"].set(ys))
     m = res.lse_terms[:, 0].cpu().numpy()
@@ -310,7 +310,7 @@ def test_analytic_reference_filter_matches_oracle(device, n):
             assert inc == pytest.approx(osmc.log_mean_exp(lws[t]), abs=2e-7)
             x_in = xs[t][anc[t]]
         np.testing.assert_array_equal(res.state[0].cpu().numpy(), x_in)
-    plain = ParticleFilter(lgssm_step, n).run(gj.key(17), torch.from_numpy(x0), gj.C["y"].set(torch.from_numpy(ys)), record=True)
+    plain = ParticleFilter(lgssm_step, n, mode="graph").run(gj.key(17), torch.from_numpy(x0), gj.C["y"].set(torch.from_numpy(ys)), record=True)
     assert torch.equal(plain.history["log_weights"][0], res.history["log_weights"][0])
     assert plain.log_increments[0].item() == pytest.approx(res.log_increments[0].item(), abs=2e-7)
 
