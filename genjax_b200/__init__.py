@@ -70,6 +70,7 @@ from .gen.scan import Scan, ScanTrace, accumulate, iterate, iterate_final, reduc
 from .gen.vmap_combinator import Vmap, VmapTrace, repeat, vmap_combinator
 from .inference.sp import Algorithm, Marginal, SampleDistribution, Target, marginal
 from . import inference
+from .core.render import render_html
 
 C = ChoiceMapBuilder
 S = SelectionBuilder

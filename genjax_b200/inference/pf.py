@@ -45,9 +45,63 @@ class PFResult:
     state: tuple  # final (resampled) per-particle state leaves
     log_marginal_likelihood: torch.Tensor  # float64 0-d, sum of the increments
     log_increments: torch.Tensor  # float64 [T]
-    lse_terms: torch.Tensor  # float64 [T, 3] = (M, S, increment)
+    lse_terms: torch.Tensor  # float64 [T, 3] = (M or E ln 2, S, increment)
     ancestors: torch.Tensor | None  # int32 [T, N] when record=True
     history: dict | None  # per-step pre-resampling state / log-weights when record=True
+    _ess: torch.Tensor | None = None
+
+    @property
+    def ess(self) -> torch.Tensor:
+        """Effective sample size (sum w)^2 / sum w^2 of every step's pre-resampling weights, float64 [T] (SURVEY section 5:
+        the per-step diagnostic of an SMC run).  Needs ``record=True`` (the weights of every step); one small kernel per step."""
+        if self._ess is None:
+            if self.history is None:
+                raise ValueError("per-step ESS needs the log-weights of every step: run with record=True")
+            lw = self.history["log_weights"]
+            T = lw.shape[0]
+            ess = torch.empty(T, dtype=torch.float64, device=lw.device)
+            ws = smc_ops.WeightWorkspace(lw.shape[1], lw.device)
+            for t in range(T):
+                ess[t] = smc_ops.weight_ess(lw[t].contiguous(), ws.lse_terms(lw[t].contiguous()))
+            self._ess = ess
+        return self._ess
+
+    def genealogy(self) -> torch.Tensor:
+        """int32 [T, N]: row t holds, for every FINAL particle, the index of its ancestor among step t's particles (the
+        ancestry history of the surviving lineages, composed from the recorded per-step ancestors)."""
+        if self.ancestors is None:
+            raise ValueError("the genealogy needs the ancestors of every step: run with record=True")
+        T, n = self.ancestors.shape
+        out = torch.empty((T, n), dtype=torch.int32, device=self.ancestors.device)
+        cur = self.ancestors[T - 1]
+        out[T - 1] = cur
+        for t in range(T - 2, -1, -1):
+            cur = smc_ops.gather_rows(self.ancestors[t].contiguous(), cur.contiguous())
+            out[t] = cur
+        return out
+
+    def state_dict(self) -> dict:
+        """Checkpoint of a filter run as CPU tensors: final state, log-marginal-likelihood terms and, for a
+        recorded run, the ancestry and effective-sample-size history.  ``ParticleFilter.run(key, state, obs[t0:])`` from
+        ``state`` resumes the filter; the estimate of the whole run is the sum of the parts."""
+        d = {"format": "genjax_b200.PFResult/1", "state": [s.detach().cpu() for s in self.state],
+             "log_increments": self.log_increments.detach().cpu(), "lse_terms": self.lse_terms.detach().cpu(),
+             "log_marginal_likelihood": float(self.log_marginal_likelihood.item())}
+        if self.ancestors is not None:
+            d["ancestors"] = self.ancestors.detach().cpu()
+            d["genealogy"] = self.genealogy().detach().cpu()
+            d["ess"] = self.ess.detach().cpu()
+        return d
+
+    def save(self, path) -> None:
+        torch.save(self.state_dict(), path)
+
+    @staticmethod
+    def load(path) -> dict:
+        d = torch.load(path, map_location="cpu", weights_only=True)
+        if d.get("format") != "genjax_b200.PFResult/1":
+            raise ValueError("not a genjax_b200 PFResult checkpoint")
+        return d
 
 
 class ParticleFilter:

@@ -24,6 +24,10 @@ NVCC_FLAGS = [
     "-O3",
     "-std=c++17",
     "-lineinfo",
+    # no implicit mul+add contraction: every fp32 operation of the generated model bodies and of the distribution library is
+    # then ONE IEEE operation, exactly what the NumPy oracle executes (explicit FMAs are written as __fmaf_rn and restated
+    # with oracle/rng.py fma32), so sampled values are bit-exact against the oracle instead of within a tolerance
+    "-fmad=false",
     "--shared",
     "-Xcompiler",
     "-fPIC",
@@ -51,7 +55,7 @@ def _header_digest() -> str:
     for p in sorted(list(CSRC.glob("*.cuh")) + [INCLUDE / "genjax_b200.h"]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
-    h.update(" ".join(_extra_flags()).encode())
+    h.update(" ".join(NVCC_FLAGS + _extra_flags()).encode())
     return h.hexdigest()
 
 

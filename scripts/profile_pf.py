@@ -22,9 +22,10 @@ ap.add_argument("--dim", type=int, default=1)
 ap.add_argument("--particles", type=int, default=1 << 20)
 ap.add_argument("--T", type=int, default=8)
 ap.add_argument("--graph", action="store_true")
-ap.add_argument("--mode", default="persistent")
+ap.add_argument("--mode", default="step")
 ap.add_argument("--reference-max", default="running")
 ap.add_argument("--single-pass", action="store_true")
+ap.add_argument("--obs-sd", type=float, default=None)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 n, d, T = a.particles, a.dim, a.T
@@ -34,7 +35,7 @@ x0 = torch.from_numpy(g.standard_normal((n, d) if d > 1 else n).astype(np.float3
 if d == 1:
     model, shared = lgssm_step, ()
 else:
-    model, shared = lgssm_step_vec, (torch.full((d,), LG_Q, device=dev), torch.full((d,), LG_R, device=dev))
+    model, shared = lgssm_step_vec, (torch.full((d,), LG_Q, device=dev), torch.full((d,), LG_R if a.obs_sd is None else a.obs_sd, device=dev))
 pf = ParticleFilter(model, n, mode=a.mode, reference_max=a.reference_max, single_pass=a.single_pass)
 res = pf.run(gj.key(1), x0, gj.C["y"].set(torch.from_numpy(ys).to(dev)), shared_args=shared, use_graph=a.graph)
 torch.cuda.synchronize()

@@ -176,3 +176,44 @@ def test_step_filter_matches_kalman_over_seeds(device):
     ests = [pf.run(gj.key(seed), x0, gj.C["y"].set(torch.from_numpy(ys))).log_marginal_likelihood.item() for seed in range(4)]
     assert np.mean(ests) == pytest.approx(exact, abs=0.05)
     assert np.std(ests) < 0.08
+
+
+def test_filter_result_diagnostics_checkpoint_and_html(device, tmp_path):
+    """per-step ESS, the ancestry (genealogy) of the surviving lineages, a checkpoint of the
+    run as CPU tensors, resuming a filter from it, and the jax-free render_html."""
+    gj, wl, ParticleFilter = _wl()
+    n, T = 6000, 6
+    ys = osmc.simulate_lgssm(1, T, 1, wl.LG_A, wl.LG_Q, wl.LG_C, wl.LG_R)[:, 0]
+    x0 = np.random.default_rng(7).standard_normal(n).astype(F32)
+    obs = gj.C["y"].set(torch.from_numpy(ys))
+    pf = ParticleFilter(wl.lgssm_step, n)
+    res = pf.run(gj.key(4), torch.from_numpy(x0), obs, record=True)
+    lws = res.history["log_weights"].cpu().numpy().astype(np.float64)
+    w = np.exp(lws - lws.max(1, keepdims=True))
+    np.testing.assert_allclose(res.ess.cpu().numpy(), w.sum(1) ** 2 / (w * w).sum(1), rtol=1e-5)
+    assert (res.ess > 1).all() and (res.ess <= n).all()
+    # genealogy: composing the recorded ancestors backwards
+    anc = res.ancestors.cpu().numpy()
+    cur = anc[T - 1].copy()
+    gen = res.genealogy().cpu().numpy()
+    assert np.array_equal(gen[T - 1], cur)
+    for t in range(T - 2, -1, -1):
+        cur = anc[t][cur]
+        assert np.array_equal(gen[t], cur)
+    assert len(np.unique(gen[0])) <= len(np.unique(gen[T - 1]))  # lineages coalesce backwards in time
+    with pytest.raises(ValueError):
+        pf.run(gj.key(4), torch.from_numpy(x0), obs).ess
+    # checkpoint round trip + resume: filtering y[:3] then y[3:] from the saved state is a filter over all six steps
+    path = tmp_path / "pf.pt"
+    first = pf.run(gj.key(4), torch.from_numpy(x0), gj.C["y"].set(torch.from_numpy(ys[:3])), record=True)
+    first.save(path)
+    ck = type(first).load(path)
+    assert ck["format"] == "genjax_b200.PFResult/1" and ck["ancestors"].shape == (3, n) and ck["ess"].shape == (3,)
+    assert torch.equal(ck["state"][0], first.state[0].cpu())
+    second = pf.run(gj.key(5), ck["state"][0], gj.C["y"].set(torch.from_numpy(ys[3:])))
+    total = ck["log_marginal_likelihood"] + second.log_marginal_likelihood.item()
+    exact = osmc.kalman_logz(ys, wl.LG_A, wl.LG_Q, wl.LG_C, wl.LG_R)
+    assert total == pytest.approx(exact, abs=0.5)
+    page = gj.render_html(res)
+    assert page.startswith("<div") and "PFResult" in page and "ESS per step" in page
+    assert "ChoiceMap" in gj.render_html(obs) and "float32" in gj.render_html({"x": torch.zeros(3)})
