@@ -577,55 +577,61 @@ __global__ void __launch_bounds__(kThreads) te_resample_kernel(const __grid_cons
   }
 }
 
-// The table of one step as a launch of its own: one CTA of 512 threads per device, resident beside the step kernel.
-// Polls the mailbox until every tile of every rank carries the step's tag (the cross-rank hand-off), then E, the
-// aligned tile masses, their inclusive prefix, the offspring count at every tile boundary, and the parent-tile range of
-// every local window.  Same arithmetic as te_finish_step's last-CTA path (gjb_step.cuh), four times the threads.
-constexpr int kTabThreads = 512;  // 16 K registers: fits beside three resident step CTAs
-__global__ void __launch_bounds__(kTabThreads) te_table_kernel(const __grid_constant__ gjb_te_table_args A) {
+// The table of one step as a launch of its own: ONE small CTA per device (256 threads, <= 32 registers, 16 KB of shared
+// memory) so that it becomes resident BESIDE the step kernel's CTAs as soon as they have all started -- an SM that hosts
+// three step CTAs has room for it -- and the next step kernel, launched behind it with programmatic stream
+// serialization, can start early too.  It polls this device's mailbox until every tile of every rank carries the step's
+// tag (the cross-rank hand-off), then E, the aligned tile masses, their inclusive prefix, the offspring count at every
+// tile boundary, and the parent-tile range of every local window.  Same arithmetic as te_finish_step's last-CTA path.
+constexpr int kTabThreads = 256;
+__global__ void __launch_bounds__(kTabThreads, 8) te_table_kernel(const __grid_constant__ gjb_te_table_args A) {
   __shared__ int32_t cnt[kTeMaxTiles];
-  __shared__ uint64_t red[kTabThreads / 32];
-  __shared__ int32_t ired[kTabThreads / 32];
+  __shared__ __align__(16) uint64_t red[kTabThreads / 32];
+  __shared__ __align__(16) int32_t ired[kTabThreads / 32];
   pdl_launch_dependents();
   const gjb_step_link* L = A.link;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_tiles = L->world * L->tiles_per_rank;
+  const int per = (n_tiles + kTabThreads - 1) / kTabThreads;
+  const int t0 = tid * per;
   const uint32_t tag = te_tag(L, A.step);
   const uint64_t* box = te_mail_slot(L->mailbox[L->rank], A.step, 0);
-  constexpr int kPer = kTeMaxTiles / kTabThreads;  // 8 records per thread, blocked
-  uint64_t m[kPer];
-  int e[kPer];
+  gjb_step_table* tab = A.table_out;
+  // pass 1: wait for every record, E = max exponent over tiles with mass
   int emax = GJB_TE_E_NONE;
-#pragma unroll
-  for (int k = 0; k < kPer; ++k) {
-    const int t = tid * kPer + k;
-    m[k] = 0; e[k] = GJB_TE_E_NONE;
+  for (int k = 0; k < per; ++k) {
+    const int t = t0 + k;
     if (t < n_tiles) {
       const uint64_t* r = box + (int64_t)t * GJB_TE_LL_WORDS;
       uint64_t w0, w1, w2;
       for (;;) {
         w0 = te_ld_volatile(r); w1 = te_ld_volatile(r + 1); w2 = te_ld_volatile(r + 2);
         if ((uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag && (uint32_t)(w2 >> 32) == tag) break;
-        __nanosleep(250);
+        __nanosleep(100);
       }
-      m[k] = (w0 & 0xffffffffull) | (w1 << 32);
-      e[k] = (int)(uint32_t)w2;
-      if (m[k]) emax = max(emax, e[k]);
+      if ((w0 & 0xffffffffull) | (w1 << 32)) emax = max(emax, (int)(uint32_t)w2);
     }
   }
   emax = __reduce_max_sync(0xffffffffu, emax);
   if (lane == 0) ired[warp] = emax;
   __syncthreads();
-  int E = lane < kTabThreads / 32 ? ired[lane] : GJB_TE_E_NONE;
-  E = __reduce_max_sync(0xffffffffu, E);
-  uint64_t pre[kPer];
-  uint8_t sft[kPer];
-  uint64_t run = 0;
+  int E = ired[0];
 #pragma unroll
-  for (int k = 0; k < kPer; ++k) {
-    sft[k] = (uint8_t)(m[k] ? min(E - e[k], 63) : 63);
-    run += m[k] >> sft[k];
-    pre[k] = run;
+  for (int w = 1; w < kTabThreads / 32; ++w) E = max(E, ired[w]);
+  // pass 2: aligned masses (records re-read from L2: they are complete now), thread-local inclusive prefix -> table
+  uint64_t run = 0;
+  for (int k = 0; k < per; ++k) {
+    const int t = t0 + k;
+    if (t < n_tiles) {
+      const uint64_t* r = box + (int64_t)t * GJB_TE_LL_WORDS;
+      const ulonglong2 w01 = __ldcg(reinterpret_cast<const ulonglong2*>(r));
+      const uint64_t m = (w01.x & 0xffffffffull) | (w01.y << 32);
+      const int e = (int)(uint32_t)__ldcg(reinterpret_cast<const unsigned long long*>(r + 2));
+      const int sft = m ? min(E - e, 63) : 63;
+      run += m >> sft;
+      tab->pre[t] = run;
+      tab->shf[t] = (uint8_t)sft;
+    }
   }
   uint64_t inc = run;
 #pragma unroll
@@ -635,26 +641,21 @@ __global__ void __launch_bounds__(kTabThreads) te_table_kernel(const __grid_cons
   }
   if (lane == 31) red[warp] = inc;
   __syncthreads();
-  uint64_t wv = lane < kTabThreads / 32 ? red[lane] : 0ull, winc = wv;  // every warp scans the warp totals
+  uint64_t excl = inc - run, S = 0;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint64_t v = __shfl_up_sync(0xffffffffu, winc, o);
-    if (lane >= o) winc += v;
+  for (int w = 0; w < kTabThreads / 32; ++w) {
+    const uint64_t v = red[w];
+    if (w < warp) excl += v;
+    S += v;
   }
-  const uint64_t S = __shfl_sync(0xffffffffu, winc, 31);
-  const uint64_t wexc = __shfl_sync(0xffffffffu, winc - wv, warp);
-  const uint64_t excl = wexc + inc - run;
   const double u0 = resample_u0(__ldg(A.reskey), __ldg(A.reskey + 1), (uint64_t)__ldg(A.reskey + 2) | ((uint64_t)__ldg(A.reskey + 3) << 32));
   const double scale = S ? __ddiv_rn((double)A.n_total, (double)S) : 0.0;
   const int32_t nt = (int32_t)A.n_total;
-  gjb_step_table* tab = A.table_out;
-#pragma unroll
-  for (int k = 0; k < kPer; ++k) {
-    const int t = tid * kPer + k;
+  for (int k = 0; k < per; ++k) {
+    const int t = t0 + k;
     if (t < n_tiles) {
-      const uint64_t cur = pre[k] + excl;
+      const uint64_t cur = tab->pre[t] + excl;  // (this thread's own store of pass 2)
       tab->pre[t] = cur;
-      tab->shf[t] = sft[k];
       cnt[t] = S ? offspring_cnt(cur, S, scale, u0, nt) : 0;
     }
   }
@@ -683,7 +684,7 @@ __global__ void __launch_bounds__(kTabThreads) te_table_kernel(const __grid_cons
     tab->win[w][1] = lo < n_tiles ? lo : n_tiles - 1;
   }
   __syncthreads();
-  if (tid == 0) {  // the tag goes last: the next step kernel's CTAs are spinning on it
+  if (tid == 0) {  // the tag goes last (only the opt-in flag hand-off reads it)
     __threadfence();
     te_st_volatile(reinterpret_cast<uint64_t*>(&tab->tag), (uint64_t)tag);
   }

@@ -427,7 +427,7 @@ __device__ __forceinline__ void te_finish_step(const gjb_step_link* __restrict__
     for (;;) {
       w0 = te_ld_volatile(r); w1 = te_ld_volatile(r + 1); w2 = te_ld_volatile(r + 2);
       if ((uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag && (uint32_t)(w2 >> 32) == tag) break;
-      __nanosleep(250);
+      __nanosleep(40);
     }
     m = (w0 & 0xffffffffull) | (w1 << 32);
     e = (int)(uint32_t)w2;

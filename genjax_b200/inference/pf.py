@@ -290,6 +290,10 @@ class _Plan:
             # 1 M particles, 19-22 us against 26 us per step -- the serial tail of the last CTA costs more than the
             # redundant prefix work it saves)
             self.te_table = os.environ.get("GJB_STEP_TABLE", "0") == "1"
+            # ... and who builds the table: the step kernel's last CTA (default; B200: 22.5 us per step on one device, 28 us
+            # on two) or gjb_te_table, a small kernel resident beside the step kernel (24.5 / 32 us: its launch and the
+            # dependent launch behind it cost more than the last CTA's serial tail)
+            self.te_table_kernel = os.environ.get("GJB_STEP_TABLE_KERNEL", "0") == "1"
             self.te_recs = torch.empty((2, tiles, 2), dtype=torch.int64, device=device)
             self.te_cdf = torch.empty((2, tiles * cabi.TE_TILE), dtype=torch.int64, device=device)
             # what the last CTA of each launch leaves for the next (one table per step parity), the tile-record
@@ -425,7 +429,10 @@ class _Plan:
                     A.ancestors_out = self.anc[t - 1].data_ptr()
             A.cdf_out = self.te_cdf[t & 1].data_ptr()
             if self.te_table:
-                A.link = self.te_link.data_ptr()  # (table_out stays NULL: the CTAs mail their records, gjb_te_table does the rest)
+                A.link = self.te_link.data_ptr()
+                if not self.te_table_kernel:  # the step kernel's last CTA builds the table
+                    A.table_out = self.te_tables[t & 1].data_ptr()
+                    A.lse_out = self.lse[t].data_ptr()
                 B = cabi.TeTableArgs()
                 B.link, B.step, B.flags = self.te_link.data_ptr(), t, (cabi.STEP_PDL if pdl else 0)
                 B.slot_offset, B.n_local, B.n_total = 0, n, n
@@ -554,7 +561,7 @@ class _Plan:
         if self.stepmode:  # ONE launch per step, the closing resampling of the last step, the final gather(s)
             for t in range(self.T):
                 cabi.check(lib.gjb_model_pf_step(C.byref(self.sargs[t]), stream), "gjb_model_pf_step")
-                if self.te_table:
+                if self.te_table and self.te_table_kernel:
                     cabi.check(core.gjb_te_table(C.byref(self.targs[t]), stream), "gjb_te_table")
             cabi.check(core.gjb_te_resample(C.byref(self.te_close), stream), "gjb_te_resample")
             last = (self.T - 1) if self.record else ((self.T - 1) & 1)

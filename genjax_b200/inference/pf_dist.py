@@ -447,6 +447,7 @@ class _DistStepPlan:
         self.obs_sites = {ir.site_index(a): a for a in obs}
         self.graph = None
         pdl = os.environ.get("GJB_PDL", "1") != "0"
+        self.table_kernel = os.environ.get("GJB_STEP_TABLE_KERNEL", "0") == "1"
         dist.barrier(pf.group)  # every rank has zeroed its arena before anyone mails into it
         # ---- per-step arguments
         self.sargs = []
@@ -483,7 +484,10 @@ class _DistStepPlan:
                 if record:
                     A.ancestors_out = self.anc[t - 1].data_ptr()
             A.cdf_out = self.cdf[t & 1].data_ptr()
-            A.link = self.link.data_ptr()  # (table_out stays NULL: the CTAs mail their records, gjb_te_table does the rest)
+            A.link = self.link.data_ptr()
+            if not self.table_kernel:  # default: the step kernel's last CTA builds the table (measured faster, see pf.py)
+                A.table_out = self.tables[t & 1].data_ptr()
+                A.lse_out = self.lse[t].data_ptr()
             self.sargs.append(A)
             B = cabi.TeTableArgs()
             B.link, B.step, B.flags = self.link.data_ptr(), t, (cabi.STEP_PDL if pdl else 0)
@@ -517,7 +521,8 @@ class _DistStepPlan:
         lib = self.cm.lib
         for t in range(self.T):
             cabi.check(lib.gjb_model_pf_step(C.byref(self.sargs[t]), stream), "gjb_model_pf_step")
-            cabi.check(core.gjb_te_table(C.byref(self.targs[t]), stream), "gjb_te_table")
+            if self.table_kernel:
+                cabi.check(core.gjb_te_table(C.byref(self.targs[t]), stream), "gjb_te_table")
         cabi.check(core.gjb_te_resample(C.byref(self.close), stream), "gjb_te_resample")
         for k in range(len(self.bufs)):
             cabi.check(core.gjb_gather_rows_peers(C.byref(self.final_peers[k]), self.anc[self.last].data_ptr(),
@@ -528,7 +533,7 @@ class _DistStepPlan:
         cabi.check(core.gjb_epoch_bump(self.epoch.data_ptr(), stream), "gjb_epoch_bump")
 
     def launches_per_run(self) -> int:
-        return 2 * self.T + 3 + len(self.bufs)  # step kernel + table kernel per step, closing resample, gathers, barrier, epoch
+        return (2 if self.table_kernel else 1) * self.T + 3 + len(self.bufs)  # step kernel (+ table kernel) per step, closing resample, gathers, barrier, epoch
 
     def execute(self, key, state0, shared, obs, use_graph):
         tab = torch.from_numpy(pf_key_table(key, self.T).view(np.int32))

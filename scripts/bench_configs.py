@@ -98,7 +98,7 @@ def hmm():
     z0 = torch.from_numpy(z0_all[rank * n:(rank + 1) * n]).to(dev)
     shared = (torch.from_numpy(trans).to(dev), torch.from_numpy(obs).to(dev))
     obs_chm = gj.C["y"].set(torch.from_numpy(ys).to(dev))
-    pf = DistributedParticleFilter(hmm_step, n) if world > 1 else ParticleFilter(hmm_step, n, mode="graph")
+    pf = DistributedParticleFilter(hmm_step, n) if world > 1 else ParticleFilter(hmm_step, n)  # both: the single-launch step kernel
     ms, res = _time(lambda: pf.run(gj.key(11), z0, obs_chm, shared_args=shared), reps=2)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
