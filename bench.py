@@ -67,7 +67,7 @@ def parse():
     ap.add_argument("--single-pass", action="store_true",
                     help="with --reference-max analytic: ONE launch per step (output-slot resampling of the previous step fused "
                          "into the model kernel, model_kernel_static_pull; DESIGN.md section 10 -- not yet measured on a device)")
-    ap.add_argument("--mode", default="step", choices=["persistent", "graph", "step"],
+    ap.add_argument("--mode", default="step", choices=["persistent", "graph", "step", "steps"],
                     help="step: ONE launch per filter step (pf_step_kernel: output-slot resampling of the previous step + gather + "
                          "propose + logpdf + tile-exponent masses), captured in a CUDA graph; graph: round 1's 2 launches per step; "
                          "persistent: one cooperative launch per filter")
@@ -593,6 +593,22 @@ def run_ours(args):
             "achieved": st_gbs, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": st_gbs / peak, "traffic": None,
             "kernel_us": st_ms * 1e3, "algorithmic_bytes_per_launch": st_bytes, "algorithmic_bytes_per_particle_step": 8 * d + 24,
             "note": "per GPU; algorithmic bytes = SURVEY 8d's whole-step figure (8d + 24 per particle-step)",
+        }
+    elif getattr(plan, "stepsmode", False):
+        # ALL steps are one cooperative launch: its duration / T is the step
+        ss_ms = time_launches(lambda: plan.cm.lib.gjb_model_pf_steps(C.byref(plan.steps_args), stream), 10, 2) / T
+        st_bytes = (8 * d + 24) * n
+        st_gbs = st_bytes / (ss_ms * 1e-3) / 1e9
+        kernels["pf_steps_kernel"] = {
+            "kernel_us": ss_ms * 1e3, "algorithmic_bytes_per_launch": st_bytes * T, "achieved": st_gbs, "frac": st_gbs / peak,
+            "what": "all T filter steps in ONE cooperative launch (one grid barrier per step): per step output-slot systematic "
+                    "resampling of the previous step + ancestor gather + propose + logpdf + within-tile CDF / tile record "
+                    "(gjb_model_pf_steps); kernel_us = launch duration / T"}
+        roofline = {
+            "bound": "hbm", "kernel": "pf_steps_kernel: " + kernels["pf_steps_kernel"]["what"],
+            "achieved": st_gbs, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": st_gbs / peak, "traffic": None,
+            "kernel_us": ss_ms * 1e3, "algorithmic_bytes_per_launch": st_bytes * T, "algorithmic_bytes_per_particle_step": 8 * d + 24,
+            "note": "algorithmic bytes = SURVEY 8d's whole-step figure (8d + 24 per particle-step) x T steps per launch",
         }
     elif getattr(plan, "stepmode", False):
         # the step IS one kernel: launch t = 1 (reads step 0's CDF / tile records, writes its own) is what every later

@@ -597,19 +597,15 @@ __global__ void __launch_bounds__(kTabThreads, 8) te_table_kernel(const __grid_c
   const uint32_t tag = te_tag(L, A.step);
   const uint64_t* box = te_mail_slot(L->mailbox[L->rank], A.step, 0);
   gjb_step_table* tab = A.table_out;
-  // pass 1: wait for every record, E = max exponent over tiles with mass
+  // pass 1: wait for every record (batched tag polls), E = max exponent over tiles with mass
+  te_wait_records(box, t0, per, n_tiles, tag);
   int emax = GJB_TE_E_NONE;
   for (int k = 0; k < per; ++k) {
     const int t = t0 + k;
     if (t < n_tiles) {
       const uint64_t* r = box + (int64_t)t * GJB_TE_LL_WORDS;
-      uint64_t w0, w1, w2;
-      for (;;) {
-        w0 = te_ld_volatile(r); w1 = te_ld_volatile(r + 1); w2 = te_ld_volatile(r + 2);
-        if ((uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag && (uint32_t)(w2 >> 32) == tag) break;
-        __nanosleep(100);
-      }
-      if ((w0 & 0xffffffffull) | (w1 << 32)) emax = max(emax, (int)(uint32_t)w2);
+      const ulonglong2 w01 = __ldcg(reinterpret_cast<const ulonglong2*>(r));
+      if ((w01.x & 0xffffffffull) | (w01.y << 32)) emax = max(emax, (int)(uint32_t)__ldcg(reinterpret_cast<const unsigned long long*>(r + 2)));
     }
   }
   emax = __reduce_max_sync(0xffffffffu, emax);
@@ -730,6 +726,21 @@ __global__ void __launch_bounds__(1024) ess_kernel(const float* __restrict__ log
     double ta = 0.0, tb = 0.0;
     for (int w = 0; w < 32; ++w) { ta += s1[w]; tb += s2[w]; }
     out[0] = tb > 0.0 ? ta * ta / tb : 0.0;
+  }
+}
+
+// Per-step key table of a filter run (core/key.py pf_key_table, oracle/smc.py pf_step_keys), derived on the device from
+// the run key's two (collapsed) words: row t = {prop_k0, prop_k1, res_k0, res_k1, res_idx_lo = 1, res_idx_hi = 0, mn_k0, mn_k1}.
+__global__ void pf_key_table_kernel(uint32_t k0, uint32_t k1, int T, uint32_t* __restrict__ out) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+    const uint2 f = threefry2x32_20(k0, k1, 0u, (uint32_t)t);             // fold_in(key, t)
+    const uint2 s = threefry2x32_20(f.x, f.y, 0x73706C74u, 0u);           // split(.): words of lanes 0 (propose) and 1 (resample)
+    const uint2 p = threefry2x32_20(s.x, s.y, 0x73706C74u, 0u);           // split(k_prop, N): the proposal lanes' words
+    const uint2 c = threefry2x32_20(s.x, s.y, 0x5851F42Du, 1u);           // k_res collapsed (lane 1 folded into the words)
+    const uint2 m = threefry2x32_20(c.x, c.y, 0x73706C74u, 0u);           // split(k_res, N): the multinomial lanes' words
+    uint4* o = reinterpret_cast<uint4*>(out + 8 * (int64_t)t);
+    o[0] = make_uint4(p.x, p.y, s.x, s.y);
+    o[1] = make_uint4(1u, 0u, m.x, m.y);
   }
 }
 
@@ -974,6 +985,12 @@ int gjb_select_rows(const int32_t* mask, const void* a, const void* b, void* out
 int gjb_weight_ess(const float* logw, int64_t n, const double* lse3, double* out, void* stream) {
   if (!logw || !lse3 || !out || n <= 0) return GJB_E_ARG;
   ess_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logw, n, lse3, out);
+  return launch_status();
+}
+
+int gjb_pf_key_table(uint32_t key0, uint32_t key1, int32_t T, uint32_t* out, void* stream) {
+  if (!out || T <= 0 || (reinterpret_cast<uintptr_t>(out) & 15)) return GJB_E_ARG;
+  pf_key_table_kernel<<<(T + 127) / 128 < 64 ? (T + 127) / 128 : 64, 128, 0, (cudaStream_t)stream>>>(key0, key1, T, out);
   return launch_status();
 }
 

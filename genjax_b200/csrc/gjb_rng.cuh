@@ -26,6 +26,25 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
   return c;
 }
 
+// threefry2x32-20 (Salmon et al. 2011): the HOST key tree (core/key.py split / fold_in) restated for the device, used
+// only to derive a filter run's per-step key table on the device (gjb_pf_key_table) instead of shipping it from the host.
+__device__ __forceinline__ uint2 threefry2x32_20(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1) {
+  const uint32_t ks[3] = {k0, k1, 0x1BD11BDAu ^ k0 ^ k1};
+  const int rot[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+  uint32_t x0 = c0 + ks[0], x1 = c1 + ks[1];
+#pragma unroll
+  for (int g = 0; g < 5; ++g) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      x0 += x1;
+      x1 = ((x1 << rot[g & 1][r]) | (x1 >> (32 - rot[g & 1][r]))) ^ x0;
+    }
+    x0 += ks[(g + 1) % 3];
+    x1 += ks[(g + 2) % 3] + (uint32_t)(g + 1);
+  }
+  return make_uint2(x0, x1);
+}
+
 struct Lane {
   uint32_t k0, k1, lo, hi;  // batch key + global particle index
   __device__ __forceinline__ uint4 words(uint32_t site, uint32_t chunk) const {

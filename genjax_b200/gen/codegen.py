@@ -918,6 +918,102 @@ class _Generator:
         out.append("}")
         return out
 
+    def steps_kernel(self) -> list[str]:
+        """ALL T filter steps in ONE cooperative launch (include/genjax_b200.h ``gjb_model_pf_steps``; one device, every
+        window's CTA co-resident): the body of ``pf_step_kernel`` (table-free form) in a loop over t, with ONE grid-wide
+        barrier per step where the per-step form has a kernel boundary.  The random numbers of step t + 1 are drawn BEFORE
+        that barrier, so they overlap the wait for the slowest CTA of step t."""
+        ir = self.ir
+        out = ["__global__ void __launch_bounds__(kThreads, 4) pf_steps_kernel(const __grid_constant__ gjb_steps_args Q) {"]
+        out.append("  __shared__ gjb::TeSmem sm;")
+        out.extend(self.stage_lines("Q.shared"))
+        out.append("  Uni U; make_uni(U, Q.scalars);")
+        out.append("  uint32_t fl[NS];")
+        out.append(f"  for (int j = 0; j < {self.ns}; ++j) fl[j] = kPfFl[j];")
+        out.append("  const int tid = threadIdx.x;")
+        out.append("  const int64_t n = Q.n;")
+        out.append("  const int64_t w_loc = (int64_t)blockIdx.x * gjb::kTeTile;")
+        out.append("  const int w_n = (n - w_loc) < gjb::kTeTile ? (int)(n - w_loc) : gjb::kTeTile;")
+        out.append("  const int n_tiles = (int)gridDim.x;")
+        out.append("  const int64_t cdf_stride = (int64_t)n_tiles * gjb::kTeTile;")
+        wbuf = "reinterpret_cast<float*>(sm.pre)" if self.group else "reinterpret_cast<float*>(sm.heads)"
+        out.append(f"  float* const wbuf = {wbuf};")
+        if not self.group:
+            out.append("  const int64_t q0 = (w_loc >> 2) + tid * 2;")
+            out.append("  const int64_t qw = (w_loc + w_n + 3) >> 2;")
+        out.append("  for (int t = 0; t < Q.T; ++t) {")
+        out.append("    const int slot = Q.record ? t : (t & 1);")
+        out.append("    const int pslot = Q.record ? t - 1 : ((t - 1) & 1);")
+        out.append("    const uint32_t* kt = Q.keys + 8 * t;")
+        out.append("    const uint32_t key0 = __ldg(kt), key1 = __ldg(kt + 1);")
+        if not self.group:
+            out.append("    QRng R0, R1;  // this step's random numbers: independent of the previous step, drawn before its barrier")
+            out.append("    quad_rng<true>(fl, key0, key1, (Q.idx_offset >> 2) + (uint64_t)q0, R0);")
+            out.append("    quad_rng<true>(fl, key0, key1, (Q.idx_offset >> 2) + (uint64_t)q0 + 1, R1);")
+        out.append("    if (t > 0) cooperative_groups::this_grid().sync();  // step t - 1: every CDF row, tile record and state row is written")
+        out.append("    Io io;")
+        out.append("    for (int i = 0; i < NA; ++i) io.args[i] = Q.shared[i];")
+        out.append("    for (int j = 0; j < NS; ++j) { io.site_in[j] = nullptr; io.site_out[j] = nullptr; }")
+        out.append("    for (int k = 0; k < NR; ++k) io.ret_out[k] = nullptr;")
+        out.append("    io.gather = nullptr; io.score_in = nullptr; io.weight_in = nullptr; io.score_out = nullptr; io.peers = nullptr;")
+        out.append("    io.m_ref = nullptr; io.tile_mass = nullptr;")
+        for i in range(len(ir.ret_leaves)):
+            out.append(f"    io.args[{i}] = t == 0 ? Q.state0[{i}] : (const void*)((const char*)Q.state_buf[{i}] + (int64_t)pslot * Q.state_stride[{i}]);")
+        for sdef in ir.sites:
+            j = sdef.index
+            out.append(f"    if (Q.obs[{j}]) io.site_in[{j}] = (const char*)Q.obs[{j}] + (int64_t)t * Q.obs_stride[{j}];")
+        for k, r in enumerate(ir.ret_leaves):
+            dst = f"(void*)((char*)Q.state_buf[{k}] + (int64_t)slot * Q.state_stride[{k}])"
+            if isinstance(r, Expr) and r.op == "site" and r.attr not in (self.pf_obs or ()):
+                out.append(f"    io.site_out[{r.attr}] = {dst};")
+            else:
+                out.append(f"    io.ret_out[{k}] = {dst};")
+        out.append("    io.weight_out = Q.record ? Q.logw + (int64_t)t * n : (t == Q.T - 1 ? Q.logw : nullptr);")
+        out.append("    io.te_w = wbuf - w_loc;")
+        out.append("    if (t > 0) {  // ancestors of MY slots: output-slot systematic resampling of step t - 1")
+        out.append("      const uint32_t* kp = Q.keys + 8 * (t - 1) + 2;")
+        out.append("      const double u0 = gjb::resample_u0(__ldg(kp), __ldg(kp + 1), (uint64_t)__ldg(kp + 2) | ((uint64_t)__ldg(kp + 3) << 32));")
+        out.append("      const gjb_tile_rec* recs = Q.recs + (int64_t)((t - 1) & 1) * n_tiles;")
+        out.append("      const uint64_t* cdf = Q.cdf + (int64_t)((t - 1) & 1) * cdf_stride;")
+        out.append("      int32_t anc[gjb::kTeItems];")
+        out.append("      int E;")
+        out.append("      uint64_t S;")
+        out.append("      if (n_tiles <= 2 * kThreads) {")
+        out.append("        const gjb::TeRecs2 recs2 = gjb::te_load_recs2<true>(recs, n_tiles);")
+        out.append("        S = gjb::te_pull<true, true>(recs, n_tiles, cdf, nullptr, n, u0, w_loc, w_n, sm, anc, &E, &recs2);")
+        out.append("      } else {")
+        out.append("        S = gjb::te_pull<true, false>(recs, n_tiles, cdf, nullptr, n, u0, w_loc, w_n, sm, anc, &E);")
+        out.append("      }")
+        out.append("      if (blockIdx.x == 0 && tid == 0) gjb::te_write_lse(Q.lse + 3 * (t - 1), E, S, n);")
+        out.append("      const int4 a0 = make_int4(anc[0], anc[1], anc[2], anc[3]), a1 = make_int4(anc[4], anc[5], anc[6], anc[7]);")
+        out.append("      *reinterpret_cast<int4*>(sm.heads + tid * gjb::kTeItems) = a0;")
+        out.append("      *reinterpret_cast<int4*>(sm.heads + tid * gjb::kTeItems + 4) = a1;")
+        out.append("      if (Q.record) {")
+        out.append("        int32_t* o = Q.ancestors + (int64_t)(t - 1) * n + w_loc + tid * gjb::kTeItems;")
+        out.append("        if (tid * gjb::kTeItems + gjb::kTeItems <= w_n && (reinterpret_cast<uintptr_t>(o) & 15) == 0) { reinterpret_cast<int4*>(o)[0] = a0; reinterpret_cast<int4*>(o)[1] = a1; }")
+        out.append("        else for (int k = 0; k < gjb::kTeItems; ++k) if (tid * gjb::kTeItems + k < w_n) o[k] = anc[k];")
+        out.append("      }")
+        out.append("      io.gather = sm.heads - w_loc;")
+        out.append("    }")
+        out.append("    float run_max = -INFINITY;")
+        if self.group:
+            out.append("    __syncthreads();")
+            out.append("    run_groups<true, true, true>(io, U, fl, n, Q.idx_offset, key0, key1, w_loc, w_loc + w_n, kPPB, run_max);")
+            out.append("    __syncthreads();")
+        else:
+            out.append("    if (q0 < qw) run_quads<true, true, false, true, true>(io, U, fl, n, Q.idx_offset, key0, key1, q0, q0 + 1, 1, run_max, &R0);")
+            out.append("    if (q0 + 1 < qw) run_quads<true, true, false, true, true>(io, U, fl, n, Q.idx_offset, key0, key1, q0 + 1, q0 + 2, 1, run_max, &R1);")
+        out.append("    float lw[gjb::kTeItems];")
+        out.append("#pragma unroll")
+        out.append("    for (int k = 0; k < gjb::kTeItems; ++k) lw[k] = (tid * gjb::kTeItems + k < w_n) ? wbuf[tid * gjb::kTeItems + k] : -INFINITY;")
+        if self.group:
+            out.append("    __syncthreads();")
+        out.append("    gjb::te_publish(lw, Q.cdf + (int64_t)(t & 1) * cdf_stride + w_loc, Q.recs + (int64_t)(t & 1) * n_tiles + blockIdx.x, sm);")
+        out.append("    __syncthreads();  // the shared scratch is reused by the next step")
+        out.append("  }")
+        out.append("}")
+        return out
+
     def pf_kernel(self) -> list[str]:
         """The persistent particle-filter kernel (None when the model's return
         leaves cannot feed back as its leading particle arguments)."""
@@ -1040,6 +1136,7 @@ class _Generator:
         self.has_step = pf and self.pf_obs is not None and staged <= 640
         if self.has_step:
             out.extend(self.step_kernel())
+            out.extend(self.steps_kernel())
         chain_ext = None
         if self.chain is not None:
             from . import codegen_chain
@@ -1130,6 +1227,27 @@ int gjb_model_pf_run(const gjb_pf_args* a, void* stream) { (void)a; (void)stream
             static_dispatch = "if (a->tile_mass || a->m_ref) return GJB_E_MODE;  // needs the filter-flag instantiation"
         if getattr(self, "has_step", False):
             step_code = """
+static int pf_steps_capacity() {  // CTAs of pf_steps_kernel that are co-resident on this device
+  return gjb::resident_blocks((const void*)pf_steps_kernel, kThreads, 8);
+}
+int gjb_model_pf_steps_fits(int64_t n) {
+  if (n <= 0) return 0;
+  return (n + gjb::kTeTile - 1) / gjb::kTeTile <= pf_steps_capacity() ? 1 : 0;
+}
+int gjb_model_pf_steps(const gjb_steps_args* a, void* stream) {
+  if (!a || a->n <= 0 || a->T <= 0 || !a->keys || !a->cdf || !a->recs || !a->lse) return GJB_E_ARG;
+  if ((a->idx_offset & 3) != 0) return GJB_E_ARG;
+  if (a->n > (1LL << 26) || (a->n + gjb::kTeTile - 1) / gjb::kTeTile > gjb::kTeMaxTiles) return GJB_E_RANGE;
+  if ((reinterpret_cast<uintptr_t>(a->cdf) & 15) || (reinterpret_cast<uintptr_t>(a->recs) & 15)) return GJB_E_ARG;
+  if (a->record ? (!a->logw || !a->ancestors) : !a->logw) return GJB_E_ARG;
+  for (int k = 0; k < NR; ++k) if (!a->state0[k] || !a->state_buf[k]) return GJB_E_ARG;
+  const int64_t tiles = (a->n + gjb::kTeTile - 1) / gjb::kTeTile;
+  if (tiles > pf_steps_capacity()) return GJB_E_RANGE;  // every window's CTA must be resident (one grid barrier per step)
+  void* params[1] = {(void*)a};
+  const cudaError_t e = cudaLaunchCooperativeKernel((const void*)pf_steps_kernel, dim3((unsigned)tiles), dim3(kThreads), params, 0, (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaGetLastError();
+}
 #ifdef GJB_TRACE
 int gjb_model_trace_read(unsigned long long* dst, int n) {  // scratch/trace_step.py
   cudaDeviceSynchronize();
@@ -1169,6 +1287,8 @@ int gjb_model_pf_step(const gjb_step_args* a, void* stream) {
         else:
             step_code = """
 int gjb_model_pf_step(const gjb_step_args* a, void* stream) { (void)a; (void)stream; return GJB_E_MODE; }
+int gjb_model_pf_steps_fits(int64_t n) { (void)n; return 0; }
+int gjb_model_pf_steps(const gjb_steps_args* a, void* stream) { (void)a; (void)stream; return GJB_E_MODE; }
 """
         chain_code = chain_ext if chain_ext is not None else """
 int gjb_model_mh_chain(const gjb_chain_args* a, void* stream) { (void)a; (void)stream; return GJB_E_MODE; }

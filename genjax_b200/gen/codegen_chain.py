@@ -275,7 +275,9 @@ CHAIN_STAGE
       float fwd = 0.0f;
 #pragma unroll
       for (int k = 0; k < kD; ++k) { prop[k] = loc[k] + scale[k] * z[k]; fwd += gjb::Normal::logpdf(prop[k], loc[k], scale[k]); }
-      prop_fn(UPR, X, prop, A.step_size, loc, scale);
+      // backward proposal arguments: at the PROPOSED state (Metropolis-Hastings), or -- compat -- at the OLD state, which is
+      // what rejuvenate.py:84-86 does (`argument_mapping(bwd_chm)` with bwd_chm the discarded, i.e. old, choices)
+      if (!A.compat_stale_grad) prop_fn(UPR, X, prop, A.step_size, loc, scale);
       float bwd = 0.0f;
 #pragma unroll
       for (int k = 0; k < kD; ++k) bwd += gjb::Normal::logpdf(q[k], loc[k], scale[k]);
@@ -317,7 +319,7 @@ CHAIN_STAGE
       chain_normals(lane, t1, p);                           // sample_momenta, hmc.py:120-130
       const float k0 = std_normal_logpdf_sum(p, 1.0f);      // assess_momenta(p_0)
 #pragma unroll
-      for (int k = 0; k < kD; ++k) { q[k] = q0[k]; gc[k] = g0[k]; }
+      for (int k = 0; k < kD; ++k) { q[k] = q0[k]; gc[k] = g0[k]; g[k] = g0[k]; }  // (g = g0: n_leapfrog == 0 must not carry an uninitialised gradient)
       float lp = lp0;
       for (int l = 0; l < A.n_leapfrog; ++l) {              // kernel, hmc.py:170-186
 #pragma unroll
@@ -356,10 +358,14 @@ _CHECK = r"""
 
 _EXTERN_MH = r"""
 int gjb_model_mh_chain(const gjb_chain_args* a, void* stream) {""" + _CHECK + r"""
-  int64_t blocks = (a->n + 127) / 128;
-  const int64_t cap = gjb::resident_blocks((const void*)mh_chain_kernel, 128, 16);
+  // chains keep their state in registers for the whole launch: spread them over ALL SMs before filling one -- 8192 chains
+  // (one GPU's share of configs[4]) in 128-thread blocks would occupy 64 of the 148 SMs
+  int tpb = 128;
+  while (tpb > 32 && (a->n + tpb - 1) / tpb < 2 * 148) tpb >>= 1;
+  int64_t blocks = (a->n + tpb - 1) / tpb;
+  const int64_t cap = gjb::resident_blocks((const void*)mh_chain_kernel, tpb, 16);
   if (blocks > cap) blocks = cap;
-  mh_chain_kernel<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(*a);
+  mh_chain_kernel<<<(int)blocks, tpb, 0, (cudaStream_t)stream>>>(*a);
   return (int)cudaGetLastError();
 }
 """
@@ -367,10 +373,14 @@ int gjb_model_mh_chain(const gjb_chain_args* a, void* stream) {""" + _CHECK + r"
 _EXTERN_HMC = r"""
 int gjb_model_hmc_chain(const gjb_chain_args* a, void* stream) {""" + _CHECK + r"""
   if (a->n_leapfrog < 0) return GJB_E_ARG;
-  int64_t blocks = (a->n + 127) / 128;
-  const int64_t cap = gjb::resident_blocks((const void*)hmc_chain_kernel, 128, 16);
+  // chains keep their state in registers for the whole launch: spread them over ALL SMs before filling one -- 8192 chains
+  // (one GPU's share of configs[4]) in 128-thread blocks would occupy 64 of the 148 SMs
+  int tpb = 128;
+  while (tpb > 32 && (a->n + tpb - 1) / tpb < 2 * 148) tpb >>= 1;
+  int64_t blocks = (a->n + tpb - 1) / tpb;
+  const int64_t cap = gjb::resident_blocks((const void*)hmc_chain_kernel, tpb, 16);
   if (blocks > cap) blocks = cap;
-  hmc_chain_kernel<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(*a);
+  hmc_chain_kernel<<<(int)blocks, tpb, 0, (cudaStream_t)stream>>>(*a);
   return (int)cudaGetLastError();
 }
 """

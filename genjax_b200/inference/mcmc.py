@@ -210,9 +210,14 @@ class Rejuvenate(EditRequest):
     ``proposal(*argument_mapping(current choice map))`` and weight by
     ``w + bwd_score - fwd_score``.  Normal-family proposals are fused."""
 
-    def __init__(self, proposal, argument_mapping):
+    def __init__(self, proposal, argument_mapping, reference_compat: bool = True):
+        """``reference_compat=True`` (default) scores the backward move exactly as rejuvenate.py:84-86: the proposal's
+        arguments are ``argument_mapping(bwd_chm)`` with ``bwd_chm`` the discarded (OLD) choices, so the backward score is
+        ``log q(old; mapping(old))``.  ``reference_compat=False`` is Metropolis-Hastings' ``log q(old; mapping(new))``
+        (what ``mh_chain`` uses).  Identical for proposals that ignore the current choice."""
         from ..gen.distributions import mv_normal_diag, normal
 
+        self.reference_compat = bool(reference_compat)
         if proposal not in (normal, mv_normal_diag) and getattr(proposal, "name", None) != "mv_normal_diag":
             raise NotImplementedError("fused Rejuvenate supports normal / mv_normal_diag proposals")
         self.proposal = proposal
@@ -238,7 +243,7 @@ class Rejuvenate(EditRequest):
         sel = Selection.all().extend(*addr)
         latent = _selected_sites(trace, sel)
         res = _run_chain("mh", key, trace, latent, (self._mapping(),) * len(latent), n_steps=1, step_size=1.0,
-                         accept=False)
+                         accept=False, compat_stale_grad=self.reference_compat)
         old = ChoiceMap.empty()
         for j in latent:
             s = trace.cm.ir.sites[j]

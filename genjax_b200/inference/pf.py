@@ -8,20 +8,25 @@ mapping_tutorial.ipynb cell 37; reweight formula inference/smc.py:383):
             log_w += w;  idx ~ categorical(log_w - logsumexp(log_w)) per offspring
             x_prev = trs.get_retval()[idx]
 
-``ParticleFilter`` is that idiom on the GPU in one of two forms:
+``ParticleFilter`` is that idiom on the GPU:
 
-  * ``mode="persistent"`` (default): the whole T-step filter is ONE cooperative
-    launch of the model's generated ``pf_kernel`` (gen/codegen.py,
-    ``gjb_model_pf_run``): per step (A) ancestor gather + propose + logpdf +
-    running max, (B) exact integer weight mass per CTA, (C) CDF scan +
-    systematic offspring ranges + log-marginal increment, separated by
-    grid-wide barriers instead of kernel boundaries;
-  * ``mode="graph"``: the same three phases as three launches per step
-    (``gjb_model_launch`` / ``gjb_weight_mass`` / ``gjb_resample_systematic``)
-    captured once as a CUDA graph.
+  * ``mode="auto"`` (default) -> ``"step"``: ONE launch per filter step
+    (``gjb_model_pf_step``, gen/codegen.py ``pf_step_kernel``, csrc/gjb_step.cuh):
+    every CTA resolves the ancestors of its own 2048 offspring slots from the
+    previous step's tile-exponent integer CDF (output-slot systematic
+    resampling), gathers, proposes, scores, and publishes the CDF row + tile
+    record of its new weights; T launches + a closing ``gjb_te_resample`` in one
+    CUDA graph, programmatic dependent launch between the steps;
+  * ``mode="steps"``: the same step body for all T steps in ONE cooperative
+    launch (``gjb_model_pf_steps``), a grid barrier per step;
+  * ``mode="graph"``: round 1's two launches per step over the exact-max CDF
+    (``gjb_model_launch`` + ``gjb_mass_resample_systematic``), also the form
+    behind ``resampler="multinomial"`` and ``reference_max="analytic"``;
+  * ``mode="persistent"``: round 1's cooperative kernel, three grid barriers per step.
 
-Both read device-resident keys / observations / initial state and give
-bit-identical results.
+"step" / "steps" agree bit for bit with each other, "graph" / "persistent" with each
+other; the two families are different realisations of the same estimator (their
+integer CDFs quantise the masses against different references).
 """
 
 from __future__ import annotations
@@ -123,8 +128,10 @@ class ParticleFilter:
         masses; a bound so loose that every mass underflows shows up as ``lse_terms[:, 1] == 0``."""
         if resampler not in ("systematic", "multinomial"):
             raise ValueError(f"resampler must be 'systematic' or 'multinomial', not {resampler!r}")
-        if mode not in ("auto", "persistent", "graph", "step"):
+        if mode not in ("auto", "persistent", "graph", "step", "steps"):
             raise ValueError(mode)
+        if mode == "steps" and reference_max != "running":
+            raise ValueError("mode='steps' forms its masses per tile (tile-exponent CDF); it takes no reference_max")
         if resampler == "multinomial":
             # the reference idiom itself: N independent categorical draws over the normalised weights per step
             # (mapping_tutorial.ipynb cell 37; inference/smc.py:102-109), as inverse-CDF draws over the exact integer CDF
@@ -274,8 +281,13 @@ class _Plan:
         tiles = (n + cabi.TE_TILE - 1) // cabi.TE_TILE
         step_ok = (tiles <= cabi.TE_MAX_TILES and pf.n_total == n and n <= (1 << 26) and pf.idx_offset % 4 == 0
                    and T < 65535 and self.cm.info.get("pf_step", False))
-        self.stepmode = pf.mode == "step" or (pf.mode == "auto" and step_ok)
-        self.mode = "step" if self.stepmode else ("graph" if pf.mode == "auto" else pf.mode)
+        # "steps": the same step body for ALL T steps in ONE cooperative launch (one grid barrier per step instead of a kernel
+        # boundary); needs a co-resident CTA per 2048-slot window (1 M particles: 512 of 592 slots on a B200)
+        self.stepsmode = pf.mode == "steps"
+        if self.stepsmode and not (step_ok and self.cm.lib.gjb_model_pf_steps_fits(n)):
+            raise NotImplementedError("mode='steps' needs a step-capable model on one device and a resident CTA per 2048 particles")
+        self.stepmode = pf.mode in ("step", "steps") or (pf.mode == "auto" and step_ok)
+        self.mode = ("steps" if self.stepsmode else "step") if self.stepmode else ("graph" if pf.mode == "auto" else pf.mode)
         if self.stepmode:
             if tiles > cabi.TE_MAX_TILES or pf.n_total > (1 << 26):
                 raise NotImplementedError(f"mode='step' resamples over at most {cabi.TE_MAX_TILES} tiles of {cabi.TE_TILE} "
@@ -333,6 +345,8 @@ class _Plan:
             self._build_pf_args()
         elif self.stepmode:
             self._build_step_args()
+            if self.stepsmode:
+                self._build_steps_args()
         else:
             self._build_args()
 
@@ -456,6 +470,36 @@ class _Plan:
         R.ancestors = self.anc[last].data_ptr()
         self.te_close = R
 
+    def _build_steps_args(self):
+        """One ``gjb_steps_args`` for the cooperative all-steps launch (the closing resampling is ``self.te_close``)."""
+        pf, ir, T, n = self.pf, self.ir, self.T, self.pf.n
+        if self.te_table:
+            raise NotImplementedError("mode='steps' is the table-free form")
+        Q = cabi.StepsArgs()
+        Q.n, Q.idx_offset, Q.T, Q.record = n, pf.idx_offset, T, int(self.record)
+        Q.keys = self.keys.data_ptr()
+        for i, s in enumerate(self.state_in):
+            Q.state0[i] = s.data_ptr()
+            Q.state_buf[i] = self.bufs[i].data_ptr()
+            Q.state_stride[i] = self.bufs[i][0].numel() * 4
+        for k, s in enumerate(self.shared):
+            i = len(self.state_in) + k
+            if isinstance(s, torch.Tensor):
+                Q.shared[i] = s.data_ptr()
+            else:
+                Q.scalars[i] = float(s)
+        for j, addr in self.obs_sites.items():
+            o = self.obs[addr]
+            Q.obs[j] = o.data_ptr()
+            Q.obs_stride[j] = (o[0].numel() if o.ndim > 1 else 1) * 4
+        Q.logw = (self.logw_hist if self.record else self.logw).data_ptr()
+        if self.record:
+            Q.ancestors = self.anc.data_ptr()
+        Q.cdf = self.te_cdf.data_ptr()
+        Q.recs = self.te_recs.data_ptr()
+        Q.lse = self.lse.data_ptr()
+        self.steps_args = Q
+
     def _build_args(self):
         pf, ir, T, n = self.pf, self.ir, self.T, self.pf.n
         self.margs = []
@@ -549,9 +593,23 @@ class _Plan:
             self.rargs.append((lw, R))
 
     def _enqueue(self):
+        """Enqueue one filter run.  With ``GJB_NVTX=1`` the run and its phases are bracketed by NVTX ranges (``pf.run`` >
+        ``pf.steps`` / ``pf.close``) for Nsight Systems timelines; ranges are host-side markers and cost nothing on the device."""
+        import os
+
+        if os.environ.get("GJB_NVTX") == "1":
+            torch.cuda.nvtx.range_push(f"pf.run[{self.mode}] n={self.pf.n} T={self.T}")
+            try:
+                return self._enqueue_impl()
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return self._enqueue_impl()
+
+    def _enqueue_impl(self):
         core = cabi.core()
         stream = cabi.stream_ptr(self.device)
         lib = self.cm.lib
+        nvtx = __import__("os").environ.get("GJB_NVTX") == "1"
         if self.persistent:
             cabi.check(lib.gjb_model_pf_run(C.byref(self.pf_args), stream), "gjb_model_pf_run")
             last = (self.T - 1) if self.record else ((self.T - 1) & 1)
@@ -559,15 +617,24 @@ class _Plan:
                 smc_ops.gather_rows(self.bufs[k][last], self.anc[last], self.final[k])
             return
         if self.stepmode:  # ONE launch per step, the closing resampling of the last step, the final gather(s)
-            for t in range(self.T):
+            if nvtx:
+                torch.cuda.nvtx.range_push("pf.steps: resample(t-1) + gather + propose + logpdf + masses(t)")
+            for t in range(0 if self.stepsmode else self.T):  # (mode "steps": one cooperative launch below instead)
                 cabi.check(lib.gjb_model_pf_step(C.byref(self.sargs[t]), stream), "gjb_model_pf_step")
                 if self.te_table and self.te_table_kernel:
                     cabi.check(core.gjb_te_table(C.byref(self.targs[t]), stream), "gjb_te_table")
+            if self.stepsmode:
+                cabi.check(lib.gjb_model_pf_steps(C.byref(self.steps_args), stream), "gjb_model_pf_steps")
+            if nvtx:
+                torch.cuda.nvtx.range_pop()
+                torch.cuda.nvtx.range_push("pf.close: resample(T-1) + final gather")
             cabi.check(core.gjb_te_resample(C.byref(self.te_close), stream), "gjb_te_resample")
             last = (self.T - 1) if self.record else ((self.T - 1) & 1)
             for k in range(len(self.bufs)):
                 smc_ops.gather_rows(self.bufs[k][last], self.anc[last], self.final[k])
             cabi.check(core.gjb_epoch_bump(self.te_epoch.data_ptr(), stream), "gjb_epoch_bump")  # new record tags next run
+            if nvtx:
+                torch.cuda.nvtx.range_pop()
             return
         if self.analytic and self.single_pass:  # 1 launch per step + one closing resampling launch
             self.tm3.zero_()
@@ -634,7 +701,7 @@ class _Plan:
         if self.persistent:
             return 2 + len(self.bufs)  # init + persistent filter kernel + final gather(s)
         if self.stepmode:
-            return self.T + 2 + len(self.bufs)  # T step kernels, closing resample, final gather(s), epoch bump
+            return (1 if self.stepsmode else self.T) + 2 + len(self.bufs)  # step kernel(s), closing resample, final gather(s), epoch bump
         if self.analytic and self.single_pass:
             return self.T + 1 + len(self.bufs)  # (+ one memset node)
         if self.analytic:
@@ -644,8 +711,10 @@ class _Plan:
         return 1 + (2 if getattr(self, "fuse_mass_resample", False) else 3) * self.T + len(self.bufs)
 
     def execute(self, key, state0, shared, obs, use_graph):
-        tab = torch.from_numpy(pf_key_table(key, self.T).view(np.int32))
-        self.keys.copy_(tab, non_blocking=True)
+        # the per-step key table is derived on the device from the run key's two words (3 us; the NumPy threefry of
+        # core/key.py pf_key_table costs 0.4-1.2 ms of host time per run, a quarter of a 1 M-particle, 100-step run)
+        w0, w1 = key.collapsed()
+        cabi.check(cabi.core().gjb_pf_key_table(w0, w1, self.T, self.keys.data_ptr(), cabi.stream_ptr(self.device)), "gjb_pf_key_table")
         for dst, src in zip(self.state_in, state0):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)

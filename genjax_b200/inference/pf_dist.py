@@ -342,8 +342,10 @@ class _DistPlan:
         return (3 + 3 * self.T if self.pf.fused else 2 + 6 * self.T) + len(self.bufs)  # pull: 3/step too, 2 hand-offs
 
     def execute(self, key, state0, shared, obs, use_graph):
-        tab = torch.from_numpy(pf_key_table(key, self.T).view(np.int32))
-        self.keys.copy_(tab, non_blocking=True)
+        # the per-step key table is derived on the device from the run key's two words (3 us; the NumPy threefry of
+        # core/key.py pf_key_table costs 0.4-1.2 ms of host time per run, a quarter of a 1 M-particle, 100-step run)
+        w0, w1 = key.collapsed()
+        cabi.check(cabi.core().gjb_pf_key_table(w0, w1, self.T, self.keys.data_ptr(), cabi.stream_ptr(self.device)), "gjb_pf_key_table")
         for dst, src in zip(self.state_in, state0):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
@@ -536,8 +538,10 @@ class _DistStepPlan:
         return (2 if self.table_kernel else 1) * self.T + 3 + len(self.bufs)  # step kernel (+ table kernel) per step, closing resample, gathers, barrier, epoch
 
     def execute(self, key, state0, shared, obs, use_graph):
-        tab = torch.from_numpy(pf_key_table(key, self.T).view(np.int32))
-        self.keys.copy_(tab, non_blocking=True)
+        # the per-step key table is derived on the device from the run key's two words (3 us; the NumPy threefry of
+        # core/key.py pf_key_table costs 0.4-1.2 ms of host time per run, a quarter of a 1 M-particle, 100-step run)
+        w0, w1 = key.collapsed()
+        cabi.check(cabi.core().gjb_pf_key_table(w0, w1, self.T, self.keys.data_ptr(), cabi.stream_ptr(self.device)), "gjb_pf_key_table")
         for dst, src in zip(self.state_in, state0):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)

@@ -13,7 +13,7 @@ import torch
 
 from . import build
 
-ABI_VERSION = 13  # GJB_ABI_VERSION of include/genjax_b200.h this binding mirrors (tests/test_abi.py keeps them equal)
+ABI_VERSION = 15  # GJB_ABI_VERSION of include/genjax_b200.h this binding mirrors (tests/test_abi.py keeps them equal)
 GJB_MAX_SITES = 16
 GJB_MAX_ARGS = 16
 GJB_MAX_RETS = 8
@@ -257,6 +257,30 @@ class StepArgs(C.Structure):
     ]
 
 
+class StepsArgs(C.Structure):
+    """``gjb_steps_args`` (include/genjax_b200.h section 2)."""
+
+    _fields_ = [
+        ("n", _i64),
+        ("idx_offset", _u64),
+        ("T", _i32),
+        ("record", _i32),
+        ("keys", _p),
+        ("state0", _p * GJB_MAX_RETS),
+        ("state_buf", _p * GJB_MAX_RETS),
+        ("state_stride", _i64 * GJB_MAX_RETS),
+        ("shared", _p * GJB_MAX_ARGS),
+        ("scalars", C.c_float * GJB_MAX_ARGS),
+        ("obs", _p * GJB_MAX_SITES),
+        ("obs_stride", _i64 * GJB_MAX_SITES),
+        ("logw", _p),
+        ("ancestors", _p),
+        ("cdf", _p),
+        ("recs", _p),
+        ("lse", _p),
+    ]
+
+
 class ChainArgs(C.Structure):
     """``gjb_chain_args`` (include/genjax_b200.h)."""
 
@@ -311,6 +335,7 @@ CORE_PROTOTYPES = {
     "gjb_te_masses": (C.c_int, [_p, _i64, _p, _p, _p]),
     "gjb_te_resample": (C.c_int, [C.POINTER(TeResampleArgs), _p]),
     "gjb_te_table": (C.c_int, [C.POINTER(TeTableArgs), _p]),
+    "gjb_pf_key_table": (C.c_int, [_u32, _u32, _i32, _p, _p]),
     "gjb_philox_fill": (C.c_int, [_u32, _u32, _u64, _u32, _u32, _i64, _p, _p]),
     "gjb_normal_fill": (C.c_int, [_u32, _u32, _u64, _u32, _i64, _i32, _p, _p]),
 }
@@ -321,6 +346,8 @@ MODEL_PROTOTYPES = {
     "gjb_model_pf_grid": (C.c_int, [_i64]),
     "gjb_model_pf_run": (C.c_int, [C.POINTER(PfArgs), _p]),
     "gjb_model_pf_step": (C.c_int, [C.POINTER(StepArgs), _p]),
+    "gjb_model_pf_steps_fits": (C.c_int, [_i64]),
+    "gjb_model_pf_steps": (C.c_int, [C.POINTER(StepsArgs), _p]),
     "gjb_model_mh_chain": (C.c_int, [C.POINTER(ChainArgs), _p]),
     "gjb_model_hmc_chain": (C.c_int, [C.POINTER(ChainArgs), _p]),
 }

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GJB_ABI_VERSION 13
+#define GJB_ABI_VERSION 15
 
 #define GJB_E_ARG (-1)      /* null / misaligned pointer, negative size          */
 #define GJB_E_RANGE (-2)    /* size beyond what the kernel supports              */
@@ -361,6 +361,13 @@ typedef struct gjb_te_resample_args {
 
 int gjb_te_resample(const gjb_te_resample_args* a, void* stream);
 
+/*
+ * The per-step key table of a filter run, derived ON THE DEVICE from the run key's two words (threefry2x32-20, the host
+ * key tree of core/key.py): row t = {prop_k0, prop_k1, res_k0, res_k1, res_idx_lo, res_idx_hi, mn_k0, mn_k1} with
+ * (k_prop, k_res) = split(fold_in(key, t)) -- `jax.random.fold_in / split` of the cookbook filter loop.  out: [T, 8].
+ */
+int gjb_pf_key_table(uint32_t key0, uint32_t key1, int32_t T, uint32_t* out, void* stream);
+
 /* Raw Philox words / N(0,1) draws for RNG known-answer tests. */
 int gjb_philox_fill(uint32_t key0, uint32_t key1, uint64_t idx_offset,
                     uint32_t site, uint32_t chunk, int64_t n, uint32_t* out4,
@@ -532,6 +539,36 @@ typedef struct gjb_step_args {
 int gjb_model_pf_step(const gjb_step_args* a, void* stream);
 
 /*
+ * ALL T steps of the same filter in ONE cooperative launch (one device; every window of 2048 slots needs a co-resident
+ * CTA: gjb_model_pf_steps_fits(n)): the per-step kernel's table-free body in a loop, ONE grid-wide barrier per step
+ * where gjb_model_pf_step has a kernel boundary; the random numbers of step t + 1 are drawn before the barrier of step
+ * t.  lse rows 0 .. T-2 and (record) ancestor rows 0 .. T-2 are written by this launch, the last step is resampled by
+ * gjb_te_resample(cdf + ((T-1) & 1) * tiles * 2048, recs + ((T-1) & 1) * tiles).
+ */
+typedef struct gjb_steps_args {
+  int64_t n;                 /* particles                                         */
+  uint64_t idx_offset;       /* RNG lane of particle 0 (multiple of 4)            */
+  int32_t T;                 /* filter steps                                      */
+  int32_t record;            /* 1: state_buf / logw / ancestors keep all T steps  */
+  const uint32_t* keys;      /* [T, 8] key table (gjb_pf_args.keys)               */
+  const void* state0[GJB_MAX_RETS];     /* initial state leaves [n(, d)]           */
+  void* state_buf[GJB_MAX_RETS];        /* [slots, n(, d)]; slots = record ? T : 2 */
+  int64_t state_stride[GJB_MAX_RETS];   /* bytes between slots                     */
+  const void* shared[GJB_MAX_ARGS];     /* shared args, indexed by model arg position */
+  float scalars[GJB_MAX_ARGS];
+  const void* obs[GJB_MAX_SITES];       /* observed sites: [T, ...] values (null = proposed) */
+  int64_t obs_stride[GJB_MAX_SITES];    /* bytes per step                          */
+  float* logw;               /* record ? [T, n] : [n] (the last step's weights)    */
+  int32_t* ancestors;        /* record: [T, n] (row T-1 is left to gjb_te_resample); else unused */
+  uint64_t* cdf;             /* [2, ceil(n / 2048) * 2048] scratch                 */
+  gjb_tile_rec* recs;        /* [2, ceil(n / 2048)] scratch                        */
+  double* lse;               /* [T, 3]                                            */
+} gjb_steps_args;
+
+int gjb_model_pf_steps_fits(int64_t n);
+int gjb_model_pf_steps(const gjb_steps_args* a, void* stream);
+
+/*
  * Batched MCMC drivers generated for the same model (one chain per lane).
  *   mh  : Rejuvenate-style random-walk proposal on the selected sites +
  *         accept `log(u) < alpha` (inference/requests/rejuvenate.py:70-94;
@@ -562,7 +599,8 @@ typedef struct gjb_chain_args {
   int32_t step0;             /* global index of the first transition (RNG)      */
   float step_size;           /* MH proposal scale / HMC eps                     */
   int32_t n_leapfrog;        /* HMC L                                           */
-  int32_t compat_stale_grad; /* HMC: reproduce hmc.py:186                       */
+  int32_t compat_stale_grad; /* reference-compat switch.  HMC: reproduce hmc.py:186 (the carried gradient); MH: take the
+                                backward proposal arguments at the OLD state as rejuvenate.py:84-86 does */
 } gjb_chain_args;
 
 int gjb_model_mh_chain(const gjb_chain_args* a, void* stream);

@@ -57,8 +57,10 @@ def _normal_sum(v, loc, scale):
     return out
 
 
-def mh_chain(logp, q, key, n_steps, step_size=1.0, proposal=None, accept=True, step0=0):
+def mh_chain(logp, q, key, n_steps, step_size=1.0, proposal=None, accept=True, step0=0, bwd_at_old=False):
     """``logp(q[n, D]) -> float32[n]``; ``proposal(q) -> (loc, scale)`` (default: random walk).
+    ``bwd_at_old=True``: the backward proposal arguments are taken at the OLD state, as rejuvenate.py:84-86 does
+    (``argument_mapping(bwd_chm)``, bwd_chm = the discarded choices); False: Metropolis-Hastings.
     Returns (q, logp(q), accept_count, last alpha)."""
     words, idx = rng.lanes(key)
     q = np.asarray(q, dtype=F32).copy()
@@ -76,7 +78,7 @@ def mh_chain(logp, q, key, n_steps, step_size=1.0, proposal=None, accept=True, s
         scale = np.broadcast_to(np.asarray(scale, dtype=F32), q.shape)
         prop = (loc + scale * z).astype(F32)
         fwd = _normal_sum(prop, loc, scale)
-        loc_b, scale_b = proposal(prop)
+        loc_b, scale_b = proposal(q if bwd_at_old else prop)
         loc_b = np.broadcast_to(np.asarray(loc_b, dtype=F32), q.shape)
         scale_b = np.broadcast_to(np.asarray(scale_b, dtype=F32), q.shape)
         bwd = _normal_sum(q, loc_b, scale_b)

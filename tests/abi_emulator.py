@@ -139,6 +139,18 @@ class EmulatedModelLib:
         sites = [{"addr": list(s.addr), "dist": s.dist.name} for s in self.ir.sites]
         return json.dumps({"name": self.ir.name, "sites": sites, "emulated": True, "pf_step": True}).encode()
 
+    def gjb_model_pf_steps_fits(self, n):
+        return 1 if n <= 2048 else 0  # the SIMT host run of a cooperative kernel is a grid of ONE block
+
+    def gjb_model_pf_steps(self, a_ref, stream):
+        import simt_kernels
+        from genjax_b200.gen import codegen
+
+        source = getattr(self, "source", None) or codegen.generate(self.ir, getattr(self, "pf_obs", None), self.chain)
+        lib = simt_kernels.model(source)
+        self.launches += 1
+        return lib.s_pf_steps(a_ref)
+
     def gjb_model_pf_step(self, a_ref, stream):
         """The single-launch filter step is a block-level kernel: always the GENERATED source with real block semantics
         (tests/simt_kernels.py), also when the other launches of this library interpret the IR."""
@@ -366,7 +378,7 @@ def _emulated_chain(lib, a_ref, kind):
             return loc, scale
 
         q, lp, acc, alpha = omcmc.mh_chain(logp, state.copy(), key, int(A.n_steps), float(A.step_size), proposal, accept,
-                                           int(A.step0))
+                                           int(A.step0), bwd_at_old=bool(A.compat_stale_grad))
     else:
         try:
             grads = AD.grad(logp_e, lat_vals)
@@ -500,9 +512,15 @@ class EmulatedCore:
     oracle/smc.py.  Multi-GPU, fused cooperative and filter entry points are GPU-only and absent on purpose."""
 
     def gjb_abi_version(self):
-        return 13
+        return 15
 
     def gjb_mass_resample_fits(self, n):
+        return 0
+
+    def gjb_pf_key_table(self, key0, key1, T, out, stream):
+        from genjax_b200.core.key import PRNGKey, pf_key_table
+
+        _arr(out, 8 * T, C.c_uint32, np.uint32)[:] = pf_key_table(PRNGKey((key0, key1), 0), T).reshape(-1)
         return 0
 
     def gjb_epoch_bump(self, epoch, stream):

@@ -19,6 +19,8 @@
 #define __align__(n) __attribute__((aligned(n)))
 
 struct uint4 { uint32_t x, y, z, w; };
+struct uint2 { uint32_t x, y; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 struct int4 { int32_t x, y, z, w; };
 struct int2 { int32_t x, y; };
 struct ulonglong2 { unsigned long long x, y; };

@@ -89,6 +89,10 @@ int s_te_table(const gjb_te_table_args* a) {
   simt::launch(1, gjb::kTabThreads, [=] { gjb::te_table_kernel(A); });
   return 0;
 }
+int s_pf_key_table(uint32_t k0, uint32_t k1, int T, uint32_t* out) {
+  simt::launch(2, 128, [=] { gjb::pf_key_table_kernel(k0, k1, T, out); });
+  return 0;
+}
 int s_gather_rows(const uint32_t* src, const int32_t* anc, uint32_t* dst, int64_t n_out, int w, int grid) {
   simt::launch(grid, 256, [=] { gjb::gather_rows_kernel<uint32_t>(src, anc, dst, n_out, w); });
   return 0;
@@ -148,6 +152,14 @@ extern "C" int s_pf_step(const gjb_step_args* a) {
   return 0;
 }
 '''
+STEPS_DRIVER = r'''
+extern "C" int s_pf_steps(const gjb_steps_args* q) {  // cooperative: a grid of ONE block only (n <= 2048)
+  const gjb_steps_args Q = *q;
+  if (Q.n > gjb::kTeTile) return -2;
+  simt::launch(1, kThreads, [=] { pf_steps_kernel(Q); });
+  return 0;
+}
+'''
 PF_DRIVER = r'''
 extern "C" int s_pf_run(const gjb_pf_args* q) {  // the persistent cooperative filter as a grid of ONE block
   const gjb_pf_args Q = *q;
@@ -176,6 +188,8 @@ def model(source: str):
         text += PF_DRIVER
     if "pf_step_kernel(" in body:
         text += STEP_DRIVER
+    if "pf_steps_kernel(" in body:
+        text += STEPS_DRIVER
     for kind in ("mh", "hmc"):
         if f"{kind}_chain_kernel(" in body:
             text += CHAIN_DRIVER % {"kind": kind}

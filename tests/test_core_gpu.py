@@ -162,3 +162,17 @@ def test_gather_rows(device, shape):
     anc = torch.randint(0, shape[0], (777,), generator=g, dtype=torch.int32).to(device)
     out = ops.gather_rows(src, anc)
     assert torch.equal(out, src[anc.long()])
+
+
+def test_device_key_table_equals_the_host_key_tree(device):
+    """gjb_pf_key_table: the filter's per-step keys derived on the device == core/key.py pf_key_table (host threefry)."""
+    import genjax_b200 as gj
+    from genjax_b200.core.key import pf_key_table
+    from genjax_b200.runtime import cabi
+
+    for seed, T in ((314159, 100), (7, 1), (2**40 + 5, 1000)):
+        k = gj.fold_in(gj.key(seed), 3)
+        w0, w1 = k.collapsed()
+        out = torch.zeros((T, 8), dtype=torch.int32, device=device)
+        cabi.check(cabi.core().gjb_pf_key_table(w0, w1, T, out.data_ptr(), cabi.stream_ptr(device)), "gjb_pf_key_table")
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), pf_key_table(k, T))

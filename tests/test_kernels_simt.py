@@ -166,3 +166,22 @@ def test_tile_exponent_masses_and_pull_resampling(core, n, scale, kind):
             assert lse[1] == float(smc.te_cdf(lw)[1])
         else:
             assert lse[1] == 0.0 and lse[2] == -np.inf
+
+
+def test_device_key_table_equals_the_host_key_tree(core):
+    """pf_key_table_kernel (threefry2x32-20 on the device) == core/key.py pf_key_table == oracle/smc.py pf_step_keys:
+    proposal words, resample key, multinomial lane words of every step."""
+    import genjax_b200 as gj
+    from genjax_b200.core.key import pf_key_table
+
+    for seed, T in ((314159, 100), (7, 1), (2**40 + 5, 333)):
+        k = gj.fold_in(gj.key(seed), 3)
+        w0, w1 = k.collapsed()
+        out = np.zeros((T, 8), dtype=np.uint32)
+        core.s_pf_key_table(C.c_uint32(w0), C.c_uint32(w1), C.c_int(T), _p(out))
+        assert np.array_equal(out, pf_key_table(k, T))
+        okey = rng.fold_in(rng.key(seed), 3)
+        for t in (0, T - 1):
+            kp, kr = smc.pf_step_keys(okey, t)
+            assert tuple(out[t, 2:4]) == kr.words and out[t, 4] == kr.index
+            assert tuple(out[t, 0:2]) == rng.split(kp, 4).words and tuple(out[t, 6:8]) == rng.split(kr, 4).words

@@ -307,3 +307,32 @@ def test_eight_schools_hmc_config5_small(device):
     assert mu.mean() == pytest.approx(q[:, 0].mean(), abs=0.25)
     assert lt.mean() == pytest.approx(q[:, 1].mean(), abs=0.08)
     assert mu.std() == pytest.approx(q[:, 0].std(), rel=0.1)
+
+
+def test_rejuvenate_backward_score_reference_compat(device):
+    """rejuvenate.py:84-88: the reference scores the backward move with ``argument_mapping(bwd_chm)``, bwd_chm = the OLD
+    choice, i.e. log q(old; mapping(old)); ``Rejuvenate(..., reference_compat=False)`` is Metropolis-Hastings'
+    log q(old; mapping(new)).  With a random-walk proposal N(chm, s) the two differ by z^2 / 2."""
+    gj = _gj()
+    from genjax_b200.inference.requests import Rejuvenate, StaticRequest
+
+    @gj.gen
+    def model():
+        gj.normal(0.0, 3.0) @ "y1"
+
+    n, s = 4000, 0.3
+    tr = model.simulate(gj.split(gj.key(7), n), ())
+    old = tr.get_choices()["y1"]
+    kb = gj.split(gj.key(8), n)
+    outs = {}
+    for compat in (True, False):
+        req = StaticRequest({"y1": Rejuvenate(gj.normal, lambda chm: (chm.get_value(), s), reference_compat=compat)})
+        new_tr, w, _, _ = req.edit(kb, tr, ())
+        outs[compat] = (new_tr.get_choices()["y1"], w)
+    new = outs[True][0]
+    assert torch.equal(new, outs[False][0])  # same proposal draw
+    dlp = gj.normal.logpdf(new, 0.0, 3.0) - gj.normal.logpdf(old, 0.0, 3.0)
+    fwd = gj.normal.logpdf(new, old, s)
+    torch.testing.assert_close(outs[True][1], dlp + gj.normal.logpdf(old, old, s) - fwd, rtol=2e-4, atol=2e-4)   # reference
+    torch.testing.assert_close(outs[False][1], dlp + gj.normal.logpdf(old, new, s) - fwd, rtol=2e-4, atol=2e-4)  # MH: = dlp
+    assert Rejuvenate(gj.normal, lambda chm: (0.0, 1.0)).reference_compat

@@ -217,3 +217,33 @@ def test_filter_result_diagnostics_checkpoint_and_html(device, tmp_path):
     page = gj.render_html(res)
     assert page.startswith("<div") and "PFResult" in page and "ESS per step" in page
     assert "ChoiceMap" in gj.render_html(obs) and "float32" in gj.render_html({"x": torch.zeros(3)})
+
+
+@pytest.mark.parametrize("n,T", [(7, 5), (6000, 6), (1 << 20, 12)])
+def test_all_steps_in_one_cooperative_launch_equal_the_per_step_launches(device, n, T):
+    """mode="steps" (gjb_model_pf_steps: the whole filter in ONE cooperative launch, one grid barrier per step) ==
+    mode="step" (one launch per step), bit for bit: ancestors, states, weights, increments, final state; scalar and
+    vector models; record and ping-pong buffers."""
+    gj, wl, ParticleFilter = _wl()
+    ys = osmc.simulate_lgssm(1, T, 1, wl.LG_A, wl.LG_Q, wl.LG_C, wl.LG_R)[:, 0]
+    x0 = torch.from_numpy(np.random.default_rng(n).standard_normal(n).astype(F32))
+    obs = gj.C["y"].set(torch.from_numpy(ys))
+    for record in (True, False):
+        a = ParticleFilter(wl.lgssm_step, n, mode="steps").run(gj.key(17), x0, obs, record=record)
+        b = ParticleFilter(wl.lgssm_step, n, mode="step").run(gj.key(17), x0, obs, record=record)
+        assert torch.equal(a.log_increments, b.log_increments) and torch.equal(a.state[0], b.state[0])
+        if record:
+            assert torch.equal(a.ancestors, b.ancestors) and torch.equal(a.history["log_weights"], b.history["log_weights"])
+            assert torch.equal(a.history["state"][0], b.history["state"][0])
+    if n >= 6000:
+        d = 8
+        q, r = torch.full((d,), wl.LG_Q), torch.full((d,), 0.5 * math.sqrt(d))
+        ysv = torch.from_numpy(osmc.simulate_lgssm(2, T, d, wl.LG_A, wl.LG_Q, wl.LG_C, 0.5 * math.sqrt(d)))
+        x0v = torch.from_numpy(np.random.default_rng(3).standard_normal((min(n, 70_000), d)).astype(F32))
+        nv = x0v.shape[0]
+        a = ParticleFilter(wl.lgssm_step_vec, nv, mode="steps").run(gj.key(5), x0v, gj.C["y"].set(ysv), (q, r), record=True)
+        b = ParticleFilter(wl.lgssm_step_vec, nv, mode="step").run(gj.key(5), x0v, gj.C["y"].set(ysv), (q, r), record=True)
+        assert torch.equal(a.ancestors, b.ancestors) and torch.equal(a.log_increments, b.log_increments)
+        assert torch.equal(a.state[0], b.state[0])
+    with pytest.raises(NotImplementedError):  # more windows than resident CTAs: the per-step form is the one to use
+        ParticleFilter(wl.lgssm_step, 1 << 22, mode="steps").run(gj.key(1), torch.zeros(1 << 22), gj.C["y"].set(torch.from_numpy(ys)))

@@ -81,3 +81,21 @@ def test_step_filter_integer_state(emu):
     pf = ParticleFilter(hmm_step, n, mode="step")
     res = pf.run(gj.key(9), torch.from_numpy(z0), gj.C["y"].set(torch.from_numpy(ys)), (torch.from_numpy(trans), torch.from_numpy(obsl)), record=True)
     check_against_oracle(res, z0, [{"y": np.int32(y)} for y in ys], o_hmm, 9, n, T, shared=(trans, obsl))
+
+
+@pytest.mark.parametrize("n", [7, 2048])
+def test_all_steps_in_one_cooperative_launch_equal_the_per_step_launches(emu, n):
+    """mode="steps" (gjb_model_pf_steps: every step of the filter in ONE cooperative launch, a grid barrier per step) ==
+    mode="step", bit for bit; on the host a cooperative grid is one block, so up to one tile here (the device test runs
+    1 M particles)."""
+    T = 5
+    ys = osmc.simulate_lgssm(1, T, 1, LG_A, LG_Q, LG_C, LG_R)[:, 0]
+    x0 = torch.from_numpy(np.random.default_rng(n).standard_normal(n).astype(F32))
+    obs = gj.C["y"].set(torch.from_numpy(ys))
+    for record in (True, False):
+        a = ParticleFilter(lgssm_step, n, mode="steps").run(gj.key(17), x0, obs, record=record)
+        b = ParticleFilter(lgssm_step, n, mode="step").run(gj.key(17), x0, obs, record=record)
+        assert torch.equal(a.log_increments, b.log_increments) and torch.equal(a.state[0], b.state[0])
+        if record:
+            assert torch.equal(a.ancestors, b.ancestors) and torch.equal(a.history["log_weights"], b.history["log_weights"])
+            assert torch.equal(a.history["state"][0], b.history["state"][0])
