@@ -697,9 +697,13 @@ def run_ours(args):
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             tr = json.load(f).get(f"d{d}", {})
-        key_ = "mass_resample_kernel_dram_bytes_per_launch" if "mass_resample" in roofline["kernel"] else "model_kernel_dram_bytes_per_launch"
-        roofline["traffic"] = tr.get(key_)
-        roofline["traffic_source"] = tr.get("source")
+        # keyed by the kernel the roofline names: a capture of another kernel never stands in (round 1's constant went stale)
+        kname = roofline["kernel"].split(":")[0].split(" ")[0]
+        roofline["traffic"] = tr.get(kname + "_dram_bytes_per_launch")
+        roofline["traffic_source"] = tr.get(kname + "_source", tr.get("source")) if roofline["traffic"] is not None else \
+            f"no committed ncu capture of {kname} at d={d}"
+        if roofline["traffic"] is not None and global_resample:
+            roofline["traffic_source"] += " (single-device capture)"
     except Exception:
         pass
     roofline["working_set_note"] = (
