@@ -29,43 +29,83 @@ def _time(fn, reps=3):
     return e0.elapsed_time(e1) / reps, out
 
 
+def _shard():
+    """(world, rank, device): chains are sharded by global index; no collective on the data path."""
+    import torch.distributed as dist
+
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+    return world, rank
+
+
+def _fingerprint(t):
+    """sha1 of a tensor's bytes: chain i's result depends on its GLOBAL index only, so the same chains give the same
+    fingerprint on 1 and on R GPUs (R-independence check)."""
+    import hashlib
+
+    return hashlib.sha1(t.detach().cpu().numpy().tobytes()).hexdigest()[:16]
+
+
+def _finish(world, ms):
+    import torch.distributed as dist
+
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
 def mh():
     from genjax_b200.inference.mcmc import mh_chain
     from genjax_b200.workloads import gmm_target
 
-    K, D, n, steps = 8, 8, 262_144, 1000
+    world, rank = _shard()
+    K, D, n_total, steps = 8, 8, 262_144, 1000
+    n = n_total // world
     g = np.random.default_rng(1)
     mu = torch.from_numpy(g.uniform(-4, 4, size=(K, D)).astype(np.float32))
     args = (torch.zeros(K), mu, torch.full((K,), 0.7))
-    tr = gmm_target.simulate(gj.split(gj.key(2), n), args)
-    kb = gj.split(gj.key(3), n)
+    lanes = slice(rank * n, (rank + 1) * n)  # this rank's chains = lanes of the GLOBAL key batches
+    tr = gmm_target.simulate(gj.split(gj.key(2), n_total)[lanes], args)
+    kb = gj.split(gj.key(3), n_total)[lanes]
     ms, res = _time(lambda: mh_chain(kb, tr, gj.S["x"], step_size=0.5, n_steps=steps, rebuild_trace=False))
+    ms = _finish(world, ms)
     x = res.trace.state.cpu().numpy()
     occ = np.bincount(((x[:, None, :] - mu.numpy()[None]) ** 2).sum(-1).argmin(1), minlength=K) / n
-    print(json.dumps({"config": "configs[2] GMM MH", "chains": n, "steps": steps, "ms": ms,
-                      "chain_steps_per_s": n * steps / (ms * 1e-3), "accept_rate": float(res.accept_rate),
-                      "component_occupancy": [round(float(o), 4) for o in occ],
-                      "hbm_bytes_per_launch": 2 * n * (4 * D + 4), "note": "state in registers; 1 launch = 1000 transitions"}))
+    if rank == 0:
+        print(json.dumps({"config": "configs[2] GMM MH", "n_gpus": world, "chains": n_total, "steps": steps, "ms": ms,
+                          "chain_steps_per_s": n_total * steps / (ms * 1e-3), "accept_rate": float(res.accept_rate),
+                          "component_occupancy_rank0": [round(float(o), 4) for o in occ],
+                          "fingerprint_chains_0_1023": _fingerprint(res.trace.state[:1024]),
+                          "hbm_bytes_per_launch": 2 * n * (4 * D + 4), "note": "state in registers; 1 launch = 1000 transitions"}))
 
 
 def hmc():
     from genjax_b200.inference.mcmc import hmc_chain
     from genjax_b200.workloads import EIGHT_SCHOOLS_SIGMA, EIGHT_SCHOOLS_Y, eight_schools
 
-    n, iters, L = 8192, 200, 10
+    world, rank = _shard()
+    n_total = int(os.environ.get("GJB_HMC_CHAINS", "65536" if world > 1 else "8192"))  # configs[4]: 64 K chains over 8 GPUs
+    n, iters, L = n_total // world, 200, 10
+    lanes = slice(rank * n, (rank + 1) * n)
     y, sig = torch.tensor(EIGHT_SCHOOLS_Y), torch.tensor(EIGHT_SCHOOLS_SIGMA)
-    tr, _ = eight_schools.importance(gj.split(gj.key(4), n), gj.C["y"].set(y), (sig,))
+    tr, _ = eight_schools.importance(gj.split(gj.key(4), n_total)[lanes], gj.C["y"].set(y), (sig,))
     sel = gj.S["mu"] | gj.S["log_tau"] | gj.S["theta"]
-    kb = gj.split(gj.key(5), n)
+    kb = gj.split(gj.key(5), n_total)[lanes]
     out = {}
     for compat in (False, True):
         ms, res = _time(lambda: hmc_chain(kb, tr, sel, eps=0.05, L=L, n_iters=iters, compat_stale_grad=compat, rebuild_trace=False))
+        ms = _finish(world, ms)
         st = res.trace.state
         out["compat_hmc_py_186" if compat else "textbook"] = {
-            "ms": ms, "leapfrogs_per_s": n * iters * L / (ms * 1e-3), "accept_rate": float(res.accept_rate),
-            "mean_mu": float(st[:, 0].mean()), "mean_log_tau": float(st[:, 1].mean())}
-    print(json.dumps({"config": "configs[4] 8-schools HMC, one GPU's share (8192 of 65536 chains)", "chains": n,
-                      "iters": iters, "L": L, "eps": 0.05, **out}))
+            "ms": ms, "leapfrogs_per_s": n_total * iters * L / (ms * 1e-3), "accept_rate": float(res.accept_rate),
+            "mean_mu_rank0": float(st[:, 0].mean()), "mean_log_tau_rank0": float(st[:, 1].mean()),
+            "fingerprint_chains_0_1023": _fingerprint(st[:1024])}
+    if rank == 0:
+        print(json.dumps({"config": "configs[4] 8-schools HMC", "n_gpus": world, "chains": n_total,
+                          "iters": iters, "L": L, "eps": 0.05, **out}))
 
 
 def hmm():
