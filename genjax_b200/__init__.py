@@ -68,6 +68,8 @@ from .gen.gfi import (
 from .gen.static import Batched, StaticGenerativeFunction, StaticTrace, gen, vmap
 from .gen.scan import Scan, ScanTrace, accumulate, iterate, iterate_final, reduce, scan
 from .gen.vmap_combinator import Vmap, VmapTrace, repeat, vmap_combinator
+from .gen.switch import MaskCombinator, Switch, mask, mix, or_else, switch
+from .core.mask import Mask
 from .inference.sp import Algorithm, Marginal, SampleDistribution, Target, marginal
 from . import inference
 from .core.render import render_html

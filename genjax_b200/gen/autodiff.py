@@ -140,6 +140,9 @@ def model_logp(ir, site_values: dict | None = None) -> Expr:
     total = None
     for s in ir.sites:
         lp = logpdf_expr(s.dist, s.value, s.args)
+        flag = s.flag() if hasattr(s, "flag") else None
+        if flag is not None:  # a site under a Switch branch / Mask counts only where it is valid (switch.py:171, mask.py:84)
+            lp = E.where(flag, lp, E.const(0.0))
         total = lp if total is None else total + lp
     if total is None:
         return E.const(0.0)

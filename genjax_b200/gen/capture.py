@@ -19,6 +19,7 @@ from typing import Any, Callable
 
 from . import expr as E
 from .expr import Expr
+from .expr import I32 as I32_
 
 
 class AddressReuse(Exception):
@@ -60,6 +61,20 @@ class SiteSpec:
     dist: Any  # Distribution
     args: list  # Expr per canonical distribution argument
     value: Expr  # the site's value node
+    # dynamic structure (combinators/switch.py, mask.py): a site inside a Switch branch exists only where ``live`` holds
+    # (elsewhere its value reads 0, as the zero-filled sub-traces of the unselected branches, switch.py:171-180); a site
+    # under a MaskCombinator is always visited but contributes its log-density only where ``scored`` holds (mask.py:84).
+    live: Expr | None = None
+    scored: Expr | None = None
+    excl: tuple = ()  # ((switch id, branch), ...) -- two sites may share an address iff they sit in different branches
+    cmask: Expr | None = None  # hidden per-particle argument: bit 0 = take the supplied value (else sample), bit 1 = the
+    #                            site's log-density stays out of the weight (Mask-ed constraints, distribution.py:129-142)
+
+    def flag(self) -> Expr | None:
+        """Where the choice is valid: what ``chm.mask(flag)`` / ``ChoiceMap.switch`` report for it."""
+        if self.live is None:
+            return self.scored
+        return self.live if self.scored is None else E.binary("and", self.live, self.scored)
 
 
 @dataclass
@@ -73,12 +88,22 @@ class ModelIR:
     width: int = 0  # vector event width D (0 = all scalar)
     digest: str = ""
     subcalls: dict = dataclasses.field(default_factory=dict)  # address prefix of a nested @gen call -> (arg leaves, ret leaves)
+    flag_leaves: list = dataclasses.field(default_factory=list)  # validity predicates written out after the return leaves
+    flag_of: dict = dataclasses.field(default_factory=dict)  # site index -> position in flag_leaves
+    n_user_args: int = -1  # model arguments proper; the rest are hidden constraint-mask arguments (SiteSpec.cmask)
 
     def site_index(self, addr: tuple) -> int:
-        for s in self.sites:
-            if s.addr == addr:
-                return s.index
+        hits = [s.index for s in self.sites if s.addr == addr]
+        if len(hits) == 1:
+            return hits[0]
+        if hits:
+            raise NotImplementedError(f"address {addr} names a site in several Switch branches")
         raise KeyError(addr)
+
+    @property
+    def dynamic(self) -> bool:
+        """Does the model hold sites under a Switch / MaskCombinator or Mask-ed constraints?"""
+        return bool(self.flag_of) or any(s.cmask is not None for s in self.sites)
 
     def addresses(self) -> list:
         return [s.addr for s in self.sites]
@@ -88,22 +113,62 @@ _CAPTURE: contextvars.ContextVar = contextvars.ContextVar("genjax_b200_capture",
 
 
 class _Capture:
-    def __init__(self):
+    def __init__(self, cmask_addrs=(), n_args: int = 0):
         self.sites: list[SiteSpec] = []
         self.prefix: tuple = ()
-        self.addrs: set = set()
+        self.addrs: dict = {}  # full address -> exclusivity tags of the sites recorded there
         self.subcalls: dict = {}
+        self.frames: list = []  # (kind "switch" | "mask", id, branch, predicate Expr)
+        self.cmask_addrs = set(cmask_addrs)
+        self.extra_args: list = []  # (ArgSpec, Expr) hidden arguments appended after the model's own
+        self.n_args = n_args
+        self._ids = 0
+
+    def new_id(self) -> int:
+        self._ids += 1
+        return self._ids
+
+    def frame(self, kind: str, ident: int, branch: int, pred: Expr):
+        cap = self
+
+        class _Frame:
+            def __enter__(self):
+                cap.frames.append((kind, ident, branch, pred))
+
+            def __exit__(self, *exc):
+                cap.frames.pop()
+                return False
+
+        return _Frame()
+
+    def _preds(self):
+        live = scored = None
+        for kind, _i, _b, pred in self.frames:
+            if kind == "switch":
+                live = pred if live is None else E.binary("and", live, pred)
+            else:
+                scored = pred if scored is None else E.binary("and", scored, pred)
+        return live, scored
 
     def record(self, addr, dist, args) -> Expr:
         full = self.prefix + addr
-        if full in self.addrs:
-            raise AddressReuse(full if len(full) > 1 else full[0])
-        self.addrs.add(full)
+        excl = tuple((i, b) for kind, i, b, _p in self.frames if kind == "switch")
+        for other in self.addrs.get(full, ()):
+            # the same address may be visited once per branch of one Switch (ChoiceMap.switch merges them)
+            if not any(i == j and b != c for i, b in excl for j, c in other):
+                raise AddressReuse(full if len(full) > 1 else full[0])
+        self.addrs.setdefault(full, []).append(excl)
         cargs = dist.canonical_args(args)
         dtype, shape = dist.value_type(cargs)
         idx = len(self.sites)
         v = Expr("site", (), dtype, shape, idx)
-        self.sites.append(SiteSpec(idx, full, dist, cargs, v))
+        live, scored = self._preds()
+        cmask = None
+        if full in self.cmask_addrs:
+            k = self.n_args + len(self.extra_args)
+            cmask = Expr("arg", (), I32_, (), {"index": k, "kind": "particle"})
+            self.extra_args.append((ArgSpec("particle", I32_, ()), cmask))
+        self.sites.append(SiteSpec(idx, full, dist, cargs, v, live, scored, excl, cmask))
         return v
 
 
@@ -119,6 +184,10 @@ def trace_site(addr, gen_fn, args):
     from ..core.choice_map import _norm_addr
 
     addr = _norm_addr(addr)
+    if isinstance(gen_fn, GenerativeFunctionClosure_()):
+        # ``f(a)(b) @ addr`` / ``normal(0., 1.).or_else(...)(...)``: a closure used as a callee
+        args = tuple(gen_fn.args) + tuple(args)
+        gen_fn = gen_fn.gen_fn
     if hasattr(gen_fn, "capture_inline"):
         # nested @gen call: inline its sites under the address prefix
         old = cap.prefix
@@ -133,6 +202,24 @@ def trace_site(addr, gen_fn, args):
     return cap.record(addr, gen_fn, args)
 
 
+def GenerativeFunctionClosure_():
+    from .gfi import GenerativeFunctionClosure
+
+    return GenerativeFunctionClosure
+
+
+def inline_call(gen_fn, args):
+    """Run ``gen_fn(*args)`` at the CURRENT address prefix of the capture: a nested ``@gen`` function / combinator inlines
+    its sites, a distribution records one site at the prefix itself (its address is the callee's, ``()`` below it)."""
+    cap = _CAPTURE.get()
+    if isinstance(gen_fn, GenerativeFunctionClosure_()):
+        args = tuple(gen_fn.args) + tuple(args)
+        gen_fn = gen_fn.gen_fn
+    if hasattr(gen_fn, "capture_inline"):
+        return gen_fn.capture_inline(tuple(args))
+    return cap.record((), gen_fn, tuple(args))
+
+
 # ----------------------------------------------------------------- pytrees
 
 
@@ -142,10 +229,13 @@ def flatten(tree) -> tuple[list, Any]:
 
     def go(t):
         from ..core.choice_map import ChoiceMap
+        from ..core.mask import Mask
 
         if isinstance(t, ChoiceMap):
             # a choice map is a pytree of its leaves (the reference's ChoiceMap is a Pytree, choice_map.py:847)
             return ("chm", [(addr, go(v)) for addr, v in t.leaves()])
+        if isinstance(t, Mask):
+            return ("mask", (go(t.value), go(t.flag)))
         if type(t).__name__ == "Target" and hasattr(t, "constraint") and hasattr(t, "p"):
             # Target(p, args, constraint): p is static, args and constraint are traced (sp.py:53-81)
             return ("target", (t.p, go(t.args), go(t.constraint)))
@@ -175,6 +265,16 @@ def unflatten(tree, leaves):
         for addr, sub in payload:
             out = out | ChoiceMap.entry(unflatten(sub, leaves), *addr)
         return out
+    if kind == "mask":
+        from ..core.mask import Mask
+
+        v, f = payload
+        f = unflatten(f, leaves)
+        if hasattr(f, "dtype") and hasattr(f, "to") and not isinstance(f, Expr):
+            import torch
+
+            f = f.to(torch.bool)
+        return Mask(unflatten(v, leaves), f)
     if kind == "target":
         from ..inference.sp import Target
 
@@ -194,13 +294,15 @@ def unflatten(tree, leaves):
     return leaves[payload]
 
 
-def capture(source: Callable, name: str, arg_specs: list, arg_tree) -> ModelIR:
-    """Run ``source`` on symbolic args built from ``arg_specs``."""
+def capture(source: Callable, name: str, arg_specs: list, arg_tree, cmask_addrs=()) -> ModelIR:
+    """Run ``source`` on symbolic args built from ``arg_specs``.  ``cmask_addrs``: addresses whose constraint carries a
+    per-particle validity flag (a hidden int32 argument per such site is appended to the model's own)."""
+    arg_specs = list(arg_specs)
     arg_exprs = [
         Expr("arg", (), spec.dtype, spec.shape, {"index": i, "kind": spec.kind}) for i, spec in enumerate(arg_specs)
     ]
     sym_args = unflatten(arg_tree, arg_exprs)
-    cap = _Capture()
+    cap = _Capture(cmask_addrs, len(arg_specs))
     tok = _CAPTURE.set(cap)
     try:
         ret = source(*sym_args)
@@ -219,10 +321,32 @@ def capture(source: Callable, name: str, arg_specs: list, arg_tree) -> ModelIR:
             widths.add(r.shape[0])
     if len(widths) > 1:
         raise NotImplementedError(f"all vector-valued choices/arguments of one model must share one width, got {widths}")
+    n_user = len(arg_specs)
+    for spec, e in cap.extra_args:
+        arg_specs.append(spec)
+        arg_exprs.append(e)
+    missing = set(cmask_addrs) - {s.addr for s in cap.sites}
+    if missing:
+        raise KeyError(f"masked constraint at {sorted(missing)}: no such site")
     ir = ModelIR(name, list(arg_specs), arg_exprs, cap.sites, ret_leaves, ret_tree, width=(widths.pop() if widths else 0),
-                 subcalls=cap.subcalls)
+                 subcalls=cap.subcalls, n_user_args=n_user)
+    # validity flags of the sites under a Switch / MaskCombinator leave the kernel as extra (hidden) return leaves
+    seen: dict = {}
+    for s in cap.sites:
+        f = s.flag()
+        if f is None:
+            continue
+        key = (s.live._id if s.live is not None else 0, s.scored._id if s.scored is not None else 0)
+        if key not in seen:
+            seen[key] = len(ir.flag_leaves)
+            ir.flag_leaves.append(f)
+        ir.flag_of[s.index] = seen[key]
     if len(ir.sites) > 16:
         raise NotImplementedError("more than 16 random-choice sites in one static model")
+    if len(ir.args) > 16:
+        raise NotImplementedError("more than 16 model arguments (hidden constraint masks included)")
+    if len(ir.ret_leaves) + len(ir.flag_leaves) > 8:
+        raise NotImplementedError("more than 8 return leaves (validity flags of Switch / Mask sites included)")
     return ir
 
 
@@ -231,7 +355,9 @@ def ir_fingerprint(ir: ModelIR) -> str:
     roots = []
     for s in ir.sites:
         roots.extend(s.args)
+        roots.extend(p for p in (s.live, s.scored, s.cmask) if p is not None)
     roots.extend(r for r in ir.ret_leaves if isinstance(r, Expr))
+    roots.extend(ir.flag_leaves)
     order = E.topo(roots)
     ids = {e._id: i for i, e in enumerate(order)}
     desc = {
@@ -243,4 +369,8 @@ def ir_fingerprint(ir: ModelIR) -> str:
         "sites": [(s.addr, s.dist.name, [ids[a._id] for a in s.args]) for s in ir.sites],
         "rets": [ids[r._id] if isinstance(r, Expr) else ("const", repr(r)) for r in ir.ret_leaves],
     }
+    if ir.dynamic:
+        desc["dynamic"] = [(ids[s.live._id] if s.live is not None else None, ids[s.scored._id] if s.scored is not None else None,
+                            s.cmask.attr["index"] if s.cmask is not None else None) for s in ir.sites]
+        desc["flags"] = [ids[f._id] for f in ir.flag_leaves]
     return hashlib.sha256(json.dumps(desc, default=str).encode()).hexdigest()[:16]

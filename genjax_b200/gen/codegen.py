@@ -319,8 +319,25 @@ class _Emitter:
         for a in s.args:
             self.emit_expr(a)
         fl = f"FL({j})"
-        need = f"(need_score || ({fl} & GJB_SITE_WEIGHT))"
-        self.w(f"// site {j} {'/'.join(map(str, s.addr))!r}: {d.name}")
+        samp, wt = f"({fl} & GJB_SITE_SAMPLE)", f"({fl} & GJB_SITE_WEIGHT)"
+        if s.cmask is not None:
+            # Mask-ed constraint (distribution.py:129-142): per particle, bit 0 = take the supplied value, else draw one;
+            # bit 1 = keep this site out of the weight
+            self.emit_expr(s.cmask)
+            cm = self.ref(s.cmask)
+            samp = f"(({fl} & GJB_SITE_SAMPLE) || !({cm} & 1))"
+            wt = f"(({fl} & GJB_SITE_WEIGHT) && !({cm} & 2))"
+        gates = []
+        for pred in (s.live, s.scored):
+            if pred is not None:
+                self.emit_expr(pred)
+                gates.append(f"({self.ref(pred)} != 0)")
+        live = gates[0] if s.live is not None else None
+        need = f"(need_score || {wt})"
+        if gates:
+            need = f"({need} && {' && '.join(gates)})"
+        self.w(f"// site {j} {'/'.join(map(str, s.addr))!r}: {d.name}"
+               + (" [dynamic: exists / is scored only where its Switch branch / Mask flag holds]" if gates else ""))
         if not d.vector:
             vt = "int" if s.value.dtype == I32 else "float"
             if d.name == "categorical":
@@ -329,21 +346,25 @@ class _Emitter:
             else:
                 a = [self.ref(x) for x in s.args]
             self.w(f"{vt} s{j};")
-            self.w(f"if ({fl} & GJB_SITE_SAMPLE) s{j} = {d.emit_sample(j, a, self)}; else s{j} = in_s{j};")
+            self.w(f"if {samp} s{j} = {d.emit_sample(j, a, self)}; else s{j} = in_s{j};")
+            if live:
+                self.w(f"if (!{live}) s{j} = 0;")
             if d.name == "normal":
                 inv, lc = self.normal_consts(j, s.args[1])
                 lp = f"gjb::Normal::logpdf_r(s{j}, {a[0]}, {inv}, {lc})"
             else:
                 lp = d.emit_logpdf(f"s{j}", a, self)
-            self.w(f"if {need} {{ const float lp = {lp}; score += lp; if ({fl} & GJB_SITE_WEIGHT) weight += lp; }}")
+            self.w(f"if {need} {{ const float lp = {lp}; score += lp; if {wt} weight += lp; }}")
             return
         if d.name == "gmm_diag":
             logits, mu, sigma = s.args
             K, D = mu.shape
             a = f"{self.ref(logits)}, {self.ref(mu)}, {self.ref(sigma)}"
             self.w(f"float s{j}[{D}];")
-            self.w(f"if ({fl} & GJB_SITE_SAMPLE) gjb::GmmDiag::sample<{K}, {D}>(rng, {j + 1}u, {a}, s{j}); else {{ for (int k = 0; k < {D}; ++k) s{j}[k] = in_s{j}[k]; }}")
-            self.w(f"if {need} {{ const float lp = gjb::GmmDiag::logpdf<{K}, {D}>(s{j}, {a}); score += lp; if ({fl} & GJB_SITE_WEIGHT) weight += lp; }}")
+            self.w(f"if {samp} gjb::GmmDiag::sample<{K}, {D}>(rng, {j + 1}u, {a}, s{j}); else {{ for (int k = 0; k < {D}; ++k) s{j}[k] = in_s{j}[k]; }}")
+            if live:
+                self.w(f"if (!{live}) {{ for (int k = 0; k < {D}; ++k) s{j}[k] = 0.0f; }}")
+            self.w(f"if {need} {{ const float lp = gjb::GmmDiag::logpdf<{K}, {D}>(s{j}, {a}); score += lp; if {wt} weight += lp; }}")
             return
         if d.name == "mv_normal":
             loc, cov = s.args
@@ -353,8 +374,10 @@ class _Emitter:
             self.uni_init.append(f"  U.ld{j} = gjb::MvNormal::cholesky<{D}>({self.ref(cov)}, U.L{j});")
             lc = self.ref(loc)
             self.w(f"float s{j}[{D}];")
-            self.w(f"if ({fl} & GJB_SITE_SAMPLE) gjb::MvNormal::sample<{D}>(rng, {j + 1}u, {lc}, U.L{j}, s{j}); else {{ for (int k = 0; k < {D}; ++k) s{j}[k] = in_s{j}[k]; }}")
-            self.w(f"if {need} {{ const float lp = gjb::MvNormal::logpdf<{D}>(s{j}, {lc}, U.L{j}, U.ld{j}); score += lp; if ({fl} & GJB_SITE_WEIGHT) weight += lp; }}")
+            self.w(f"if {samp} gjb::MvNormal::sample<{D}>(rng, {j + 1}u, {lc}, U.L{j}, s{j}); else {{ for (int k = 0; k < {D}; ++k) s{j}[k] = in_s{j}[k]; }}")
+            if live:
+                self.w(f"if (!{live}) {{ for (int k = 0; k < {D}; ++k) s{j}[k] = 0.0f; }}")
+            self.w(f"if {need} {{ const float lp = gjb::MvNormal::logpdf<{D}>(s{j}, {lc}, U.L{j}, U.ld{j}); score += lp; if {wt} weight += lp; }}")
             return
         if d.name != "mv_normal_diag":
             raise NotImplementedError(d.name)
@@ -363,15 +386,19 @@ class _Emitter:
         inv, lc = self.normal_consts(j, scale, vec_width=D)
         if self.group:
             self.w(f"gjb::V4 s{j};")
-            self.w(f"if ({fl} & GJB_SITE_SAMPLE) s{j} = gjb::mvn_diag_sample(rng, {j + 1}u, (uint32_t)lane, {self.as_v4(loc)}, {self.as_v4(scale)}); else s{j} = in_s{j};")
-            self.w(f"if {need} {{ const float lp = gjb::mvn_diag_logpdf4_r(s{j}, {self.as_v4(loc)}, {inv}, {lc}); vscore += lp; if ({fl} & GJB_SITE_WEIGHT) vweight += lp; }}")
+            self.w(f"if {samp} s{j} = gjb::mvn_diag_sample(rng, {j + 1}u, (uint32_t)lane, {self.as_v4(loc)}, {self.as_v4(scale)}); else s{j} = in_s{j};")
+            if live:
+                self.w(f"if (!{live}) s{j} = gjb::v4_splat(0.0f);")
+            self.w(f"if {need} {{ const float lp = gjb::mvn_diag_logpdf4_r(s{j}, {self.as_v4(loc)}, {inv}, {lc}); vscore += lp; if {wt} vweight += lp; }}")
         else:
             self.w(f"float s{j}[{D}];")
-            self.w(f"if ({fl} & GJB_SITE_SAMPLE) {{")
+            self.w(f"if {samp} {{")
             self.w(f"  for (int c = 0; c < {(D + 3) // 4}; ++c) {{ const float4 z = gjb::normal4(rng, {j + 1}u, (uint32_t)c); const float zz[4] = {{z.x, z.y, z.z, z.w}};")
             self.w(f"    for (int t = 0; t < 4; ++t) {{ const int k = 4 * c + t; if (k < {D}) s{j}[k] = {self.elem_ref(loc, 'k')} + {self.elem_ref(scale, 'k')} * zz[t]; }} }}")
             self.w(f"}} else {{ for (int k = 0; k < {D}; ++k) s{j}[k] = in_s{j}[k]; }}")
-            self.w(f"if {need} {{ float lp = -{lc}; for (int k = 0; k < {D}; ++k) {{ const float z = s{j}[k] * {inv}[k] - {self.elem_ref(loc, 'k')} * {inv}[k]; lp -= 0.5f * (z * z); }} score += lp; if ({fl} & GJB_SITE_WEIGHT) weight += lp; }}")
+            if live:
+                self.w(f"if (!{live}) {{ for (int k = 0; k < {D}; ++k) s{j}[k] = 0.0f; }}")
+            self.w(f"if {need} {{ float lp = -{lc}; for (int k = 0; k < {D}; ++k) {{ const float z = s{j}[k] * {inv}[k] - {self.elem_ref(loc, 'k')} * {inv}[k]; lp -= 0.5f * (z * z); }} score += lp; if {wt} weight += lp; }}")
 
 
 def _info_json(ir: ModelIR, mapping: str, G: int, pf_step: bool = False) -> str:
@@ -428,12 +455,14 @@ class _Generator:
         self.em = _Emitter(ir, group=self.group)
         self.ns = len(ir.sites)
         self.na = max(len(ir.args), 1)
-        self.nr = max(len(ir.ret_leaves), 1)
+        # what the model kernels write through ret_out: the return leaves, then the validity flags of dynamic sites
+        self.all_rets = list(ir.ret_leaves) + list(ir.flag_leaves)
+        self.nr = max(len(self.all_rets), 1)
         em = self.em
         for s in ir.sites:
             em.emit_site(s)
         self.ret_names = []
-        for r in ir.ret_leaves:
+        for r in self.all_rets:
             if isinstance(r, Expr):
                 em.emit_expr(r)
                 if self.group:
@@ -541,7 +570,7 @@ class _Generator:
                 bind.append(f"      const float* in_s{j} = p[u].s{j};")
                 save.append(f"      for (int k = 0; k < {D}; ++k) p[u].s{j}[k] = s{j}[k];")
                 post.append(f"    if (io.site_out[{j}]) {{ for (int u = lo; u < hi; ++u) for (int k = 0; k < {D}; ++k) reinterpret_cast<float*>(io.site_out[{j}])[(i0 + u) * {D} + k] = p[u].s{j}[k]; }}")
-        for k, r in enumerate(ir.ret_leaves):
+        for k, r in enumerate(self.all_rets):
             is_vec = isinstance(r, Expr) and r.ndim == 1
             is_int = isinstance(r, Expr) and r.dtype == I32
             if is_vec:
@@ -577,7 +606,8 @@ class _Generator:
                 qrng_decl.append(f"  float4 Z{j};")
                 qrng_fill.append(f"  R.Z{j} = make_float4(0.f, 0.f, 0.f, 0.f);")
                 rngpre.append(f"    const float4& Z{j} = R.Z{j}; (void)Z{j};")
-            qrng_fill.append(f"  if (FL({j}) & GJB_SITE_SAMPLE) {{ R.W{j} = gjb::quad_words(key0, key1, quad, {j + 1}u);"
+            draw_if = "true" if s.cmask is not None else f"FL({j}) & GJB_SITE_SAMPLE"
+            qrng_fill.append(f"  if ({draw_if}) {{ R.W{j} = gjb::quad_words(key0, key1, quad, {j + 1}u);"
                              + (f" R.Z{j} = gjb::normal4_of(R.W{j});" if kind == "normal" else "") + " }")
         if n_q == 0:
             qrng_decl.append("  int unused;")
@@ -677,13 +707,14 @@ class _Generator:
                     pre.append(f"      uint4 W{j} = make_uint4(0u, 0u, 0u, 0u); (void)W{j};")
                     if kind == "normal":
                         pre.append(f"      float4 Z{j} = make_float4(0.f, 0.f, 0.f, 0.f); (void)Z{j};")
-                    pre.append(f"      if (FL({j}) & GJB_SITE_SAMPLE) {{ W{j} = gjb::quad_words(key0, key1, (idx_offset + (uint64_t)i) >> 2, {j + 1}u);"
+                    draw_if = "true" if s.cmask is not None else f"FL({j}) & GJB_SITE_SAMPLE"
+                    pre.append(f"      if ({draw_if}) {{ W{j} = gjb::quad_words(key0, key1, (idx_offset + (uint64_t)i) >> 2, {j + 1}u);"
                                + (f" Z{j} = gjb::normal4_of(W{j});" if kind == "normal" else "") + " }")
             else:
                 pre.append(f"      gjb::V4 in_s{j} = gjb::v4_splat(0.0f);")
                 pre.append(f"      if (!(FL({j}) & GJB_SITE_SAMPLE) && valid) in_s{j} = gjb::v4_ldg(reinterpret_cast<const float*>(io.site_in[{j}]) + ((FL({j}) & GJB_SITE_BCAST) ? 0 : i * {D}) + 4 * lane);")
                 post.append(f"      if (io.site_out[{j}] && valid) *reinterpret_cast<float4*>(reinterpret_cast<float*>(io.site_out[{j}]) + i * {D} + 4 * lane) = gjb::v4_to(s{j});")
-        for k, r in enumerate(ir.ret_leaves):
+        for k, r in enumerate(self.all_rets):
             if isinstance(r, Expr) and r.ndim == 1:
                 post.append(f"      if (io.ret_out[{k}] && valid) *reinterpret_cast<float4*>(reinterpret_cast<float*>(io.ret_out[{k}]) + i * {D} + 4 * lane) = gjb::v4_to({self.ret_names[k]});")
             else:

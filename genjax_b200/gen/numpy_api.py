@@ -67,15 +67,41 @@ def sum(x, axis=None):  # noqa: A001
     return _torch.sum(_torch.as_tensor(x)) if axis is None else _torch.sum(_torch.as_tensor(x), dim=axis)
 
 
+class _ScalarType:
+    """``jnp.int32`` / ``jnp.float32``: a dtype that also converts when called (``jnp.int32(flag)`` on a traced value)."""
+
+    def __init__(self, name: str, torch_dtype):
+        self.name, self.torch = name, torch_dtype
+
+    def __call__(self, x):
+        if isinstance(x, _Expr):
+            return _E.cast(x, self.name)
+        if isinstance(x, _torch.Tensor):
+            return x.to(self.torch)
+        return int(x) if self.name == "int32" else float(x)
+
+    def __repr__(self):
+        return self.name
+
+    def __eq__(self, other):
+        return other is self or other == self.torch
+
+    __hash__ = object.__hash__
+
+
+def _tdt(dtype):
+    return getattr(dtype, "torch", dtype)
+
+
 def array(x, dtype=None):
     if isinstance(x, _Expr):
-        return x
-    return _torch.as_tensor(x, dtype=dtype)
+        return x if dtype is None else _E.cast(x, str(dtype))
+    return _torch.as_tensor(x, dtype=_tdt(dtype))
 
 
 asarray = array
-float32 = _torch.float32
-int32 = _torch.int32
+float32 = _ScalarType("float32", _torch.float32)
+int32 = _ScalarType("int32", _torch.int32)
 pi = _math.pi
 inf = _math.inf
 
@@ -162,15 +188,15 @@ def logical_not(a):
 
 
 def zeros(shape, dtype=None):
-    return _torch.zeros(shape, dtype=dtype or _torch.float32)
+    return _torch.zeros(shape, dtype=_tdt(dtype) or _torch.float32)
 
 
 def ones(shape, dtype=None):
-    return _torch.ones(shape, dtype=dtype or _torch.float32)
+    return _torch.ones(shape, dtype=_tdt(dtype) or _torch.float32)
 
 
 def arange(*args, dtype=None):
-    return _torch.arange(*args, dtype=dtype)
+    return _torch.arange(*args, dtype=_tdt(dtype))
 
 
 e = _math.e

@@ -24,6 +24,7 @@ import torch
 
 from ..core.choice_map import ChoiceMap, Selection
 from ..core.key import KeyBatch, PRNGKey, lanes_of
+from ..core.mask import Mask
 from ..runtime import build, cabi
 from . import capture as cap
 from . import codegen
@@ -68,6 +69,8 @@ def _mark(tree, axes):
     """Wrap leaves with ``Batched`` where the in_axes tree says 0."""
     if isinstance(tree, ChoiceMap):
         def wrap(v):
+            if isinstance(v, Mask):  # a masked constraint: value and flag both carry the particle axis
+                return Mask(wrap(v.value), v.flag)
             if isinstance(v, torch.Tensor) and v.ndim == 0:
                 return v  # a 0-d leaf has no particle axis: shared by all particles
             return Batched(v)
@@ -223,7 +226,8 @@ class StaticTrace(Trace):
     ``batched=False`` traces expose 0-d / event-shaped views."""
 
     def __init__(self, gen_fn, cm: CompiledModel, bound: _BoundArgs, args, n, batched, values, score, ret_leaves,
-                 bcast):
+                 bcast, flags=None):
+        self.flags = flags or {}  # site index -> int32 [n]: where a site under a Switch branch / Mask is valid
         self.gen_fn = gen_fn
         self.cm = cm
         self.bound = bound
@@ -266,13 +270,24 @@ class StaticTrace(Trace):
             v = v.reshape(ev).expand((self.n,) + ev)
         if getattr(s.dist, "bool_valued", False) and isinstance(v, torch.Tensor):
             v = v.to(torch.bool)
+        f = self.flags.get(s.index)
+        if f is not None:
+            # ``inner.get_choices().mask(check)`` (mask.py:83) / ``ChoiceMap.switch(idx, sub_chms)`` (switch.py:75-78)
+            v = Mask(v, self._view(f).to(torch.bool))
         return v
 
     def get_choices(self) -> ChoiceMap:
-        chm = ChoiceMap.empty()
-        for s in self.cm.ir.sites:
-            chm = chm | ChoiceMap.entry(self._site_value(s), *s.addr)
-        return chm
+        return _choices_from_sites(self, self.cm.ir.sites)
+
+    @property
+    def inner(self):
+        """``MaskTrace.inner`` (mask.py:55): the trace of the masked callee -- the same choices, scored without the mask."""
+        mc = getattr(self.gen_fn, "_mask_of", None)
+        if mc is None:
+            raise AttributeError("inner")
+        if getattr(self, "_inner", None) is None:
+            self._inner = mc._inner_trace(self)
+        return self._inner
 
     def get_subtrace(self, *addr):
         """``tr.get_subtrace("x")`` / ``tr.get_subtrace("f", "x")`` (generative_function.py:141-175,
@@ -318,7 +333,20 @@ class StaticTrace(Trace):
         rets = [g(r, False) for r in self.ret_leaves]
         args = _take_args(self.args, sel)
         return StaticTrace(self.gen_fn, self.cm, None, args, int(sel.numel()), out_batched, values,
-                           g(self.score, False), rets, dict(self.bcast))
+                           g(self.score, False), rets, dict(self.bcast), {k: g(f, False) for k, f in self.flags.items()})
+
+
+def _choices_from_sites(trace: StaticTrace, sites) -> ChoiceMap:
+    """Choice map of ``sites``.  An address visited in several branches of one Switch holds the OR of the branches'
+    masked values (``ChoiceMap.switch``, choice_map.py ``switch``; ``Mask.__or__``, functional_types.py:309)."""
+    by_addr: dict = {}
+    for s in sites:
+        by_addr.setdefault(s.addr, []).append(trace._site_value(s))
+    chm = ChoiceMap.empty()
+    for addr, vals in by_addr.items():
+        v = vals[0] if len(vals) == 1 else Mask.or_n(*vals)
+        chm = chm | ChoiceMap.entry(v, *addr)
+    return chm
 
 
 class ZeroTrace(Trace):
@@ -510,11 +538,13 @@ class StaticGenerativeFunction(GenerativeFunction):
             return self.source(*args[0], **args[1])
         return self.source(*args)
 
-    def compiled_for(self, bound: _BoundArgs) -> CompiledModel:
-        sig = bound.signature()
+    def compiled_for(self, bound: _BoundArgs, cmask: frozenset = frozenset()) -> CompiledModel:
+        """``cmask``: addresses whose constraint is a ``Mask`` with a per-particle flag -- a variant of the model with
+        one hidden flag argument per such site (gen/capture.py ``SiteSpec.cmask``)."""
+        sig = bound.signature() + ((tuple(sorted(cmask, key=repr)),) if cmask else ())
         cm = self._cache.get(sig)
         if cm is None:
-            ir = cap.capture(self.source, self.__name__, bound.specs, bound.tree)
+            ir = cap.capture(self.source, self.__name__, bound.specs, bound.tree, cmask_addrs=cmask)
             cm = compile_ir(ir)
             self._cache[sig] = cm
         return cm
@@ -547,7 +577,7 @@ class StaticGenerativeFunction(GenerativeFunction):
     # -- engine ------------------------------------------------------------
     def _run(self, key, args, constraints: ChoiceMap | None, *, sample_addrs=None, prev: StaticTrace | None = None,
              weight_mode: str = "generate", weight_in=None, score_in=None, n=None, batched=None, want_score=True,
-             gather=None, wmax=None):
+             gather=None, wmax=None, weight_sites=None, revive=False):
         """One fused launch.  ``weight_mode``:
         "generate": weight = sum logpdf over constrained sites;
         "delta":    weight = new score - prev score (update / regenerate);
@@ -567,16 +597,62 @@ class StaticGenerativeFunction(GenerativeFunction):
         # resolve the batch size
         sizes = [s for s in (n_key if key_batched else None, bound.n_batched, n, prev.n if prev is not None and prev.batched else None) if s is not None]
         cvals = {}
+        cmasks = {}  # site index -> int32 [n] flag words of a Mask-ed constraint (see SiteSpec.cmask)
+        mask_discard = {}  # site index -> flag of an update's Mask-ed constraint (the discard is masked by it)
         for s in ir.sites:
             sub = constraints.get_submap(*s.addr)
             if sub.has_value():
                 v = sub.get_value()
+                if isinstance(v, Batched) and isinstance(v.value, Mask):
+                    v = Mask(Batched(v.value.value), v.value.flag)
+                if isinstance(v, Mask):
+                    # distribution.py:129-142 (generate) / :190-226 (update): where the flag holds the site is
+                    # constrained, elsewhere it is drawn (generate) or keeps its value (update)
+                    flag, v = v.primal_flag(), v.value
+                    if key is None and prev is None:
+                        pass  # assess scores the wrapped value whatever the flag says (distribution.py:404-417)
+                    elif isinstance(flag, bool) or (isinstance(flag, torch.Tensor) and flag.ndim == 0):
+                        if not bool(flag):
+                            continue
+                    else:
+                        f = _dev_tensor(flag, device, want_int=True)
+                        sizes.append(f.shape[0])
+                        if prev is not None and not (sample_addrs is not None and s.addr in sample_addrs):
+                            raw = v.value if isinstance(v, Batched) else v
+                            new_v = _dev_tensor(raw, device, want_int=(s.value.dtype == I32))
+                            old_v = prev.values[s.index]
+                            fb = f.to(torch.bool).reshape((-1,) + (1,) * (old_v.ndim - 1))
+                            v = Batched(torch.where(fb, new_v.expand_as(old_v) if new_v.ndim <= old_v.ndim else new_v, old_v))
+                            mask_discard[s.index] = f.to(torch.bool)
+                        else:
+                            cmasks[s.index] = torch.where(f != 0, 1, 2).to(torch.int32)
+                            if not isinstance(v, Batched):
+                                raw = _dev_tensor(v, device, want_int=(s.value.dtype == I32))
+                                if tuple(raw.shape) != (f.shape[0],) + tuple(s.value.shape):
+                                    raw = raw.expand((f.shape[0],) + tuple(raw.shape)).contiguous()
+                                v = Batched(raw)
                 if isinstance(v, Batched):
                     t = _dev_tensor(v.value, device, want_int=(s.value.dtype == I32))
                     sizes.append(t.shape[0])
                     cvals[s.index] = (t, False)
                 else:
                     cvals[s.index] = (v, True)
+        if revive and prev is not None:
+            # Switch.edit with a changed index (switch.py:226-246): a site whose branch was not the selected one has
+            # no value to keep -- it is drawn afresh where it comes alive.  (A site under BOTH a Switch and a Mask is
+            # also redrawn where only its mask was off: the two flags leave the kernel as one.)
+            for s in ir.sites:
+                if s.live is not None and s.index not in cvals and s.index in prev.flags \
+                        and not (sample_addrs is not None and s.addr in sample_addrs):
+                    if key is None:
+                        raise ValueError("an update that may change a Switch index needs a key")
+                    cmasks[s.index] = (prev.flags[s.index] != 0).to(torch.int32)
+                    cvals[s.index] = (prev.values[s.index], bool(prev.bcast[s.index]))
+        if cmasks:
+            if gather is not None:
+                raise NotImplementedError("Mask-ed constraints together with an ancestor gather")
+            cm = self.compiled_for(bound, frozenset(ir.sites[j].addr for j in cmasks))
+            ir = cm.ir
         if sizes:
             n_run = sizes[0]
             if any(x != n_run for x in sizes):
@@ -623,15 +699,23 @@ class StaticGenerativeFunction(GenerativeFunction):
                         raise ValueError(f"batched constraint at {s.addr} has shape {tuple(t.shape)}")
                 A.site_in[j] = t.data_ptr()
                 flags |= cabi.SITE_BCAST if is_b else 0
-                if weight_mode in ("generate", "delta"):
+                if weight_mode in ("generate", "delta") and (weight_sites is None or j in weight_sites):
                     flags |= cabi.SITE_WEIGHT
                 values[j], bcast[j] = t, is_b
                 keep.append(t)
+                if j in cmasks:
+                    # per particle the kernel keeps the supplied value or draws one: the outcome goes to a fresh buffer
+                    cmt = cmasks[j].contiguous()
+                    A.args[s.cmask.attr["index"]] = cmt.data_ptr()
+                    out = torch.empty((n_run,) + ev, dtype=tdt, device=device)
+                    A.site_out[j] = out.data_ptr()
+                    values[j], bcast[j] = out, False
+                    keep.append(cmt)
             elif prev is not None and not (sample_addrs is not None and s.addr in sample_addrs):
                 t = prev.values[j]
                 A.site_in[j] = t.data_ptr()
                 flags |= cabi.SITE_BCAST if prev.bcast[j] else 0
-                if weight_mode == "delta":
+                if weight_mode == "delta" or (weight_sites is not None and j in weight_sites):
                     flags |= cabi.SITE_WEIGHT
                 values[j], bcast[j] = t, prev.bcast[j]
             else:
@@ -674,8 +758,16 @@ class StaticGenerativeFunction(GenerativeFunction):
             else:
                 ret_leaves.append(r)
 
+        flag_bufs = []
+        for m in range(len(ir.flag_leaves)):
+            fb = torch.empty(n_run, dtype=torch.int32, device=device)
+            A.ret_out[len(ir.ret_leaves) + m] = fb.data_ptr()
+            flag_bufs.append(fb)
+
         cabi.check(cm.lib.gjb_model_launch(C.byref(A), cabi.stream_ptr(device)), f"gjb_model_launch({self.__name__})")
-        tr = StaticTrace(self, cm, bound, args, n_run, is_batched, values, score, ret_leaves, bcast)
+        tr = StaticTrace(self, cm, bound, args, n_run, is_batched, values, score, ret_leaves, bcast,
+                         {j: flag_bufs[m] for j, m in ir.flag_of.items()})
+        tr._mask_discard = mask_discard
         return tr, weight
 
     def _w(self, tr: StaticTrace, w):
@@ -700,21 +792,19 @@ class StaticGenerativeFunction(GenerativeFunction):
             return torch.zeros_like(trace.get_score())
         scores = self._site_scores(trace)
         tot = torch.zeros_like(trace.score)
-        for s in trace.cm.ir.sites:
-            if selection(s.addr).check():
-                tot = tot + scores[s.addr]
+        for addr in dict.fromkeys(s.addr for s in trace.cm.ir.sites):
+            if selection(addr).check():
+                tot = tot + scores[addr]
         return tot if trace.batched else tot[0]
 
     def _site_scores(self, trace: StaticTrace) -> dict:
-        """addr -> [n] logpdf: one generate launch per site with only that site weighted."""
+        """addr -> [n] logpdf: one launch per site, every value read back from the trace, only that site weighted (an
+        address visited in several Switch branches sums its sites: at most one of them is alive per particle)."""
         out = {}
-        full = _rebatch(trace)
         for s in trace.cm.ir.sites:
-            only = ChoiceMap.entry(full.get_submap(*s.addr), *s.addr)
-            rest = trace  # other sites read from the previous trace without weight
-            _, w = self._run(None, trace.args, only, prev=rest, weight_mode="generate", n=trace.n,
-                             batched=trace.batched, want_score=False)
-            out[s.addr] = w
+            _, w = self._run(None, trace.args, None, prev=trace, weight_mode="generate", weight_sites={s.index},
+                             n=trace.n, batched=trace.batched, want_score=False)
+            out[s.addr] = w if s.addr not in out else out[s.addr] + w
         return out
 
     def edit(self, key, trace: StaticTrace, request: EditRequest, argdiffs):
@@ -722,23 +812,24 @@ class StaticGenerativeFunction(GenerativeFunction):
         if new_args == () and trace.args != ():
             new_args = trace.args
         new_args = _carry_batch_marks(new_args, trace.args)
+        # a Switch index may move with the arguments OR with an upstream choice: sites of a branch that comes alive are
+        # drawn afresh (switch.py:226-246), so every edit of a model holding Switch sites runs the per-particle form
+        revive = key is not None and any(s.live is not None for s in trace.cm.ir.sites)
         if isinstance(request, Update):
             tr, w = self._run(key, new_args, _rebatch_constraint(request.constraint, trace), prev=trace,
-                              weight_mode="delta", n=trace.n, batched=trace.batched)
-            discard = ChoiceMap.empty()
-            for s in trace.cm.ir.sites:
-                if request.constraint.get_submap(*s.addr).has_value():
-                    discard = discard | ChoiceMap.entry(trace._site_value(s), *s.addr)
+                              weight_mode="delta", n=trace.n, batched=trace.batched, revive=revive)
+            discard = _choices_from_sites(trace, [s for s in trace.cm.ir.sites
+                                                  if request.constraint.get_submap(*s.addr).has_value()])
+            if tr._mask_discard:  # ``old_choices.mask(flag)`` (distribution.py:222-224)
+                flags = {trace.cm.ir.sites[j].addr: f for j, f in tr._mask_discard.items()}
+                discard = _mask_leaves(discard, flags, trace.batched)
             retdiff = Diff.unknown_change(tr.get_retval())
             return tr, self._w(tr, w), retdiff, Update(discard)
         if isinstance(request, Regenerate):
             sel = {s.addr for s in trace.cm.ir.sites if request.selection(s.addr).check()}
             tr, w = self._run(key, new_args, None, prev=trace, sample_addrs=sel, weight_mode="delta", n=trace.n,
-                              batched=trace.batched)
-            discard = ChoiceMap.empty()
-            for s in trace.cm.ir.sites:
-                if s.addr in sel:
-                    discard = discard | ChoiceMap.entry(trace._site_value(s), *s.addr)
+                              batched=trace.batched, revive=revive)
+            discard = _choices_from_sites(trace, [s for s in trace.cm.ir.sites if s.addr in sel])
             return tr, self._w(tr, w), Diff.unknown_change(tr.get_retval()), Update(discard)
         if isinstance(request, EmptyRequest):
             return request.edit(key, trace, argdiffs)
@@ -760,6 +851,17 @@ def _carry_batch_marks(new_args, old_args):
     return new_args
 
 
+def _mask_leaves(chm: ChoiceMap, flags: dict, batched: bool) -> ChoiceMap:
+    """Wrap the leaves at the addresses of ``flags`` in ``Mask(value, flag)``."""
+    out = ChoiceMap.empty()
+    for addr, v in chm.leaves():
+        f = flags.get(addr)
+        if f is not None:
+            v = Mask.build(v, f if batched else f[0])
+        out = out | ChoiceMap.entry(v, *addr)
+    return out
+
+
 def _rebatch(trace: StaticTrace) -> ChoiceMap:
     """Choice map of a trace with batched leaves marked for re-launch."""
     chm = ChoiceMap.empty()
@@ -777,6 +879,8 @@ def _rebatch_constraint(chm: ChoiceMap, trace: StaticTrace) -> ChoiceMap:
     def mark(v):
         if isinstance(v, Batched):
             return v
+        if isinstance(v, Mask):
+            return Mask(mark(v.value), v.flag)
         if isinstance(v, torch.Tensor) and v.ndim >= 1 and v.shape[0] == trace.n:
             return Batched(v)
         return v
@@ -890,10 +994,8 @@ def _edit_static_request(gf, key, trace, request: StaticRequest, argdiffs):
         sel_addrs = {s.addr for s in ir.sites if sel(s.addr).check() and not constraint.get_submap(*s.addr).has_value()}
         tr, w = gf._run(key, new_args, _rebatch_constraint(constraint, trace), prev=trace, sample_addrs=sel_addrs,
                         weight_mode="delta", n=trace.n, batched=trace.batched)
-        discard = ChoiceMap.empty()
-        for s in ir.sites:
-            if s.addr in sel_addrs or constraint.get_submap(*s.addr).has_value():
-                discard = discard | ChoiceMap.entry(trace._site_value(s), *s.addr)
+        discard = _choices_from_sites(trace, [s for s in ir.sites
+                                              if s.addr in sel_addrs or constraint.get_submap(*s.addr).has_value()])
         w, rd, b = gf._w(tr, w), Diff.unknown_change(tr.get_retval()), Update(discard)
     if weight is not None:
         w = weight + w

@@ -233,11 +233,20 @@ class EmulatedModelLib:
                 sample, logpdf = od.DISTS[s.dist.name]
             else:  # no oracle sampler: score through the symbolic log-density (gen/autodiff.py), refuse to sample
                 sample, logpdf = None, None
-            if fl & 1:
+            # dynamic structure (SiteSpec.live / scored / cmask): per-particle predicates
+            cmw = None if getattr(s, "cmask", None) is None else np.broadcast_to(np.asarray(evaluate(s.cmask, env, cache)), (n,)).astype(np.int64)
+            live = None if getattr(s, "live", None) is None else np.broadcast_to(np.asarray(evaluate(s.live, env, cache)), (n,)) != 0
+            scored = None if getattr(s, "scored", None) is None else np.broadcast_to(np.asarray(evaluate(s.scored, env, cache)), (n,)) != 0
+
+            def _draw():
                 if sample is None:
                     raise NotImplementedError(f"emulator: no oracle sampler for {s.dist.name}")
-                v = np.asarray(sample(words, idx, j + 1, *args))
-                v = np.broadcast_to(v.astype(dt), (n,) + ev).copy()
+                with np.errstate(all="ignore"):
+                    d = np.asarray(sample(words, idx, j + 1, *args))
+                return np.broadcast_to(d.astype(dt), (n,) + ev).copy()
+
+            if fl & 1:
+                v = _draw()
             else:
                 if not A.site_in[j]:
                     return -1
@@ -246,7 +255,32 @@ class EmulatedModelLib:
                     v = np.broadcast_to(v, (n,) + ev)
                 else:
                     v = _view(A.site_in[j], n * _prod(ev), dt).reshape((n,) + ev).copy()
-            if need_score or (fl & 2):
+                if cmw is not None:
+                    take = (cmw & 1).astype(bool).reshape((n,) + (1,) * len(ev))
+                    v = np.where(take, v, _draw()).astype(dt)
+            if live is not None:
+                v = np.where(live.reshape((n,) + (1,) * len(ev)), v, 0).astype(dt)
+            gate = None
+            for g_ in (live, scored):
+                if g_ is not None:
+                    gate = g_ if gate is None else (gate & g_)
+            if gate is not None or cmw is not None:  # the general (masked) accumulation
+                if need_score or (fl & 2):
+                    vv = v.astype(bool) if getattr(s.dist, "bool_valued", False) else v
+                    with np.errstate(all="ignore"):
+                        if logpdf is None:
+                            from genjax_b200.gen import autodiff as AD
+
+                            env[("site", j)] = v
+                            lp = np.broadcast_to(np.asarray(evaluate(AD.logpdf_expr(s.dist, s.value, s.args), env, {}), dtype=F32), (n,))
+                        else:
+                            lp = np.broadcast_to(np.asarray(logpdf(vv, *args), dtype=F32), (n,))
+                    on = np.ones(n, dtype=bool) if gate is None else gate
+                    score = np.where(on, (score + lp).astype(F32), score)
+                    if fl & 2:
+                        won = on if cmw is None else (on & ((cmw & 2) == 0))
+                        weight = np.where(won, (weight + lp).astype(F32), weight)
+            elif need_score or (fl & 2):
                 vv = v.astype(bool) if getattr(s.dist, "bool_valued", False) else v
                 if logpdf is None:
                     from genjax_b200.gen import autodiff as AD
@@ -262,7 +296,7 @@ class EmulatedModelLib:
             out = _view(A.site_out[j], n * _prod(ev), dt)
             if out is not None:
                 out[:] = np.ascontiguousarray(v).reshape(-1)
-        for k, r in enumerate(ir.ret_leaves):
+        for k, r in enumerate(list(ir.ret_leaves) + list(getattr(ir, "flag_leaves", []))):
             if not A.ret_out[k]:
                 continue
             val = evaluate(r, env, cache)

@@ -1,0 +1,543 @@
+"""Dynamic structure on the fused kernels: Switch / MaskCombinator / mix / or_else and Mask-ed
+constraints, against the oracle's restatement (oracle/gfi.py ``_Handler.switch`` / ``.mask``) on shared Philox lanes, and
+through the reference's own assertions (tests/generative_functions/test_switch_combinator.py, test_mask_combinator.py,
+test_mix_combinator.py, test_or_else.py)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dists as od
+from oracle import gfi as ogfi
+from oracle import rng as orng
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+def _gj():
+    import genjax_b200 as gj
+
+    return gj
+
+
+def _np(t):
+    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+def _nlp(v, mu, sd):
+    return od.DISTS["normal"][1](np.asarray(v, dtype=F32), F32(mu), F32(sd))
+
+
+# ------------------------------------------------------------------ Switch inside @gen, per-particle index
+
+
+def _regime_models():
+    gj = _gj()
+    jnp = gj.numpy
+
+    @gj.gen
+    def calm(x):
+        y = gj.normal(x, 0.5) @ "y"
+        return y
+
+    @gj.gen
+    def wild(x):
+        s = gj.exponential(2.0) @ "s"
+        y = gj.normal(x + 1.0, 1.0 + s) @ "y"
+        return y * 2.0
+
+    @gj.gen
+    def model(x):
+        b = gj.flip(0.3) @ "b"
+        r = calm.switch(wild)(jnp.int32(b), (x,), (x,)) @ "r"
+        z = gj.normal(r, 0.1) @ "z"
+        return r + z
+
+    def o_calm(h, x):
+        return h.normal(("r", "y"), x, F32(0.5))
+
+    def o_wild(h, x):
+        s = h.exponential(("r", "s"), F32(2.0))
+        y = h.normal(("r", "y"), (x + F32(1.0)).astype(F32), (F32(1.0) + s).astype(F32))
+        return (y * F32(2.0)).astype(F32)
+
+    def o_model(h, x):
+        b = h.flip("b", F32(0.3))
+        r = h.switch(b.astype(np.int32), [o_calm, o_wild], [(x,), (x,)])
+        z = h.normal("z", r, F32(0.1))
+        return (r + z).astype(F32)
+
+    return model, o_model
+
+
+def test_switch_in_gen_fn_matches_oracle(device):
+    """simulate / importance / update over a KeyBatch with the branch index drawn PER PARTICLE: values (zeros in the
+    unselected branch), validity flags, score, weight and return value against the oracle."""
+    gj = _gj()
+    model, o_model = _regime_models()
+    n = 20_001
+    x = torch.linspace(-1.0, 1.0, n)
+    kb = gj.split(gj.key(7), n)
+    okb = orng.split(orng.key(7), n)
+    xs = x.numpy().astype(F32)
+
+    tr = gj.vmap(model.simulate, in_axes=(0, (0,)))(kb, (x,))
+    otr = ogfi.simulate(o_model, okb, (xs,))
+    chm = tr.get_choices()
+    b = _np(chm["b"]).astype(bool)
+    assert (b != otr.choices["b"].astype(bool)).mean() < 1e-4
+    same = b == otr.choices["b"].astype(bool)
+    y = chm["r", "y"]
+    assert isinstance(y, gj.Mask) and bool(_np(y.flag).all())  # "y" is visited by both branches: always valid
+    s = chm["r", "s"]
+    assert isinstance(s, gj.Mask)
+    np.testing.assert_array_equal(_np(s.flag), b)  # "s" exists in the second branch only
+    assert (_np(s.value)[~b] == 0).all()  # the unselected branch reads back zeros (switch.py:171-180)
+    np.testing.assert_allclose(_np(y.value)[same], otr.choices[("r", "y")][same], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(_np(s.value)[same], otr.choices[("r", "s")][same], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(_np(tr.get_score())[same], otr.get_score()[same], rtol=3e-5, atol=3e-5)
+    np.testing.assert_allclose(_np(tr.get_retval())[same], otr.get_retval()[same], rtol=3e-5, atol=3e-5)
+    assert 0.27 < b.mean() < 0.33
+
+    # importance: constrain the shared address and the branch flag per particle
+    bc = (torch.arange(n) % 3 == 0)
+    yc = torch.full((n,), 0.25)
+    cons = gj.C["b"].set(bc) | gj.C["r", "y"].set(yc)
+    tr2, w = gj.vmap(model.importance, in_axes=(0, 0, (0,)))(kb, cons, (x,))
+    otr2, ow = ogfi.generate(o_model, okb, {"b": bc.numpy().astype(np.int32), ("r", "y"): yc.numpy()}, (xs,))
+    np.testing.assert_allclose(_np(w), ow, rtol=3e-5, atol=3e-5)
+    np.testing.assert_allclose(_np(tr2.get_score()), otr2.get_score(), rtol=3e-5, atol=3e-5)
+    np.testing.assert_array_equal(_np(tr2.get_choices()["r", "s"].flag), bc.numpy())
+
+    # assess(choices of a trace) == its score (test_or_else.py:28-55 for the same identity)
+    score, ret = gj.vmap(model.assess, in_axes=(0, (0,)))(tr2.get_choices(), (x,))
+    np.testing.assert_allclose(_np(score), _np(tr2.get_score()), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(_np(ret), _np(tr2.get_retval()), rtol=1e-6, atol=1e-6)
+
+    # update that flips the index through an upstream choice: the branch that comes alive is drawn afresh, the weight is
+    # new score - old score plus nothing else (switch.py:226-246, 299-300)
+    flip = gj.C["b"].set(~bc)
+    ku = gj.split(gj.key(8), n)
+    tr3, w3, _, disc = tr2.update(ku, flip)
+    otr3, ow3, _ = ogfi.update(o_model, orng.split(orng.key(8), n), otr2, {"b": (~bc).numpy().astype(np.int32)})
+    np.testing.assert_allclose(_np(w3), ow3, rtol=5e-5, atol=5e-5)
+    np.testing.assert_allclose(_np(tr3.get_score()), _np(tr2.get_score()) + _np(w3), rtol=5e-5, atol=5e-5)
+    np.testing.assert_array_equal(_np(tr3.get_choices()["r", "s"].flag), (~bc).numpy())
+    s3, os3 = _np(tr3.get_choices()["r", "s"].value), otr3.choices[("r", "s")]
+    np.testing.assert_allclose(s3, os3, rtol=2e-5, atol=2e-5)
+    assert "b" in disc
+
+
+def test_switch_combinator_simulate_in_gen_fn(device):
+    """test_switch_combinator.py:28-44."""
+    gj = _gj()
+    jnp = gj.numpy
+
+    @gj.gen
+    def f():
+        x = gj.normal(0.0, 1.0) @ "x"
+        return x
+
+    @gj.gen
+    def model():
+        b = gj.flip(0.5) @ "b"
+        s = f.switch(f)(jnp.int32(b), (), ()) @ "s"
+        return s
+
+    tr = model.simulate(gj.key(314159), ())
+    assert tr.get_retval() == tr.get_choices()["s", "x"].unmask()
+
+
+def _two_branches():
+    gj = _gj()
+
+    @gj.gen
+    def simple_normal():
+        _y1 = gj.normal(0.0, 1.0) @ "y1"
+        _y2 = gj.normal(0.0, 1.0) @ "y2"
+
+    @gj.gen
+    def simple_flip():
+        _y3 = gj.flip(0.3) @ "y3"
+
+    return simple_normal.switch(simple_flip)
+
+
+def test_switch_combinator_simulate_and_choice_map(device):
+    """test_switch_combinator.py:46-101."""
+    gj = _gj()
+    sw = _two_branches()
+    key, sub = gj.split(gj.key(314159), 2)
+    tr = sw.simulate(sub, (0, (), ()))
+    chm = tr.get_choices()
+    v1, v2 = chm["y1"], chm["y2"]
+    s1, _ = gj.normal.assess(gj.C.v(v1), (0.0, 1.0))
+    s2, _ = gj.normal.assess(gj.C.v(v2), (0.0, 1.0))
+    assert tr.get_score().item() == pytest.approx((s1 + s2).item(), rel=1e-6)
+    assert tr.get_args() == (0, (), ())
+    assert "y1" in chm and "y2" in chm and "y3" in chm
+    assert chm["y3"] == gj.Mask(torch.tensor(False), torch.tensor(False))
+    tr = sw.simulate(key, (1, (), ()))
+    b = tr.get_choices().get_submap("y3")
+    fs, _ = gj.flip.assess(b, (0.3,))
+    assert tr.get_score().item() == pytest.approx(fs.item(), rel=1e-6)
+    assert tr.get_args()[0] == 1
+
+
+def test_switch_combinator_importance(device):
+    """test_switch_combinator.py:103-150."""
+    gj = _gj()
+    sw = _two_branches()
+    k = gj.split(gj.key(314159), 3)
+    tr, w = sw.importance(k[0], gj.C.n(), (0, (), ()))
+    v1, v2 = tr.get_choices().get_submap("y1"), tr.get_choices().get_submap("y2")
+    s1, _ = gj.normal.assess(v1, (0.0, 1.0))
+    s2, _ = gj.normal.assess(v2, (0.0, 1.0))
+    assert tr.get_score().item() == pytest.approx((s1 + s2).item(), rel=1e-6)
+    assert w.item() == 0.0
+    tr, w = sw.importance(k[1], gj.C.n(), (1, (), ()))
+    fs, _ = gj.flip.assess(tr.get_choices().get_submap("y3"), (0.3,))
+    assert tr.get_score().item() == pytest.approx(fs.item(), rel=1e-6) and w.item() == 0.0
+    tr, w = sw.importance(k[2], gj.C["y3"].set(1), (1, (), ()))
+    fs, _ = gj.flip.assess(tr.get_choices().get_submap("y3"), (0.3,))
+    assert tr.get_score().item() == pytest.approx(fs.item(), rel=1e-6)
+    assert w.item() == tr.get_score().item() == pytest.approx(math.log(0.3), rel=1e-6)
+
+
+def test_switch_combinator_update(device):
+    """test_switch_combinator.py:152-217: no-change update keeps everything; an index change re-scores under the new
+    branch with weight = new score - old score."""
+    gj = _gj()
+
+    @gj.gen
+    def simple_normal():
+        _y1 = gj.normal(0.0, 1.0) @ "y1"
+        _y2 = gj.normal(0.0, 1.0) @ "y2"
+
+    sw = simple_normal.switch()
+    k = gj.split(gj.key(314159), 4)
+    tr = sw.simulate(k[0], (0, ()))
+    v1, v2, score = tr.get_choices()["y1"], tr.get_choices()["y2"], tr.get_score()
+    tr2, _, _, _ = sw.update(k[1], tr, gj.C.n(), (gj.Diff.no_change(0), ()))
+    assert score == tr2.get_score()
+    assert v1 == tr2.get_choices()["y1"] and v2 == tr2.get_choices()["y2"]
+
+    @gj.gen
+    def regular():
+        return gj.normal(0.0, 1.0) @ "x"
+
+    @gj.gen
+    def outlier():
+        return gj.normal(0.0, 10.0) @ "x"
+
+    sw = regular.switch(outlier)
+    tr, wt = sw.importance(k[2], gj.C["x"].set(2.0), (0, (), ()))
+    assert tr.get_args()[0] == 0
+    assert tr.get_score().item() == pytest.approx(float(_nlp(2.0, 0.0, 1.0)), rel=1e-6)
+    assert wt.item() == tr.get_score().item()
+    new_tr, new_wt, _, _ = sw.update(k[3], tr, gj.C.n(), (gj.Diff.unknown_change(1), (), ()))
+    assert new_tr.get_args()[0] == 1
+    assert new_tr.get_score().item() != tr.get_score().item()
+    assert tr.get_score().item() + new_wt.item() == pytest.approx(new_tr.get_score().item(), rel=1e-5)
+
+
+def test_switch_vectorized_access_empty_branch_and_return_types(device):
+    """test_switch_combinator.py:219-276 and :278-300."""
+    gj = _gj()
+    jnp = gj.numpy
+
+    @gj.gen
+    def f1():
+        return gj.normal(0.0, 1.0) @ "y"
+
+    @gj.gen
+    def f2():
+        return gj.normal(0.0, 2.0) @ "y"
+
+    s = f1.switch(f2)
+    tr = s.simulate(gj.split(gj.key(17), 3), (0, (), ()))
+    assert tuple(tr.get_choices()["y"].unmask().shape) == (3,)
+
+    @gj.gen
+    def f():
+        return gj.normal(0.0, 1.0) @ "x"
+
+    @gj.gen
+    def empty():
+        return jnp.asarray(0.0)
+
+    @gj.gen
+    def model():
+        b = gj.flip(0.5) @ "b"
+        return f.switch(empty)(jnp.int32(b), (), ()) @ "s"
+
+    tr, _ = model.importance(gj.key(314159), gj.C["b"].set(1), ())
+    assert 0.0 == tr.get_retval()
+
+    @gj.gen
+    def identity(x):
+        return jnp.asarray(x)
+
+    @gj.gen
+    def bool_branch(_):
+        return jnp.asarray(True)
+
+    sm = gj.switch(identity, bool_branch)
+    out = sm(1, (10,), (10,))(gj.key(0))
+    assert out.item() == 1 and out.dtype == torch.int32
+
+    @gj.gen
+    def three(x):
+        return jnp.ones(3)
+
+    @gj.gen
+    def four(_):
+        return jnp.ones(4)
+
+    with pytest.raises(ValueError, match="Incompatible shapes for broadcasting"):
+        three.switch(four)(0, (10,), (10,))(gj.key(0))
+
+
+# ---------------------------------------------------------------------------- MaskCombinator
+
+
+def _masked_model():
+    gj = _gj()
+
+    @gj.mask
+    @gj.gen
+    def model(x):
+        z = gj.normal(x, 1.0) @ "z"
+        return z
+
+    return model
+
+
+def test_mask_combinator_simulate_assess_importance(device):
+    """test_mask_combinator.py:39-63."""
+    gj = _gj()
+    model = _masked_model()
+    key = gj.key(314159)
+    tr = model.simulate(key, (True, -4.0))
+    assert tr.get_score() == tr.inner.get_score()
+    assert tr.get_retval() == gj.Mask(tr.inner.get_retval(), torch.tensor(True))
+    tr = model.simulate(key, (False, -4.0))
+    assert tr.get_score() == 0.0
+    assert tr.get_retval() == gj.Mask(tr.inner.get_retval(), torch.tensor(False))
+    assert tr.inner.get_score().item() != 0.0  # the callee ran: only its score is dropped
+
+    tr = model.simulate(key, (False, 2.0))
+    assert tr.get_score() == 0.0 and not tr.get_retval().flag
+    score, retval = model.assess(tr.get_choices(), tr.get_args())
+    assert score == 0.0 and not retval.flag
+    _, w = model.importance(key, gj.C["z"].set(-2.0), tr.get_args())
+    assert w == 0.0
+
+
+def test_mask_combinator_update_weights(device):
+    """test_mask_combinator.py:65-103: the four transitions of the check argument."""
+    gj = _gj()
+    model = _masked_model()
+    key = gj.key(314159)
+    Diff = gj.Diff
+    tr = model.simulate(key, (True, 2.0))
+    w = tr.update(key, gj.C.n(), (Diff.unknown_change(True), Diff.no_change(2.0)))[1]
+    assert w == tr.inner.update(key, gj.C.n())[1] and w == 0.0
+    w = tr.update(key, gj.C.n(), (Diff.unknown_change(False), Diff.no_change(2.0)))[1]
+    assert w == -tr.get_score()
+
+    tr = model.simulate(key, (False, 2.0))
+    w = tr.update(key, gj.C.n(), (Diff.unknown_change(True), Diff.no_change(2.0)))[1]
+    assert w == tr.inner.update(key, gj.C.n())[1] + tr.inner.get_score()
+    assert w == tr.inner.update(key, gj.C.n())[0].get_score()
+    w = tr.update(key, gj.C.n(), (Diff.unknown_change(False), Diff.no_change(2.0)))[1]
+    assert w == 0.0 and w == tr.get_score()
+
+
+def test_mask_combinator_batched_flags_match_oracle(device):
+    """A flag per particle (the vmapped use, test_mask_combinator.py:105-131 ``init.mask().vmap``): score = flag *
+    inner score, values drawn either way, against the oracle."""
+    gj = _gj()
+
+    @gj.gen
+    def model(c, x):
+        a = gj.normal(x, 1.0) @ "a"
+        m = gj.normal.mask()(c, a, 0.5) @ "m"
+        return m
+
+    def o_model(h, c, x):
+        a = h.normal("a", x, F32(1.0))
+        v, flag = h.mask(c, lambda hh: hh.normal("m", a, F32(0.5)))
+        return v, flag
+
+    n = 10_007
+    c = (torch.arange(n) % 2 == 0)
+    x = torch.linspace(0.0, 1.0, n)
+    tr = gj.vmap(model.simulate, in_axes=(0, (0, 0)))(gj.split(gj.key(3), n), (c, x))
+    otr = ogfi.simulate(o_model, orng.split(orng.key(3), n), (c.numpy(), x.numpy().astype(F32)))
+    m = tr.get_choices()["m"]
+    np.testing.assert_array_equal(_np(m.flag), c.numpy())
+    np.testing.assert_allclose(_np(m.value), otr.choices["m"], rtol=2e-5, atol=2e-5)  # drawn where masked too
+    np.testing.assert_allclose(_np(tr.get_score()), otr.get_score(), rtol=3e-5, atol=3e-5)
+    rv = tr.get_retval()
+    assert isinstance(rv, gj.Mask)
+    np.testing.assert_array_equal(_np(rv.flag), c.numpy())
+    lp_a = _nlp(_np(tr.get_choices()["a"]), x.numpy(), 1.0)
+    lp_m = _nlp(_np(m.value), _np(tr.get_choices()["a"]), 0.5)
+    np.testing.assert_allclose(_np(tr.get_score()), lp_a + c.numpy() * lp_m, rtol=3e-5, atol=3e-5)
+
+
+def test_mask_fails_with_vector_mask(device):
+    """test_mask_combinator.py:226-244."""
+    gj = _gj()
+
+    @gj.gen
+    def model():
+        return gj.normal(0.0, 1.0) @ "x"
+
+    with pytest.raises(TypeError):
+        model.mask().simulate(gj.key(1), (torch.tensor([True, True, False]),))
+
+
+# ---------------------------------------------------------------- Mask-ed constraints (distribution.py:129-142)
+
+
+def test_masked_constraint_generate_and_update_match_oracle(device):
+    """A ``Mask(value, flag)`` constraint: constrained (and weighted) where the flag holds, drawn elsewhere; in an update
+    the new value where the flag holds, the old one elsewhere, discard masked by the same flag."""
+    gj = _gj()
+
+    @gj.gen
+    def model(mu):
+        x = gj.normal(mu, 2.0) @ "x"
+        y = gj.normal(x, 0.5) @ "y"
+        return y
+
+    def o_model(h, mu):
+        x = h.normal("x", mu, F32(2.0))
+        return h.normal("y", x, F32(0.5))
+
+    n = 9_001
+    flag = torch.arange(n) % 4 != 0
+    xc = torch.linspace(-2.0, 2.0, n)
+    kb, okb = gj.split(gj.key(21), n), orng.split(orng.key(21), n)
+    cons = gj.C["x"].set(gj.Mask(xc, flag))
+    tr, w = model.importance(kb, cons, (0.5,))
+    otr, ow = ogfi.generate(o_model, okb, {"x": ("mask", xc.numpy(), flag.numpy())}, (F32(0.5),))
+    np.testing.assert_allclose(_np(tr.get_choices()["x"]), otr.choices["x"], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(_np(w), ow, rtol=3e-5, atol=3e-5)
+    f = flag.numpy()
+    np.testing.assert_array_equal(_np(tr.get_choices()["x"])[f], xc.numpy()[f])
+    assert (_np(w)[~f] == 0).all()
+    np.testing.assert_allclose(_np(w)[f], _nlp(xc.numpy()[f], 0.5, 2.0), rtol=3e-5, atol=3e-5)
+
+    new_x = torch.full((n,), 1.25)
+    tr2, w2, _, disc = tr.update(gj.split(gj.key(22), n), gj.C["x"].set(gj.Mask(new_x, flag)))
+    otr2, ow2, od2 = ogfi.update(o_model, orng.split(orng.key(22), n), otr, {"x": ("mask", new_x.numpy(), f)})
+    np.testing.assert_allclose(_np(w2), ow2, rtol=5e-5, atol=5e-5)
+    x2 = _np(tr2.get_choices()["x"])
+    assert (x2[f] == 1.25).all()
+    np.testing.assert_array_equal(x2[~f], _np(tr.get_choices()["x"])[~f])
+    d = disc["x"]
+    assert isinstance(d, gj.Mask)
+    np.testing.assert_array_equal(_np(d.flag), f)
+    np.testing.assert_array_equal(_np(d.value), _np(tr.get_choices()["x"]))
+
+    # concrete flags dissolve (functional_types.py:211-231): True = plain constraint, False = no constraint
+    tr_t, w_t = model.importance(kb, gj.C["x"].set(gj.Mask(xc, True)), (0.5,))
+    np.testing.assert_allclose(_np(w_t), _nlp(xc.numpy(), 0.5, 2.0), rtol=3e-5, atol=3e-5)
+    tr_f, w_f = model.importance(kb, gj.C["x"].set(gj.Mask(xc, False)), (0.5,))
+    assert (_np(w_f) == 0).all()
+
+
+# ------------------------------------------------------------------------------ mix / or_else
+
+
+def test_mix_basic_and_marginal_density(device):
+    """test_mix_combinator.py:23-50, plus: the average importance weight of an observed ``y`` estimates the mixture
+    density (closed form)."""
+    gj = _gj()
+
+    @gj.gen
+    def comp1(x):
+        return gj.normal(x, 1.0) @ "y"
+
+    @gj.gen
+    def comp2(x):
+        return gj.normal(x + 2.0, 0.5) @ "y"
+
+    mixture = gj.mix(comp1, comp2)
+    logits = torch.tensor([-0.1, -0.2])
+    tr = mixture.simulate(gj.key(0), (logits, (0.0,), (0.0,)))
+    chm = tr.get_choices()
+    assert "mixture_component" in chm and ("component_sample", "y") in chm
+    choices = gj.C["mixture_component"].set(0) | gj.C["component_sample", "y"].set(1.0)
+    score, _ = mixture.assess(choices, (logits, (0.0,), (0.0,)))
+    p = np.exp(np.array([-0.1, -0.2])) / np.exp(np.array([-0.1, -0.2])).sum()
+    assert score.item() == pytest.approx(math.log(p[0]) + float(_nlp(1.0, 0.0, 1.0)), rel=1e-5)
+
+    n = 200_000
+    _, w = mixture.importance(gj.split(gj.key(5), n), gj.C["component_sample", "y"].set(1.7), (logits, (0.0,), (0.0,)))
+    est = float(torch.logsumexp(w.double(), 0)) - math.log(n)
+    exact = math.log(p[0] * math.exp(float(_nlp(1.7, 0.0, 1.0))) + p[1] * math.exp(float(_nlp(1.7, 2.0, 0.5))))
+    assert est == pytest.approx(exact, abs=0.01)
+
+
+def test_or_else(device):
+    """test_or_else.py:23-55 (top level and inside a @gen body, distributions as branches)."""
+    gj = _gj()
+
+    @gj.gen
+    def f():
+        return gj.normal(0.0, 1.0) @ "value"
+
+    f_or_f = f.or_else(f)
+    key = gj.key(314159)
+    args = (True, (), ())
+    tr = f_or_f.simulate(key, args)
+    score, ret = f_or_f.assess(f_or_f.simulate(key, args).get_choices(), args)
+    assert tr.get_score() == score and tr.get_retval() == ret
+
+    @gj.gen
+    def g():
+        flip = gj.flip(0.5) @ "flip"
+        return gj.normal(0.0, 1.0).or_else(gj.normal(2.0, 1.0))(flip, (), ()) @ "value"
+
+    n = 4096
+    tr = g.simulate(gj.split(key, n), ())
+    score, ret = gj.vmap(g.assess, in_axes=(0, None))(tr.get_choices(), ())
+    np.testing.assert_array_equal(_np(tr.get_score()), _np(score))
+    np.testing.assert_array_equal(_np(tr.get_retval()), _np(ret))
+    fl = _np(tr.get_choices()["flip"]).astype(bool)
+    v = _np(tr.get_choices()["value"].unmask())
+    lp = np.where(fl, _nlp(v, 0.0, 1.0), _nlp(v, 2.0, 1.0)) + F32(math.log(0.5))
+    np.testing.assert_allclose(_np(tr.get_score()), lp, rtol=3e-5, atol=3e-5)
+    assert abs(v[~fl].mean() - 2.0) < 0.15 and abs(v[fl].mean()) < 0.15
+
+
+def test_switch_model_in_importance_sampling(device):
+    """End to end through the SMC layer: ImportanceK over a model with a per-particle Switch estimates the evidence of
+    a two-regime observation model (closed form)."""
+    gj = _gj()
+    jnp = gj.numpy
+
+    @gj.gen
+    def model():
+        b = gj.flip(0.25) @ "b"
+        mu = gj.normal(0.0, 1.0) @ "mu"
+        return gj.normal(mu, 0.5).or_else(gj.normal(mu, 3.0))(b, (), ()) @ "obs"
+
+    target = gj.Target(model, (), gj.C["obs"].set(1.0))
+    n = 400_000
+    from genjax_b200.inference.smc import ImportanceK
+
+    alg = ImportanceK(target, k_particles=n)
+    lz = alg.run_smc(gj.key(9)).get_log_marginal_likelihood_estimate()
+
+    def nmix(v, s2):
+        return math.exp(-0.5 * v * v / s2) / math.sqrt(2 * math.pi * s2)
+
+    exact = math.log(0.25 * nmix(1.0, 1.0 + 0.25) + 0.75 * nmix(1.0, 1.0 + 9.0))
+    assert float(lz) == pytest.approx(exact, abs=0.01)
