@@ -356,6 +356,26 @@ class _Emitter:
                 lp = d.emit_logpdf(f"s{j}", a, self)
             self.w(f"if {need} {{ const float lp = {lp}; score += lp; if {wt} weight += lp; }}")
             return
+        if getattr(d, "base", None) is not None:
+            # dist.repeat / dist.vmap: N independent draws of a scalar primitive in one vector site (per-thread arrays)
+            D = s.value.shape[0]
+            b = d.base
+            ak = ", ".join(self.elem_ref(x, "k") for x in s.args)
+            draw = "zz[t]" if b.rng_kind == "normal" else "gjb::u01(ww[t])"
+            self.w(f"float s{j}[{D}];")
+            self.w(f"if {samp} {{")
+            self.w(f"  for (int c = 0; c < {(D + 3) // 4}; ++c) {{")
+            if b.rng_kind == "normal":
+                self.w(f"    const float4 z = gjb::normal4(rng, {j + 1}u, (uint32_t)c); const float zz[4] = {{z.x, z.y, z.z, z.w}};")
+            else:
+                self.w(f"    const uint4 wd = rng.words({j + 1}u, (uint32_t)c); const uint32_t ww[4] = {{wd.x, wd.y, wd.z, wd.w}};")
+            self.w(f"    for (int t = 0; t < 4; ++t) {{ const int k = 4 * c + t; if (k < {D}) s{j}[k] = gjb::{b.cuda}::sample({draw}, {ak}); }} }}")
+            self.w(f"}} else {{ for (int k = 0; k < {D}; ++k) s{j}[k] = in_s{j}[k]; }}")
+            if live:
+                self.w(f"if (!{live}) {{ for (int k = 0; k < {D}; ++k) s{j}[k] = 0.0f; }}")
+            self.w(f"if {need} {{ float lp = 0.0f; for (int k = 0; k < {D}; ++k) lp += gjb::{b.cuda}::logpdf(s{j}[k], {ak}); "
+                   f"score += lp; if {wt} weight += lp; }}")
+            return
         if d.name == "gmm_diag":
             logits, mu, sigma = s.args
             K, D = mu.shape

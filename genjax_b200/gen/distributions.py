@@ -345,6 +345,79 @@ _Normal.repeat = _normal_repeat
 _Normal.vmap = _normal_vmap
 
 
+class _Repeated(Distribution):
+    """``dist.repeat(n=N)`` / ``dist.vmap(in_axes=...)`` for a scalar primitive: ONE vector site of N independent draws
+    (combinators/repeat.py:37-41; vmap.py:180-218: the score is the sum of the inner scores).  Arguments shared by all
+    draws stay scalars, mapped ones are width-N vectors.  Element k draws from word ``k % 4`` of chunk ``k // 4`` of the
+    particle's own Philox stream (as mv_normal_diag does), through the base primitive's device sampler and log-density."""
+
+    vector = True
+    rng_kind = "lane"
+
+    def __init__(self, base: Distribution, n: int | None, in_axes=0):
+        if base.vector or base.value_dtype != F32 or base.rng_kind not in ("uniform", "normal") \
+                or type(base).emit_sample is not Distribution.emit_sample:
+            raise NotFusable(f"{base.name}.repeat / .vmap: only float-valued scalar primitives drawn from one uniform or "
+                             "one normal word can be mapped into a vector site")
+        self.base = base
+        self.n = None if n is None else int(n)
+        self.in_axes = in_axes
+        self.name = f"repeat_{base.name}"
+        self.cuda = base.cuda
+        self.n_args = base.n_args
+
+    def _canonical(self, args, kwargs):
+        cargs = [E.lift(a) for a in self.base._canonical(args, kwargs)]
+        axes = self.in_axes if isinstance(self.in_axes, (tuple, list)) else (self.in_axes,) * len(cargs)
+        if len(axes) != len(cargs):
+            raise ValueError("vmap in_axes specification must be a tree prefix of the corresponding value")
+        widths = {a.shape[0] for a in cargs if a.ndim == 1} | ({self.n} if self.n is not None else set())
+        if len(widths) != 1:
+            raise TypeError(f"{self.name}: cannot infer one axis size from the arguments (got {sorted(widths)}); pass "
+                            "n= / axis_size=")
+        for a, ax in zip(cargs, axes):
+            if a.ndim > 1 or (ax is None and a.ndim == 1):
+                raise TypeError(f"{self.name}: argument of shape {a.shape} under in_axes={ax}")
+        return cargs
+
+    def value_type(self, cargs):
+        widths = {a.shape[0] for a in cargs if a.ndim == 1} | ({self.n} if self.n is not None else set())
+        return F32, (widths.pop(),)
+
+    def logpdf_expr(self, v, args):
+        from . import autodiff as AD
+
+        lp = AD.logpdf_expr(self.base, v, list(args))
+        return E.vsum(lp) if lp.ndim == 1 else lp * float(v.shape[0])
+
+    def __repr__(self):
+        return f"genjax.{self.base.name}.repeat(n={self.n})"
+
+
+def _dist_repeat(self, n: int):
+    """``dist.repeat(n=N)`` (generative_function.py ``repeat``; combinators/repeat.py:25-79)."""
+    return _Repeated(self, n)
+
+
+def _dist_vmap(self, in_axes=0, axis_size: int | None = None):
+    """``dist.vmap(in_axes=...)`` (generative_function.py ``vmap``; combinators/vmap.py:384): the axis size comes from
+    the mapped arguments, or from ``axis_size=`` when every argument is shared."""
+    return _Repeated(self, axis_size, in_axes)
+
+
+Distribution.repeat = _dist_repeat
+Distribution.vmap = _dist_vmap
+_Normal.repeat = _normal_repeat
+
+
+def _normal_vmap2(self, in_axes=0, axis_size: int | None = None):
+    # the lane-group fast path needs the width up front; without it the generic vector site infers it from the arguments
+    return _RepeatedNormal(axis_size) if axis_size is not None else _Repeated(self, None, in_axes)
+
+
+_Normal.vmap = _normal_vmap2
+
+
 class _GmmDiag(Distribution):
     """Mixture of K diagonal Gaussians with one scale per component:
     ``gmm_diag(logits[K], mu[K, D], sigma[K])`` -- the fusable form of the

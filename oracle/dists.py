@@ -587,3 +587,86 @@ DISTS = {
     "student_t": (student_t_sample, student_t_logpdf),
     "poisson": (poisson_sample, poisson_logpdf),
 }
+
+
+# ---------------------------------------------------------------- dist.repeat / dist.vmap (combinators/repeat.py, vmap.py)
+# N independent draws of a scalar primitive as ONE vector site: element k takes word k % 4 of chunk k // 4 of the lane's own
+# stream (the uniform, or the Box-Muller normal of that slot) and goes through the scalar sampler; the log-density is the
+# sum of the elements' (vmap.py:180-218: score = sum of the inner scores), accumulated in element order.
+
+
+class _FixedDraws:
+    """Make the scalar samplers above read given draws instead of the quad stream."""
+
+    def __init__(self, u, z):
+        self.u, self.z = u, z
+
+    def __enter__(self):
+        self.saved = (rng.quad_u01, rng.quad_normal)
+        rng.quad_u01 = lambda *a: self.u
+        rng.quad_normal = lambda *a: self.z
+
+    def __exit__(self, *exc):
+        rng.quad_u01, rng.quad_normal = self.saved
+        return False
+
+
+def _elem(a, k, n):
+    a = _f(a)
+    if a.ndim == 2 or (a.ndim == 1 and a.shape[0] != n):
+        return a[..., k]
+    return a
+
+
+def repeated(base: str, width: int):
+    """(sampler, logpdf) of ``base.repeat(n=width)``."""
+    b_sample, b_logpdf = DISTS[base]
+
+    def sample(words, idx, site, *args):
+        idx_ = np.asarray(idx, dtype=np.uint64)
+        n = idx_.shape[0]
+        out = np.empty((n, width), dtype=F32)
+        for c in range((width + 3) // 4):
+            w = rng.site_words(words, idx_, site, c)
+            z = rng.normal4(words, idx_, site, c)
+            for t in range(4):
+                k = 4 * c + t
+                if k < width:
+                    with _FixedDraws(rng.u01(w[t]), z[t]):
+                        out[:, k] = b_sample(words, idx_, site, *[_elem(a, k, n) for a in args])
+        return out
+
+    def logpdf(v, *args):
+        v = _f(v)
+        n = v.shape[0] if v.ndim == 2 else 1
+        tot = None
+        for k in range(width):
+            lp = _f(b_logpdf(v[..., k], *[_elem(a, k, n) for a in args]))
+            tot = lp if tot is None else (tot + lp).astype(F32)
+        return tot
+
+    return sample, logpdf
+
+
+class _Dists(dict):
+    """``DISTS["repeat_<base>"]`` resolves lazily; the width comes from the arguments at call time."""
+
+    def __contains__(self, name):
+        return dict.__contains__(self, name) or (isinstance(name, str) and name.startswith("repeat_") and dict.__contains__(self, name[7:]))
+
+    def __missing__(self, name):
+        if isinstance(name, str) and name.startswith("repeat_") and dict.__contains__(self, name[7:]):
+            base = name[7:]
+
+            def sample(words, idx, site, *args, width=None):
+                w = width or max(_f(a).shape[-1] for a in args if _f(a).ndim >= 1)
+                return repeated(base, w)[0](words, idx, site, *args)
+
+            def logpdf(v, *args):
+                return repeated(base, _f(v).shape[-1])[1](v, *args)
+
+            return sample, logpdf
+        raise KeyError(name)
+
+
+DISTS = _Dists(DISTS)

@@ -229,7 +229,9 @@ class EmulatedModelLib:
             ev = tuple(s.value.shape)
             dt = F32 if s.value.dtype == "f32" else I32
             args = [evaluate(e, env, cache) for e in s.args]
-            if s.dist.name in od.DISTS:
+            if getattr(s.dist, "base", None) is not None:  # dist.repeat / dist.vmap: a vector site of iid scalar draws
+                sample, logpdf = od.repeated(s.dist.base.name, ev[0])
+            elif s.dist.name in od.DISTS:
                 sample, logpdf = od.DISTS[s.dist.name]
             else:  # no oracle sampler: score through the symbolic log-density (gen/autodiff.py), refuse to sample
                 sample, logpdf = None, None
