@@ -13,8 +13,10 @@ leaves are traced arrays; here they are plain host objects whose leaves are
 torch tensors (or Python scalars) and they resolve, at capture time, to per-site
 flags {sampled, constrained, selected} for the fused kernels.
 
-Dynamic structure (array-valued index addresses, ``Switch``, masks with traced
-flags) is out of scope and raises
+Dynamic structure: leaves may be ``Mask(value, flag)`` (core/mask.py) -- what the
+traces of ``Switch`` / ``MaskCombinator`` models report and what a Mask-ed
+constraint is written as (gen/switch.py, gen/static.py).  Array-valued index
+addresses and ``chm.mask(traced flag)`` on whole maps raise
 ``NotImplementedError``.
 """
 

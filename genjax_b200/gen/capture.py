@@ -67,8 +67,16 @@ class SiteSpec:
     live: Expr | None = None
     scored: Expr | None = None
     excl: tuple = ()  # ((switch id, branch), ...) -- two sites may share an address iff they sit in different branches
+    stack: tuple = ()  # positions in ``addr`` that are the step index of an unrolled Scan: the choice map shows the
+    #                    steps stacked along an axis under the address without them (``chm["tracks", :, "x"]``)
     cmask: Expr | None = None  # hidden per-particle argument: bit 0 = take the supplied value (else sample), bit 1 = the
     #                            site's log-density stays out of the weight (Mask-ed constraints, distribution.py:129-142)
+
+    @property
+    def sel_addr(self) -> tuple:
+        """The address a Selection sees: the step index of an unrolled Scan is transparent to it (Scan hands the same
+        selection to every step, scan.py:417-507)."""
+        return tuple(a for i, a in enumerate(self.addr) if i not in self.stack) if self.stack else self.addr
 
     def flag(self) -> Expr | None:
         """Where the choice is valid: what ``chm.mask(flag)`` / ``ChoiceMap.switch`` report for it."""
@@ -120,6 +128,7 @@ class _Capture:
         self.subcalls: dict = {}
         self.frames: list = []  # (kind "switch" | "mask", id, branch, predicate Expr)
         self.cmask_addrs = set(cmask_addrs)
+        self.scan_positions: tuple = ()  # address positions holding the step index of the enclosing unrolled Scans
         self.extra_args: list = []  # (ArgSpec, Expr) hidden arguments appended after the model's own
         self.n_args = n_args
         self._ids = 0
@@ -168,7 +177,7 @@ class _Capture:
             k = self.n_args + len(self.extra_args)
             cmask = Expr("arg", (), I32_, (), {"index": k, "kind": "particle"})
             self.extra_args.append((ArgSpec("particle", I32_, ()), cmask))
-        self.sites.append(SiteSpec(idx, full, dist, cargs, v, live, scored, excl, cmask))
+        self.sites.append(SiteSpec(idx, full, dist, cargs, v, live, scored, excl, self.scan_positions, cmask))
         return v
 
 
@@ -223,13 +232,17 @@ def inline_call(gen_fn, args):
 # ----------------------------------------------------------------- pytrees
 
 
-def flatten(tree) -> tuple[list, Any]:
-    """Minimal pytree flatten over tuple / list / dict."""
+def flatten(tree, is_leaf=None) -> tuple[list, Any]:
+    """Minimal pytree flatten over tuple / list / dict (``is_leaf(node)`` stops the descent, as in jax.tree_util)."""
     leaves: list = []
 
     def go(t):
         from ..core.choice_map import ChoiceMap
         from ..core.mask import Mask
+
+        if is_leaf is not None and is_leaf(t):
+            leaves.append(t)
+            return ("leaf", len(leaves) - 1)
 
         if isinstance(t, ChoiceMap):
             # a choice map is a pytree of its leaves (the reference's ChoiceMap is a Pytree, choice_map.py:847)
@@ -341,12 +354,12 @@ def capture(source: Callable, name: str, arg_specs: list, arg_tree, cmask_addrs=
             seen[key] = len(ir.flag_leaves)
             ir.flag_leaves.append(f)
         ir.flag_of[s.index] = seen[key]
-    if len(ir.sites) > 16:
-        raise NotImplementedError("more than 16 random-choice sites in one static model")
+    if len(ir.sites) > 32:
+        raise NotImplementedError("more than 32 random-choice sites in one static model (GJB_MAX_SITES)")
     if len(ir.args) > 16:
         raise NotImplementedError("more than 16 model arguments (hidden constraint masks included)")
-    if len(ir.ret_leaves) + len(ir.flag_leaves) > 8:
-        raise NotImplementedError("more than 8 return leaves (validity flags of Switch / Mask sites included)")
+    if len(ir.ret_leaves) + len(ir.flag_leaves) > 16:
+        raise NotImplementedError("more than 16 return leaves (validity flags of Switch / Mask sites included)")
     return ir
 
 

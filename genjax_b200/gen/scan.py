@@ -16,9 +16,12 @@ Choices are addressed ``[t, addr]`` / ``[:, addr]``; the trace stores one fused
 ``StaticTrace`` per step and stacks on demand.
 
 This is the API row, not the fast path: a bootstrap filter over a time series
-belongs on ``inference.pf.ParticleFilter`` (2 launches per step, no per-step
-host work).  Nesting a ``Scan`` inside an ``@gen`` body is not supported (the
-capture pass fuses static bodies only).
+belongs on ``inference.pf.ParticleFilter`` (one launch per step, no per-step
+host work).  A ``Scan`` called inside an ``@gen`` body (``kernel.scan(n=T)(c, xs)
+@ "addr"``) is UNROLLED into the caller's fused kernel (``capture_inline``): the
+length is static, ``T x sites-per-step`` must fit the site table.  The same
+unrolled form (``Scan.unrolled``) carries moves over all steps at once, e.g. HMC
+over ``Selection.at["x"]`` of a scanned trace (inference/mcmc.py).
 """
 
 from __future__ import annotations
@@ -169,6 +172,15 @@ def _stack_time(per_step: list, batched: bool):
     return cap.unflatten(shape, out)
 
 
+def _stack_lists(per_step: list):
+    """Leaf-wise lists over the steps of an unrolled scan: ``[(a_0, b_0), (a_1, b_1)] -> ([a_0, a_1], [b_0, b_1])``."""
+    if not per_step:
+        return None
+    flat = [cap.flatten(y) for y in per_step]
+    shape = flat[0][1]
+    return cap.unflatten(shape, [[f[0][j] for f in flat] for j in range(len(flat[0][0]))])
+
+
 # -------------------------------------------------------------------- trace
 
 
@@ -271,6 +283,61 @@ class Scan(GenerativeFunction):
         if len(args) != 2:
             raise TypeError("a scanned generative function takes (carry, xs)")
         return args
+
+    # -- nested use: ``kernel.scan(n=T)(carry, xs) @ "addr"`` inside an @gen body ------------------------------------
+    def capture_inline(self, args):
+        """The scan UNROLLED into the caller's fused kernel: step t's sites are recorded under ``(..., t, addr)`` (the
+        reference addresses them ``[..., t, addr]`` / ``[..., :, addr]``, scan.py:81-99), the carry is threaded through
+        as traced values.  The length must be static (``n=`` or the leading size of ``xs``) and ``T x sites per step``
+        has to fit the kernel's site table (GJB_MAX_SITES); the per-step outputs come back as Python lists of length T."""
+        c = cap.current_capture()
+        if c is None:
+            raise RuntimeError("a Scan can only be traced inside a @gen function body")
+        carry, xs = self._unpack(args)
+        leaves, shape = cap.flatten(xs)
+        sizes = {int(v.shape[0]) for v in leaves if hasattr(v, "shape") and len(v.shape) >= 1}
+        if len(sizes) > 1 or (sizes and self.length is not None and sizes != {self.length}):
+            raise ValueError(f"scan got values with different leading axis sizes: {sorted(sizes)} (n={self.length})")
+        if not sizes and self.length is None:
+            raise ValueError("scan needs `n=` when nothing is scanned over")
+        T = sizes.pop() if sizes else int(self.length)
+        prefix, positions = c.prefix, c.scan_positions
+        init, ys = carry, []
+        try:
+            c.scan_positions = positions + (len(prefix),)
+            for t in range(T):
+                c.prefix = prefix + (t,)
+                x_t = cap.unflatten(shape, [v[t] for v in leaves])
+                carry, y = self.kernel_gen_fn.capture_inline((carry, x_t))
+                ys.append(y)
+        finally:
+            c.prefix, c.scan_positions = prefix, positions
+        stacked = _stack_lists(ys)
+        if self.post is None:
+            return carry, stacked
+        if self.post is _prepend_initial:  # accumulate / iterate: [init, c_1, ..., c_T]
+            i_leaves, _ = cap.flatten(init)
+            c_leaves, c_shape = cap.flatten(stacked, is_leaf=lambda v: isinstance(v, list))
+            return cap.unflatten(c_shape, [[i] + list(cs) for i, cs in zip(i_leaves, c_leaves)])
+        return self.post((init, xs), (carry, stacked))
+
+    def unrolled(self, T: int) -> StaticGenerativeFunction:
+        """The whole scan as ONE static model ``(carry, xs) -> carry`` (sites ``(t, addr)``): what a move over all steps
+        at once -- HMC over ``Selection.at["x"]`` of a scanned trace, tests/inference/test_requests.py:237-255 -- runs on."""
+        cache = self.__dict__.setdefault("_unrolled", {})
+        fn = cache.get(T)
+        if fn is None:
+            inner = Scan(self.kernel_gen_fn, length=T)
+            unpack = self._unpack
+
+            def source(*args):
+                carry, xs = unpack(args)
+                return inner.capture_inline((carry, xs))[0]
+
+            fn = StaticGenerativeFunction(source)
+            fn.__name__ = f"{self.kernel_gen_fn.__name__}_unrolled{T}"
+            cache[T] = fn
+        return fn
 
     def _setup(self, key, args, constraint):
         device = cabi.require_cuda()

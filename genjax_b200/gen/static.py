@@ -340,12 +340,25 @@ def _choices_from_sites(trace: StaticTrace, sites) -> ChoiceMap:
     """Choice map of ``sites``.  An address visited in several branches of one Switch holds the OR of the branches'
     masked values (``ChoiceMap.switch``, choice_map.py ``switch``; ``Mask.__or__``, functional_types.py:309)."""
     by_addr: dict = {}
+    stacks: dict = {}
     for s in sites:
         by_addr.setdefault(s.addr, []).append(trace._site_value(s))
+        if s.stack:
+            stacks[s.addr] = s.stack
+    merged = {addr: (vals[0] if len(vals) == 1 else Mask.or_n(*vals)) for addr, vals in by_addr.items()}
     chm = ChoiceMap.empty()
-    for addr, vals in by_addr.items():
-        v = vals[0] if len(vals) == 1 else Mask.or_n(*vals)
-        chm = chm | ChoiceMap.entry(v, *addr)
+    # the steps of an unrolled Scan read back stacked along a time axis (after the particle axis), under the address
+    # without the step index -- what ScanTrace.get_choices shows (scan.py:81-84: the inner trace is vectorised)
+    groups: dict = {}
+    for addr, v in merged.items():
+        st = stacks.get(addr)
+        if st and len(st) == 1 and isinstance(v, torch.Tensor):
+            groups.setdefault(addr[: st[0]] + addr[st[0] + 1:], []).append((addr[st[0]], v))
+        else:
+            chm = chm | ChoiceMap.entry(v, *addr)
+    for addr, steps in groups.items():
+        steps.sort(key=lambda p: p[0])
+        chm = chm | ChoiceMap.entry(torch.stack([v for _, v in steps], dim=1 if trace.batched else 0), *addr)
     return chm
 
 
@@ -792,8 +805,8 @@ class StaticGenerativeFunction(GenerativeFunction):
             return torch.zeros_like(trace.get_score())
         scores = self._site_scores(trace)
         tot = torch.zeros_like(trace.score)
-        for addr in dict.fromkeys(s.addr for s in trace.cm.ir.sites):
-            if selection(addr).check():
+        for addr, sel_addr in dict.fromkeys((s.addr, s.sel_addr) for s in trace.cm.ir.sites):
+            if selection(sel_addr).check():
                 tot = tot + scores[addr]
         return tot if trace.batched else tot[0]
 
@@ -826,7 +839,7 @@ class StaticGenerativeFunction(GenerativeFunction):
             retdiff = Diff.unknown_change(tr.get_retval())
             return tr, self._w(tr, w), retdiff, Update(discard)
         if isinstance(request, Regenerate):
-            sel = {s.addr for s in trace.cm.ir.sites if request.selection(s.addr).check()}
+            sel = {s.addr for s in trace.cm.ir.sites if request.selection(s.sel_addr).check()}
             tr, w = self._run(key, new_args, None, prev=trace, sample_addrs=sel, weight_mode="delta", n=trace.n,
                               batched=trace.batched, revive=revive)
             discard = _choices_from_sites(trace, [s for s in trace.cm.ir.sites if s.addr in sel])
@@ -961,7 +974,7 @@ def _edit_static_request(gf, key, trace, request: StaticRequest, argdiffs):
         sel = sel | s
 
     if annot:
-        moved = {s.index for s in ir.sites if sel(s.addr).check() or constraint.get_submap(*s.addr).has_value()}
+        moved = {s.index for s in ir.sites if sel(s.sel_addr).check() or constraint.get_submap(*s.addr).has_value()}
         for a, sub in custom:
             moved |= set(sub.moved_sites(trace, a))
         changed_args = _changed_arg_leaves(argdiffs)
@@ -991,7 +1004,7 @@ def _edit_static_request(gf, key, trace, request: StaticRequest, argdiffs):
         if new_args == () and trace.args != ():
             new_args = trace.args
         new_args = _carry_batch_marks(new_args, trace.args)
-        sel_addrs = {s.addr for s in ir.sites if sel(s.addr).check() and not constraint.get_submap(*s.addr).has_value()}
+        sel_addrs = {s.addr for s in ir.sites if sel(s.sel_addr).check() and not constraint.get_submap(*s.addr).has_value()}
         tr, w = gf._run(key, new_args, _rebatch_constraint(constraint, trace), prev=trace, sample_addrs=sel_addrs,
                         weight_mode="delta", n=trace.n, batched=trace.batched)
         discard = _choices_from_sites(trace, [s for s in ir.sites

@@ -44,7 +44,7 @@ def _chain_model(trace: StaticTrace, latent: tuple, proposals: tuple):
 
 
 def _selected_sites(trace: StaticTrace, selection: Selection) -> tuple:
-    return tuple(s.index for s in trace.cm.ir.sites if selection(s.addr).check())
+    return tuple(s.index for s in trace.cm.ir.sites if selection(s.sel_addr).check())
 
 
 class ChainResult:
@@ -287,8 +287,38 @@ class HMC(EditRequest):
         changed = _depends(tr.cm.ir.ret_leaves, set(latent), set())
         return res.trace, w, (Diff.unknown_change(ret) if changed else Diff.no_change(ret)), Update(old)
 
-    def edit(self, key, tr: StaticTrace, argdiffs):
+    def edit(self, key, tr, argdiffs):
+        from ..gen.scan import ScanTrace
+
+        if isinstance(tr, ScanTrace):
+            return self._edit_scan(key, tr, argdiffs)
         return self.edit_at(key, tr, (), argdiffs)
+
+    def _edit_scan(self, key, tr, argdiffs):
+        """HMC over the selected choices of EVERY step of a scanned trace at once (tests/inference/test_requests.py:
+        237-255): the scan is unrolled into one static model (``Scan.unrolled``), the move runs in its fused chain kernel
+        (one launch: all steps' latents in registers, the gradient through the whole chain of carries), and the scanned
+        trace is rebuilt by an update with the moved values."""
+        from ..gen.static import Batched
+
+        assert Diff.static_check_no_change(argdiffs if argdiffs not in (None, ()) else ()), \
+            "HMC needs unchanged arguments (hmc.py:163)"
+        scan = tr.gen_fn
+        T = tr.scan_length
+        U = scan.unrolled(T)
+        chm = ChoiceMap.empty()
+        for t, inner in enumerate(tr.inner):
+            for s in inner.cm.ir.sites:
+                v = inner.values[s.index]
+                chm = chm | ChoiceMap.entry(v if inner.bcast[s.index] else Batched(v), t, *s.addr)
+        utr, _ = U._run(None, tuple(tr.args), chm, weight_mode="none", n=tr.n, batched=True)
+        new_u, w, _, _ = self.edit_at(key, utr, (), ())
+        moved = ChoiceMap.empty()
+        for j in self.moved_sites(utr):
+            s = utr.cm.ir.sites[j]
+            moved = moved | ChoiceMap.entry(Batched(new_u.values[j]), *s.addr)
+        new_tr, _, retdiff, bwd = scan.edit(key, tr, Update(moved), Diff.no_change(tr.args))
+        return new_tr, (w if tr.batched else w[0]), retdiff, bwd
 
 
 def SafeHMC(selection: Selection, eps, L: int = 10):

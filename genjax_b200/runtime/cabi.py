@@ -13,10 +13,10 @@ import torch
 
 from . import build
 
-ABI_VERSION = 15  # GJB_ABI_VERSION of include/genjax_b200.h this binding mirrors (tests/test_abi.py keeps them equal)
-GJB_MAX_SITES = 16
+ABI_VERSION = 16  # GJB_ABI_VERSION of include/genjax_b200.h this binding mirrors (tests/test_abi.py keeps them equal)
+GJB_MAX_SITES = 32
 GJB_MAX_ARGS = 16
-GJB_MAX_RETS = 8
+GJB_MAX_RETS = 16
 GJB_HEAVY_WS_WORDS = 4 + 3 * 1024
 TE_TILE = 2048
 TE_MAX_TILES = 4096

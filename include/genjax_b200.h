@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GJB_ABI_VERSION 15
+#define GJB_ABI_VERSION 16
 
 #define GJB_E_ARG (-1)      /* null / misaligned pointer, negative size          */
 #define GJB_E_RANGE (-2)    /* size beyond what the kernel supports              */
@@ -378,9 +378,9 @@ int gjb_normal_fill(uint32_t key0, uint32_t key1, uint64_t idx_offset,
 
 /* -------------------------------------------------------- 2. per-model .so */
 
-#define GJB_MAX_SITES 16
+#define GJB_MAX_SITES 32   /* a Scan unrolled into its caller brings length x sites-per-step of them */
 #define GJB_MAX_ARGS 16
-#define GJB_MAX_RETS 8
+#define GJB_MAX_RETS 16
 
 /* site_flags bits */
 #define GJB_SITE_SAMPLE 1u     /* draw the value (else read site_in)            */

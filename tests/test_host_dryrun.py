@@ -25,6 +25,7 @@ _MCMC = "not gmm"  # the mixture has no oracle sampler; everything else runs its
     ["tests/test_zzz_static_reference_gpu.py"],
     ["tests/test_switch_gpu.py"],
     ["tests/test_dist_vmap_gpu.py"],
+    ["tests/test_scan_nested_gpu.py"],
     # the filter, chain and core-kernel tests reach entry points that exist on the GPU only; these do not
     ["tests/test_pf_gpu.py", "-k", _PF],
     ["tests/test_zz_mv_normal_gpu.py"],
