@@ -476,7 +476,15 @@ class ChoiceMap:
         return sel
 
     def mask(self, flag):
-        return self.filter(flag) if isinstance(flag, bool) else self.filter(_not_a_flag(flag))
+        """``chm.mask(flag)`` (choice_map.py ``mask``): a concrete flag keeps or empties the map; a flag array wraps every
+        leaf in ``Mask(value, flag)`` -- the form a Mask-ed constraint takes (distribution.py:129-142)."""
+        if isinstance(flag, bool):
+            return self.filter(flag)
+        if hasattr(flag, "shape") and hasattr(flag, "dtype"):
+            from .mask import Mask
+
+            return self.map_leaves(lambda v: Mask.build(v, flag))
+        return self.filter(_not_a_flag(flag))
 
     def simplify(self) -> "ChoiceMap":
         return self

@@ -291,8 +291,12 @@ class HMC(EditRequest):
         from ..gen.scan import ScanTrace
 
         if isinstance(tr, ScanTrace):
-            return self._edit_scan(key, tr, argdiffs)
-        return self.edit_at(key, tr, (), argdiffs)
+            new_tr, w, retdiff, _ = self._edit_scan(key, tr, argdiffs)
+        else:
+            new_tr, w, retdiff, _ = self.edit_at(key, tr, (), argdiffs)
+        # hmc.py:205-210: the backward request of an HMC move is the same move (``edit_at``, the form a StaticRequest
+        # composes, keeps handing back the discarded choices)
+        return new_tr, w, retdiff, HMC(self.selection, self.eps, self.L)
 
     def _edit_scan(self, key, tr, argdiffs):
         """HMC over the selected choices of EVERY step of a scanned trace at once (tests/inference/test_requests.py:

@@ -218,11 +218,22 @@ class SMCAlgorithm(Algorithm):
         chm = target.filter_to_unconstrained(particle.get_choices())
         return log_density_estimate, chm
 
+    #: smc.py:181-198 scores ``sample_particle(sub_key)`` of the conditional-SMC collection -- a particle drawn by weight,
+    #: not necessarily the retained one.  That is the default here (results identical to the reference's); set
+    #: ``reference_compat = False`` on an algorithm to score the retained particle (the last slot), whose choices are ``v``.
+    reference_compat = True
+
     def estimate_logpdf(self, key: PRNGKey, v: ChoiceMap, *args):
         (target,) = args
         algorithm = ChangeTarget(self, target)
-        particle_collection = algorithm.run_csmc(key, v)
-        particle = particle_collection.get_particle(-1 % len(particle_collection))
+        if self.reference_compat:
+            kb = split(key)
+            key, sub_key = kb[0], kb[1]
+            particle_collection = algorithm.run_csmc(key, v)
+            particle = particle_collection.sample_particle(sub_key)
+        else:
+            particle_collection = algorithm.run_csmc(key, v)
+            particle = particle_collection.get_particle(-1 % len(particle_collection))
         log_density_estimate = particle.get_score() - particle_collection.get_log_marginal_likelihood_estimate()
         return log_density_estimate
 

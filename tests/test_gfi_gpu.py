@@ -300,8 +300,16 @@ def test_custom_proposal_marginal_and_conditional_smc(device):
     assert len(pc2) == k and pc2.get_particles().get_choices()["x"][-1].item() == pytest.approx(0.4)
     np.testing.assert_allclose(pc2.get_log_weights().cpu().numpy(), exact_logz, atol=2e-5)
     # GenSP density estimate of the retained value == the exact posterior density N(0.4; y/2, sqrt(1/2))
+    alg.reference_compat = False
     est = alg.estimate_logpdf(gj.key(4), retained, target)
     assert est.item() == pytest.approx(float(od.normal_logpdf(F32(0.4), F32(yv / 2), F32(math.sqrt(0.5)))), abs=1e-4)
+    # the default is smc.py:181-198 to the letter: the particle scored is ``sample_particle(sub_key)`` of the collection
+    alg.reference_compat = True
+    kb4 = gj.split(gj.key(4))
+    pc_c = ChangeTarget(alg, target).run_csmc(kb4[0], retained)
+    drawn = pc_c.sample_particle(kb4[1])
+    est_c = alg.estimate_logpdf(gj.key(4), retained, target)
+    assert est_c.item() == pytest.approx((drawn.get_score() - pc_c.get_log_marginal_likelihood_estimate()).item(), abs=1e-6)
     # without a proposal: prior particles, the retained one scored by the likelihood
     alg0 = ImportanceK(target, k_particles=64)
     pc3 = alg0.run_csmc(gj.key(5), retained)
