@@ -507,8 +507,8 @@ __device__ __forceinline__ void te_finish_step(const gjb_step_link* __restrict__
     if (w < warp) excl += v;
     S += v;
   }
-  // cumulative offspring count at every tile boundary (shared memory, when it fits the window scratch), the table
-  const bool cnt_in_smem = n_tiles <= kTeTile;
+  // the table, and the cumulative offspring count at every tile boundary: it takes the prefix's place in shared memory
+  // (the window searches below probe counts only; recomputing the fp64 count per probe was ~2 us at 4096 tiles)
   const double u0 = resample_u0(__ldg(reskey), __ldg(reskey + 1), (uint64_t)__ldg(reskey + 2) | ((uint64_t)__ldg(reskey + 3) << 32));
   const double scale = S ? __ddiv_rn((double)n_total, (double)S) : 0.0;
   const int32_t nt = (int32_t)n_total;
@@ -516,10 +516,9 @@ __device__ __forceinline__ void te_finish_step(const gjb_step_link* __restrict__
     const int t = t0 + k;
     if (t < n_tiles) {
       const uint64_t cur = sm.pre[t] + excl;
-      sm.pre[t] = cur;
       tab->pre[t] = cur;
       tab->shf[t] = sm.shf[t];
-      if (cnt_in_smem && S) sm.heads[t] = offspring_cnt(cur, S, scale, u0, nt);
+      sm.pre[t] = S ? (uint64_t)(int64_t)offspring_cnt(cur, S, scale, u0, nt) : 0ull;
     }
   }
   if (tid == 0) {
@@ -527,7 +526,7 @@ __device__ __forceinline__ void te_finish_step(const gjb_step_link* __restrict__
     if (lse_out) te_write_lse(lse_out, E, S, n_total);
     *L->ticket = 0u;  // the next launch on the stream starts from zero
   }
-  __syncthreads();  // sm.pre / sm.heads complete
+  __syncthreads();  // sm.pre (now counts) complete
   // window table: for each local window the first tile whose offspring reach it and the tile that owns its last slot
   const int n_win = (int)((n_local + kTeTile - 1) / kTeTile);
   if (S != 0) {
@@ -538,14 +537,14 @@ __device__ __forceinline__ void te_finish_step(const gjb_step_link* __restrict__
       int lo = 0, hi = n_tiles;  // smallest p with cnt(P_p) > ws
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const int64_t c = cnt_in_smem ? (int64_t)sm.heads[mid] : (int64_t)offspring_cnt(sm.pre[mid], S, scale, u0, nt);
+        const int64_t c = (int64_t)sm.pre[mid];
         if (c > ws) hi = mid; else lo = mid + 1;
       }
       const int p_first = lo;
       hi = n_tiles;                // smallest p with cnt(P_p) >= we (lo continues from p_first)
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const int64_t c = cnt_in_smem ? (int64_t)sm.heads[mid] : (int64_t)offspring_cnt(sm.pre[mid], S, scale, u0, nt);
+        const int64_t c = (int64_t)sm.pre[mid];
         if (c >= we) hi = mid; else lo = mid + 1;
       }
       tab->win[w][0] = p_first;
