@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(kThreads) te_resample_kernel(const __grid_cons
 // tag (the cross-rank hand-off), then E, the aligned tile masses, their inclusive prefix, the offspring count at every
 // tile boundary, and the parent-tile range of every local window.  Same arithmetic as te_finish_step's last-CTA path.
 constexpr int kTabThreads = 256;
-__global__ void __launch_bounds__(kTabThreads, 8) te_table_kernel(const __grid_constant__ gjb_te_table_args A) {
+__global__ void __launch_bounds__(kTabThreads, 4) te_table_kernel(const __grid_constant__ gjb_te_table_args A) {
   __shared__ int32_t cnt[kTeMaxTiles];
   __shared__ __align__(16) uint64_t red[kTabThreads / 32];
   __shared__ __align__(16) int32_t ired[kTabThreads / 32];
@@ -600,13 +600,13 @@ __global__ void __launch_bounds__(kTabThreads, 8) te_table_kernel(const __grid_c
   // pass 1: wait for every record (batched tag polls), E = max exponent over tiles with mass
   te_wait_records(box, t0, per, n_tiles, tag);
   int emax = GJB_TE_E_NONE;
-  for (int k = 0; k < per; ++k) {
-    const int t = t0 + k;
-    if (t < n_tiles) {
-      const uint64_t* r = box + (int64_t)t * GJB_TE_LL_WORDS;
-      const ulonglong2 w01 = __ldcg(reinterpret_cast<const ulonglong2*>(r));
-      if ((w01.x & 0xffffffffull) | (w01.y << 32)) emax = max(emax, (int)(uint32_t)__ldcg(reinterpret_cast<const unsigned long long*>(r + 2)));
-    }
+  uint64_t bm[8];
+  int be[8];
+  for (int b = 0; b < per; b += 8) {  // 8 records per round trip (te_load_batch)
+    te_load_batch(box, t0 + b, per - b, n_tiles, bm, be);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (bm[k]) emax = max(emax, be[k]);
   }
   emax = __reduce_max_sync(0xffffffffu, emax);
   if (lane == 0) ired[warp] = emax;
@@ -616,17 +616,17 @@ __global__ void __launch_bounds__(kTabThreads, 8) te_table_kernel(const __grid_c
   for (int w = 1; w < kTabThreads / 32; ++w) E = max(E, ired[w]);
   // pass 2: aligned masses (records re-read from L2: they are complete now), thread-local inclusive prefix -> table
   uint64_t run = 0;
-  for (int k = 0; k < per; ++k) {
-    const int t = t0 + k;
-    if (t < n_tiles) {
-      const uint64_t* r = box + (int64_t)t * GJB_TE_LL_WORDS;
-      const ulonglong2 w01 = __ldcg(reinterpret_cast<const ulonglong2*>(r));
-      const uint64_t m = (w01.x & 0xffffffffull) | (w01.y << 32);
-      const int e = (int)(uint32_t)__ldcg(reinterpret_cast<const unsigned long long*>(r + 2));
-      const int sft = m ? min(E - e, 63) : 63;
-      run += m >> sft;
-      tab->pre[t] = run;
-      tab->shf[t] = (uint8_t)sft;
+  for (int b = 0; b < per; b += 8) {
+    te_load_batch(box, t0 + b, per - b, n_tiles, bm, be);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int t = t0 + b + k;
+      if (b + k < per && t < n_tiles) {
+        const int sft = bm[k] ? min(E - be[k], 63) : 63;
+        run += bm[k] >> sft;
+        tab->pre[t] = run;
+        tab->shf[t] = (uint8_t)sft;
+      }
     }
   }
   uint64_t inc = run;

@@ -413,6 +413,23 @@ __device__ __forceinline__ void te_wait_records(const uint64_t* box, int t0, int
   }
 }
 
+// Masses and exponents of the (complete) records [t0, t0 + 8) clipped to `cnt` and n_tiles: 16 independent L2 loads.
+__device__ __forceinline__ void te_load_batch(const uint64_t* box, int t0, int cnt, int n_tiles, uint64_t (&m)[8], int (&e)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int t = t0 + k;
+    m[k] = 0;
+    e[k] = GJB_TE_E_NONE;
+    if (k < cnt && t < n_tiles) {
+      const uint64_t* r = box + (int64_t)t * GJB_TE_LL_WORDS;
+      const ulonglong2 w01 = __ldcg(reinterpret_cast<const ulonglong2*>(r));
+      const unsigned long long w2 = __ldcg(reinterpret_cast<const unsigned long long*>(r + 2));
+      m[k] = (w01.x & 0xffffffffull) | (w01.y << 32);
+      e[k] = (int)(uint32_t)w2;
+    }
+  }
+}
+
 // {E ln 2, S, log-mean-exp} of a resampling (one thread)
 __device__ __forceinline__ void te_write_lse(double* out, int E, uint64_t S, int64_t n_total);
 
@@ -423,7 +440,7 @@ __device__ __forceinline__ void te_write_lse(double* out, int E, uint64_t S, int
 // weights.  Uses sm.pre / sm.shf / sm.red / sm.ired (the CTA's window data is dead by now).
 __device__ __forceinline__ void te_finish_step(const gjb_step_link* __restrict__ L, int step, int64_t slot_offset, int64_t n_local,
                                                int64_t n_total, const uint32_t* __restrict__ reskey, gjb_step_table* __restrict__ tab,
-                                               double* __restrict__ lse_out, TeSmem& sm) {
+                                               double* __restrict__ lse_out, TeSmem& sm, bool light = false) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int world = L->world, tpr = L->tiles_per_rank;
   const uint32_t tag = te_tag(L, step);
@@ -445,27 +462,18 @@ __device__ __forceinline__ void te_finish_step(const gjb_step_link* __restrict__
   const int per = (n_tiles + kThreads - 1) / kThreads;
   const int t0 = tid * per;
   const uint64_t* box = te_mail_slot(L->mailbox[L->rank], step, 0);
-  constexpr int kKeep = 4;  // records a thread keeps in registers between the two passes (n_tiles <= 1024)
-  uint64_t km[kKeep];
-  int ke[kKeep];
-  // pass 1: wait for every record (this is the cross-rank barrier of the step), E = max exponent over tiles with mass
+  // pass 1: wait for every record (this is the cross-rank barrier of the step), E = max exponent over tiles with mass.
+  // Records are read 8 at a time with all 16 loads in flight (te_load_batch): a record-by-record loop pays one L2 round
+  // trip per record per thread, which at 4096 tiles (16 records per thread, two passes) was ~9 us of the 8-GPU step.
   te_wait_records(box, t0, per, n_tiles, tag);
   int emax = GJB_TE_E_NONE;
-  auto rec_at = [&](int t, uint64_t& m, int& e) {  // (complete now: plain L2 loads)
-    const uint64_t* r = box + (int64_t)t * GJB_TE_LL_WORDS;
-    const ulonglong2 w01 = __ldcg(reinterpret_cast<const ulonglong2*>(r));
-    m = (w01.x & 0xffffffffull) | (w01.y << 32);
-    e = (int)(uint32_t)__ldcg(reinterpret_cast<const unsigned long long*>(r + 2));
-    if (m) emax = max(emax, e);
-  };
+  uint64_t bm[8];
+  int be[8];
+  for (int b = 0; b < per; b += 8) {
+    te_load_batch(box, t0 + b, per - b, n_tiles, bm, be);
 #pragma unroll
-  for (int k = 0; k < kKeep; ++k) {
-    km[k] = 0; ke[k] = GJB_TE_E_NONE;
-    if (k < per && t0 + k < n_tiles) rec_at(t0 + k, km[k], ke[k]);
-  }
-  for (int k = kKeep; k < per; ++k) {
-    uint64_t m; int e;
-    if (t0 + k < n_tiles) rec_at(t0 + k, m, e);
+    for (int k = 0; k < 8; ++k)
+      if (bm[k]) emax = max(emax, be[k]);
   }
   emax = __reduce_max_sync(0xffffffffu, emax);
   if (lane == 0) sm.ired[warp] = emax;
@@ -473,23 +481,58 @@ __device__ __forceinline__ void te_finish_step(const gjb_step_link* __restrict__
   int E = sm.ired[0];
 #pragma unroll
   for (int w = 1; w < kThreads / 32; ++w) E = max(E, sm.ired[w]);
-  // pass 2: aligned masses, inclusive prefix (records beyond the kept ones are re-read: they are complete now)
-  uint64_t run = 0;
-  auto fold = [&](int t, uint64_t m, int e) {
-    const int sft = m ? min(E - e, 63) : 63;
-    run += m >> sft;
-    sm.pre[t] = run;
-    sm.shf[t] = (uint8_t)sft;
-  };
+  if (light) {
+    // GJB_STEP_LIGHT: rank totals at the global alignment, their inclusive prefix -- nothing per tile.  (Exactly the sums
+    // the full table holds at the rank boundaries: sum_p (mass_p >> min(E - e_p, 63)) in tile order.)
+    if (tid < world) sm.pre[tid] = 0ull;
+    __syncthreads();
+    uint64_t acc = 0;
+    int cur = -1;
+    for (int b = 0; b < per; b += 8) {
+      te_load_batch(box, t0 + b, per - b, n_tiles, bm, be);
 #pragma unroll
-  for (int k = 0; k < kKeep; ++k)
-    if (k < per && t0 + k < n_tiles) fold(t0 + k, km[k], ke[k]);
-  for (int k = kKeep; k < per; ++k) {
-    const int t = t0 + k;
-    if (t < n_tiles) {
-      const uint64_t* r = box + (int64_t)t * GJB_TE_LL_WORDS;
-      const ulonglong2 w01 = __ldcg(reinterpret_cast<const ulonglong2*>(r));
-      fold(t, (w01.x & 0xffffffffull) | (w01.y << 32), (int)(uint32_t)__ldcg(reinterpret_cast<const unsigned long long*>(r + 2)));
+      for (int k = 0; k < 8; ++k) {
+        const int t = t0 + b + k;
+        if (b + k < per && t < n_tiles && bm[k]) {
+          const int r = t / tpr;
+          if (r != cur) {
+            if (acc) atomicAdd(reinterpret_cast<unsigned long long*>(&sm.pre[cur]), (unsigned long long)acc);
+            acc = 0;
+            cur = r;
+          }
+          acc += bm[k] >> min(E - be[k], 63);
+        }
+      }
+    }
+    if (acc) atomicAdd(reinterpret_cast<unsigned long long*>(&sm.pre[cur]), (unsigned long long)acc);
+    __syncthreads();
+    if (tid == 0) {
+      uint64_t run = 0;
+      for (int r = 0; r < world; ++r) {
+        run += sm.pre[r];
+        tab->pre[r] = run;
+      }
+      tab->S = run; tab->E = E; tab->n_tiles_total = n_tiles;
+      if (lse_out) te_write_lse(lse_out, E, run, n_total);
+      *L->ticket = 0u;
+      __threadfence();
+      te_st_volatile(reinterpret_cast<uint64_t*>(&tab->tag), (uint64_t)tag | (1ull << 32));  // {tag, reserved = 1: rank-level table}
+    }
+    return;
+  }
+  // pass 2: aligned masses, thread-local inclusive prefix (the records are complete: plain batched L2 loads)
+  uint64_t run = 0;
+  for (int b = 0; b < per; b += 8) {
+    te_load_batch(box, t0 + b, per - b, n_tiles, bm, be);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int t = t0 + b + k;
+      if (b + k < per && t < n_tiles) {
+        const int sft = bm[k] ? min(E - be[k], 63) : 63;
+        run += bm[k] >> sft;
+        sm.pre[t] = run;
+        sm.shf[t] = (uint8_t)sft;
+      }
     }
   }
   uint64_t inc = run;
@@ -660,6 +703,146 @@ __device__ __forceinline__ uint64_t te_pull_table(const gjb_step_table* __restri
 #pragma unroll
   for (int k = 0; k < kTeItems; ++k) anc[k] = max(v[k], pre) - 1;
   GJB_TP(6);
+  return S;
+}
+
+// Consumer on a RANK-level table (GJB_STEP_LIGHT): S, E and the ranks' prefix come from the table the previous launch's
+// last CTA left; the tile prefix is formed here, rank by rank, for the ranks whose tiles have offspring in this window (one,
+// or two next to a rank boundary) from the records in this device's own mailbox `box` (complete: the table was written
+// after every record had arrived).  Per rank this is te_pull's work on that rank's tiles.  Same outputs as te_pull.
+template <bool kCg>
+__device__ __forceinline__ uint64_t te_pull_light(const gjb_step_table* __restrict__ tab, const uint64_t* __restrict__ box, int world,
+                                                  int tpr, const gjb_peers* cdf_peers, int64_t n_total, double u0, int64_t w_lo,
+                                                  int w_n, TeSmem& sm, int32_t (&anc)[kTeItems], int* e_out) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t S = __ldcg(reinterpret_cast<const unsigned long long*>(&tab->S));
+  const int E = __ldcg(&tab->E);
+  *e_out = E;
+  if (tid == 0) { sm.p_lo = 0x7fffffff; sm.p_hi = -1; }
+  *reinterpret_cast<int4*>(sm.heads + tid * kTeItems) = make_int4(0, 0, 0, 0);
+  *reinterpret_cast<int4*>(sm.heads + tid * kTeItems + 4) = make_int4(0, 0, 0, 0);
+  if (S == 0) {
+#pragma unroll
+    for (int k = 0; k < kTeItems; ++k) anc[k] = (int32_t)(w_lo + tid * kTeItems + k);
+    return 0;
+  }
+  const double scale = __ddiv_rn((double)n_total, (double)S);
+  const int32_t nt = (int32_t)n_total;
+  const int32_t wl = (int32_t)w_lo, wh = (int32_t)(w_lo + w_n);
+  __syncthreads();
+  // ---- which ranks hold parents of this window
+  if (tid < world) {
+    const uint64_t rp = tid ? __ldcg(reinterpret_cast<const unsigned long long*>(&tab->pre[tid - 1])) : 0ull;
+    const uint64_t rc = __ldcg(reinterpret_cast<const unsigned long long*>(&tab->pre[tid]));
+    if (rc != rp && offspring_cnt(rc, S, scale, u0, nt) > wl && offspring_cnt(rp, S, scale, u0, nt) < wh) {
+      atomicMin(&sm.p_lo, tid);
+      atomicMax(&sm.p_hi, tid);
+    }
+  }
+  __syncthreads();
+  const int r_lo = sm.p_lo, r_hi = sm.p_hi;
+  const int per = (tpr + kThreads - 1) / kThreads;
+  const int t0 = tid * per;
+  for (int r = r_lo; r <= r_hi; ++r) {
+    __syncthreads();  // r_lo / r_hi (first round) or the previous rank's prefix have been read by everyone
+    const uint64_t rbase = r ? __ldcg(reinterpret_cast<const unsigned long long*>(&tab->pre[r - 1])) : 0ull;
+    if (tid == 0) { sm.p_lo = 0x7fffffff; sm.p_hi = -1; }
+    // aligned masses of this rank's tiles, thread-local inclusive prefix
+    uint64_t run = 0;
+    for (int k = 0; k < per; ++k) {
+      const int t = t0 + k;
+      if (t < tpr) {
+        const uint64_t* rec = box + (int64_t)(r * tpr + t) * GJB_TE_LL_WORDS;
+        const ulonglong2 w01 = __ldcg(reinterpret_cast<const ulonglong2*>(rec));
+        const unsigned long long w2 = __ldcg(reinterpret_cast<const unsigned long long*>(rec + 2));
+        const uint64_t m = (w01.x & 0xffffffffull) | (w01.y << 32);
+        const int sft = m ? min(E - (int)(uint32_t)w2, 63) : 63;
+        run += m >> sft;
+        sm.pre[t] = run;
+        sm.shf[t] = (uint8_t)sft;
+      }
+    }
+    uint64_t inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint64_t v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) sm.red[warp] = inc;
+    __syncthreads();
+    uint64_t excl = rbase + inc - run;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w)
+      if (w < warp) excl += sm.red[w];
+    // absolute prefix; which of this rank's tiles have offspring in the window (a contiguous range)
+    {
+      int lo = 0x7fffffff, hi = -1;
+      uint64_t prev = excl;
+      int32_t cnt_prev = offspring_cnt(prev, S, scale, u0, nt);
+      for (int k = 0; k < per; ++k) {
+        const int t = t0 + k;
+        if (t < tpr) {
+          const uint64_t cur = sm.pre[t] + excl;
+          sm.pre[t] = cur;
+          const int32_t cnt_cur = offspring_cnt(cur, S, scale, u0, nt);
+          if (cur != prev && cnt_cur > wl && cnt_prev < wh) {
+            lo = min(lo, t);
+            hi = max(hi, t);
+          }
+          prev = cur;
+          cnt_prev = cnt_cur;
+        }
+      }
+      if (hi >= 0) { atomicMin(&sm.p_lo, lo); atomicMax(&sm.p_hi, hi); }
+    }
+    __syncthreads();
+    const int p_lo = sm.p_lo, p_hi = sm.p_hi;
+    // every parent with offspring in the window drops its id (+1) at its first slot
+    const uint64_t* rows = reinterpret_cast<const uint64_t*>(cdf_peers->base[r]) + tid * kTeItems;
+    for (int p = p_lo; p <= p_hi; ++p) {
+      const uint64_t base = p ? sm.pre[p - 1] : rbase;
+      if (sm.pre[p] != base) {
+        uint64_t c[kTeItems], c_prev;
+        te_ld_row<kCg>(rows + (int64_t)p * kTeTile, c, c_prev);
+        const int sft = sm.shf[p];
+        int32_t prev = min(max(offspring_cnt(base + (c_prev >> sft), S, scale, u0, nt), wl), wh);
+        const int32_t last = min(max(offspring_cnt(base + (c[kTeItems - 1] >> sft), S, scale, u0, nt), wl), wh);
+        if (last > prev) {
+          const int32_t id1 = (r * tpr + p) * kTeTile + tid * kTeItems + 1;
+#pragma unroll
+          for (int k = 0; k < kTeItems; ++k) {
+            const int32_t cur = (k == kTeItems - 1) ? last : min(max(offspring_cnt(base + (c[k] >> sft), S, scale, u0, nt), wl), wh);
+            if (cur > prev) sm.heads[prev - wl] = id1 + k;
+            prev = cur;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- inclusive max-scan over the window (as te_pull)
+  int32_t v[kTeItems];
+  {
+    const int4 a = *reinterpret_cast<const int4*>(sm.heads + tid * kTeItems);
+    const int4 b = *reinterpret_cast<const int4*>(sm.heads + tid * kTeItems + 4);
+    v[0] = a.x; v[1] = max(v[0], a.y); v[2] = max(v[1], a.z); v[3] = max(v[2], a.w);
+    v[4] = max(v[3], b.x); v[5] = max(v[4], b.y); v[6] = max(v[5], b.z); v[7] = max(v[6], b.w);
+  }
+  int32_t incm = v[kTeItems - 1];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t t = __shfl_up_sync(0xffffffffu, incm, o);
+    if (lane >= o) incm = max(incm, t);
+  }
+  if (lane == 31) sm.ired[warp] = incm;
+  const int32_t wexc = __shfl_up_sync(0xffffffffu, incm, 1);
+  __syncthreads();
+  int32_t pre = lane ? wexc : 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w)
+    if (w < warp) pre = max(pre, sm.ired[w]);
+#pragma unroll
+  for (int k = 0; k < kTeItems; ++k) anc[k] = max(v[k], pre) - 1;
   return S;
 }
 

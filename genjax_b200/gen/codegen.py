@@ -860,7 +860,11 @@ class _Generator:
         propose + logpdf through the generated body -> te_publish (within-tile CDF + tile record of the new
         weights).  Block-level synchronisation only; csrc/gjb_step.cuh."""
         ir = self.ir
-        out = ["__global__ void __launch_bounds__(kThreads, 4) pf_step_kernel(const __grid_constant__ gjb_step_args A) {"]
+        out = ["// kDist: the launch carries a gjb_step_link (several GPUs, or the table forms on one device): peer loads, the prefix",
+               "// tables and the cross-rank hand-off at the end of the CTA.  kDist = false is the single-device table-free step: none of",
+               "// that code is in its kernel (two instantiations, chosen by the launcher), so it costs the hot path no registers.",
+               "template <bool kDist>",
+               "__global__ void __launch_bounds__(kThreads, 4) pf_step_kernel_t(const __grid_constant__ gjb_step_args A) {"]
         out.append("  __shared__ gjb::TeSmem sm;")
         out.extend(self.stage_lines("A.args"))
         out.append("  Uni U; make_uni(U, A.scalars);")
@@ -902,17 +906,20 @@ class _Generator:
         out.append("  // its tile's data was fenced into L2, so the flag covers the bulk data too.  Table-free form: wait for the previous launch.")
         out.append("  // (measured on B200: the flag hand-off is SLOWER than the kernel boundary, 30.7 vs 22.5 us per step on one device, so it is")
         out.append("  // opt-in: GJB_STEP_FLAGWAIT)")
-        out.append("  const bool flagged = A.table_in && A.link && (A.flags & GJB_STEP_FLAGWAIT);")
+        out.append("  const bool flagged = kDist && A.table_in && A.link && (A.flags & GJB_STEP_FLAGWAIT);")
         out.append("  if (!flagged) gjb::pdl_wait();")
         out.append("  if (A.prev_cdf) {  // ancestors of MY slots: output-slot systematic resampling of the previous step")
         out.append("    const double u0 = gjb::resample_u0(__ldg(A.prev_key), __ldg(A.prev_key + 1), (uint64_t)__ldg(A.prev_key + 2) | ((uint64_t)__ldg(A.prev_key + 3) << 32));")
         out.append("    int32_t anc[gjb::kTeItems];")
         out.append("    int E;")
         out.append("    const int64_t w_glob = A.slot_offset + w_loc;")
-        out.append("    if (A.table_in) {  // the previous launch's last CTA left the prefix table: no prefix work here")
+        out.append("    if (kDist && A.table_in) {  // the previous launch's last CTA left the prefix table: no prefix work here")
         out.append("      // (peer memory is read through L2 (ld.global.cg); on one device the read-only path is used: griddepcontrol.wait")
         out.append("      // above makes the previous launch's writes visible to it, measured 1.4 us per step faster than .cg)")
-        out.append("      if (A.cdf_peers) gjb::te_pull_table<true>(A.table_in, (int)blockIdx.x, A.prev_cdf, A.cdf_peers, A.n_total, u0, w_glob, w_n, sm, anc, &E,")
+        out.append("      if (A.cdf_peers && A.link && (A.flags & GJB_STEP_LIGHT))  // rank-level table: the tile prefix of the parents' rank(s) is formed here")
+        out.append("        gjb::te_pull_light<true>(A.table_in, gjb::te_mail_slot(A.link->mailbox[A.link->rank], A.step - 1, 0), A.link->world,")
+        out.append("                                 A.link->tiles_per_rank, A.cdf_peers, A.n_total, u0, w_glob, w_n, sm, anc, &E);")
+        out.append("      else if (A.cdf_peers) gjb::te_pull_table<true>(A.table_in, (int)blockIdx.x, A.prev_cdf, A.cdf_peers, A.n_total, u0, w_glob, w_n, sm, anc, &E,")
         out.append("                                                flagged ? gjb::te_tag(A.link, A.step - 1) : 0u);")
         out.append("      else gjb::te_pull_table<false>(A.table_in, (int)blockIdx.x, A.prev_cdf, nullptr, A.n_total, u0, w_glob, w_n, sm, anc, &E,")
         out.append("                                     flagged ? gjb::te_tag(A.link, A.step - 1) : 0u);")
@@ -935,17 +942,17 @@ class _Generator:
         out.append("      else for (int k = 0; k < gjb::kTeItems; ++k) if (tid * gjb::kTeItems + k < w_n) o[k] = anc[k];")
         out.append("    }")
         out.append("    io.gather = sm.heads - w_loc;")
-        out.append("    io.peers = A.peer_args;")
+        out.append("    io.peers = kDist ? A.peer_args : nullptr;")
         out.append("  }")
         out.append("  float run_max = -INFINITY;")
         if self.group:
             out.append("  __syncthreads();  // every group reads ancestors other threads resolved")
-            out.append("  if (A.cdf_peers) run_groups<true, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, w_loc, w_loc + w_n, kPPB, run_max);")
+            out.append("  if (kDist && A.cdf_peers) run_groups<true, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, w_loc, w_loc + w_n, kPPB, run_max);")
             out.append("  else run_groups<false, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, w_loc, w_loc + w_n, kPPB, run_max);")
             out.append("  __syncthreads();  // the window's weights are complete")
         else:
             if hoist:
-                out.append("  if (A.cdf_peers) {")
+                out.append("  if (kDist && A.cdf_peers) {")
                 out.append("    if (q0 < qw) run_quads<true, true, false, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0, q0 + 1, 1, run_max, &R0);")
                 out.append("    if (q0 + 1 < qw) run_quads<true, true, false, true, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0 + 1, q0 + 2, 1, run_max, &R1);")
                 out.append("  } else {")
@@ -954,7 +961,7 @@ class _Generator:
                 out.append("  }")
             else:
                 out.append("  const int64_t qe = q0 + 2 < qw ? q0 + 2 : qw;")
-                out.append("  if (A.cdf_peers) run_quads<true, true, false, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0, qe, 1, run_max);")
+                out.append("  if (kDist && A.cdf_peers) run_quads<true, true, false, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0, qe, 1, run_max);")
                 out.append("  else run_quads<false, true, false, true>(io, U, fl, A.n, A.idx_offset, key0, key1, q0, qe, 1, run_max);")
         out.append("  GJB_TP(8);")
         out.append("  float lw[gjb::kTeItems];")
@@ -964,7 +971,7 @@ class _Generator:
             out.append("  __syncthreads();  // wbuf aliases sm.pre: everyone has its weights before te_publish reuses the scratch")
         out.append("  gjb::te_publish(lw, A.cdf_out + w_loc, A.recs_out ? A.recs_out + blockIdx.x : nullptr, sm);")
         out.append("  GJB_TP(11);")
-        out.append("  if (A.link) gjb::te_finish_step(A.link, A.step, A.slot_offset, A.n, A.n_total, A.key_dev + 2, A.table_out, A.lse_out, sm);")
+        out.append("  if (kDist && A.link) gjb::te_finish_step(A.link, A.step, A.slot_offset, A.n, A.n_total, A.key_dev + 2, A.table_out, A.lse_out, sm, (A.flags & GJB_STEP_LIGHT) != 0);")
         out.append("  GJB_TP(15);")
         out.append("}")
         return out
@@ -1321,6 +1328,7 @@ int gjb_model_pf_step(const gjb_step_args* a, void* stream) {
     if (!a->table_in && (a->n_tiles_total <= 0 || a->n_tiles_total > gjb::kTeMaxTiles || (int64_t)a->n_tiles_total * gjb::kTeTile < a->n_total)) return GJB_E_ARG;
     if ((reinterpret_cast<uintptr_t>(a->prev_cdf) & 15) || (reinterpret_cast<uintptr_t>(a->prev_recs) & 15)) return GJB_E_ARG;
   }
+  if (!a->link && (a->table_in || a->table_out || a->cdf_peers || a->peer_args)) return GJB_E_ARG;  // those need the link
   const int64_t tiles = (a->n + gjb::kTeTile - 1) / gjb::kTeTile;
   if (a->flags & GJB_STEP_PDL) {
     cudaLaunchConfig_t cfg = {};
@@ -1329,9 +1337,10 @@ int gjb_model_pf_step(const gjb_step_args* a, void* stream) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return (int)cudaLaunchKernelEx(&cfg, pf_step_kernel, *a);
+    return (int)cudaLaunchKernelEx(&cfg, a->link ? pf_step_kernel_t<true> : pf_step_kernel_t<false>, *a);
   }
-  pf_step_kernel<<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a);
+  if (a->link) pf_step_kernel_t<true><<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a);
+  else pf_step_kernel_t<false><<<(int)tiles, kThreads, 0, (cudaStream_t)stream>>>(*a);
   return (int)cudaGetLastError();
 }
 """

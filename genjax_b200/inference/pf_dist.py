@@ -450,6 +450,10 @@ class _DistStepPlan:
         self.graph = None
         pdl = os.environ.get("GJB_PDL", "1") != "0"
         self.table_kernel = os.environ.get("GJB_STEP_TABLE_KERNEL", "0") == "1"
+        # rank-level table (GJB_STEP_LIGHT): the last CTA reduces the records to S, E and the ranks' prefix; the consumers
+        # form the tile prefix of their parents' rank(s) themselves.  GJB_STEP_LIGHT=0: the full per-tile table.
+        self.light = (not self.table_kernel) and os.environ.get("GJB_STEP_LIGHT", "1") != "0"
+        self.table_full = torch.zeros(C.sizeof(cabi.StepTable), dtype=torch.uint8, device=device)
         dist.barrier(pf.group)  # every rank has zeroed its arena before anyone mails into it
         # ---- per-step arguments
         self.sargs = []
@@ -459,6 +463,8 @@ class _DistStepPlan:
             A.n, A.n_total, A.idx_offset, A.slot_offset = n, pf.n_total, rank * n, rank * n
             A.step = t
             A.flags = (cabi.STEP_PDL if (pdl and t > 0) else 0) | (cabi.STEP_FLAGWAIT if os.environ.get("GJB_STEP_FLAGWAIT") == "1" else 0)
+            if self.light:
+                A.flags |= cabi.STEP_LIGHT
             A.key_dev = self.keys[t].data_ptr()
             slot = t if record else (t & 1)
             pslot = (t - 1) if record else ((t - 1) & 1)
@@ -503,6 +509,10 @@ class _DistStepPlan:
         R = cabi.TeResampleArgs()
         R.cdf = self.cdf[(T - 1) & 1].data_ptr()
         R.table = self.tables[(T - 1) & 1].data_ptr()
+        if self.light:
+            # the closing resampling reads a per-tile table: built once per run by the table kernel from the last step's records
+            self.targs[T - 1].table_out = self.table_full.data_ptr()
+            R.table = self.table_full.data_ptr()
         R.cdf_peers = self.cdf_peers[(T - 1) & 1].data_ptr()
         R.n_tiles_total, R.n_total, R.out_lo, R.out_n = tiles * world, pf.n_total, rank * n, n
         R.key_dev = self.keys[T - 1][2:].data_ptr()
@@ -525,6 +535,8 @@ class _DistStepPlan:
             cabi.check(lib.gjb_model_pf_step(C.byref(self.sargs[t]), stream), "gjb_model_pf_step")
             if self.table_kernel:
                 cabi.check(core.gjb_te_table(C.byref(self.targs[t]), stream), "gjb_te_table")
+        if self.light:
+            cabi.check(core.gjb_te_table(C.byref(self.targs[self.T - 1]), stream), "gjb_te_table(closing)")
         cabi.check(core.gjb_te_resample(C.byref(self.close), stream), "gjb_te_resample")
         for k in range(len(self.bufs)):
             cabi.check(core.gjb_gather_rows_peers(C.byref(self.final_peers[k]), self.anc[self.last].data_ptr(),
@@ -535,7 +547,7 @@ class _DistStepPlan:
         cabi.check(core.gjb_epoch_bump(self.epoch.data_ptr(), stream), "gjb_epoch_bump")
 
     def launches_per_run(self) -> int:
-        return (2 if self.table_kernel else 1) * self.T + 3 + len(self.bufs)  # step kernel (+ table kernel) per step, closing resample, gathers, barrier, epoch
+        return (2 if self.table_kernel else 1) * self.T + 3 + len(self.bufs) + (1 if self.light else 0)  # step kernel (+ table kernel) per step, closing resample, gathers, barrier, epoch
 
     def execute(self, key, state0, shared, obs, use_graph):
         # the per-step key table is derived on the device from the run key's two words (3 us; the NumPy threefry of

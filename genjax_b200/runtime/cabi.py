@@ -24,6 +24,7 @@ TE_LL_WORDS = 4
 TE_MAILBOX_WORDS = 2 * TE_MAX_TILES * TE_LL_WORDS
 STEP_PDL = 1
 STEP_FLAGWAIT = 2
+STEP_LIGHT = 4
 MASS_MAX_PARTICLES = 1 << 27
 
 SITE_SAMPLE = 1

@@ -342,6 +342,11 @@ typedef struct gjb_te_table_args {
                                 kernel on the stream drains; a step kernel draws its random numbers, then waits
                                 (griddepcontrol.wait) before it touches anything the previous launch wrote */
 #define GJB_STEP_FLAGWAIT 2u /* step kernel, table form: spin on the table's tag instead of waiting for the kernel boundary */
+#define GJB_STEP_LIGHT 4u    /* step kernel with `link`: the last CTA leaves a RANK-level table only -- S, E and, in pre[0 .. world),
+                                the inclusive prefix of the ranks' aligned masses (`reserved` = 1) -- and the consumers of the next
+                                launch form the tile prefix of the one or two ranks their window's parents live on themselves, from
+                                the records in their own mailbox (as the single-device table-free form does for its 512 tiles).  The
+                                serial tail of a step shrinks from a 4096-tile prefix + window searches to one reduction. */
 int gjb_te_table(const gjb_te_table_args* a, void* stream);
 
 typedef struct gjb_te_resample_args {

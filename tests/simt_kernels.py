@@ -148,7 +148,8 @@ STEP_DRIVER = r'''
 extern "C" int s_pf_step(const gjb_step_args* a) {
   const gjb_step_args A = *a;
   const int tiles = (int)((A.n + gjb::kTeTile - 1) / gjb::kTeTile);
-  simt::launch(tiles, kThreads, [=] { pf_step_kernel(A); });
+  if (A.link) simt::launch(tiles, kThreads, [=] { pf_step_kernel_t<true>(A); });
+  else simt::launch(tiles, kThreads, [=] { pf_step_kernel_t<false>(A); });
   return 0;
 }
 '''
@@ -186,7 +187,7 @@ def model(source: str):
         text += PULL_DRIVER
     if "pf_kernel(" in body:
         text += PF_DRIVER
-    if "pf_step_kernel(" in body:
+    if "pf_step_kernel_t(" in body:
         text += STEP_DRIVER
     if "pf_steps_kernel(" in body:
         text += STEPS_DRIVER
