@@ -467,7 +467,10 @@ def run_ours(args):
         flush.fill_(k & 0xFF)
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(device)
+        # every timed step starts from a barrier + synchronize on all ranks: with global resampling a rank's step cannot
+        # finish before the slowest rank has STARTED it, so without the barrier the host-side skew between the ranks'
+        # Python loops (L2 flush, synchronize, launch) would be counted as device time of the step
+        barrier()
         e0.record()
         res = one(100 + k, False)
         e1.record()
@@ -503,7 +506,7 @@ def run_ours(args):
             flush.fill_(k & 0xFF)
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize(device)
+            barrier()  # (the all-gather of the shard terms couples the ranks: same reason as above)
             e0.record()
             r_i = one(300 + k, False, pf_i, False)
             e1.record()

@@ -712,11 +712,36 @@ __device__ __forceinline__ uint64_t te_pull_table(const gjb_step_table* __restri
 // after every record had arrived).  Per rank this is te_pull's work on that rank's tiles.  Same outputs as te_pull.
 template <bool kCg>
 __device__ __forceinline__ uint64_t te_pull_light(const gjb_step_table* __restrict__ tab, const uint64_t* __restrict__ box, int world,
-                                                  int tpr, const gjb_peers* cdf_peers, int64_t n_total, double u0, int64_t w_lo,
-                                                  int w_n, TeSmem& sm, int32_t (&anc)[kTeItems], int* e_out) {
+                                                  int tpr, int rank_self, const gjb_peers* cdf_peers, int64_t n_total, double u0,
+                                                  int64_t w_lo, int w_n, TeSmem& sm, int32_t (&anc)[kTeItems], int* e_out) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ONE exposed L2 round trip for everything the prefix work needs: S, E, the two rank prefixes this thread tests, and --
+  // speculatively -- this thread's records of the device's OWN rank (where nearly every window's parents live)
   const uint64_t S = __ldcg(reinterpret_cast<const unsigned long long*>(&tab->S));
   const int E = __ldcg(&tab->E);
+  uint64_t rp = 0, rc = 0;
+  if (tid < world) {
+    rp = tid ? __ldcg(reinterpret_cast<const unsigned long long*>(&tab->pre[tid - 1])) : 0ull;
+    rc = __ldcg(reinterpret_cast<const unsigned long long*>(&tab->pre[tid]));
+  }
+  const int per = (tpr + kThreads - 1) / kThreads;
+  const int t0 = tid * per;
+  const bool spec = per <= 2;
+  uint64_t sm_[2] = {0ull, 0ull};
+  int se_[2] = {GJB_TE_E_NONE, GJB_TE_E_NONE};
+  if (spec) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int t = t0 + k;
+      if (k < per && t < tpr) {
+        const uint64_t* rec = box + (int64_t)(rank_self * tpr + t) * GJB_TE_LL_WORDS;
+        const ulonglong2 w01 = __ldcg(reinterpret_cast<const ulonglong2*>(rec));
+        const unsigned long long w2 = __ldcg(reinterpret_cast<const unsigned long long*>(rec + 2));
+        sm_[k] = (w01.x & 0xffffffffull) | (w01.y << 32);
+        se_[k] = (int)(uint32_t)w2;
+      }
+    }
+  }
   *e_out = E;
   if (tid == 0) { sm.p_lo = 0x7fffffff; sm.p_hi = -1; }
   *reinterpret_cast<int4*>(sm.heads + tid * kTeItems) = make_int4(0, 0, 0, 0);
@@ -731,35 +756,43 @@ __device__ __forceinline__ uint64_t te_pull_light(const gjb_step_table* __restri
   const int32_t wl = (int32_t)w_lo, wh = (int32_t)(w_lo + w_n);
   __syncthreads();
   // ---- which ranks hold parents of this window
-  if (tid < world) {
-    const uint64_t rp = tid ? __ldcg(reinterpret_cast<const unsigned long long*>(&tab->pre[tid - 1])) : 0ull;
-    const uint64_t rc = __ldcg(reinterpret_cast<const unsigned long long*>(&tab->pre[tid]));
-    if (rc != rp && offspring_cnt(rc, S, scale, u0, nt) > wl && offspring_cnt(rp, S, scale, u0, nt) < wh) {
-      atomicMin(&sm.p_lo, tid);
-      atomicMax(&sm.p_hi, tid);
-    }
+  if (tid < world && rc != rp && offspring_cnt(rc, S, scale, u0, nt) > wl && offspring_cnt(rp, S, scale, u0, nt) < wh) {
+    atomicMin(&sm.p_lo, tid);
+    atomicMax(&sm.p_hi, tid);
   }
   __syncthreads();
   const int r_lo = sm.p_lo, r_hi = sm.p_hi;
-  const int per = (tpr + kThreads - 1) / kThreads;
-  const int t0 = tid * per;
+  GJB_TP(2);
   for (int r = r_lo; r <= r_hi; ++r) {
     __syncthreads();  // r_lo / r_hi (first round) or the previous rank's prefix have been read by everyone
-    const uint64_t rbase = r ? __ldcg(reinterpret_cast<const unsigned long long*>(&tab->pre[r - 1])) : 0ull;
+    const uint64_t rbase = r ? __ldcg(reinterpret_cast<const unsigned long long*>(&tab->pre[r - 1])) : 0ull;  // (L1/L2 hit: read above)
     if (tid == 0) { sm.p_lo = 0x7fffffff; sm.p_hi = -1; }
     // aligned masses of this rank's tiles, thread-local inclusive prefix
     uint64_t run = 0;
-    for (int k = 0; k < per; ++k) {
-      const int t = t0 + k;
-      if (t < tpr) {
-        const uint64_t* rec = box + (int64_t)(r * tpr + t) * GJB_TE_LL_WORDS;
-        const ulonglong2 w01 = __ldcg(reinterpret_cast<const ulonglong2*>(rec));
-        const unsigned long long w2 = __ldcg(reinterpret_cast<const unsigned long long*>(rec + 2));
-        const uint64_t m = (w01.x & 0xffffffffull) | (w01.y << 32);
-        const int sft = m ? min(E - (int)(uint32_t)w2, 63) : 63;
-        run += m >> sft;
-        sm.pre[t] = run;
-        sm.shf[t] = (uint8_t)sft;
+    if (spec && r == rank_self) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int t = t0 + k;
+        if (k < per && t < tpr) {
+          const int sft = sm_[k] ? min(E - se_[k], 63) : 63;
+          run += sm_[k] >> sft;
+          sm.pre[t] = run;
+          sm.shf[t] = (uint8_t)sft;
+        }
+      }
+    } else {
+      for (int k = 0; k < per; ++k) {
+        const int t = t0 + k;
+        if (t < tpr) {
+          const uint64_t* rec = box + (int64_t)(r * tpr + t) * GJB_TE_LL_WORDS;
+          const ulonglong2 w01 = __ldcg(reinterpret_cast<const ulonglong2*>(rec));
+          const unsigned long long w2 = __ldcg(reinterpret_cast<const unsigned long long*>(rec + 2));
+          const uint64_t m = (w01.x & 0xffffffffull) | (w01.y << 32);
+          const int sft = m ? min(E - (int)(uint32_t)w2, 63) : 63;
+          run += m >> sft;
+          sm.pre[t] = run;
+          sm.shf[t] = (uint8_t)sft;
+        }
       }
     }
     uint64_t inc = run;
@@ -770,6 +803,7 @@ __device__ __forceinline__ uint64_t te_pull_light(const gjb_step_table* __restri
     }
     if (lane == 31) sm.red[warp] = inc;
     __syncthreads();
+    GJB_TP(3);
     uint64_t excl = rbase + inc - run;
 #pragma unroll
     for (int w = 0; w < kThreads / 32; ++w)
@@ -797,6 +831,7 @@ __device__ __forceinline__ uint64_t te_pull_light(const gjb_step_table* __restri
     }
     __syncthreads();
     const int p_lo = sm.p_lo, p_hi = sm.p_hi;
+    GJB_TP(4);
     // every parent with offspring in the window drops its id (+1) at its first slot
     const uint64_t* rows = reinterpret_cast<const uint64_t*>(cdf_peers->base[r]) + tid * kTeItems;
     for (int p = p_lo; p <= p_hi; ++p) {
@@ -820,6 +855,7 @@ __device__ __forceinline__ uint64_t te_pull_light(const gjb_step_table* __restri
     }
   }
   __syncthreads();
+  GJB_TP(5);
   // ---- inclusive max-scan over the window (as te_pull)
   int32_t v[kTeItems];
   {
@@ -843,6 +879,7 @@ __device__ __forceinline__ uint64_t te_pull_light(const gjb_step_table* __restri
     if (w < warp) pre = max(pre, sm.ired[w]);
 #pragma unroll
   for (int k = 0; k < kTeItems; ++k) anc[k] = max(v[k], pre) - 1;
+  GJB_TP(6);
   return S;
 }
 

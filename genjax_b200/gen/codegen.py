@@ -901,6 +901,12 @@ class _Generator:
             out.append("  quad_rng<true>(fl, key0, key1, (A.idx_offset >> 2) + (uint64_t)q0, R0);")
             out.append("  quad_rng<true>(fl, key0, key1, (A.idx_offset >> 2) + (uint64_t)q0 + 1, R1);")
         out.append("  GJB_TP(1);")
+        out.append("  // constants of the link (not written by any launch): read before the wait, off the critical path")
+        out.append("  int lk_world = 1, lk_tpr = 0, lk_rank = 0; const uint64_t* lk_box = nullptr;")
+        out.append("  if (kDist && A.link && A.step > 0 && (A.flags & GJB_STEP_LIGHT)) {")
+        out.append("    lk_world = A.link->world; lk_tpr = A.link->tiles_per_rank; lk_rank = A.link->rank;")
+        out.append("    lk_box = gjb::te_mail_slot(A.link->mailbox[lk_rank], A.step - 1, 0);")
+        out.append("  }")
         out.append("  // table form: the table kernel runs BESIDE the step kernels and flags its table with the step's tag; the CTAs spin on")
         out.append("  // that flag (te_pull_table) instead of waiting for a kernel boundary -- every record behind the table was mailed after")
         out.append("  // its tile's data was fenced into L2, so the flag covers the bulk data too.  Table-free form: wait for the previous launch.")
@@ -908,6 +914,7 @@ class _Generator:
         out.append("  // opt-in: GJB_STEP_FLAGWAIT)")
         out.append("  const bool flagged = kDist && A.table_in && A.link && (A.flags & GJB_STEP_FLAGWAIT);")
         out.append("  if (!flagged) gjb::pdl_wait();")
+        out.append("  GJB_TP(12);")
         out.append("  if (A.prev_cdf) {  // ancestors of MY slots: output-slot systematic resampling of the previous step")
         out.append("    const double u0 = gjb::resample_u0(__ldg(A.prev_key), __ldg(A.prev_key + 1), (uint64_t)__ldg(A.prev_key + 2) | ((uint64_t)__ldg(A.prev_key + 3) << 32));")
         out.append("    int32_t anc[gjb::kTeItems];")
@@ -917,8 +924,7 @@ class _Generator:
         out.append("      // (peer memory is read through L2 (ld.global.cg); on one device the read-only path is used: griddepcontrol.wait")
         out.append("      // above makes the previous launch's writes visible to it, measured 1.4 us per step faster than .cg)")
         out.append("      if (A.cdf_peers && A.link && (A.flags & GJB_STEP_LIGHT))  // rank-level table: the tile prefix of the parents' rank(s) is formed here")
-        out.append("        gjb::te_pull_light<true>(A.table_in, gjb::te_mail_slot(A.link->mailbox[A.link->rank], A.step - 1, 0), A.link->world,")
-        out.append("                                 A.link->tiles_per_rank, A.cdf_peers, A.n_total, u0, w_glob, w_n, sm, anc, &E);")
+        out.append("        gjb::te_pull_light<true>(A.table_in, lk_box, lk_world, lk_tpr, lk_rank, A.cdf_peers, A.n_total, u0, w_glob, w_n, sm, anc, &E);")
         out.append("      else if (A.cdf_peers) gjb::te_pull_table<true>(A.table_in, (int)blockIdx.x, A.prev_cdf, A.cdf_peers, A.n_total, u0, w_glob, w_n, sm, anc, &E,")
         out.append("                                                flagged ? gjb::te_tag(A.link, A.step - 1) : 0u);")
         out.append("      else gjb::te_pull_table<false>(A.table_in, (int)blockIdx.x, A.prev_cdf, nullptr, A.n_total, u0, w_glob, w_n, sm, anc, &E,")

@@ -450,9 +450,12 @@ class _DistStepPlan:
         self.graph = None
         pdl = os.environ.get("GJB_PDL", "1") != "0"
         self.table_kernel = os.environ.get("GJB_STEP_TABLE_KERNEL", "0") == "1"
-        # rank-level table (GJB_STEP_LIGHT): the last CTA reduces the records to S, E and the ranks' prefix; the consumers
-        # form the tile prefix of their parents' rank(s) themselves.  GJB_STEP_LIGHT=0: the full per-tile table.
-        self.light = (not self.table_kernel) and os.environ.get("GJB_STEP_LIGHT", "1") != "0"
+        # rank-level table (GJB_STEP_LIGHT=1, opt-in): the last CTA reduces the records to S, E and the ranks' prefix; the
+        # consumers form the tile prefix of their parents' rank(s) themselves.  Measured on 2 / 4 / 8 B200s
+        # (profiles/r2_call26_*): 39.8 / 42.9 / 51.7 us per step against 29.0 / 36.0 / 53.0 for the per-tile table built by
+        # the last CTA -- the longer dependent-load chain in every consumer CTA costs more than the shorter serial tail
+        # saves until 8 ranks, so the per-tile table stays the default.
+        self.light = (not self.table_kernel) and os.environ.get("GJB_STEP_LIGHT", "0") == "1"
         self.table_full = torch.zeros(C.sizeof(cabi.StepTable), dtype=torch.uint8, device=device)
         dist.barrier(pf.group)  # every rank has zeroed its arena before anyone mails into it
         # ---- per-step arguments

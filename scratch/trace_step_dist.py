@@ -27,9 +27,11 @@ buf = (C.c_ulonglong * (tiles * 16))()
 lib.gjb_model_trace_read.argtypes = [C.c_void_p, C.c_int]
 assert lib.gjb_model_trace_read(buf, tiles * 16) == 0
 t = np.frombuffer(buf, dtype=np.uint64).reshape(tiles, 16).astype(np.int64)
-names = {0: "entry", 1: "RNG drawn", 4: "pdl_wait + table + first rows", 5: "parent loop", 6: "max-scan", 8: "gather + body",
+light = os.environ.get("GJB_STEP_LIGHT", "1") != "0" and os.environ.get("GJB_STEP_TABLE_KERNEL", "0") != "1"
+names = {0: "entry", 1: "RNG drawn", 12: "wait for the previous launch", 2: "table S/E + rank range", 3: "records + rank prefix",
+         4: "tile range" if light else "table + first rows", 5: "parent loop", 6: "max-scan", 8: "gather + body",
          9: "tile max", 10: "masses + scan", 11: "cdf stores", 15: "mail records"}
-order = [0, 1, 4, 5, 6, 8, 9, 10, 11]
+order = [0, 1, 12, 2, 3, 4, 5, 6, 8, 9, 10, 11] if light else [0, 1, 12, 4, 5, 6, 8, 9, 10, 11]
 for r in range(world):
     if r == rank:
         print(f"[rank {rank}] pf_step_kernel (global resampling, {world} GPUs): cycles per phase, mean [p95] max(CTA)")
