@@ -750,6 +750,26 @@ using namespace gjb;
 
 extern "C" {
 
+// ---- measurement probe (not part of the ABI header; scratch/probe_remote_stores.py): `ctas` CTAs each issue `dests` x `words`
+// 8-byte volatile stores into `dst` (a peer-mapped buffer), the record-mailing pattern of te_finish_step, or -- coalesced = 1 --
+// ONE CTA writes the same words with consecutive threads on consecutive addresses.
+__global__ void remote_store_probe_kernel(uint64_t* dst, int dests, int words, int coalesced, uint64_t tag) {
+  if (coalesced) {
+    const int total = (int)gridDim.x * dests * words;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) te_st_volatile(dst + i, tag | (uint64_t)i);
+    return;
+  }
+  if ((int)threadIdx.x < dests) {
+    __threadfence();
+    uint64_t* d = dst + ((int64_t)threadIdx.x * gridDim.x + blockIdx.x) * 4;
+    for (int w = 0; w < words; ++w) te_st_volatile(d + w, tag | (uint64_t)w);
+  }
+}
+int gjb_remote_store_probe(void* dst, int ctas, int dests, int words, int coalesced, uint64_t tag, void* stream) {
+  remote_store_probe_kernel<<<coalesced ? 8 : ctas, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint64_t*>(dst), dests, words, coalesced, tag);
+  return launch_status();
+}
+
 int gjb_abi_version(void) { return GJB_ABI_VERSION; }
 
 int64_t gjb_resample_workspace_bytes(int64_t n) {

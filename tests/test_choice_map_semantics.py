@@ -191,8 +191,13 @@ def test_extend_through_at():  # test_extend_through_at
 def test_mask_extend_merge():  # test_mask / test_extend / test_merge / test_static_is_empty
     chm = ChoiceMap.kw(x=1, y=2)
     assert chm.mask(True) == chm and chm.mask(False).static_is_empty()
+    # a flag ARRAY wraps every leaf in Mask(value, flag) (choice_map.py ``mask``; the form of a Mask-ed constraint)
+    from genjax_b200 import Mask
+
+    masked = chm.mask(torch.tensor(True))
+    assert isinstance(masked["x"], Mask) and masked["x"].value == 1 and bool(masked["x"].flag)
     with pytest.raises(NotImplementedError):
-        chm.mask(torch.tensor(True))
+        chm.mask("not a flag")
     ext = ChoiceMap.choice(1).extend("a", "b")
     assert ext["a", "b"] == 1 and ext.get_value() is None and ext.get_submap("a", "b").get_value() == 1
     assert ChoiceMap.empty().extend("a", "b").static_is_empty()
