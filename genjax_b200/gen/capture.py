@@ -232,6 +232,15 @@ def inline_call(gen_fn, args):
 # ----------------------------------------------------------------- pytrees
 
 
+class StackedList(list):
+    """Per-element values of an unrolled Scan / Vmap: a Python list while the body is captured (``ys[0]``, ``sum(ys)``);
+    as a return value its tensor leaves come back stacked along the mapped axis (after the particle axis), which is what
+    the reference's vectorised traces hold."""
+
+
+_STACK_DIM: contextvars.ContextVar = contextvars.ContextVar("genjax_b200_stack_dim", default=0)
+
+
 def flatten(tree, is_leaf=None) -> tuple[list, Any]:
     """Minimal pytree flatten over tuple / list / dict (``is_leaf(node)`` stops the descent, as in jax.tree_util)."""
     leaves: list = []
@@ -257,6 +266,8 @@ def flatten(tree, is_leaf=None) -> tuple[list, Any]:
             return ("dataclass", (type(t), [(f.name, go(getattr(t, f.name))) for f in dataclasses.fields(t)]))
         if isinstance(t, tuple):
             return ("tuple", [go(x) for x in t])
+        if isinstance(t, StackedList):
+            return ("stack", [go(x) for x in t])
         if isinstance(t, list):
             return ("list", [go(x) for x in t])
         if isinstance(t, dict):
@@ -296,6 +307,13 @@ def unflatten(tree, leaves):
     if kind == "dataclass":
         cls, fields = payload
         return cls(**{name: unflatten(sub, leaves) for name, sub in fields})
+    if kind == "stack":
+        items = [unflatten(x, leaves) for x in payload]
+        if items and all(hasattr(v, "dim") and hasattr(v, "device") for v in items):
+            import torch
+
+            return torch.stack(items, dim=min(_STACK_DIM.get(), items[0].dim()))
+        return StackedList(items)
     if kind == "tuple":
         return tuple(unflatten(x, leaves) for x in payload)
     if kind == "list":
@@ -344,6 +362,9 @@ def capture(source: Callable, name: str, arg_specs: list, arg_tree, cmask_addrs=
     ir = ModelIR(name, list(arg_specs), arg_exprs, cap.sites, ret_leaves, ret_tree, width=(widths.pop() if widths else 0),
                  subcalls=cap.subcalls, n_user_args=n_user)
     # validity flags of the sites under a Switch / MaskCombinator leave the kernel as extra (hidden) return leaves
+    # (``flag_of`` indexes the combined list [return leaves..., hidden flag leaves...]; a flag the model itself returns --
+    # the ``Mask(retval, check)`` of a MaskCombinator -- is not written twice)
+    returned = {r._id: k for k, r in enumerate(ret_leaves) if isinstance(r, Expr) and r.ndim == 0}
     seen: dict = {}
     for s in cap.sites:
         f = s.flag()
@@ -351,8 +372,11 @@ def capture(source: Callable, name: str, arg_specs: list, arg_tree, cmask_addrs=
             continue
         key = (s.live._id if s.live is not None else 0, s.scored._id if s.scored is not None else 0)
         if key not in seen:
-            seen[key] = len(ir.flag_leaves)
-            ir.flag_leaves.append(f)
+            if f._id in returned:
+                seen[key] = returned[f._id]
+            else:
+                seen[key] = len(ret_leaves) + len(ir.flag_leaves)
+                ir.flag_leaves.append(f)
         ir.flag_of[s.index] = seen[key]
     if len(ir.sites) > 32:
         raise NotImplementedError("more than 32 random-choice sites in one static model (GJB_MAX_SITES)")

@@ -178,7 +178,7 @@ def _stack_lists(per_step: list):
         return None
     flat = [cap.flatten(y) for y in per_step]
     shape = flat[0][1]
-    return cap.unflatten(shape, [[f[0][j] for f in flat] for j in range(len(flat[0][0]))])
+    return cap.unflatten(shape, [cap.StackedList(f[0][j] for f in flat) for j in range(len(flat[0][0]))])
 
 
 # -------------------------------------------------------------------- trace
@@ -318,7 +318,7 @@ class Scan(GenerativeFunction):
         if self.post is _prepend_initial:  # accumulate / iterate: [init, c_1, ..., c_T]
             i_leaves, _ = cap.flatten(init)
             c_leaves, c_shape = cap.flatten(stacked, is_leaf=lambda v: isinstance(v, list))
-            return cap.unflatten(c_shape, [[i] + list(cs) for i, cs in zip(i_leaves, c_leaves)])
+            return cap.unflatten(c_shape, [cap.StackedList([i] + list(cs)) for i, cs in zip(i_leaves, c_leaves)])
         return self.post((init, xs), (carry, stacked))
 
     def unrolled(self, T: int) -> StaticGenerativeFunction:

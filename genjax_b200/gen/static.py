@@ -258,7 +258,11 @@ class StaticTrace(Trace):
 
     def get_retval(self):
         leaves = [self._view(r) for r in self.ret_leaves]
-        return cap.unflatten(self.cm.ir.ret_tree, leaves)
+        tok = cap._STACK_DIM.set(1 if self.batched else 0)  # unrolled Scan / Vmap outputs stack after the particle axis
+        try:
+            return cap.unflatten(self.cm.ir.ret_tree, leaves)
+        finally:
+            cap._STACK_DIM.reset(tok)
 
     def _site_value(self, s):
         v = self.values[s.index]
@@ -352,13 +356,31 @@ def _choices_from_sites(trace: StaticTrace, sites) -> ChoiceMap:
     groups: dict = {}
     for addr, v in merged.items():
         st = stacks.get(addr)
-        if st and len(st) == 1 and isinstance(v, torch.Tensor):
-            groups.setdefault(addr[: st[0]] + addr[st[0] + 1:], []).append((addr[st[0]], v))
+        if st and len(st) == 1 and isinstance(v, (torch.Tensor, Mask)):
+            groups.setdefault(addr[: st[0]] + addr[st[0] + 1:], []).append((addr[st[0]], v, addr))
         else:
             chm = chm | ChoiceMap.entry(v, *addr)
+    dim = 1 if trace.batched else 0
+    totals: dict = {}
+    for s in trace.cm.ir.sites:
+        if s.stack and len(s.stack) == 1:
+            k = s.addr[: s.stack[0]] + s.addr[s.stack[0] + 1:]
+            totals.setdefault(k, set()).add(s.addr[s.stack[0]])
     for addr, steps in groups.items():
         steps.sort(key=lambda p: p[0])
-        chm = chm | ChoiceMap.entry(torch.stack([v for _, v in steps], dim=1 if trace.batched else 0), *addr)
+        vals = [v for _, v, _ in steps]
+        if len({i for i, _, _ in steps}) < len(totals.get(addr, ())):
+            # only some elements (the discard of an update at one index): they stay under their own indices
+            for _, v, full in steps:
+                chm = chm | ChoiceMap.entry(v, *full)
+        elif all(isinstance(v, Mask) for v in vals):  # masked elements: Mask(stacked values, stacked flags)
+            chm = chm | ChoiceMap.entry(Mask(torch.stack([v.value for v in vals], dim=dim),
+                                             torch.stack([v.flag for v in vals], dim=dim)), *addr)
+        elif any(isinstance(v, Mask) for v in vals):  # (some elements masked, some not: kept apart under their indices)
+            for _, v, full in steps:
+                chm = chm | ChoiceMap.entry(v, *full)
+        else:
+            chm = chm | ChoiceMap.entry(torch.stack(vals, dim=dim), *addr)
     return chm
 
 
@@ -778,8 +800,9 @@ class StaticGenerativeFunction(GenerativeFunction):
             flag_bufs.append(fb)
 
         cabi.check(cm.lib.gjb_model_launch(C.byref(A), cabi.stream_ptr(device)), f"gjb_model_launch({self.__name__})")
+        n_ret = len(ir.ret_leaves)
         tr = StaticTrace(self, cm, bound, args, n_run, is_batched, values, score, ret_leaves, bcast,
-                         {j: flag_bufs[m] for j, m in ir.flag_of.items()})
+                         {j: (ret_leaves[m] if m < n_ret else flag_bufs[m - n_ret]) for j, m in ir.flag_of.items()})
         tr._mask_discard = mask_discard
         return tr, weight
 

@@ -208,6 +208,92 @@ class MaskCombinator(_InlinedCombinator):
         return tr
 
 
+def _mapped_size(tree, axes, sizes: list):
+    """Leading sizes of the leaves mapped along axis 0 (``axes``: a tree prefix of 0 / None, as jax.vmap's in_axes)."""
+    if isinstance(axes, (tuple, list)) and isinstance(tree, (tuple, list)):
+        if len(axes) != len(tree):
+            raise ValueError("vmap in_axes specification must be a tree prefix of the corresponding value")
+        for t, a in zip(tree, axes):
+            _mapped_size(t, a, sizes)
+        return
+    if axes is None:
+        return
+    if axes != 0:
+        raise NotImplementedError("only in_axes of 0 / None are supported")
+    for leaf in cap.flatten(tree)[0]:
+        if hasattr(leaf, "shape") and len(leaf.shape) >= 1:
+            sizes.append(int(leaf.shape[0]))
+        elif isinstance(leaf, (list, tuple)):
+            sizes.append(len(leaf))
+        else:
+            raise ValueError("vmap in_axes=0 on a value without a leading axis")
+
+
+def _index_mapped(tree, axes, i: int):
+    if isinstance(axes, (tuple, list)) and isinstance(tree, (tuple, list)):
+        return type(tree)(_index_mapped(t, a, i) for t, a in zip(tree, axes))
+    if axes is None:
+        return tree
+    leaves, shape = cap.flatten(tree)
+    return cap.unflatten(shape, [v[i] for v in leaves])
+
+
+def unrolled_vmap(gen_fn, in_axes, axis_size, args):
+    """``gen_fn.vmap(in_axes=...)(*args) @ addr`` inside an ``@gen`` body: the mapped axis is UNROLLED into the caller's
+    fused kernel (vmap.py:180-218: the inner call per element, scores summed) -- element i's sites are recorded under
+    ``(..., i, addr)`` and read back stacked (``chm[addr, :, sub]``), the per-element return values come back stacked.
+    This is also how a vmapped function runs under an outer particle batch (the two axes the top-level ``Vmap`` cannot
+    hold).  ``n x sites per element`` has to fit the kernel's site table."""
+    c = cap.current_capture()
+    if c is None:
+        raise RuntimeError("a vmapped generative function can only be traced inside a @gen function body")
+    args = tuple(args)
+    axes = tuple(in_axes) if isinstance(in_axes, (tuple, list)) else (in_axes,) * len(args)
+    if len(axes) != len(args):
+        raise ValueError("vmap in_axes specification must be a tree prefix of the corresponding value")
+    sizes: list = []
+    for a, ax in zip(args, axes):
+        _mapped_size(a, ax, sizes)
+    if sizes and any(s != sizes[0] for s in sizes):
+        raise IndexError(f"vmap got inconsistent sizes for the mapped axis: {sizes}")
+    n = sizes[0] if sizes else axis_size
+    if n is None:
+        raise ValueError("vmap has nothing to map over (every in_axes entry is None); use repeat(n=...)")
+    prefix, positions = c.prefix, c.scan_positions
+    rets = []
+    try:
+        c.scan_positions = positions + (len(prefix),)
+        for i in range(int(n)):
+            c.prefix = prefix + (i,)
+            rets.append(cap.inline_call(gen_fn, tuple(_index_mapped(a, ax, i) for a, ax in zip(args, axes))))
+    finally:
+        c.prefix, c.scan_positions = prefix, positions
+    from .scan import _stack_lists
+
+    return _stack_lists(rets)
+
+
+class UnrolledVmap(_InlinedCombinator):
+    """``combinator.vmap(in_axes=...)`` for the inlined combinators (``f.mask().vmap()``, ``f.switch(g).vmap()``)."""
+
+    def __init__(self, gen_fn, in_axes=0, axis_size: int | None = None):
+        self.gen_fn, self.in_axes, self.axis_size = gen_fn, in_axes, axis_size
+
+    def __repr__(self):
+        return f"Vmap({self.gen_fn!r}, in_axes={self.in_axes})"
+
+    def capture_inline(self, args):
+        return unrolled_vmap(self.gen_fn, self.in_axes, self.axis_size, args)
+
+
+def _combinator_vmap(self, in_axes=0, axis_size: int | None = None):
+    return UnrolledVmap(self, in_axes, axis_size)
+
+
+_InlinedCombinator.vmap = _combinator_vmap
+_InlinedCombinator.repeat = lambda self, n: UnrolledVmap(self, None, int(n))
+
+
 def switch(*gen_fns) -> Switch:
     """``genjax.switch(f, g, ...)`` (switch.py:313-354)."""
     return Switch(*gen_fns)

@@ -13,9 +13,13 @@ A constraint that names only SOME indices (``C[0, "z"].set(3.0)``) splits the
 lanes into contiguous runs with the same constrained addresses, one launch per
 run (per-site flags are uniform within a launch).
 
-Top-level use with a single key only; a vmapped function under an outer
-particle batch (two batch axes) is not supported -- inside an ``@gen`` body use
-``normal.vmap(...)`` / ``normal.repeat(n=...)`` (gen/distributions.py).
+With a single key the mapped axis is the launch's lane axis.  Under an OUTER
+particle batch (a ``KeyBatch``, per-particle arguments) and inside an ``@gen``
+body (``f.vmap(in_axes=...)(*args) @ "addr"``) the mapped axis is UNROLLED into
+the fused kernel (``capture_inline`` -> gen/switch.py ``unrolled_vmap``): element
+i's sites are ``(..., i, addr)``, read back stacked; ``n x sites per element``
+must fit the site table.  For primitives, ``dist.vmap(...)`` / ``dist.repeat(n=)``
+(gen/distributions.py) make ONE vector site instead.
 """
 
 from __future__ import annotations
@@ -145,6 +149,12 @@ class Vmap(GenerativeFunction):
         self.axis_size = axis_size  # repeat(n=...): nothing is mapped, the axis has this length
         self.__name__ = f"vmap({gen_fn.__name__})"
 
+    # -- nested use: ``f.vmap(in_axes=...)(*args) @ "addr"`` inside an @gen body: unrolled into the caller's kernel
+    def capture_inline(self, args):
+        from .switch import unrolled_vmap
+
+        return unrolled_vmap(self.gen_fn, self.in_axes if self.in_axes is not None else None, self.axis_size, args)
+
     # -- helpers -----------------------------------------------------------
     def _bind(self, key, args):
         if isinstance(key, KeyBatch):
@@ -235,24 +245,47 @@ class Vmap(GenerativeFunction):
             inner.args = marked  # the concatenation kept the first run's slice; the trace spans all lanes
         return inner, (torch.cat(weight).sum() if weight else None), discard
 
+    def _unrolled(self) -> StaticGenerativeFunction:
+        """The same function with the mapped axis unrolled into ONE static model (``capture_inline``): the form that runs
+        under an OUTER particle batch -- a batched key, or per-particle arguments (vmap.py:180-275 under ``jax.vmap``)."""
+        if getattr(self, "_unrolled_fn", None) is None:
+            fn = StaticGenerativeFunction(lambda *args: self.capture_inline(args))
+            fn.__name__ = f"{self.gen_fn.__name__}_vmap_unrolled"
+            self._unrolled_fn = fn
+        return self._unrolled_fn
+
+    @staticmethod
+    def _outer_batch(key, args) -> bool:
+        if isinstance(key, KeyBatch):
+            return True
+        return any(isinstance(v, Batched) for v in cap.flatten(tuple(args))[0])
+
     # -- GFI ---------------------------------------------------------------
     def simulate(self, key: PRNGKey, args: tuple) -> VmapTrace:
+        if self._outer_batch(key, args):
+            return self._unrolled().simulate(key, tuple(args))
         _, marked, n = self._bind(key, args)
         inner, _, _ = self._launch_runs(key, marked, n, None, None, "simulate")
         return VmapTrace(self, inner, args, n)
 
     def generate(self, key: PRNGKey, constraint: ChoiceMap, args: tuple):
+        if self._outer_batch(key, args):
+            return self._unrolled().generate(key, constraint, tuple(args))
         device, marked, n = self._bind(key, args)
         inner, w, _ = self._launch_runs(key, marked, n, constraint, None, "generate")
         return VmapTrace(self, inner, args, n), w
 
     def assess(self, sample: ChoiceMap, args: tuple):
+        if self._outer_batch(None, args) or any(isinstance(v, Batched) for _, v in sample.leaves()):
+            return self._unrolled().assess(sample, tuple(args))
         _, marked, n = self._bind(None, args)
         inner, _, _ = self._launch_runs(None, marked, n, sample, None, "assess")
         tr = VmapTrace(self, inner, args, n)
         return tr.get_score(), tr.get_retval()
 
     def project(self, key, trace: VmapTrace, selection: Selection):
+        if not isinstance(trace, VmapTrace):  # a trace of the unrolled form (outer particle batch)
+            return self._unrolled().project(key, trace, selection)
         return self.gen_fn.project(key, trace.inner, selection).sum()
 
     def _edit_index(self, key, trace: VmapTrace, request: IndexRequest, argdiffs):
@@ -271,6 +304,10 @@ class Vmap(GenerativeFunction):
         return new, w.reshape(-1)[0], Diff.unknown_change(new.get_retval()), IndexRequest(idx, bwd)
 
     def edit(self, key, trace: VmapTrace, request: EditRequest, argdiffs):
+        if not isinstance(trace, VmapTrace):  # a trace of the unrolled form (outer particle batch)
+            if isinstance(request, IndexRequest):
+                raise NotImplementedError("IndexRequest on a vmapped trace under an outer particle batch")
+            return self._unrolled().edit(key, trace, request, argdiffs)
         if isinstance(request, IndexRequest):
             return self._edit_index(key, trace, request, argdiffs)
         if not isinstance(request, (Update, Regenerate)):

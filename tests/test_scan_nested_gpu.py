@@ -160,3 +160,98 @@ def test_simple_scan_hmc(device):
     x = _np(cur.get_choices()[:, "x"])
     assert x.shape == (n, 10)
     assert np.abs(x.mean(0) - 3.0).max() < 8e-3 * 3.0
+
+
+def test_vmap_nested_in_gen_under_a_particle_batch(device):
+    """``f.vmap(in_axes=...)(...) @ addr`` inside a body: the mapped axis is unrolled into the caller's kernel, which is
+    also how a vmapped function runs under an outer particle batch (vmap.py:180-218).  Plain @gen callee, a masked
+    callee over a vector of flags (test_mask_combinator.py:105-131, 160-176) and a masked distribution."""
+    gj = _gj()
+
+    @gj.gen
+    def elem(m, s):
+        z = gj.normal(m, s) @ "z"
+        return z * 2.0
+
+    @gj.gen
+    def init():
+        return gj.normal(0.0, 1.0) @ "x"
+
+    masks = torch.tensor([True, False, True])
+
+    @gj.gen
+    def model(locs, x):
+        zs = elem.vmap(in_axes=(0, None))(locs, 0.5) @ "elems"
+        vm = init.mask().vmap(in_axes=(0,))(masks) @ "init"
+        rats = gj.normal.mask().vmap(in_axes=(0, None, None))(masks, x, 1.0) @ "rats"
+        return zs, vm, rats
+
+    n = 5003
+    locs = torch.tensor([-1.0, 0.0, 1.0, 2.0])
+    tr = model.simulate(gj.split(gj.key(51), n), (locs, 0.25))
+    zs, vm, rats = tr.get_retval()
+    chm = tr.get_choices()
+    z = _np(chm["elems", :, "z"])
+    assert z.shape == (n, 4) and tuple(zs.shape) == (n, 4)
+    np.testing.assert_allclose(_np(zs), 2.0 * z, rtol=1e-6)
+    np.testing.assert_allclose(z.mean(0), locs.numpy(), atol=0.05)
+    assert isinstance(vm, gj.Mask) and tuple(vm.value.shape) == (n, 3)
+    np.testing.assert_array_equal(_np(vm.flag), np.broadcast_to(masks.numpy(), (n, 3)))
+    xi = chm["init", :, "x"]
+    assert isinstance(xi, gj.Mask) and tuple(xi.value.shape) == (n, 3)
+    np.testing.assert_array_equal(_np(xi.value), _np(vm.value))
+    r = chm["rats"]
+    assert isinstance(r, gj.Mask) and tuple(r.value.shape) == (n, 3) and isinstance(rats, gj.Mask)
+    mk = masks.numpy().astype(F32)
+    want = (od.normal_logpdf(z, locs.numpy()[None, :], F32(0.5)).sum(1)
+            + (mk[None, :] * od.normal_logpdf(_np(xi.value), F32(0.0), F32(1.0))).sum(1)
+            + (mk[None, :] * od.normal_logpdf(_np(r.value), F32(0.25), F32(1.0))).sum(1))
+    np.testing.assert_allclose(_np(tr.get_score()), want, rtol=1e-4, atol=1e-4)
+    # the masked elements are drawn all the same (mask.py:158-165: the callee always runs)
+    assert (np.abs(_np(xi.value)[:, 1]) > 0).all()
+
+    # constraints over the mapped axis, per element and as a whole
+    cons = gj.C["elems", :, "z"].set(torch.tensor([0.5, 0.5, 0.5, 0.5])) | gj.C["rats", 0].set(1.5)
+    tr2, w = model.importance(gj.split(gj.key(52), n), cons, (locs, 0.25))
+    want_w = float(od.normal_logpdf(F32(0.5), locs.numpy(), F32(0.5)).sum() + od.normal_logpdf(F32(1.5), F32(0.25), F32(1.0)))
+    np.testing.assert_allclose(_np(w), want_w, rtol=1e-5)
+    assert (_np(tr2.get_choices()["rats"].value)[:, 0] == 1.5).all()
+
+    # top level: a vector of flags through mask().vmap() (test_mask_combinator.py:238-244)
+    tr3 = init.mask().vmap().simulate(gj.key(1), (masks,))
+    assert bool((tr3.get_retval().flag == masks.to(tr3.get_retval().flag.device)).all())
+
+
+def test_top_level_vmap_under_an_outer_particle_batch(device):
+    """``model.vmap(in_axes=...)`` called with a KeyBatch (``jax.vmap`` over split keys of a vmapped generative function,
+    tests/generative_functions/test_vmap_combinator.py:208-228): two batch axes, the inner one unrolled into the kernel.
+    simulate / importance / update (vmap.py:237-275) against the closed forms."""
+    gj = _gj()
+
+    @gj.gen
+    def elem(m, s):
+        z = gj.normal(m, s) @ "z"
+        return z + 1.0
+
+    vm = elem.vmap(in_axes=(0, None))
+    n, k = 3001, 5
+    locs = torch.linspace(-2.0, 2.0, k)
+    kb = gj.split(gj.key(61), n)
+    tr = vm.simulate(kb, (locs, 0.5))
+    z = _np(tr.get_choices()[:, "z"])
+    assert z.shape == (n, k)
+    np.testing.assert_allclose(_np(tr.get_retval()), z + 1.0, rtol=1e-6)
+    np.testing.assert_allclose(_np(tr.get_score()), od.normal_logpdf(z, locs.numpy()[None, :], F32(0.5)).sum(1), rtol=1e-4, atol=1e-4)
+    assert abs(z.mean(0) - locs.numpy()).max() < 0.05
+
+    obs = torch.tensor([0.1, 0.2, 0.3, 0.4, 0.5])
+    tr2, w = vm.importance(kb, gj.C[:, "z"].set(obs), (locs, 0.5))
+    want = float(od.normal_logpdf(obs.numpy(), locs.numpy(), F32(0.5)).sum())
+    np.testing.assert_allclose(_np(w), want, rtol=1e-5)
+    # update one element of every particle's vector (vmap.py:237-275 under the outer batch)
+    tr3, w3, _, disc = tr.update(gj.split(gj.key(62), n), gj.C[2, "z"].set(0.0))
+    z3 = _np(tr3.get_choices()[:, "z"])
+    assert (z3[:, 2] == 0).all() and (np.delete(z3, 2, 1) == np.delete(z, 2, 1)).all()
+    dw = od.normal_logpdf(F32(0.0), F32(locs[2].item()), F32(0.5)) - od.normal_logpdf(z[:, 2], F32(locs[2].item()), F32(0.5))
+    np.testing.assert_allclose(_np(w3), dw, rtol=2e-4, atol=2e-4)
+    np.testing.assert_array_equal(_np(disc[2, "z"]), z[:, 2])

@@ -541,3 +541,135 @@ def test_switch_model_in_importance_sampling(device):
 
     exact = math.log(0.25 * nmix(1.0, 1.0 + 0.25) + 0.75 * nmix(1.0, 1.0 + 9.0))
     assert float(lz) == pytest.approx(exact, abs=0.01)
+
+
+def test_particle_filter_over_a_switching_model(device):
+    """The headline path over a model with dynamic structure: a regime-switching state-space model (10 % of the steps
+    jump) through the one-launch-per-step filter and through the exact-max graph filter; log-evidence against a grid
+    forward filter."""
+    gj = _gj()
+    jnp = gj.numpy
+    from genjax_b200.inference.pf import ParticleFilter
+
+    @gj.gen
+    def calm(x):
+        return gj.normal(0.9 * x, 0.3) @ "x"
+
+    @gj.gen
+    def jump(x):
+        return gj.normal(0.0, 3.0) @ "x"
+
+    @gj.gen
+    def step(x_prev):
+        b = gj.flip(0.1) @ "b"
+        x = calm.switch(jump)(jnp.int32(b), (x_prev,), (x_prev,)) @ "s"
+        gj.normal(x, 0.5) @ "y"
+        return x
+
+    ys = np.array([0.1, 0.2, 3.0, 2.9, 0.0, -1.0, -0.8, 2.0], dtype=np.float64)
+    # grid forward filter: x_0 = 0, p(x_t | x) = 0.9 N(0.9 x, 0.3) + 0.1 N(0, 3), y_t ~ N(x_t, 0.5)
+    g = np.linspace(-14.0, 14.0, 5601)
+    dx = g[1] - g[0]
+
+    def npdf(v, m, s):
+        return np.exp(-0.5 * ((v - m) / s) ** 2) / (s * math.sqrt(2 * math.pi))
+
+    K = 0.9 * npdf(g[:, None], 0.9 * g[None, :], 0.3) + 0.1 * npdf(g[:, None], 0.0, 3.0)  # K[i, j] = p(g_i | g_j)
+    prior = 0.9 * npdf(g, 0.0, 0.3) + 0.1 * npdf(g, 0.0, 3.0)  # from x_0 = 0
+    exact = 0.0
+    for t, y in enumerate(ys):
+        pred = prior if t == 0 else K @ post * dx
+        joint = pred * npdf(y, g, 0.5)
+        z = joint.sum() * dx
+        exact += math.log(z)
+        post = joint / z
+    on_device = torch.device(device).type == "cuda"
+    n = (1 << 18) if on_device else 4096  # (the host dry run executes the kernels thread by thread)
+    tol = 0.03 if on_device else 0.25
+    x0 = torch.zeros(n)
+    obs = gj.C["y"].set(torch.from_numpy(ys.astype(np.float32)))
+    got = {}
+    for mode in ("step", "graph"):
+        res = ParticleFilter(step, n, mode=mode).run(gj.key(5), x0, obs, use_graph=on_device)
+        got[mode] = float(res.log_marginal_likelihood)
+        assert got[mode] == pytest.approx(exact, abs=tol), (mode, got[mode], exact)
+    assert got["step"] == pytest.approx(got["graph"], abs=1e-4)  # same particles, two CDF realisations of one estimator
+
+
+def test_three_branches_clamped_index_nested_mask_project_and_regenerate(device):
+    """Edge cases against the oracle: three branches with out-of-range indices (clamped, switch.py:108), a
+    MaskCombinator inside a branch, ``project`` on a selection that names a branch-local address, and ``Regenerate`` of a
+    branch-local site (distribution.py:258-300 through switch.py:262-306)."""
+    gj = _gj()
+    jnp = gj.numpy
+
+    @gj.gen
+    def a(x):
+        return gj.normal(x, 1.0) @ "v"
+
+    @gj.gen
+    def b(x):
+        u = gj.uniform(0.0, 2.0) @ "u"
+        return gj.normal(x + u, 0.5) @ "v"
+
+    @gj.gen
+    def c(x):
+        w = gj.normal.mask()(x > 0.0, 0.0, 2.0) @ "w"  # only scored where x > 0
+        return gj.laplace(x, 1.0) @ "v"
+
+    @gj.gen
+    def model(k, x):
+        r = a.switch(b, c)(k, (x,), (x,), (x,)) @ "r"
+        return gj.normal(r, 0.2) @ "obs"
+
+    def o_model(h, k, x):
+        def oa(hh, xx):
+            return hh.normal(("r", "v"), xx, F32(1.0))
+
+        def ob(hh, xx):
+            u = hh.uniform(("r", "u"), F32(0.0), F32(2.0))
+            return hh.normal(("r", "v"), (xx + u).astype(F32), F32(0.5))
+
+        def oc(hh, xx):
+            hh.mask(xx > 0, lambda h3: h3.normal(("r", "w"), F32(0.0), F32(2.0)))
+            return hh.laplace(("r", "v"), xx, F32(1.0))
+
+        r = h.switch(k, [oa, ob, oc], [(x,), (x,), (x,)])
+        return h.normal("obs", r, F32(0.2))
+
+    n = 12_289
+    k = (torch.arange(n) % 7 - 2).to(torch.int32)  # -2 .. 4: clamps to 0 .. 2
+    x = torch.linspace(-2.0, 2.0, n)
+    kb, okb = gj.split(gj.key(41), n), orng.split(orng.key(41), n)
+    kn, xn = k.numpy(), x.numpy().astype(F32)
+    tr = gj.vmap(model.simulate, in_axes=(0, (0, 0)))(kb, (k, x))
+    otr = ogfi.simulate(o_model, okb, (kn, xn))
+    kc = np.clip(kn, 0, 2)
+    chm = tr.get_choices()
+    v = chm["r", "v"]
+    assert bool(_np(v.flag).all())
+    ok = np.isclose(_np(v.value), otr.choices[("r", "v")], rtol=1e-4, atol=1e-5)
+    assert ok.mean() > 0.999
+    np.testing.assert_array_equal(_np(chm["r", "u"].flag), kc == 1)
+    np.testing.assert_array_equal(_np(chm["r", "w"].flag), (kc == 2) & (xn > 0))
+    w_val = _np(chm["r", "w"].value)
+    assert (w_val[kc != 2] == 0).all() and (w_val[(kc == 2) & (xn <= 0)] != 0).all()  # masked, but drawn inside its branch
+    np.testing.assert_allclose(_np(tr.get_score())[ok], otr.get_score()[ok], rtol=1e-4, atol=1e-4)
+
+    # project: the score of the selected addresses, 0 where their branch is not the selected one
+    pu = _np(tr.project(gj.key(0), gj.S["r", "u"]))
+    np.testing.assert_allclose(pu, np.where(kc == 1, math.log(0.5), 0.0), atol=1e-6)
+    pw = _np(tr.project(gj.key(0), gj.S["r", "w"]))
+    want_w = np.where((kc == 2) & (xn > 0), od.DISTS["normal"][1](w_val.astype(F32), F32(0.0), F32(2.0)), 0.0)
+    np.testing.assert_allclose(pw, want_w, rtol=1e-5, atol=1e-5)
+
+    # regenerate the branch-local uniform: weight = change of the valid score
+    k2 = gj.split(gj.key(42), n)
+    tr2, w2, _, disc = tr.edit(k2, gj.Regenerate(gj.S["r", "u"]))
+    otr2, ow2, _ = ogfi.regenerate(o_model, orng.split(orng.key(42), n), otr, [("r", "u")])
+    np.testing.assert_allclose(_np(w2)[ok], ow2[ok], rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(_np(tr2.get_score())[ok], (_np(tr.get_score()) + _np(w2))[ok], rtol=2e-4, atol=2e-4)
+    assert (_np(w2)[kc != 1] == 0).all()
+    u2 = tr2.get_choices()["r", "u"]
+    np.testing.assert_array_equal(_np(u2.flag), kc == 1)
+    assert (_np(u2.value)[kc == 1] != _np(chm["r", "u"].value)[kc == 1]).mean() > 0.99

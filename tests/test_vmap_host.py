@@ -134,8 +134,9 @@ def test_vmap_validation(emu):  # test_vmap_validation
         foo.vmap(in_axes=(0, (0, None))).simulate(gj.key(0), (10.0, torch.arange(3.0)))
     with pytest.raises(IndexError):
         foo.vmap(in_axes=0).simulate(gj.key(0), (torch.arange(2.0), torch.arange(3.0)))
-    with pytest.raises(NotImplementedError):
-        foo.vmap(in_axes=(0, None)).simulate(gj.split(gj.key(0), 4), (torch.arange(2.0), 1.0))
+    # under an outer particle batch (a KeyBatch) the mapped axis is unrolled into the kernel: [particles, mapped] leaves
+    tr = foo.vmap(in_axes=(0, None)).simulate(gj.split(gj.key(0), 4), (torch.arange(2.0), 1.0))
+    assert tuple(tr.get_choices()[:, "x"].shape) == (4, 2) and tuple(tr.get_retval().shape) == (4, 2)
 
 
 def test_closure_call_zero_length_and_repeat_importance(emu):
