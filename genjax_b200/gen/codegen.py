@@ -509,6 +509,7 @@ class _Generator:
         out.append(f"constexpr int kPfMinBlocks = {3 if self.group else 4};  // CTAs per SM the filter kernel is compiled for")
         out.append("constexpr int kPfCacheTiles = 2;  // tiles per CTA whose masses stay in shared memory between phases")
         out.append(f"constexpr int NS = {max(self.ns, 1)}, NA = {self.na}, NR = {self.nr};")
+        out.append(f"constexpr int kNState = {len(self.ir.ret_leaves)};  // return leaves proper (NR also counts the validity flags of dynamic sites)")
         if self.group:
             out.append(f"constexpr int G = {self.G};")
             out.append("constexpr int kPPB = kThreads / G;  // particles per block iteration")
@@ -1307,7 +1308,7 @@ int gjb_model_pf_steps(const gjb_steps_args* a, void* stream) {
   if (a->n > (1LL << 26) || (a->n + gjb::kTeTile - 1) / gjb::kTeTile > gjb::kTeMaxTiles) return GJB_E_RANGE;
   if ((reinterpret_cast<uintptr_t>(a->cdf) & 15) || (reinterpret_cast<uintptr_t>(a->recs) & 15)) return GJB_E_ARG;
   if (a->record ? (!a->logw || !a->ancestors) : !a->logw) return GJB_E_ARG;
-  for (int k = 0; k < NR; ++k) if (!a->state0[k] || !a->state_buf[k]) return GJB_E_ARG;
+  for (int k = 0; k < kNState; ++k) if (!a->state0[k] || !a->state_buf[k]) return GJB_E_ARG;
   const int64_t tiles = (a->n + gjb::kTeTile - 1) / gjb::kTeTile;
   if (tiles > pf_steps_capacity()) return GJB_E_RANGE;  // every window's CTA must be resident (one grid barrier per step)
   void* params[1] = {(void*)a};
@@ -1328,7 +1329,7 @@ int gjb_model_pf_step(const gjb_step_args* a, void* stream) {
   if ((a->idx_offset & 3) != 0 || a->slot_offset < 0 || (a->slot_offset % gjb::kTeTile) != 0) return GJB_E_ARG;
   if (a->step < 0 || a->step >= 65535) return GJB_E_RANGE;  // 16-bit step field of the record tags
   if (reinterpret_cast<uintptr_t>(a->cdf_out) & 15) return GJB_E_ARG;
-  for (int k = 0; k < NR; ++k) if (!a->state_out[k]) return GJB_E_ARG;
+  for (int k = 0; k < kNState; ++k) if (!a->state_out[k]) return GJB_E_ARG;
   // S <= n_total * (2^36 + 1) must stay below 2^63 (signed conversion in offspring_cnt)
   if (a->n_total > (1LL << 26)) return GJB_E_RANGE;
   if ((a->n_total + gjb::kTeTile - 1) / gjb::kTeTile > gjb::kTeMaxTiles) return GJB_E_RANGE;
