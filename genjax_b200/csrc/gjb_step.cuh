@@ -25,7 +25,10 @@
 #ifdef GJB_TRACE
 __device__ unsigned long long gjb_trace_buf[1024 * 16];
 __device__ __forceinline__ unsigned long long gjb_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define GJB_TP(i) do { if (threadIdx.x == 0 && blockIdx.x < 1024) gjb_trace_buf[blockIdx.x * 16 + (i)] = ((i) >= 14) ? gjb_globaltimer() : (unsigned long long)clock64(); } while (0)
+// slots 7 / 13 (globaltimer too): written by the rank's LAST CTA only -- all records arrived / table written; cleared at entry
+#define GJB_TP(i) do { if (threadIdx.x == 0 && blockIdx.x < 1024) { \
+    if ((i) == 0) { gjb_trace_buf[blockIdx.x * 16 + 7] = 0ull; gjb_trace_buf[blockIdx.x * 16 + 13] = 0ull; } \
+    gjb_trace_buf[blockIdx.x * 16 + (i)] = ((i) >= 14 || (i) == 7 || (i) == 13) ? gjb_globaltimer() : (unsigned long long)clock64(); } } while (0)
 #else
 #define GJB_TP(i) do {} while (0)
 #endif
@@ -478,6 +481,7 @@ __device__ __forceinline__ void te_finish_step(const gjb_step_link* __restrict__
   emax = __reduce_max_sync(0xffffffffu, emax);
   if (lane == 0) sm.ired[warp] = emax;
   __syncthreads();
+  GJB_TP(7);  // (every thread of the last CTA has seen its records)
   int E = sm.ired[0];
 #pragma unroll
   for (int w = 1; w < kThreads / 32; ++w) E = max(E, sm.ired[w]);
@@ -595,6 +599,7 @@ __device__ __forceinline__ void te_finish_step(const gjb_step_link* __restrict__
     }
   }
   __syncthreads();
+  GJB_TP(13);
   if (tid == 0) {
     __threadfence();
     te_st_volatile(reinterpret_cast<uint64_t*>(&tab->tag), (uint64_t)tag);

@@ -50,12 +50,12 @@ def _nvcc() -> str:
     raise BuildError("nvcc not found")
 
 
-def _header_digest() -> str:
+def _header_digest(extra: bool = True) -> str:
     h = hashlib.sha256()
     for p in sorted(list(CSRC.glob("*.cuh")) + [INCLUDE / "genjax_b200.h"]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
-    h.update(" ".join(NVCC_FLAGS + _extra_flags()).encode())
+    h.update(" ".join(NVCC_FLAGS + (_extra_flags() if extra else [])).encode())
     return h.hexdigest()
 
 
@@ -64,8 +64,8 @@ def _extra_flags() -> list[str]:
     return os.environ.get("GJB_NVCC_EXTRA", "").split()
 
 
-def _compile(src: Path, out: Path, log: Path) -> None:
-    cmd = [_nvcc(), *NVCC_FLAGS, *_extra_flags(), f"-I{CSRC}", f"-I{INCLUDE}", "-o", str(out), str(src)]
+def _compile(src: Path, out: Path, log: Path, extra: bool = True) -> None:
+    cmd = [_nvcc(), *NVCC_FLAGS, *(_extra_flags() if extra else []), f"-I{CSRC}", f"-I{INCLUDE}", "-o", str(out), str(src)]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log.write_text(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     if proc.returncode != 0:
@@ -79,10 +79,12 @@ def build_core(force: bool = False) -> Path:
         src = CSRC / "gjb_core.cu"
         out = LIB / "libgjb_core.so"
         stamp = LIB / "libgjb_core.hash"
-        digest = hashlib.sha256(src.read_bytes() + _header_digest().encode()).hexdigest()
+        # (the diagnostic flags of $GJB_NVCC_EXTRA are for the generated model kernels: the core library keeps one build,
+        # so a traced multi-process run does not recompile it in every rank)
+        digest = hashlib.sha256(src.read_bytes() + _header_digest(extra=False).encode()).hexdigest()
         if not force and out.exists() and stamp.exists() and stamp.read_text() == digest:
             return out
-        _compile(src, out, LIB / "libgjb_core.log")
+        _compile(src, out, LIB / "libgjb_core.log", extra=False)
         stamp.write_text(digest)
         return out
 
