@@ -524,19 +524,18 @@ __device__ __forceinline__ void te_finish_step(const gjb_step_link* __restrict__
     }
     return;
   }
-  // pass 2: aligned masses, thread-local inclusive prefix (the records are complete: plain batched L2 loads)
+  // pass 2: the thread's total aligned mass (records are complete: plain batched L2 loads), block scan.
+  // Nothing per tile goes through shared memory with the thread-contiguous index t = tid * per + k: at per = 16 that is
+  // a 128-byte stride, a 32-way bank conflict on every access -- measured as a 21 us table build at 8 ranks
+  // (profiles/r2_call34_trace_8gpu.txt).  The offspring counts the window searches probe are stored TRANSPOSED
+  // (slot k * kThreads + tid: consecutive threads, consecutive words).
   uint64_t run = 0;
   for (int b = 0; b < per; b += 8) {
     te_load_batch(box, t0 + b, per - b, n_tiles, bm, be);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int t = t0 + b + k;
-      if (b + k < per && t < n_tiles) {
-        const int sft = bm[k] ? min(E - be[k], 63) : 63;
-        run += bm[k] >> sft;
-        sm.pre[t] = run;
-        sm.shf[t] = (uint8_t)sft;
-      }
+      if (b + k < per && t < n_tiles && bm[k]) run += bm[k] >> min(E - be[k], 63);
     }
   }
   uint64_t inc = run;
@@ -554,18 +553,29 @@ __device__ __forceinline__ void te_finish_step(const gjb_step_link* __restrict__
     if (w < warp) excl += v;
     S += v;
   }
-  // the table, and the cumulative offspring count at every tile boundary: it takes the prefix's place in shared memory
-  // (the window searches below probe counts only; recomputing the fp64 count per probe was ~2 us at 4096 tiles)
+  // pass 3: the records once more -- absolute prefix and shift into the table, cumulative offspring count at every tile
+  // boundary into shared memory
   const double u0 = resample_u0(__ldg(reskey), __ldg(reskey + 1), (uint64_t)__ldg(reskey + 2) | ((uint64_t)__ldg(reskey + 3) << 32));
   const double scale = S ? __ddiv_rn((double)n_total, (double)S) : 0.0;
   const int32_t nt = (int32_t)n_total;
-  for (int k = 0; k < per; ++k) {
-    const int t = t0 + k;
-    if (t < n_tiles) {
-      const uint64_t cur = sm.pre[t] + excl;
-      tab->pre[t] = cur;
-      tab->shf[t] = sm.shf[t];
-      sm.pre[t] = S ? (uint64_t)(int64_t)offspring_cnt(cur, S, scale, u0, nt) : 0ull;
+  {
+    uint64_t cur = excl;
+    for (int b = 0; b < per; b += 8) {
+      te_load_batch(box, t0 + b, per - b, n_tiles, bm, be);
+      const bool whole = b + 8 <= per && t0 + b + 8 <= n_tiles && ((t0 + b) & 7) == 0;  // 8 aligned tiles: their shifts leave as one word
+      uint64_t packed = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int t = t0 + b + k;
+        if (b + k < per && t < n_tiles) {
+          const int sft = bm[k] ? min(E - be[k], 63) : 63;
+          cur += bm[k] >> sft;
+          tab->pre[t] = cur;
+          if (whole) packed |= (uint64_t)sft << (8 * k); else tab->shf[t] = (uint8_t)sft;
+          sm.pre[(b + k) * kThreads + tid] = S ? (uint64_t)(int64_t)offspring_cnt(cur, S, scale, u0, nt) : 0ull;
+        }
+      }
+      if (whole) *reinterpret_cast<uint64_t*>(tab->shf + t0 + b) = packed;  // (shf sits at an 8-byte aligned offset of gjb_step_table)
     }
   }
   if (tid == 0) {
@@ -573,8 +583,9 @@ __device__ __forceinline__ void te_finish_step(const gjb_step_link* __restrict__
     if (lse_out) te_write_lse(lse_out, E, S, n_total);
     *L->ticket = 0u;  // the next launch on the stream starts from zero
   }
-  __syncthreads();  // sm.pre (now counts) complete
+  __syncthreads();  // the counts are complete
   // window table: for each local window the first tile whose offspring reach it and the tile that owns its last slot
+  auto cnt_at = [&](int p) -> int64_t { return (int64_t)sm.pre[(p % per) * kThreads + p / per]; };
   const int n_win = (int)((n_local + kTeTile - 1) / kTeTile);
   if (S != 0) {
     for (int w = tid; w < n_win; w += kThreads) {
@@ -584,15 +595,13 @@ __device__ __forceinline__ void te_finish_step(const gjb_step_link* __restrict__
       int lo = 0, hi = n_tiles;  // smallest p with cnt(P_p) > ws
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const int64_t c = (int64_t)sm.pre[mid];
-        if (c > ws) hi = mid; else lo = mid + 1;
+        if (cnt_at(mid) > ws) hi = mid; else lo = mid + 1;
       }
       const int p_first = lo;
       hi = n_tiles;                // smallest p with cnt(P_p) >= we (lo continues from p_first)
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const int64_t c = (int64_t)sm.pre[mid];
-        if (c >= we) hi = mid; else lo = mid + 1;
+        if (cnt_at(mid) >= we) hi = mid; else lo = mid + 1;
       }
       tab->win[w][0] = p_first;
       tab->win[w][1] = lo < n_tiles ? lo : n_tiles - 1;
