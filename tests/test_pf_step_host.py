@@ -99,3 +99,23 @@ def test_all_steps_in_one_cooperative_launch_equal_the_per_step_launches(emu, n)
         if record:
             assert torch.equal(a.ancestors, b.ancestors) and torch.equal(a.history["log_weights"], b.history["log_weights"])
             assert torch.equal(a.history["state"][0], b.history["state"][0])
+
+
+@pytest.mark.parametrize("n", [2048, 6000])
+def test_step_filter_table_form_matches_oracle(emu, monkeypatch, n):
+    """The multi-GPU form of the step kernel on one device (GJB_STEP_TABLE=1: tile records go through the mailbox, the
+    CTA that draws the last ticket builds the prefix / window table, the next launch consumes it -- te_finish_step +
+    te_pull_table of csrc/gjb_step.cuh): same ancestors, states, weights and increments as the oracle and as the
+    table-free form, bit for bit."""
+    monkeypatch.setenv("GJB_STEP_TABLE", "1")
+    T = 5
+    ys = osmc.simulate_lgssm(1, T, 1, LG_A, LG_Q, LG_C, LG_R)[:, 0]
+    x0 = np.random.default_rng(n).standard_normal(n).astype(F32)
+    pf = ParticleFilter(lgssm_step, n, mode="step")
+    res = pf.run(gj.key(17), torch.from_numpy(x0), gj.C["y"].set(torch.from_numpy(ys)), record=True)
+    assert next(iter(pf._plans.values())).te_table
+    check_against_oracle(res, x0, [{"y": F32(y)} for y in ys], o_step, 17, n, T)
+    monkeypatch.setenv("GJB_STEP_TABLE", "0")
+    ref = ParticleFilter(lgssm_step, n, mode="step").run(gj.key(17), torch.from_numpy(x0), gj.C["y"].set(torch.from_numpy(ys)), record=True)
+    assert torch.equal(res.ancestors, ref.ancestors) and torch.equal(res.log_increments, ref.log_increments)
+    assert torch.equal(res.state[0], ref.state[0])
