@@ -298,10 +298,13 @@ class _Plan:
             import os
 
             # table form: the last CTA of each launch builds the tile-prefix table for the next (the form several devices
-            # need); table-free form: every CTA forms the prefix from the plain tile records (faster on ONE device: B200,
-            # 1 M particles, 19-22 us against 26 us per step -- the serial tail of the last CTA costs more than the
-            # redundant prefix work it saves)
-            self.te_table = os.environ.get("GJB_STEP_TABLE", "0") == "1"
+            # need); table-free form: every CTA forms the prefix from the plain tile records.  The redundant prefix work
+            # of the table-free form grows with the SQUARE of the tile count, the last CTA's serial tail linearly.
+            # Measured on one B200 (profiles/r2_call37/38_table_form_cost_1gpu.txt, us per step, table-free / table):
+            # 1024 tiles 31.3 / 41.8, 1536 tiles 44.9 / 57.1, 2048 tiles 100.4 / 75.5, 4096 tiles 389.6 / 147.5 -- so the
+            # table form is the default from 2048 tiles (4 194 304 particles) up.  Same ancestors either way.
+            env = os.environ.get("GJB_STEP_TABLE")
+            self.te_table = (env == "1") if env is not None else (tiles >= 2048 and not self.stepsmode)
             # ... and who builds the table: the step kernel's last CTA (default; B200: 22.5 us per step on one device, 28 us
             # on two) or gjb_te_table, a small kernel resident beside the step kernel (24.5 / 32 us: its launch and the
             # dependent launch behind it cost more than the last CTA's serial tail)
